@@ -1,0 +1,181 @@
+/* ltxcuda.h -- C ABI of libltxcuda.so: the B200 (sm_100a) implementation of the LTX-2 denoise hot path.
+ *
+ * The reference (VincentGourbin/ltx-video-swift-mlx) has no plugin/FFI interface: every model is a Swift Module
+ * calling MLX directly.  This header is the drop-in boundary at the three narrowest Swift call sites;
+ * each entry point cites the Swift symbol it replaces (paths relative to Sources/LTXVideo/).  A SwiftPM C target
+ * (`CLTXCuda`) exposes it to the unchanged `LTXPipeline`.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the library owns device memory and weights;
+ *   - every function returns 0 on success, non-zero on failure (LTX_ERR_*); `ltx_last_error` gives the message
+ *     (maps to LTXError.generationFailed / .weightLoadingFailed / .invalidConfiguration, LTXVideo.swift:66-107);
+ *   - no CPU fallback: without an sm_100a device `ltx_ctx_create` fails;
+ *   - a context is thread-compatible (calls are serialised by `actor LTXPipeline`, Pipeline/LTXPipeline.swift:117);
+ *   - `*_dev` variants take device pointers, enqueue on the context stream and do not synchronise.
+ */
+#ifndef LTXCUDA_H_
+#define LTXCUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define LTX_OK 0
+#define LTX_ERR_INVALID_CONFIGURATION 1 /* LTXError.invalidConfiguration */
+#define LTX_ERR_INVALID_ARGUMENT 2      /* LTXError.generationFailed (bad shapes / pointers) */
+#define LTX_ERR_CUDA 3                  /* LTXError.generationFailed (device error) */
+#define LTX_ERR_WEIGHTS 4               /* LTXError.weightLoadingFailed */
+#define LTX_ERR_UNSUPPORTED 5
+
+typedef enum { LTX_F32 = 0, LTX_BF16 = 1, LTX_F16 = 2 } ltx_dtype;
+
+typedef struct ltx_ctx ltx_ctx;
+
+/* Mirrors LTXTransformerConfig (Configuration/LTXConfig.swift:83-156) plus the VAE channel plan
+ * (Models/VAE/VideoDecoder.swift:331-355).  Zero-initialise and call ltx_config_default for the LTX-2 values. */
+typedef struct {
+  int32_t num_layers;        /* 48 */
+  int32_t num_heads;         /* 32 */
+  int32_t head_dim;          /* 128 (only value supported by the attention kernel) */
+  int32_t in_channels;       /* 128 */
+  int32_t out_channels;      /* 128 */
+  int32_t caption_channels;  /* 3840 */
+  int32_t ffn_mult;          /* 4 */
+  float rope_theta;          /* 10000 */
+  int32_t max_pos[3];        /* {20, 2048, 2048} */
+  float timestep_scale_multiplier; /* 1000 */
+  float norm_eps;            /* 1e-6 */
+  int32_t vae_latent_channels;   /* 128 */
+  int32_t vae_base_channels;     /* 1024 */
+  int32_t vae_blocks_per_stage;  /* 5 */
+  int32_t vae_patch_size;        /* 4 */
+} ltx_config;
+
+void ltx_config_default(ltx_config* cfg);
+const char* ltx_version(void);
+
+/* LTXPipeline.init / loadModels (Pipeline/LTXPipeline.swift:189,217): one context per GPU. */
+int ltx_ctx_create(const ltx_config* cfg, int device, ltx_ctx** out);
+int ltx_ctx_destroy(ltx_ctx* ctx);
+const char* ltx_last_error(const ltx_ctx* ctx);
+int ltx_sync(ltx_ctx* ctx);
+
+/* Weight ingestion: replaces LTXWeightLoader.applyTransformerWeights / applyVAEWeights
+ * (Utils/ModelDownloader.swift:972-1064).  `key` is the post-mapping name (mapTransformerKey :756-803,
+ * mapVAEWeights :808-899), e.g. "transformer_blocks.3.attn1.to_q.weight", "vae.up_blocks_0.res_blocks.0.conv1.conv.weight"
+ * (VAE keys carry the prefix "vae.").  Matrices / conv kernels are stored as bf16 (the loader's fp32->bf16 cast,
+ * :1005-1012), vectors and tables as fp32. */
+int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dtype dtype, const int64_t* shape, int ndim);
+/* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
+ * which: 1 = DiT, 2 = VAE decoder, 3 = both. */
+int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);
+/* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16.  Replaces quantize(model:groupSize:bits:)
+ * (Pipeline/LTXPipeline.swift:323-333); 8 / 4 (MLX affine, group 64) are reserved and return LTX_ERR_UNSUPPORTED. */
+int ltx_finalize_weights(ltx_ctx* ctx, int quant_bits, int group_size);
+
+/* Per-forward runtime flags: setSTGSkipFlags / clearSTGSkipFlags / setCrossAttentionScale
+ * (Models/Transformer/LTXTransformer.swift:497-526). */
+#define LTX_MAX_FLAG_BLOCKS 64
+typedef struct {
+  int32_t n_stg_blocks;                      /* blocks whose skip flags are set (empty = normal pass) */
+  int32_t stg_blocks[LTX_MAX_FLAG_BLOCKS];
+  int32_t skip_self_attn;                    /* applied to stg_blocks */
+  int32_t skip_ff;
+  int32_t n_cas_blocks;                      /* blocks with a cross-attention scale != 1 */
+  int32_t cas_blocks[LTX_MAX_FLAG_BLOCKS];
+  float cross_attn_scale;
+  uint64_t context_key;  /* 0: recompute caption projection + text K/V; else cache them under this key (step-invariant) */
+} ltx_dit_flags;
+
+/* LTXTransformer.callAsFunction(latent:context:timesteps:contextMask:latentShape:)
+ * (Models/Transformer/LTXTransformer.swift:235-486).
+ *   latent   [B, N, in_channels]   (N = F*H*W, token order F-major then H then W, Pipeline/LatentUtils.swift:29-31)
+ *   context  [B, S, caption_channels]
+ *   timesteps[B] sigma in [0,1]    (ts_per_token != 0, [B,N], is not implemented yet: LTX_ERR_UNSUPPORTED)
+ *   mask     [B, S] int32, 1 = attend, NULL = all ones
+ *   out      [B, N, out_channels] fp32 velocity
+ * Host-pointer variant copies in/out and synchronises. */
+int ltx_dit_forward(ltx_ctx* ctx, const void* latent, ltx_dtype latent_dtype, const void* context, ltx_dtype context_dtype,
+                    const float* timesteps, int ts_per_token, const int32_t* mask, int B, int N, int S, int F, int H,
+                    int W, const ltx_dit_flags* flags, float* out_velocity);
+int ltx_dit_forward_dev(ltx_ctx* ctx, const void* latent, ltx_dtype latent_dtype, const void* context,
+                        ltx_dtype context_dtype, const float* timesteps, int ts_per_token, const int32_t* mask, int B, int N,
+                        int S, int F, int H, int W, const ltx_dit_flags* flags, float* out_velocity);
+/* LTXTransformer.clearRoPECache (:202) + drops the cached text K/V. */
+int ltx_dit_clear_caches(ltx_ctx* ctx);
+
+/* applyCFG + applyGuidanceRescale (Pipeline/LatentUtils.swift:131-183), STG / GE lines (Pipeline/LTXPipeline.swift:920-927)
+ * and LTXScheduler.step(latent:velocity:sigma:sigmaNext:) (Scheduler/LTXScheduler.swift:305-327), fused, fp32.
+ *   latent in/out [n]; v_uncond / v_stg / v_prev may be NULL; v_prev is read (if use_prev) and then overwritten with
+ *   the velocity actually used (the GE momentum state). */
+int ltx_guided_euler_step(ltx_ctx* ctx, float* latent, const float* v_cond, const float* v_uncond, const float* v_stg,
+                          float* v_prev, int use_prev, size_t n, float cfg_scale, float rescale_phi, float stg_scale,
+                          float ge_gamma, float sigma, float sigma_next);
+int ltx_guided_euler_step_dev(ltx_ctx* ctx, float* latent, const float* v_cond, const float* v_uncond, const float* v_stg,
+                              float* v_prev, int use_prev, size_t n, float cfg_scale, float rescale_phi, float stg_scale,
+                              float ge_gamma, float sigma, float sigma_next);
+
+/* Device-resident fast path for the generateVideo step loop (Pipeline/LTXPipeline.swift:793-956): the latent, both
+ * text contexts and the GE state stay in HBM between steps. */
+typedef struct {
+  float sigma, sigma_next;
+  float cfg_scale;      /* <= 1: no unconditional pass */
+  float rescale_phi;
+  float stg_scale;      /* <= 0: no perturbed pass */
+  float ge_gamma;
+  int32_t n_stg_blocks;
+  int32_t stg_blocks[LTX_MAX_FLAG_BLOCKS];
+  int32_t step_index;   /* GE applies for step_index > 0 */
+} ltx_step_params;
+/* noise [in_channels, F, H, W] fp32 host; latent = noise * sigma0 (:793).  neg_context may be NULL. */
+int ltx_denoise_begin(ltx_ctx* ctx, const float* noise, int F, int H, int W, float sigma0, const void* context,
+                      ltx_dtype context_dtype, const int32_t* mask, const void* neg_context, const int32_t* neg_mask, int S);
+int ltx_denoise_step(ltx_ctx* ctx, const ltx_step_params* p);
+/* copies the current latent [in_channels, F, H, W] fp32 to the host (synchronises). */
+int ltx_denoise_get_latent(ltx_ctx* ctx, float* latent_out);
+/* device pointer of the resident latent (for chaining into ltx_vae_decode_dev). */
+int ltx_denoise_latent_dev(ltx_ctx* ctx, float** latent_dev);
+
+/* decodeVideo(latent:decoder:timestep:temporalTileSize:temporalTileOverlap:) untiled
+ * (Models/VAE/VideoDecoder.swift:466-508 -> VideoDecoder.callAsFunction :358-449).
+ *   latent [128, F', H', W'] fp32 ; timestep < 0 = none ; decode_noise (same shape) required when timestep >= 0;
+ *   out_frames [8(F'-1)+1, 32H', 32W', 3] fp32 in [0,1]. */
+int ltx_vae_decode(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                   int causal, float* out_frames);
+int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep,
+                       const float* decode_noise, int causal, float* out_frames);
+
+/* Number of kernels launched by this context so far (bench.py reports the per-step delta as gpu_launches). */
+uint64_t ltx_launch_count(const ltx_ctx* ctx);
+
+/* ---- diagnostic single-kernel entry points (device pointers; used by the parity tests and the profiler) ---- */
+/* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) ; mode: 0 bf16 out, 1 gelu bf16 out, 3 fp32 out; force_bn: 0 auto, 128, 256. */
+int ltx_op_gemm(ltx_ctx* ctx, const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int mode,
+                int force_bn);
+/* x[M,N] (fp32) += (A B^T + bias) * (gate_a[n] + gate_b[n]) * scale ; shadow (bf16, nullable) = new x. */
+int ltx_op_gemm_resid(ltx_ctx* ctx, const void* A, const void* B, const float* bias, float* x, const float* gate_a,
+                      const float* gate_b, void* shadow, int M, int N, int K, float scale);
+/* O = softmax(Q K^T * scale + key_bias) V ; Q [B*Nq, H*128], K [B*Nk, H*128], Vt [H*128, ldv], all bf16. */
+int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldv, const float* key_bias, void* O,
+                     int B, int H, int Nq, int Nk, float scale);
+int ltx_op_rmsnorm_mod(ltx_ctx* ctx, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
+                       const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm);
+int ltx_op_qknorm_rope(ltx_ctx* ctx, void* x_bf16, int M, int D, const float* w, const float* cos_tab, const float* sin_tab,
+                       int rows_per_rope, float eps);
+/* 3x3x3 conv on a channels-last fp32 volume [T,H,W,Cin] -> [T,H,W,Cout] fp32 with reflect/replicate padding. */
+int ltx_op_conv3d(ltx_ctx* ctx, const float* x, const void* w_bf16_27_O_I, const float* bias, float* out, int T, int H,
+                  int W, int Cin, int Cout, int causal);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTXCUDA_H_ */

@@ -1,0 +1,234 @@
+"""LtxContext: owner of one libltxcuda context (one GPU).  Thin, typed wrapper over the C ABI; all arithmetic happens
+inside libltxcuda.so."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import LTX_BF16, LTX_F16, LTX_F32, LtxConfig, LtxDitFlags, LtxError, LtxStepParams
+
+
+@dataclass
+class LTXTransformerConfig:
+    """Mirror of LTXTransformerConfig (Configuration/LTXConfig.swift:83-156) + the VAE channel plan."""
+    num_layers: int = 48
+    num_attention_heads: int = 32
+    attention_head_dim: int = 128
+    in_channels: int = 128
+    out_channels: int = 128
+    caption_channels: int = 3840
+    ffn_mult: int = 4
+    rope_theta: float = 10000.0
+    max_pos: Tuple[int, int, int] = (20, 2048, 2048)
+    timestep_scale_multiplier: float = 1000.0
+    norm_eps: float = 1e-6
+    vae_latent_channels: int = 128
+    vae_base_channels: int = 1024
+    vae_blocks_per_stage: int = 5
+    vae_patch_size: int = 4
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_attention_heads * self.attention_head_dim
+
+    def to_c(self) -> LtxConfig:
+        c = LtxConfig()
+        c.num_layers, c.num_heads, c.head_dim = self.num_layers, self.num_attention_heads, self.attention_head_dim
+        c.in_channels, c.out_channels, c.caption_channels = self.in_channels, self.out_channels, self.caption_channels
+        c.ffn_mult, c.rope_theta = self.ffn_mult, self.rope_theta
+        for i in range(3):
+            c.max_pos[i] = self.max_pos[i]
+        c.timestep_scale_multiplier, c.norm_eps = self.timestep_scale_multiplier, self.norm_eps
+        c.vae_latent_channels, c.vae_base_channels = self.vae_latent_channels, self.vae_base_channels
+        c.vae_blocks_per_stage, c.vae_patch_size = self.vae_blocks_per_stage, self.vae_patch_size
+        return c
+
+
+def _host(a, dtype=None) -> np.ndarray:
+    """Contiguous host ndarray from a numpy array or a CPU torch tensor (bf16 tensors are viewed as uint16)."""
+    if hasattr(a, "detach"):
+        import torch
+        t = a.detach().cpu().contiguous()
+        if t.dtype == torch.bfloat16:
+            return t.view(torch.uint16).numpy()
+        a = t.numpy()
+    a = np.ascontiguousarray(a)
+    if dtype is not None and a.dtype != dtype:
+        a = np.ascontiguousarray(a.astype(dtype))
+    return a
+
+
+def _dtype_code(a) -> int:
+    if hasattr(a, "detach"):
+        import torch
+        return {torch.float32: LTX_F32, torch.bfloat16: LTX_BF16, torch.float16: LTX_F16}[a.dtype]
+    return {np.dtype(np.float32): LTX_F32, np.dtype(np.float16): LTX_F16, np.dtype(np.uint16): LTX_BF16}[np.asarray(a).dtype]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_flags(stg_blocks: Sequence[int] = (), skip_self_attn: bool = False, skip_ff: bool = False,
+               cas_blocks: Sequence[int] = (), cross_attn_scale: float = 1.0, context_key: int = 0) -> LtxDitFlags:
+    f = LtxDitFlags()
+    f.n_stg_blocks = len(stg_blocks)
+    for i, b in enumerate(stg_blocks):
+        f.stg_blocks[i] = int(b)
+    f.skip_self_attn, f.skip_ff = int(skip_self_attn), int(skip_ff)
+    f.n_cas_blocks = len(cas_blocks)
+    for i, b in enumerate(cas_blocks):
+        f.cas_blocks[i] = int(b)
+    f.cross_attn_scale = float(cross_attn_scale)
+    f.context_key = int(context_key)
+    return f
+
+
+class LtxContext:
+    def __init__(self, config: Optional[LTXTransformerConfig] = None, device: int = 0):
+        self.lib = _lib.load()
+        self.config = config or LTXTransformerConfig()
+        self.device = device
+        h = C.c_void_p()
+        cfg = self.config.to_c()
+        rc = self.lib.ltx_ctx_create(C.byref(cfg), device, C.byref(h))
+        if rc != 0:
+            raise LtxError(rc, self.lib.ltx_last_error(None).decode())
+        self.handle = h
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise LtxError(rc, self.lib.ltx_last_error(self.handle).decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ltx_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.ltx_sync(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ltx_launch_count(self.handle))
+
+    # ------------------------------------------------------------------ weights
+    def load_tensor(self, key: str, value):
+        code = _dtype_code(value)
+        a = _host(value)
+        shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+        self._check(self.lib.ltx_load_tensor(self.handle, key.encode(), _ptr(a), code, shape, a.ndim))
+
+    def load_weights(self, weights: Dict[str, object], prefix: str = ""):
+        for k, v in weights.items():
+            self.load_tensor(prefix + k, v)
+
+    def init_random_weights(self, which: int = 3, seed: int = 0):
+        self._check(self.lib.ltx_init_random_weights(self.handle, which, seed))
+
+    def finalize_weights(self, quant_bits: int = 16, group_size: int = 64):
+        self._check(self.lib.ltx_finalize_weights(self.handle, quant_bits, group_size))
+
+    # ------------------------------------------------------------------ DiT
+    def dit_forward(self, latent, context, timesteps, mask, fhw: Tuple[int, int, int],
+                    flags: Optional[LtxDitFlags] = None) -> np.ndarray:
+        """Host-buffer call (the Swift seam): latent [B,N,C], context [B,S,Cc], timesteps [B], mask [B,S]|None."""
+        lc, cc = _dtype_code(latent), _dtype_code(context)
+        lat, ctx = _host(latent), _host(context)
+        ts = _host(timesteps, np.float32)
+        mk = None if mask is None else _host(mask, np.int32)
+        B, N = lat.shape[0], lat.shape[1]
+        S = ctx.shape[1]
+        out = np.empty((B, N, self.config.out_channels), dtype=np.float32)
+        F, H, W = fhw
+        self._check(self.lib.ltx_dit_forward(self.handle, _ptr(lat), lc, _ptr(ctx), cc, _ptr(ts), 0, _ptr(mk), B, N, S, F, H, W,
+                                             C.byref(flags) if flags is not None else None, _ptr(out)))
+        return out
+
+    def dit_forward_dev(self, latent_ptr: int, latent_dtype: int, context_ptr: int, context_dtype: int, ts_ptr: int,
+                        mask_ptr: Optional[int], B: int, N: int, S: int, fhw, flags: Optional[LtxDitFlags], out_ptr: int):
+        F, H, W = fhw
+        self._check(self.lib.ltx_dit_forward_dev(self.handle, latent_ptr, latent_dtype, context_ptr, context_dtype, ts_ptr, 0,
+                                                 mask_ptr, B, N, S, F, H, W,
+                                                 C.byref(flags) if flags is not None else None, out_ptr))
+
+    def clear_caches(self):
+        self._check(self.lib.ltx_dit_clear_caches(self.handle))
+
+    # ------------------------------------------------------------------ guidance + Euler
+    def guided_euler_step(self, latent: np.ndarray, v_cond, v_uncond=None, v_stg=None, v_prev=None, use_prev: bool = False,
+                          cfg_scale: float = 1.0, rescale_phi: float = 0.0, stg_scale: float = 0.0, ge_gamma: float = 0.0,
+                          sigma: float = 1.0, sigma_next: float = 0.0) -> np.ndarray:
+        """In place on `latent` (fp32 host array); `v_prev` (if given) is updated with the velocity used."""
+        assert latent.dtype == np.float32 and latent.flags["C_CONTIGUOUS"]
+        vc = _host(v_cond, np.float32)
+        vu = None if v_uncond is None else _host(v_uncond, np.float32)
+        vs = None if v_stg is None else _host(v_stg, np.float32)
+        if v_prev is not None:
+            assert v_prev.dtype == np.float32 and v_prev.flags["C_CONTIGUOUS"]
+        self._check(self.lib.ltx_guided_euler_step(self.handle, _ptr(latent), _ptr(vc), _ptr(vu), _ptr(vs), _ptr(v_prev),
+                                                   int(use_prev), latent.size, cfg_scale, rescale_phi, stg_scale, ge_gamma,
+                                                   sigma, sigma_next))
+        return latent
+
+    # ------------------------------------------------------------------ resident denoise session
+    def denoise_begin(self, noise, fhw, sigma0: float, context, mask=None, neg_context=None, neg_mask=None):
+        nz = _host(noise, np.float32)
+        cc = _dtype_code(context)
+        ctx = _host(context)
+        S = ctx.shape[-2]
+        mk = None if mask is None else _host(mask, np.int32)
+        nctx = None if neg_context is None else _host(neg_context)
+        nmk = None if neg_mask is None else _host(neg_mask, np.int32)
+        F, H, W = fhw
+        self._check(self.lib.ltx_denoise_begin(self.handle, _ptr(nz), F, H, W, sigma0, _ptr(ctx), cc, _ptr(mk), _ptr(nctx),
+                                               _ptr(nmk), S))
+        self._session_shape = (self.config.in_channels, F, H, W)
+
+    def denoise_step(self, sigma: float, sigma_next: float, step_index: int, cfg_scale: float = 1.0, rescale_phi: float = 0.0,
+                     stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0):
+        p = LtxStepParams()
+        p.sigma, p.sigma_next, p.cfg_scale, p.rescale_phi = sigma, sigma_next, cfg_scale, rescale_phi
+        p.stg_scale, p.ge_gamma, p.step_index = stg_scale, ge_gamma, step_index
+        p.n_stg_blocks = len(stg_blocks)
+        for i, b in enumerate(stg_blocks):
+            p.stg_blocks[i] = int(b)
+        self._check(self.lib.ltx_denoise_step(self.handle, C.byref(p)))
+
+    def denoise_get_latent(self) -> np.ndarray:
+        out = np.empty(self._session_shape, dtype=np.float32)
+        self._check(self.lib.ltx_denoise_get_latent(self.handle, _ptr(out)))
+        return out
+
+    def denoise_latent_dev(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.ltx_denoise_latent_dev(self.handle, C.byref(p)))
+        return p.value
+
+    # ------------------------------------------------------------------ VAE
+    def vae_decode(self, latent, timestep: Optional[float] = None, decode_noise=None, causal: bool = False) -> np.ndarray:
+        lat = _host(latent, np.float32)
+        if lat.ndim == 5:
+            lat = lat[0]
+        Cc, Fp, Hp, Wp = lat.shape
+        lat = np.ascontiguousarray(lat)
+        nz = None if decode_noise is None else _host(decode_noise, np.float32)
+        out = np.empty((8 * (Fp - 1) + 1, 32 * Hp, 32 * Wp, 3), dtype=np.float32)
+        self._check(self.lib.ltx_vae_decode(self.handle, _ptr(lat), Fp, Hp, Wp, -1.0 if timestep is None else float(timestep),
+                                            _ptr(nz), int(causal), _ptr(out)))
+        return out
+
+    def vae_decode_dev(self, latent_ptr: int, fhw, out_ptr: int, causal: bool = False):
+        Fp, Hp, Wp = fhw
+        self._check(self.lib.ltx_vae_decode_dev(self.handle, latent_ptr, Fp, Hp, Wp, -1.0, None, int(causal), out_ptr))

@@ -1,0 +1,422 @@
+// extern "C" surface of libltxcuda.so (include/ltxcuda.h).  Every entry point catches C++ exceptions and maps
+// them to the integer status + ltx_last_error() contract.
+#include <cstring>
+
+#include "ctx.h"
+
+using namespace ltx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename Fn>
+int guarded(ltx_ctx* c, Fn&& fn) {
+  if (!c) return LTX_ERR_INVALID_ARGUMENT;
+  try {
+    LTX_CUDA(cudaSetDevice(c->device));
+    fn();
+    return LTX_OK;
+  } catch (const LtxError& e) {
+    c->last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    c->last_error = e.what();
+    return LTX_ERR_CUDA;
+  }
+}
+
+size_t dsize(int dt) { return dt == LTX_F32 ? 4 : 2; }
+
+void h2d(ltx_ctx* c, DevBuf& buf, const void* host, size_t bytes) {
+  buf.reserve(bytes);
+  LTX_CUDA(cudaMemcpyAsync(buf.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ltx_version(void) { return "ltxcuda 0.1.0 (sm_100a)"; }
+
+void ltx_config_default(ltx_config* cfg) {
+  if (!cfg) return;
+  cfg->num_layers = 48;
+  cfg->num_heads = 32;
+  cfg->head_dim = 128;
+  cfg->in_channels = 128;
+  cfg->out_channels = 128;
+  cfg->caption_channels = 3840;
+  cfg->ffn_mult = 4;
+  cfg->rope_theta = 10000.0f;
+  cfg->max_pos[0] = 20;
+  cfg->max_pos[1] = 2048;
+  cfg->max_pos[2] = 2048;
+  cfg->timestep_scale_multiplier = 1000.0f;
+  cfg->norm_eps = 1e-6f;
+  cfg->vae_latent_channels = 128;
+  cfg->vae_base_channels = 1024;
+  cfg->vae_blocks_per_stage = 5;
+  cfg->vae_patch_size = 4;
+}
+
+int ltx_ctx_create(const ltx_config* cfg, int device, ltx_ctx** out) {
+  if (!cfg || !out) return LTX_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    LTX_CHECK(e == cudaSuccess && ndev > 0, LTX_ERR_CUDA, "no CUDA device available (libltxcuda has no CPU fallback)");
+    LTX_CHECK(device >= 0 && device < ndev, LTX_ERR_INVALID_ARGUMENT, "bad device index");
+    cudaDeviceProp prop;
+    LTX_CUDA(cudaGetDeviceProperties(&prop, device));
+    LTX_CHECK(prop.major == 10, LTX_ERR_CUDA,
+              std::string("libltxcuda requires an sm_100a (Blackwell) device, found ") + prop.name);
+    LTX_CHECK(cfg->head_dim == 128, LTX_ERR_INVALID_CONFIGURATION, "head_dim must be 128");
+    LTX_CHECK(cfg->num_layers > 0 && cfg->num_heads > 0 && cfg->ffn_mult > 0, LTX_ERR_INVALID_CONFIGURATION,
+              "bad transformer configuration");
+    LTX_CUDA(cudaSetDevice(device));
+    ltx_ctx* c = new ltx_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    LTX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return LTX_OK;
+  } catch (const LtxError& e) {
+    g_create_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return LTX_ERR_CUDA;
+  }
+}
+
+int ltx_ctx_destroy(ltx_ctx* c) {
+  if (!c) return LTX_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->tensors)
+    if (kv.second.ptr) cudaFree(kv.second.ptr);
+  for (void* p : c->owned) cudaFree(p);
+  DevBuf* bufs[] = {&c->api_lat, &c->api_ctx, &c->lat_in, &c->ctx_in, &c->ts_in, &c->mask_in, &c->x, &c->xb, &c->h, &c->qk, &c->vt, &c->att, &c->q2,
+                    &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
+                    &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
+                    &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
+                    &c->v_lat, &c->v_noise, &c->v_frames};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return LTX_OK;
+}
+
+const char* ltx_last_error(const ltx_ctx* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
+
+int ltx_sync(ltx_ctx* c) {
+  return guarded(c, [&] { LTX_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+uint64_t ltx_launch_count(const ltx_ctx* c) { return c ? c->launches : 0; }
+
+int ltx_load_tensor(ltx_ctx* c, const char* key, const void* host_data, ltx_dtype dtype, const int64_t* shape, int ndim) {
+  return guarded(c, [&] {
+    LTX_CHECK(key != nullptr, LTX_ERR_INVALID_ARGUMENT, "null key");
+    load_tensor_host(c, key, host_data, dtype, shape, ndim);
+  });
+}
+
+int ltx_init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
+  return guarded(c, [&] { init_random_weights(c, which, seed); });
+}
+
+int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
+  return guarded(c, [&] {
+    (void)group_size;
+    LTX_CHECK(quant_bits == 16, LTX_ERR_UNSUPPORTED, "only bf16 weights (quant_bits = 16) are implemented");
+    if (c->tensors.count("patchify_proj.weight")) dit_finalize(c);
+    if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);
+    LTX_CHECK(c->dit_ready || c->vae.ready, LTX_ERR_WEIGHTS, "no weights loaded");
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_dit_forward_dev(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, const void* context,
+                        ltx_dtype context_dtype, const float* timesteps, int ts_per_token, const int32_t* mask, int B, int N,
+                        int S, int F, int H, int W, const ltx_dit_flags* flags, float* out_velocity) {
+  return guarded(c, [&] {
+    dit_forward_dev(c, latent, latent_dtype, context, context_dtype, timesteps, ts_per_token, mask, B, N, S, F, H, W, flags,
+                    out_velocity);
+  });
+}
+
+int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, const void* context, ltx_dtype context_dtype,
+                    const float* timesteps, int ts_per_token, const int32_t* mask, int B, int N, int S, int F, int H,
+                    int W, const ltx_dit_flags* flags, float* out_velocity) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && context && timesteps && out_velocity, LTX_ERR_INVALID_ARGUMENT, "null tensor");
+    LTX_CHECK(B >= 1 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
+    LTX_CHECK(ts_per_token == 0, LTX_ERR_UNSUPPORTED, "per-token timesteps are not implemented");
+    const ltx_config& g = c->cfg;
+    const size_t R = static_cast<size_t>(B) * N;
+    // the staged copies live in dedicated buffers (dit_forward_dev's own staging buffers are distinct: it is told bf16
+    // inputs are already on the device only when no cast is needed)
+    DevBuf& lat = c->api_lat;
+    DevBuf& ctx = c->api_ctx;
+    h2d(c, lat, latent, R * g.in_channels * dsize(latent_dtype));
+    const bool cached = flags && flags->context_key != 0 &&
+                        ((c->text[0].key == flags->context_key && c->text[0].B == B && c->text[0].S == S) ||
+                         (c->text[1].key == flags->context_key && c->text[1].B == B && c->text[1].S == S));
+    if (!cached) h2d(c, ctx, context, static_cast<size_t>(B) * S * g.caption_channels * dsize(context_dtype));
+    h2d(c, c->ts_in, timesteps, static_cast<size_t>(B) * 4);
+    const int32_t* mask_dev = nullptr;
+    if (mask) {
+      h2d(c, c->mask_in, mask, static_cast<size_t>(B) * S * 4);
+      mask_dev = c->mask_in.as<int32_t>();
+    }
+    c->vel.reserve(R * g.out_channels * 4);
+    dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), 0, mask_dev, B, N, S, F, H, W,
+                    flags, c->vel.as<float>());
+    LTX_CUDA(cudaMemcpyAsync(out_velocity, c->vel.ptr, R * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_dit_clear_caches(ltx_ctx* c) {
+  return guarded(c, [&] { dit_clear_caches(c); });
+}
+
+int ltx_guided_euler_step_dev(ltx_ctx* c, float* latent, const float* v_cond, const float* v_uncond, const float* v_stg,
+                              float* v_prev, int use_prev, size_t n, float cfg_scale, float rescale_phi, float stg_scale,
+                              float ge_gamma, float sigma, float sigma_next) {
+  return guarded(c, [&] {
+    c->scratch.reserve(64 * sizeof(double));
+    GuidedEulerArgs a;
+    a.latent = latent; a.v_cond = v_cond; a.v_uncond = v_uncond; a.v_stg = v_stg; a.v_prev = v_prev;
+    a.use_prev = use_prev; a.v_out = nullptr; a.n = n; a.cfg = cfg_scale; a.phi = rescale_phi; a.stg = stg_scale;
+    a.ge_gamma = ge_gamma; a.sigma = sigma; a.sigma_next = sigma_next; a.scratch = c->scratch.as<double>();
+    launch_guided_euler(a, c->stream);
+    c->launches += (v_uncond && rescale_phi > 0.f) ? 2 : 1;
+  });
+}
+
+int ltx_guided_euler_step(ltx_ctx* c, float* latent, const float* v_cond, const float* v_uncond, const float* v_stg,
+                          float* v_prev, int use_prev, size_t n, float cfg_scale, float rescale_phi, float stg_scale,
+                          float ge_gamma, float sigma, float sigma_next) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && v_cond && n > 0, LTX_ERR_INVALID_ARGUMENT, "null tensor");
+    const size_t bytes = n * 4;
+    h2d(c, c->s_latent, latent, bytes);
+    h2d(c, c->s_vc, v_cond, bytes);
+    if (v_uncond) h2d(c, c->s_vu, v_uncond, bytes);
+    if (v_stg) h2d(c, c->s_vs, v_stg, bytes);
+    if (v_prev) {
+      if (use_prev) h2d(c, c->s_vprev, v_prev, bytes);
+      else c->s_vprev.reserve(bytes);
+    }
+    c->scratch.reserve(64 * sizeof(double));
+    GuidedEulerArgs a;
+    a.latent = c->s_latent.as<float>(); a.v_cond = c->s_vc.as<float>();
+    a.v_uncond = v_uncond ? c->s_vu.as<float>() : nullptr;
+    a.v_stg = v_stg ? c->s_vs.as<float>() : nullptr;
+    a.v_prev = v_prev ? c->s_vprev.as<float>() : nullptr;
+    a.use_prev = use_prev; a.v_out = nullptr; a.n = n; a.cfg = cfg_scale; a.phi = rescale_phi; a.stg = stg_scale;
+    a.ge_gamma = ge_gamma; a.sigma = sigma; a.sigma_next = sigma_next; a.scratch = c->scratch.as<double>();
+    launch_guided_euler(a, c->stream);
+    c->launches += (v_uncond && rescale_phi > 0.f) ? 2 : 1;
+    LTX_CUDA(cudaMemcpyAsync(latent, c->s_latent.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (v_prev) LTX_CUDA(cudaMemcpyAsync(v_prev, c->s_vprev.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+// ---------------------------------------------------------------- resident denoise session
+int ltx_denoise_begin(ltx_ctx* c, const float* noise, int F, int H, int W, float sigma0, const void* context,
+                      ltx_dtype context_dtype, const int32_t* mask, const void* neg_context, const int32_t* neg_mask, int S) {
+  return guarded(c, [&] {
+    LTX_CHECK(noise && context && F > 0 && H > 0 && W > 0 && S > 0, LTX_ERR_INVALID_ARGUMENT, "bad denoise_begin arguments");
+    const ltx_config& g = c->cfg;
+    LTX_CHECK(g.in_channels == g.out_channels, LTX_ERR_INVALID_CONFIGURATION, "in/out channels must match");
+    const size_t n = static_cast<size_t>(g.in_channels) * F * H * W;
+    c->s_F = F; c->s_H = H; c->s_W = W; c->s_S = S;
+    c->s_ctx_dtype = context_dtype;
+    h2d(c, c->s_latent, noise, n * 4);
+    launch_scale_f32(c->s_latent.as<float>(), sigma0, static_cast<int64_t>(n), c->stream);  // P/LTXPipeline.swift:793
+    c->launches++;
+    const size_t cbytes = static_cast<size_t>(S) * g.caption_channels * dsize(context_dtype);
+    h2d(c, c->s_ctx_pos, context, cbytes);
+    c->s_has_mask_pos = mask != nullptr;
+    if (mask) h2d(c, c->s_mask_pos, mask, static_cast<size_t>(S) * 4);
+    c->s_has_neg = neg_context != nullptr;
+    if (neg_context) {
+      h2d(c, c->s_ctx_neg, neg_context, cbytes);
+      c->s_has_mask_neg = neg_mask != nullptr;
+      if (neg_mask) h2d(c, c->s_mask_neg, neg_mask, static_cast<size_t>(S) * 4);
+    }
+    c->s_tok.reserve(n * 2);
+    c->s_vc.reserve(n * 4);
+    c->s_vu.reserve(n * 4);
+    c->s_vs.reserve(n * 4);
+    c->s_vprev.reserve(n * 4);
+    c->vel.reserve(n * 4);
+    c->s_sigma.reserve(16);
+    c->s_serial += 2;  // fresh context-cache keys for this session
+    dit_clear_caches(c);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
+  return guarded(c, [&] {
+    LTX_CHECK(p != nullptr && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "denoise_step before denoise_begin");
+    LTX_CHECK(p->sigma > 0.f, LTX_ERR_INVALID_ARGUMENT, "sigma must be > 0");
+    const ltx_config& g = c->cfg;
+    const int C = g.in_channels, F = c->s_F, H = c->s_H, W = c->s_W, S = c->s_S;
+    const int T = F * H * W;
+    const size_t n = static_cast<size_t>(C) * T;
+    cudaStream_t st = c->stream;
+    // patchify(latent).asType(.bfloat16)  (P/LTXPipeline.swift:815)
+    launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
+    LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
+    c->launches++;
+    const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
+    auto pass = [&](bool neg, bool stg, float* v_lat) {
+      ltx_dit_flags fl = {};
+      fl.cross_attn_scale = 1.0f;
+      fl.context_key = neg ? key_neg : key_pos;
+      if (stg) {
+        fl.n_stg_blocks = p->n_stg_blocks;
+        for (int i = 0; i < p->n_stg_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i) fl.stg_blocks[i] = p->stg_blocks[i];
+        fl.skip_self_attn = 1;
+      }
+      const void* cx = neg ? c->s_ctx_neg.ptr : c->s_ctx_pos.ptr;
+      const int32_t* mk = neg ? (c->s_has_mask_neg ? c->s_mask_neg.as<int32_t>() : nullptr)
+                              : (c->s_has_mask_pos ? c->s_mask_pos.as<int32_t>() : nullptr);
+      dit_forward_dev(c, c->s_tok.ptr, LTX_BF16, cx, c->s_ctx_dtype, c->s_sigma.as<float>(), 0, mk, 1, T, S, F, H, W, &fl,
+                      c->vel.as<float>());
+      launch_unpatchify(c->vel.as<float>(), v_lat, C, T, st);  // velocity back to [C, F, H, W]
+      c->launches++;
+    };
+    const bool use_cfg = p->cfg_scale > 1.0f && c->s_has_neg;
+    const bool use_stg = p->stg_scale > 0.f && p->n_stg_blocks > 0;
+    pass(false, false, c->s_vc.as<float>());
+    if (use_cfg) pass(true, false, c->s_vu.as<float>());
+    if (use_stg) pass(false, true, c->s_vs.as<float>());
+    GuidedEulerArgs a;
+    a.latent = c->s_latent.as<float>(); a.v_cond = c->s_vc.as<float>();
+    a.v_uncond = use_cfg ? c->s_vu.as<float>() : nullptr;
+    a.v_stg = use_stg ? c->s_vs.as<float>() : nullptr;
+    a.v_prev = c->s_vprev.as<float>();
+    a.use_prev = p->step_index > 0 ? 1 : 0;
+    a.v_out = nullptr; a.n = n; a.cfg = p->cfg_scale; a.phi = p->rescale_phi; a.stg = p->stg_scale;
+    a.ge_gamma = p->ge_gamma; a.sigma = p->sigma; a.sigma_next = p->sigma_next; a.scratch = c->scratch.as<double>();
+    launch_guided_euler(a, st);
+    c->launches += (use_cfg && p->rescale_phi > 0.f) ? 2 : 1;
+  });
+}
+
+int ltx_denoise_get_latent(ltx_ctx* c, float* out) {
+  return guarded(c, [&] {
+    LTX_CHECK(out && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "no denoise session");
+    const size_t n = static_cast<size_t>(c->cfg.in_channels) * c->s_F * c->s_H * c->s_W;
+    LTX_CUDA(cudaMemcpyAsync(out, c->s_latent.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_denoise_latent_dev(ltx_ctx* c, float** p) {
+  return guarded(c, [&] {
+    LTX_CHECK(p && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "no denoise session");
+    *p = c->s_latent.as<float>();
+  });
+}
+
+// ---------------------------------------------------------------- VAE
+int ltx_vae_decode_dev(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                       int causal, float* out_frames) {
+  return guarded(c, [&] { vae_decode_dev(c, latent, Fp, Hp, Wp, timestep, decode_noise, causal, out_frames); });
+}
+
+int ltx_vae_decode(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                   int causal, float* out_frames) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && out_frames && Fp > 0 && Hp > 0 && Wp > 0, LTX_ERR_INVALID_ARGUMENT, "bad vae_decode arguments");
+    const size_t n = static_cast<size_t>(c->cfg.vae_latent_channels) * Fp * Hp * Wp;
+    h2d(c, c->v_lat, latent, n * 4);
+    const float* nz = nullptr;
+    if (timestep >= 0.f) {
+      LTX_CHECK(decode_noise != nullptr, LTX_ERR_INVALID_ARGUMENT, "decode_noise is required when timestep >= 0");
+      h2d(c, c->v_noise, decode_noise, n * 4);
+      nz = c->v_noise.as<float>();
+    }
+    const size_t fo = static_cast<size_t>(8 * (Fp - 1) + 1) * (32 * Hp) * (32 * Wp) * 3;
+    c->v_frames.reserve(fo * 4);
+    vae_decode_dev(c, c->v_lat.as<float>(), Fp, Hp, Wp, timestep, nz, causal, c->v_frames.as<float>());
+    LTX_CUDA(cudaMemcpyAsync(out_frames, c->v_frames.ptr, fo * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+// ---------------------------------------------------------------- diagnostic single-kernel ops
+int ltx_op_gemm(ltx_ctx* c, const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int mode,
+                int force_bn) {
+  return guarded(c, [&] {
+    LTX_CHECK(mode == EPI_BF16 || mode == EPI_GELU_BF16 || mode == EPI_F32, LTX_ERR_INVALID_ARGUMENT, "bad mode");
+    GemmEpi e;
+    e.mode = mode; e.out = C; e.ldo = N; e.bias = bias;
+    launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);
+    c->launches++;
+  });
+}
+
+int ltx_op_gemm_resid(ltx_ctx* c, const void* A, const void* B, const float* bias, float* x, const float* gate_a,
+                      const float* gate_b, void* shadow, int M, int N, int K, float scale) {
+  return guarded(c, [&] {
+    GemmEpi e;
+    e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = bias; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = 0;
+    e.rows_per_gate = M > 0 ? M : 1; e.shadow = reinterpret_cast<bf16*>(shadow); e.lds = N; e.scale = scale;
+    launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_attention(ltx_ctx* c, const void* Q, const void* K, const void* Vt, int64_t ldv, const float* key_bias, void* O,
+                     int B, int H, int Nq, int Nk, float scale) {
+  return guarded(c, [&] {
+    const int D = H * 128;
+    launch_attention(reinterpret_cast<const bf16*>(Q), D, reinterpret_cast<const bf16*>(K), D,
+                     reinterpret_cast<const bf16*>(Vt), ldv, key_bias, reinterpret_cast<bf16*>(O), D, B, H, Nq, Nk, D, scale,
+                     c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_rmsnorm_mod(ltx_ctx* c, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
+                       const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm) {
+  return guarded(c, [&] {
+    launch_rmsnorm_mod(x, reinterpret_cast<bf16*>(out_bf16), M, D, tbl_shift, tbl_scale, ada_shift, ada_scale, 0, M, eps,
+                       layernorm, c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_qknorm_rope(ltx_ctx* c, void* x_bf16, int M, int D, const float* w, const float* cos_tab, const float* sin_tab,
+                       int rows_per_rope, float eps) {
+  return guarded(c, [&] {
+    launch_qknorm_rope(reinterpret_cast<bf16*>(x_bf16), D, M, D, w, cos_tab, sin_tab, rows_per_rope, eps, c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_conv3d(ltx_ctx* c, const float* x, const void* w, const float* bias, float* out, int T, int H, int W, int Cin,
+                  int Cout, int causal) {
+  return guarded(c, [&] {
+    c->v_pad.reserve(static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * Cin * 2);
+    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, Cin, 0, nullptr, nullptr, causal, c->stream);
+    ConvEpi e;
+    e.mode = 0; e.out = out; e.bias = bias; e.resid = nullptr; e.Cin = Cin;
+    launch_conv3d(c->v_pad.as<bf16>(), reinterpret_cast<const bf16*>(w), T, H, W, Cin, Cout, e, c->stream);
+    c->launches += 2;
+  });
+}
+
+}  // extern "C"

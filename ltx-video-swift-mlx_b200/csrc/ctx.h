@@ -1,0 +1,143 @@
+// libltxcuda context: device weights, workspaces and caches for one GPU.
+#pragma once
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ltxcuda.h"
+#include "ltx_internal.h"
+
+namespace ltx {
+
+struct DevTensor {
+  void* ptr = nullptr;
+  int dtype = LTX_F32;  // storage dtype on the device: LTX_BF16 or LTX_F32
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t n) {
+    if (n <= bytes) return;
+    if (ptr) LTX_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+    LTX_CUDA(cudaMalloc(&ptr, n));
+    bytes = n;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+struct AttnWeights {
+  const bf16 *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr;  // [D, D]; attn1: wq points at the packed [2D, D] q|k
+  const float *bq = nullptr, *bk = nullptr, *bv = nullptr, *bo = nullptr;
+  const float *q_norm = nullptr, *k_norm = nullptr;
+};
+
+struct BlockWeights {
+  const float* sst = nullptr;  // scale_shift_table [6, D]
+  AttnWeights a1, a2;
+  const bf16 *w_in = nullptr, *w_out = nullptr;
+  const float *b_in = nullptr, *b_out = nullptr;
+};
+
+struct TextCache {  // caption projection + per-block cross-attention K / V^T (step-invariant)
+  uint64_t key = 0;
+  int B = 0, S = 0;
+  int64_t ldv = 0;
+  DevBuf k;    // [L][B*S, D] bf16
+  DevBuf vt;   // [L][D, ldv] bf16
+  DevBuf bias; // [B, S] fp32 additive key bias (or unused when no mask)
+  bool has_bias = false;
+};
+
+struct ConvW {
+  const bf16* w = nullptr;  // [27][Cout][Cin]
+  const float* b = nullptr;
+  int cin = 0, cout = 0;
+};
+struct VaeResBlock {
+  ConvW c1, c2;
+  const float* sst = nullptr;  // [4, C] rows shift1, scale1, shift2, scale2
+};
+struct VaeWeights {
+  bool ready = false;
+  const float *mean = nullptr, *std = nullptr;
+  ConvW conv_in, conv_out;
+  std::vector<std::vector<VaeResBlock>> stages;  // 4 stages x blocks_per_stage
+  std::vector<ConvW> ups;                        // 3 depth-to-space convs
+  const float* last_sst = nullptr;               // [2, C_last] rows shift, scale
+};
+
+}  // namespace ltx
+
+struct ltx_ctx {
+  ltx_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  mutable std::string last_error;
+  uint64_t launches = 0;
+
+  std::map<std::string, ltx::DevTensor> tensors;  // raw tensors by post-mapping key
+  std::vector<void*> owned;                       // packed allocations made by finalize
+  bool dit_ready = false;
+  std::vector<ltx::BlockWeights> blocks;
+  const ltx::bf16 *w_patch = nullptr, *w_t1 = nullptr, *w_t2 = nullptr, *w_ada = nullptr, *w_c1 = nullptr, *w_c2 = nullptr,
+                  *w_out = nullptr;
+  const float *b_patch = nullptr, *b_t1 = nullptr, *b_t2 = nullptr, *b_ada = nullptr, *b_c1 = nullptr, *b_c2 = nullptr,
+              *b_out = nullptr, *sst_out = nullptr;
+  ltx::VaeWeights vae;
+
+  // ---- DiT workspaces (grow-only)
+  ltx::DevBuf lat_in, ctx_in, ts_in, mask_in;      // staged inputs
+  ltx::DevBuf api_lat, api_ctx;                    // host-API upload buffers
+  ltx::DevBuf x, xb, h, qk, vt, att, q2, ffh, vel;  // activations
+  ltx::DevBuf se, t1, emb, ada;                     // timestep path
+  ltx::DevBuf c1, c2;                               // caption projection
+  ltx::DevBuf rope_cos, rope_sin;
+  int rope_f = 0, rope_h = 0, rope_w = 0;
+  ltx::TextCache text[2];
+  int text_rr = 0;
+  ltx::DevBuf scratch;  // small fp64 scratch for reductions
+
+  // ---- resident denoise session
+  ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma;
+  int s_F = 0, s_H = 0, s_W = 0, s_S = 0;
+  bool s_has_neg = false, s_has_mask_pos = false, s_has_mask_neg = false;
+  int s_ctx_dtype = LTX_BF16;
+  uint64_t s_serial = 0;
+
+  // ---- VAE workspaces
+  ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames;
+};
+
+namespace ltx {
+// dit.cu
+void dit_finalize(ltx_ctx* c);
+void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
+                     const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
+                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev);
+void dit_clear_caches(ltx_ctx* c);
+// vae.cu
+void vae_finalize(ltx_ctx* c);
+void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
+                    int causal, float* frames_dev);
+// weights.cu
+const DevTensor& get_tensor(ltx_ctx* c, const std::string& key);
+void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int dtype, const int64_t* shape, int ndim);
+void init_random_weights(ltx_ctx* c, int which, uint64_t seed);
+}  // namespace ltx

@@ -1,0 +1,384 @@
+// LTX-2 video DiT forward on one B200: orchestration of the sm_100a kernels.
+// Restates LTXTransformer.callAsFunction (Models/Transformer/LTXTransformer.swift:235-486) and
+// BasicTransformerBlock.callAsFunction (Models/Transformer/LTXTransformerBlock.swift:187-232).
+//
+// HBM layout (token-major, rows r = b*N + token):
+//   x   fp32 [R, D]   residual stream          xb  bf16 [R, D]  bf16 shadow of x (A operand of the cross-attn q-proj)
+//   h   bf16 [R, D]   AdaLN output             qk  bf16 [R, 2D] fused q|k projection (normed + RoPE'd in place)
+//   vt  bf16 [D, ldv] V^T (K-major for P V)    att bf16 [R, D]  attention output
+//   ffh bf16 [R, 4D]  GELU(FFN in)             text cache: per block K [B*S, D], V^T [D, ldv2] (step-invariant)
+#include <cmath>
+
+#include "ctx.h"
+
+namespace ltx {
+
+namespace {
+
+struct Launcher {
+  ltx_ctx* c;
+  void count(int n = 1) { c->launches += n; }
+};
+
+const bf16* wbf(ltx_ctx* c, const std::string& k, int64_t r, int64_t cc) {
+  const DevTensor& t = get_tensor(c, k);
+  LTX_CHECK(t.dtype == LTX_BF16 && t.shape.size() == 2 && t.shape[0] == r && t.shape[1] == cc, LTX_ERR_WEIGHTS,
+            "bad shape for '" + k + "'");
+  return reinterpret_cast<const bf16*>(t.ptr);
+}
+const float* wf(ltx_ctx* c, const std::string& k, int64_t n) {
+  const DevTensor& t = get_tensor(c, k);
+  LTX_CHECK(t.dtype == LTX_F32 && t.numel() == n, LTX_ERR_WEIGHTS, "bad shape for '" + k + "'");
+  return reinterpret_cast<const float*>(t.ptr);
+}
+
+// Host fp64 RoPE table, token-major [N, D/2] (T/LTXRoPE.swift:375-488, 552-610; see oracle.rope_table).
+void build_rope(ltx_ctx* c, int F, int H, int W) {
+  if (c->rope_f == F && c->rope_h == H && c->rope_w == W && c->rope_cos.ptr) return;
+  const ltx_config& g = c->cfg;
+  const int D = g.num_heads * g.head_dim;
+  const int half = D / 2;
+  const int n_idx = std::max(1, D / 6);
+  const int pad = std::max(0, half - n_idx * 3);
+  const int64_t N = static_cast<int64_t>(F) * H * W;
+  std::vector<float> cs(static_cast<size_t>(N) * half), sn(static_cast<size_t>(N) * half);
+  std::vector<double> idx(n_idx);
+  for (int i = 0; i < n_idx; ++i) {
+    const double t = n_idx > 1 ? static_cast<double>(i) / (n_idx - 1) : 0.0;
+    idx[i] = std::pow(static_cast<double>(g.rope_theta), t) * (M_PI / 2.0);
+  }
+  for (int f = 0; f < F; ++f) {
+    // pixel-space temporal mid-point with the causal fix, divided by fps = 24 -- all in fp32 like the reference
+    const float ts = 8.0f, fi = static_cast<float>(f);
+    const float st = std::max(fi * ts + (1.0f - ts), 0.0f), en = std::max((fi + 1.0f) * ts + (1.0f - ts), 0.0f);
+    const float pt = ((st + en) / 2.0f) / 24.0f;
+    for (int y = 0; y < H; ++y) {
+      const float phh = static_cast<float>(y) * 32.0f + 16.0f;
+      for (int x = 0; x < W; ++x) {
+        const float pw = static_cast<float>(x) * 32.0f + 16.0f;
+        const int64_t n = (static_cast<int64_t>(f) * H + y) * W + x;
+        const double sc[3] = {static_cast<double>(pt) / g.max_pos[0] * 2.0 - 1.0,
+                              static_cast<double>(phh) / g.max_pos[1] * 2.0 - 1.0,
+                              static_cast<double>(pw) / g.max_pos[2] * 2.0 - 1.0};
+        float* cr = &cs[static_cast<size_t>(n) * half];
+        float* sr = &sn[static_cast<size_t>(n) * half];
+        for (int p = 0; p < pad; ++p) { cr[p] = 1.0f; sr[p] = 0.0f; }
+        for (int k = 0; k < n_idx; ++k)
+          for (int d = 0; d < 3; ++d) {
+            const int o = pad + k * 3 + d;
+            if (o >= half) continue;
+            const double a = idx[k] * sc[d];
+            cr[o] = static_cast<float>(std::cos(a));
+            sr[o] = static_cast<float>(std::sin(a));
+          }
+      }
+    }
+  }
+  const size_t bytes = cs.size() * sizeof(float);
+  c->rope_cos.reserve(bytes);
+  c->rope_sin.reserve(bytes);
+  LTX_CUDA(cudaMemcpyAsync(c->rope_cos.ptr, cs.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+  LTX_CUDA(cudaMemcpyAsync(c->rope_sin.ptr, sn.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+  LTX_CUDA(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  c->rope_f = F; c->rope_h = H; c->rope_w = W;
+}
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+bool in_list(int v, const int32_t* lst, int n) {
+  for (int i = 0; i < n; ++i)
+    if (lst[i] == v) return true;
+  return false;
+}
+
+// caption projection + per-block text K / V^T (T/LTXTimestepEmbedding.swift:146-151, T/LTXAttention.swift:171-180)
+TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, const int32_t* mask_dev, int B, int S,
+                        uint64_t key) {
+  const ltx_config& g = c->cfg;
+  const int D = g.num_heads * g.head_dim, L = g.num_layers, Cc = g.caption_channels;
+  if (key != 0)
+    for (auto& t : c->text)
+      if (t.key == key && t.B == B && t.S == S) return t;
+  // miss: take an un-keyed slot if there is one, otherwise evict round-robin
+  int slot = -1;
+  for (int i = 0; i < 2; ++i)
+    if (c->text[i].key == 0) { slot = i; break; }
+  if (slot < 0) slot = (c->text_rr++) & 1;
+  TextCache& tc = c->text[slot];
+  const int64_t R = static_cast<int64_t>(B) * S;
+  tc.key = key; tc.B = B; tc.S = S;
+  tc.ldv = round_up(R, 8);
+  tc.k.reserve(static_cast<size_t>(L) * R * D * 2);
+  tc.vt.reserve(static_cast<size_t>(L) * D * tc.ldv * 2);
+  cudaStream_t st = c->stream;
+  // stage context as bf16
+  const bf16* ctx_bf;
+  if (context_dtype == LTX_BF16) {
+    ctx_bf = reinterpret_cast<const bf16*>(context);
+  } else {
+    LTX_CHECK(context_dtype == LTX_F32, LTX_ERR_UNSUPPORTED, "context dtype must be bf16 or f32");
+    LTX_CHECK((R * Cc) % 4 == 0, LTX_ERR_INVALID_ARGUMENT, "context size");
+    c->ctx_in.reserve(static_cast<size_t>(R) * Cc * 2);
+    launch_cast_f32_bf16(reinterpret_cast<const float*>(context), c->ctx_in.as<bf16>(), R * Cc, st);
+    c->launches++;
+    ctx_bf = c->ctx_in.as<bf16>();
+  }
+  c->c1.reserve(static_cast<size_t>(R) * D * 2);
+  c->c2.reserve(static_cast<size_t>(R) * D * 2);
+  GemmEpi e;
+  e.mode = EPI_GELU_BF16; e.out = c->c1.ptr; e.ldo = D; e.bias = c->b_c1;
+  launch_gemm(ctx_bf, Cc, c->w_c1, Cc, static_cast<int>(R), D, Cc, e, st);
+  e.mode = EPI_BF16; e.out = c->c2.ptr; e.bias = c->b_c2;
+  launch_gemm(c->c1.as<bf16>(), D, c->w_c2, D, static_cast<int>(R), D, D, e, st);
+  c->launches += 2;
+  for (int i = 0; i < L; ++i) {
+    const AttnWeights& a = c->blocks[i].a2;
+    bf16* kd = tc.k.as<bf16>() + static_cast<int64_t>(i) * R * D;
+    bf16* vd = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * tc.ldv;
+    GemmEpi ek;
+    ek.mode = EPI_BF16; ek.out = kd; ek.ldo = D; ek.bias = a.bk;
+    launch_gemm(c->c2.as<bf16>(), D, a.wk, D, static_cast<int>(R), D, D, ek, st);
+    launch_qknorm_rope(kd, D, static_cast<int>(R), D, a.k_norm, nullptr, nullptr, 1, g.norm_eps, st);
+    GemmEpi ev;  // V^T[D, R] = Wv [D, D] * c^T
+    ev.mode = EPI_BF16; ev.out = vd; ev.ldo = tc.ldv; ev.bias = a.bv; ev.bias_per_row = 1;
+    launch_gemm(a.wv, D, c->c2.as<bf16>(), D, D, static_cast<int>(R), D, ev, st);
+    c->launches += 3;
+  }
+  tc.has_bias = mask_dev != nullptr;
+  if (mask_dev) {
+    tc.bias.reserve(static_cast<size_t>(R) * 4);
+    launch_mask_to_bias(mask_dev, tc.bias.as<float>(), static_cast<int>(R), st);
+    c->launches++;
+  }
+  return tc;
+}
+
+}  // namespace
+
+void dit_clear_caches(ltx_ctx* c) {
+  c->rope_f = c->rope_h = c->rope_w = 0;
+  for (auto& t : c->text) { t.key = 0; t.B = t.S = 0; }
+}
+
+// Pack raw tensors into kernel-ready pointers.  attn1 to_q|to_k are concatenated into one [2D, D] operand so the
+// q and k projections run as a single N = 2D GEMM (better wave quantisation at M = 1536).
+void dit_finalize(ltx_ctx* c) {
+  const ltx_config& g = c->cfg;
+  LTX_CHECK(g.head_dim == 128, LTX_ERR_INVALID_CONFIGURATION, "head_dim must be 128");
+  const int64_t D = static_cast<int64_t>(g.num_heads) * g.head_dim, FF = g.ffn_mult * D;
+  LTX_CHECK(g.in_channels % 8 == 0 && g.caption_channels % 8 == 0 && g.out_channels % 8 == 0, LTX_ERR_INVALID_CONFIGURATION,
+            "channel counts must be multiples of 8");
+  c->w_patch = wbf(c, "patchify_proj.weight", D, g.in_channels);
+  c->b_patch = wf(c, "patchify_proj.bias", D);
+  c->w_t1 = wbf(c, "adaln_single.emb.linear_1.weight", D, 256);
+  c->b_t1 = wf(c, "adaln_single.emb.linear_1.bias", D);
+  c->w_t2 = wbf(c, "adaln_single.emb.linear_2.weight", D, D);
+  c->b_t2 = wf(c, "adaln_single.emb.linear_2.bias", D);
+  c->w_ada = wbf(c, "adaln_single.linear.weight", 6 * D, D);
+  c->b_ada = wf(c, "adaln_single.linear.bias", 6 * D);
+  c->w_c1 = wbf(c, "caption_projection.linear_1.weight", D, g.caption_channels);
+  c->b_c1 = wf(c, "caption_projection.linear_1.bias", D);
+  c->w_c2 = wbf(c, "caption_projection.linear_2.weight", D, D);
+  c->b_c2 = wf(c, "caption_projection.linear_2.bias", D);
+  c->sst_out = wf(c, "scale_shift_table", 2 * D);
+  c->w_out = wbf(c, "proj_out.weight", g.out_channels, D);
+  c->b_out = wf(c, "proj_out.bias", g.out_channels);
+  c->blocks.assign(g.num_layers, BlockWeights());
+  for (int i = 0; i < g.num_layers; ++i) {
+    const std::string p = "transformer_blocks." + std::to_string(i) + ".";
+    BlockWeights& b = c->blocks[i];
+    b.sst = wf(c, p + "scale_shift_table", 6 * D);
+    // attn1: pack q|k
+    {
+      const bf16* wq = wbf(c, p + "attn1.to_q.weight", D, D);
+      const bf16* wk = wbf(c, p + "attn1.to_k.weight", D, D);
+      const float* bq = wf(c, p + "attn1.to_q.bias", D);
+      const float* bk = wf(c, p + "attn1.to_k.bias", D);
+      bf16* wqk = nullptr;
+      float* bqk = nullptr;
+      LTX_CUDA(cudaMalloc(&wqk, static_cast<size_t>(2) * D * D * 2));
+      c->owned.push_back(wqk);
+      LTX_CUDA(cudaMalloc(&bqk, static_cast<size_t>(2) * D * 4));
+      c->owned.push_back(bqk);
+      LTX_CUDA(cudaMemcpyAsync(wqk, wq, static_cast<size_t>(D) * D * 2, cudaMemcpyDeviceToDevice, c->stream));
+      LTX_CUDA(cudaMemcpyAsync(wqk + D * D, wk, static_cast<size_t>(D) * D * 2, cudaMemcpyDeviceToDevice, c->stream));
+      LTX_CUDA(cudaMemcpyAsync(bqk, bq, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, c->stream));
+      LTX_CUDA(cudaMemcpyAsync(bqk + D, bk, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, c->stream));
+      LTX_CUDA(cudaStreamSynchronize(c->stream));
+      // the unpacked copies are no longer needed
+      for (const char* k : {"attn1.to_q.weight", "attn1.to_k.weight"}) {
+        auto it = c->tensors.find(p + k);
+        cudaFree(it->second.ptr);
+        c->tensors.erase(it);
+      }
+      b.a1.wq = wqk; b.a1.wk = wqk + D * D; b.a1.bq = bqk; b.a1.bk = bqk + D;
+    }
+    b.a1.wv = wbf(c, p + "attn1.to_v.weight", D, D);
+    b.a1.bv = wf(c, p + "attn1.to_v.bias", D);
+    b.a1.wo = wbf(c, p + "attn1.to_out.weight", D, D);
+    b.a1.bo = wf(c, p + "attn1.to_out.bias", D);
+    b.a1.q_norm = wf(c, p + "attn1.q_norm.weight", D);
+    b.a1.k_norm = wf(c, p + "attn1.k_norm.weight", D);
+    b.a2.wq = wbf(c, p + "attn2.to_q.weight", D, D);
+    b.a2.bq = wf(c, p + "attn2.to_q.bias", D);
+    b.a2.wk = wbf(c, p + "attn2.to_k.weight", D, D);
+    b.a2.bk = wf(c, p + "attn2.to_k.bias", D);
+    b.a2.wv = wbf(c, p + "attn2.to_v.weight", D, D);
+    b.a2.bv = wf(c, p + "attn2.to_v.bias", D);
+    b.a2.wo = wbf(c, p + "attn2.to_out.weight", D, D);
+    b.a2.bo = wf(c, p + "attn2.to_out.bias", D);
+    b.a2.q_norm = wf(c, p + "attn2.q_norm.weight", D);
+    b.a2.k_norm = wf(c, p + "attn2.k_norm.weight", D);
+    b.w_in = wbf(c, p + "ff.project_in.proj.weight", FF, D);
+    b.b_in = wf(c, p + "ff.project_in.proj.bias", FF);
+    b.w_out = wbf(c, p + "ff.project_out.weight", D, FF);
+    b.b_out = wf(c, p + "ff.project_out.bias", D);
+  }
+  c->scratch.reserve(64 * sizeof(double));
+  c->dit_ready = true;
+}
+
+void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
+                     const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
+                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev) {
+  LTX_CHECK(c->dit_ready, LTX_ERR_WEIGHTS, "DiT weights not finalized");
+  LTX_CHECK(ts_per_token == 0, LTX_ERR_UNSUPPORTED, "per-token timesteps are not implemented");
+  LTX_CHECK(B >= 1 && B <= 4 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
+  LTX_CHECK(static_cast<int64_t>(F) * H * W == N, LTX_ERR_INVALID_ARGUMENT, "N must equal F*H*W");
+  LTX_CHECK(latent && context && timesteps_dev && out_velocity_dev, LTX_ERR_INVALID_ARGUMENT, "null tensor");
+  const ltx_config& g = c->cfg;
+  const int D = g.num_heads * g.head_dim, FFD = g.ffn_mult * D, Hh = g.num_heads, L = g.num_layers;
+  const int Cin = g.in_channels, Cout = g.out_channels;
+  const int R = B * N;
+  const float eps = g.norm_eps;
+  const float att_scale = 1.0f / sqrtf(static_cast<float>(g.head_dim));
+  cudaStream_t st = c->stream;
+  ltx_dit_flags noflags = {};
+  noflags.cross_attn_scale = 1.0f;
+  if (!flags) flags = &noflags;
+  LTX_CHECK(flags->n_stg_blocks >= 0 && flags->n_stg_blocks <= LTX_MAX_FLAG_BLOCKS && flags->n_cas_blocks >= 0 &&
+                flags->n_cas_blocks <= LTX_MAX_FLAG_BLOCKS,
+            LTX_ERR_INVALID_ARGUMENT, "bad flag block counts");
+
+  // ---- workspaces
+  const int64_t ldv = round_up(R, 8);
+  c->x.reserve(static_cast<size_t>(R) * D * 4);
+  c->xb.reserve(static_cast<size_t>(R) * D * 2);
+  c->h.reserve(static_cast<size_t>(R) * D * 2);
+  c->qk.reserve(static_cast<size_t>(R) * 2 * D * 2);
+  c->vt.reserve(static_cast<size_t>(D) * ldv * 2);
+  c->att.reserve(static_cast<size_t>(R) * D * 2);
+  c->q2.reserve(static_cast<size_t>(R) * D * 2);
+  c->ffh.reserve(static_cast<size_t>(R) * FFD * 2);
+  c->se.reserve(static_cast<size_t>(B) * 256 * 4);
+  c->t1.reserve(static_cast<size_t>(B) * D * 4);
+  c->emb.reserve(static_cast<size_t>(B) * D * 4);
+  c->ada.reserve(static_cast<size_t>(B) * 6 * D * 4);
+  float* x = c->x.as<float>();
+  bf16* xb = c->xb.as<bf16>();
+  bf16* h = c->h.as<bf16>();
+  bf16* qk = c->qk.as<bf16>();
+  bf16* vt = c->vt.as<bf16>();
+  bf16* att = c->att.as<bf16>();
+  bf16* q2 = c->q2.as<bf16>();
+  bf16* ffh = c->ffh.as<bf16>();
+  float* ada = c->ada.as<float>();
+  float* emb = c->emb.as<float>();
+
+  // ---- step-invariant pieces
+  build_rope(c, F, H, W);
+  TextCache& tc = prepare_text(c, context, context_dtype, mask_dev, B, S, flags->context_key);
+  const float* key_bias = tc.has_bias ? tc.bias.as<float>() : nullptr;
+
+  // ---- patchify_proj (T/LTXTransformer.swift:257); the reference's bf16 Linear output is rounded to bf16
+  const bf16* lat_bf;
+  if (latent_dtype == LTX_BF16) {
+    lat_bf = reinterpret_cast<const bf16*>(latent);
+  } else {
+    LTX_CHECK(latent_dtype == LTX_F32, LTX_ERR_UNSUPPORTED, "latent dtype must be bf16 or f32");
+    c->lat_in.reserve(static_cast<size_t>(R) * Cin * 2);
+    launch_cast_f32_bf16(reinterpret_cast<const float*>(latent), c->lat_in.as<bf16>(), static_cast<int64_t>(R) * Cin, st);
+    c->launches++;
+    lat_bf = c->lat_in.as<bf16>();
+  }
+  {
+    GemmEpi e;
+    e.mode = EPI_BF16; e.out = xb; e.ldo = D; e.bias = c->b_patch;
+    launch_gemm(lat_bf, Cin, c->w_patch, Cin, R, D, Cin, e, st);
+    launch_cast_bf16_f32(xb, x, static_cast<int64_t>(R) * D, st);
+    c->launches += 2;
+  }
+  // ---- timestep path (T/LTXTimestepEmbedding.swift:62-124): fp32 activations, bf16 weights
+  launch_sincos_embed(timesteps_dev, g.timestep_scale_multiplier, c->se.as<float>(), B, 256, st);
+  launch_gemv(c->w_t1, c->b_t1, c->se.as<float>(), c->t1.as<float>(), B, D, 256, 0, st);
+  launch_gemv(c->w_t2, c->b_t2, c->t1.as<float>(), emb, B, D, D, 1, st);
+  launch_gemv(c->w_ada, c->b_ada, emb, ada, B, 6 * D, D, 1, st);
+  c->launches += 4;
+
+  const int64_t ada_ld = 6 * static_cast<int64_t>(D);
+  for (int i = 0; i < L; ++i) {
+    const BlockWeights& bw = c->blocks[i];
+    const bool flagged = in_list(i, flags->stg_blocks, flags->n_stg_blocks);
+    const bool skip_sa = flagged && flags->skip_self_attn;
+    const bool skip_ff = flagged && flags->skip_ff;
+    const float cas = in_list(i, flags->cas_blocks, flags->n_cas_blocks) ? flags->cross_attn_scale : 1.0f;
+    if (!skip_sa) {
+      // h = rms(x) * (1 + scale_msa) + shift_msa      (T/LTXTransformerBlock.swift:72-83, rows 0/1 of table+ada)
+      launch_rmsnorm_mod(x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, N, eps, 0, st);
+      GemmEpi e;
+      e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
+      launch_gemm(h, D, bw.a1.wq, D, R, 2 * D, D, e, st);  // fused q|k projection
+      GemmEpi ev;
+      ev.mode = EPI_BF16; ev.out = vt; ev.ldo = ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
+      launch_gemm(bw.a1.wv, D, h, D, D, R, D, ev, st);  // V^T
+      launch_qknorm_rope(qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, st);
+      launch_qknorm_rope(qk + D, 2 * D, R, D, bw.a1.k_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, st);
+      launch_attention(qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale, st);
+      GemmEpi eo;  // x += (att Wo^T + bo) * gate_msa ; refresh the bf16 shadow
+      eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a1.bo;
+      eo.gate_a = ada + 2 * D; eo.gate_b = bw.sst + 2 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
+      eo.shadow = xb; eo.lds = D;
+      launch_gemm(att, D, bw.a1.wo, D, R, D, D, eo, st);
+      c->launches += 7;
+    }
+    {
+      // cross-attention on the UN-normalised stream (T/LTXTransformerBlock.swift:205-214)
+      GemmEpi e;
+      e.mode = EPI_BF16; e.out = q2; e.ldo = D; e.bias = bw.a2.bq;
+      launch_gemm(xb, D, bw.a2.wq, D, R, D, D, e, st);
+      launch_qknorm_rope(q2, D, R, D, bw.a2.q_norm, nullptr, nullptr, 1, eps, st);
+      const bf16* k2 = tc.k.as<bf16>() + static_cast<int64_t>(i) * B * S * D;
+      const bf16* v2 = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * tc.ldv;
+      launch_attention(q2, D, k2, D, v2, tc.ldv, key_bias, att, D, B, Hh, N, S, D, att_scale, st);
+      GemmEpi eo;
+      eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a2.bo; eo.scale = cas;
+      const bool next_needs_shadow = skip_ff && (i + 1 < L) &&
+                                     in_list(i + 1, flags->stg_blocks, flags->n_stg_blocks) && flags->skip_self_attn;
+      if (next_needs_shadow) { eo.shadow = xb; eo.lds = D; }
+      launch_gemm(att, D, bw.a2.wo, D, R, D, D, eo, st);
+      c->launches += 4;
+    }
+    if (!skip_ff) {
+      launch_rmsnorm_mod(x, h, R, D, bw.sst + 3 * D, bw.sst + 4 * D, ada + 3 * D, ada + 4 * D, ada_ld, N, eps, 0, st);
+      GemmEpi e;
+      e.mode = EPI_GELU_BF16; e.out = ffh; e.ldo = FFD; e.bias = bw.b_in;
+      launch_gemm(h, D, bw.w_in, D, R, FFD, D, e, st);
+      GemmEpi eo;
+      eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.b_out;
+      eo.gate_a = ada + 5 * D; eo.gate_b = bw.sst + 5 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
+      const bool next_needs_shadow =
+          (i + 1 < L) && in_list(i + 1, flags->stg_blocks, flags->n_stg_blocks) && flags->skip_self_attn;
+      if (next_needs_shadow) { eo.shadow = xb; eo.lds = D; }
+      launch_gemm(ffh, FFD, bw.w_out, FFD, R, D, FFD, eo, st);
+      c->launches += 3;
+    }
+  }
+  // ---- output head (T/LTXTransformer.swift:208-224): LayerNorm(no affine) * (1 + scale) + shift ; proj_out
+  launch_rmsnorm_mod(x, h, R, D, c->sst_out, c->sst_out + D, emb, emb, D, N, eps, 1, st);
+  GemmEpi e;
+  e.mode = EPI_F32; e.out = out_velocity_dev; e.ldo = Cout; e.bias = c->b_out;
+  launch_gemm(h, D, c->w_out, D, R, Cout, D, e, st);
+  c->launches += 2;
+}
+
+}  // namespace ltx

@@ -1,0 +1,307 @@
+// bf16 GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T with fused epilogues.
+//
+// Replaces the MLX `Linear`/`addMM` calls on the DiT path (SURVEY K1,K3,K5,K9,K10,K12,K13,K14;
+// T/LTXAttention.swift:171-175,217, T/LTXFeedForward.swift:47-51, T/LTXTransformer.swift:223,257).
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2-D boxes [128|BN rows x 64 cols] into a 128B-swizzled smem ring
+//   warp 1   : MMA issuer    -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16), accumulators in TMEM,
+//                               two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1
+//   warps 2-5: epilogue      -- tcgen05.ld (thread = output row, 32 columns at a time) -> bias / GELU / gate*residual
+// Edges: TMA zero-fills out-of-bounds rows/columns (M, N, K tails); the epilogue masks rows >= M and columns >= N.
+#include "ltx_internal.h"
+#include "ptx.cuh"
+
+namespace ltx {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512
+  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16;
+};
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, int M, int N,
+                                               const GemmEpi& ep) {
+  // One thread owns `row`, columns [col0, col0+32).
+  if (row >= M || col0 >= N) return;
+  const float rowbias = (ep.bias && ep.bias_per_row) ? ep.bias[row] : 0.0f;
+  const bool full = (col0 + 32 <= N);
+  if (MODE == EPI_GATE_RESID) {
+    float* xr = ep.resid + static_cast<int64_t>(row) * ep.ldr + col0;
+    const float* ga = ep.gate_a ? ep.gate_a + static_cast<int64_t>(row / ep.rows_per_gate) * ep.gate_ld + col0 : nullptr;
+    const float* gb = ep.gate_b ? ep.gate_b + col0 : nullptr;
+    bf16* sh = ep.shadow ? ep.shadow + static_cast<int64_t>(row) * ep.lds + col0 : nullptr;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 xv = *reinterpret_cast<const float4*>(xr + j);
+        float4 bv = (ep.bias && !ep.bias_per_row) ? *reinterpret_cast<const float4*>(ep.bias + col0 + j)
+                                                  : make_float4(rowbias, rowbias, rowbias, rowbias);
+        float4 gv = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (ga) {
+          gv = *reinterpret_cast<const float4*>(ga + j);
+          if (gb) {
+            float4 t = *reinterpret_cast<const float4*>(gb + j);
+            gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
+          }
+        }
+        xv.x += (__uint_as_float(r[j + 0]) + bv.x) * gv.x * ep.scale;
+        xv.y += (__uint_as_float(r[j + 1]) + bv.y) * gv.y * ep.scale;
+        xv.z += (__uint_as_float(r[j + 2]) + bv.z) * gv.z * ep.scale;
+        xv.w += (__uint_as_float(r[j + 3]) + bv.w) * gv.w * ep.scale;
+        *reinterpret_cast<float4*>(xr + j) = xv;
+        if (sh) {
+          uint2 pk = make_uint2(pack_bf16(xv.x, xv.y), pack_bf16(xv.z, xv.w));
+          *reinterpret_cast<uint2*>(sh + j) = pk;
+        }
+      }
+    } else {
+      for (int j = 0; j < 32 && col0 + j < N; ++j) {
+        float b = ep.bias ? (ep.bias_per_row ? rowbias : ep.bias[col0 + j]) : 0.f;
+        float g = ga ? (ga[j] + (gb ? gb[j] : 0.f)) : 1.f;
+        float v = xr[j] + (__uint_as_float(r[j]) + b) * g * ep.scale;
+        xr[j] = v;
+        if (sh) sh[j] = __float2bfloat16(v);
+      }
+    }
+  } else if (MODE == EPI_F32) {
+    float* o = reinterpret_cast<float*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 bv = (ep.bias && !ep.bias_per_row) ? *reinterpret_cast<const float4*>(ep.bias + col0 + j)
+                                                  : make_float4(rowbias, rowbias, rowbias, rowbias);
+        float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                               __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    } else {
+      for (int j = 0; j < 32 && col0 + j < N; ++j) {
+        float b = ep.bias ? (ep.bias_per_row ? rowbias : ep.bias[col0 + j]) : 0.f;
+        o[j] = __uint_as_float(r[j]) + b;
+      }
+    }
+  } else {  // EPI_BF16 / EPI_GELU_BF16
+    bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t += 4) {
+          float4 bv = (ep.bias && !ep.bias_per_row) ? *reinterpret_cast<const float4*>(ep.bias + col0 + j + t)
+                                                    : make_float4(rowbias, rowbias, rowbias, rowbias);
+          v[t + 0] = __uint_as_float(r[j + t + 0]) + bv.x;
+          v[t + 1] = __uint_as_float(r[j + t + 1]) + bv.y;
+          v[t + 2] = __uint_as_float(r[j + t + 2]) + bv.z;
+          v[t + 3] = __uint_as_float(r[j + t + 3]) + bv.w;
+        }
+        if (MODE == EPI_GELU_BF16) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = gelu_tanh(v[t]);
+        }
+        uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(o + j) = pk;
+      }
+    } else {
+      for (int j = 0; j < 32 && col0 + j < N; ++j) {
+        float b = ep.bias ? (ep.bias_per_row ? rowbias : ep.bias[col0 + j]) : 0.f;
+        float v = __uint_as_float(r[j]) + b;
+        if (MODE == EPI_GELU_BF16) v = gelu_tanh(v);
+        o[j] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                  const GemmEpi ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        const uint32_t aphase = (t >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int as = t & 1;
+      const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, M, N, ep);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int MODE>
+void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpi& epi,
+                 cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_bf16_tcgen05<BN, MODE>;
+  if (!configured) {
+    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM)));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, epi);
+  LTX_CUDA(cudaGetLastError());
+}
+
+template <int BN>
+void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpi& epi,
+               cudaStream_t stream) {
+  switch (epi.mode) {
+    case EPI_BF16: launch_impl<BN, EPI_BF16>(tmA, tmB, M, N, K, epi, stream); break;
+    case EPI_GELU_BF16: launch_impl<BN, EPI_GELU_BF16>(tmA, tmB, M, N, K, epi, stream); break;
+    case EPI_GATE_RESID: launch_impl<BN, EPI_GATE_RESID>(tmA, tmB, M, N, K, epi, stream); break;
+    case EPI_F32: launch_impl<BN, EPI_F32>(tmA, tmB, M, N, K, epi, stream); break;
+    default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
+  }
+}
+
+}  // namespace
+
+void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                 cudaStream_t stream, int force_bn) {
+  LTX_CHECK(M > 0 && N > 0 && K > 0, 2, "GEMM: empty problem");
+  LTX_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, 2, "GEMM: K and leading dims must be multiples of 8");
+  if (epi.mode == EPI_GATE_RESID) {
+    LTX_CHECK(epi.resid != nullptr && epi.ldr % 4 == 0, 2, "GEMM: residual epilogue needs fp32 resid with ld % 4 == 0");
+    LTX_CHECK(epi.shadow == nullptr || epi.lds % 4 == 0, 2, "GEMM: shadow ld must be a multiple of 4");
+  } else {
+    LTX_CHECK(epi.out != nullptr, 2, "GEMM: missing output");
+    LTX_CHECK(epi.ldo % (epi.mode == EPI_F32 ? 4 : 8) == 0, 2, "GEMM: output ld alignment");
+  }
+  // Tile-shape heuristic: 128x256 tiles halve the per-flop smem traffic; fall back to 128x128 when the 256-wide
+  // grid would leave most SMs idle or waste a large tail wave.
+  int bn = force_bn;
+  if (bn == 0) {
+    const int sms = device_sm_count();
+    const int mt = (M + BM - 1) / BM;
+    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+    auto waves_eff = [&](int tiles) { return static_cast<double>(tiles) / (((tiles + sms - 1) / sms) * sms); };
+    // cost model: time ~ waves * tile_cost ; 128x256 tile costs 2 units at ~1.0 efficiency, 128x128 costs 1 unit at ~0.85
+    const double c256 = ((t256 + sms - 1) / sms) * 2.0;
+    const double c128 = ((t128 + sms - 1) / sms) * 1.0 / 0.85;
+    (void)waves_eff;
+    bn = (N >= 256 && c256 <= c128) ? 256 : 128;
+  }
+  CUtensorMap tmA = make_tmap_2d(A, M, K, lda, BM);
+  CUtensorMap tmB = make_tmap_2d(B, N, K, ldb, bn);
+  if (bn == 256)
+    launch_bn<256>(tmA, tmB, M, N, K, epi, stream);
+  else
+    launch_bn<128>(tmA, tmB, M, N, K, epi, stream);
+}
+
+}  // namespace ltx

@@ -1,0 +1,131 @@
+// Internal declarations shared by the libltxcuda translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace ltx {
+
+typedef __nv_bfloat16 bf16;
+
+struct LtxError : public std::runtime_error {
+  int code;
+  LtxError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define LTX_CHECK(cond, code, msg)                                                                  \
+  do {                                                                                              \
+    if (!(cond)) throw ::ltx::LtxError((code), std::string(msg) + " [" #cond "] at " __FILE__ ":" + \
+                                                   std::to_string(__LINE__));                       \
+  } while (0)
+#define LTX_CUDA(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      throw ::ltx::LtxError(3, std::string("CUDA error: ") + cudaGetErrorString(_e) + " in " #expr " at " + \
+                                   __FILE__ ":" + std::to_string(__LINE__));                                 \
+  } while (0)
+
+// ---------------------------------------------------------------- TMA descriptors (tmap.cu)
+// 2-D row-major bf16 matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
+CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                         uint32_t box_cols = 64);
+// 4-D channels-last bf16 volume [T, H, W, C] (C fastest); box = [bt, bh, bw, 64 channels], 128B swizzle.
+CUtensorMap make_tmap_thwc(const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C, uint32_t bt, uint32_t bh,
+                           uint32_t bw);
+int device_sm_count();
+
+// ---------------------------------------------------------------- GEMM (gemm.cu)
+enum EpiMode : int {
+  EPI_BF16 = 0,        // out_bf16[m,n] = acc + bias
+  EPI_GELU_BF16 = 1,   // out_bf16[m,n] = gelu_tanh(acc + bias)
+  EPI_GATE_RESID = 2,  // resid[m,n] += (acc + bias) * gate * scale ; optional bf16 shadow of the new resid
+  EPI_F32 = 3,         // out_f32[m,n] = acc + bias
+};
+
+struct GemmEpi {
+  int mode = EPI_BF16;
+  void* out = nullptr;  // bf16 or f32, row pitch ldo (elements)
+  int64_t ldo = 0;
+  const float* bias = nullptr;  // [N], or [M] when bias_per_row
+  int bias_per_row = 0;
+  float* resid = nullptr;  // EPI_GATE_RESID: fp32 [M, ldr]
+  int64_t ldr = 0;
+  const float* gate_a = nullptr;  // gate = gate_a[(m / rows_per_gate) * gate_ld + n] + gate_b[n]; nullptr -> gate = 1
+  const float* gate_b = nullptr;
+  int64_t gate_ld = 0;
+  int rows_per_gate = 1;
+  bf16* shadow = nullptr;  // optional bf16 copy of the updated residual, row pitch lds
+  int64_t lds = 0;
+  float scale = 1.0f;
+};
+
+// C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 K-major (row pitch lda / ldb elements, multiples of 8).
+void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                 cudaStream_t stream, int force_bn = 0);
+
+// ---------------------------------------------------------------- attention (attention.cu)
+// Q [B*Nq, D], K [B*Nk, D] bf16 (head h = columns h*128..h*128+127); Vt [D, ldv] bf16 (row h*128+d, column b*Nk+j);
+// key_bias: optional fp32 [B, Nk] additive logits bias; O [B*Nq, D] bf16.  softmax(q k^T * scale + bias) v.
+void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldv,
+                      const float* key_bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
+                      cudaStream_t stream);
+
+// ---------------------------------------------------------------- elementwise / row kernels (elementwise.cu)
+// out_bf16[m,:] = norm(x[m,:]) * (1 + tbl_scale[n] + ada_scale[g*ada_ld + n]) + tbl_shift[n] + ada_shift[g*ada_ld + n],
+// g = m / rows_per_mod; norm = weight-less RMSNorm (layernorm = 0) or affine-less LayerNorm (layernorm = 1).
+void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tbl_shift, const float* tbl_scale,
+                        const float* ada_shift, const float* ada_scale, int64_t ada_ld, int rows_per_mod, float eps,
+                        int layernorm, cudaStream_t s);
+// In place on bf16 [M, ld]: y = rms(x[:, :D]) * w, then optional split-RoPE with cos/sin [rows_per_rope, D/2] (token-major).
+void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
+                        int rows_per_rope, float eps, cudaStream_t s);
+void launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s);
+void launch_cast_bf16_f32(const bf16* in, float* out, int64_t n, cudaStream_t s);
+// y[o] = act_out( sum_i W[o,i] * act_in(x[i]) + b[o] ), bf16 W [O,I]; tiny-M path for the timestep MLP (M rows).
+void launch_gemv(const bf16* W, const float* bias, const float* x, float* y, int M, int O, int I, int silu_in,
+                 cudaStream_t s);
+void launch_mask_to_bias(const int32_t* mask, float* bias, int n, cudaStream_t s);
+void launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
+void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s);
+// latent [C, T] (channel-major, T = F*H*W tokens) <-> tokens [T, C]
+void launch_patchify(const float* latent, bf16* tok_bf16, float* tok_f32, int C, int T, cudaStream_t s);
+void launch_unpatchify(const float* tok, float* latent, int C, int T, cudaStream_t s);
+// guidance + Euler (P/LatentUtils.swift:131-183, P/LTXPipeline.swift:920-927, S/LTXScheduler.swift:305-327)
+struct GuidedEulerArgs {
+  float* latent;          // in/out fp32 [n]
+  const float* v_cond;    // [n]
+  const float* v_uncond;  // nullable
+  const float* v_stg;     // nullable
+  float* v_prev;          // nullable in/out (GE momentum state)
+  int use_prev;           // apply GE (step > 0)
+  float* v_out;           // nullable: final velocity
+  size_t n;
+  float cfg, phi, stg, ge_gamma, sigma, sigma_next;
+  double* scratch;  // >= 8 doubles of device scratch for the rescale reductions
+};
+void launch_guided_euler(const GuidedEulerArgs& a, cudaStream_t s);
+void launch_fill_normal_bf16(bf16* p, int64_t n, float std, float mean, uint64_t seed, cudaStream_t s);
+void launch_fill_normal_f32(float* p, int64_t n, float std, float mean, uint64_t seed, cudaStream_t s);
+
+// ---------------------------------------------------------------- VAE kernels (conv3d.cu)
+struct ConvEpi {
+  int mode;                 // 0: out_f32 = acc + bias (+ resid) ; 1: depth-to-space scatter (+ tiled d2s residual) ; 2: unpatchify+clip to frames
+  float* out;               // mode 0: [T,H,W,Cout] fp32 ; mode 1: [2T-1,2H,2W,Cout/8] fp32 ; mode 2: [T,4H,4W,3] fp32
+  const float* bias;        // [Cout]
+  const float* resid;       // mode 0: nullable [T,H,W,Cout] ; mode 1: conv input x fp32 [T,H,W,Cin]
+  int Cin;
+};
+// x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [27][Cout][Cin]; 3x3x3 cross-correlation.
+void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
+                   cudaStream_t s);
+// pad (+ optional pixel-norm * (1+scale) + shift -> SiLU, or per-channel affine) from fp32 [T,H,W,C] into bf16 [T+2,H+2,W+2,C]
+// mode 0: copy ; 1: x*a[c]+b[c] (denormalise) ; 2: silu(pn(x)*(1+a[c])+b[c])
+void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
+                     int causal, cudaStream_t s);
+
+}  // namespace ltx

@@ -1,0 +1,70 @@
+// Host-side TMA descriptor construction.  cuTensorMapEncodeTiled is fetched through the runtime's driver entry
+// point lookup so that libltxcuda.so has no link-time dependency on libcuda.so (it must build on a GPU-less box).
+#include <mutex>
+
+#include "ltx_internal.h"
+
+namespace ltx {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  LTX_CHECK(fn != nullptr, 3, "cuTensorMapEncodeTiled not available (no CUDA driver / no sm_100a device)");
+  return fn;
+}
+
+CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                         uint32_t box_cols) {
+  LTX_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, 2, "TMA base must be 16-byte aligned");
+  LTX_CHECK((ld * 2) % 16 == 0, 2, "TMA row pitch must be a multiple of 16 bytes");
+  LTX_CHECK(box_rows <= 256 && box_cols * 2 == 128, 2, "TMA box: <=256 rows, 128-byte inner extent");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTX_CHECK(r == CUDA_SUCCESS, 3, "cuTensorMapEncodeTiled(2d) failed: " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+CUtensorMap make_tmap_thwc(const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C, uint32_t bt, uint32_t bh,
+                           uint32_t bw) {
+  LTX_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, 2, "TMA base must be 16-byte aligned");
+  LTX_CHECK(C % 8 == 0, 2, "channels must be a multiple of 8");
+  LTX_CHECK(bt * bh * bw <= 256 && bw <= 256 && bh <= 256, 2, "TMA conv box too large");
+  CUtensorMap m;
+  cuuint64_t dims[4] = {C, W, H, T};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, bw, bh, bt};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTX_CHECK(r == CUDA_SUCCESS, 3, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    LTX_CUDA(cudaGetDevice(&dev));
+    LTX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+}  // namespace ltx

@@ -1,0 +1,162 @@
+// Video-VAE decoder on one B200.  Restates VideoDecoder.callAsFunction (Models/VAE/VideoDecoder.swift:358-449) and
+// decodeVideo's untiled path (:466-508) on top of the implicit-GEMM conv kernel (conv3d.cu).
+//
+// HBM layout: every activation is channels-last fp32 [T, H, W, C] (the residual stream stays fp32); each conv reads a
+// bf16 padded copy produced by the fused pixel-norm/scale-shift/SiLU prologue and writes fp32 through its epilogue
+// (+bias, +residual, depth-to-space scatter, or unpatchify+clip straight into the [F, H, W, 3] frame buffer).
+#include "ctx.h"
+
+namespace ltx {
+
+namespace {
+
+__global__ void permute_conv_weight_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int O, int I) {
+  // in [O][I][27] -> out [27][O][I]
+  const int64_t n = static_cast<int64_t>(O) * I * 27;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % I);
+    const int o = static_cast<int>((idx / I) % O);
+    const int tap = static_cast<int>(idx / (static_cast<int64_t>(I) * O));
+    out[idx] = in[(static_cast<int64_t>(o) * I + i) * 27 + tap];
+  }
+}
+
+__global__ void noise_mix_kernel(float* __restrict__ x, const float* __restrict__ nz, int64_t n, float scale) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    x[i] = nz[i] * scale + (1.0f - scale) * x[i];
+}
+
+ConvW pack_conv(ltx_ctx* c, const std::string& name, int64_t cout, int64_t cin) {
+  const DevTensor& w = get_tensor(c, name + ".conv.weight");
+  LTX_CHECK(w.dtype == LTX_BF16 && w.shape.size() == 5 && w.shape[0] == cout && w.shape[1] == cin && w.shape[2] == 3 &&
+                w.shape[3] == 3 && w.shape[4] == 3,
+            LTX_ERR_WEIGHTS, "bad shape for '" + name + ".conv.weight'");
+  const DevTensor& b = get_tensor(c, name + ".conv.bias");
+  LTX_CHECK(b.dtype == LTX_F32 && b.numel() == cout, LTX_ERR_WEIGHTS, "bad shape for '" + name + ".conv.bias'");
+  bf16* packed = nullptr;
+  const int64_t n = cout * cin * 27;
+  LTX_CUDA(cudaMalloc(&packed, static_cast<size_t>(n) * 2));
+  c->owned.push_back(packed);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  permute_conv_weight_kernel<<<static_cast<int>(blocks), 256, 0, c->stream>>>(reinterpret_cast<const bf16*>(w.ptr), packed,
+                                                                             static_cast<int>(cout), static_cast<int>(cin));
+  LTX_CUDA(cudaGetLastError());
+  LTX_CUDA(cudaStreamSynchronize(c->stream));
+  auto it = c->tensors.find(name + ".conv.weight");
+  cudaFree(it->second.ptr);
+  c->tensors.erase(it);
+  ConvW r;
+  r.w = packed; r.b = reinterpret_cast<const float*>(b.ptr); r.cin = static_cast<int>(cin); r.cout = static_cast<int>(cout);
+  return r;
+}
+
+const float* vf(ltx_ctx* c, const std::string& k, int64_t n) {
+  const DevTensor& t = get_tensor(c, k);
+  LTX_CHECK(t.dtype == LTX_F32 && t.numel() == n, LTX_ERR_WEIGHTS, "bad shape for '" + k + "'");
+  return reinterpret_cast<const float*>(t.ptr);
+}
+
+void conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
+          int causal, int epi_mode, float* out, const float* resid) {
+  c->v_pad.reserve(static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * w.cin * 2);
+  launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, causal, c->stream);
+  ConvEpi e;
+  e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin;
+  launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream);
+  c->launches += 2;
+}
+
+}  // namespace
+
+void vae_finalize(ltx_ctx* c) {
+  const ltx_config& g = c->cfg;
+  LTX_CHECK(g.vae_base_channels % 512 == 0 || g.vae_base_channels % 64 == 0, LTX_ERR_INVALID_CONFIGURATION, "vae channels");
+  LTX_CHECK((g.vae_base_channels / 8) % 64 == 0, LTX_ERR_INVALID_CONFIGURATION,
+            "vae_base_channels / 8 must be a multiple of 64");
+  LTX_CHECK(g.vae_latent_channels % 64 == 0, LTX_ERR_INVALID_CONFIGURATION, "vae_latent_channels must be a multiple of 64");
+  VaeWeights& v = c->vae;
+  const int64_t C = g.vae_latent_channels;
+  v.mean = vf(c, "vae.mean_of_means", C);
+  v.std = vf(c, "vae.std_of_means", C);
+  int64_t ch = g.vae_base_channels;
+  v.conv_in = pack_conv(c, "vae.conv_in", ch, C);
+  v.stages.clear();
+  v.ups.clear();
+  for (int st = 0; st < 4; ++st) {
+    const std::string blk = "vae.up_blocks_" + std::to_string(2 * st);
+    std::vector<VaeResBlock> rbs;
+    for (int j = 0; j < g.vae_blocks_per_stage; ++j) {
+      const std::string rb = blk + ".res_blocks." + std::to_string(j);
+      VaeResBlock r;
+      r.c1 = pack_conv(c, rb + ".conv1", ch, ch);
+      r.c2 = pack_conv(c, rb + ".conv2", ch, ch);
+      r.sst = vf(c, rb + ".scale_shift_table", 4 * ch);
+      rbs.push_back(r);
+    }
+    v.stages.push_back(rbs);
+    if (st < 3) {
+      v.ups.push_back(pack_conv(c, "vae.up_blocks_" + std::to_string(2 * st + 1) + ".conv", 4 * ch, ch));
+      ch /= 2;
+    }
+  }
+  v.last_sst = vf(c, "vae.last_scale_shift_table", 2 * ch);
+  v.conv_out = pack_conv(c, "vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
+  LTX_CHECK(g.vae_patch_size == 4, LTX_ERR_INVALID_CONFIGURATION, "vae_patch_size must be 4");
+  v.ready = true;
+}
+
+void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
+                    int causal, float* frames_dev) {
+  VaeWeights& v = c->vae;
+  LTX_CHECK(v.ready, LTX_ERR_WEIGHTS, "VAE weights not finalized");
+  LTX_CHECK(latent_dev && frames_dev && Fp > 0 && Hp > 1 && Wp > 1, LTX_ERR_INVALID_ARGUMENT, "bad vae_decode arguments");
+  LTX_CHECK(timestep < 0.f, LTX_ERR_UNSUPPORTED,
+            "timestep-conditioned VAE decode is not implemented (pipeline default is timestep = nil)");
+  (void)noise_dev;
+  const ltx_config& g = c->cfg;
+  cudaStream_t st = c->stream;
+  const int C0 = g.vae_latent_channels;
+  int T = Fp, H = Hp, W = Wp;
+  // worst-case activation sizes over the stages: x at stage s has ch_s channels on a (T_s, H_s, W_s) grid
+  size_t max_x = 0;
+  {
+    int t = Fp, h = Hp, w = Wp;
+    int64_t ch = g.vae_base_channels;
+    for (int s = 0; s < 4; ++s) {
+      max_x = std::max(max_x, static_cast<size_t>(t) * h * w * ch);
+      if (s < 3) { t = 2 * t - 1; h *= 2; w *= 2; ch /= 2; }
+    }
+    max_x = std::max(max_x, static_cast<size_t>(Fp) * Hp * Wp * C0);
+  }
+  c->v_a.reserve(max_x * 4);
+  c->v_b.reserve(max_x * 4);
+  c->v_h.reserve(max_x * 4);
+  float* x = c->v_a.as<float>();
+  float* y = c->v_b.as<float>();
+  float* hbuf = c->v_h.as<float>();
+  // [C, T*H*W] -> channels-last [T*H*W, C]
+  launch_patchify(latent_dev, nullptr, hbuf, C0, T * H * W, st);
+  c->launches++;
+  // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
+  conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr);
+  int64_t ch = g.vae_base_channels;
+  for (int s = 0; s < 4; ++s) {
+    for (const VaeResBlock& rb : v.stages[s]) {
+      // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
+      conv(c, x, 2, rb.sst + ch, rb.sst, rb.c1, T, H, W, causal, 0, hbuf, nullptr);
+      conv(c, hbuf, 2, rb.sst + 3 * ch, rb.sst + 2 * ch, rb.c2, T, H, W, causal, 0, x, x);
+    }
+    if (s < 3) {
+      conv(c, x, 0, nullptr, nullptr, v.ups[s], T, H, W, causal, 1, y, x);  // conv -> d2s -> drop frame 0 -> + tiled d2s(x)
+      std::swap(x, y);
+      T = 2 * T - 1; H *= 2; W *= 2; ch /= 2;
+    }
+  }
+  // pn * (1 + scale) + shift -> SiLU -> conv_out -> unpatchify -> (x+1)/2 clip -> [F, H, W, 3]   (:419-444, 501-505)
+  conv(c, x, 2, v.last_sst + ch, v.last_sst, v.conv_out, T, H, W, causal, 2, frames_dev, nullptr);
+}
+
+}  // namespace ltx

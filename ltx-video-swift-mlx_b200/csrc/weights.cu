@@ -1,0 +1,173 @@
+// Weight ingestion for libltxcuda: host tensors under the reference's post-mapping key names
+// (Utils/ModelDownloader.swift:756-899) are copied to the device as bf16 (matrices / conv kernels, mirroring the
+// loader's fp32->bf16 cast at :1005-1012) or fp32 (biases, norm weights, scale-shift tables).
+#include <cuda_fp16.h>
+
+#include "ctx.h"
+
+namespace ltx {
+
+namespace {
+
+template <typename S>
+__device__ __forceinline__ float to_f32(S v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ in, D* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = to_f32<S>(in[i]);
+    if (sizeof(D) == 2)
+      reinterpret_cast<bf16*>(out)[i] = __float2bfloat16(v);
+    else
+      reinterpret_cast<float*>(out)[i] = v;
+  }
+}
+
+template <typename S>
+void convert_to(const void* src, void* dst, int dst_dtype, int64_t n, cudaStream_t s) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  if (dst_dtype == LTX_BF16)
+    convert_kernel<S, bf16><<<static_cast<int>(blocks), 256, 0, s>>>(reinterpret_cast<const S*>(src),
+                                                                     reinterpret_cast<bf16*>(dst), n);
+  else
+    convert_kernel<S, float><<<static_cast<int>(blocks), 256, 0, s>>>(reinterpret_cast<const S*>(src),
+                                                                      reinterpret_cast<float*>(dst), n);
+  LTX_CUDA(cudaGetLastError());
+}
+
+size_t dtype_size(int dt) { return dt == LTX_F32 ? 4 : 2; }
+
+bool ends_with(const std::string& s, const std::string& suf) {
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+int storage_dtype(const std::string& key, int ndim) {
+  return (ends_with(key, ".weight") && ndim >= 2) ? LTX_BF16 : LTX_F32;
+}
+
+DevTensor& alloc_tensor(ltx_ctx* c, const std::string& key, const std::vector<int64_t>& shape) {
+  auto it = c->tensors.find(key);
+  if (it != c->tensors.end()) {
+    if (it->second.ptr) cudaFree(it->second.ptr);
+    c->tensors.erase(it);
+  }
+  DevTensor t;
+  t.shape = shape;
+  t.dtype = storage_dtype(key, static_cast<int>(shape.size()));
+  size_t bytes = static_cast<size_t>(t.numel()) * dtype_size(t.dtype);
+  LTX_CUDA(cudaMalloc(&t.ptr, bytes < 16 ? 16 : bytes));
+  return c->tensors[key] = t;
+}
+
+void fill(ltx_ctx* c, const std::string& key, const std::vector<int64_t>& shape, float stdv, float mean, uint64_t& seed) {
+  DevTensor& t = alloc_tensor(c, key, shape);
+  seed += 0x632BE59BD9B4E019ull;
+  if (t.dtype == LTX_BF16)
+    launch_fill_normal_bf16(reinterpret_cast<bf16*>(t.ptr), t.numel(), stdv, mean, seed, c->stream);
+  else
+    launch_fill_normal_f32(reinterpret_cast<float*>(t.ptr), t.numel(), stdv, mean, seed, c->stream);
+}
+
+}  // namespace
+
+const DevTensor& get_tensor(ltx_ctx* c, const std::string& key) {
+  auto it = c->tensors.find(key);
+  LTX_CHECK(it != c->tensors.end(), LTX_ERR_WEIGHTS, "missing weight tensor '" + key + "'");
+  return it->second;
+}
+
+void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int dtype, const int64_t* shape, int ndim) {
+  LTX_CHECK(host != nullptr && ndim >= 0 && ndim <= 8, LTX_ERR_INVALID_ARGUMENT, "load_tensor: bad arguments");
+  LTX_CHECK(dtype == LTX_F32 || dtype == LTX_BF16 || dtype == LTX_F16, LTX_ERR_INVALID_ARGUMENT, "load_tensor: bad dtype");
+  std::vector<int64_t> shp(shape, shape + ndim);
+  DevTensor& t = alloc_tensor(c, key, shp);
+  const int64_t n = t.numel();
+  if (n == 0) return;
+  const size_t src_bytes = static_cast<size_t>(n) * dtype_size(dtype);
+  if (dtype == t.dtype) {
+    LTX_CUDA(cudaMemcpyAsync(t.ptr, host, src_bytes, cudaMemcpyHostToDevice, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+    return;
+  }
+  void* stage = nullptr;
+  LTX_CUDA(cudaMalloc(&stage, src_bytes));
+  LTX_CUDA(cudaMemcpyAsync(stage, host, src_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (dtype == LTX_F32)
+    convert_to<float>(stage, t.ptr, t.dtype, n, c->stream);
+  else if (dtype == LTX_BF16)
+    convert_to<bf16>(stage, t.ptr, t.dtype, n, c->stream);
+  else
+    convert_to<__half>(stage, t.ptr, t.dtype, n, c->stream);
+  LTX_CUDA(cudaStreamSynchronize(c->stream));
+  LTX_CUDA(cudaFree(stage));
+}
+
+// Random-init weights of the named architecture (SURVEY Appendix C shapes).  Scales keep activations O(1):
+// Linear N(0, 1/in), biases N(0, 0.02^2), scale-shift tables N(0, 0.1^2), q/k norm weights 1 + N(0, 0.1^2).
+void init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
+  const ltx_config& g = c->cfg;
+  const int64_t D = static_cast<int64_t>(g.num_heads) * g.head_dim;
+  uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345;
+  auto lin = [&](const std::string& name, int64_t out_f, int64_t in_f, float wscale = 1.0f) {
+    fill(c, name + ".weight", {out_f, in_f}, wscale / sqrtf(static_cast<float>(in_f)), 0.f, s);
+    fill(c, name + ".bias", {out_f}, 0.02f, 0.f, s);
+  };
+  if (which & 1) {
+    lin("patchify_proj", D, g.in_channels);
+    lin("adaln_single.emb.linear_1", D, 256);
+    lin("adaln_single.emb.linear_2", D, D);
+    lin("adaln_single.linear", 6 * D, D, 0.5f);
+    lin("caption_projection.linear_1", D, g.caption_channels);
+    lin("caption_projection.linear_2", D, D);
+    for (int i = 0; i < g.num_layers; ++i) {
+      const std::string p = "transformer_blocks." + std::to_string(i) + ".";
+      fill(c, p + "scale_shift_table", {6, D}, 0.1f, 0.f, s);
+      for (const char* a : {"attn1", "attn2"}) {
+        for (const char* l : {"to_q", "to_k", "to_v", "to_out"}) lin(p + a + "." + l, D, D);
+        fill(c, p + a + ".q_norm.weight", {D}, 0.1f, 1.0f, s);
+        fill(c, p + a + ".k_norm.weight", {D}, 0.1f, 1.0f, s);
+      }
+      lin(p + "ff.project_in.proj", g.ffn_mult * D, D);
+      lin(p + "ff.project_out", D, g.ffn_mult * D);
+    }
+    fill(c, "scale_shift_table", {2, D}, 0.1f, 0.f, s);
+    lin("proj_out", g.out_channels, D);
+  }
+  if (which & 2) {
+    auto conv = [&](const std::string& name, int64_t cout, int64_t cin) {
+      fill(c, name + ".conv.weight", {cout, cin, 3, 3, 3}, 1.0f / sqrtf(27.0f * cin), 0.f, s);
+      fill(c, name + ".conv.bias", {cout}, 0.02f, 0.f, s);
+    };
+    const int64_t C = g.vae_latent_channels;
+    fill(c, "vae.mean_of_means", {C}, 0.1f, 0.f, s);
+    fill(c, "vae.std_of_means", {C}, 0.05f, 1.0f, s);
+    int64_t ch = g.vae_base_channels;
+    conv("vae.conv_in", ch, C);
+    for (int st = 0; st < 4; ++st) {
+      const std::string blk = "vae.up_blocks_" + std::to_string(2 * st);
+      for (int j = 0; j < g.vae_blocks_per_stage; ++j) {
+        const std::string rb = blk + ".res_blocks." + std::to_string(j);
+        conv(rb + ".conv1", ch, ch);
+        conv(rb + ".conv2", ch, ch);
+        fill(c, rb + ".scale_shift_table", {4, ch}, 0.1f, 0.f, s);
+      }
+      if (st < 3) {
+        conv("vae.up_blocks_" + std::to_string(2 * st + 1) + ".conv", 4 * ch, ch);
+        ch /= 2;
+      }
+    }
+    fill(c, "vae.last_scale_shift_table", {2, ch}, 0.1f, 0.f, s);
+    conv("vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
+  }
+  LTX_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+}  // namespace ltx

@@ -1,0 +1,610 @@
+"""CPU oracle for the LTX-2 denoise hot path (DiT step, guidance+Euler, video-VAE decode).
+
+TEST INFRASTRUCTURE ONLY.  This file is a CPU restatement (PyTorch, fp32 with an fp64 switch) of the
+reference's algorithm, written from the Swift sources under /root/reference (read-only, not present on
+the GPU box).  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs
+of `bench.py` may import it -- as the checker or the timed CPU baseline, never as the product path.
+
+PARITY UNPINNED: the reference (Swift + MLX 0.30.6) cannot be built or imported here (no swift, no mlx)
+and ships no golden vectors for this path (its only test is `testVersion`).  The arithmetic lives in the
+un-vendored third-party package `mlx-swift` (Package.swift:21, exact 0.30.6); the semantics assumed for
+its primitives are the published ones:
+  rmsNorm(x,w,eps) = x * rsqrt(mean(x^2)+eps) * w       (fp32 accumulation)
+  scaledDotProductAttention = softmax_fp32(q k^T * scale + mask) v
+  Linear = x W^T + b (W [out,in]);  LayerNorm(affine:false) uses the population variance
+  geluApproximate = 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)));  variance = population (ddof 0)
+  type promotion bf16 (x) f32 -> f32.
+The only in-source known-answer data are the sigma tables (S/LTXScheduler.swift:18-36) and the shape
+formulae; those are checked in tests/test_oracle.py.
+
+File:line citations are relative to /root/reference/Sources/LTXVideo/ (T/ = Models/Transformer,
+V/ = Models/VAE, P/ = Pipeline, S/ = Scheduler, C/ = Configuration).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------
+# configuration (C/LTXConfig.swift:122-139)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class DiTConfig:
+    num_layers: int = 48
+    num_heads: int = 32
+    head_dim: int = 128
+    in_channels: int = 128
+    out_channels: int = 128
+    caption_channels: int = 3840
+    ffn_mult: int = 4                      # T/LTXFeedForward.swift:39
+    rope_theta: float = 10000.0
+    max_pos: Tuple[int, int, int] = (20, 2048, 2048)
+    timestep_scale_multiplier: float = 1000.0
+    norm_eps: float = 1e-6
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_heads * self.head_dim
+
+
+@dataclass
+class VAEConfig:
+    latent_channels: int = 128
+    # channel plan V/VideoDecoder.swift:331-355 : res @c0, d2s, res @c0/2, d2s, res @c0/4, d2s, res @c0/8
+    base_channels: int = 1024
+    blocks_per_stage: int = 5
+    patch_size: int = 4
+    causal: bool = False                   # VideoDecoder() default, V/VideoDecoder.swift:320
+    timestep_conditioning: bool = False
+
+    @property
+    def stage_channels(self) -> List[int]:
+        c = self.base_channels
+        return [c, c // 2, c // 4, c // 8]
+
+
+def bf16_round(x: Tensor) -> Tensor:
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# seeded random-init weights under the reference's post-mapping key names (SURVEY Appendix C,
+# U/ModelDownloader.swift:756-899).  Values are bf16-representable when bf16=True, mirroring the loader's
+# fp32->bf16 cast (U/ModelDownloader.swift:1005-1012).
+# ----------------------------------------------------------------------------------------------
+def make_dit_weights(cfg: DiTConfig, seed: int = 0, bf16: bool = True) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    D = cfg.inner_dim
+    w: Dict[str, Tensor] = {}
+
+    def lin(name: str, out_f: int, in_f: int, wstd: Optional[float] = None):
+        std = wstd if wstd is not None else 1.0 / math.sqrt(in_f)
+        w[name + ".weight"] = torch.randn(out_f, in_f, generator=g) * std
+        w[name + ".bias"] = torch.randn(out_f, generator=g) * 0.02
+
+    lin("patchify_proj", D, cfg.in_channels)
+    lin("adaln_single.emb.linear_1", D, 256)
+    lin("adaln_single.emb.linear_2", D, D)
+    lin("adaln_single.linear", 6 * D, D, wstd=0.5 / math.sqrt(D))
+    lin("caption_projection.linear_1", D, cfg.caption_channels)
+    lin("caption_projection.linear_2", D, D)
+    for i in range(cfg.num_layers):
+        p = f"transformer_blocks.{i}."
+        w[p + "scale_shift_table"] = torch.randn(6, D, generator=g) * 0.1
+        for a in ("attn1", "attn2"):
+            for l in ("to_q", "to_k", "to_v", "to_out"):
+                lin(p + f"{a}.{l}", D, D)
+            w[p + f"{a}.q_norm.weight"] = 1.0 + 0.1 * torch.randn(D, generator=g)
+            w[p + f"{a}.k_norm.weight"] = 1.0 + 0.1 * torch.randn(D, generator=g)
+        lin(p + "ff.project_in.proj", cfg.ffn_mult * D, D)
+        lin(p + "ff.project_out", D, cfg.ffn_mult * D)
+    w["scale_shift_table"] = torch.randn(2, D, generator=g) * 0.1
+    lin("proj_out", cfg.out_channels, D)
+    if bf16:
+        w = {k: bf16_round(v) for k, v in w.items()}
+    return w
+
+
+def make_vae_weights(cfg: VAEConfig, seed: int = 0) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, Tensor] = {}
+
+    def conv(name: str, cout: int, cin: int):
+        w[name + ".conv.weight"] = torch.randn(cout, cin, 3, 3, 3, generator=g) / math.sqrt(27 * cin)
+        w[name + ".conv.bias"] = torch.randn(cout, generator=g) * 0.02
+
+    def lin(name: str, out_f: int, in_f: int):
+        w[name + ".weight"] = torch.randn(out_f, in_f, generator=g) / math.sqrt(in_f)
+        w[name + ".bias"] = torch.randn(out_f, generator=g) * 0.02
+
+    C = cfg.latent_channels
+    w["mean_of_means"] = torch.randn(C, generator=g) * 0.1
+    w["std_of_means"] = 1.0 + 0.1 * torch.rand(C, generator=g)
+    w["timestep_scale_multiplier"] = torch.tensor(1000.0)
+    chans = cfg.stage_channels
+    conv("conv_in", chans[0], C)
+    for s, c in enumerate(chans):
+        blk = f"up_blocks_{2 * s}"
+        for j in range(cfg.blocks_per_stage):
+            conv(f"{blk}.res_blocks.{j}.conv1", c, c)
+            conv(f"{blk}.res_blocks.{j}.conv2", c, c)
+            w[f"{blk}.res_blocks.{j}.scale_shift_table"] = torch.randn(4, c, generator=g) * 0.1
+        lin(f"{blk}.time_embedder.timestep_embedder.linear_1", 256, 256)
+        lin(f"{blk}.time_embedder.timestep_embedder.linear_2", 4 * c, 256)
+        if s < len(chans) - 1:
+            conv(f"up_blocks_{2 * s + 1}.conv", 4 * c, c)
+    w["last_scale_shift_table"] = torch.randn(2, chans[-1], generator=g) * 0.1
+    lin("last_time_embedder.timestep_embedder.linear_1", 256, 256)
+    lin("last_time_embedder.timestep_embedder.linear_2", 2 * chans[-1], 256)
+    conv("conv_out", 3 * cfg.patch_size * cfg.patch_size, chans[-1])
+    return w
+
+
+# ----------------------------------------------------------------------------------------------
+# primitives (assumed MLX semantics, see header)
+# ----------------------------------------------------------------------------------------------
+def linear(x: Tensor, w: Dict[str, Tensor], name: str) -> Tensor:
+    return x @ w[name + ".weight"].to(x.dtype).t() + w[name + ".bias"].to(x.dtype)
+
+
+def rms_norm(x: Tensor, weight: Optional[Tensor], eps: float) -> Tensor:
+    y = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return y if weight is None else y * weight.to(x.dtype)
+
+
+def gelu_tanh(x: Tensor) -> Tensor:                     # T/LTXFeedForward.swift:10-13
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x.pow(3))))
+
+
+def silu(x: Tensor) -> Tensor:
+    return x * torch.sigmoid(x)
+
+
+def sinusoidal_embedding(t: Tensor, dim: int = 256) -> Tensor:
+    """T/LTXTimestepEmbedding.swift:17-54: [cos(t f_k), sin(t f_k)], f_k = exp(-ln(1e4) k/half); fp32."""
+    half = dim // 2
+    k = torch.arange(half, dtype=torch.float32) / float(half)
+    freqs = torch.exp(-math.log(10000.0) * k)
+    args = t.reshape(-1, 1).to(torch.float32) * freqs.reshape(1, -1)
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# RoPE (T/LTXRoPE.swift)
+# ----------------------------------------------------------------------------------------------
+def position_grid(F: int, H: int, W: int, t_scale: int = 8, s_scale: int = 32, fps: float = 24.0) -> Tensor:
+    """T/LTXRoPE.swift:552-610: pixel-space mid-points, causal fix on t, t divided by fps. [3, F*H*W] fp32."""
+    f = torch.arange(F, dtype=torch.float32)
+    start = torch.clamp(f * t_scale + (1 - t_scale), min=0)
+    end = torch.clamp((f + 1) * t_scale + (1 - t_scale), min=0)
+    tc = ((start + end) / 2.0) / fps
+    hc = torch.arange(H, dtype=torch.float32) * s_scale + s_scale / 2.0
+    wc = torch.arange(W, dtype=torch.float32) * s_scale + s_scale / 2.0
+    tg = tc.view(F, 1, 1).expand(F, H, W).reshape(-1)
+    hg = hc.view(1, H, 1).expand(F, H, W).reshape(-1)
+    wg = wc.view(1, 1, W).expand(F, H, W).reshape(-1)
+    return torch.stack([tg, hg, wg], 0)
+
+
+def rope_table(cfg: DiTConfig, F: int, H: int, W: int) -> Tuple[Tensor, Tensor]:
+    """T/LTXRoPE.swift:375-488 (doublePrecision path, split type): returns cos, sin [heads, N, head_dim/2] fp32."""
+    D = cfg.inner_dim
+    grid = position_grid(F, H, W).to(torch.float64)           # (3, N), fp32 values widened (:388-417)
+    n_dims = 3
+    num_idx = max(1, D // (2 * n_dims))                        # :396
+    i = torch.arange(num_idx, dtype=torch.float64)
+    t = i / (num_idx - 1) if num_idx > 1 else torch.zeros(1, dtype=torch.float64)
+    idx = torch.pow(torch.tensor(cfg.rope_theta, dtype=torch.float64), t) * (math.pi / 2.0)   # :398-404
+    max_pos = torch.tensor(cfg.max_pos, dtype=torch.float64).view(3, 1)
+    scaled = (grid / max_pos) * 2.0 - 1.0                      # (3, N)  :419-427
+    # freqs[n, fi*3 + d] = idx[fi] * scaled[d, n]               :432-441
+    freqs = (idx.view(1, num_idx, 1) * scaled.t().reshape(-1, 1, n_dims)).reshape(-1, num_idx * n_dims)
+    cos, sin = torch.cos(freqs), torch.sin(freqs)
+    pad = max(0, D // 2 - num_idx * n_dims)                    # :451-476 left pad with identity
+    N = freqs.shape[0]
+    cos = torch.cat([torch.ones(N, pad, dtype=torch.float64), cos], 1).to(torch.float32)
+    sin = torch.cat([torch.zeros(N, pad, dtype=torch.float64), sin], 1).to(torch.float32)
+    hd2 = (D // 2) // cfg.num_heads
+    cos = cos.view(N, cfg.num_heads, hd2).permute(1, 0, 2).contiguous()   # :484-488
+    sin = sin.view(N, cfg.num_heads, hd2).permute(1, 0, 2).contiguous()
+    return cos, sin
+
+
+def apply_split_rope(x: Tensor, cos: Tensor, sin: Tensor, heads: int) -> Tensor:
+    """T/LTXRoPE.swift:84-149: x [B,N,D] viewed [B,H,N,d]; halves (x1|x2); y1=x1 c - x2 s, y2 = x2 c + x1 s."""
+    B, N, D = x.shape
+    d = D // heads
+    xh = x.view(B, N, heads, d).permute(0, 2, 1, 3)
+    x1, x2 = xh[..., : d // 2], xh[..., d // 2:]
+    c, s = cos.to(x.dtype).unsqueeze(0), sin.to(x.dtype).unsqueeze(0)
+    y = torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1)
+    return y.permute(0, 2, 1, 3).reshape(B, N, D)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention (T/LTXAttention.swift:160-218)
+# ----------------------------------------------------------------------------------------------
+def sdpa(q: Tensor, k: Tensor, v: Tensor, heads: int, bias: Optional[Tensor]) -> Tensor:
+    B, Nq, D = q.shape
+    Nk = k.shape[1]
+    d = D // heads
+    qh = q.view(B, Nq, heads, d).permute(0, 2, 1, 3)
+    kh = k.view(B, Nk, heads, d).permute(0, 2, 1, 3)
+    vh = v.view(B, Nk, heads, d).permute(0, 2, 1, 3)
+    s = (qh @ kh.transpose(-1, -2)) * (1.0 / math.sqrt(d))       # :208
+    if bias is not None:
+        s = s + bias.to(s.dtype)
+    p = torch.softmax(s, dim=-1)
+    o = p @ vh
+    return o.permute(0, 2, 1, 3).reshape(B, Nq, D)
+
+
+def attention(w: Dict[str, Tensor], prefix: str, x: Tensor, ctx: Optional[Tensor], cfg: DiTConfig,
+              rope: Optional[Tuple[Tensor, Tensor]], bias: Optional[Tensor], bf16_kv: bool = False) -> Tensor:
+    c = x if ctx is None else ctx
+    q = linear(x, w, prefix + ".to_q")
+    k = linear(c, w, prefix + ".to_k")
+    v = linear(c, w, prefix + ".to_v")
+    if bf16_kv:                                  # text branch stays bf16 in the reference
+        k, v = bf16_round(k), bf16_round(v)
+    q = rms_norm(q, w[prefix + ".q_norm.weight"], cfg.norm_eps)          # :179-180, across all heads
+    k = rms_norm(k, w[prefix + ".k_norm.weight"], cfg.norm_eps)
+    if bf16_kv:
+        k = bf16_round(k)
+    if rope is not None:                                                  # :185-189
+        q = apply_split_rope(q, rope[0], rope[1], cfg.num_heads)
+        k = apply_split_rope(k, rope[0], rope[1], cfg.num_heads)
+    o = sdpa(q, k, v, cfg.num_heads, bias)
+    return linear(o, w, prefix + ".to_out")
+
+
+# ----------------------------------------------------------------------------------------------
+# transformer block (T/LTXTransformerBlock.swift:187-232) and full forward (T/LTXTransformer.swift:235-486)
+# ----------------------------------------------------------------------------------------------
+def block_forward(w: Dict[str, Tensor], i: int, x: Tensor, ada: Tensor, ctx: Tensor, bias: Optional[Tensor],
+                  rope: Tuple[Tensor, Tensor], cfg: DiTConfig, skip_self_attn: bool = False,
+                  skip_ff: bool = False, cross_attn_scale: float = 1.0, bf16_kv: bool = False) -> Tensor:
+    """x [B,N,D]; ada [B,1|N,6,D]; ctx [B,S,D] (already caption-projected)."""
+    p = f"transformer_blocks.{i}"
+    m = w[p + ".scale_shift_table"].to(x.dtype).view(1, 1, 6, -1) + ada         # :163-185
+    shift_msa, scale_msa, gate_msa = m[:, :, 0], m[:, :, 1], m[:, :, 2]
+    shift_mlp, scale_mlp, gate_mlp = m[:, :, 3], m[:, :, 4], m[:, :, 5]
+    if not skip_self_attn:                                                        # :199
+        h = rms_norm(x, None, cfg.norm_eps) * (1 + scale_msa) + shift_msa        # :72-83
+        x = x + attention(w, p + ".attn1", h, None, cfg, rope, None) * gate_msa   # :202
+    ca = attention(w, p + ".attn2", x, ctx, cfg, None, bias, bf16_kv=bf16_kv)     # :205-210, x NOT normalised
+    if cross_attn_scale != 1.0:
+        ca = ca * cross_attn_scale
+    x = x + ca
+    if not skip_ff:
+        h = rms_norm(x, None, cfg.norm_eps) * (1 + scale_mlp) + shift_mlp
+        ff = linear(gelu_tanh(linear(h, w, p + ".ff.project_in.proj")), w, p + ".ff.project_out")
+        x = x + ff * gate_mlp                                                     # :225-229
+    return x
+
+
+def timestep_path(w: Dict[str, Tensor], sigma: Tensor, cfg: DiTConfig, dtype: torch.dtype) -> Tuple[Tensor, Tensor]:
+    """T/LTXTransformer.swift:105-121 + T/LTXTimestepEmbedding.swift:62-124. sigma [B] or [B,N].
+    Returns ada [B,1|N,6,D], emb [B,1|N,D]."""
+    B = sigma.shape[0]
+    t = sigma.to(torch.float32) * cfg.timestep_scale_multiplier
+    se = sinusoidal_embedding(t.reshape(-1)).to(dtype)
+    emb = linear(silu(linear(se, w, "adaln_single.emb.linear_1")), w, "adaln_single.emb.linear_2")
+    ada = linear(silu(emb), w, "adaln_single.linear")
+    D = cfg.inner_dim
+    return ada.view(B, -1, 6, D), emb.view(B, -1, D)
+
+
+def caption_projection(w: Dict[str, Tensor], context: Tensor, mlx_bf16: bool) -> Tensor:
+    """T/LTXTimestepEmbedding.swift:146-151."""
+    h = linear(context, w, "caption_projection.linear_1")
+    if mlx_bf16:
+        h = bf16_round(h)
+    h = gelu_tanh(h)
+    if mlx_bf16:
+        h = bf16_round(h)
+    h = linear(h, w, "caption_projection.linear_2")
+    if mlx_bf16:
+        h = bf16_round(h)
+    return h
+
+
+def dit_forward(w: Dict[str, Tensor], cfg: DiTConfig, latent: Tensor, context: Tensor, sigma: Tensor,
+                mask: Optional[Tensor], fhw: Tuple[int, int, int], stg_blocks: Sequence[int] = (),
+                skip_self_attn: bool = False, skip_ff: bool = False,
+                cross_attn_scale: Optional[Dict[int, float]] = None,
+                dtype: torch.dtype = torch.float32, mlx_bf16: bool = True,
+                return_blocks: bool = False):
+    """Velocity prediction.  latent [B,N,C_in], context [B,S,C_cap], sigma [B]|[B,N], mask [B,S] (1=attend).
+    mlx_bf16=True mimics the reference's bf16 mode: bf16-rounded inputs, bf16 patchify/caption/text-KV branch,
+    fp32 everywhere else.  mlx_bf16=False is the all-fp32 (or fp64) mode."""
+    F, H, W = fhw
+    latent = latent.to(dtype)
+    context = context.to(dtype)
+    if mlx_bf16:
+        latent, context = bf16_round(latent), bf16_round(context)     # P/LTXPipeline.swift:815
+    x = linear(latent, w, "patchify_proj")                            # T/LTXTransformer.swift:257
+    if mlx_bf16:
+        x = bf16_round(x)
+    ada, emb = timestep_path(w, sigma, cfg, dtype)                    # :274
+    c = caption_projection(w, context, mlx_bf16)                      # :303
+    bias = None
+    if mask is not None:                                              # :141-156
+        bias = ((1.0 - mask.to(dtype)) * -10000.0).view(mask.shape[0], 1, 1, mask.shape[-1])
+    rope = rope_table(cfg, F, H, W)                                   # :322
+    blocks_out = []
+    for i in range(cfg.num_layers):                                   # :446-465
+        in_stg = i in stg_blocks
+        x = block_forward(w, i, x, ada, c, bias, rope, cfg,
+                          skip_self_attn=skip_self_attn and in_stg, skip_ff=skip_ff and in_stg,
+                          cross_attn_scale=(cross_attn_scale or {}).get(i, 1.0), bf16_kv=mlx_bf16)
+        if return_blocks:
+            blocks_out.append(x.clone())
+    # processOutput :208-224 -- LayerNorm(no affine, eps 1e-6), rows: 0 = shift, 1 = scale
+    o = w["scale_shift_table"].to(dtype).view(1, 1, 2, -1) + emb.unsqueeze(2)
+    mu = x.mean(-1, keepdim=True)
+    var = (x - mu).pow(2).mean(-1, keepdim=True)
+    y = (x - mu) * torch.rsqrt(var + cfg.norm_eps)
+    y = y * (1 + o[:, :, 1]) + o[:, :, 0]
+    vel = linear(y, w, "proj_out")
+    if return_blocks:
+        return vel, blocks_out
+    return vel
+
+
+def single_block_forward(w: Dict[str, Tensor], cfg: DiTConfig, x: Tensor, ctx: Tensor, sigma: Tensor,
+                         fhw: Tuple[int, int, int], block: int = 0, dtype=torch.float32) -> Tensor:
+    """BASELINE config 1: one BasicTransformerBlock, fp32, context already inner_dim wide, mask all ones."""
+    ada, _ = timestep_path(w, sigma, cfg, dtype)
+    rope = rope_table(cfg, *fhw)
+    return block_forward(w, block, x.to(dtype), ada, ctx.to(dtype), None, rope, cfg)
+
+
+# ----------------------------------------------------------------------------------------------
+# latent utils, guidance, scheduler (P/LatentUtils.swift, S/LTXScheduler.swift, P/LTXPipeline.swift:800-956)
+# ----------------------------------------------------------------------------------------------
+def patchify(latent: Tensor) -> Tensor:                  # P/LatentUtils.swift:20-36  (B,C,F,H,W)->(B,N,C)
+    B, C, F, H, W = latent.shape
+    return latent.permute(0, 2, 3, 4, 1).reshape(B, F * H * W, C)
+
+
+def unpatchify(x: Tensor, fhw: Tuple[int, int, int]) -> Tensor:   # :38-54
+    B, N, C = x.shape
+    F, H, W = fhw
+    return x.view(B, F, H, W, C).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def latent_shape(frames: int, height: int, width: int) -> Tuple[int, int, int]:
+    """P/VideoLatentShape.swift:35-41."""
+    return (frames - 1) // 8 + 1, height // 32, width // 32
+
+
+DISTILLED_SIGMA_VALUES = [1.0, 0.99375, 0.9875, 0.98125, 0.975, 0.909375, 0.725, 0.421875, 0.0]   # S/LTXScheduler.swift:18-28
+STAGE_2_DISTILLED_SIGMA_VALUES = [0.909375, 0.725, 0.421875, 0.0]                                   # :31-36
+BASE_SHIFT_ANCHOR, MAX_SHIFT_ANCHOR = 1024, 4096
+
+
+def _f32(x: float) -> float:
+    return float(torch.tensor(x, dtype=torch.float32))
+
+
+def set_timesteps(num_steps: int, distilled: bool, token_count: Optional[int], max_shift: float = 2.05,
+                  base_shift: float = 0.95, stretch: bool = True, terminal: float = 0.1) -> List[float]:
+    """S/LTXScheduler.swift:74-182, evaluated in float32 like the Swift `Float` code."""
+    f32 = torch.float32
+    T = lambda v: torch.tensor(v, dtype=f32)
+    if distilled:
+        s = T([v for v in DISTILLED_SIGMA_VALUES if v > 0])
+        if token_count is not None:
+            tok = min(token_count, MAX_SHIFT_ANCHOR)
+            mm = (T(max_shift) - T(base_shift)) / (T(float(MAX_SHIFT_ANCHOR)) - T(float(BASE_SHIFT_ANCHOR)))
+            b = T(base_shift) - mm * T(float(BASE_SHIFT_ANCHOR))
+            mu = T(float(tok)) * mm + b
+            e = torch.exp(mu)
+            shifted = e / (e + (1.0 / s - 1.0))
+            s = torch.where((s == 0) | (s == 1.0), s, shifted)
+            if stretch:
+                om = 1.0 - s
+                last = om[-1]
+                if last > 0:
+                    scale = last / (1.0 - T(terminal))
+                    s = torch.where(s == 0, torch.zeros_like(s), 1.0 - (1.0 - s) / scale)
+        return [float(v) for v in s] + [0.0]
+    tok = min(token_count if token_count is not None else MAX_SHIFT_ANCHOR, MAX_SHIFT_ANCHOR)
+    s = 1.0 - torch.arange(num_steps + 1, dtype=f32) / float(num_steps)
+    mm = (T(max_shift) - T(base_shift)) / (T(float(MAX_SHIFT_ANCHOR)) - T(float(BASE_SHIFT_ANCHOR)))
+    b = T(base_shift) - mm * T(float(BASE_SHIFT_ANCHOR))
+    e = torch.exp(T(float(tok)) * mm + b)
+    safe = torch.where(s == 0, torch.ones_like(s), s)
+    s = torch.where(s == 0, torch.zeros_like(s), e / (e + (1.0 / safe - 1.0)))
+    if stretch and num_steps > 0:
+        om = 1.0 - s
+        scale = om[num_steps - 1] / (1.0 - T(terminal))
+        s = torch.where(s == 0, torch.zeros_like(s), 1.0 - om / scale)
+    return [float(v) for v in s]
+
+
+def apply_cfg(uncond: Tensor, cond: Tensor, scale: float) -> Tensor:      # P/LatentUtils.swift:131-141
+    return cond + (scale - 1.0) * (cond - uncond)
+
+
+def guidance_rescale(cfg_out: Tensor, cond: Tensor, phi: float) -> Tensor:   # :164-183
+    if phi <= 0:
+        return cfg_out
+    dims = list(range(1, cfg_out.ndim))
+    s_cfg = torch.sqrt(cfg_out.var(dim=dims, unbiased=False, keepdim=True) + 1e-8)
+    s_cond = torch.sqrt(cond.var(dim=dims, unbiased=False, keepdim=True) + 1e-8)
+    return phi * (cfg_out * (s_cond / s_cfg)) + (1.0 - phi) * cfg_out
+
+
+def euler_step(latent: Tensor, velocity: Tensor, sigma: float, sigma_next: float) -> Tensor:   # S/LTXScheduler.swift:305-327
+    den = latent - sigma * velocity
+    if sigma_next > 0:
+        return den + sigma_next * (latent - den) / sigma
+    return den
+
+
+def guided_euler_step(latent: Tensor, v_cond: Tensor, v_uncond: Optional[Tensor], v_stg: Optional[Tensor],
+                      v_prev: Optional[Tensor], cfg_scale: float, phi: float, stg_scale: float, ge_gamma: float,
+                      sigma: float, sigma_next: float) -> Tuple[Tensor, Tensor]:
+    """P/LTXPipeline.swift:861-935 in fp32.  Returns (new latent, velocity used) ; velocity feeds GE next step."""
+    v = v_cond.float()
+    if v_uncond is not None:
+        v = apply_cfg(v_uncond.float(), v_cond.float(), cfg_scale)
+        v = guidance_rescale(v, v_cond.float(), phi)
+    if v_stg is not None and stg_scale > 0:
+        v = v + stg_scale * (v - v_stg.float())                # :920
+    if ge_gamma > 0 and v_prev is not None:
+        v = ge_gamma * (v - v_prev) + v_prev                   # :924-927
+    return euler_step(latent.float(), v, sigma, sigma_next), v
+
+
+def denoise_loop(w, cfg: DiTConfig, noise: Tensor, context: Tensor, mask: Optional[Tensor], sigmas: Sequence[float],
+                 neg_context: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None, cfg_scale: float = 1.0,
+                 phi: float = 0.0, stg_scale: float = 0.0, stg_blocks: Sequence[int] = (29,), ge_gamma: float = 0.0,
+                 mlx_bf16: bool = True, dtype=torch.float32, return_velocities: bool = False):
+    """P/LTXPipeline.swift:793-956 (generateVideo step loop).  noise [1,C,F,H,W] fp32."""
+    latent = noise.float() * sigmas[0]                           # :793
+    fhw = tuple(noise.shape[2:])
+    v_prev = None
+    vels = []
+    for step in range(len(sigmas) - 1):
+        sg, sn = sigmas[step], sigmas[step + 1]
+        tok = patchify(latent)
+        ts = torch.tensor([sg], dtype=torch.float32)
+        vc = unpatchify(dit_forward(w, cfg, tok, context, ts, mask, fhw, dtype=dtype, mlx_bf16=mlx_bf16), fhw).float()
+        vu = vs = None
+        if cfg_scale > 1.0 and neg_context is not None:
+            vu = unpatchify(dit_forward(w, cfg, tok, neg_context, ts, neg_mask, fhw, dtype=dtype, mlx_bf16=mlx_bf16), fhw).float()
+        if stg_scale > 0:
+            vs = unpatchify(dit_forward(w, cfg, tok, context, ts, mask, fhw, stg_blocks=stg_blocks, skip_self_attn=True,
+                                        dtype=dtype, mlx_bf16=mlx_bf16), fhw).float()
+        latent, v_prev = guided_euler_step(latent, vc, vu, vs, v_prev, cfg_scale, phi, stg_scale, ge_gamma, sg, sn)
+        vels.append(v_prev)
+    return (latent, vels) if return_velocities else latent
+
+
+# ----------------------------------------------------------------------------------------------
+# video VAE decoder (V/VideoConvolution.swift:202-348, V/VideoDecoder.swift)
+# ----------------------------------------------------------------------------------------------
+def conv3d_full(x: Tensor, weight: Tensor, bias: Tensor, causal: bool = False, spatial_pad: str = "reflect") -> Tensor:
+    """V/VideoConvolution.swift:238-347.  x [B,C,T,H,W]; 3x3x3 cross-correlation, pad H/W by 1 (reflect | zeros |
+    replicate), pad T by frame replication: causal ? 2 x first : 1 x first + 1 x last."""
+    mode = {"reflect": "reflect", "zeros": "constant", "replicate": "replicate"}[spatial_pad]
+    B, C, T, H, W = x.shape
+    x2 = torch.nn.functional.pad(x.reshape(B, C * T, H, W), (1, 1, 1, 1), mode=mode).view(B, C, T, H + 2, W + 2)
+    if causal:
+        x2 = torch.cat([x2[:, :, :1], x2[:, :, :1], x2], dim=2)
+    else:
+        x2 = torch.cat([x2[:, :, :1], x2, x2[:, :, -1:]], dim=2)
+    return torch.nn.functional.conv3d(x2, weight.to(x.dtype), bias.to(x.dtype))
+
+
+def pixel_norm(x: Tensor, eps: float = 1e-8) -> Tensor:          # V/VideoDecoder.swift:29-32
+    return x / torch.sqrt(x.pow(2).mean(dim=1, keepdim=True) + eps)
+
+
+def depth_to_space(x: Tensor, c_out: int) -> Tensor:            # :201-212
+    B, _, T, H, W = x.shape
+    o = x.reshape(B, c_out, 2, 2, 2, T, H, W).permute(0, 1, 5, 2, 6, 3, 7, 4)
+    return o.reshape(B, c_out, 2 * T, 2 * H, 2 * W)
+
+
+def vae_time_embed(w, prefix: str, t: Tensor) -> Tensor:         # :37-52, 11-24
+    e = sinusoidal_embedding(t, 256).to(t.dtype if t.dtype.is_floating_point else torch.float32)
+    h = e @ w[prefix + ".timestep_embedder.linear_1.weight"].t() + w[prefix + ".timestep_embedder.linear_1.bias"]
+    h = silu(h)
+    return h @ w[prefix + ".timestep_embedder.linear_2.weight"].t() + w[prefix + ".timestep_embedder.linear_2.bias"]
+
+
+def vae_resblock(w, prefix: str, x: Tensor, causal: bool, time_emb: Optional[Tensor]) -> Tensor:   # :93-130
+    C = x.shape[1]
+    tbl = w[prefix + ".scale_shift_table"].to(x.dtype).unsqueeze(0)                 # rows shift1, scale1, shift2, scale2
+    if time_emb is not None:
+        tbl = tbl + time_emb.view(-1, 4, C).to(x.dtype)
+    sh1, sc1, sh2, sc2 = [tbl[:, r].reshape(-1, C, 1, 1, 1) for r in range(4)]
+    h = silu(pixel_norm(x) * (sc1 + 1) + sh1)
+    h = conv3d_full(h, w[prefix + ".conv1.conv.weight"], w[prefix + ".conv1.conv.bias"], causal)
+    h = silu(pixel_norm(h) * (sc2 + 1) + sh2)
+    h = conv3d_full(h, w[prefix + ".conv2.conv.weight"], w[prefix + ".conv2.conv.bias"], causal)
+    return h + x
+
+
+def vae_d2s_up(w, prefix: str, x: Tensor, causal: bool) -> Tensor:                  # :214-251
+    C = x.shape[1]
+    r = depth_to_space(x, C // 8)[:, :, 1:]
+    r = torch.cat([r, r, r, r], dim=1)
+    h = conv3d_full(x, w[prefix + ".conv.conv.weight"], w[prefix + ".conv.conv.bias"], causal)
+    h = depth_to_space(h, C // 2)[:, :, 1:]
+    return h + r
+
+
+def vae_unpatchify(x: Tensor, p: int = 4) -> Tensor:                                # :257-275
+    B, CP, T, H, W = x.shape
+    c = CP // (p * p)
+    o = x.reshape(B, c, 1, p, p, T, H, W).permute(0, 1, 5, 2, 6, 4, 7, 3)
+    return o.reshape(B, c, T, H * p, W * p)
+
+
+def vae_decode(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float] = None,
+               decode_noise: Optional[Tensor] = None, dtype=torch.float32, return_stages: bool = False):
+    """V/VideoDecoder.swift:358-449.  latent [1,128,F',H',W'] -> [1,3,8(F'-1)+1,32H',32W']."""
+    x = latent.to(dtype)
+    w = {k: v.to(dtype) for k, v in w.items()}
+    B = x.shape[0]
+    t = None
+    if timestep is not None:                                                         # :368-375
+        assert decode_noise is not None, "noise must be passed in explicitly (SURVEY H7)"
+        x = decode_noise.to(dtype) * 0.025 + (1.0 - 0.025) * x
+        t = torch.full((B,), float(timestep), dtype=dtype) * w["timestep_scale_multiplier"]
+    x = x * w["std_of_means"].view(1, -1, 1, 1, 1) + w["mean_of_means"].view(1, -1, 1, 1, 1)   # :379-381
+    x = conv3d_full(x, w["conv_in.conv.weight"], w["conv_in.conv.bias"], cfg.causal)            # :385
+    stages = []
+    chans = cfg.stage_channels
+    for s in range(len(chans)):
+        blk = f"up_blocks_{2 * s}"
+        te = vae_time_embed(w, blk + ".time_embedder", t) if t is not None else None
+        for j in range(cfg.blocks_per_stage):
+            x = vae_resblock(w, f"{blk}.res_blocks.{j}", x, cfg.causal, te)
+        stages.append(x)
+        if s < len(chans) - 1:
+            x = vae_d2s_up(w, f"up_blocks_{2 * s + 1}", x, cfg.causal)
+            stages.append(x)
+    C = chans[-1]
+    tbl = w["last_scale_shift_table"].unsqueeze(0)                                    # rows shift, scale :419-436
+    if t is not None:
+        tbl = tbl + vae_time_embed(w, "last_time_embedder", t).view(B, 2, C)
+    x = pixel_norm(x) * (tbl[:, 1].reshape(-1, C, 1, 1, 1) + 1) + tbl[:, 0].reshape(-1, C, 1, 1, 1)
+    x = silu(x)
+    x = conv3d_full(x, w["conv_out.conv.weight"], w["conv_out.conv.bias"], cfg.causal)          # :439
+    x = vae_unpatchify(x, cfg.patch_size)                                                        # :444
+    return (x, stages) if return_stages else x
+
+
+def decode_video(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float] = None,
+                 decode_noise: Optional[Tensor] = None, dtype=torch.float32) -> Tensor:
+    """V/VideoDecoder.swift:466-508 (untiled): frames [F,H,W,3] in [0,1]."""
+    if latent.ndim == 4:
+        latent = latent.unsqueeze(0)
+    x = vae_decode(w, cfg, latent, timestep, decode_noise, dtype)
+    x = torch.clamp((x + 1.0) / 2.0, 0.0, 1.0)
+    return x[0].permute(1, 2, 3, 0).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# metrics used by the parity tests
+# ----------------------------------------------------------------------------------------------
+def rel_l2(a: Tensor, b: Tensor) -> float:
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def psnr(a: Tensor, b: Tensor, peak: float = 1.0) -> float:
+    mse = float((a.double() - b.double()).pow(2).mean())
+    return 99.0 if mse == 0 else 10.0 * math.log10(peak * peak / mse)

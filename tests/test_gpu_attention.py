@@ -1,0 +1,53 @@
+"""tcgen05 flash-attention parity (ltx_op_attention) against an fp32 torch softmax(QK^T)V."""
+import math
+
+import pytest
+import torch
+
+from helpers import product, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = product().LtxContext(product().LTXTransformerConfig(num_layers=1, num_attention_heads=1), 0)
+    yield c
+    c.close()
+
+
+CASES = [  # B, H, Nq, Nk, masked
+    (1, 1, 128, 128, False), (1, 2, 48, 48, False), (1, 2, 300, 300, False), (1, 2, 200, 40, True),
+    (2, 2, 130, 70, True), (1, 4, 1536, 1536, False), (1, 4, 1536, 1024, True), (3, 1, 257, 129, False),
+]
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,masked", CASES)
+def test_attention(ctx, B, H, Nq, Nk, masked):
+    D = H * 128
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H * 100 + Nq + Nk)
+    q = torch.randn(B * Nq, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B * Nk, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B * Nk, D, device="cuda", generator=g).bfloat16()
+    ldv = (B * Nk + 7) // 8 * 8
+    vt = torch.zeros(D, ldv, device="cuda", dtype=torch.bfloat16)
+    vt[:, : B * Nk] = v.t()
+    bias = None
+    if masked:
+        m = (torch.rand(B, Nk, device="cuda", generator=g) > 0.3).float()
+        m[:, 0] = 1
+        bias = ((1 - m) * -10000.0).contiguous()
+    o = torch.full((B * Nq, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(128)
+    ctx._check(ctx.lib.ltx_op_attention(ctx.handle, q.data_ptr(), k.data_ptr(), vt.data_ptr(), ldv,
+                                        bias.data_ptr() if bias is not None else None, o.data_ptr(), B, H, Nq, Nk, scale))
+    ctx.sync()
+    qh = q.float().view(B, Nq, H, 128).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Nk, H, 128).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Nk, H, 128).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if bias is not None:
+        s = s + bias.view(B, 1, 1, Nk)
+    ref = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B * Nq, D)
+    assert torch.isfinite(o.float()).all()
+    assert rel_l2(o.float(), ref) <= 1e-2   # P and O are rounded to bf16

@@ -1,0 +1,97 @@
+"""Full DiT forward / denoise-loop parity against the CPU oracle (rel-L2 <= 1e-2 in bf16 mode, north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, make_ctx_with_dit, rel_l2, small_dit_config, product
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+def _inputs(ocfg, fhw, S, seed, B=1, mask_prefix=0):
+    g = torch.Generator().manual_seed(seed)
+    N = fhw[0] * fhw[1] * fhw[2]
+    lat = torch.randn(B, N, ocfg.in_channels, generator=g).bfloat16()
+    ctx = torch.randn(B, S, ocfg.caption_channels, generator=g)
+    ctx = (ctx / ctx.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()     # unit-RMS rows like the real connector
+    mask = torch.ones(B, S, dtype=torch.int32)
+    if mask_prefix:
+        mask[:, :mask_prefix] = 0
+    return lat, ctx, mask
+
+
+@pytest.mark.parametrize("layers,heads,fhw,S,B,mask_prefix", [
+    (2, 2, (2, 4, 6), 40, 1, 7), (3, 4, (4, 8, 10), 150, 1, 0), (2, 2, (1, 4, 4), 24, 2, 5),
+])
+def test_dit_forward_matches_oracle(layers, heads, fhw, S, B, mask_prefix):
+    ocfg, pcfg = small_dit_config(layers, heads)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=layers * 10 + heads)
+    lat, cx, mask = _inputs(ocfg, fhw, S, 5, B, mask_prefix)
+    sig = torch.tensor([0.7, 0.3][:B])
+    ref = O.dit_forward(w, ocfg, lat.float(), cx.float(), sig, mask if mask_prefix else None, fhw)
+    out = ctx.dit_forward(lat, cx, sig.numpy(), mask if mask_prefix else None, fhw)
+    assert np.isfinite(out).all()
+    err = rel_l2(out, ref)
+    assert err <= TOL, err
+    # fp32 host inputs take the cast path and must agree with the bf16 call
+    out2 = ctx.dit_forward(lat.float(), cx.float(), sig.numpy(), mask if mask_prefix else None, fhw)
+    assert rel_l2(out2, out) <= 1e-6
+    ctx.close()
+
+
+def test_dit_stg_and_cross_scale_flags():
+    ocfg, pcfg = small_dit_config(3, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=3)
+    fhw, S = (2, 4, 6), 40
+    lat, cx, mask = _inputs(ocfg, fhw, S, 9)
+    sig = torch.tensor([0.5])
+    ctxmod = product()
+    for stg in ([0], [1], [2], [0, 1]):
+        ref = O.dit_forward(w, ocfg, lat.float(), cx.float(), sig, None, fhw, stg_blocks=stg, skip_self_attn=True)
+        out = ctx.dit_forward(lat, cx, sig.numpy(), None, fhw, ctxmod.make_flags(stg_blocks=stg, skip_self_attn=True))
+        assert rel_l2(out, ref) <= TOL
+    ref = O.dit_forward(w, ocfg, lat.float(), cx.float(), sig, None, fhw, stg_blocks=[1], skip_self_attn=True, skip_ff=True)
+    out = ctx.dit_forward(lat, cx, sig.numpy(), None, fhw, ctxmod.make_flags(stg_blocks=[1], skip_self_attn=True, skip_ff=True))
+    assert rel_l2(out, ref) <= TOL
+    ref = O.dit_forward(w, ocfg, lat.float(), cx.float(), sig, None, fhw, cross_attn_scale={1: 0.25})
+    out = ctx.dit_forward(lat, cx, sig.numpy(), None, fhw, ctxmod.make_flags(cas_blocks=[1], cross_attn_scale=0.25))
+    assert rel_l2(out, ref) <= TOL
+    ctx.close()
+
+
+def test_context_cache_key_is_equivalent():
+    ocfg, pcfg = small_dit_config(2, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=4)
+    fhw, S = (2, 4, 6), 40
+    lat, cx, mask = _inputs(ocfg, fhw, S, 13, mask_prefix=3)
+    sig = np.array([0.6], dtype=np.float32)
+    ctxmod = product()
+    a = ctx.dit_forward(lat, cx, sig, mask, fhw)
+    b = ctx.dit_forward(lat, cx, sig, mask, fhw, ctxmod.make_flags(context_key=77))
+    c = ctx.dit_forward(lat, cx, sig, mask, fhw, ctxmod.make_flags(context_key=77))    # served from the cache
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(b, c)
+    ctx.close()
+
+
+@pytest.mark.parametrize("guided", [False, True])
+def test_denoise_loop_matches_oracle(guided):
+    ocfg, pcfg = small_dit_config(3, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=6)
+    fhw, S = (2, 4, 6), 40
+    g = torch.Generator().manual_seed(21)
+    noise = torch.randn(1, 128, *fhw, generator=g)
+    _, cx, mask = _inputs(ocfg, fhw, S, 17)
+    _, ncx, _ = _inputs(ocfg, fhw, S, 18)
+    sigmas = O.set_timesteps(4, False, 48) if guided else O.set_timesteps(8, True, 48)[4:]
+    kw = dict(neg_context=ncx.float(), cfg_scale=4.0, phi=0.7, stg_scale=0.5, stg_blocks=(1,), ge_gamma=0.1) if guided else {}
+    ref = O.denoise_loop(w, ocfg, noise, cx.float(), None, sigmas, **kw)
+    ctx.denoise_begin(noise[0].numpy(), fhw, sigmas[0], cx, None, ncx if guided else None, None)
+    for i in range(len(sigmas) - 1):
+        ctx.denoise_step(sigmas[i], sigmas[i + 1], i, cfg_scale=4.0 if guided else 1.0, rescale_phi=0.7 if guided else 0.0,
+                         stg_scale=0.5 if guided else 0.0, stg_blocks=(1,) if guided else (), ge_gamma=0.1 if guided else 0.0)
+    out = ctx.denoise_get_latent()
+    err = rel_l2(out, ref[0])
+    assert err <= 2e-2, err      # several guided steps compound the per-step 1e-2 velocity tolerance
+    ctx.close()

@@ -1,0 +1,23 @@
+"""Video-VAE decode parity against the CPU oracle: PSNR >= 40 dB on [0,1] frames (bf16 activations into the convs)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, make_ctx_with_vae, small_vae_config
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("base,blocks,fhw", [(512, 1, (2, 3, 4)), (512, 2, (3, 4, 6)), (1024, 1, (1, 2, 3))])
+def test_vae_decode_matches_oracle(base, blocks, fhw):
+    ocfg, pcfg = small_vae_config(base, blocks)
+    ctx, w = make_ctx_with_vae(ocfg, pcfg, seed=base + blocks)
+    g = torch.Generator().manual_seed(31)
+    z = torch.randn(1, 128, *fhw, generator=g)
+    ref = O.decode_video(w, ocfg, z)
+    out = ctx.vae_decode(z[0].numpy())
+    assert out.shape == tuple(ref.shape) == (8 * (fhw[0] - 1) + 1, 32 * fhw[1], 32 * fhw[2], 3)
+    assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
+    p = O.psnr(torch.from_numpy(out), ref)
+    assert p >= 40.0, p
+    ctx.close()
