@@ -153,6 +153,14 @@ int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp
 
 /* Number of kernels launched by this context so far (bench.py reports the per-step delta as gpu_launches). */
 uint64_t ltx_launch_count(const ltx_ctx* ctx);
+/* The CUDA stream (cudaStream_t) every kernel of this context is enqueued on -- for CUDA-event timing by the caller. */
+int ltx_get_stream(ltx_ctx* ctx, void** stream);
+/* Per-kernel-class device timing (the B200 counterpart of GenerationTimings / --profile, LTXVideo.swift:255-297):
+ * when enabled, every launch is bracketed by CUDA events on the context stream.  ltx_get_profile synchronises, sums
+ * elapsed ms / algorithmic flops / algorithmic bytes / launch counts per class and clears the records.
+ * Classes: 0 GEMM, 1 attention, 2 norm/RoPE rows, 3 conv3d, 4 VAE prologue, 5 other; n_classes must be >= 8. */
+int ltx_set_profiling(ltx_ctx* ctx, int enabled);
+int ltx_get_profile(ltx_ctx* ctx, double* ms, double* flops, double* bytes, uint64_t* counts, int n_classes);
 
 /* ---- diagnostic single-kernel entry points (device pointers; used by the parity tests and the profiler) ---- */
 /* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) ; mode: 0 bf16 out, 1 gelu bf16 out, 3 fp32 out; force_bn: 0 auto, 128, 256. */
@@ -161,8 +169,9 @@ int ltx_op_gemm(ltx_ctx* ctx, const void* A, const void* B, const float* bias, v
 /* x[M,N] (fp32) += (A B^T + bias) * (gate_a[n] + gate_b[n]) * scale ; shadow (bf16, nullable) = new x. */
 int ltx_op_gemm_resid(ltx_ctx* ctx, const void* A, const void* B, const float* bias, float* x, const float* gate_a,
                       const float* gate_b, void* shadow, int M, int N, int K, float scale);
-/* O = softmax(Q K^T * scale + key_bias) V ; Q [B*Nq, H*128], K [B*Nk, H*128], Vt [H*128, ldv], all bf16. */
-int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldv, const float* key_bias, void* O,
+/* O = softmax(Q K^T * scale + key_bias) V ; Q [B*Nq, H*128], K [B*Nk, H*128], Vt [H*128, B*ldvb] (batch b owns
+ * columns [b*ldvb, b*ldvb + Nk), ldvb % 8 == 0), all bf16. */
+int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
                      int B, int H, int Nq, int Nk, float scale);
 int ltx_op_rmsnorm_mod(ltx_ctx* ctx, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm);

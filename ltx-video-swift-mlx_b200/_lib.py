@@ -62,6 +62,9 @@ SIGNATURES = {
     "ltx_vae_decode": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_decode_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_launch_count": (_U64, [_P]),
+    "ltx_get_stream": (_I, [_P, C.POINTER(_P)]),
+    "ltx_set_profiling": (_I, [_P, _I]),
+    "ltx_get_profile": (_I, [_P, _P, _P, _P, _P, _I]),
     "ltx_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "ltx_op_gemm_resid": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F]),
     "ltx_op_attention": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _F]),

@@ -123,6 +123,25 @@ class LtxContext:
     def launch_count(self) -> int:
         return int(self.lib.ltx_launch_count(self.handle))
 
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.ltx_get_stream(self.handle, C.byref(p)))
+        return p.value or 0
+
+    def set_profiling(self, enabled: bool):
+        self._check(self.lib.ltx_set_profiling(self.handle, int(enabled)))
+
+    PROFILE_CLASSES = ("gemm", "attention", "rows", "conv3d", "vae_prologue", "other")
+
+    def get_profile(self) -> Dict[str, dict]:
+        n = 8
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        self._check(self.lib.ltx_get_profile(self.handle, ms, fl, by, cnt, n))
+        return {name: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(cnt[i]))
+                for i, name in enumerate(self.PROFILE_CLASSES)}
+
     # ------------------------------------------------------------------ weights
     def load_tensor(self, key: str, value):
         code = _dtype_code(value)

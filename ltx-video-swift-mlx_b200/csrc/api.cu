@@ -118,6 +118,37 @@ int ltx_sync(ltx_ctx* c) {
 
 uint64_t ltx_launch_count(const ltx_ctx* c) { return c ? c->launches : 0; }
 
+int ltx_get_stream(ltx_ctx* c, void** stream) {
+  return guarded(c, [&] {
+    LTX_CHECK(stream != nullptr, LTX_ERR_INVALID_ARGUMENT, "null out pointer");
+    *stream = reinterpret_cast<void*>(c->stream);
+  });
+}
+
+int ltx_set_profiling(ltx_ctx* c, int enabled) {
+  return guarded(c, [&] {
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& r : c->prof_recs) { c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b); }
+    c->prof_recs.clear();
+    c->prof_on = enabled != 0;
+  });
+}
+
+int ltx_get_profile(ltx_ctx* c, double* ms, double* flops, double* bytes, uint64_t* counts, int n_classes) {
+  return guarded(c, [&] {
+    LTX_CHECK(ms && flops && bytes && counts && n_classes >= PROF_NCLASS, LTX_ERR_INVALID_ARGUMENT, "bad profile buffers");
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n_classes; ++i) { ms[i] = 0; flops[i] = 0; bytes[i] = 0; counts[i] = 0; }
+    for (auto& r : c->prof_recs) {
+      float t = 0.f;
+      LTX_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; counts[r.cls] += 1;
+      c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+  });
+}
+
 int ltx_load_tensor(ltx_ctx* c, const char* key, const void* host_data, ltx_dtype dtype, const int64_t* shape, int ndim) {
   return guarded(c, [&] {
     LTX_CHECK(key != nullptr, LTX_ERR_INVALID_ARGUMENT, "null key");
@@ -240,8 +271,10 @@ int ltx_denoise_begin(ltx_ctx* c, const float* noise, int F, int H, int W, float
     c->s_F = F; c->s_H = H; c->s_W = W; c->s_S = S;
     c->s_ctx_dtype = context_dtype;
     h2d(c, c->s_latent, noise, n * 4);
-    launch_scale_f32(c->s_latent.as<float>(), sigma0, static_cast<int64_t>(n), c->stream);  // P/LTXPipeline.swift:793
-    c->launches++;
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * n);
+      launch_scale_f32(c->s_latent.as<float>(), sigma0, static_cast<int64_t>(n), c->stream);  // P/LTXPipeline.swift:793
+    }
     const size_t cbytes = static_cast<size_t>(S) * g.caption_channels * dsize(context_dtype);
     h2d(c, c->s_ctx_pos, context, cbytes);
     c->s_has_mask_pos = mask != nullptr;
@@ -275,9 +308,11 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     const size_t n = static_cast<size_t>(C) * T;
     cudaStream_t st = c->stream;
     // patchify(latent).asType(.bfloat16)  (P/LTXPipeline.swift:815)
-    launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * n);
+      launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
+    }
     LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
-    c->launches++;
     const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
     auto pass = [&](bool neg, bool stg, float* v_lat) {
       ltx_dit_flags fl = {};
@@ -293,8 +328,8 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
                               : (c->s_has_mask_pos ? c->s_mask_pos.as<int32_t>() : nullptr);
       dit_forward_dev(c, c->s_tok.ptr, LTX_BF16, cx, c->s_ctx_dtype, c->s_sigma.as<float>(), 0, mk, 1, T, S, F, H, W, &fl,
                       c->vel.as<float>());
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * n);
       launch_unpatchify(c->vel.as<float>(), v_lat, C, T, st);  // velocity back to [C, F, H, W]
-      c->launches++;
     };
     const bool use_cfg = p->cfg_scale > 1.0f && c->s_has_neg;
     const bool use_stg = p->stg_scale > 0.f && p->n_stg_blocks > 0;
@@ -309,8 +344,9 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     a.use_prev = p->step_index > 0 ? 1 : 0;
     a.v_out = nullptr; a.n = n; a.cfg = p->cfg_scale; a.phi = p->rescale_phi; a.stg = p->stg_scale;
     a.ge_gamma = p->ge_gamma; a.sigma = p->sigma; a.sigma_next = p->sigma_next; a.scratch = c->scratch.as<double>();
+    ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * n * (4.0 + (use_cfg ? 1.0 : 0.0) + (use_stg ? 1.0 : 0.0)),
+                 (use_cfg && p->rescale_phi > 0.f) ? 2 : 1);
     launch_guided_euler(a, st);
-    c->launches += (use_cfg && p->rescale_phi > 0.f) ? 2 : 1;
   });
 }
 
@@ -379,12 +415,12 @@ int ltx_op_gemm_resid(ltx_ctx* c, const void* A, const void* B, const float* bia
   });
 }
 
-int ltx_op_attention(ltx_ctx* c, const void* Q, const void* K, const void* Vt, int64_t ldv, const float* key_bias, void* O,
+int ltx_op_attention(ltx_ctx* c, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
                      int B, int H, int Nq, int Nk, float scale) {
   return guarded(c, [&] {
     const int D = H * 128;
     launch_attention(reinterpret_cast<const bf16*>(Q), D, reinterpret_cast<const bf16*>(K), D,
-                     reinterpret_cast<const bf16*>(Vt), ldv, key_bias, reinterpret_cast<bf16*>(O), D, B, H, Nq, Nk, D, scale,
+                     reinterpret_cast<const bf16*>(Vt), ldvb, key_bias, reinterpret_cast<bf16*>(O), D, B, H, Nq, Nk, D, scale,
                      c->stream);
     c->launches++;
   });

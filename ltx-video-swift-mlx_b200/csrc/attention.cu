@@ -99,8 +99,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tma_load_2d(sK + s * TILE_BYTES + HALF_BYTES, &tmK, &k_full[s], h * HD + 64, krow);
         mbar_wait(&v_empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-        tma_load_2d(sV + s * TILE_BYTES, &tmV, &v_full[s], krow, h * HD);
-        tma_load_2d(sV + s * TILE_BYTES + HALF_BYTES, &tmV, &v_full[s], krow + 64, h * HD);
+        // V^T is a 3-D map (keys, features, batch): keys past Nk are zero-filled, never another batch's columns
+        tma_load_3d(sV + s * TILE_BYTES, &tmV, &v_full[s], j * TK, h * HD, b);
+        tma_load_3d(sV + s * TILE_BYTES + HALF_BYTES, &tmV, &v_full[s], j * TK + 64, h * HD, b);
       }
     }
   } else if (warp == 1) {
@@ -259,12 +260,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 }  // namespace
 
-void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldv,
+void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                       const float* key_bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
                       cudaStream_t stream) {
   LTX_CHECK(D == H * HD, 2, "attention: head_dim must be 128");
   LTX_CHECK(Nq > 0 && Nk > 0 && B > 0, 2, "attention: empty problem");
-  LTX_CHECK(ldv % 8 == 0 && ldv >= static_cast<int64_t>(B) * Nk, 2, "attention: V^T pitch");
+  LTX_CHECK(ldvb % 8 == 0 && ldvb >= Nk, 2, "attention: V^T per-batch pitch must be a multiple of 8 and >= Nk");
   static bool configured = false;
   if (!configured) {
     LTX_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -273,7 +274,7 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
   }
   CUtensorMap tmQ = make_tmap_2d(Q, static_cast<uint64_t>(B) * Nq, D, ldq, 128);
   CUtensorMap tmK = make_tmap_2d(K, static_cast<uint64_t>(B) * Nk, D, ldk, 128);
-  CUtensorMap tmV = make_tmap_2d(Vt, D, static_cast<uint64_t>(B) * Nk, ldv, 128);
+  CUtensorMap tmV = make_tmap_3d(Vt, Nk, D, B, static_cast<uint64_t>(B) * ldvb, ldvb, 64, 128);
   AttnParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
   p.scale_log2 = scale * 1.4426950408889634f;

@@ -85,8 +85,22 @@ struct VaeWeights {
 
 }  // namespace ltx
 
+namespace ltx {
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_CONV = 3, PROF_PREP = 4, PROF_OTHER = 5, PROF_NCLASS = 8 };
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double flops, bytes;
+};
+}  // namespace ltx
+
 struct ltx_ctx {
   ltx_config cfg;
+  // ---- optional per-kernel-class timing (CUDA events on the context stream around every launch)
+  bool prof_on = false;
+  std::vector<ltx::ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+
   int device = 0;
   cudaStream_t stream = nullptr;
   mutable std::string last_error;
@@ -126,6 +140,29 @@ struct ltx_ctx {
 };
 
 namespace ltx {
+// RAII scope: times the launches issued inside it when profiling is on, and counts them.
+struct ProfScope {
+  ltx_ctx* c;
+  ProfRec r;
+  bool on;
+  ProfScope(ltx_ctx* ctx, int cls, double flops, double bytes, int launches = 1) : c(ctx), on(ctx->prof_on) {
+    c->launches += launches;
+    if (!on) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+      else LTX_CUDA(cudaEventCreate(&e));
+      return e;
+    };
+    r.a = get(); r.b = get(); r.cls = cls; r.flops = flops; r.bytes = bytes;
+    LTX_CUDA(cudaEventRecord(r.a, c->stream));
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, c->stream);
+    c->prof_recs.push_back(r);
+  }
+};
 // dit.cu
 void dit_finalize(ltx_ctx* c);
 void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,

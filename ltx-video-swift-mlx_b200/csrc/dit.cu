@@ -15,10 +15,27 @@ namespace ltx {
 
 namespace {
 
-struct Launcher {
-  ltx_ctx* c;
-  void count(int n = 1) { c->launches += n; }
-};
+// profiled launch helpers (flop / byte counts are the algorithmic ones used by bench.py's roofline)
+void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e) {
+  ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
+  launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream);
+}
+void attention(ltx_ctx* c, const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
+               const float* bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale) {
+  ProfScope ps(c, PROF_ATTN, 4.0 * B * H * static_cast<double>(Nq) * Nk * 128.0,
+               2.0 * B * (2.0 * Nq + 2.0 * Nk) * D);
+  launch_attention(Q, ldq, K, ldk, Vt, ldvb, bias, O, ldo, B, H, Nq, Nk, D, scale, c->stream);
+}
+void norm_mod(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* ts, const float* tsc, const float* as,
+              const float* asc, int64_t ada_ld, int rows_per_mod, float eps, int ln) {
+  ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * 6.0);
+  launch_rmsnorm_mod(x, out, M, D, ts, tsc, as, asc, ada_ld, rows_per_mod, eps, ln, c->stream);
+}
+void qknorm(ltx_ctx* c, bf16* x, int64_t ld, int M, int D, const float* w, const float* cs, const float* sn, int rpr,
+            float eps) {
+  ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)));
+  launch_qknorm_rope(x, ld, M, D, w, cs, sn, rpr, eps, c->stream);
+}
 
 const bf16* wbf(ltx_ctx* c, const std::string& k, int64_t r, int64_t cc) {
   const DevTensor& t = get_tensor(c, k);
@@ -107,9 +124,9 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
   TextCache& tc = c->text[slot];
   const int64_t R = static_cast<int64_t>(B) * S;
   tc.key = key; tc.B = B; tc.S = S;
-  tc.ldv = round_up(R, 8);
+  tc.ldv = round_up(S, 8);  // per-batch pitch of V^T; row pitch is B * ldv
   tc.k.reserve(static_cast<size_t>(L) * R * D * 2);
-  tc.vt.reserve(static_cast<size_t>(L) * D * tc.ldv * 2);
+  tc.vt.reserve(static_cast<size_t>(L) * D * B * tc.ldv * 2);
   cudaStream_t st = c->stream;
   // stage context as bf16
   const bf16* ctx_bf;
@@ -119,36 +136,38 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
     LTX_CHECK(context_dtype == LTX_F32, LTX_ERR_UNSUPPORTED, "context dtype must be bf16 or f32");
     LTX_CHECK((R * Cc) % 4 == 0, LTX_ERR_INVALID_ARGUMENT, "context size");
     c->ctx_in.reserve(static_cast<size_t>(R) * Cc * 2);
-    launch_cast_f32_bf16(reinterpret_cast<const float*>(context), c->ctx_in.as<bf16>(), R * Cc, st);
-    c->launches++;
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * Cc);
+      launch_cast_f32_bf16(reinterpret_cast<const float*>(context), c->ctx_in.as<bf16>(), R * Cc, st);
+    }
     ctx_bf = c->ctx_in.as<bf16>();
   }
   c->c1.reserve(static_cast<size_t>(R) * D * 2);
   c->c2.reserve(static_cast<size_t>(R) * D * 2);
   GemmEpi e;
   e.mode = EPI_GELU_BF16; e.out = c->c1.ptr; e.ldo = D; e.bias = c->b_c1;
-  launch_gemm(ctx_bf, Cc, c->w_c1, Cc, static_cast<int>(R), D, Cc, e, st);
+  gemm(c, ctx_bf, Cc, c->w_c1, Cc, static_cast<int>(R), D, Cc, e);
   e.mode = EPI_BF16; e.out = c->c2.ptr; e.bias = c->b_c2;
-  launch_gemm(c->c1.as<bf16>(), D, c->w_c2, D, static_cast<int>(R), D, D, e, st);
-  c->launches += 2;
+  gemm(c, c->c1.as<bf16>(), D, c->w_c2, D, static_cast<int>(R), D, D, e);
   for (int i = 0; i < L; ++i) {
     const AttnWeights& a = c->blocks[i].a2;
     bf16* kd = tc.k.as<bf16>() + static_cast<int64_t>(i) * R * D;
-    bf16* vd = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * tc.ldv;
+    bf16* vd = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * B * tc.ldv;
     GemmEpi ek;
     ek.mode = EPI_BF16; ek.out = kd; ek.ldo = D; ek.bias = a.bk;
-    launch_gemm(c->c2.as<bf16>(), D, a.wk, D, static_cast<int>(R), D, D, ek, st);
-    launch_qknorm_rope(kd, D, static_cast<int>(R), D, a.k_norm, nullptr, nullptr, 1, g.norm_eps, st);
-    GemmEpi ev;  // V^T[D, R] = Wv [D, D] * c^T
-    ev.mode = EPI_BF16; ev.out = vd; ev.ldo = tc.ldv; ev.bias = a.bv; ev.bias_per_row = 1;
-    launch_gemm(a.wv, D, c->c2.as<bf16>(), D, D, static_cast<int>(R), D, ev, st);
-    c->launches += 3;
+    gemm(c, c->c2.as<bf16>(), D, a.wk, D, static_cast<int>(R), D, D, ek);
+    qknorm(c, kd, D, static_cast<int>(R), D, a.k_norm, nullptr, nullptr, 1, g.norm_eps);
+    for (int b = 0; b < B; ++b) {  // V^T[D, S] = Wv [D, D] * c_b^T, one column block per batch
+      GemmEpi ev;
+      ev.mode = EPI_BF16; ev.out = vd + b * tc.ldv; ev.ldo = B * tc.ldv; ev.bias = a.bv; ev.bias_per_row = 1;
+      gemm(c, a.wv, D, c->c2.as<bf16>() + static_cast<int64_t>(b) * S * D, D, D, S, D, ev);
+    }
   }
   tc.has_bias = mask_dev != nullptr;
   if (mask_dev) {
     tc.bias.reserve(static_cast<size_t>(R) * 4);
+    ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * R);
     launch_mask_to_bias(mask_dev, tc.bias.as<float>(), static_cast<int>(R), st);
-    c->launches++;
   }
   return tc;
 }
@@ -261,12 +280,12 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
             LTX_ERR_INVALID_ARGUMENT, "bad flag block counts");
 
   // ---- workspaces
-  const int64_t ldv = round_up(R, 8);
+  const int64_t ldv = round_up(N, 8);  // per-batch pitch of V^T
   c->x.reserve(static_cast<size_t>(R) * D * 4);
   c->xb.reserve(static_cast<size_t>(R) * D * 2);
   c->h.reserve(static_cast<size_t>(R) * D * 2);
   c->qk.reserve(static_cast<size_t>(R) * 2 * D * 2);
-  c->vt.reserve(static_cast<size_t>(D) * ldv * 2);
+  c->vt.reserve(static_cast<size_t>(D) * B * ldv * 2);
   c->att.reserve(static_cast<size_t>(R) * D * 2);
   c->q2.reserve(static_cast<size_t>(R) * D * 2);
   c->ffh.reserve(static_cast<size_t>(R) * FFD * 2);
@@ -297,23 +316,27 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   } else {
     LTX_CHECK(latent_dtype == LTX_F32, LTX_ERR_UNSUPPORTED, "latent dtype must be bf16 or f32");
     c->lat_in.reserve(static_cast<size_t>(R) * Cin * 2);
-    launch_cast_f32_bf16(reinterpret_cast<const float*>(latent), c->lat_in.as<bf16>(), static_cast<int64_t>(R) * Cin, st);
-    c->launches++;
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * Cin);
+      launch_cast_f32_bf16(reinterpret_cast<const float*>(latent), c->lat_in.as<bf16>(), static_cast<int64_t>(R) * Cin, st);
+    }
     lat_bf = c->lat_in.as<bf16>();
   }
   {
     GemmEpi e;
     e.mode = EPI_BF16; e.out = xb; e.ldo = D; e.bias = c->b_patch;
-    launch_gemm(lat_bf, Cin, c->w_patch, Cin, R, D, Cin, e, st);
+    gemm(c, lat_bf, Cin, c->w_patch, Cin, R, D, Cin, e);
+    ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * D);
     launch_cast_bf16_f32(xb, x, static_cast<int64_t>(R) * D, st);
-    c->launches += 2;
   }
   // ---- timestep path (T/LTXTimestepEmbedding.swift:62-124): fp32 activations, bf16 weights
-  launch_sincos_embed(timesteps_dev, g.timestep_scale_multiplier, c->se.as<float>(), B, 256, st);
-  launch_gemv(c->w_t1, c->b_t1, c->se.as<float>(), c->t1.as<float>(), B, D, 256, 0, st);
-  launch_gemv(c->w_t2, c->b_t2, c->t1.as<float>(), emb, B, D, D, 1, st);
-  launch_gemv(c->w_ada, c->b_ada, emb, ada, B, 6 * D, D, 1, st);
-  c->launches += 4;
+  {
+    ProfScope ps(c, PROF_OTHER, 2.0 * B * D * (256.0 + 7.0 * D), 2.0 * D * (256.0 + 7.0 * D), 4);
+    launch_sincos_embed(timesteps_dev, g.timestep_scale_multiplier, c->se.as<float>(), B, 256, st);
+    launch_gemv(c->w_t1, c->b_t1, c->se.as<float>(), c->t1.as<float>(), B, D, 256, 0, st);
+    launch_gemv(c->w_t2, c->b_t2, c->t1.as<float>(), emb, B, D, D, 1, st);
+    launch_gemv(c->w_ada, c->b_ada, emb, ada, B, 6 * D, D, 1, st);
+  }
 
   const int64_t ada_ld = 6 * static_cast<int64_t>(D);
   for (int i = 0; i < L; ++i) {
@@ -324,61 +347,59 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     const float cas = in_list(i, flags->cas_blocks, flags->n_cas_blocks) ? flags->cross_attn_scale : 1.0f;
     if (!skip_sa) {
       // h = rms(x) * (1 + scale_msa) + shift_msa      (T/LTXTransformerBlock.swift:72-83, rows 0/1 of table+ada)
-      launch_rmsnorm_mod(x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, N, eps, 0, st);
+      norm_mod(c, x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, N, eps, 0);
       GemmEpi e;
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
-      launch_gemm(h, D, bw.a1.wq, D, R, 2 * D, D, e, st);  // fused q|k projection
-      GemmEpi ev;
-      ev.mode = EPI_BF16; ev.out = vt; ev.ldo = ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
-      launch_gemm(bw.a1.wv, D, h, D, D, R, D, ev, st);  // V^T
-      launch_qknorm_rope(qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, st);
-      launch_qknorm_rope(qk + D, 2 * D, R, D, bw.a1.k_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, st);
-      launch_attention(qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale, st);
+      gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
+      for (int b = 0; b < B; ++b) {  // V^T, one column block per batch
+        GemmEpi ev;
+        ev.mode = EPI_BF16; ev.out = vt + b * ldv; ev.ldo = B * ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
+        gemm(c, bw.a1.wv, D, h + static_cast<int64_t>(b) * N * D, D, D, N, D, ev);
+      }
+      qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps);
+      qknorm(c, qk + D, 2 * D, R, D, bw.a1.k_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps);
+      attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
       GemmEpi eo;  // x += (att Wo^T + bo) * gate_msa ; refresh the bf16 shadow
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a1.bo;
       eo.gate_a = ada + 2 * D; eo.gate_b = bw.sst + 2 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
       eo.shadow = xb; eo.lds = D;
-      launch_gemm(att, D, bw.a1.wo, D, R, D, D, eo, st);
-      c->launches += 7;
+      gemm(c, att, D, bw.a1.wo, D, R, D, D, eo);
     }
     {
       // cross-attention on the UN-normalised stream (T/LTXTransformerBlock.swift:205-214)
       GemmEpi e;
       e.mode = EPI_BF16; e.out = q2; e.ldo = D; e.bias = bw.a2.bq;
-      launch_gemm(xb, D, bw.a2.wq, D, R, D, D, e, st);
-      launch_qknorm_rope(q2, D, R, D, bw.a2.q_norm, nullptr, nullptr, 1, eps, st);
+      gemm(c, xb, D, bw.a2.wq, D, R, D, D, e);
+      qknorm(c, q2, D, R, D, bw.a2.q_norm, nullptr, nullptr, 1, eps);
       const bf16* k2 = tc.k.as<bf16>() + static_cast<int64_t>(i) * B * S * D;
-      const bf16* v2 = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * tc.ldv;
-      launch_attention(q2, D, k2, D, v2, tc.ldv, key_bias, att, D, B, Hh, N, S, D, att_scale, st);
+      const bf16* v2 = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * B * tc.ldv;
+      attention(c, q2, D, k2, D, v2, tc.ldv, key_bias, att, D, B, Hh, N, S, D, att_scale);
       GemmEpi eo;
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a2.bo; eo.scale = cas;
       const bool next_needs_shadow = skip_ff && (i + 1 < L) &&
                                      in_list(i + 1, flags->stg_blocks, flags->n_stg_blocks) && flags->skip_self_attn;
       if (next_needs_shadow) { eo.shadow = xb; eo.lds = D; }
-      launch_gemm(att, D, bw.a2.wo, D, R, D, D, eo, st);
-      c->launches += 4;
+      gemm(c, att, D, bw.a2.wo, D, R, D, D, eo);
     }
     if (!skip_ff) {
-      launch_rmsnorm_mod(x, h, R, D, bw.sst + 3 * D, bw.sst + 4 * D, ada + 3 * D, ada + 4 * D, ada_ld, N, eps, 0, st);
+      norm_mod(c, x, h, R, D, bw.sst + 3 * D, bw.sst + 4 * D, ada + 3 * D, ada + 4 * D, ada_ld, N, eps, 0);
       GemmEpi e;
       e.mode = EPI_GELU_BF16; e.out = ffh; e.ldo = FFD; e.bias = bw.b_in;
-      launch_gemm(h, D, bw.w_in, D, R, FFD, D, e, st);
+      gemm(c, h, D, bw.w_in, D, R, FFD, D, e);
       GemmEpi eo;
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.b_out;
       eo.gate_a = ada + 5 * D; eo.gate_b = bw.sst + 5 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
       const bool next_needs_shadow =
           (i + 1 < L) && in_list(i + 1, flags->stg_blocks, flags->n_stg_blocks) && flags->skip_self_attn;
       if (next_needs_shadow) { eo.shadow = xb; eo.lds = D; }
-      launch_gemm(ffh, FFD, bw.w_out, FFD, R, D, FFD, eo, st);
-      c->launches += 3;
+      gemm(c, ffh, FFD, bw.w_out, FFD, R, D, FFD, eo);
     }
   }
   // ---- output head (T/LTXTransformer.swift:208-224): LayerNorm(no affine) * (1 + scale) + shift ; proj_out
-  launch_rmsnorm_mod(x, h, R, D, c->sst_out, c->sst_out + D, emb, emb, D, N, eps, 1, st);
+  norm_mod(c, x, h, R, D, c->sst_out, c->sst_out + D, emb, emb, D, N, eps, 1);
   GemmEpi e;
   e.mode = EPI_F32; e.out = out_velocity_dev; e.ldo = Cout; e.bias = c->b_out;
-  launch_gemm(h, D, c->w_out, D, R, Cout, D, e, st);
-  c->launches += 2;
+  gemm(c, h, D, c->w_out, D, R, Cout, D, e);
 }
 
 }  // namespace ltx

@@ -37,6 +37,9 @@ CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_
 // 4-D channels-last bf16 volume [T, H, W, C] (C fastest); box = [bt, bh, bw, 64 channels], 128B swizzle.
 CUtensorMap make_tmap_thwc(const void* base, uint64_t T, uint64_t H, uint64_t W, uint64_t C, uint32_t bt, uint32_t bh,
                            uint32_t bw);
+// 3-D bf16 tensor (d0 fastest); strides in elements; box = [box0 (64), box1, 1].
+CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                         uint32_t box0, uint32_t box1);
 int device_sm_count();
 
 // ---------------------------------------------------------------- GEMM (gemm.cu)
@@ -69,9 +72,9 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
                  cudaStream_t stream, int force_bn = 0);
 
 // ---------------------------------------------------------------- attention (attention.cu)
-// Q [B*Nq, D], K [B*Nk, D] bf16 (head h = columns h*128..h*128+127); Vt [D, ldv] bf16 (row h*128+d, column b*Nk+j);
-// key_bias: optional fp32 [B, Nk] additive logits bias; O [B*Nq, D] bf16.  softmax(q k^T * scale + bias) v.
-void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldv,
+// Q [B*Nq, D], K [B*Nk, D] bf16 (head h = columns h*128..h*128+127); Vt [D, B*ldvb] bf16 (row h*128+d, column
+// b*ldvb + j, ldvb % 8 == 0); key_bias: optional fp32 [B, Nk] additive logits bias; O [B*Nq, D] bf16.
+void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                       const float* key_bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
                       cudaStream_t stream);
 

@@ -57,6 +57,24 @@ CUtensorMap make_tmap_thwc(const void* base, uint64_t T, uint64_t H, uint64_t W,
   return m;
 }
 
+CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
+                         uint32_t box0, uint32_t box1) {
+  // bf16 tensor, dims (d0 fastest, d1, d2), strides in ELEMENTS for d1 / d2; box = [box0, box1, 1], 128B swizzle.
+  LTX_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, 2, "TMA base must be 16-byte aligned");
+  LTX_CHECK((stride1 * 2) % 16 == 0 && (stride2 * 2) % 16 == 0, 2, "TMA strides must be multiples of 16 bytes");
+  LTX_CHECK(box0 * 2 == 128 && box1 <= 256, 2, "TMA box: 128-byte inner extent, <= 256 rows");
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTX_CHECK(r == CUDA_SUCCESS, 3, "cuTensorMapEncodeTiled(3d) failed: " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {

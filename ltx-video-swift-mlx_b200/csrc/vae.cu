@@ -62,11 +62,15 @@ const float* vf(ltx_ctx* c, const std::string& k, int64_t n) {
 void conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
           int causal, int epi_mode, float* out, const float* resid) {
   c->v_pad.reserve(static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * w.cin * 2);
-  launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, causal, c->stream);
+  const double vox = static_cast<double>(T) * H * W;
+  {
+    ProfScope ps(c, PROF_PREP, 0.0, vox * w.cin * 4.0 + static_cast<double>(T + 2) * (H + 2) * (W + 2) * w.cin * 2.0);
+    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, causal, c->stream);
+  }
   ConvEpi e;
   e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin;
+  ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * w.cin * w.cout * vox, vox * (w.cin * 2.0 + w.cout * 4.0) + 27.0 * w.cin * w.cout * 2.0);
   launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream);
-  c->launches += 2;
 }
 
 }  // namespace
@@ -138,8 +142,10 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
   float* y = c->v_b.as<float>();
   float* hbuf = c->v_h.as<float>();
   // [C, T*H*W] -> channels-last [T*H*W, C]
-  launch_patchify(latent_dev, nullptr, hbuf, C0, T * H * W, st);
-  c->launches++;
+  {
+    ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * C0 * T * H * W);
+    launch_patchify(latent_dev, nullptr, hbuf, C0, T * H * W, st);
+  }
   // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
   conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr);
   int64_t ch = g.vae_base_channels;

@@ -1,0 +1,54 @@
+"""The generateVideo step loop (Pipeline/LTXPipeline.swift:793-956) over libltxcuda, in two forms:
+
+* `denoise_host_seam`  -- call-for-call what the Swift pipeline does at the three seams of SURVEY 8b: host latent ->
+  LTXTransformer(...) 1-3x per step -> guided Euler, all through host buffers (H2D/D2H every call).  This is the `e2e`
+  path of bench.py.
+* `denoise_resident`   -- the device-resident fast path (ltx_denoise_begin / ltx_denoise_step): latent, text caches and
+  GE state stay in HBM; one D2H at the end."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .context import LtxContext
+from .latent_utils import VideoLatentShape, patchify, unpatchify
+from .transformer import LTXTransformer
+
+
+def denoise_host_seam(ctx: LtxContext, noise: np.ndarray, context, mask, sigmas: Sequence[float], neg_context=None,
+                      neg_mask=None, cfg_scale: float = 1.0, guidance_rescale: float = 0.0, stg_scale: float = 0.0,
+                      stg_blocks: Sequence[int] = (29,), ge_gamma: float = 0.0, cache_text: bool = True) -> np.ndarray:
+    """noise [1,C,F,H,W] fp32 host.  Returns the final latent [1,C,F,H,W]."""
+    _, C, F, H, W = noise.shape
+    shape = VideoLatentShape(1, C, F, H, W)
+    tr = LTXTransformer(ctx)
+    latent = np.ascontiguousarray(noise.astype(np.float32) * np.float32(sigmas[0]))      # :793
+    v_prev = np.zeros_like(latent)
+    use_cfg = cfg_scale > 1.0 and neg_context is not None
+    for step in range(len(sigmas) - 1):
+        sg, sn = float(sigmas[step]), float(sigmas[step + 1])
+        tok = patchify(latent)                                                            # :815 (cast to bf16 on device)
+        ts = np.array([sg], dtype=np.float32)
+        vc = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=1 if cache_text else 0), shape)
+        vu = vs = None
+        if use_cfg:                                                                       # :829-848
+            vu = unpatchify(tr(tok, neg_context, ts, neg_mask, shape.fhw, context_key=2 if cache_text else 0), shape)
+        if stg_scale > 0:                                                                 # :897-921
+            tr.set_stg_skip_flags(True, False, stg_blocks)
+            vs = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=1 if cache_text else 0), shape)
+            tr.clear_stg_skip_flags()
+        ctx.guided_euler_step(latent, vc, vu, vs, v_prev, use_prev=step > 0, cfg_scale=cfg_scale,
+                              rescale_phi=guidance_rescale, stg_scale=stg_scale, ge_gamma=ge_gamma, sigma=sg, sigma_next=sn)
+    return latent
+
+
+def denoise_resident(ctx: LtxContext, noise: np.ndarray, context, mask, sigmas: Sequence[float], neg_context=None,
+                     neg_mask=None, cfg_scale: float = 1.0, guidance_rescale: float = 0.0, stg_scale: float = 0.0,
+                     stg_blocks: Sequence[int] = (29,), ge_gamma: float = 0.0, fetch: bool = True) -> Optional[np.ndarray]:
+    _, C, F, H, W = noise.shape
+    ctx.denoise_begin(noise[0], (F, H, W), float(sigmas[0]), context, mask, neg_context, neg_mask)
+    for step in range(len(sigmas) - 1):
+        ctx.denoise_step(float(sigmas[step]), float(sigmas[step + 1]), step, cfg_scale, guidance_rescale, stg_scale,
+                         tuple(stg_blocks) if stg_scale > 0 else (), ge_gamma)
+    return ctx.denoise_get_latent()[None] if fetch else None

@@ -1,0 +1,30 @@
+"""decodeVideo -- host mirror of Models/VAE/VideoDecoder.swift:466-508 over libltxcuda."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from ._lib import LtxError
+from .context import LtxContext
+
+
+class VideoDecoder:
+    """Handle on the decoder weights held by an LtxContext (VideoDecoder(), causal: false by default, :320)."""
+
+    def __init__(self, ctx: LtxContext, causal: bool = False):
+        self.ctx = ctx
+        self.causal = causal
+        self.timestep_conditioning = False
+
+
+def decode_video(latent, decoder: VideoDecoder, timestep: Optional[float] = None, temporal_tile_size: int = 0,
+                 temporal_tile_overlap: int = 1, decode_noise=None) -> np.ndarray:
+    """latent [1,128,F',H',W'] or [128,F',H',W'] fp32 -> frames [F,H,W,3] fp32 in [0,1].
+    The reference's temporal tiling (:517-602) is an approximation that is off by default (vaeTemporalTileSize 0,
+    Configuration/MemoryOptimizationConfig.swift:78-84); only the exact untiled decode is provided."""
+    lat = np.asarray(latent, dtype=np.float32)
+    frames_lat = lat.shape[-3]
+    if temporal_tile_size > 0 and frames_lat > temporal_tile_size:
+        raise LtxError(5, "temporal tiling (overlap-blend approximation) is not implemented; decode untiled")
+    return decoder.ctx.vae_decode(lat, timestep, decode_noise, decoder.causal)

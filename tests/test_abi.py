@@ -1,0 +1,57 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/ltxcuda.h declares, and fails loudly (no CPU
+fallback) when no device is present."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from helpers import ROOT, product
+
+product()
+from ltx_video_swift_mlx_b200 import _lib  # noqa: E402
+from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig  # noqa: E402
+
+HEADER = os.path.join(ROOT, "include", "ltxcuda.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ltx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (ltx_[a-z0-9_]+)", out))
+    assert set(syms) <= exported, sorted(set(syms) - exported)
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    assert lib.ltx_version().startswith(b"ltxcuda")
+
+
+def test_struct_layouts_match_header():
+    lib = _lib.load()
+    cfg = _lib.LtxConfig()
+    lib.ltx_config_default(ctypes.byref(cfg))
+    assert (cfg.num_layers, cfg.num_heads, cfg.head_dim, cfg.caption_channels) == (48, 32, 128, 3840)
+    assert list(cfg.max_pos) == [20, 2048, 2048] and cfg.vae_patch_size == 4 and abs(cfg.norm_eps - 1e-6) < 1e-12
+    assert ctypes.sizeof(_lib.LtxDitFlags) == 4 * (1 + 64 + 2 + 1 + 64 + 1) + 4 + 8   # incl. padding before the u64
+    assert ctypes.sizeof(_lib.LtxStepParams) == 4 * (6 + 1 + 64 + 1)
+
+
+def test_only_sm100_sass_in_library():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less host")
+def test_no_cpu_fallback():
+    with pytest.raises(_lib.LtxError) as e:
+        LtxContext(LTXTransformerConfig(), 0)
+    assert e.value.code == 3 and "no CPU fallback" in str(e.value)

@@ -29,9 +29,10 @@ def test_attention(ctx, B, H, Nq, Nk, masked):
     q = torch.randn(B * Nq, D, device="cuda", generator=g).bfloat16()
     k = torch.randn(B * Nk, D, device="cuda", generator=g).bfloat16()
     v = torch.randn(B * Nk, D, device="cuda", generator=g).bfloat16()
-    ldv = (B * Nk + 7) // 8 * 8
-    vt = torch.zeros(D, ldv, device="cuda", dtype=torch.bfloat16)
-    vt[:, : B * Nk] = v.t()
+    ldv = (Nk + 7) // 8 * 8                      # per-batch pitch; padding columns hold NaN on purpose (never read)
+    vt = torch.full((D, B * ldv), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for b in range(B):
+        vt[:, b * ldv: b * ldv + Nk] = v[b * Nk:(b + 1) * Nk].t()
     bias = None
     if masked:
         m = (torch.rand(B, Nk, device="cuda", generator=g) > 0.3).float()

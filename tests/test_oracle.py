@@ -1,0 +1,141 @@
+"""CPU checks of the oracle itself: known-answer constants from the reference's sources, closed-form cases, the
+committed golden fixtures (regression pin of our restatement) and fp32-vs-fp64 self-consistency."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_sigma_tables_match_reference_constants():
+    # S/LTXScheduler.swift:18-36 literal tables
+    assert O.DISTILLED_SIGMA_VALUES == [1.0, 0.99375, 0.9875, 0.98125, 0.975, 0.909375, 0.725, 0.421875, 0.0]
+    assert O.STAGE_2_DISTILLED_SIGMA_VALUES == O.DISTILLED_SIGMA_VALUES[5:]
+    # without a token count the distilled schedule is the raw table (:104-106)
+    assert np.allclose(O.set_timesteps(8, True, None), O.DISTILLED_SIGMA_VALUES)
+
+
+def test_sigma_kats_from_survey():
+    # values obtained by executing S/LTXScheduler.swift:74-182 in float32
+    kat = {512: [1, .99326, .986474, .979642, .972764, .897623, .653374, .1, 0],
+           1536: [1, .994059, .988067, .982024, .975929, .908606, .680049, .1, 0],
+           6144: [1, .995145, .990236, .985273, .980255, .923979, .720582, .1, 0]}
+    for n, want in kat.items():
+        assert np.allclose(O.set_timesteps(8, True, n), want, atol=2e-6)
+    dev = O.set_timesteps(40, False, 1536)
+    assert len(dev) == 41 and np.allclose(dev[:4], [1, .99204, .98381, .97528], atol=1e-5)
+    assert np.allclose(dev[-3:], [.16485, .1, 0], atol=1e-5)
+    g = np.load(os.path.join(GOLD, "sigmas.npz"))
+    assert np.array_equal(g["distilled_1536"], np.array(O.set_timesteps(8, True, 1536)))
+    assert np.array_equal(g["dev40_1536"], np.array(dev))
+
+
+def test_latent_geometry():
+    # P/VideoLatentShape.swift:35-41 ; frame formula 8(F'-1)+1 (V/VideoDecoder.swift:294)
+    assert O.latent_shape(25, 512, 768) == (4, 16, 24)
+    assert O.latent_shape(121, 512, 768) == (16, 16, 24)
+    assert O.latent_shape(9, 512, 512) == (2, 16, 16)
+    x = torch.arange(2 * 3 * 2 * 4 * 5, dtype=torch.float32).view(2, 3, 2, 4, 5)
+    assert torch.equal(O.unpatchify(O.patchify(x), (2, 4, 5)), x)
+
+
+def test_rope_table_structure():
+    cfg = O.DiTConfig()
+    cos, sin = O.rope_table(cfg, 2, 3, 4)
+    assert cos.shape == (32, 24, 64) and sin.shape == (32, 24, 64)
+    # the two left-pad entries are the identity rotation (T/LTXRoPE.swift:451-476) and land in head 0
+    assert torch.all(cos[0, :, :2] == 1) and torch.all(sin[0, :, :2] == 0)
+    assert torch.allclose(cos ** 2 + sin ** 2, torch.ones_like(cos), atol=1e-6)
+    # first real frequency: idx_0 = pi/2 times the t position scaled to [-1, 1]
+    grid = O.position_grid(2, 3, 4)
+    st = 2 * (grid[0].double() / 20) - 1
+    assert torch.allclose(cos[0, :, 2].double(), torch.cos(st * math.pi / 2), atol=1e-6)
+    # rotation by the identity leaves padded channels untouched
+    x = torch.randn(1, 24, 4096)
+    y = O.apply_split_rope(x, cos, sin, 32)
+    assert torch.equal(y[0, :, :2], x[0, :, :2]) and torch.equal(y[0, :, 64:66], x[0, :, 64:66])
+    assert torch.allclose(y.norm(), x.norm(), rtol=1e-5)
+
+
+def test_guidance_closed_forms():
+    g = torch.Generator().manual_seed(0)
+    x, vc, vu = [torch.randn(1, 8, 2, 3, 4, generator=g) for _ in range(3)]
+    out, v = O.guided_euler_step(x, vc, None, None, None, 1.0, 0, 0, 0, 0.5, 0.0)
+    assert torch.allclose(out, x - 0.5 * vc)                      # sigma' = 0 returns the denoised sample
+    assert torch.equal(O.apply_cfg(vu, vc, 1.0), vc)              # scale 1 returns cond
+    r = O.guidance_rescale(O.apply_cfg(vu, vc, 4.0), vc, 1.0)     # phi = 1: std of the result equals std of cond
+    assert abs(float(r.std(unbiased=False)) - float(vc.std(unbiased=False))) < 1e-4
+    out2, _ = O.guided_euler_step(x, vc, None, None, None, 1.0, 0, 0, 0, 0.5, 0.25)
+    assert torch.allclose(out2, x + (0.25 - 0.5) * vc, atol=1e-6)  # Euler: x + (sigma' - sigma) v
+    gd = np.load(os.path.join(GOLD, "guidance.npz"))
+    o, vv = O.guided_euler_step(*[torch.from_numpy(gd[k]) for k in ("x", "vc", "vu", "vs", "vp")], 4.0, 0.7, 0.5, 0.3, 0.8, 0.6)
+    assert np.allclose(o.numpy(), gd["out"], atol=1e-6) and np.allclose(vv.numpy(), gd["v"], atol=1e-6)
+
+
+def test_conv3d_full_equals_three_conv2d_slices():
+    # the reference executes the 3x3x3 conv as 3 conv2d calls over shifted temporal slices (V/VideoConvolution.swift:310-339)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 6, 4, 5, 7, generator=g)
+    w = torch.randn(8, 6, 3, 3, 3, generator=g)
+    b = torch.randn(8, generator=g)
+    for causal in (False, True):
+        ref = O.conv3d_full(x, w, b, causal)
+        xp = torch.nn.functional.pad(x.reshape(1, 24, 5, 7), (1, 1, 1, 1), mode="reflect").view(1, 6, 4, 7, 9)
+        xp = torch.cat([xp[:, :, :1]] * (2 if causal else 1) + [xp] + ([] if causal else [xp[:, :, -1:]]), 2)
+        acc = 0
+        for kt in range(3):
+            sl = xp[:, :, kt:kt + 4].permute(0, 2, 1, 3, 4).reshape(4, 6, 7, 9)
+            acc = acc + torch.nn.functional.conv2d(sl, w[:, :, kt])
+        got = acc.view(1, 4, 8, 5, 7).permute(0, 2, 1, 3, 4) + b.view(1, -1, 1, 1, 1)
+        assert torch.allclose(ref, got, atol=1e-4)
+
+
+def test_d2s_and_unpatchify_are_permutations():
+    x = torch.arange(1 * 16 * 2 * 3 * 4, dtype=torch.float32).view(1, 16, 2, 3, 4)
+    y = O.depth_to_space(x, 2)
+    assert y.shape == (1, 2, 4, 6, 8) and torch.equal(y.flatten().sort().values, x.flatten())
+    # channel c*8 + p1*4 + p2*2 + p3 lands at (2t+p1, 2h+p2, 2w+p3)
+    assert y[0, 1, 2 * 1 + 1, 2 * 2 + 0, 2 * 3 + 1] == x[0, 1 * 8 + 1 * 4 + 0 * 2 + 1, 1, 2, 3]
+    z = torch.arange(1 * 48 * 2 * 3 * 4, dtype=torch.float32).view(1, 48, 2, 3, 4)
+    u = O.vae_unpatchify(z, 4)
+    assert u.shape == (1, 3, 2, 12, 16)
+    # channel c*16 + pa*4 + pb lands at row 4h + pb, column 4w + pa (pW before pH, V/VideoDecoder.swift:270-272)
+    assert u[0, 2, 1, 4 * 2 + 3, 4 * 1 + 2] == z[0, 2 * 16 + 2 * 4 + 3, 1, 2, 1]
+
+
+def test_dit_oracle_golden_and_fp64():
+    g = np.load(os.path.join(GOLD, "dit_small.npz"))
+    cfg = O.DiTConfig(num_layers=2, num_heads=2, head_dim=128, caption_channels=192)
+    w = O.make_dit_weights(cfg, 1234)
+    args = (torch.from_numpy(g["latent"]), torch.from_numpy(g["context"]), torch.from_numpy(g["sigma"]),
+            torch.from_numpy(g["mask"]), (2, 4, 6))
+    vel = O.dit_forward(w, cfg, *args)
+    assert O.rel_l2(vel, torch.from_numpy(g["velocity"])) < 1e-5
+    v64 = O.dit_forward(w, cfg, *args, dtype=torch.float64)
+    assert O.rel_l2(vel, v64) < 1e-4                     # fp32 oracle is within the fp32-mode tolerance of fp64
+    stg = O.dit_forward(w, cfg, *args, stg_blocks=[1], skip_self_attn=True)
+    assert O.rel_l2(stg, torch.from_numpy(g["velocity_stg"])) < 1e-5
+    assert O.rel_l2(stg, vel) > 1e-2                     # the perturbed pass really differs
+    # mask semantic: additive -10000 on padded keys == dropping those keys
+    m0 = args[3].clone()
+    keep = m0[0].bool()
+    dropped = O.dit_forward(w, cfg, args[0], args[1][:, keep], args[2], None, (2, 4, 6))
+    assert O.rel_l2(vel, dropped) < 1e-5
+
+
+def test_vae_oracle_golden():
+    g = np.load(os.path.join(GOLD, "vae_small.npz"))
+    cfg = O.VAEConfig(base_channels=512, blocks_per_stage=1)
+    w = O.make_vae_weights(cfg, 99)
+    w = {k: (O.bf16_round(v) if k.endswith("conv.weight") else v) for k, v in w.items()}
+    fr = O.decode_video(w, cfg, torch.from_numpy(g["latent"]))
+    assert fr.shape == (9, 64, 96, 3) and float(fr.min()) >= 0 and float(fr.max()) <= 1
+    assert O.psnr(fr, torch.from_numpy(g["frames"].astype(np.float32))) > 55      # fixture stored as fp16
+    # frame count formula and the causal switch
+    cfg_c = O.VAEConfig(base_channels=512, blocks_per_stage=1, causal=True)
+    assert O.psnr(O.decode_video(w, cfg_c, torch.from_numpy(g["latent"])), fr) < 50
