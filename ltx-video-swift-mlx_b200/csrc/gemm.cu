@@ -9,6 +9,12 @@
 //                               two accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1
 //   warps 2-5: epilogue      -- tcgen05.ld (thread = output row, 32 columns at a time) -> bias / GELU / gate*residual
 // Edges: TMA zero-fills out-of-bounds rows/columns (M, N, K tails); the epilogue masks rows >= M and columns >= N.
+//
+// Tile width BN is a RUNTIME parameter (any multiple of 16 in [32, 256]: it only changes the TMA box, the UMMA
+// instruction descriptor and the epilogue trip count).  The launcher picks the width that fits the output into whole
+// waves of 148 CTAs ("wave-fitted" tiles): at M = 1536 an N = 4096 GEMM runs as 12 x 24 tiles of 128x176 (2 waves, 97 %
+// full) instead of 12 x 16 tiles of 128x256 (2 waves, 65 % full); N = 8192 / 16384 use 128x224 (3 / 6 waves, 99 % full).
+// A stream-K variant (split last wave + fp32 partial fix-up) was measured slower than this on B200 and was dropped.
 #include "ltx_internal.h"
 #include "ptx.cuh"
 
@@ -20,22 +26,23 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 
-template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = 4;
+  static constexpr int BN_MAX = 256;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512
-  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16;
+  static constexpr uint32_t B_STRIDE = BN_MAX * BK * 2;  // smem stage pitch of the B ring (a stage holds bn <= 256 rows)
+  static constexpr uint32_t TMEM_COLS = 512;             // two accumulator stages of up to 256 columns
+  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_STRIDE) + (2 * STAGES + 4) * 8 + 16;
 };
 
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, int M, int N,
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row, int col0, int ncols, int M, int N,
                                                const GemmEpi& ep) {
-  // One thread owns `row`, columns [col0, col0+32).
+  // One thread owns `row`, columns [col0, col0+ncols), ncols = 32 (or 16 for the tail chunk of a tile).
   if (row >= M || col0 >= N) return;
   const float rowbias = (ep.bias && ep.bias_per_row) ? ep.bias[row] : 0.0f;
-  const bool full = (col0 + 32 <= N);
+  const bool full = (col0 + ncols <= N);   // whole chunk in range -> vector path (ncols is 16 or 32)
+  if (col0 + ncols < N) N = col0 + ncols;  // never touch the next tile's columns from a 16-wide tail chunk
   if (MODE == EPI_GATE_RESID) {
     float* xr = ep.resid + static_cast<int64_t>(row) * ep.ldr + col0;
     const float* ga = ep.gate_a ? ep.gate_a + static_cast<int64_t>(row / ep.rows_per_gate) * ep.gate_ld + col0 : nullptr;
@@ -44,6 +51,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
+        if (j >= ncols) break;
         float4 xv = *reinterpret_cast<const float4*>(xr + j);
         float4 bv = (ep.bias && !ep.bias_per_row) ? *reinterpret_cast<const float4*>(ep.bias + col0 + j)
                                                   : make_float4(rowbias, rowbias, rowbias, rowbias);
@@ -79,6 +87,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
+        if (j >= ncols) break;
         float4 bv = (ep.bias && !ep.bias_per_row) ? *reinterpret_cast<const float4*>(ep.bias + col0 + j)
                                                   : make_float4(rowbias, rowbias, rowbias, rowbias);
         float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
@@ -96,6 +105,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
+        if (j >= ncols) break;
         float v[8];
 #pragma unroll
         for (int t = 0; t < 8; t += 4) {
@@ -124,17 +134,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
   }
 }
 
-template <int BN, int MODE>
+template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                  const GemmEpi ep) {
-  using Cfg = GemmCfg<BN>;
+                  int BN, const GemmEpi ep) {
+  using Cfg = GemmCfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STRIDE);
+  const uint32_t b_bytes = static_cast<uint32_t>(BN) * BK * 2;
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -174,16 +185,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m_blk = tile % num_m, n_blk = tile / num_m;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + b_bytes);
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+          tma_load_2d(sB + stage * Cfg::B_STRIDE, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -192,12 +203,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t aphase = (t >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * Cfg::BN_MAX;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STRIDE);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
@@ -219,13 +230,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::BN_MAX;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, M, N, ep);
+        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
+      }
+      if (BN & 16) {  // 16-column tail chunk of a tile whose width is an odd multiple of 16
+        uint32_t r[32];
+        tmem_ld16(taddr + (BN & ~31), r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
       }
       tc_fence_before();
       __syncwarp();
@@ -241,32 +258,37 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int BN, int MODE>
-void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpi& epi,
+template <int MODE>
+void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, const GemmEpi& epi,
                  cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg;
   static bool configured = false;
-  auto kern = gemm_bf16_tcgen05<BN, MODE>;
+  auto kern = gemm_bf16_tcgen05<MODE>;
   if (!configured) {
     LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM)));
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, epi);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, BN, epi);
   LTX_CUDA(cudaGetLastError());
 }
 
-template <int BN>
-void launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpi& epi,
-               cudaStream_t stream) {
-  switch (epi.mode) {
-    case EPI_BF16: launch_impl<BN, EPI_BF16>(tmA, tmB, M, N, K, epi, stream); break;
-    case EPI_GELU_BF16: launch_impl<BN, EPI_GELU_BF16>(tmA, tmB, M, N, K, epi, stream); break;
-    case EPI_GATE_RESID: launch_impl<BN, EPI_GATE_RESID>(tmA, tmB, M, N, K, epi, stream); break;
-    case EPI_F32: launch_impl<BN, EPI_F32>(tmA, tmB, M, N, K, epi, stream); break;
-    default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
+// Tile width that minimises (waves x width): time ~ ceil(tiles / #SM) * (BN + c0), c0 = fixed per-tile cost in columns.
+int fit_tile_width(int M, int N, int sms) {
+  const int num_m = (M + BM - 1) / BM;
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 16) {
+    const int num_n = (N + bn - 1) / bn;
+    const long long tiles = static_cast<long long>(num_m) * num_n;
+    const long long waves = (tiles + sms - 1) / sms;
+    // narrow tiles re-read A more often and are smem-bandwidth bound below ~176 columns: penalise them mildly
+    const double eff = bn >= 176 ? 1.0 : (bn >= 128 ? 0.92 : 0.75);
+    const double cost = static_cast<double>(waves) * (bn + 12.0) / eff;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
+  return best;
 }
 
 }  // namespace
@@ -282,26 +304,19 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
     LTX_CHECK(epi.out != nullptr, 2, "GEMM: missing output");
     LTX_CHECK(epi.ldo % (epi.mode == EPI_F32 ? 4 : 8) == 0, 2, "GEMM: output ld alignment");
   }
-  // Tile-shape heuristic: 128x256 tiles halve the per-flop smem traffic; fall back to 128x128 when the 256-wide
-  // grid would leave most SMs idle or waste a large tail wave.
+  // force_bn: 0 = wave-fitted width (see fit_tile_width); otherwise a multiple of 16 in [32, 256]
   int bn = force_bn;
-  if (bn == 0) {
-    const int sms = device_sm_count();
-    const int mt = (M + BM - 1) / BM;
-    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
-    auto waves_eff = [&](int tiles) { return static_cast<double>(tiles) / (((tiles + sms - 1) / sms) * sms); };
-    // cost model: time ~ waves * tile_cost ; 128x256 tile costs 2 units at ~1.0 efficiency, 128x128 costs 1 unit at ~0.85
-    const double c256 = ((t256 + sms - 1) / sms) * 2.0;
-    const double c128 = ((t128 + sms - 1) / sms) * 1.0 / 0.85;
-    (void)waves_eff;
-    bn = (N >= 256 && c256 <= c128) ? 256 : 128;
-  }
+  if (bn == 0) bn = fit_tile_width(M, N, device_sm_count());
+  LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "GEMM: tile width must be a multiple of 16 in [32, 256]");
   CUtensorMap tmA = make_tmap_2d(A, M, K, lda, BM);
   CUtensorMap tmB = make_tmap_2d(B, N, K, ldb, bn);
-  if (bn == 256)
-    launch_bn<256>(tmA, tmB, M, N, K, epi, stream);
-  else
-    launch_bn<128>(tmA, tmB, M, N, K, epi, stream);
+  switch (epi.mode) {
+    case EPI_BF16: launch_impl<EPI_BF16>(tmA, tmB, M, N, K, bn, epi, stream); break;
+    case EPI_GELU_BF16: launch_impl<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, epi, stream); break;
+    case EPI_GATE_RESID: launch_impl<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, epi, stream); break;
+    case EPI_F32: launch_impl<EPI_F32>(tmA, tmB, M, N, K, bn, epi, stream); break;
+    default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
+  }
 }
 
 }  // namespace ltx

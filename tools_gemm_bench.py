@@ -1,0 +1,39 @@
+"""Micro-benchmark of the tcgen05 GEMM on the DiT shapes (device time via CUDA events on the library stream)."""
+import math, sys, torch
+sys.path.insert(0, ".")
+import ltx_video_swift_mlx_b200  # noqa
+from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
+
+ctx = LtxContext(LTXTransformerConfig(num_layers=1, num_attention_heads=1), 0)
+stream = torch.cuda.ExternalStream(ctx.stream)
+shapes = [("qk", 1536, 8192, 4096, 0), ("vT", 4096, 1536, 4096, 0), ("out", 1536, 4096, 4096, 2), ("ffn_in", 1536, 16384, 4096, 1),
+          ("ffn_out", 1536, 4096, 16384, 2), ("proj_out", 1536, 128, 4096, 3), ("big", 8192, 8192, 8192, 0)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for name, M, N, K, mode in shapes:
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+    bias = torch.randn(max(M, N), device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    x = torch.zeros(M, N, device="cuda")
+    g = torch.ones(N, device="cuda")
+    for bn in ([0, 256, 224, 192, 176, 128] if N > 128 else [0, 128, 64, 32]):
+        def run():
+            if mode == 2:
+                ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                                     g.data_ptr(), g.data_ptr(), None, M, N, K, 0.5))
+            else:
+                ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn))
+        if mode == 2 and bn != 0:
+            continue
+        for _ in range(3):
+            run()
+        ctx.sync()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); run(); e1.record(stream); ctx.sync(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        print(f"{name:9s} M={M} N={N} K={K} mode={mode} bn={bn:5d}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
