@@ -32,9 +32,10 @@ void norm_mod(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* 
   launch_rmsnorm_mod(x, out, M, D, ts, tsc, as, asc, ada_ld, rows_per_mod, eps, ln, c->stream);
 }
 void qknorm(ltx_ctx* c, bf16* x, int64_t ld, int M, int D, const float* w, const float* cs, const float* sn, int rpr,
-            float eps) {
-  ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)));
-  launch_qknorm_rope(x, ld, M, D, w, cs, sn, rpr, eps, c->stream);
+            float eps, const float* w_second = nullptr) {
+  const int segs = w_second ? 2 : 1;
+  ProfScope ps(c, PROF_ROW, 0.0, segs * static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)), (D == 4096) ? 1 : segs);
+  launch_qknorm_rope(x, ld, M, D, w, cs, sn, rpr, eps, c->stream, w_second);
 }
 
 const bf16* wbf(ltx_ctx* c, const std::string& k, int64_t r, int64_t cc) {
@@ -163,8 +164,16 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
       gemm(c, a.wv, D, c->c2.as<bf16>() + static_cast<int64_t>(b) * S * D, D, D, S, D, ev);
     }
   }
-  tc.has_bias = mask_dev != nullptr;
+  // An all-ones mask (what the real text connector emits, LTXTextEncoder.swift:514-520) adds a zero bias: skip it.
+  bool any_masked = false;
   if (mask_dev) {
+    std::vector<int32_t> hm(static_cast<size_t>(R));
+    LTX_CUDA(cudaMemcpyAsync(hm.data(), mask_dev, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, st));
+    LTX_CUDA(cudaStreamSynchronize(st));
+    for (int32_t v : hm) any_masked |= (v == 0);
+  }
+  tc.has_bias = any_masked;
+  if (any_masked) {
     tc.bias.reserve(static_cast<size_t>(R) * 4);
     ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * R);
     launch_mask_to_bias(mask_dev, tc.bias.as<float>(), static_cast<int>(R), st);
@@ -356,8 +365,7 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
         ev.mode = EPI_BF16; ev.out = vt + b * ldv; ev.ldo = B * ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
         gemm(c, bw.a1.wv, D, h + static_cast<int64_t>(b) * N * D, D, D, N, D, ev);
       }
-      qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps);
-      qknorm(c, qk + D, 2 * D, R, D, bw.a1.k_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps);
+      qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, bw.a1.k_norm);
       attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
       GemmEpi eo;  // x += (att Wo^T + bo) * gate_msa ; refresh the bf16 shadow
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a1.bo;

@@ -74,6 +74,72 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_kernel(const float* __restric
   }
 }
 
+// Fast path: D == 4 * VPT * 256.  Each thread keeps its VPT float4 column groups of the row in registers (one global
+// read), and its slice of the combined modulation vectors stays in registers across the ROWS rows a CTA processes
+// (the generic kernel re-read 4 x 16 KB of table/ada vectors from L2 per row, 2.7x the row's own HBM traffic).
+template <int VPT, int ROWS>
+__global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* __restrict__ x, bf16* __restrict__ out, int M,
+                                                                const float* __restrict__ tbl_shift,
+                                                                const float* __restrict__ tbl_scale,
+                                                                const float* __restrict__ ada_shift,
+                                                                const float* __restrict__ ada_scale, int64_t ada_ld,
+                                                                int rows_per_mod, float eps, int layernorm) {
+  __shared__ float red[33];
+  constexpr int D = 4 * VPT * 256;
+  const int row0 = blockIdx.x * ROWS;
+  int cur_mod = -1;
+  float4 sc[VPT], sh[VPT];
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int row = row0 + rr;
+    if (row >= M) break;   // uniform across the CTA
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
+    float4 v[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) v[k] = xr[threadIdx.x + k * 256];
+    const int mod = row / rows_per_mod;
+    if (mod != cur_mod) {
+      cur_mod = mod;
+      const int64_t aoff = static_cast<int64_t>(mod) * ada_ld;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const float4 a = reinterpret_cast<const float4*>(tbl_scale)[i], b = reinterpret_cast<const float4*>(ada_scale + aoff)[i];
+        const float4 c = reinterpret_cast<const float4*>(tbl_shift)[i], d = reinterpret_cast<const float4*>(ada_shift + aoff)[i];
+        sc[k] = make_float4(1.f + a.x + b.x, 1.f + a.y + b.y, 1.f + a.z + b.z, 1.f + a.w + b.w);
+        sh[k] = make_float4(c.x + d.x, c.y + d.y, c.z + d.z, c.w + d.w);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      s1 += v[k].x + v[k].y + v[k].z + v[k].w;
+      s2 += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+    float mean = 0.f, rstd;
+    if (layernorm) {
+      mean = block_sum(s1, red) / D;
+      float sv = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        sv += a * a + b * b + c * c + d * d;
+      }
+      rstd = rsqrtf(block_sum(sv, red) / D + eps);
+    } else {
+      rstd = rsqrtf(block_sum(s2, red) / D + eps);
+    }
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(row) * D);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const float y0 = (v[k].x - mean) * rstd * sc[k].x + sh[k].x;
+      const float y1 = (v[k].y - mean) * rstd * sc[k].y + sh[k].y;
+      const float y2 = (v[k].z - mean) * rstd * sc[k].z + sh[k].z;
+      const float y3 = (v[k].w - mean) * rstd * sc[k].w + sh[k].w;
+      orow[threadIdx.x + k * 256] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // q/k RMSNorm across all heads (learned weight) + split RoPE, in place on bf16 rows.
 // T/LTXAttention.swift:179-189, T/LTXRoPE.swift:84-149.  cos/sin: [rows_per_rope, D/2] fp32, index h*64 + j.
@@ -127,6 +193,73 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, 
     } else {
 #pragma unroll
       for (int t = 0; t < 8; ++t) { y1[t] = x1[t]; y2[t] = x2[t]; }
+    }
+    *reinterpret_cast<uint4*>(xr + c1) =
+        make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
+    *reinterpret_cast<uint4*>(xr + c2) =
+        make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
+  }
+}
+
+// Fast path: D == 16 * 256 -> exactly one (x1, x2) pair-chunk per thread, kept in registers between the reduction and the
+// rotation (one global read); the learned weight slice stays in registers across the ROWS rows of a CTA; blockIdx.y
+// selects the segment (q | k of the fused projection: column offset seg * D, weight w0 / w1) so both norms are one launch.
+template <int ROWS>
+__global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict__ x, int64_t ld, int M,
+                                                                const float* __restrict__ w0, const float* __restrict__ w1,
+                                                                const float* __restrict__ cosb, const float* __restrict__ sinb,
+                                                                int rows_per_rope, float eps) {
+  __shared__ float red[33];
+  constexpr int D = 4096;
+  const int seg = blockIdx.y;
+  const float* w = seg == 0 ? w0 : w1;
+  const int hh = threadIdx.x >> 3, jc = (threadIdx.x & 7) * 8;
+  const int c1 = hh * 128 + jc, c2 = c1 + 64;
+  float wa[8], wb[8];
+#pragma unroll
+  for (int t = 0; t < 8; t += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(w + c1 + t), b = *reinterpret_cast<const float4*>(w + c2 + t);
+    wa[t] = a.x; wa[t + 1] = a.y; wa[t + 2] = a.z; wa[t + 3] = a.w;
+    wb[t] = b.x; wb[t + 1] = b.y; wb[t + 2] = b.z; wb[t + 3] = b.w;
+  }
+  const int row0 = blockIdx.x * ROWS;
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const int row = row0 + rr;
+    if (row >= M) break;
+    bf16* xr = x + static_cast<int64_t>(row) * ld + static_cast<int64_t>(seg) * D;
+    const uint4 u1 = *reinterpret_cast<const uint4*>(xr + c1);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(xr + c2);
+    float cs[8], sn[8];
+    if (cosb) {
+      const int64_t fo = static_cast<int64_t>(row % rows_per_rope) * (D >> 1) + hh * 64 + jc;
+#pragma unroll
+      for (int t = 0; t < 8; t += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(cosb + fo + t), b = *reinterpret_cast<const float4*>(sinb + fo + t);
+        cs[t] = a.x; cs[t + 1] = a.y; cs[t + 2] = a.z; cs[t + 3] = a.w;
+        sn[t] = b.x; sn[t + 1] = b.y; sn[t + 2] = b.z; sn[t + 3] = b.w;
+      }
+    }
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2);
+    float x1[8], x2[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = __bfloat1622float2(a2[t]), fb = __bfloat1622float2(b2[t]);
+      x1[2 * t] = fa.x; x1[2 * t + 1] = fa.y; x2[2 * t] = fb.x; x2[2 * t + 1] = fb.y;
+      ss += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+    }
+    const float rstd = rsqrtf(block_sum(ss, red) / D + eps);
+    float y1[8], y2[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float a = x1[t] * rstd * wa[t], b = x2[t] * rstd * wb[t];
+      if (cosb) {
+        y1[t] = a * cs[t] - b * sn[t];
+        y2[t] = b * cs[t] + a * sn[t];
+      } else {
+        y1[t] = a; y2[t] = b;
+      }
     }
     *reinterpret_cast<uint4*>(xr + c1) =
         make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
@@ -343,16 +476,37 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
                         const float* ada_shift, const float* ada_scale, int64_t ada_ld, int rows_per_mod, float eps,
                         int layernorm, cudaStream_t s) {
   LTX_CHECK(D % 4 == 0 && M > 0 && ada_ld % 4 == 0, 2, "rmsnorm_mod: D must be a multiple of 4");
+  if (D == 4096) {
+    constexpr int ROWS = 4;
+    rmsnorm_mod_fast_kernel<4, ROWS><<<(M + ROWS - 1) / ROWS, 256, 0, s>>>(x, out, M, tbl_shift, tbl_scale, ada_shift, ada_scale,
+                                                                          ada_ld, rows_per_mod > 0 ? rows_per_mod : 1, eps,
+                                                                          layernorm);
+    LTX_CUDA(cudaGetLastError());
+    return;
+  }
   rmsnorm_mod_kernel<<<M, 256, 0, s>>>(x, out, D, tbl_shift, tbl_scale, ada_shift, ada_scale, ada_ld,
                                        rows_per_mod > 0 ? rows_per_mod : 1, eps, layernorm);
   LTX_CUDA(cudaGetLastError());
 }
 
 void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
-                        int rows_per_rope, float eps, cudaStream_t s) {
+                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second) {
+  // w_second != nullptr: also normalise the second segment x[:, D:2D] with that weight (fused q|k projection output)
   LTX_CHECK(D % 128 == 0 && ld % 8 == 0 && M > 0, 2, "qknorm_rope: D must be a multiple of 128");
-  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rows_per_rope > 0 ? rows_per_rope : 1, eps);
+  const int rpr = rows_per_rope > 0 ? rows_per_rope : 1;
+  if (D == 4096) {
+    constexpr int ROWS = 4;
+    dim3 grid((M + ROWS - 1) / ROWS, w_second ? 2 : 1);
+    qknorm_rope_fast_kernel<ROWS><<<grid, 256, 0, s>>>(x, ld, M, w, w_second, cosb, sinb, rpr, eps);
+    LTX_CUDA(cudaGetLastError());
+    return;
+  }
+  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps);
   LTX_CUDA(cudaGetLastError());
+  if (w_second) {
+    qknorm_rope_kernel<<<M, 256, 0, s>>>(x + D, ld, D, w_second, cosb, sinb, rpr, eps);
+    LTX_CUDA(cudaGetLastError());
+  }
 }
 
 void launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s) {

@@ -85,8 +85,9 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
                         const float* ada_shift, const float* ada_scale, int64_t ada_ld, int rows_per_mod, float eps,
                         int layernorm, cudaStream_t s);
 // In place on bf16 [M, ld]: y = rms(x[:, :D]) * w, then optional split-RoPE with cos/sin [rows_per_rope, D/2] (token-major).
+// w_second != nullptr: the same for the second segment x[:, D:2D] with that weight (q | k of the fused projection).
 void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
-                        int rows_per_rope, float eps, cudaStream_t s);
+                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second = nullptr);
 void launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s);
 void launch_cast_bf16_f32(const bf16* in, float* out, int64_t n, cudaStream_t s);
 // y[o] = act_out( sum_i W[o,i] * act_in(x[i]) + b[o] ), bf16 W [O,I]; tiny-M path for the timestep MLP (M rows).

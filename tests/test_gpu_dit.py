@@ -23,6 +23,7 @@ def _inputs(ocfg, fhw, S, seed, B=1, mask_prefix=0):
 
 @pytest.mark.parametrize("layers,heads,fhw,S,B,mask_prefix", [
     (2, 2, (2, 4, 6), 40, 1, 7), (3, 4, (4, 8, 10), 150, 1, 0), (2, 2, (1, 4, 4), 24, 2, 5),
+    (1, 32, (2, 4, 6), 40, 1, 7),    # full LTX-2 width (D = 4096): exercises the D-specialised row kernels
 ])
 def test_dit_forward_matches_oracle(layers, heads, fhw, S, B, mask_prefix):
     ocfg, pcfg = small_dit_config(layers, heads)
