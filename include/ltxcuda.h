@@ -151,6 +151,21 @@ int ltx_vae_decode(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, fl
 int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep,
                        const float* decode_noise, int causal, float* out_frames);
 
+/* ---- multi-GPU: one process and one context per GPU of an NVLink/NVSwitch box; NCCL communicators are owned by the context.
+ * The reference has no multi-device code; correctness contract: N-GPU result == 1-GPU result.
+ *   world_size = pass_groups * sp_size, rank = group * sp_size + sp_rank.
+ *   sp_size     : Ulysses sequence parallelism of ltx_dit_forward* / ltx_denoise_step (tokens sharded over the sp ranks for
+ *                 row-wise ops, heads sharded inside self-attention, NCCL all-to-all in between); must divide num_heads and N.
+ *                 Every rank passes the full inputs and receives the full velocity.
+ *   pass_groups : ltx_denoise_step runs pass p (conditional, unconditional, STG) on group p % pass_groups and broadcasts
+ *                 the velocities; the guided Euler update is replicated.
+ *   ltx_vae_decode* shards the latent frames in contiguous temporal slabs over all ranks, exchanging one boundary frame
+ *   per convolution with each neighbour (exact, unlike the reference's overlap-blend tiling); every rank gets all frames.
+ * ltx_dist_get_unique_id fills a 128-byte NCCL id on one rank; the caller ships it to the others (torch.distributed, MPI, ...). */
+int ltx_dist_get_unique_id(void* id_out_128);
+int ltx_dist_init(ltx_ctx* ctx, const void* unique_id_128, int rank, int world_size, int sp_size, int pass_groups);
+int ltx_dist_info(const ltx_ctx* ctx, int* rank, int* world_size, int* sp_size, int* pass_groups);
+
 /* Number of kernels launched by this context so far (bench.py reports the per-step delta as gpu_launches). */
 uint64_t ltx_launch_count(const ltx_ctx* ctx);
 /* The CUDA stream (cudaStream_t) every kernel of this context is enqueued on -- for CUDA-event timing by the caller. */

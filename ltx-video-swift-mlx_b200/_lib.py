@@ -61,6 +61,9 @@ SIGNATURES = {
     "ltx_denoise_latent_dev": (_I, [_P, C.POINTER(_P)]),
     "ltx_vae_decode": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_decode_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
+    "ltx_dist_get_unique_id": (_I, [_P]),
+    "ltx_dist_init": (_I, [_P, _P, _I, _I, _I, _I]),
+    "ltx_dist_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "ltx_launch_count": (_U64, [_P]),
     "ltx_get_stream": (_I, [_P, C.POINTER(_P)]),
     "ltx_set_profiling": (_I, [_P, _I]),

@@ -132,7 +132,7 @@ class LtxContext:
     def set_profiling(self, enabled: bool):
         self._check(self.lib.ltx_set_profiling(self.handle, int(enabled)))
 
-    PROFILE_CLASSES = ("gemm", "attention", "rows", "conv3d", "vae_prologue", "other")
+    PROFILE_CLASSES = ("gemm", "attention", "rows", "conv3d", "vae_prologue", "other", "comm")
 
     def get_profile(self) -> Dict[str, dict]:
         n = 8
@@ -141,6 +141,20 @@ class LtxContext:
         self._check(self.lib.ltx_get_profile(self.handle, ms, fl, by, cnt, n))
         return {name: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(cnt[i]))
                 for i, name in enumerate(self.PROFILE_CLASSES)}
+
+    # ------------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.ltx_dist_get_unique_id(buf)
+        if rc != 0:
+            raise LtxError(rc, lib.ltx_last_error(None).decode())
+        return buf.raw
+
+    def dist_init(self, unique_id: bytes, rank: int, world_size: int, sp_size: int = 1, pass_groups: int = 1):
+        assert len(unique_id) == 128
+        self._check(self.lib.ltx_dist_init(self.handle, unique_id, rank, world_size, sp_size, pass_groups))
 
     # ------------------------------------------------------------------ weights
     def load_tensor(self, key: str, value):

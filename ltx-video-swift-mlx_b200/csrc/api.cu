@@ -95,6 +95,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
   if (!c) return LTX_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  try { dist_destroy(c); } catch (...) {}
   for (auto& kv : c->tensors)
     if (kv.second.ptr) cudaFree(kv.second.ptr);
   for (void* p : c->owned) cudaFree(p);
@@ -117,6 +118,33 @@ int ltx_sync(ltx_ctx* c) {
 }
 
 uint64_t ltx_launch_count(const ltx_ctx* c) { return c ? c->launches : 0; }
+
+int ltx_dist_get_unique_id(void* id_out_128) {
+  if (!id_out_128) return LTX_ERR_INVALID_ARGUMENT;
+  try {
+    dist_get_unique_id(id_out_128);
+    return LTX_OK;
+  } catch (const LtxError& e) {
+    g_create_error = e.what();
+    return e.code;
+  }
+}
+
+int ltx_dist_init(ltx_ctx* c, const void* unique_id_128, int rank, int world_size, int sp_size, int pass_groups) {
+  return guarded(c, [&] {
+    LTX_CHECK(unique_id_128 != nullptr, LTX_ERR_INVALID_ARGUMENT, "null unique id");
+    dist_init(c, unique_id_128, rank, world_size, sp_size, pass_groups);
+  });
+}
+
+int ltx_dist_info(const ltx_ctx* c, int* rank, int* world_size, int* sp_size, int* pass_groups) {
+  if (!c) return LTX_ERR_INVALID_ARGUMENT;
+  if (rank) *rank = c->dist.rank;
+  if (world_size) *world_size = c->dist.world;
+  if (sp_size) *sp_size = c->dist.sp;
+  if (pass_groups) *pass_groups = c->dist.groups;
+  return LTX_OK;
+}
 
 int ltx_get_stream(ltx_ctx* c, void** stream) {
   return guarded(c, [&] {
@@ -333,9 +361,21 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     };
     const bool use_cfg = p->cfg_scale > 1.0f && c->s_has_neg;
     const bool use_stg = p->stg_scale > 0.f && p->n_stg_blocks > 0;
-    pass(false, false, c->s_vc.as<float>());
-    if (use_cfg) pass(true, false, c->s_vu.as<float>());
-    if (use_stg) pass(false, true, c->s_vs.as<float>());
+    // pass p runs on pass group p % groups (all groups when there is one); velocities are then broadcast from the
+    // first rank of the owning group so that every rank applies the same guided Euler update to its replicated latent
+    struct PassDef { bool neg, stg; float* v; };
+    PassDef passes[3];
+    int n_pass = 0;
+    passes[n_pass++] = {false, false, c->s_vc.as<float>()};
+    if (use_cfg) passes[n_pass++] = {true, false, c->s_vu.as<float>()};
+    if (use_stg) passes[n_pass++] = {false, true, c->s_vs.as<float>()};
+    const int groups = c->dist.groups;
+    for (int i = 0; i < n_pass; ++i)
+      if (groups == 1 || (i % groups) == c->dist.group) pass(passes[i].neg, passes[i].stg, passes[i].v);
+    if (groups > 1) {
+      ProfScope ps(c, PROF_COMM, 0.0, 4.0 * n * n_pass, n_pass);
+      for (int i = 0; i < n_pass; ++i) dist_broadcast(c, passes[i].v, n * 4, (i % groups) * c->dist.sp);
+    }
     GuidedEulerArgs a;
     a.latent = c->s_latent.as<float>(); a.v_cond = c->s_vc.as<float>();
     a.v_uncond = use_cfg ? c->s_vu.as<float>() : nullptr;

@@ -66,13 +66,13 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
     // residual: x[t,h,w,(c mod Cin/8)*8 + p]   (VideoDecoder.swift:201-251)
     const int Cf = g.Cout >> 3;        // output channels
     const int Cr = g.Cin >> 3;         // residual d2s channels (tiled x4)
-    const int To = 2 * g.T - 1, Ho = 2 * g.H, Wo = 2 * g.W;
+    const int Ho = 2 * g.H, Wo = 2 * g.W;
     const float* xr = ep.resid + vox * g.Cin;
     const int c0 = col0 >> 3;          // first of 4 output channels covered by these 32 columns
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const int p1 = p >> 2, p2 = (p >> 1) & 1, p3 = p & 1;
-      const int to = 2 * t + p1 - 1;
+      const int to = 2 * t + p1 - 1 + ep.t_shift;
       if (to < 0) continue;
       float v[4];
 #pragma unroll
@@ -82,7 +82,6 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
         v[cc] = __uint_as_float(r[cc * 8 + p]) + ep.bias[co] + xr[(c % Cr) * 8 + p];
       }
       float* o = ep.out + ((static_cast<int64_t>(to) * Ho + (2 * h + p2)) * Wo + (2 * w + p3)) * Cf + c0;
-      (void)To;
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {

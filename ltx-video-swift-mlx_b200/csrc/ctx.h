@@ -86,7 +86,13 @@ struct VaeWeights {
 }  // namespace ltx
 
 namespace ltx {
-enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_CONV = 3, PROF_PREP = 4, PROF_OTHER = 5, PROF_NCLASS = 8 };
+struct DistState {
+  void* comm_world = nullptr;  // ncclComm_t
+  void* comm_sp = nullptr;     // sequence-parallel sub-communicator (== world when pass_groups == 1)
+  bool sp_is_world = true;
+  int rank = 0, world = 1, sp = 1, groups = 1, group = 0, sp_rank = 0;
+};
+enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_CONV = 3, PROF_PREP = 4, PROF_OTHER = 5, PROF_COMM = 6, PROF_NCLASS = 8 };
 struct ProfRec {
   cudaEvent_t a, b;
   int cls;
@@ -96,6 +102,7 @@ struct ProfRec {
 
 struct ltx_ctx {
   ltx_config cfg;
+  ltx::DistState dist;
   // ---- optional per-kernel-class timing (CUDA events on the context stream around every launch)
   bool prof_on = false;
   std::vector<ltx::ProfRec> prof_recs;
@@ -173,6 +180,15 @@ void dit_clear_caches(ltx_ctx* c);
 void vae_finalize(ltx_ctx* c);
 void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
                     int causal, float* frames_dev);
+// dist.cu
+void dist_get_unique_id(void* out128);
+void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int sp_size, int pass_groups);
+void dist_destroy(ltx_ctx* c);
+void dist_broadcast(ltx_ctx* c, void* buf, size_t bytes, int root_world_rank);
+void dist_allgather_sp(ltx_ctx* c, const void* send, void* recv, size_t bytes_per_rank);
+void dist_all_to_all_sp(ltx_ctx* c, const void* const* send, void* const* recv, int n_tensors, size_t bytes_per_peer);
+void dist_halo_exchange(ltx_ctx* c, const void* send_prev, void* recv_prev, const void* send_next, void* recv_next,
+                        size_t bytes, int n_active);
 // weights.cu
 const DevTensor& get_tensor(ltx_ctx* c, const std::string& key);
 void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int dtype, const int64_t* shape, int ndim);

@@ -342,13 +342,13 @@ __global__ void __launch_bounds__(256) gemv_kernel(const bf16* __restrict__ W, c
 // patchify / unpatchify (P/LatentUtils.swift:20-54): [C, T] <-> [T, C] transposes through a padded smem tile.
 // ---------------------------------------------------------------------------------------------
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
-                                 int R, int Cc) {
-  // in [R, Cc] -> out [Cc, R]
+                                 int R, int Cc, int64_t ld_in) {
+  // in [R, Cc] (row pitch ld_in) -> out [Cc, R]
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[static_cast<int64_t>(r) * Cc + c] : 0.f;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[static_cast<int64_t>(r) * ld_in + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -555,12 +555,18 @@ void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int 
 
 void launch_patchify(const float* latent, bf16* tok_bf16, float* tok_f32, int C, int T, cudaStream_t s) {
   dim3 grid((T + 31) / 32, (C + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(latent, tok_f32, tok_bf16, C, T);
+  transpose_kernel<<<grid, block, 0, s>>>(latent, tok_f32, tok_bf16, C, T, T);
+  LTX_CUDA(cudaGetLastError());
+}
+void launch_transpose_slice(const float* in, int64_t ld_in, int rows, int cols, float* out, cudaStream_t s) {
+  // in [rows, cols] with row pitch ld_in -> out [cols, rows]
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(in, out, nullptr, rows, cols, ld_in);
   LTX_CUDA(cudaGetLastError());
 }
 void launch_unpatchify(const float* tok, float* latent, int C, int T, cudaStream_t s) {
   dim3 grid((C + 31) / 32, (T + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(tok, latent, nullptr, T, C);
+  transpose_kernel<<<grid, block, 0, s>>>(tok, latent, nullptr, T, C, C);
   LTX_CUDA(cudaGetLastError());
 }
 

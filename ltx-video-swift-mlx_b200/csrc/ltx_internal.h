@@ -99,6 +99,7 @@ void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int 
 // latent [C, T] (channel-major, T = F*H*W tokens) <-> tokens [T, C]
 void launch_patchify(const float* latent, bf16* tok_bf16, float* tok_f32, int C, int T, cudaStream_t s);
 void launch_unpatchify(const float* tok, float* latent, int C, int T, cudaStream_t s);
+void launch_transpose_slice(const float* in, int64_t ld_in, int rows, int cols, float* out, cudaStream_t s);
 // guidance + Euler (P/LatentUtils.swift:131-183, P/LTXPipeline.swift:920-927, S/LTXScheduler.swift:305-327)
 struct GuidedEulerArgs {
   float* latent;          // in/out fp32 [n]
@@ -123,6 +124,8 @@ struct ConvEpi {
   const float* bias;        // [Cout]
   const float* resid;       // mode 0: nullable [T,H,W,Cout] ; mode 1: conv input x fp32 [T,H,W,Cin]
   int Cin;
+  int t_shift = 0;          // mode 1: output frame = 2t + p1 - 1 + t_shift (1 on temporal shards other than the first,
+                            // which keep the frame the first shard trims; frames < 0 are dropped)
 };
 // x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [27][Cout][Cin]; 3x3x3 cross-correlation.
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,

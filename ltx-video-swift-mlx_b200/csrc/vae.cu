@@ -59,16 +59,25 @@ const float* vf(ltx_ctx* c, const std::string& k, int64_t n) {
   return reinterpret_cast<const float*>(t.ptr);
 }
 
+// n_active > 1: this rank holds a temporal slab; the two time-padding frames of the conv input come from the
+// neighbouring ranks (the global first / last slab keep the replicated frame the prologue wrote).
 void conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
-          int causal, int epi_mode, float* out, const float* resid) {
+          int causal, int epi_mode, float* out, const float* resid, int n_active = 1, int t_shift = 0) {
   c->v_pad.reserve(static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * w.cin * 2);
   const double vox = static_cast<double>(T) * H * W;
   {
     ProfScope ps(c, PROF_PREP, 0.0, vox * w.cin * 4.0 + static_cast<double>(T + 2) * (H + 2) * (W + 2) * w.cin * 2.0);
     launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, causal, c->stream);
   }
+  if (n_active > 1) {
+    const size_t frame = static_cast<size_t>(H + 2) * (W + 2) * w.cin;  // one padded frame, contiguous in v_pad
+    bf16* pad = c->v_pad.as<bf16>();
+    ProfScope ps(c, PROF_COMM, 0.0, 4.0 * frame * 2.0);
+    dist_halo_exchange(c, pad + frame, pad, pad + static_cast<size_t>(T) * frame, pad + static_cast<size_t>(T + 1) * frame,
+                       frame * 2, n_active);
+  }
   ConvEpi e;
-  e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin;
+  e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin; e.t_shift = t_shift;
   ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * w.cin * w.cout * vox, vox * (w.cin * 2.0 + w.cout * 4.0) + 27.0 * w.cin * w.cout * 2.0);
   launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream);
 }
@@ -123,46 +132,77 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
   const ltx_config& g = c->cfg;
   cudaStream_t st = c->stream;
   const int C0 = g.vae_latent_channels;
-  int T = Fp, H = Hp, W = Wp;
-  // worst-case activation sizes over the stages: x at stage s has ch_s channels on a (T_s, H_s, W_s) grid
-  size_t max_x = 0;
-  {
-    int t = Fp, h = Hp, w = Wp;
+  // ---- temporal sharding: the first n_active ranks own contiguous slabs of latent frames [f0, f1)
+  const int world = c->dist.world, rank = c->dist.rank;
+  const int n_active = (c->dist.comm_world && world > 1) ? std::min(world, Fp) : 1;
+  LTX_CHECK(n_active == 1 || !causal, LTX_ERR_UNSUPPORTED, "temporally sharded decode supports the non-causal decoder only");
+  auto slab = [&](int r, int& f0, int& f1) {
+    const int base = Fp / n_active, rem = Fp % n_active;
+    f0 = r * base + std::min(r, rem);
+    f1 = f0 + base + (r < rem ? 1 : 0);
+  };
+  int f0 = 0, f1 = Fp;
+  if (n_active > 1 && rank < n_active) slab(rank, f0, f1);
+  const bool active = rank < n_active;
+  const int Ho = 32 * Hp, Wo = 32 * Wp;
+  const size_t frame_elems = static_cast<size_t>(Ho) * Wo * 3;
+  if (active) {
+    int T = f1 - f0, H = Hp, W = Wp;
+    const int t_shift = (n_active > 1 && rank > 0) ? 1 : 0;
+    // worst-case activation sizes over the stages: x at stage s has ch_s channels on a (T_s, H_s, W_s) grid
+    size_t max_x = 0;
+    {
+      int t = T, h = Hp, w = Wp;
+      int64_t ch = g.vae_base_channels;
+      for (int s = 0; s < 4; ++s) {
+        max_x = std::max(max_x, static_cast<size_t>(t) * h * w * ch);
+        if (s < 3) { t = 2 * t - 1 + t_shift; h *= 2; w *= 2; ch /= 2; }
+      }
+      max_x = std::max(max_x, static_cast<size_t>(T) * Hp * Wp * C0);
+    }
+    c->v_a.reserve(max_x * 4);
+    c->v_b.reserve(max_x * 4);
+    c->v_h.reserve(max_x * 4);
+    float* x = c->v_a.as<float>();
+    float* y = c->v_b.as<float>();
+    float* hbuf = c->v_h.as<float>();
+    // [C, F*H*W] (frames f0..f1) -> channels-last [T*H*W, C]
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * C0 * T * H * W);
+      launch_transpose_slice(latent_dev + static_cast<size_t>(f0) * H * W, static_cast<int64_t>(Fp) * H * W, C0, T * H * W, hbuf,
+                             st);
+    }
+    // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
+    conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr, n_active);
     int64_t ch = g.vae_base_channels;
     for (int s = 0; s < 4; ++s) {
-      max_x = std::max(max_x, static_cast<size_t>(t) * h * w * ch);
-      if (s < 3) { t = 2 * t - 1; h *= 2; w *= 2; ch /= 2; }
+      for (const VaeResBlock& rb : v.stages[s]) {
+        // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
+        conv(c, x, 2, rb.sst + ch, rb.sst, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
+        conv(c, hbuf, 2, rb.sst + 3 * ch, rb.sst + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
+      }
+      if (s < 3) {
+        // conv -> d2s -> drop frame 0 (first slab only) -> + tiled d2s(x)
+        conv(c, x, 0, nullptr, nullptr, v.ups[s], T, H, W, causal, 1, y, x, n_active, t_shift);
+        std::swap(x, y);
+        T = 2 * T - 1 + t_shift; H *= 2; W *= 2; ch /= 2;
+      }
     }
-    max_x = std::max(max_x, static_cast<size_t>(Fp) * Hp * Wp * C0);
+    // pn * (1 + scale) + shift -> SiLU -> conv_out -> unpatchify -> (x+1)/2 clip -> [F, H, W, 3]   (:419-444, 501-505)
+    const int out_f0 = f0 == 0 ? 0 : 8 * (f0 - 1) + 1;
+    conv(c, x, 2, v.last_sst + ch, v.last_sst, v.conv_out, T, H, W, causal, 2, frames_dev + static_cast<size_t>(out_f0) * frame_elems,
+         nullptr, n_active);
   }
-  c->v_a.reserve(max_x * 4);
-  c->v_b.reserve(max_x * 4);
-  c->v_h.reserve(max_x * 4);
-  float* x = c->v_a.as<float>();
-  float* y = c->v_b.as<float>();
-  float* hbuf = c->v_h.as<float>();
-  // [C, T*H*W] -> channels-last [T*H*W, C]
-  {
-    ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * C0 * T * H * W);
-    launch_patchify(latent_dev, nullptr, hbuf, C0, T * H * W, st);
-  }
-  // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
-  conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr);
-  int64_t ch = g.vae_base_channels;
-  for (int s = 0; s < 4; ++s) {
-    for (const VaeResBlock& rb : v.stages[s]) {
-      // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
-      conv(c, x, 2, rb.sst + ch, rb.sst, rb.c1, T, H, W, causal, 0, hbuf, nullptr);
-      conv(c, hbuf, 2, rb.sst + 3 * ch, rb.sst + 2 * ch, rb.c2, T, H, W, causal, 0, x, x);
-    }
-    if (s < 3) {
-      conv(c, x, 0, nullptr, nullptr, v.ups[s], T, H, W, causal, 1, y, x);  // conv -> d2s -> drop frame 0 -> + tiled d2s(x)
-      std::swap(x, y);
-      T = 2 * T - 1; H *= 2; W *= 2; ch /= 2;
+  if (n_active > 1) {
+    // all ranks receive every slab (an all-gather with unequal counts, as one broadcast per owner)
+    ProfScope ps(c, PROF_COMM, 0.0, 4.0 * frame_elems * (8.0 * (Fp - 1) + 1), n_active);
+    for (int r = 0; r < n_active; ++r) {
+      int a0, a1;
+      slab(r, a0, a1);
+      const int o0 = a0 == 0 ? 0 : 8 * (a0 - 1) + 1, o1 = 8 * (a1 - 1) + 1;
+      dist_broadcast(c, frames_dev + static_cast<size_t>(o0) * frame_elems, static_cast<size_t>(o1 - o0) * frame_elems * 4, r);
     }
   }
-  // pn * (1 + scale) + shift -> SiLU -> conv_out -> unpatchify -> (x+1)/2 clip -> [F, H, W, 3]   (:419-444, 501-505)
-  conv(c, x, 2, v.last_sst + ch, v.last_sst, v.conv_out, T, H, W, causal, 2, frames_dev, nullptr);
 }
 
 }  // namespace ltx
