@@ -99,7 +99,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
   for (auto& kv : c->tensors)
     if (kv.second.ptr) cudaFree(kv.second.ptr);
   for (void* p : c->owned) cudaFree(p);
-  DevBuf* bufs[] = {&c->api_lat, &c->api_ctx, &c->lat_in, &c->ctx_in, &c->ts_in, &c->mask_in, &c->x, &c->xb, &c->h, &c->qk, &c->vt, &c->att, &c->q2,
+  DevBuf* bufs[] = {&c->sp_send, &c->sp_recv, &c->sp_vt, &c->sp_vel, &c->api_lat, &c->api_ctx, &c->lat_in, &c->ctx_in, &c->ts_in, &c->mask_in, &c->x, &c->xb, &c->h, &c->qk, &c->vt, &c->att, &c->q2,
                     &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
                     &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,

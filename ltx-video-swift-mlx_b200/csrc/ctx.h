@@ -134,6 +134,7 @@ struct ltx_ctx {
   ltx::TextCache text[2];
   int text_rr = 0;
   ltx::DevBuf scratch;  // small fp64 scratch for reductions
+  ltx::DevBuf sp_send, sp_recv, sp_vt, sp_vel;  // Ulysses exchange buffers
 
   // ---- resident denoise session
   ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma;

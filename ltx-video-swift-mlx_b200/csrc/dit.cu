@@ -16,9 +16,10 @@ namespace ltx {
 namespace {
 
 // profiled launch helpers (flop / byte counts are the algorithmic ones used by bench.py's roofline)
-void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e) {
+void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e,
+          int a_kblock = 0, int64_t a_kblock_stride = 0) {
   ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
-  launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream);
+  launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
 }
 void attention(ltx_ctx* c, const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                const float* bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale) {
@@ -32,10 +33,10 @@ void norm_mod(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* 
   launch_rmsnorm_mod(x, out, M, D, ts, tsc, as, asc, ada_ld, rows_per_mod, eps, ln, c->stream);
 }
 void qknorm(ltx_ctx* c, bf16* x, int64_t ld, int M, int D, const float* w, const float* cs, const float* sn, int rpr,
-            float eps, const float* w_second = nullptr) {
+            float eps, const float* w_second = nullptr, const QkOut* blocked = nullptr) {
   const int segs = w_second ? 2 : 1;
   ProfScope ps(c, PROF_ROW, 0.0, segs * static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)), (D == 4096) ? 1 : segs);
-  launch_qknorm_rope(x, ld, M, D, w, cs, sn, rpr, eps, c->stream, w_second);
+  launch_qknorm_rope(x, ld, M, D, w, cs, sn, rpr, eps, c->stream, w_second, blocked);
 }
 
 const bf16* wbf(ltx_ctx* c, const std::string& k, int64_t r, int64_t cc) {
@@ -277,7 +278,14 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   const ltx_config& g = c->cfg;
   const int D = g.num_heads * g.head_dim, FFD = g.ffn_mult * D, Hh = g.num_heads, L = g.num_layers;
   const int Cin = g.in_channels, Cout = g.out_channels;
-  const int R = B * N;
+  // ---- Ulysses sequence parallelism: this rank owns tokens [tok0, tok0 + Nl) for every row-wise op
+  const int P = (c->dist.comm_world && c->dist.sp > 1) ? c->dist.sp : 1;
+  LTX_CHECK(P == 1 || (B == 1 && N % P == 0 && Hh % P == 0), LTX_ERR_INVALID_ARGUMENT,
+            "sequence parallelism needs B == 1 and N, num_heads divisible by sp_size");
+  const int Nl = N / P, tok0 = (P > 1 ? c->dist.sp_rank : 0) * Nl;
+  const int R = (P > 1) ? Nl : B * N;      // local rows
+  const int Nq = (P > 1) ? Nl : N;         // local query rows per batch
+  const int Csp = D / P, Hl = Hh / P;      // per-rank feature slice / heads inside self-attention
   const float eps = g.norm_eps;
   const float att_scale = 1.0f / sqrtf(static_cast<float>(g.head_dim));
   cudaStream_t st = c->stream;
@@ -312,11 +320,28 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   bf16* ffh = c->ffh.as<bf16>();
   float* ada = c->ada.as<float>();
   float* emb = c->emb.as<float>();
+  const int64_t blk = static_cast<int64_t>(Nl) * Csp;   // elements one rank sends to one peer per tensor
+  bf16 *qsend = nullptr, *ksend = nullptr, *vsend = nullptr, *qrecv = nullptr, *krecv = nullptr, *vrecv = nullptr,
+       *osend = nullptr, *orecv = nullptr, *vt_sp = nullptr;
+  if (P > 1) {
+    c->sp_send.reserve(static_cast<size_t>(3) * P * blk * 2);
+    c->sp_recv.reserve(static_cast<size_t>(3) * P * blk * 2);
+    c->sp_vt.reserve(static_cast<size_t>(Csp) * ldv * 2);
+    c->sp_vel.reserve(static_cast<size_t>(Nl) * Cout * 4);
+    qsend = c->sp_send.as<bf16>(); ksend = qsend + P * blk; vsend = ksend + P * blk;
+    qrecv = c->sp_recv.as<bf16>(); krecv = qrecv + P * blk; vrecv = krecv + P * blk;
+    osend = qsend;   // the attention output [N, Csp] reuses the q send buffer, its exchange lands in the q recv buffer
+    orecv = qrecv;
+    vt_sp = c->sp_vt.as<bf16>();
+  }
 
   // ---- step-invariant pieces
   build_rope(c, F, H, W);
   TextCache& tc = prepare_text(c, context, context_dtype, mask_dev, B, S, flags->context_key);
   const float* key_bias = tc.has_bias ? tc.bias.as<float>() : nullptr;
+  const float* cos_l = c->rope_cos.as<float>() + static_cast<int64_t>(tok0) * (D / 2);
+  const float* sin_l = c->rope_sin.as<float>() + static_cast<int64_t>(tok0) * (D / 2);
+  const int rows_per_b = (P > 1) ? Nl : N;   // rows sharing one modulation / gate vector, and the RoPE period
 
   // ---- patchify_proj (T/LTXTransformer.swift:257); the reference's bf16 Linear output is rounded to bf16
   const bf16* lat_bf;
@@ -324,13 +349,14 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     lat_bf = reinterpret_cast<const bf16*>(latent);
   } else {
     LTX_CHECK(latent_dtype == LTX_F32, LTX_ERR_UNSUPPORTED, "latent dtype must be bf16 or f32");
-    c->lat_in.reserve(static_cast<size_t>(R) * Cin * 2);
+    c->lat_in.reserve(static_cast<size_t>(B) * N * Cin * 2);
     {
-      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * Cin);
-      launch_cast_f32_bf16(reinterpret_cast<const float*>(latent), c->lat_in.as<bf16>(), static_cast<int64_t>(R) * Cin, st);
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * B * N * Cin);
+      launch_cast_f32_bf16(reinterpret_cast<const float*>(latent), c->lat_in.as<bf16>(), static_cast<int64_t>(B) * N * Cin, st);
     }
     lat_bf = c->lat_in.as<bf16>();
   }
+  lat_bf += static_cast<int64_t>(tok0) * Cin;
   {
     GemmEpi e;
     e.mode = EPI_BF16; e.out = xb; e.ldo = D; e.bias = c->b_patch;
@@ -356,22 +382,54 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     const float cas = in_list(i, flags->cas_blocks, flags->n_cas_blocks) ? flags->cross_attn_scale : 1.0f;
     if (!skip_sa) {
       // h = rms(x) * (1 + scale_msa) + shift_msa      (T/LTXTransformerBlock.swift:72-83, rows 0/1 of table+ada)
-      norm_mod(c, x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, N, eps, 0);
+      norm_mod(c, x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, rows_per_b, eps, 0);
       GemmEpi e;
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
       gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
-      for (int b = 0; b < B; ++b) {  // V^T, one column block per batch
+      if (P == 1) {
+        for (int b = 0; b < B; ++b) {  // V^T, one column block per batch
+          GemmEpi ev;
+          ev.mode = EPI_BF16; ev.out = vt + b * ldv; ev.ldo = B * ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
+          gemm(c, bw.a1.wv, D, h + static_cast<int64_t>(b) * N * D, D, D, N, D, ev);
+        }
+        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rows_per_b, eps, bw.a1.k_norm);
+        attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
+      } else {
+        // ---- Ulysses: q/k (normed + RoPE'd, which needs the full feature row) and v leave in a head-blocked layout,
+        // one all-to-all turns [Nl tokens, all heads] into [all tokens, Hl heads]; attention runs on the local heads;
+        // a second all-to-all returns the output rows to their owners, K-blocked, straight into the to_out GEMM.
         GemmEpi ev;
-        ev.mode = EPI_BF16; ev.out = vt + b * ldv; ev.ldo = B * ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
-        gemm(c, bw.a1.wv, D, h + static_cast<int64_t>(b) * N * D, D, D, N, D, ev);
+        ev.mode = EPI_BF16; ev.out = vsend; ev.ldo = Csp; ev.bias = bw.a1.bv; ev.col_block = Csp; ev.col_block_stride = blk;
+        gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
+        QkOut qo;
+        qo.out[0] = qsend; qo.out[1] = ksend; qo.heads_per_block = Hl; qo.block_stride = blk; qo.ld = Csp;
+        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rows_per_b, eps, bw.a1.k_norm, &qo);
+        {
+          ProfScope ps(c, PROF_COMM, 0.0, 3.0 * 2.0 * P * blk * 2.0);
+          const void* sb[3] = {qsend, ksend, vsend};
+          void* rb[3] = {qrecv, krecv, vrecv};
+          dist_all_to_all_sp(c, sb, rb, 3, static_cast<size_t>(blk) * 2);
+        }
+        {
+          ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * N * Csp);
+          launch_transpose_bf16(vrecv, Csp, N, Csp, vt_sp, ldv, st);
+        }
+        attention(c, qrecv, Csp, krecv, Csp, vt_sp, ldv, nullptr, osend, Csp, 1, Hl, N, N, Csp, att_scale);
+        {
+          ProfScope ps(c, PROF_COMM, 0.0, 2.0 * P * blk * 2.0);
+          const void* sb[1] = {osend};
+          void* rb[1] = {orecv};
+          dist_all_to_all_sp(c, sb, rb, 1, static_cast<size_t>(blk) * 2);
+        }
       }
-      qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, c->rope_cos.as<float>(), c->rope_sin.as<float>(), N, eps, bw.a1.k_norm);
-      attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
       GemmEpi eo;  // x += (att Wo^T + bo) * gate_msa ; refresh the bf16 shadow
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a1.bo;
-      eo.gate_a = ada + 2 * D; eo.gate_b = bw.sst + 2 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
+      eo.gate_a = ada + 2 * D; eo.gate_b = bw.sst + 2 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = rows_per_b;
       eo.shadow = xb; eo.lds = D;
-      gemm(c, att, D, bw.a1.wo, D, R, D, D, eo);
+      if (P == 1)
+        gemm(c, att, D, bw.a1.wo, D, R, D, D, eo);
+      else
+        gemm(c, orecv, Csp, bw.a1.wo, D, R, D, D, eo, Csp, blk);
     }
     {
       // cross-attention on the UN-normalised stream (T/LTXTransformerBlock.swift:205-214)
@@ -381,7 +439,7 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
       qknorm(c, q2, D, R, D, bw.a2.q_norm, nullptr, nullptr, 1, eps);
       const bf16* k2 = tc.k.as<bf16>() + static_cast<int64_t>(i) * B * S * D;
       const bf16* v2 = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * B * tc.ldv;
-      attention(c, q2, D, k2, D, v2, tc.ldv, key_bias, att, D, B, Hh, N, S, D, att_scale);
+      attention(c, q2, D, k2, D, v2, tc.ldv, key_bias, att, D, B, Hh, Nq, S, D, att_scale);
       GemmEpi eo;
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.a2.bo; eo.scale = cas;
       const bool next_needs_shadow = skip_ff && (i + 1 < L) &&
@@ -390,13 +448,13 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
       gemm(c, att, D, bw.a2.wo, D, R, D, D, eo);
     }
     if (!skip_ff) {
-      norm_mod(c, x, h, R, D, bw.sst + 3 * D, bw.sst + 4 * D, ada + 3 * D, ada + 4 * D, ada_ld, N, eps, 0);
+      norm_mod(c, x, h, R, D, bw.sst + 3 * D, bw.sst + 4 * D, ada + 3 * D, ada + 4 * D, ada_ld, rows_per_b, eps, 0);
       GemmEpi e;
       e.mode = EPI_GELU_BF16; e.out = ffh; e.ldo = FFD; e.bias = bw.b_in;
       gemm(c, h, D, bw.w_in, D, R, FFD, D, e);
       GemmEpi eo;
       eo.mode = EPI_GATE_RESID; eo.resid = x; eo.ldr = D; eo.bias = bw.b_out;
-      eo.gate_a = ada + 5 * D; eo.gate_b = bw.sst + 5 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = N;
+      eo.gate_a = ada + 5 * D; eo.gate_b = bw.sst + 5 * D; eo.gate_ld = ada_ld; eo.rows_per_gate = rows_per_b;
       const bool next_needs_shadow =
           (i + 1 < L) && in_list(i + 1, flags->stg_blocks, flags->n_stg_blocks) && flags->skip_self_attn;
       if (next_needs_shadow) { eo.shadow = xb; eo.lds = D; }
@@ -404,10 +462,14 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     }
   }
   // ---- output head (T/LTXTransformer.swift:208-224): LayerNorm(no affine) * (1 + scale) + shift ; proj_out
-  norm_mod(c, x, h, R, D, c->sst_out, c->sst_out + D, emb, emb, D, N, eps, 1);
+  norm_mod(c, x, h, R, D, c->sst_out, c->sst_out + D, emb, emb, D, rows_per_b, eps, 1);
   GemmEpi e;
-  e.mode = EPI_F32; e.out = out_velocity_dev; e.ldo = Cout; e.bias = c->b_out;
+  e.mode = EPI_F32; e.out = (P > 1) ? c->sp_vel.ptr : out_velocity_dev; e.ldo = Cout; e.bias = c->b_out;
   gemm(c, h, D, c->w_out, D, R, Cout, D, e);
+  if (P > 1) {  // every rank receives the full velocity [N, Cout]
+    ProfScope ps(c, PROF_COMM, 0.0, 4.0 * N * Cout);
+    dist_allgather_sp(c, c->sp_vel.ptr, out_velocity_dev, static_cast<size_t>(Nl) * Cout * 4);
+  }
 }
 
 }  // namespace ltx

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, int64_t ld, int D,
                                                            const float* __restrict__ w, const float* __restrict__ cosb,
-                                                           const float* __restrict__ sinb, int rows_per_rope, float eps) {
+                                                           const float* __restrict__ sinb, int rows_per_rope, float eps,
+                                                           bf16* __restrict__ bout, int hpb, int64_t bstride, int64_t bld) {
   __shared__ float red[33];
   const int row = blockIdx.x;
   bf16* xr = x + static_cast<int64_t>(row) * ld;
@@ -194,9 +195,16 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, 
 #pragma unroll
       for (int t = 0; t < 8; ++t) { y1[t] = x1[t]; y2[t] = x2[t]; }
     }
-    *reinterpret_cast<uint4*>(xr + c1) =
+    bf16* o1 = xr + c1;
+    bf16* o2 = xr + c2;
+    if (bout) {
+      bf16* ob = bout + static_cast<int64_t>(hh / hpb) * bstride + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+      o1 = ob;
+      o2 = ob + 64;
+    }
+    *reinterpret_cast<uint4*>(o1) =
         make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
-    *reinterpret_cast<uint4*>(xr + c2) =
+    *reinterpret_cast<uint4*>(o2) =
         make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
   }
 }
@@ -208,11 +216,14 @@ template <int ROWS>
 __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict__ x, int64_t ld, int M,
                                                                 const float* __restrict__ w0, const float* __restrict__ w1,
                                                                 const float* __restrict__ cosb, const float* __restrict__ sinb,
-                                                                int rows_per_rope, float eps) {
+                                                                int rows_per_rope, float eps, bf16* __restrict__ bout0,
+                                                                bf16* __restrict__ bout1, int hpb, int64_t bstride,
+                                                                int64_t bld) {
   __shared__ float red[33];
   constexpr int D = 4096;
   const int seg = blockIdx.y;
   const float* w = seg == 0 ? w0 : w1;
+  bf16* bout = seg == 0 ? bout0 : bout1;
   const int hh = threadIdx.x >> 3, jc = (threadIdx.x & 7) * 8;
   const int c1 = hh * 128 + jc, c2 = c1 + 64;
   float wa[8], wb[8];
@@ -261,9 +272,16 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
         y1[t] = a; y2[t] = b;
       }
     }
-    *reinterpret_cast<uint4*>(xr + c1) =
+    bf16* o1 = xr + c1;
+    bf16* o2 = xr + c2;
+    if (bout) {
+      bf16* ob = bout + static_cast<int64_t>(hh / hpb) * bstride + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+      o1 = ob;
+      o2 = ob + 64;
+    }
+    *reinterpret_cast<uint4*>(o1) =
         make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
-    *reinterpret_cast<uint4*>(xr + c2) =
+    *reinterpret_cast<uint4*>(o2) =
         make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
   }
 }
@@ -490,23 +508,48 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
 }
 
 void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
-                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second) {
+                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second, const QkOut* blocked) {
   // w_second != nullptr: also normalise the second segment x[:, D:2D] with that weight (fused q|k projection output)
   LTX_CHECK(D % 128 == 0 && ld % 8 == 0 && M > 0, 2, "qknorm_rope: D must be a multiple of 128");
   const int rpr = rows_per_rope > 0 ? rows_per_rope : 1;
+  bf16* b0 = blocked ? blocked->out[0] : nullptr;
+  bf16* b1 = blocked ? blocked->out[1] : nullptr;
+  const int hpb = blocked ? blocked->heads_per_block : 1;
+  const int64_t bs = blocked ? blocked->block_stride : 0, bld = blocked ? blocked->ld : 0;
+  LTX_CHECK(!blocked || (hpb > 0 && (D / 128) % hpb == 0 && b0 && (!w_second || b1)), 2, "qknorm_rope: bad blocked output");
   if (D == 4096) {
     constexpr int ROWS = 4;
     dim3 grid((M + ROWS - 1) / ROWS, w_second ? 2 : 1);
-    qknorm_rope_fast_kernel<ROWS><<<grid, 256, 0, s>>>(x, ld, M, w, w_second, cosb, sinb, rpr, eps);
+    qknorm_rope_fast_kernel<ROWS><<<grid, 256, 0, s>>>(x, ld, M, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs, bld);
     LTX_CUDA(cudaGetLastError());
     return;
   }
-  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps);
+  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps, b0, hpb, bs, bld);
   LTX_CUDA(cudaGetLastError());
   if (w_second) {
-    qknorm_rope_kernel<<<M, 256, 0, s>>>(x + D, ld, D, w_second, cosb, sinb, rpr, eps);
+    qknorm_rope_kernel<<<M, 256, 0, s>>>(x + D, ld, D, w_second, cosb, sinb, rpr, eps, b1, hpb, bs, bld);
     LTX_CUDA(cudaGetLastError());
   }
+}
+
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, int64_t ld_in, int R, int Cc, bf16* __restrict__ out,
+                                      int64_t ld_out) {
+  __shared__ bf16 tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[static_cast<int64_t>(r) * ld_in + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < Cc && r < R) out[static_cast<int64_t>(c) * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+void launch_transpose_bf16(const bf16* in, int64_t ld_in, int R, int C, bf16* out, int64_t ld_out, cudaStream_t s) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, s>>>(in, ld_in, R, C, out, ld_out);
+  LTX_CUDA(cudaGetLastError());
 }
 
 void launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s) {

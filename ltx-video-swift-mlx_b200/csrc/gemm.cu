@@ -102,6 +102,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
     }
   } else {  // EPI_BF16 / EPI_GELU_BF16
     bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
+    if (ep.col_block > 0)
+      o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(col0 / ep.col_block) * ep.col_block_stride +
+          static_cast<int64_t>(row) * ep.ldo + (col0 % ep.col_block);
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -137,7 +140,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                  int BN, const GemmEpi ep) {
+                  int BN, int a_kblock, const GemmEpi ep) {
   using Cfg = GemmCfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -186,7 +189,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + b_bytes);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
+          if (a_kblock > 0)   // K-blocked A: 3-D map (k in block, row, block)
+            tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], (kb * BK) % a_kblock, m_blk * BM, (kb * BK) / a_kblock);
+          else
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
           tma_load_2d(sB + stage * Cfg::B_STRIDE, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -259,8 +265,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 template <int MODE>
-void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, const GemmEpi& epi,
-                 cudaStream_t stream) {
+void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, int a_kblock,
+                 const GemmEpi& epi, cudaStream_t stream) {
   using Cfg = GemmCfg;
   static bool configured = false;
   auto kern = gemm_bf16_tcgen05<MODE>;
@@ -270,7 +276,7 @@ void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, BN, epi);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, BN, a_kblock, epi);
   LTX_CUDA(cudaGetLastError());
 }
 
@@ -294,7 +300,7 @@ int fit_tile_width(int M, int N, int sms) {
 }  // namespace
 
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
-                 cudaStream_t stream, int force_bn) {
+                 cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride) {
   LTX_CHECK(M > 0 && N > 0 && K > 0, 2, "GEMM: empty problem");
   LTX_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, 2, "GEMM: K and leading dims must be multiples of 8");
   if (epi.mode == EPI_GATE_RESID) {
@@ -308,13 +314,22 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   int bn = force_bn;
   if (bn == 0) bn = fit_tile_width(M, N, device_sm_count());
   LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "GEMM: tile width must be a multiple of 16 in [32, 256]");
-  CUtensorMap tmA = make_tmap_2d(A, M, K, lda, BM);
+  LTX_CHECK(epi.col_block == 0 || ((epi.mode == EPI_BF16 || epi.mode == EPI_GELU_BF16) && epi.col_block % 32 == 0 &&
+                                   N % epi.col_block == 0),
+            2, "GEMM: column-blocked output needs a bf16 epilogue and col_block % 32 == 0");
+  CUtensorMap tmA;
+  if (a_kblock > 0) {
+    LTX_CHECK(a_kblock % BK == 0 && K % a_kblock == 0 && lda == a_kblock, 2, "GEMM: bad K-blocked A layout");
+    tmA = make_tmap_3d(A, a_kblock, M, K / a_kblock, lda, a_kblock_stride, 64, BM);
+  } else {
+    tmA = make_tmap_2d(A, M, K, lda, BM);
+  }
   CUtensorMap tmB = make_tmap_2d(B, N, K, ldb, bn);
   switch (epi.mode) {
-    case EPI_BF16: launch_impl<EPI_BF16>(tmA, tmB, M, N, K, bn, epi, stream); break;
-    case EPI_GELU_BF16: launch_impl<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, epi, stream); break;
-    case EPI_GATE_RESID: launch_impl<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, epi, stream); break;
-    case EPI_F32: launch_impl<EPI_F32>(tmA, tmB, M, N, K, bn, epi, stream); break;
+    case EPI_BF16: launch_impl<EPI_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_GELU_BF16: launch_impl<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_GATE_RESID: launch_impl<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_F32: launch_impl<EPI_F32>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
     default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
   }
 }

@@ -65,11 +65,19 @@ struct GemmEpi {
   bf16* shadow = nullptr;  // optional bf16 copy of the updated residual, row pitch lds
   int64_t lds = 0;
   float scale = 1.0f;
+  // bf16 outputs only: column-blocked destination (Ulysses send layout): element (m, n) goes to
+  // out[(n / col_block) * col_block_stride + m * ldo + n % col_block]; col_block = 0 -> plain row-major.
+  int col_block = 0;
+  int64_t col_block_stride = 0;
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 K-major (row pitch lda / ldb elements, multiples of 8).
+// a_kblock > 0: A is K-blocked (Ulysses receive layout): element (m, k) lives at A[(k / a_kblock) * a_kblock_stride +
+// m * lda + k % a_kblock] (a_kblock % 64 == 0, lda = a_kblock).
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
-                 cudaStream_t stream, int force_bn = 0);
+                 cudaStream_t stream, int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
+// bf16 [R, C] (row pitch ld_in) -> [C, R] (row pitch ld_out)
+void launch_transpose_bf16(const bf16* in, int64_t ld_in, int R, int C, bf16* out, int64_t ld_out, cudaStream_t s);
 
 // ---------------------------------------------------------------- attention (attention.cu)
 // Q [B*Nq, D], K [B*Nk, D] bf16 (head h = columns h*128..h*128+127); Vt [D, B*ldvb] bf16 (row h*128+d, column
@@ -86,8 +94,16 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
                         int layernorm, cudaStream_t s);
 // In place on bf16 [M, ld]: y = rms(x[:, :D]) * w, then optional split-RoPE with cos/sin [rows_per_rope, D/2] (token-major).
 // w_second != nullptr: the same for the second segment x[:, D:2D] with that weight (q | k of the fused projection).
+// QkOut (optional): write the result out of place in the head-blocked Ulysses send layout instead of in place:
+// head h of segment g goes to out[g][(h / heads_per_block) * block_stride + row * ld + (h % heads_per_block) * 128 + d].
+struct QkOut {
+  bf16* out[2] = {nullptr, nullptr};
+  int heads_per_block = 0;
+  int64_t block_stride = 0, ld = 0;
+};
 void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
-                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second = nullptr);
+                        int rows_per_rope, float eps, cudaStream_t s, const float* w_second = nullptr,
+                        const QkOut* blocked = nullptr);
 void launch_cast_f32_bf16(const float* in, bf16* out, int64_t n, cudaStream_t s);
 void launch_cast_bf16_f32(const bf16* in, float* out, int64_t n, cudaStream_t s);
 // y[o] = act_out( sum_i W[o,i] * act_in(x[i]) + b[o] ), bf16 W [O,I]; tiny-M path for the timestep MLP (M rows).

@@ -40,6 +40,7 @@ def test_attention(ctx, B, H, Nq, Nk, masked):
         bias = ((1 - m) * -10000.0).contiguous()
     o = torch.full((B * Nq, D), float("nan"), device="cuda", dtype=torch.bfloat16)
     scale = 1 / math.sqrt(128)
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     ctx._check(ctx.lib.ltx_op_attention(ctx.handle, q.data_ptr(), k.data_ptr(), vt.data_ptr(), ldv,
                                         bias.data_ptr() if bias is not None else None, o.data_ptr(), B, H, Nq, Nk, scale))
     ctx.sync()

@@ -30,6 +30,7 @@ def test_conv3d(ctx, T, H, W, Cin, Cout, causal):
     w_dev = w.permute(2, 3, 4, 0, 1).reshape(27, Cout, Cin).contiguous().cuda().bfloat16()
     b_dev = b.cuda()
     out = torch.full((T, H, W, Cout), float("nan"), device="cuda")
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     ctx._check(ctx.lib.ltx_op_conv3d(ctx.handle, x_cl.data_ptr(), w_dev.data_ptr(), b_dev.data_ptr(), out.data_ptr(), T, H, W,
                                      Cin, Cout, causal))
     ctx.sync()

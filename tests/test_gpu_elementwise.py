@@ -21,6 +21,7 @@ def test_rmsnorm_mod(ctx, M, D, layernorm):
     x = torch.randn(M, D, device="cuda", generator=g) * 3 + 0.5
     ts, tc, as_, ac = [torch.randn(D, device="cuda", generator=g) * 0.3 for _ in range(4)]
     out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     ctx._check(ctx.lib.ltx_op_rmsnorm_mod(ctx.handle, x.data_ptr(), out.data_ptr(), M, D, ts.data_ptr(), tc.data_ptr(),
                                           as_.data_ptr(), ac.data_ptr(), 1e-6, layernorm))
     ctx.sync()
@@ -45,6 +46,7 @@ def test_qknorm_rope(ctx, heads, fhw, rope):
     cos_t = cos.permute(1, 0, 2).reshape(N, D // 2).contiguous().cuda()
     sin_t = sin.permute(1, 0, 2).reshape(N, D // 2).contiguous().cuda()
     y = x.clone()
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     ctx._check(ctx.lib.ltx_op_qknorm_rope(ctx.handle, y.data_ptr(), N, D, w.data_ptr(), cos_t.data_ptr() if rope else None,
                                           sin_t.data_ptr() if rope else None, N, 1e-6))
     ctx.sync()

@@ -39,6 +39,7 @@ def test_gemm(ctx, M, N, K, bn, mode):
     B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if mode == 3 else torch.bfloat16)
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     rc = ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn)
     ctx._check(rc)
     ctx.sync()
@@ -61,6 +62,7 @@ def test_gemm_gate_residual(ctx, M, N, K):
     x0 = torch.randn(M, N, device="cuda", generator=g)
     x = x0.clone()
     shadow = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize()   # inputs were produced on torch\'s stream; the library runs on its own
     ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), x.data_ptr(), ga.data_ptr(),
                                          gb.data_ptr(), shadow.data_ptr(), M, N, K, 0.5))
     ctx.sync()
