@@ -165,6 +165,8 @@ int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp
 int ltx_dist_get_unique_id(void* id_out_128);
 int ltx_dist_init(ltx_ctx* ctx, const void* unique_id_128, int rank, int world_size, int sp_size, int pass_groups);
 int ltx_dist_info(const ltx_ctx* ctx, int* rank, int* world_size, int* sp_size, int* pass_groups);
+/* Destroys the communicators (collective); the context can be re-initialised with a different layout afterwards. */
+int ltx_dist_shutdown(ltx_ctx* ctx);
 
 /* Number of kernels launched by this context so far (bench.py reports the per-step delta as gpu_launches). */
 uint64_t ltx_launch_count(const ltx_ctx* ctx);

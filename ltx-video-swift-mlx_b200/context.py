@@ -156,6 +156,9 @@ class LtxContext:
         assert len(unique_id) == 128
         self._check(self.lib.ltx_dist_init(self.handle, unique_id, rank, world_size, sp_size, pass_groups))
 
+    def dist_shutdown(self):
+        self._check(self.lib.ltx_dist_shutdown(self.handle))
+
     # ------------------------------------------------------------------ weights
     def load_tensor(self, key: str, value):
         code = _dtype_code(value)

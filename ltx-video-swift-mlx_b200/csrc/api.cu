@@ -137,6 +137,13 @@ int ltx_dist_init(ltx_ctx* c, const void* unique_id_128, int rank, int world_siz
   });
 }
 
+int ltx_dist_shutdown(ltx_ctx* c) {
+  return guarded(c, [&] {
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+    dist_destroy(c);
+  });
+}
+
 int ltx_dist_info(const ltx_ctx* c, int* rank, int* world_size, int* sp_size, int* pass_groups) {
   if (!c) return LTX_ERR_INVALID_ARGUMENT;
   if (rank) *rank = c->dist.rank;
