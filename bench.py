@@ -377,6 +377,20 @@ def run_ours(args, rank, world, local_rank):
         return
 
     pk = peaks()
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (FFN-in launch), if present
+    traffic, traffic_note = None, None
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_gemm_ffn_in_ncu_raw.csv"))))
+        hdr, units, last = rows[0], rows[1], rows[-1]
+
+        def _bytes(k):
+            v, u = float(last[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
+        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01_gemm_ffn_in_ncu_raw.csv"
+    except Exception:
+        pass
     gemm = prof["gemm"]
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     conv = vprof["conv3d"]
@@ -393,7 +407,8 @@ def run_ours(args, rank, world, local_rank):
                  path="ltx_dit_forward + ltx_guided_euler_step with pinned host buffers (text cached by context_key)"),
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05 (all GEMM launches of one step)", achieved=achieved,
-                      peak=pk["tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["tflops_sustained"], traffic=None,
+                      peak=pk["tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["tflops_sustained"], traffic=traffic,
+                      traffic_note=traffic_note,
                       peak_source=pk["source"] + ", sustained bf16", launches=gemm["launches"], ms=gemm["ms"]),
         kernel_classes={k: v for k, v in prof.items() if v["launches"]},
         cpu_baseline=dict(value=1.0 / cpu_sec if cpu_sec == cpu_sec else None, unit="steps/s", cores=cores, kind="port", sample=desc),
