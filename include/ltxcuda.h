@@ -75,8 +75,10 @@ int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dt
 /* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
  * which: 1 = DiT, 2 = VAE decoder, 3 = both. */
 int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);
-/* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16.  Replaces quantize(model:groupSize:bits:)
- * (Pipeline/LTXPipeline.swift:323-333); 8 / 4 (MLX affine, group 64) are reserved and return LTX_ERR_UNSUPPORTED. */
+/* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16; 8 / 4 replace every GEMM weight of the DiT by
+ * per-64-group affine codes (w ~= s*q + beta) consumed by the dequant-fused GEMM -- the counterpart of
+ * quantize(model:groupSize:64,bits:) (Pipeline/LTXPipeline.swift:323-333).  The exact MLX rounding rule is not in the
+ * reference tree; ours is plain min/max affine with bf16 scales. */
 int ltx_finalize_weights(ltx_ctx* ctx, int quant_bits, int group_size);
 
 /* Per-forward runtime flags: setSTGSkipFlags / clearSTGSkipFlags / setCrossAttentionScale
@@ -186,6 +188,12 @@ int ltx_op_gemm(ltx_ctx* ctx, const void* A, const void* B, const float* bias, v
 /* x[M,N] (fp32) += (A B^T + bias) * (gate_a[n] + gate_b[n]) * scale ; shadow (bf16, nullable) = new x. */
 int ltx_op_gemm_resid(ltx_ctx* ctx, const void* A, const void* B, const float* bias, float* x, const float* gate_a,
                       const float* gate_b, void* shadow, int M, int N, int K, float scale);
+/* per-64-group affine quantiser / dequantiser and the dequant-fused GEMM (codes [N,K] bytes or [N,K/2] nibbles;
+ * scales, biases fp32 [K/64, N]); mode / force_bn as in ltx_op_gemm. */
+int ltx_op_quantize(ltx_ctx* ctx, const void* w_bf16, int N, int K, int bits, void* q_out, float* scales_out, float* biases_out);
+int ltx_op_dequantize(ltx_ctx* ctx, const void* q, const float* scales, const float* biases, int N, int K, int bits, void* w_bf16);
+int ltx_op_gemm_q(ltx_ctx* ctx, const void* A, const void* q, const float* scales, const float* biases, int bits,
+                  const float* bias, void* C, int M, int N, int K, int mode, int force_bn);
 /* O = softmax(Q K^T * scale + key_bias) V ; Q [B*Nq, H*128], K [B*Nk, H*128], Vt [H*128, B*ldvb] (batch b owns
  * columns [b*ldvb, b*ldvb + Nk), ldvb % 8 == 0), all bf16. */
 int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,

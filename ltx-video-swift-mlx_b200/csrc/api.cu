@@ -197,9 +197,12 @@ int ltx_init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
 
 int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
   return guarded(c, [&] {
-    (void)group_size;
-    LTX_CHECK(quant_bits == 16, LTX_ERR_UNSUPPORTED, "only bf16 weights (quant_bits = 16) are implemented");
-    if (c->tensors.count("patchify_proj.weight")) dit_finalize(c);
+    LTX_CHECK(quant_bits == 16 || quant_bits == 8 || quant_bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");
+    LTX_CHECK(quant_bits == 16 || group_size == 64, LTX_ERR_UNSUPPORTED, "only group_size 64 is implemented");
+    if (c->tensors.count("patchify_proj.weight")) {
+      dit_finalize(c);
+      if (quant_bits != 16) dit_quantize(c, quant_bits);
+    }
     if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);
     LTX_CHECK(c->dit_ready || c->vae.ready, LTX_ERR_WEIGHTS, "no weights loaded");
     LTX_CUDA(cudaStreamSynchronize(c->stream));
@@ -458,6 +461,36 @@ int ltx_op_gemm_resid(ltx_ctx* c, const void* A, const void* B, const float* bia
     e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = bias; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = 0;
     e.rows_per_gate = M > 0 ? M : 1; e.shadow = reinterpret_cast<bf16*>(shadow); e.lds = N; e.scale = scale;
     launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_quantize(ltx_ctx* c, const void* w_bf16, int N, int K, int bits, void* q_out, float* scales_out, float* biases_out) {
+  return guarded(c, [&] {
+    launch_quantize(reinterpret_cast<const bf16*>(w_bf16), N, K, bits, reinterpret_cast<uint8_t*>(q_out), scales_out, biases_out,
+                    c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_dequantize(ltx_ctx* c, const void* q, const float* scales, const float* biases, int N, int K, int bits, void* w_bf16) {
+  return guarded(c, [&] {
+    QuantW W;
+    W.q = reinterpret_cast<const uint8_t*>(q); W.scales = scales; W.biases = biases; W.bits = bits; W.n = N; W.k = K;
+    launch_dequantize(W, reinterpret_cast<bf16*>(w_bf16), c->stream);
+    c->launches++;
+  });
+}
+
+int ltx_op_gemm_q(ltx_ctx* c, const void* A, const void* q, const float* scales, const float* biases, int bits, const float* bias,
+                  void* C, int M, int N, int K, int mode, int force_bn) {
+  return guarded(c, [&] {
+    LTX_CHECK(mode == EPI_BF16 || mode == EPI_GELU_BF16 || mode == EPI_F32, LTX_ERR_INVALID_ARGUMENT, "bad mode");
+    QuantW W;
+    W.q = reinterpret_cast<const uint8_t*>(q); W.scales = scales; W.biases = biases; W.bits = bits; W.n = N; W.k = K;
+    GemmEpi e;
+    e.mode = mode; e.out = C; e.ldo = N; e.bias = bias;
+    launch_gemm_q(reinterpret_cast<const bf16*>(A), K, W, M, N, K, e, c->stream, force_bn);
     c->launches++;
   });
 }

@@ -114,6 +114,8 @@ struct ltx_ctx {
   uint64_t launches = 0;
 
   std::map<std::string, ltx::DevTensor> tensors;  // raw tensors by post-mapping key
+  std::unordered_map<const void*, ltx::QuantW> qw;  // quantised replacements, keyed by the bf16 weight pointer they replace
+  int quant_bits = 16;
   std::vector<void*> owned;                       // packed allocations made by finalize
   bool dit_ready = false;
   std::vector<ltx::BlockWeights> blocks;
@@ -173,6 +175,7 @@ struct ProfScope {
 };
 // dit.cu
 void dit_finalize(ltx_ctx* c);
+void dit_quantize(ltx_ctx* c, int bits);
 void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
                      const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
                      int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev);

@@ -19,7 +19,29 @@ namespace {
 void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e,
           int a_kblock = 0, int64_t a_kblock_stride = 0) {
   ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
+  auto it = c->qw.empty() ? c->qw.end() : c->qw.find(B);
+  if (it != c->qw.end()) {   // weight was replaced by int8 / int4 codes: dequant-fused kernel
+    LTX_CHECK(a_kblock == 0, LTX_ERR_UNSUPPORTED, "quantised weights are not supported together with sequence parallelism");
+    launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream);
+    return;
+  }
   launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
+}
+// V^T [D, ncols] (row pitch ld_out) = (h Wv^T + bv)^T for one batch.  bf16 weights: run the projection with the weight as
+// the A operand so the result lands transposed; quantised weights must be the B operand: project into `tmp`, transpose.
+void v_transposed(ltx_ctx* c, const bf16* wv, const float* bv, const bf16* hrows, int rows, int D, bf16* out, int64_t ld_out,
+                  bf16* tmp) {
+  if (c->qw.empty() || c->qw.find(wv) == c->qw.end()) {
+    GemmEpi ev;
+    ev.mode = EPI_BF16; ev.out = out; ev.ldo = ld_out; ev.bias = bv; ev.bias_per_row = 1;
+    gemm(c, wv, D, hrows, D, D, rows, D, ev);
+    return;
+  }
+  GemmEpi ev;
+  ev.mode = EPI_BF16; ev.out = tmp; ev.ldo = D; ev.bias = bv;
+  gemm(c, hrows, D, wv, D, rows, D, D, ev);
+  ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * rows * D);
+  launch_transpose_bf16(tmp, D, rows, D, out, ld_out, c->stream);
 }
 void attention(ltx_ctx* c, const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                const float* bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale) {
@@ -159,11 +181,9 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
     ek.mode = EPI_BF16; ek.out = kd; ek.ldo = D; ek.bias = a.bk;
     gemm(c, c->c2.as<bf16>(), D, a.wk, D, static_cast<int>(R), D, D, ek);
     qknorm(c, kd, D, static_cast<int>(R), D, a.k_norm, nullptr, nullptr, 1, g.norm_eps);
-    for (int b = 0; b < B; ++b) {  // V^T[D, S] = Wv [D, D] * c_b^T, one column block per batch
-      GemmEpi ev;
-      ev.mode = EPI_BF16; ev.out = vd + b * tc.ldv; ev.ldo = B * tc.ldv; ev.bias = a.bv; ev.bias_per_row = 1;
-      gemm(c, a.wv, D, c->c2.as<bf16>() + static_cast<int64_t>(b) * S * D, D, D, S, D, ev);
-    }
+    for (int b = 0; b < B; ++b)  // V^T[D, S] per batch, one column block each
+      v_transposed(c, a.wv, a.bv, c->c2.as<bf16>() + static_cast<int64_t>(b) * S * D, S, D, vd + b * tc.ldv, B * tc.ldv,
+                   c->c1.as<bf16>());
   }
   // An all-ones mask (what the real text connector emits, LTXTextEncoder.swift:514-520) adds a zero bias: skip it.
   bool any_masked = false;
@@ -265,6 +285,56 @@ void dit_finalize(ltx_ctx* c) {
   }
   c->scratch.reserve(64 * sizeof(double));
   c->dit_ready = true;
+}
+
+// Replace every GEMM weight of the DiT by per-64-group affine codes (the reference quantises every Linear,
+// P/LTXPipeline.swift:323-333); the bf16 copies are freed.  The M = 1 timestep-MLP GEMVs keep bf16 weights.
+void dit_quantize(ltx_ctx* c, int bits) {
+  LTX_CHECK(c->dit_ready, LTX_ERR_WEIGHTS, "DiT weights not finalized");
+  LTX_CHECK(bits == 8 || bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");
+  const ltx_config& g = c->cfg;
+  const int D = g.num_heads * g.head_dim, FF = g.ffn_mult * D;
+  auto release = [&](const void* p) {
+    for (auto it = c->tensors.begin(); it != c->tensors.end(); ++it)
+      if (it->second.ptr == p) { cudaFree(it->second.ptr); c->tensors.erase(it); return; }
+    for (auto it = c->owned.begin(); it != c->owned.end(); ++it)
+      if (*it == p) { cudaFree(*it); c->owned.erase(it); return; }
+  };
+  // Each quantised weight gets a 16-byte device allocation whose address is its identity from now on: the struct field
+  // is repointed to it and gemm() recognises it in c->qw (the freed bf16 address could be handed out again by cudaMalloc).
+  std::vector<const void*> to_free;
+  auto qf = [&](const bf16*& w, int N, int K) {
+    LTX_CHECK(K % 64 == 0, LTX_ERR_INVALID_CONFIGURATION, "quantisation needs every Linear input width to be a multiple of 64");
+    uint8_t* q = nullptr;
+    float *s = nullptr, *b = nullptr;
+    void* handle = nullptr;
+    const size_t qbytes = static_cast<size_t>(N) * K * bits / 8, sbytes = static_cast<size_t>(K / 64) * N * 4;
+    LTX_CUDA(cudaMalloc(&q, qbytes));
+    LTX_CUDA(cudaMalloc(&s, sbytes));
+    LTX_CUDA(cudaMalloc(&b, sbytes));
+    LTX_CUDA(cudaMalloc(&handle, 16));
+    c->owned.push_back(q); c->owned.push_back(s); c->owned.push_back(b); c->owned.push_back(handle);
+    launch_quantize(w, N, K, bits, q, s, b, c->stream);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+    QuantW r;
+    r.q = q; r.scales = s; r.biases = b; r.bits = bits; r.n = N; r.k = K;
+    c->qw[handle] = r;
+    to_free.push_back(w);
+    w = reinterpret_cast<const bf16*>(handle);
+  };
+  qf(c->w_patch, D, g.in_channels);
+  qf(c->w_c1, D, g.caption_channels);
+  qf(c->w_c2, D, D);
+  qf(c->w_out, g.out_channels, D);
+  for (auto& b : c->blocks) {
+    qf(b.a1.wq, 2 * D, D);            // packed q|k
+    b.a1.wk = nullptr;
+    qf(b.a1.wv, D, D); qf(b.a1.wo, D, D);
+    qf(b.a2.wq, D, D); qf(b.a2.wk, D, D); qf(b.a2.wv, D, D); qf(b.a2.wo, D, D);
+    qf(b.w_in, FF, D); qf(b.w_out, D, FF);
+  }
+  for (const void* p : to_free) release(p);
+  c->quant_bits = bits;
 }
 
 void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
@@ -387,11 +457,8 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
       gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
       if (P == 1) {
-        for (int b = 0; b < B; ++b) {  // V^T, one column block per batch
-          GemmEpi ev;
-          ev.mode = EPI_BF16; ev.out = vt + b * ldv; ev.ldo = B * ldv; ev.bias = bw.a1.bv; ev.bias_per_row = 1;
-          gemm(c, bw.a1.wv, D, h + static_cast<int64_t>(b) * N * D, D, D, N, D, ev);
-        }
+        for (int b = 0; b < B; ++b)  // V^T, one column block per batch
+          v_transposed(c, bw.a1.wv, bw.a1.bv, h + static_cast<int64_t>(b) * N * D, N, D, vt + b * ldv, B * ldv, q2);
         qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rows_per_b, eps, bw.a1.k_norm);
         attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
       } else {

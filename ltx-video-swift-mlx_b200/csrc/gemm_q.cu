@@ -1,0 +1,335 @@
+// Dequant-fused GEMM for sm_100a: C[M,N] = A[M,K] * dequant(Wq)[N,K]^T with the fused epilogues of gemm.cu.
+//
+// Replaces MLX `QuantizedLinear` after quantize(model:groupSize:64,bits:8|4) (P/LTXPipeline.swift:323-333,
+// C/LTXQuantizationConfig.swift:19-62): affine per-64-group weights w ~= s * q + beta, q in [0, 2^bits - 1].
+// The quantisation rule itself lives in MLX (not in the reference tree) -> parity for this kernel is pinned as
+// "dequant-fused GEMM == bf16 GEMM on the dequantised weights" (SURVEY H8); the device quantiser below is ours.
+//
+// Storage: q as bytes [N, K] (8-bit) or packed nibbles [N, K/2] (4-bit, even k in the low nibble); scale / bias fp32
+// (bf16-representable, like MLX's bf16 scales) transposed to [K/64, N] so one k-block's 64-wide group row is contiguous.
+//
+// Kernel = gemm.cu's pipeline plus a dequant stage between TMA and MMA (group size 64 == BK, one scale per row per k-block):
+//   warp 0     : TMA producer -- A tile (bf16, swizzled) + raw q tile (bytes, unswizzled) per stage
+//   warps 6-13 : dequant      -- 16 codes per thread-chunk: byte -> fp32 via PRMT magic (0x4B000000 | q) - 2^23, one FFMA with
+//                                (s, beta), cvt to bf16x2, 16-byte stores into the 128B-swizzled K-major B operand buffer,
+//                                fence.proxy.async, arrive
+//   warp 1     : MMA issuer (tcgen05.mma, TMEM accumulators, two stages)      warps 2-5: epilogue
+// HBM / L2 traffic for weights drops 2x (int8) / 4x (int4); the tensor core still runs bf16 x bf16 -> fp32.
+#include "gemm_epilogue.cuh"
+#include "ltx_internal.h"
+#include "ptx.cuh"
+
+namespace ltx {
+
+namespace {
+
+constexpr int QBM = 128, QBK = 64;
+constexpr int Q_THREADS = 448;      // 14 warps
+constexpr int Q_DEQ_WARPS = 8;
+constexpr int Q_STAGES = 3;
+constexpr int Q_BN_MAX = 256;
+constexpr uint32_t QA_BYTES = QBM * QBK * 2;           // 16 KB
+constexpr uint32_t QR_STRIDE = Q_BN_MAX * QBK;         // raw codes, up to 16 KB
+constexpr uint32_t QB_STRIDE = Q_BN_MAX * QBK * 2;     // dequantised bf16 operand, up to 32 KB
+constexpr size_t Q_SMEM = 1024 + Q_STAGES * (QA_BYTES + QR_STRIDE + QB_STRIDE) + (3 * Q_STAGES + 4) * 8 + 16;
+
+__device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s, float b) {
+  // two codes (bytes i0, i1 of `word`) -> s*q+b -> packed bf16x2
+  const uint32_t sel0 = 0x7650u + i0, sel1 = 0x7650u + i1;
+  const float f0 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel0)) - 8388608.0f;
+  const float f1 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel1)) - 8388608.0f;
+  return pack_bf16(fmaf(f0, s, b), fmaf(f1, s, b));
+}
+
+template <int MODE, int BITS>
+__global__ void __launch_bounds__(Q_THREADS, 1)
+gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, int M, int N, int K, int BN,
+               const float* __restrict__ scales, const float* __restrict__ biases, const GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + Q_STAGES * QA_BYTES;
+  uint8_t* sR = sB + Q_STAGES * QB_STRIDE;
+  uint64_t* full_raw = reinterpret_cast<uint64_t*>(sR + Q_STAGES * QR_STRIDE);
+  uint64_t* full_deq = full_raw + Q_STAGES;
+  uint64_t* empty = full_deq + Q_STAGES;
+  uint64_t* tfull = empty + Q_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + QBM - 1) / QBM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + QBK - 1) / QBK;
+  constexpr int ROW_BYTES = (BITS == 8) ? 64 : 32;       // raw bytes per row per k-block
+  const uint32_t raw_bytes = static_cast<uint32_t>(BN) * ROW_BYTES;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmQ);
+    for (int i = 0; i < Q_STAGES; ++i) {
+      mbar_init(&full_raw[i], 1);
+      mbar_init(&full_deq[i], Q_DEQ_WARPS);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_raw[stage], QA_BYTES + raw_bytes);
+          tma_load_2d(sA + stage * QA_BYTES, &tmA, &full_raw[stage], kb * QBK, m_blk * QBM);
+          tma_load_2d(sR + stage * QR_STRIDE, &tmQ, &full_raw[stage], kb * ROW_BYTES, n_blk * BN);
+          if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(QBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int as = t & 1;
+        const uint32_t aphase = (t >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Q_BN_MAX;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_deq[stage], phase);   // dequant warps waited on the TMA barrier first: A has landed too
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * QA_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * QB_STRIDE);
+#pragma unroll
+          for (int k = 0; k < QBK / 16; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int as = t & 1;
+      const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * QBM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Q_BN_MAX;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
+      }
+      if (BN & 16) {
+        uint32_t r[32];
+        tmem_ld16(taddr + (BN & ~31), r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  } else {
+    // ---- dequant warps: raw codes -> bf16 operand tile (K-major, 128 B per row, 128B swizzle)
+    const int dt = threadIdx.x - 6 * 32;                 // 0..255
+    constexpr int CH_PER_ROW = ROW_BYTES / 16;           // 16-byte raw chunks per row: 4 (int8) / 2 (int4)
+    const int chunks = BN * CH_PER_ROW;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile / num_m) * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_raw[stage], phase);
+        const uint8_t* raw = sR + stage * QR_STRIDE;
+        uint8_t* dst = sB + stage * QB_STRIDE;
+        const float* srow = scales + static_cast<int64_t>(kb) * N;
+        const float* brow = biases + static_cast<int64_t>(kb) * N;
+        for (int c = dt; c < chunks; c += Q_DEQ_WARPS * 32) {
+          const int row = c / CH_PER_ROW, part = c % CH_PER_ROW;
+          const int n = n0 + row;
+          const float s = n < N ? __ldg(srow + n) : 0.f, b = n < N ? __ldg(brow + n) : 0.f;
+          const uint4 u = *reinterpret_cast<const uint4*>(raw + row * ROW_BYTES + part * 16);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          uint8_t* drow = dst + row * 128;
+          if (BITS == 8) {
+            // 16 codes -> logical 16-byte chunks 2*part, 2*part+1 of the row
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o[2 * i] = deq2(w[i], 0, 1, s, b);
+              o[2 * i + 1] = deq2(w[i], 2, 3, s, b);
+            }
+            *reinterpret_cast<uint4*>(drow + (((2 * part) ^ (row & 7)) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(drow + (((2 * part + 1) ^ (row & 7)) * 16)) = make_uint4(o[4], o[5], o[6], o[7]);
+          } else {
+            // 32 codes (nibbles, even k low) -> logical chunks 4*part .. 4*part+3
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t lo = w[i] & 0x0F0F0F0Fu, hi = (w[i] >> 4) & 0x0F0F0F0Fu;   // codes k = 8i + {0,2,4,6} / {1,3,5,7}
+              // interleave back to k order: (lo.b0, hi.b0), (lo.b1, hi.b1), ...
+              const uint32_t e01 = __byte_perm(lo, hi, 0x5140);   // bytes: lo0, hi0, lo1, hi1
+              const uint32_t e23 = __byte_perm(lo, hi, 0x7362);   // bytes: lo2, hi2, lo3, hi3
+              const uint4 v = make_uint4(deq2(e01, 0, 1, s, b), deq2(e01, 2, 3, s, b), deq2(e23, 0, 1, s, b), deq2(e23, 2, 3, s, b));
+              *reinterpret_cast<uint4*>(drow + (((4 * part + i) ^ (row & 7)) * 16)) = v;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_deq[stage]);
+        if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device quantiser: one warp per (row, 64-group).  Affine min/max: s = (max - min) / (2^bits - 1), beta = min,
+// q = clamp(rint((w - beta) / s)); s and beta are rounded to bf16 (MLX keeps them in the weight dtype).
+// ---------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void quantize_kernel(const bf16* __restrict__ w, int N, int K, uint8_t* __restrict__ q, float* __restrict__ scales,
+                                float* __restrict__ biases) {
+  const int groups = K / 64;
+  const int64_t gid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gid >= static_cast<int64_t>(N) * groups) return;
+  const int n = static_cast<int>(gid / groups), g = static_cast<int>(gid % groups);
+  const bf16* src = w + static_cast<int64_t>(n) * K + g * 64 + lane * 2;
+  const float v0 = __bfloat162float(src[0]), v1 = __bfloat162float(src[1]);
+  const float mn = -warp_max(-fminf(v0, v1)), mx = warp_max(fmaxf(v0, v1));
+  constexpr float LEVELS = (BITS == 8) ? 255.f : 15.f;
+  float s = (mx - mn) / LEVELS;
+  if (!(s > 0.f)) s = 1.0f;
+  s = __bfloat162float(__float2bfloat16(s));
+  const float beta = __bfloat162float(__float2bfloat16(mn));
+  const int q0 = static_cast<int>(fminf(fmaxf(rintf((v0 - beta) / s), 0.f), LEVELS));
+  const int q1 = static_cast<int>(fminf(fmaxf(rintf((v1 - beta) / s), 0.f), LEVELS));
+  if (BITS == 8) {
+    uint8_t* dst = q + static_cast<int64_t>(n) * K + g * 64 + lane * 2;
+    dst[0] = static_cast<uint8_t>(q0);
+    dst[1] = static_cast<uint8_t>(q1);
+  } else {
+    q[static_cast<int64_t>(n) * (K / 2) + g * 32 + lane] = static_cast<uint8_t>(q0 | (q1 << 4));
+  }
+  if (lane == 0) {
+    scales[static_cast<int64_t>(g) * N + n] = s;
+    biases[static_cast<int64_t>(g) * N + n] = beta;
+  }
+}
+
+template <int BITS>
+__global__ void dequantize_kernel(const uint8_t* __restrict__ q, const float* __restrict__ scales,
+                                  const float* __restrict__ biases, int N, int K, bf16* __restrict__ w) {
+  const int64_t total = static_cast<int64_t>(N) * K;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+    int code;
+    if (BITS == 8) code = q[i];
+    else {
+      const uint8_t b = q[static_cast<int64_t>(n) * (K / 2) + k / 2];
+      code = (k & 1) ? (b >> 4) : (b & 15);
+    }
+    const int g = k / 64;
+    w[i] = __float2bfloat16(fmaf(static_cast<float>(code), scales[static_cast<int64_t>(g) * N + n], biases[static_cast<int64_t>(g) * N + n]));
+  }
+}
+
+template <int MODE, int BITS>
+void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int K, int BN, const float* s, const float* b,
+              const GemmEpi& epi, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_q_tcgen05<MODE, BITS>;
+  if (!configured) {
+    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Q_SMEM)));
+    configured = true;
+  }
+  const int tiles = ((M + QBM - 1) / QBM) * ((N + BN - 1) / BN);
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  kern<<<grid, Q_THREADS, Q_SMEM, stream>>>(tmA, tmQ, M, N, K, BN, s, b, epi);
+  LTX_CUDA(cudaGetLastError());
+}
+
+template <int BITS>
+void launch_q_mode(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int K, int BN, const float* s, const float* b,
+                   const GemmEpi& epi, cudaStream_t stream) {
+  switch (epi.mode) {
+    case EPI_BF16: launch_q<EPI_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    case EPI_GELU_BF16: launch_q<EPI_GELU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    case EPI_GATE_RESID: launch_q<EPI_GATE_RESID, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    case EPI_F32: launch_q<EPI_F32, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
+  }
+}
+
+}  // namespace
+
+void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
+                   int force_bn) {
+  LTX_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0, 2, "quantised GEMM: K must be a multiple of the group size 64");
+  LTX_CHECK(W.bits == 8 || W.bits == 4, 2, "quantised GEMM: 8 or 4 bits");
+  LTX_CHECK(W.n == N && W.k == K && W.q && W.scales && W.biases, 2, "quantised GEMM: weight shape mismatch");
+  LTX_CHECK(lda % 8 == 0, 2, "quantised GEMM: lda must be a multiple of 8");
+  int bn = force_bn ? force_bn : gemm_fit_tile_width(M, N);
+  LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "quantised GEMM: bad tile width");
+  const uint64_t row_bytes = W.bits == 8 ? K : K / 2;
+  CUtensorMap tmA = make_tmap_2d(A, M, K, lda, QBM);
+  CUtensorMap tmQ = make_tmap_u8(W.q, N, row_bytes, bn, W.bits == 8 ? 64 : 32);
+  if (W.bits == 8)
+    launch_q_mode<8>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, epi, stream);
+  else
+    launch_q_mode<4>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, epi, stream);
+}
+
+void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s) {
+  LTX_CHECK(K % 64 == 0 && (bits == 8 || bits == 4), 2, "quantize: K % 64 == 0 and bits in {4, 8}");
+  const int64_t warps = static_cast<int64_t>(N) * (K / 64);
+  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+  if (bits == 8)
+    quantize_kernel<8><<<blocks, 256, 0, s>>>(w, N, K, q, scales, biases);
+  else
+    quantize_kernel<4><<<blocks, 256, 0, s>>>(w, N, K, q, scales, biases);
+  LTX_CUDA(cudaGetLastError());
+}
+
+void launch_dequantize(const QuantW& W, bf16* w, cudaStream_t s) {
+  int64_t blocks = (static_cast<int64_t>(W.n) * W.k + 255) / 256;
+  if (blocks > 16384) blocks = 16384;
+  if (W.bits == 8)
+    dequantize_kernel<8><<<static_cast<int>(blocks), 256, 0, s>>>(W.q, W.scales, W.biases, W.n, W.k, w);
+  else
+    dequantize_kernel<4><<<static_cast<int>(blocks), 256, 0, s>>>(W.q, W.scales, W.biases, W.n, W.k, w);
+  LTX_CUDA(cudaGetLastError());
+}
+
+}  // namespace ltx

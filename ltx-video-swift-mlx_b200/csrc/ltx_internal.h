@@ -76,6 +76,21 @@ struct GemmEpi {
 // m * lda + k % a_kblock] (a_kblock % 64 == 0, lda = a_kblock).
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                  cudaStream_t stream, int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
+int gemm_fit_tile_width(int M, int N);
+// ---------------------------------------------------------------- quantised weights (gemm_q.cu)
+struct QuantW {
+  const uint8_t* q = nullptr;    // [N, K] codes (8-bit) or [N, K/2] packed nibbles (4-bit)
+  const float* scales = nullptr; // [K/64, N]
+  const float* biases = nullptr; // [K/64, N]
+  int bits = 0, n = 0, k = 0;
+};
+// C[M,N] = A[M,K] * (s*q + beta)[N,K]^T with the epilogues of launch_gemm (group size 64)
+void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
+                   int force_bn = 0);
+void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s);
+void launch_dequantize(const QuantW& W, bf16* w, cudaStream_t s);
+// uint8 matrix [rows, row_bytes], box [box_rows, box_bytes], no swizzle
+CUtensorMap make_tmap_u8(const void* base, uint64_t rows, uint64_t row_bytes, uint32_t box_rows, uint32_t box_bytes);
 // bf16 [R, C] (row pitch ld_in) -> [C, R] (row pitch ld_out)
 void launch_transpose_bf16(const bf16* in, int64_t ld_in, int R, int C, bf16* out, int64_t ld_out, cudaStream_t s);
 

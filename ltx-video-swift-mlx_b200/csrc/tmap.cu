@@ -75,6 +75,21 @@ CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2
   return m;
 }
 
+CUtensorMap make_tmap_u8(const void* base, uint64_t rows, uint64_t row_bytes, uint32_t box_rows, uint32_t box_bytes) {
+  LTX_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_bytes % 16 == 0, 2, "TMA u8: 16-byte alignment");
+  LTX_CHECK(box_rows <= 256 && box_bytes % 16 == 0 && box_bytes <= 256, 2, "TMA u8 box");
+  CUtensorMap m;
+  cuuint64_t dims[2] = {row_bytes, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_bytes, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LTX_CHECK(r == CUDA_SUCCESS, 3, "cuTensorMapEncodeTiled(u8) failed: " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {
