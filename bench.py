@@ -332,6 +332,28 @@ def run_ours(args, rank, world, local_rank):
         return t
 
     if world == 1:
+        # qint8 weights (the reference's --transformer-quant qint8 path): same step, dequant-fused GEMMs
+        try:
+            cq = LtxContext(LTXTransformerConfig(), local_rank)
+            cq.init_random_weights(1, seed=99)
+            cq.finalize_weights(quant_bits=8)
+            sq = torch.cuda.ExternalStream(cq.stream, device=torch.device("cuda", local_rank))
+            cq.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
+            for i in range(3):
+                cq.denoise_step(pairs[i][0], pairs[i][1], i)
+            cq.sync()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(sq)
+            for i in range(6):
+                cq.denoise_step(pairs[i][0], pairs[i][1], i)
+            b.record(sq)
+            cq.sync()
+            tq = a.elapsed_time(b) / 6
+            extras["qint8"] = dict(desc="same step with int8 group-64 weights (dequant-fused tcgen05 GEMM)", ms_per_step=tq,
+                                   steps_per_s=1e3 / tq)
+            cq.close()
+        except Exception as e:   # report, do not hide
+            extras["qint8"] = dict(error=str(e))
         tg = time_guided()
         tv = time_vae121()
         extras["guided_cfg3"] = dict(desc="dev CFG 4.0 + STG 0.5 (3 forwards/step), 1 GPU", ms_per_step=tg, steps_per_s=1e3 / tg)

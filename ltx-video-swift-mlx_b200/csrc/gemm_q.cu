@@ -33,12 +33,14 @@ constexpr uint32_t QR_STRIDE = Q_BN_MAX * QBK;         // raw codes, up to 16 KB
 constexpr uint32_t QB_STRIDE = Q_BN_MAX * QBK * 2;     // dequantised bf16 operand, up to 32 KB
 constexpr size_t Q_SMEM = 1024 + Q_STAGES * (QA_BYTES + QR_STRIDE + QB_STRIDE) + (3 * Q_STAGES + 4) * 8 + 16;
 
-__device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s, float b) {
-  // two codes (bytes i0, i1 of `word`) -> s*q+b -> packed bf16x2
-  const uint32_t sel0 = 0x7650u + i0, sel1 = 0x7650u + i1;
-  const float f0 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel0)) - 8388608.0f;
-  const float f1 = __uint_as_float(__byte_perm(word, 0x4B000000u, sel1)) - 8388608.0f;
-  return pack_bf16(fmaf(f0, s, b), fmaf(f1, s, b));
+__device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s, float bm) {
+  // two codes (bytes i0, i1 of `word`) -> s*q+beta -> packed bf16x2.  PRMT drops the code byte into mantissa bits [15:8]
+  // of 0x47000000 = 2^15, giving the fp32 value 2^15 + q exactly; one FFMA with bm = beta - s*2^15 then yields s*q + beta
+  // with a single rounding (s, beta are bf16 values, so bm is exact in fp32).
+  const uint32_t sel0 = 0x7604u + (i0 << 4), sel1 = 0x7604u + (i1 << 4);
+  const float f0 = __uint_as_float(__byte_perm(word, 0x47000000u, sel0));
+  const float f1 = __uint_as_float(__byte_perm(word, 0x47000000u, sel1));
+  return pack_bf16(fmaf(f0, s, bm), fmaf(f1, s, bm));
 }
 
 template <int MODE, int BITS>
@@ -155,23 +157,48 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- dequant warps: raw codes -> bf16 operand tile (K-major, 128 B per row, 128B swizzle)
     const int dt = threadIdx.x - 6 * 32;                 // 0..255
     constexpr int CH_PER_ROW = ROW_BYTES / 16;           // 16-byte raw chunks per row: 4 (int8) / 2 (int4)
+    constexpr int MAX_IT = 4;                            // BN * CH_PER_ROW <= 1024 chunks over 256 threads
     const int chunks = BN * CH_PER_ROW;
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n0 = (tile / num_m) * BN;
+      // the rows this thread converts are the same for every k-block of the tile; their (scale, bias) for the NEXT
+      // k-block are fetched while the current one is converted, so the L2 latency is off the critical path
+      float sc[MAX_IT], bm[MAX_IT];
+      auto fetch = [&](int kb, float (&so)[MAX_IT], float (&bo)[MAX_IT]) {
+        const float* srow = scales + static_cast<int64_t>(kb) * N;
+        const float* brow = biases + static_cast<int64_t>(kb) * N;
+#pragma unroll
+        for (int it = 0; it < MAX_IT; ++it) {
+          const int c = dt + it * (Q_DEQ_WARPS * 32);
+          const int n = n0 + c / CH_PER_ROW;
+          const bool ok = c < chunks && n < N;
+          const float sv = ok ? __ldg(srow + n) : 0.f, bv = ok ? __ldg(brow + n) : 0.f;
+          so[it] = sv;
+          bo[it] = fmaf(-32768.0f, sv, bv);
+        }
+      };
+      fetch(0, sc, bm);
       for (int kb = 0; kb < num_k; ++kb) {
+        float sn[MAX_IT], bn[MAX_IT];
+        if (kb + 1 < num_k) fetch(kb + 1, sn, bn);
         mbar_wait(&full_raw[stage], phase);
         const uint8_t* raw = sR + stage * QR_STRIDE;
         uint8_t* dst = sB + stage * QB_STRIDE;
-        const float* srow = scales + static_cast<int64_t>(kb) * N;
-        const float* brow = biases + static_cast<int64_t>(kb) * N;
-        for (int c = dt; c < chunks; c += Q_DEQ_WARPS * 32) {
+        uint4 u[MAX_IT];
+#pragma unroll
+        for (int it = 0; it < MAX_IT; ++it) {
+          const int c = dt + it * (Q_DEQ_WARPS * 32);
+          if (c < chunks) u[it] = *reinterpret_cast<const uint4*>(raw + (c / CH_PER_ROW) * ROW_BYTES + (c % CH_PER_ROW) * 16);
+        }
+#pragma unroll
+        for (int it = 0; it < MAX_IT; ++it) {
+          const int c = dt + it * (Q_DEQ_WARPS * 32);
+          if (c >= chunks) continue;
           const int row = c / CH_PER_ROW, part = c % CH_PER_ROW;
-          const int n = n0 + row;
-          const float s = n < N ? __ldg(srow + n) : 0.f, b = n < N ? __ldg(brow + n) : 0.f;
-          const uint4 u = *reinterpret_cast<const uint4*>(raw + row * ROW_BYTES + part * 16);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          const float s = sc[it], b = bm[it];
+          const uint32_t w[4] = {u[it].x, u[it].y, u[it].z, u[it].w};
           uint8_t* drow = dst + row * 128;
           if (BITS == 8) {
             // 16 codes -> logical 16-byte chunks 2*part, 2*part+1 of the row
@@ -188,8 +215,7 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const uint32_t lo = w[i] & 0x0F0F0F0Fu, hi = (w[i] >> 4) & 0x0F0F0F0Fu;   // codes k = 8i + {0,2,4,6} / {1,3,5,7}
-              // interleave back to k order: (lo.b0, hi.b0), (lo.b1, hi.b1), ...
-              const uint32_t e01 = __byte_perm(lo, hi, 0x5140);   // bytes: lo0, hi0, lo1, hi1
+              const uint32_t e01 = __byte_perm(lo, hi, 0x5140);   // bytes: lo0, hi0, lo1, hi1  (k order)
               const uint32_t e23 = __byte_perm(lo, hi, 0x7362);   // bytes: lo2, hi2, lo3, hi3
               const uint4 v = make_uint4(deq2(e01, 0, 1, s, b), deq2(e01, 2, 3, s, b), deq2(e23, 0, 1, s, b), deq2(e23, 2, 3, s, b));
               *reinterpret_cast<uint4*>(drow + (((4 * part + i) ^ (row & 7)) * 16)) = v;
@@ -200,6 +226,10 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_deq[stage]);
         if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+        if (kb + 1 < num_k) {
+#pragma unroll
+          for (int it = 0; it < MAX_IT; ++it) { sc[it] = sn[it]; bm[it] = bn[it]; }
+        }
       }
     }
   }
@@ -261,7 +291,9 @@ __global__ void dequantize_kernel(const uint8_t* __restrict__ q, const float* __
       code = (k & 1) ? (b >> 4) : (b & 15);
     }
     const int g = k / 64;
-    w[i] = __float2bfloat16(fmaf(static_cast<float>(code), scales[static_cast<int64_t>(g) * N + n], biases[static_cast<int64_t>(g) * N + n]));
+    // identical arithmetic to the fused kernel's deq2(): (2^15 + q) * s + (beta - s * 2^15), one rounding each
+    const float sv = scales[static_cast<int64_t>(g) * N + n], bv = biases[static_cast<int64_t>(g) * N + n];
+    w[i] = __float2bfloat16(fmaf(32768.0f + static_cast<float>(code), sv, fmaf(-32768.0f, sv, bv)));
   }
 }
 
