@@ -134,6 +134,8 @@ typedef struct {
   int32_t n_stg_blocks;
   int32_t stg_blocks[LTX_MAX_FLAG_BLOCKS];
   int32_t step_index;   /* GE applies for step_index > 0 */
+  int32_t disable_stg_prefix_sharing; /* 0 (default): the STG pass reuses the conditional pass's blocks before the first
+                                         perturbed block (identical inputs -> identical values); 1: recompute them */
 } ltx_step_params;
 /* noise [in_channels, F, H, W] fp32 host; latent = noise * sigma0 (:793).  neg_context may be NULL. */
 int ltx_denoise_begin(ltx_ctx* ctx, const float* noise, int F, int H, int W, float sigma0, const void* context,

@@ -233,8 +233,10 @@ class LtxContext:
         self._session_shape = (self.config.in_channels, F, H, W)
 
     def denoise_step(self, sigma: float, sigma_next: float, step_index: int, cfg_scale: float = 1.0, rescale_phi: float = 0.0,
-                     stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0):
+                     stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0,
+                     share_stg_prefix: bool = True):
         p = LtxStepParams()
+        p.disable_stg_prefix_sharing = 0 if share_stg_prefix else 1
         p.sigma, p.sigma_next, p.cfg_scale, p.rescale_phi = sigma, sigma_next, cfg_scale, rescale_phi
         p.stg_scale, p.ge_gamma, p.step_index = stg_scale, ge_gamma, step_index
         p.n_stg_blocks = len(stg_blocks)

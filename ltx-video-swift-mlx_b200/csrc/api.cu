@@ -103,7 +103,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
                     &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
-                    &c->v_lat, &c->v_noise, &c->v_frames};
+                    &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
   cudaStreamDestroy(c->stream);
@@ -352,7 +352,12 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     }
     LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
     const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
-    auto pass = [&](bool neg, bool stg, float* v_lat) {
+    // the STG pass differs from the conditional pass only from its first perturbed block on; when both run
+    // on this rank the conditional pass saves the stream there and the STG pass resumes from it (bit-identical result).
+    int first_stg = -1;
+    for (int i = 0; i < p->n_stg_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i)
+      if (first_stg < 0 || p->stg_blocks[i] < first_stg) first_stg = p->stg_blocks[i];
+    auto pass = [&](bool neg, bool stg, float* v_lat, int snapshot_block, int resume_block) {
       ltx_dit_flags fl = {};
       fl.cross_attn_scale = 1.0f;
       fl.context_key = neg ? key_neg : key_pos;
@@ -365,7 +370,7 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
       const int32_t* mk = neg ? (c->s_has_mask_neg ? c->s_mask_neg.as<int32_t>() : nullptr)
                               : (c->s_has_mask_pos ? c->s_mask_pos.as<int32_t>() : nullptr);
       dit_forward_dev(c, c->s_tok.ptr, LTX_BF16, cx, c->s_ctx_dtype, c->s_sigma.as<float>(), 0, mk, 1, T, S, F, H, W, &fl,
-                      c->vel.as<float>());
+                      c->vel.as<float>(), snapshot_block, resume_block);
       ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * n);
       launch_unpatchify(c->vel.as<float>(), v_lat, C, T, st);  // velocity back to [C, F, H, W]
     };
@@ -380,8 +385,12 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     if (use_cfg) passes[n_pass++] = {true, false, c->s_vu.as<float>()};
     if (use_stg) passes[n_pass++] = {false, true, c->s_vs.as<float>()};
     const int groups = c->dist.groups;
+    const int stg_idx = use_stg ? n_pass - 1 : -1;
+    const bool share = use_stg && !p->disable_stg_prefix_sharing && first_stg > 0 && first_stg < g.num_layers &&
+                       (groups == 1 || (stg_idx % groups) == 0);   // conditional pass (index 0) and STG pass on the same group
     for (int i = 0; i < n_pass; ++i)
-      if (groups == 1 || (i % groups) == c->dist.group) pass(passes[i].neg, passes[i].stg, passes[i].v);
+      if (groups == 1 || (i % groups) == c->dist.group)
+        pass(passes[i].neg, passes[i].stg, passes[i].v, (share && i == 0) ? first_stg : -1, (share && passes[i].stg) ? first_stg : -1);
     if (groups > 1) {
       ProfScope ps(c, PROF_COMM, 0.0, 4.0 * n * n_pass, n_pass);
       for (int i = 0; i < n_pass; ++i) dist_broadcast(c, passes[i].v, n * 4, (i % groups) * c->dist.sp);

@@ -74,8 +74,16 @@ struct VaeResBlock {
   ConvW c1, c2;
   const float* sst = nullptr;  // [4, C] rows shift1, scale1, shift2, scale2
 };
+struct VaeTimeEmb {   // VAETimestepEmbedder (V/VideoDecoder.swift:37-52): Linear(256,256) -> SiLU -> Linear(256, out)
+  const bf16 *w1 = nullptr, *w2 = nullptr;
+  const float *b1 = nullptr, *b2 = nullptr;
+  int out = 0;
+};
 struct VaeWeights {
   bool ready = false;
+  bool has_time = false;                // timestep-conditioning weights are present
+  float ts_mult = 1000.0f;              // timestep_scale_multiplier
+  VaeTimeEmb stage_te[4], last_te;
   const float *mean = nullptr, *std = nullptr;
   ConvW conv_in, conv_out;
   std::vector<std::vector<VaeResBlock>> stages;  // 4 stages x blocks_per_stage
@@ -137,6 +145,8 @@ struct ltx_ctx {
   int text_rr = 0;
   ltx::DevBuf scratch;  // small fp64 scratch for reductions
   ltx::DevBuf sp_send, sp_recv, sp_vt, sp_vel;  // Ulysses exchange buffers
+  ltx::DevBuf snap_x;                           // residual-stream snapshot for the shared STG prefix
+  int snap_rows = 0;
 
   // ---- resident denoise session
   ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma;
@@ -146,7 +156,7 @@ struct ltx_ctx {
   uint64_t s_serial = 0;
 
   // ---- VAE workspaces
-  ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames;
+  ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te;
 };
 
 namespace ltx {
@@ -176,9 +186,13 @@ struct ProfScope {
 // dit.cu
 void dit_finalize(ltx_ctx* c);
 void dit_quantize(ltx_ctx* c, int bits);
+// snapshot_block >= 0: save the residual stream at the entry of that block (for a later resume);
+// resume_block >= 0: skip the embedding and blocks [0, resume_block) and continue from the saved stream (SURVEY H10:
+// the STG-perturbed pass shares every block before the first perturbed one with the conditional pass).
 void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
                      const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
-                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev);
+                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev, int snapshot_block = -1,
+                     int resume_block = -1);
 void dit_clear_caches(ltx_ctx* c);
 // vae.cu
 void vae_finalize(ltx_ctx* c);

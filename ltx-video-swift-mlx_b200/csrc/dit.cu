@@ -339,7 +339,7 @@ void dit_quantize(ltx_ctx* c, int bits) {
 
 void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
                      const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
-                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev) {
+                     int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev, int snapshot_block, int resume_block) {
   LTX_CHECK(c->dit_ready, LTX_ERR_WEIGHTS, "DiT weights not finalized");
   LTX_CHECK(ts_per_token == 0, LTX_ERR_UNSUPPORTED, "per-token timesteps are not implemented");
   LTX_CHECK(B >= 1 && B <= 4 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
@@ -427,12 +427,18 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     lat_bf = c->lat_in.as<bf16>();
   }
   lat_bf += static_cast<int64_t>(tok0) * Cin;
-  {
+  if (resume_block < 0) {
     GemmEpi e;
     e.mode = EPI_BF16; e.out = xb; e.ldo = D; e.bias = c->b_patch;
     gemm(c, lat_bf, Cin, c->w_patch, Cin, R, D, Cin, e);
     ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * D);
     launch_cast_bf16_f32(xb, x, static_cast<int64_t>(R) * D, st);
+  } else {
+    // resume from the stream saved at the entry of block `resume_block` by an identical-input pass
+    LTX_CHECK(resume_block < L && c->snap_x.ptr && c->snap_rows == R, LTX_ERR_INVALID_ARGUMENT, "no matching snapshot to resume from");
+    ProfScope ps(c, PROF_OTHER, 0.0, 14.0 * R * D, 2);
+    LTX_CUDA(cudaMemcpyAsync(x, c->snap_x.ptr, static_cast<size_t>(R) * D * 4, cudaMemcpyDeviceToDevice, st));
+    launch_cast_f32_bf16(x, xb, static_cast<int64_t>(R) * D, st);
   }
   // ---- timestep path (T/LTXTimestepEmbedding.swift:62-124): fp32 activations, bf16 weights
   {
@@ -444,8 +450,14 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   }
 
   const int64_t ada_ld = 6 * static_cast<int64_t>(D);
-  for (int i = 0; i < L; ++i) {
+  for (int i = (resume_block > 0 ? resume_block : 0); i < L; ++i) {
     const BlockWeights& bw = c->blocks[i];
+    if (i == snapshot_block) {
+      c->snap_x.reserve(static_cast<size_t>(R) * D * 4);
+      c->snap_rows = R;
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * R * D);
+      LTX_CUDA(cudaMemcpyAsync(c->snap_x.ptr, x, static_cast<size_t>(R) * D * 4, cudaMemcpyDeviceToDevice, st));
+    }
     const bool flagged = in_list(i, flags->stg_blocks, flags->n_stg_blocks);
     const bool skip_sa = flagged && flags->skip_self_attn;
     const bool skip_ff = flagged && flags->skip_ff;

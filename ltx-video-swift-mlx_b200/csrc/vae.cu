@@ -28,6 +28,11 @@ __global__ void noise_mix_kernel(float* __restrict__ x, const float* __restrict_
     x[i] = nz[i] * scale + (1.0f - scale) * x[i];
 }
 
+__global__ void add_vec_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 ConvW pack_conv(ltx_ctx* c, const std::string& name, int64_t cout, int64_t cin) {
   const DevTensor& w = get_tensor(c, name + ".conv.weight");
   LTX_CHECK(w.dtype == LTX_BF16 && w.shape.size() == 5 && w.shape[0] == cout && w.shape[1] == cin && w.shape[2] == 3 &&
@@ -116,6 +121,34 @@ void vae_finalize(ltx_ctx* c) {
     }
   }
   v.last_sst = vf(c, "vae.last_scale_shift_table", 2 * ch);
+  // optional timestep conditioning (V/VideoDecoder.swift:136-167, 311-318, 419-436)
+  v.has_time = c->tensors.count("vae.last_time_embedder.timestep_embedder.linear_1.weight") > 0;
+  if (v.has_time) {
+    auto te = [&](const std::string& pfx, int out) {
+      VaeTimeEmb t;
+      const DevTensor& w1 = get_tensor(c, pfx + ".timestep_embedder.linear_1.weight");
+      const DevTensor& w2 = get_tensor(c, pfx + ".timestep_embedder.linear_2.weight");
+      LTX_CHECK(w1.dtype == LTX_BF16 && w1.shape.size() == 2 && w1.shape[0] == 256 && w1.shape[1] == 256 && w2.dtype == LTX_BF16 &&
+                    w2.shape.size() == 2 && w2.shape[0] == out && w2.shape[1] == 256,
+                LTX_ERR_WEIGHTS, "bad time embedder shape under '" + pfx + "'");
+      t.w1 = reinterpret_cast<const bf16*>(w1.ptr); t.w2 = reinterpret_cast<const bf16*>(w2.ptr);
+      t.b1 = vf(c, pfx + ".timestep_embedder.linear_1.bias", 256);
+      t.b2 = vf(c, pfx + ".timestep_embedder.linear_2.bias", out);
+      t.out = out;
+      return t;
+    };
+    int64_t cc = g.vae_base_channels;
+    for (int st = 0; st < 4; ++st) {
+      v.stage_te[st] = te("vae.up_blocks_" + std::to_string(2 * st) + ".time_embedder", static_cast<int>(4 * cc));
+      if (st < 3) cc /= 2;
+    }
+    v.last_te = te("vae.last_time_embedder", static_cast<int>(2 * cc));
+    if (c->tensors.count("vae.timestep_scale_multiplier")) {
+      const DevTensor& m = get_tensor(c, "vae.timestep_scale_multiplier");
+      LTX_CHECK(m.dtype == LTX_F32 && m.numel() == 1, LTX_ERR_WEIGHTS, "bad timestep_scale_multiplier");
+      LTX_CUDA(cudaMemcpy(&v.ts_mult, m.ptr, 4, cudaMemcpyDeviceToHost));
+    }
+  }
   v.conv_out = pack_conv(c, "vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
   LTX_CHECK(g.vae_patch_size == 4, LTX_ERR_INVALID_CONFIGURATION, "vae_patch_size must be 4");
   v.ready = true;
@@ -126,12 +159,50 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
   VaeWeights& v = c->vae;
   LTX_CHECK(v.ready, LTX_ERR_WEIGHTS, "VAE weights not finalized");
   LTX_CHECK(latent_dev && frames_dev && Fp > 0 && Hp > 1 && Wp > 1, LTX_ERR_INVALID_ARGUMENT, "bad vae_decode arguments");
-  LTX_CHECK(timestep < 0.f, LTX_ERR_UNSUPPORTED,
-            "timestep-conditioned VAE decode is not implemented (pipeline default is timestep = nil)");
-  (void)noise_dev;
+  const bool timed = timestep >= 0.f;
+  LTX_CHECK(!timed || v.has_time, LTX_ERR_WEIGHTS, "timestep-conditioned decode needs the VAE time-embedder weights");
+  LTX_CHECK(!timed || noise_dev != nullptr, LTX_ERR_INVALID_ARGUMENT, "decode_noise is required when timestep >= 0");
   const ltx_config& g = c->cfg;
   cudaStream_t st = c->stream;
   const int C0 = g.vae_latent_channels;
+  // ---- timestep conditioning (:368-375): x = 0.025 * noise + 0.975 * x on the normalised latent; every res-block table and
+  // the last table get + time_emb(sincos(t * multiplier)).  te_buf: [sincos 256 | hidden 256 | emb 4C] scratch + effective tables.
+  const float* latent_in = latent_dev;
+  float* te_base = nullptr;
+  if (timed) {
+    const size_t n = static_cast<size_t>(C0) * Fp * Hp * Wp;
+    c->v_mix.reserve(n * 4);
+    LTX_CUDA(cudaMemcpyAsync(c->v_mix.ptr, latent_dev, n * 4, cudaMemcpyDeviceToDevice, st));
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 12.0 * n);
+      int64_t blocks = (static_cast<int64_t>(n) + 255) / 256;
+      if (blocks > 4096) blocks = 4096;
+      noise_mix_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(c->v_mix.as<float>(), noise_dev, static_cast<int64_t>(n), 0.025f);
+      LTX_CUDA(cudaGetLastError());
+    }
+    latent_in = c->v_mix.as<float>();
+    c->v_te.reserve((1 + 256 + 256 + 4 * static_cast<size_t>(g.vae_base_channels) * 2 + 64) * 4);
+    te_base = c->v_te.as<float>();
+    const float ts_host = timestep;
+    LTX_CUDA(cudaMemcpyAsync(te_base, &ts_host, 4, cudaMemcpyHostToDevice, st));
+    launch_sincos_embed(te_base, v.ts_mult, te_base + 16, 1, 256, st);
+    c->launches++;
+  }
+  // effective scale-shift table of a block: table (+ time embedding of its stage)
+  auto time_emb = [&](const VaeTimeEmb& te, float* out) {   // out[te.out]
+    ProfScope ps(c, PROF_OTHER, 0.0, 2.0 * 256 * (256 + te.out), 2);
+    launch_gemv(te.w1, te.b1, te_base + 16, te_base + 16 + 256, 1, 256, 256, 0, st);
+    launch_gemv(te.w2, te.b2, te_base + 16 + 256, out, 1, te.out, 256, 1, st);
+  };
+  float* te_stage = timed ? te_base + 16 + 512 : nullptr;                                   // [4C]
+  float* tbl_eff = timed ? te_stage + 4 * static_cast<size_t>(g.vae_base_channels) : nullptr;   // [4C]
+  auto eff_table = [&](const float* sst, int n) -> const float* {
+    if (!timed) return sst;
+    ProfScope ps(c, PROF_OTHER, 0.0, 12.0 * n);
+    add_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(tbl_eff, sst, te_stage, n);
+    LTX_CUDA(cudaGetLastError());
+    return tbl_eff;
+  };
   // ---- temporal sharding: the first n_active ranks own contiguous slabs of latent frames [f0, f1)
   const int world = c->dist.world, rank = c->dist.rank;
   const int n_active = (c->dist.comm_world && world > 1) ? std::min(world, Fp) : 1;
@@ -169,17 +240,19 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
     // [C, F*H*W] (frames f0..f1) -> channels-last [T*H*W, C]
     {
       ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * C0 * T * H * W);
-      launch_transpose_slice(latent_dev + static_cast<size_t>(f0) * H * W, static_cast<int64_t>(Fp) * H * W, C0, T * H * W, hbuf,
+      launch_transpose_slice(latent_in + static_cast<size_t>(f0) * H * W, static_cast<int64_t>(Fp) * H * W, C0, T * H * W, hbuf,
                              st);
     }
     // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
     conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr, n_active);
     int64_t ch = g.vae_base_channels;
     for (int s = 0; s < 4; ++s) {
+      if (timed) time_emb(v.stage_te[s], te_stage);   // one embedding per res-block group (:152-160)
       for (const VaeResBlock& rb : v.stages[s]) {
         // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
-        conv(c, x, 2, rb.sst + ch, rb.sst, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
-        conv(c, hbuf, 2, rb.sst + 3 * ch, rb.sst + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
+        const float* tb = eff_table(rb.sst, static_cast<int>(4 * ch));
+        conv(c, x, 2, tb + ch, tb, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
+        conv(c, hbuf, 2, tb + 3 * ch, tb + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
       }
       if (s < 3) {
         // conv -> d2s -> drop frame 0 (first slab only) -> + tiled d2s(x)
@@ -190,7 +263,9 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
     }
     // pn * (1 + scale) + shift -> SiLU -> conv_out -> unpatchify -> (x+1)/2 clip -> [F, H, W, 3]   (:419-444, 501-505)
     const int out_f0 = f0 == 0 ? 0 : 8 * (f0 - 1) + 1;
-    conv(c, x, 2, v.last_sst + ch, v.last_sst, v.conv_out, T, H, W, causal, 2, frames_dev + static_cast<size_t>(out_f0) * frame_elems,
+    if (timed) time_emb(v.last_te, te_stage);
+    const float* lt = eff_table(v.last_sst, static_cast<int>(2 * ch));
+    conv(c, x, 2, lt + ch, lt, v.conv_out, T, H, W, causal, 2, frames_dev + static_cast<size_t>(out_f0) * frame_elems,
          nullptr, n_active);
   }
   if (n_active > 1) {

@@ -159,12 +159,16 @@ void init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
         conv(rb + ".conv2", ch, ch);
         fill(c, rb + ".scale_shift_table", {4, ch}, 0.1f, 0.f, s);
       }
+      lin(blk + ".time_embedder.timestep_embedder.linear_1", 256, 256);
+      lin(blk + ".time_embedder.timestep_embedder.linear_2", 4 * ch, 256);
       if (st < 3) {
         conv("vae.up_blocks_" + std::to_string(2 * st + 1) + ".conv", 4 * ch, ch);
         ch /= 2;
       }
     }
     fill(c, "vae.last_scale_shift_table", {2, ch}, 0.1f, 0.f, s);
+    lin("vae.last_time_embedder.timestep_embedder.linear_1", 256, 256);
+    lin("vae.last_time_embedder.timestep_embedder.linear_2", 2 * ch, 256);
     conv("vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
   }
   LTX_CUDA(cudaStreamSynchronize(c->stream));

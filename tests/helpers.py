@@ -47,7 +47,7 @@ def make_ctx_with_vae(ocfg, pcfg, seed=2, bf16_weights=True):
     ctxmod = product()
     w = O.make_vae_weights(ocfg, seed)
     if bf16_weights:  # conv kernels are stored as bf16 on the device; give the oracle the same values
-        w = {k: (O.bf16_round(v) if k.endswith("conv.weight") else v) for k, v in w.items()}
+        w = {k: (O.bf16_round(v) if (k.endswith(".weight") and v.ndim >= 2) else v) for k, v in w.items()}
     ctx = ctxmod.LtxContext(pcfg, 0)
     ctx.load_weights(w, prefix="vae.")
     ctx.finalize_weights()

@@ -24,6 +24,7 @@ def _inputs(ocfg, fhw, S, seed, B=1, mask_prefix=0):
 @pytest.mark.parametrize("layers,heads,fhw,S,B,mask_prefix", [
     (2, 2, (2, 4, 6), 40, 1, 7), (3, 4, (4, 8, 10), 150, 1, 0), (2, 2, (1, 4, 4), 24, 2, 5),
     (1, 32, (2, 4, 6), 40, 1, 7),    # full LTX-2 width (D = 4096): exercises the D-specialised row kernels
+    (1, 32, (2, 16, 16), 128, 1, 0), # BASELINE config 0: one LTX-2 block, latent 512x512x9 (N = 512), 128 text tokens
 ])
 def test_dit_forward_matches_oracle(layers, heads, fhw, S, B, mask_prefix):
     ocfg, pcfg = small_dit_config(layers, heads)
@@ -95,4 +96,26 @@ def test_denoise_loop_matches_oracle(guided):
     out = ctx.denoise_get_latent()
     err = rel_l2(out, ref[0])
     assert err <= 2e-2, err      # several guided steps compound the per-step 1e-2 velocity tolerance
+    ctx.close()
+
+
+def test_stg_prefix_sharing_is_bit_identical():
+    """resuming the STG pass from the conditional pass's stream at the first perturbed block changes nothing."""
+    ocfg, pcfg = small_dit_config(4, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=8)
+    fhw, S = (2, 4, 6), 40
+    g = torch.Generator().manual_seed(23)
+    noise = torch.randn(1, 128, *fhw, generator=g)
+    _, cx, _ = _inputs(ocfg, fhw, S, 27)
+    _, ncx, _ = _inputs(ocfg, fhw, S, 28)
+    sigmas = O.set_timesteps(3, False, 48)
+    outs = []
+    for share in (True, False):
+        ctx.denoise_begin(noise[0].numpy(), fhw, sigmas[0], cx, None, ncx, None)
+        for i in range(len(sigmas) - 1):
+            ctx.denoise_step(sigmas[i], sigmas[i + 1], i, cfg_scale=3.0, stg_scale=0.5, stg_blocks=(2,), share_stg_prefix=share)
+        outs.append(ctx.denoise_get_latent())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    ref = O.denoise_loop(w, ocfg, noise, cx.float(), None, sigmas, neg_context=ncx.float(), cfg_scale=3.0, stg_scale=0.5, stg_blocks=(2,))
+    assert rel_l2(outs[0], ref[0]) <= 2e-2
     ctx.close()

@@ -21,3 +21,19 @@ def test_vae_decode_matches_oracle(base, blocks, fhw):
     p = O.psnr(torch.from_numpy(out), ref)
     assert p >= 40.0, p
     ctx.close()
+
+
+def test_vae_decode_timestep_conditioned():
+    """decodeVideo(timestep: 0.05) -- noise injection + time-embedded scale/shift tables (V/VideoDecoder.swift:368-375,
+    100-114, 419-436); the noise is passed in as data."""
+    ocfg, pcfg = small_vae_config(512, 1)
+    ctx, w = make_ctx_with_vae(ocfg, pcfg, seed=41)
+    g = torch.Generator().manual_seed(43)
+    z = torch.randn(1, 128, 2, 3, 4, generator=g)
+    nz = torch.randn(1, 128, 2, 3, 4, generator=g)
+    ref = O.decode_video(w, ocfg, z, timestep=0.05, decode_noise=nz)
+    out = ctx.vae_decode(z[0].numpy(), timestep=0.05, decode_noise=nz[0].numpy())
+    assert O.psnr(torch.from_numpy(out), ref) >= 40.0
+    plain = ctx.vae_decode(z[0].numpy())
+    assert O.psnr(torch.from_numpy(plain), ref) < 35.0      # the conditioning really changes the frames
+    ctx.close()
