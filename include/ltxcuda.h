@@ -99,7 +99,7 @@ typedef struct {
  * (Models/Transformer/LTXTransformer.swift:235-486).
  *   latent   [B, N, in_channels]   (N = F*H*W, token order F-major then H then W, Pipeline/LatentUtils.swift:29-31)
  *   context  [B, S, caption_channels]
- *   timesteps[B] sigma in [0,1]    (ts_per_token != 0, [B,N], is not implemented yet: LTX_ERR_UNSUPPORTED)
+ *   timesteps[B] sigma in [0,1], or [B,N] per token when ts_per_token != 0 (image-conditioned denoise())
  *   mask     [B, S] int32, 1 = attend, NULL = all ones
  *   out      [B, N, out_channels] fp32 velocity
  * Host-pointer variant copies in/out and synchronises. */
@@ -134,6 +134,9 @@ typedef struct {
   int32_t n_stg_blocks;
   int32_t stg_blocks[LTX_MAX_FLAG_BLOCKS];
   int32_t step_index;   /* GE applies for step_index > 0 */
+  int32_t i2v_frame0_conditioned; /* image-to-video loop (denoise(), Pipeline/LTXPipeline.swift:2237-2252, 2344-2357): the
+                                     first latent frame is a clean conditioning frame -> its tokens get timestep 0
+                                     (per-token timesteps sigma * (1 - mask)) and the Euler update skips it */
   int32_t disable_stg_prefix_sharing; /* 0 (default): the STG pass reuses the conditional pass's blocks before the first
                                          perturbed block (identical inputs -> identical values); 1: recompute them */
 } ltx_step_params;

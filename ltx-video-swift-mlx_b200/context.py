@@ -183,12 +183,13 @@ class LtxContext:
         lc, cc = _dtype_code(latent), _dtype_code(context)
         lat, ctx = _host(latent), _host(context)
         ts = _host(timesteps, np.float32)
+        per_token = 1 if ts.ndim == 2 else 0
         mk = None if mask is None else _host(mask, np.int32)
         B, N = lat.shape[0], lat.shape[1]
         S = ctx.shape[1]
         out = np.empty((B, N, self.config.out_channels), dtype=np.float32)
         F, H, W = fhw
-        self._check(self.lib.ltx_dit_forward(self.handle, _ptr(lat), lc, _ptr(ctx), cc, _ptr(ts), 0, _ptr(mk), B, N, S, F, H, W,
+        self._check(self.lib.ltx_dit_forward(self.handle, _ptr(lat), lc, _ptr(ctx), cc, _ptr(ts), per_token, _ptr(mk), B, N, S, F, H, W,
                                              C.byref(flags) if flags is not None else None, _ptr(out)))
         return out
 
@@ -234,8 +235,9 @@ class LtxContext:
 
     def denoise_step(self, sigma: float, sigma_next: float, step_index: int, cfg_scale: float = 1.0, rescale_phi: float = 0.0,
                      stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0,
-                     share_stg_prefix: bool = True):
+                     share_stg_prefix: bool = True, i2v_frame0_conditioned: bool = False):
         p = LtxStepParams()
+        p.i2v_frame0_conditioned = int(i2v_frame0_conditioned)
         p.disable_stg_prefix_sharing = 0 if share_stg_prefix else 1
         p.sigma, p.sigma_next, p.cfg_scale, p.rescale_phi = sigma, sigma_next, cfg_scale, rescale_phi
         p.stg_scale, p.ge_gamma, p.step_index = stg_scale, ge_gamma, step_index

@@ -103,7 +103,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
                     &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
-                    &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x};
+                    &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x, &c->s_ts};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
   cudaStreamDestroy(c->stream);
@@ -224,7 +224,6 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
   return guarded(c, [&] {
     LTX_CHECK(latent && context && timesteps && out_velocity, LTX_ERR_INVALID_ARGUMENT, "null tensor");
     LTX_CHECK(B >= 1 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
-    LTX_CHECK(ts_per_token == 0, LTX_ERR_UNSUPPORTED, "per-token timesteps are not implemented");
     const ltx_config& g = c->cfg;
     const size_t R = static_cast<size_t>(B) * N;
     // the staged copies live in dedicated buffers (dit_forward_dev's own staging buffers are distinct: it is told bf16
@@ -236,15 +235,15 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
                         ((c->text[0].key == flags->context_key && c->text[0].B == B && c->text[0].S == S) ||
                          (c->text[1].key == flags->context_key && c->text[1].B == B && c->text[1].S == S));
     if (!cached) h2d(c, ctx, context, static_cast<size_t>(B) * S * g.caption_channels * dsize(context_dtype));
-    h2d(c, c->ts_in, timesteps, static_cast<size_t>(B) * 4);
+    h2d(c, c->ts_in, timesteps, (ts_per_token ? R : static_cast<size_t>(B)) * 4);
     const int32_t* mask_dev = nullptr;
     if (mask) {
       h2d(c, c->mask_in, mask, static_cast<size_t>(B) * S * 4);
       mask_dev = c->mask_in.as<int32_t>();
     }
     c->vel.reserve(R * g.out_channels * 4);
-    dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), 0, mask_dev, B, N, S, F, H, W,
-                    flags, c->vel.as<float>());
+    dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), ts_per_token, mask_dev, B, N, S, F,
+                    H, W, flags, c->vel.as<float>());
     LTX_CUDA(cudaMemcpyAsync(out_velocity, c->vel.ptr, R * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -351,6 +350,16 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
       launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
     }
     LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
+    // image-conditioned loop (denoise(), P/LTXPipeline.swift:2237-2252, 2344-2357): frame-0 tokens are clean -> per-token
+    // timesteps sigma * (1 - mask), and the Euler update leaves frame 0 untouched
+    const bool i2v = p->i2v_frame0_conditioned != 0;
+    const float* ts_dev = c->s_sigma.as<float>();
+    if (i2v) {
+      c->s_ts.reserve(static_cast<size_t>(T) * 4);
+      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * T);
+      launch_fill_token_timesteps(c->s_ts.as<float>(), T, T, H * W, c->s_sigma.as<float>(), st);
+      ts_dev = c->s_ts.as<float>();
+    }
     const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
     // the STG pass differs from the conditional pass only from its first perturbed block on; when both run
     // on this rank the conditional pass saves the stream there and the STG pass resumes from it (bit-identical result).
@@ -369,7 +378,7 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
       const void* cx = neg ? c->s_ctx_neg.ptr : c->s_ctx_pos.ptr;
       const int32_t* mk = neg ? (c->s_has_mask_neg ? c->s_mask_neg.as<int32_t>() : nullptr)
                               : (c->s_has_mask_pos ? c->s_mask_pos.as<int32_t>() : nullptr);
-      dit_forward_dev(c, c->s_tok.ptr, LTX_BF16, cx, c->s_ctx_dtype, c->s_sigma.as<float>(), 0, mk, 1, T, S, F, H, W, &fl,
+      dit_forward_dev(c, c->s_tok.ptr, LTX_BF16, cx, c->s_ctx_dtype, ts_dev, i2v ? 1 : 0, mk, 1, T, S, F, H, W, &fl,
                       c->vel.as<float>(), snapshot_block, resume_block);
       ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * n);
       launch_unpatchify(c->vel.as<float>(), v_lat, C, T, st);  // velocity back to [C, F, H, W]
@@ -403,6 +412,7 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     a.use_prev = p->step_index > 0 ? 1 : 0;
     a.v_out = nullptr; a.n = n; a.cfg = p->cfg_scale; a.phi = p->rescale_phi; a.stg = p->stg_scale;
     a.ge_gamma = p->ge_gamma; a.sigma = p->sigma; a.sigma_next = p->sigma_next; a.scratch = c->scratch.as<double>();
+    if (i2v) { a.period = static_cast<size_t>(T); a.frozen = static_cast<size_t>(H) * W; }
     ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * n * (4.0 + (use_cfg ? 1.0 : 0.0) + (use_stg ? 1.0 : 0.0)),
                  (use_cfg && p->rescale_phi > 0.f) ? 2 : 1);
     launch_guided_euler(a, st);

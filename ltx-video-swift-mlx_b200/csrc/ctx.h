@@ -149,7 +149,7 @@ struct ltx_ctx {
   int snap_rows = 0;
 
   // ---- resident denoise session
-  ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma;
+  ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma, s_ts;
   int s_F = 0, s_H = 0, s_W = 0, s_S = 0;
   bool s_has_neg = false, s_has_mask_pos = false, s_has_mask_neg = false;
   int s_ctx_dtype = LTX_BF16;

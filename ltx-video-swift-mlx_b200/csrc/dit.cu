@@ -341,7 +341,6 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
                      const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F,
                      int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev, int snapshot_block, int resume_block) {
   LTX_CHECK(c->dit_ready, LTX_ERR_WEIGHTS, "DiT weights not finalized");
-  LTX_CHECK(ts_per_token == 0, LTX_ERR_UNSUPPORTED, "per-token timesteps are not implemented");
   LTX_CHECK(B >= 1 && B <= 4 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
   LTX_CHECK(static_cast<int64_t>(F) * H * W == N, LTX_ERR_INVALID_ARGUMENT, "N must equal F*H*W");
   LTX_CHECK(latent && context && timesteps_dev && out_velocity_dev, LTX_ERR_INVALID_ARGUMENT, "null tensor");
@@ -376,10 +375,12 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   c->att.reserve(static_cast<size_t>(R) * D * 2);
   c->q2.reserve(static_cast<size_t>(R) * D * 2);
   c->ffh.reserve(static_cast<size_t>(R) * FFD * 2);
-  c->se.reserve(static_cast<size_t>(B) * 256 * 4);
-  c->t1.reserve(static_cast<size_t>(B) * D * 4);
-  c->emb.reserve(static_cast<size_t>(B) * D * 4);
-  c->ada.reserve(static_cast<size_t>(B) * 6 * D * 4);
+  // timestep rows: one per batch, or one per (local) token when timesteps are per token (I2V, P/LTXPipeline.swift:2237-2252)
+  const int TR = ts_per_token ? R : B;
+  c->se.reserve(static_cast<size_t>(TR) * 256 * 4);
+  c->t1.reserve(static_cast<size_t>(TR) * D * 4);
+  c->emb.reserve(static_cast<size_t>(TR) * D * 4);
+  c->ada.reserve(static_cast<size_t>(TR) * 6 * D * 4);
   float* x = c->x.as<float>();
   bf16* xb = c->xb.as<bf16>();
   bf16* h = c->h.as<bf16>();
@@ -411,7 +412,8 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   const float* key_bias = tc.has_bias ? tc.bias.as<float>() : nullptr;
   const float* cos_l = c->rope_cos.as<float>() + static_cast<int64_t>(tok0) * (D / 2);
   const float* sin_l = c->rope_sin.as<float>() + static_cast<int64_t>(tok0) * (D / 2);
-  const int rows_per_b = (P > 1) ? Nl : N;   // rows sharing one modulation / gate vector, and the RoPE period
+  const int rope_period = (P > 1) ? Nl : N;
+  const int rows_per_b = ts_per_token ? 1 : rope_period;   // rows sharing one modulation / gate vector
 
   // ---- patchify_proj (T/LTXTransformer.swift:257); the reference's bf16 Linear output is rounded to bf16
   const bf16* lat_bf;
@@ -441,12 +443,34 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     launch_cast_f32_bf16(x, xb, static_cast<int64_t>(R) * D, st);
   }
   // ---- timestep path (T/LTXTimestepEmbedding.swift:62-124): fp32 activations, bf16 weights
-  {
+  if (!ts_per_token) {
     ProfScope ps(c, PROF_OTHER, 2.0 * B * D * (256.0 + 7.0 * D), 2.0 * D * (256.0 + 7.0 * D), 4);
     launch_sincos_embed(timesteps_dev, g.timestep_scale_multiplier, c->se.as<float>(), B, 256, st);
     launch_gemv(c->w_t1, c->b_t1, c->se.as<float>(), c->t1.as<float>(), B, D, 256, 0, st);
     launch_gemv(c->w_t2, c->b_t2, c->t1.as<float>(), emb, B, D, D, 1, st);
     launch_gemv(c->w_ada, c->b_ada, emb, ada, B, 6 * D, D, 1, st);
+  } else {
+    // one embedding per token: the same three Linears as tensor-core GEMMs over the R local rows (bf16 operands, the
+    // SiLUs fused into the first epilogue / a cast pass); timesteps [B, N] are indexed from this rank's first token
+    bf16* se_bf = reinterpret_cast<bf16*>(c->se.ptr);      // [R, 256] bf16
+    bf16* t1_bf = reinterpret_cast<bf16*>(c->t1.ptr);      // [R, D] bf16 = silu(linear_1), later silu(emb)
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * R + 512.0 * R);
+      launch_sincos_embed(timesteps_dev + tok0, g.timestep_scale_multiplier, nullptr, R, 256, st, se_bf);
+    }
+    GemmEpi e1;
+    e1.mode = EPI_SILU_BF16; e1.out = t1_bf; e1.ldo = D; e1.bias = c->b_t1;
+    gemm(c, se_bf, 256, c->w_t1, 256, R, D, 256, e1);
+    GemmEpi e2;
+    e2.mode = EPI_F32; e2.out = emb; e2.ldo = D; e2.bias = c->b_t2;
+    gemm(c, t1_bf, D, c->w_t2, D, R, D, D, e2);
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * D);
+      launch_silu_cast(emb, t1_bf, static_cast<int64_t>(R) * D, st);
+    }
+    GemmEpi e3;
+    e3.mode = EPI_F32; e3.out = ada; e3.ldo = 6 * D; e3.bias = c->b_ada;
+    gemm(c, t1_bf, D, c->w_ada, D, R, 6 * D, D, e3);
   }
 
   const int64_t ada_ld = 6 * static_cast<int64_t>(D);
@@ -471,7 +495,7 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
       if (P == 1) {
         for (int b = 0; b < B; ++b)  // V^T, one column block per batch
           v_transposed(c, bw.a1.wv, bw.a1.bv, h + static_cast<int64_t>(b) * N * D, N, D, vt + b * ldv, B * ldv, q2);
-        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rows_per_b, eps, bw.a1.k_norm);
+        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rope_period, eps, bw.a1.k_norm);
         attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);
       } else {
         // ---- Ulysses: q/k (normed + RoPE'd, which needs the full feature row) and v leave in a head-blocked layout,
@@ -482,7 +506,7 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
         gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
         QkOut qo;
         qo.out[0] = qsend; qo.out[1] = ksend; qo.heads_per_block = Hl; qo.block_stride = blk; qo.ld = Csp;
-        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rows_per_b, eps, bw.a1.k_norm, &qo);
+        qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rope_period, eps, bw.a1.k_norm, &qo);
         {
           ProfScope ps(c, PROF_COMM, 0.0, 3.0 * 2.0 * P * blk * 2.0);
           const void* sb[3] = {qsend, ksend, vsend};

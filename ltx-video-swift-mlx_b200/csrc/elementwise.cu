@@ -302,15 +302,34 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restr
 // ---------------------------------------------------------------------------------------------
 // Timestep path (T/LTXTimestepEmbedding.swift:17-124): sinusoidal embedding and small-M linear layers.
 // ---------------------------------------------------------------------------------------------
-__global__ void sincos_embed_kernel(const float* __restrict__ sigma, float mult, float* __restrict__ out, int dim) {
+__global__ void sincos_embed_kernel(const float* __restrict__ sigma, float mult, float* __restrict__ out, int dim,
+                                    bf16* __restrict__ out_bf16) {
   const int m = blockIdx.x, half = dim >> 1;
   const float t = sigma[m] * mult;
   for (int k = threadIdx.x; k < half; k += blockDim.x) {
     const float f = expf(-logf(10000.0f) * (static_cast<float>(k) / static_cast<float>(half)));
     const float a = t * f;
-    out[static_cast<int64_t>(m) * dim + k] = cosf(a);
-    out[static_cast<int64_t>(m) * dim + half + k] = sinf(a);
+    const float cv = cosf(a), sv = sinf(a);
+    if (out) {
+      out[static_cast<int64_t>(m) * dim + k] = cv;
+      out[static_cast<int64_t>(m) * dim + half + k] = sv;
+    }
+    if (out_bf16) {
+      out_bf16[static_cast<int64_t>(m) * dim + k] = __float2bfloat16(cv);
+      out_bf16[static_cast<int64_t>(m) * dim + half + k] = __float2bfloat16(sv);
+    }
   }
+}
+__global__ void silu_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(silu(v.x), silu(v.y)), pack_bf16(silu(v.z), silu(v.w)));
+  }
+}
+__global__ void fill_token_timesteps_kernel(float* __restrict__ ts, int n, int period, int frozen, const float* __restrict__ sigma) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ts[i] = (i % period) < frozen ? 0.f : sigma[0];
 }
 
 // one warp per output feature; x rows staged through registers; W streamed once with 16-byte loads.
@@ -439,6 +458,7 @@ __global__ void __launch_bounds__(256) guided_euler_kernel(GuidedEulerArgs a) {
       a.v_prev[i] = v;
     }
     if (a.v_out) a.v_out[i] = v;
+    if (a.period != 0 && (i % a.period) < a.frozen) continue;   // slice Euler: the conditioned first frame stays clean
     const float x = a.latent[i];
     const float den = x - a.sigma * v;
     a.latent[i] = (a.sigma_next > 0.f) ? den + a.sigma_next * (x - den) / a.sigma : den;
@@ -591,8 +611,17 @@ void launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s) {
   LTX_CUDA(cudaGetLastError());
 }
 
-void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s) {
-  sincos_embed_kernel<<<M, 128, 0, s>>>(sigma, mult, out, dim);
+void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s, bf16* out_bf16) {
+  sincos_embed_kernel<<<M, 128, 0, s>>>(sigma, mult, out, dim, out_bf16);
+  LTX_CUDA(cudaGetLastError());
+}
+void launch_silu_cast(const float* in, bf16* out, int64_t n, cudaStream_t s) {
+  LTX_CHECK(n % 4 == 0, 2, "silu_cast: n must be a multiple of 4");
+  silu_cast_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(in, out, n / 4);
+  LTX_CUDA(cudaGetLastError());
+}
+void launch_fill_token_timesteps(float* ts, int n, int period, int frozen, const float* sigma_dev, cudaStream_t s) {
+  fill_token_timesteps_kernel<<<(n + 255) / 256, 256, 0, s>>>(ts, n, period, frozen, sigma_dev);
   LTX_CUDA(cudaGetLastError());
 }
 

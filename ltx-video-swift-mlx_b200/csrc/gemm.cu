@@ -215,7 +215,7 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   int bn = force_bn;
   if (bn == 0) bn = fit_tile_width(M, N, device_sm_count());
   LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "GEMM: tile width must be a multiple of 16 in [32, 256]");
-  LTX_CHECK(epi.col_block == 0 || ((epi.mode == EPI_BF16 || epi.mode == EPI_GELU_BF16) && epi.col_block % 32 == 0 &&
+  LTX_CHECK(epi.col_block == 0 || ((epi.mode == EPI_BF16 || epi.mode == EPI_GELU_BF16 || epi.mode == EPI_SILU_BF16) && epi.col_block % 32 == 0 &&
                                    N % epi.col_block == 0),
             2, "GEMM: column-blocked output needs a bf16 epilogue and col_block % 32 == 0");
   CUtensorMap tmA;
@@ -231,6 +231,7 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
     case EPI_GELU_BF16: launch_impl<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
     case EPI_GATE_RESID: launch_impl<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
     case EPI_F32: launch_impl<EPI_F32>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_SILU_BF16: launch_impl<EPI_SILU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
     default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
   }
 }

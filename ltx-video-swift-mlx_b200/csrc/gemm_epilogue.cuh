@@ -70,7 +70,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
         o[j] = __uint_as_float(r[j]) + b;
       }
     }
-  } else {  // EPI_BF16 / EPI_GELU_BF16
+  } else {  // EPI_BF16 / EPI_GELU_BF16 / EPI_SILU_BF16
     bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + col0;
     if (ep.col_block > 0)
       o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(col0 / ep.col_block) * ep.col_block_stride +
@@ -93,6 +93,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = gelu_tanh(v[t]);
         }
+        if (MODE == EPI_SILU_BF16) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = silu(v[t]);
+        }
         uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         *reinterpret_cast<uint4*>(o + j) = pk;
       }
@@ -101,6 +105,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int row,
         float b = ep.bias ? (ep.bias_per_row ? rowbias : ep.bias[col0 + j]) : 0.f;
         float v = __uint_as_float(r[j]) + b;
         if (MODE == EPI_GELU_BF16) v = gelu_tanh(v);
+        if (MODE == EPI_SILU_BF16) v = silu(v);
         o[j] = __float2bfloat16(v);
       }
     }

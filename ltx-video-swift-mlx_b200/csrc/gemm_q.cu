@@ -320,6 +320,7 @@ void launch_q_mode(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N,
     case EPI_GELU_BF16: launch_q<EPI_GELU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
     case EPI_GATE_RESID: launch_q<EPI_GATE_RESID, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
     case EPI_F32: launch_q<EPI_F32, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    case EPI_SILU_BF16: launch_q<EPI_SILU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
     default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
   }
 }

@@ -48,6 +48,7 @@ enum EpiMode : int {
   EPI_GELU_BF16 = 1,   // out_bf16[m,n] = gelu_tanh(acc + bias)
   EPI_GATE_RESID = 2,  // resid[m,n] += (acc + bias) * gate * scale ; optional bf16 shadow of the new resid
   EPI_F32 = 3,         // out_f32[m,n] = acc + bias
+  EPI_SILU_BF16 = 4,   // out_bf16[m,n] = silu(acc + bias)
 };
 
 struct GemmEpi {
@@ -126,7 +127,11 @@ void launch_gemv(const bf16* W, const float* bias, const float* x, float* y, int
                  cudaStream_t s);
 void launch_mask_to_bias(const int32_t* mask, float* bias, int n, cudaStream_t s);
 void launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
-void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s);
+void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s, bf16* out_bf16 = nullptr);
+// out_bf16 = silu(in) (fp32 in)
+void launch_silu_cast(const float* in, bf16* out, int64_t n, cudaStream_t s);
+// ts[i] = (i % period) < frozen ? 0 : sigma   (per-token timesteps of the image-conditioned denoise loop)
+void launch_fill_token_timesteps(float* ts, int n, int period, int frozen, const float* sigma_dev, cudaStream_t s);
 // latent [C, T] (channel-major, T = F*H*W tokens) <-> tokens [T, C]
 void launch_patchify(const float* latent, bf16* tok_bf16, float* tok_f32, int C, int T, cudaStream_t s);
 void launch_unpatchify(const float* tok, float* latent, int C, int T, cudaStream_t s);
@@ -143,6 +148,7 @@ struct GuidedEulerArgs {
   size_t n;
   float cfg, phi, stg, ge_gamma, sigma, sigma_next;
   double* scratch;  // >= 8 doubles of device scratch for the rescale reductions
+  size_t period = 0, frozen = 0;  // elements with (i % period) < frozen keep their latent (frame-0 freeze of the I2V loop)
 };
 void launch_guided_euler(const GuidedEulerArgs& a, cudaStream_t s);
 void launch_fill_normal_bf16(bf16* p, int64_t n, float std, float mean, uint64_t seed, cudaStream_t s);

@@ -468,9 +468,13 @@ def guided_euler_step(latent: Tensor, v_cond: Tensor, v_uncond: Optional[Tensor]
 def denoise_loop(w, cfg: DiTConfig, noise: Tensor, context: Tensor, mask: Optional[Tensor], sigmas: Sequence[float],
                  neg_context: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None, cfg_scale: float = 1.0,
                  phi: float = 0.0, stg_scale: float = 0.0, stg_blocks: Sequence[int] = (29,), ge_gamma: float = 0.0,
-                 mlx_bf16: bool = True, dtype=torch.float32, return_velocities: bool = False):
-    """P/LTXPipeline.swift:793-956 (generateVideo step loop).  noise [1,C,F,H,W] fp32."""
-    latent = noise.float() * sigmas[0]                           # :793
+                 mlx_bf16: bool = True, dtype=torch.float32, return_velocities: bool = False,
+                 frame0_conditioned: bool = False, init_latent: Optional[Tensor] = None):
+    """P/LTXPipeline.swift:793-956 (generateVideo step loop).  noise [1,C,F,H,W] fp32.
+    frame0_conditioned = the image-to-video variant of denoise() (:2237-2252, 2344-2357): tokens of latent frame 0 are a
+    clean conditioning frame -> per-token timesteps sigma * (1 - mask), Euler only on frames 1+.  init_latent (if given) is
+    the starting latent (frame 0 already holding the encoded image)."""
+    latent = noise.float() * sigmas[0] if init_latent is None else init_latent.float().clone()   # :793
     fhw = tuple(noise.shape[2:])
     v_prev = None
     vels = []
@@ -478,6 +482,10 @@ def denoise_loop(w, cfg: DiTConfig, noise: Tensor, context: Tensor, mask: Option
         sg, sn = sigmas[step], sigmas[step + 1]
         tok = patchify(latent)
         ts = torch.tensor([sg], dtype=torch.float32)
+        if frame0_conditioned:
+            m = torch.zeros(1, fhw[0] * fhw[1] * fhw[2])
+            m[:, : fhw[1] * fhw[2]] = 1.0
+            ts = sg * (1.0 - m)
         vc = unpatchify(dit_forward(w, cfg, tok, context, ts, mask, fhw, dtype=dtype, mlx_bf16=mlx_bf16), fhw).float()
         vu = vs = None
         if cfg_scale > 1.0 and neg_context is not None:
@@ -485,7 +493,10 @@ def denoise_loop(w, cfg: DiTConfig, noise: Tensor, context: Tensor, mask: Option
         if stg_scale > 0:
             vs = unpatchify(dit_forward(w, cfg, tok, context, ts, mask, fhw, stg_blocks=stg_blocks, skip_self_attn=True,
                                         dtype=dtype, mlx_bf16=mlx_bf16), fhw).float()
-        latent, v_prev = guided_euler_step(latent, vc, vu, vs, v_prev, cfg_scale, phi, stg_scale, ge_gamma, sg, sn)
+        new_latent, v_prev = guided_euler_step(latent, vc, vu, vs, v_prev, cfg_scale, phi, stg_scale, ge_gamma, sg, sn)
+        if frame0_conditioned:                                   # slice Euler: frame 0 is re-attached unchanged
+            new_latent[:, :, :1] = latent[:, :, :1]
+        latent = new_latent
         vels.append(v_prev)
     return (latent, vels) if return_velocities else latent
 
