@@ -15,6 +15,8 @@
 // waves of 148 CTAs ("wave-fitted" tiles): at M = 1536 an N = 4096 GEMM runs as 12 x 24 tiles of 128x176 (2 waves, 97 %
 // full) instead of 12 x 16 tiles of 128x256 (2 waves, 65 % full); N = 8192 / 16384 use 128x224 (3 / 6 waves, 99 % full).
 // A stream-K variant (split last wave + fp32 partial fix-up) was measured slower than this on B200 and was dropped.
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "ltx_internal.h"
 #include "ptx.cuh"
@@ -210,6 +212,13 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   } else {
     LTX_CHECK(epi.out != nullptr, 2, "GEMM: missing output");
     LTX_CHECK(epi.ldo % (epi.mode == EPI_F32 ? 4 : 8) == 0, 2, "GEMM: output ld alignment");
+  }
+  // force_bn >= 1000 selects the 2-CTA pair kernel (gemm2.cu) with width force_bn - 1000 (0 = fitted); by default the
+  // pair kernel is used whenever the problem has more than one 128-row tile (LTX_GEMM_2CTA=0 disables it)
+  static const bool pair_default = [] { const char* e = getenv("LTX_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
+  if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {
+    launch_gemm_2cta(A, lda, B, ldb, M, N, K, epi, stream, force_bn >= 1000 ? force_bn - 1000 : 0, a_kblock, a_kblock_stride);
+    return;
   }
   // force_bn: 0 = wave-fitted width (see fit_tile_width); otherwise a multiple of 16 in [32, 256]
   int bn = force_bn;

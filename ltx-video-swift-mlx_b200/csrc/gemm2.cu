@@ -1,0 +1,280 @@
+// 2-CTA (cta_group::2) variant of the bf16 GEMM: a cluster of two CTAs on one TPC computes a 256 x BN tile.
+//
+// Why: the 1-CTA kernel (gemm.cu) is bound by operand delivery L2 -> SM (48 KB per k-block per CTA at 128x256).  In pair
+// mode each CTA loads its own 128 rows of A but only HALF of the B tile (BN/2 rows); tcgen05.mma.cta_group::2 (M = 256)
+// reads both halves across the pair, so a CTA moves 16 + BN/4 KB per k-block (32 KB at BN = 256) for the same flops, and
+// the smem freed by the half-size B stage buys a deeper TMA ring (6 stages).
+//
+// Protocol (mirrors the CUTLASS / DeepGEMM 2-SM pattern):
+//   * both CTAs run every warp role; only the leader (cluster rank 0) issues tcgen05.mma
+//   * TMA loads use the .cta_group::2 form and signal the LEADER's full barrier (mbarrier address with the peer bit
+//     cleared); the leader arms it with expect_tx for both CTAs' bytes, the peer adds a remote arrive
+//   * tcgen05.commit ... .multicast::cluster (mask 0b11) releases the smem stage / publishes the accumulator in BOTH CTAs
+//   * each CTA's epilogue drains its own 128 TMEM lanes and arrives remotely on the leader's tmem-empty barrier
+//   * TMEM is allocated with cta_group::2 by the same warp of both CTAs; cluster barriers bracket setup and teardown
+#include "gemm_epilogue.cuh"
+#include "ltx_internal.h"
+#include "ptx.cuh"
+
+namespace ltx {
+
+namespace {
+
+constexpr int BM2 = 128;          // rows per CTA (256 per pair)
+constexpr int BK2 = 64;
+constexpr int G2_THREADS = 192;
+constexpr int G2_STAGES = 6;
+constexpr int G2_BN_MAX = 256;
+constexpr uint32_t G2_A_BYTES = BM2 * BK2 * 2;                 // 16 KB
+constexpr uint32_t G2_B_STRIDE = (G2_BN_MAX / 2) * BK2 * 2;    // 16 KB: half of the B tile
+constexpr size_t G2_SMEM = 1024 + G2_STAGES * (G2_A_BYTES + G2_B_STRIDE) + (2 * G2_STAGES + 4) * 8 + 16;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// 2-SM TMA load: data lands in this CTA's smem, completion bytes are reported to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive (once all earlier MMAs of this thread completed) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, int BN,
+               int a_kblock, const GemmEpi ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + G2_STAGES * G2_B_STRIDE);
+  uint64_t* empty = full + G2_STAGES;
+  uint64_t* tfull = empty + G2_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_mp = (M + 2 * BM2 - 1) / (2 * BM2);   // 256-row pair tiles
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_mp * num_n;
+  const int num_k = (K + BK2 - 1) / BK2;
+  const int half_bn = BN >> 1;
+  const uint32_t b_bytes = static_cast<uint32_t>(half_bn) * BK2 * 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full[i], 2);    // leader's expect_tx arrive + the peer's remote arrive (only the leader's copy is used)
+      mbar_init(&empty[i], 1);   // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);   // multicast tcgen05.commit
+      mbar_init(&tempty[i], 8);  // 4 epilogue warps of each CTA (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int mp = tile % num_mp, n_blk = tile / num_mp;
+        const int m0 = (mp * 2 + static_cast<int>(rank)) * BM2;
+        const int n0 = n_blk * BN + static_cast<int>(rank) * half_bn;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (G2_A_BYTES + b_bytes));
+          else mbar_arrive_remote(&full[stage], 0);
+          if (a_kblock > 0)
+            tma_load_3d_2sm(sA + stage * G2_A_BYTES, &tmA, &full[stage], (kb * BK2) % a_kblock, m0, (kb * BK2) / a_kblock);
+          else
+            tma_load_2d_2sm(sA + stage * G2_A_BYTES, &tmA, &full[stage], kb * BK2, m0);
+          tma_load_2d_2sm(sB + stage * G2_B_STRIDE, &tmB, &full[stage], kb * BK2, n0);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM2, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+        const int as = t & 1;
+        const uint32_t aphase = (t >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * G2_BN_MAX;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * G2_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * G2_B_STRIDE);
+#pragma unroll
+          for (int k = 0; k < BK2 / 16; ++k)
+            umma_bf16_2cta(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int t = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++t) {
+      const int mp = tile % num_mp, n_blk = tile / num_mp;
+      const int as = t & 1;
+      const uint32_t aphase = (t >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = (mp * 2 + static_cast<int>(rank)) * BM2 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BN_MAX;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
+      }
+      if (BN & 16) {
+        uint32_t r[32];
+        tmem_ld16(taddr + (BN & ~31), r);
+        tmem_ld_wait();
+        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty[as], 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
+  }
+}
+
+template <int MODE>
+void launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, int a_kblock, const GemmEpi& epi,
+             cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = gemm_bf16_2cta<MODE>;
+  if (!configured) {
+    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G2_SMEM)));
+    configured = true;
+  }
+  const int tiles = ((M + 2 * BM2 - 1) / (2 * BM2)) * ((N + BN - 1) / BN);
+  const int clusters = device_sm_count() / 2;
+  const int grid = 2 * (tiles < clusters ? tiles : clusters);
+  kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, BN, a_kblock, epi);
+  LTX_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+// tile width for the pair kernel: whole waves of (#SM / 2) clusters over 256-row tiles; widths are multiples of 32 so that
+// each CTA's half (BN / 2) is a multiple of 16 rows of B
+int gemm2_fit_tile_width(int M, int N) {
+  const int clusters = device_sm_count() / 2;
+  const int num_mp = (M + 255) / 256;
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const long long tiles = static_cast<long long>(num_mp) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + clusters - 1) / clusters;
+    const double cost = static_cast<double>(waves) * (bn + 12.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                      cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride) {
+  int bn = force_bn ? force_bn : gemm2_fit_tile_width(M, N);
+  LTX_CHECK(bn >= 64 && bn <= 256 && bn % 32 == 0, 2, "2-CTA GEMM: tile width must be a multiple of 32 in [64, 256]");
+  CUtensorMap tmA;
+  if (a_kblock > 0) {
+    LTX_CHECK(a_kblock % BK2 == 0 && K % a_kblock == 0 && lda == a_kblock, 2, "GEMM: bad K-blocked A layout");
+    tmA = make_tmap_3d(A, a_kblock, M, K / a_kblock, lda, a_kblock_stride, 64, BM2);
+  } else {
+    tmA = make_tmap_2d(A, M, K, lda, BM2);
+  }
+  CUtensorMap tmB = make_tmap_2d(B, N, K, ldb, bn / 2);
+  switch (epi.mode) {
+    case EPI_BF16: launch2<EPI_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_GELU_BF16: launch2<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_GATE_RESID: launch2<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_F32: launch2<EPI_F32>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_SILU_BF16: launch2<EPI_SILU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
+  }
+}
+
+}  // namespace ltx

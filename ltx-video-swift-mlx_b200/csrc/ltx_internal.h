@@ -78,6 +78,9 @@ struct GemmEpi {
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                  cudaStream_t stream, int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
 int gemm_fit_tile_width(int M, int N);
+// 2-CTA (cta_group::2) pair kernel, same contract as launch_gemm (gemm2.cu)
+void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                      cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
 // ---------------------------------------------------------------- quantised weights (gemm_q.cu)
 struct QuantW {
   const uint8_t* q = nullptr;    // [N, K] codes (8-bit) or [N, K/2] packed nibbles (4-bit)

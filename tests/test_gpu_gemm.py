@@ -25,7 +25,8 @@ SHAPES = [
     (48, 520, 192, 0), (300, 264, 128, 0), (1536, 128, 4096, 0), (1000, 1000, 512, 256),
     (1536, 4096, 4096, 0), (1536, 4096, 4096, 128), (4096, 48, 256, 0), (130, 8192, 320, 0),
     (1536, 4096, 4096, 176), (1536, 4096, 4096, 240), (300, 1000, 256, 48), (1536, 8192, 4096, 0), (4096, 1536, 4096, 0), (1536, 16384, 512, 0), (2000, 2304, 1024, 0),
-    (1536, 128, 4096, 128), (19000, 256, 128, 0),
+    (1536, 128, 4096, 128), (19000, 256, 128, 0), (1536, 4096, 4096, 1192), (300, 1000, 256, 1064), (256, 256, 64, 1256),
+    (1536, 16384, 4096, 1000), (130, 264, 128, 1128),
 ]
 
 

@@ -27,25 +27,25 @@ def bench_q(name, M, N, K, bits):
     t = sorted(ts)[len(ts) // 2]
     print(f"{name:9s} M={M} N={N} K={K} int{bits}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
 
-for nm, M, N, K in [("qk", 1536, 8192, 4096), ("out", 1536, 4096, 4096), ("ffn_in", 1536, 16384, 4096), ("ffn_out", 1536, 4096, 16384)]:
+for nm, M, N, K in ([("qk", 1536, 8192, 4096), ("out", 1536, 4096, 4096), ("ffn_in", 1536, 16384, 4096), ("ffn_out", 1536, 4096, 16384)] if '--quant' in sys.argv else []):
     for bits in (8, 4):
         bench_q(nm, M, N, K, bits)
 
-for name, M, N, K, mode in shapes[:0]:
+for name, M, N, K, mode in (shapes if '--bf16' in sys.argv else []):
     A = torch.randn(M, K, device="cuda").bfloat16()
     B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     bias = torch.randn(max(M, N), device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
     x = torch.zeros(M, N, device="cuda")
     g = torch.ones(N, device="cuda")
-    for bn in ([0, 256, 224, 192, 176, 128] if N > 128 else [0, 128, 64, 32]):
+    for bn in ([0, 1256, 1224, 1192, 1160, 256, 224, 176] if N > 128 else [0, 128, 32]):
         def run():
             if mode == 2:
                 ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), x.data_ptr(),
                                                      g.data_ptr(), g.data_ptr(), None, M, N, K, 0.5))
             else:
                 ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn))
-        if mode == 2 and bn != 0:
+        if mode == 2 and bn not in (0,):
             continue
         for _ in range(3):
             run()
