@@ -35,7 +35,8 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_STRIDE = BN_MAX * BK * 2;  // smem stage pitch of the B ring (a stage holds bn <= 256 rows)
   static constexpr uint32_t TMEM_COLS = 512;             // two accumulator stages of up to 256 columns
-  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_STRIDE) + (2 * STAGES + 4) * 8 + 16;
+  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_STRIDE) + (2 * STAGES + 4) * 8 + 16 + 128 +
+                                 4 * EPI_STAGE_BYTES;  // + per-warp epilogue staging tiles
 };
 
 template <int MODE>
@@ -54,6 +55,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,21 +138,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t aphase = (t >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::BN_MAX;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
-      }
-      if (BN & 16) {  // 16-column tail chunk of a tile whose width is an odd multiple of 16
-        uint32_t r[32];
-        tmem_ld16(taddr + (BN & ~31), r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
-      }
+      epilogue_tile<MODE>(taddr, BN, epi_stage + (warp - 2) * (EPI_STAGE_BYTES / 4), lane, m_blk * BM + q * 32, n_blk * BN, M, N, ep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -215,6 +204,10 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   }
   // force_bn >= 1000 selects the 2-CTA pair kernel (gemm2.cu) with width force_bn - 1000 (0 = fitted); by default the
   // pair kernel is used whenever the problem has more than one 128-row tile (LTX_GEMM_2CTA=0 disables it)
+  if (force_bn == 0) {  // experiment hook: LTX_GEMM_FORCE_BN is re-read on every call
+    const char* e = getenv("LTX_GEMM_FORCE_BN");
+    if (e) force_bn = atoi(e);
+  }
   static const bool pair_default = [] { const char* e = getenv("LTX_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
   if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {
     launch_gemm_2cta(A, lda, B, ldb, M, N, K, epi, stream, force_bn >= 1000 ? force_bn - 1000 : 0, a_kblock, a_kblock_stride);

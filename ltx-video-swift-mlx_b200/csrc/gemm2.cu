@@ -12,6 +12,8 @@
 //   * tcgen05.commit ... .multicast::cluster (mask 0b11) releases the smem stage / publishes the accumulator in BOTH CTAs
 //   * each CTA's epilogue drains its own 128 TMEM lanes and arrives remotely on the leader's tmem-empty barrier
 //   * TMEM is allocated with cta_group::2 by the same warp of both CTAs; cluster barriers bracket setup and teardown
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "ltx_internal.h"
 #include "ptx.cuh"
@@ -27,7 +29,7 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_BN_MAX = 256;
 constexpr uint32_t G2_A_BYTES = BM2 * BK2 * 2;                 // 16 KB
 constexpr uint32_t G2_B_STRIDE = (G2_BN_MAX / 2) * BK2 * 2;    // 16 KB: half of the B tile
-constexpr size_t G2_SMEM = 1024 + G2_STAGES * (G2_A_BYTES + G2_B_STRIDE) + (2 * G2_STAGES + 4) * 8 + 16;
+constexpr size_t G2_SMEM = 1024 + G2_STAGES * (G2_A_BYTES + G2_B_STRIDE) + (2 * G2_STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -105,6 +107,7 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + G2_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -193,21 +196,9 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (t >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = (mp * 2 + static_cast<int>(rank)) * BM2 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * G2_BN_MAX;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
-      }
-      if (BN & 16) {
-        uint32_t r[32];
-        tmem_ld16(taddr + (BN & ~31), r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
-      }
+      epilogue_tile<MODE>(taddr, BN, epi_stage + (warp - 2) * (EPI_STAGE_BYTES / 4), lane,
+                          (mp * 2 + static_cast<int>(rank)) * BM2 + q * 32, n_blk * BN, M, N, ep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty[as], 0);
@@ -233,23 +224,28 @@ void launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K
   const int tiles = ((M + 2 * BM2 - 1) / (2 * BM2)) * ((N + BN - 1) / BN);
   const int clusters = device_sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, BN, a_kblock, epi);
+  static const int dbg = [] { const char* e = getenv("LTX_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  GemmEpi ep2 = epi;
+  ep2.debug = dbg;
+  kern<<<grid, G2_THREADS, G2_SMEM, stream>>>(tmA, tmB, M, N, K, BN, a_kblock, ep2);
   LTX_CUDA(cudaGetLastError());
 }
 
 }  // namespace
 
-// tile width for the pair kernel: whole waves of (#SM / 2) clusters over 256-row tiles; widths are multiples of 32 so that
-// each CTA's half (BN / 2) is a multiple of 16 rows of B
+// tile width for the pair kernel: whole waves of (#SM / 2) clusters over 256-row tiles; widths are multiples of 16 (the
+// tcgen05.mma N granularity at cta_group::2), so each CTA's half (BN / 2) is a whole number of 8-row swizzle atoms of B
 int gemm2_fit_tile_width(int M, int N) {
   const int clusters = device_sm_count() / 2;
   const int num_mp = (M + 255) / 256;
   int best = 256;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 64; bn -= 32) {
+  for (int bn = 256; bn >= 64; bn -= 16) {
     const long long tiles = static_cast<long long>(num_mp) * ((N + bn - 1) / bn);
     const long long waves = (tiles + clusters - 1) / clusters;
-    const double cost = static_cast<double>(waves) * (bn + 12.0);
+    // per-tile time is bound by operand delivery L2 -> SM, ~ (16 KB of A + 64 B x bn of B) per k-block at ~42 B/clk/SM:
+    // proportional to bn + 257 (fits the measured width sweep within 5 %); narrow tiles pay for re-reading A
+    const double cost = static_cast<double>(waves) * (bn + 257.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -258,7 +254,7 @@ int gemm2_fit_tile_width(int M, int N) {
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride) {
   int bn = force_bn ? force_bn : gemm2_fit_tile_width(M, N);
-  LTX_CHECK(bn >= 64 && bn <= 256 && bn % 32 == 0, 2, "2-CTA GEMM: tile width must be a multiple of 32 in [64, 256]");
+  LTX_CHECK(bn >= 64 && bn <= 256 && bn % 16 == 0, 2, "2-CTA GEMM: tile width must be a multiple of 16 in [64, 256]");
   CUtensorMap tmA;
   if (a_kblock > 0) {
     LTX_CHECK(a_kblock % BK2 == 0 && K % a_kblock == 0 && lda == a_kblock, 2, "GEMM: bad K-blocked A layout");

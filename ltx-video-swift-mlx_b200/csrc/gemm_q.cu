@@ -31,7 +31,7 @@ constexpr int Q_BN_MAX = 256;
 constexpr uint32_t QA_BYTES = QBM * QBK * 2;           // 16 KB
 constexpr uint32_t QR_STRIDE = Q_BN_MAX * QBK;         // raw codes, up to 16 KB
 constexpr uint32_t QB_STRIDE = Q_BN_MAX * QBK * 2;     // dequantised bf16 operand, up to 32 KB
-constexpr size_t Q_SMEM = 1024 + Q_STAGES * (QA_BYTES + QR_STRIDE + QB_STRIDE) + (3 * Q_STAGES + 4) * 8 + 16;
+constexpr size_t Q_SMEM = 1024 + Q_STAGES * (QA_BYTES + QR_STRIDE + QB_STRIDE) + (3 * Q_STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
 
 __device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s, float bm) {
   // two codes (bytes i0, i1 of `word`) -> s*q+beta -> packed bf16x2.  PRMT drops the code byte into mantissa bits [15:8]
@@ -58,6 +58,7 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + Q_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + QBM - 1) / QBM;
@@ -134,21 +135,8 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (t >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = m_blk * QBM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Q_BN_MAX;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + c * 32, 32, M, N, ep);
-      }
-      if (BN & 16) {
-        uint32_t r[32];
-        tmem_ld16(taddr + (BN & ~31), r);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(r, row, n_blk * BN + (BN & ~31), 16, M, N, ep);
-      }
+      epilogue_tile<MODE>(taddr, BN, epi_stage + (warp - 2) * (EPI_STAGE_BYTES / 4), lane, m_blk * QBM + q * 32, n_blk * BN, M, N, ep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);

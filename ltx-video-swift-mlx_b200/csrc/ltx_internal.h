@@ -70,6 +70,7 @@ struct GemmEpi {
   // out[(n / col_block) * col_block_stride + m * ldo + n % col_block]; col_block = 0 -> plain row-major.
   int col_block = 0;
   int64_t col_block_stride = 0;
+  int debug = 0;  // bit 0: skip the epilogue's global traffic (LTX_GEMM_DEBUG, timing experiments only)
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 K-major (row pitch lda / ldb elements, multiples of 8).

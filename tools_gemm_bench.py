@@ -1,5 +1,5 @@
 """Micro-benchmark of the tcgen05 GEMM on the DiT shapes (device time via CUDA events on the library stream)."""
-import math, sys, torch
+import math, os, sys, torch
 sys.path.insert(0, ".")
 import ltx_video_swift_mlx_b200  # noqa
 from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
@@ -38,15 +38,16 @@ for name, M, N, K, mode in (shapes if '--bf16' in sys.argv else []):
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
     x = torch.zeros(M, N, device="cuda")
     g = torch.ones(N, device="cuda")
-    for bn in ([0, 1256, 1224, 1192, 1160, 256, 224, 176] if N > 128 else [0, 128, 32]):
+    for bn in ([0, 1256, 1224, 1192, 1176, 1160] if N > 128 else [0, 128, 32]):
         def run():
             if mode == 2:
                 ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), x.data_ptr(),
                                                      g.data_ptr(), g.data_ptr(), None, M, N, K, 0.5))
             else:
                 ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn))
-        if mode == 2 and bn not in (0,):
-            continue
+        if mode == 2:
+            if bn: os.environ["LTX_GEMM_FORCE_BN"] = str(bn)
+            else: os.environ.pop("LTX_GEMM_FORCE_BN", None)
         for _ in range(3):
             run()
         ctx.sync()
@@ -58,4 +59,5 @@ for name, M, N, K, mode in (shapes if '--bf16' in sys.argv else []):
             e0.record(stream); run(); e1.record(stream); ctx.sync(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts)[len(ts) // 2]
+        os.environ.pop("LTX_GEMM_FORCE_BN", None)
         print(f"{name:9s} M={M} N={N} K={K} mode={mode} bn={bn:5d}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)

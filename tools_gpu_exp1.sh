@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+./tools/occ_query > gpurun_out/occ_query.txt 2>&1; cat gpurun_out/occ_query.txt
+timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x --no-header -p no:cacheprovider 2>&1 | tail -3
+echo "=== epilogue on"; timeout 600 python tools_gemm_bench.py --bf16 2>&1 | tee gpurun_out/gemm_bench_epi.log
+echo "=== epilogue off"; LTX_GEMM_DEBUG=1 timeout 600 python tools_gemm_bench.py --bf16 2>&1 | tee gpurun_out/gemm_bench_noepi.log
