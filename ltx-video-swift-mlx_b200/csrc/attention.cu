@@ -92,6 +92,8 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();   // PDL: the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -312,7 +314,7 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
   p.O = O;
   p.ldo = ldo;
   dim3 grid((Nq + 2 * TQ - 1) / (2 * TQ), H, B);
-  attention_fwd_tcgen05<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  launch_pdl(attention_fwd_tcgen05, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tmQ, tmK, tmV, p);
   LTX_CUDA(cudaGetLastError());
 }
 

@@ -131,6 +131,8 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  griddep_wait();   // PDL: the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -222,6 +224,8 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 __global__ void __launch_bounds__(256) vae_prep_kernel(const float* __restrict__ x, bf16* __restrict__ out, int T, int H,
                                                         int W, int C, int mode, const float* __restrict__ a,
                                                         const float* __restrict__ b, int tshift) {
+  griddep_launch();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
   const int64_t wid0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -286,7 +290,7 @@ void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom&
   }
   const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, CONV_THREADS, Cfg::SMEM, s>>>(tmX, tmW, g, ep);
+  launch_pdl(kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
   LTX_CUDA(cudaGetLastError());
 }
 
@@ -330,7 +334,7 @@ void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int 
   int64_t blocks = (nvox + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  vae_prep_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, out, T, H, W, C, mode, a, b, causal ? 2 : 1);
+  launch_pdl(vae_prep_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, x, out, T, H, W, C, mode, a, b, causal ? 2 : 1);
   LTX_CUDA(cudaGetLastError());
 }
 

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* __re
   __shared__ float red[33];
   constexpr int D = 4 * VPT * 256;
   const int row0 = blockIdx.x * ROWS;
+  griddep_launch();
+  griddep_wait();   // x and the ada vectors come from the preceding kernels
   int cur_mod = -1;
   float4 sc[VPT], sh[VPT];
   for (int rr = 0; rr < ROWS; ++rr) {
@@ -233,6 +235,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
     wa[t] = a.x; wa[t + 1] = a.y; wa[t + 2] = a.z; wa[t + 3] = a.w;
     wb[t] = b.x; wb[t + 1] = b.y; wb[t + 2] = b.z; wb[t + 3] = b.w;
   }
+  griddep_launch();
+  griddep_wait();   // the learned weights above are constants; x comes from the preceding GEMM
   const int row0 = blockIdx.x * ROWS;
   for (int rr = 0; rr < ROWS; ++rr) {
     const int row = row0 + rr;
@@ -516,10 +520,8 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
   LTX_CHECK(D % 4 == 0 && M > 0 && ada_ld % 4 == 0, 2, "rmsnorm_mod: D must be a multiple of 4");
   if (D == 4096) {
     constexpr int ROWS = 4;
-    rmsnorm_mod_fast_kernel<4, ROWS><<<(M + ROWS - 1) / ROWS, 256, 0, s>>>(x, out, M, tbl_shift, tbl_scale, ada_shift, ada_scale,
-                                                                          ada_ld, rows_per_mod > 0 ? rows_per_mod : 1, eps,
-                                                                          layernorm);
-    LTX_CUDA(cudaGetLastError());
+    launch_pdl(rmsnorm_mod_fast_kernel<4, ROWS>, dim3((M + ROWS - 1) / ROWS), dim3(256), 0, s, x, out, M, tbl_shift, tbl_scale,
+               ada_shift, ada_scale, ada_ld, rows_per_mod > 0 ? rows_per_mod : 1, eps, layernorm);
     return;
   }
   rmsnorm_mod_kernel<<<M, 256, 0, s>>>(x, out, D, tbl_shift, tbl_scale, ada_shift, ada_scale, ada_ld,
@@ -540,8 +542,8 @@ void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const
   if (D == 4096) {
     constexpr int ROWS = 4;
     dim3 grid((M + ROWS - 1) / ROWS, w_second ? 2 : 1);
-    qknorm_rope_fast_kernel<ROWS><<<grid, 256, 0, s>>>(x, ld, M, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs, bld);
-    LTX_CUDA(cudaGetLastError());
+    launch_pdl(qknorm_rope_fast_kernel<ROWS>, grid, dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs,
+               bld);
     return;
   }
   qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps, b0, hpb, bs, bld);

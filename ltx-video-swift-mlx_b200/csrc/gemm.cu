@@ -82,6 +82,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only from here on
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -166,8 +169,7 @@ void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM, stream>>>(tmA, tmB, M, N, K, BN, a_kblock, epi);
-  LTX_CUDA(cudaGetLastError());
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, epi);
 }
 
 // Tile width that minimises (waves x width): time ~ ceil(tiles / #SM) * (BN + c0), c0 = fixed per-tile cost in columns.
@@ -207,6 +209,13 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   if (force_bn == 0) {  // experiment hook: LTX_GEMM_FORCE_BN is re-read on every call
     const char* e = getenv("LTX_GEMM_FORCE_BN");
     if (e) force_bn = atoi(e);
+  }
+  // force_bn >= 2000 selects the 4-CTA multicast kernel (gemm4.cu) with width force_bn - 2000 (0 = fitted); LTX_GEMM_4CTA=1
+  // makes it the default for problems with more than one 128-row tile and at least two column tiles
+  static const bool quad_default = [] { const char* e = getenv("LTX_GEMM_4CTA"); return e ? atoi(e) != 0 : false; }();
+  if (force_bn >= 2000 || (force_bn == 0 && quad_default && M > 128 && N >= 512)) {
+    launch_gemm_4cta(A, lda, B, ldb, M, N, K, epi, stream, force_bn >= 2000 ? force_bn - 2000 : 0, a_kblock, a_kblock_stride);
+    return;
   }
   static const bool pair_default = [] { const char* e = getenv("LTX_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
   if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {

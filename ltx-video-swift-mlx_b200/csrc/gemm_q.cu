@@ -84,6 +84,9 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; global memory is touched only from here on
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -296,7 +299,7 @@ void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int 
   }
   const int tiles = ((M + QBM - 1) / QBM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, Q_THREADS, Q_SMEM, stream>>>(tmA, tmQ, M, N, K, BN, s, b, epi);
+  launch_pdl(kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, epi);
   LTX_CUDA(cudaGetLastError());
 }
 

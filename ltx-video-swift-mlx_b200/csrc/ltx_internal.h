@@ -30,6 +30,24 @@ struct LtxError : public std::runtime_error {
                                    __FILE__ ":" + std::to_string(__LINE__));                                 \
   } while (0)
 
+// ---------------------------------------------------------------- kernel launch with programmatic stream serialization
+// The kernel must call griddep_wait() (ptx.cuh) before touching dependent global memory.  LTX_PDL=0 launches normally.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  LTX_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
 // ---------------------------------------------------------------- TMA descriptors (tmap.cu)
 // 2-D row-major bf16 matrix [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
 CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
@@ -82,6 +100,11 @@ int gemm_fit_tile_width(int M, int N);
 // 2-CTA (cta_group::2) pair kernel, same contract as launch_gemm (gemm2.cu)
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
+// 4-CTA cluster kernel: two pairs side by side along N share A through TMA multicast (gemm4.cu), same contract
+void launch_gemm_4cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                      cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
+int gemm4_max_clusters();
+int gemm4_fit_tile_width(int M, int N);
 // ---------------------------------------------------------------- quantised weights (gemm_q.cu)
 struct QuantW {
   const uint8_t* q = nullptr;    // [N, K] codes (8-bit) or [N, K/2] packed nibbles (4-bit)

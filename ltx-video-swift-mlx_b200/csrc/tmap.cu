@@ -1,10 +1,16 @@
 // Host-side TMA descriptor construction.  cuTensorMapEncodeTiled is fetched through the runtime's driver entry
 // point lookup so that libltxcuda.so has no link-time dependency on libcuda.so (it must build on a GPU-less box).
+#include <cstdlib>
 #include <mutex>
 
 #include "ltx_internal.h"
 
 namespace ltx {
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("LTX_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
