@@ -314,7 +314,7 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
   p.O = O;
   p.ldo = ldo;
   dim3 grid((Nq + 2 * TQ - 1) / (2 * TQ), H, B);
-  launch_pdl(attention_fwd_tcgen05, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tmQ, tmK, tmV, p);
+  launch_pdl(PDL_ATTN, attention_fwd_tcgen05, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tmQ, tmK, tmV, p);
   LTX_CUDA(cudaGetLastError());
 }
 

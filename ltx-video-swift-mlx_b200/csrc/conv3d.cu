@@ -221,9 +221,9 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // Padding prologue: one warp per padded voxel.
 // mode 0: copy ; 1: x*a[c] + b[c] ; 2: silu(x / sqrt(mean_c x^2 + 1e-8) * (1 + a[c]) + b[c])
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vae_prep_kernel(const float* __restrict__ x, bf16* __restrict__ out, int T, int H,
-                                                        int W, int C, int mode, const float* __restrict__ a,
-                                                        const float* __restrict__ b, int tshift) {
+// (x, a, b are produced by preceding kernels: no const __restrict__, see griddep_wait in ptx.cuh)
+__global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out, int T, int H, int W, int C, int mode,
+                                                        const float* a, const float* b, int tshift) {
   griddep_launch();
   griddep_wait();
   const int lane = threadIdx.x & 31;
@@ -290,7 +290,7 @@ void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom&
   }
   const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  launch_pdl(kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
+  launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
   LTX_CUDA(cudaGetLastError());
 }
 
@@ -334,7 +334,7 @@ void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int 
   int64_t blocks = (nvox + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  launch_pdl(vae_prep_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, x, out, T, H, W, C, mode, a, b, causal ? 2 : 1);
+  launch_pdl(PDL_VAE, vae_prep_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, x, out, T, H, W, C, mode, a, b, causal ? 2 : 1);
   LTX_CUDA(cudaGetLastError());
 }
 

@@ -1,6 +1,8 @@
 // HBM-bound row / elementwise kernels of the DiT step: AdaLN-modulated RMSNorm / LayerNorm, q/k RMSNorm-across-heads
 // fused with split RoPE, the timestep-embedding GEMV chain, patchify / unpatchify, and the fused
 // CFG + rescale + STG + GE + Euler update.  All vectorised 16-byte accesses, fp32 math.
+#include <cstdlib>
+
 #include "ltx_internal.h"
 #include "ptx.cuh"
 
@@ -22,6 +24,26 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   }
   __syncthreads();
   return red[32];
+}
+
+// R independent sums at once (one barrier pair for all of them); every thread gets all totals; fixed summation order
+template <int R>
+__device__ __forceinline__ void block_sum_multi(float (&v)[R], float* red /* >= 8 * R floats, 256-thread CTAs */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = warp_sum(v[r]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) red[warp * R + r] = v[r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += red[w * R + r];
+    v[r] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -74,30 +96,74 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_kernel(const float* __restric
   }
 }
 
-// Fast path: D == 4 * VPT * 256.  Each thread keeps its VPT float4 column groups of the row in registers (one global
-// read), and its slice of the combined modulation vectors stays in registers across the ROWS rows a CTA processes
-// (the generic kernel re-read 4 x 16 KB of table/ada vectors from L2 per row, 2.7x the row's own HBM traffic).
+// Fast path: D == 4 * VPT * 256.  A CTA owns ROWS rows: ALL their loads are issued up front (ROWS * VPT float4 per thread in
+// flight, one global read of x), the ROWS row statistics are reduced together (one barrier pair), and the combined
+// modulation vectors are fetched once per CTA -- the kernel is one memory latency + one reduction deep instead of ROWS.
 template <int VPT, int ROWS>
-__global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* __restrict__ x, bf16* __restrict__ out, int M,
+__global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* x, bf16* out, int M,
                                                                 const float* __restrict__ tbl_shift,
                                                                 const float* __restrict__ tbl_scale,
-                                                                const float* __restrict__ ada_shift,
-                                                                const float* __restrict__ ada_scale, int64_t ada_ld,
+                                                                const float* ada_shift, const float* ada_scale, int64_t ada_ld,
                                                                 int rows_per_mod, float eps, int layernorm) {
-  __shared__ float red[33];
+  __shared__ float red[8 * ROWS];
   constexpr int D = 4 * VPT * 256;
   const int row0 = blockIdx.x * ROWS;
+  // PDL: x and the ada vectors are written by preceding kernels that may still be running when this CTA starts, so their
+  // pointers must NOT be const __restrict__: the compiler hoists such "invariant" loads above griddepcontrol.wait
   griddep_launch();
-  griddep_wait();   // x and the ada vectors come from the preceding kernels
+  griddep_wait();
+  float4 v[ROWS][VPT];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row0 + rr) * D);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+      v[rr][k] = (row0 + rr < M) ? xr[threadIdx.x + k * 256] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean[ROWS], rstd[ROWS];
+  if (layernorm) {
+    float s1[ROWS];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      s1[rr] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) s1[rr] += v[rr][k].x + v[rr][k].y + v[rr][k].z + v[rr][k].w;
+    }
+    block_sum_multi<ROWS>(s1, red);
+    float sv[ROWS];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      mean[rr] = s1[rr] / D;
+      sv[rr] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k) {
+        const float a = v[rr][k].x - mean[rr], b = v[rr][k].y - mean[rr], c = v[rr][k].z - mean[rr], d = v[rr][k].w - mean[rr];
+        sv[rr] += a * a + b * b + c * c + d * d;
+      }
+    }
+    block_sum_multi<ROWS>(sv, red);
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) rstd[rr] = rsqrtf(sv[rr] / D + eps);
+  } else {
+    float s2[ROWS];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      mean[rr] = 0.f;
+      s2[rr] = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        s2[rr] += v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y + v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w;
+    }
+    block_sum_multi<ROWS>(s2, red);
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) rstd[rr] = rsqrtf(s2[rr] / D + eps);
+  }
   int cur_mod = -1;
   float4 sc[VPT], sh[VPT];
+#pragma unroll
   for (int rr = 0; rr < ROWS; ++rr) {
     const int row = row0 + rr;
     if (row >= M) break;   // uniform across the CTA
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
-    float4 v[VPT];
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) v[k] = xr[threadIdx.x + k * 256];
     const int mod = row / rows_per_mod;
     if (mod != cur_mod) {
       cur_mod = mod;
@@ -111,32 +177,13 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* __re
         sh[k] = make_float4(c.x + d.x, c.y + d.y, c.z + d.z, c.w + d.w);
       }
     }
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      s1 += v[k].x + v[k].y + v[k].z + v[k].w;
-      s2 += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
-    }
-    float mean = 0.f, rstd;
-    if (layernorm) {
-      mean = block_sum(s1, red) / D;
-      float sv = 0.f;
-#pragma unroll
-      for (int k = 0; k < VPT; ++k) {
-        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
-        sv += a * a + b * b + c * c + d * d;
-      }
-      rstd = rsqrtf(block_sum(sv, red) / D + eps);
-    } else {
-      rstd = rsqrtf(block_sum(s2, red) / D + eps);
-    }
     uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(row) * D);
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
-      const float y0 = (v[k].x - mean) * rstd * sc[k].x + sh[k].x;
-      const float y1 = (v[k].y - mean) * rstd * sc[k].y + sh[k].y;
-      const float y2 = (v[k].z - mean) * rstd * sc[k].z + sh[k].z;
-      const float y3 = (v[k].w - mean) * rstd * sc[k].w + sh[k].w;
+      const float y0 = (v[rr][k].x - mean[rr]) * rstd[rr] * sc[k].x + sh[k].x;
+      const float y1 = (v[rr][k].y - mean[rr]) * rstd[rr] * sc[k].y + sh[k].y;
+      const float y2 = (v[rr][k].z - mean[rr]) * rstd[rr] * sc[k].z + sh[k].z;
+      const float y3 = (v[rr][k].w - mean[rr]) * rstd[rr] * sc[k].w + sh[k].w;
       orow[threadIdx.x + k * 256] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
     }
   }
@@ -211,9 +258,10 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, 
   }
 }
 
-// Fast path: D == 16 * 256 -> exactly one (x1, x2) pair-chunk per thread, kept in registers between the reduction and the
-// rotation (one global read); the learned weight slice stays in registers across the ROWS rows of a CTA; blockIdx.y
-// selects the segment (q | k of the fused projection: column offset seg * D, weight w0 / w1) so both norms are one launch.
+// Fast path: D == 16 * 256 -> exactly one (x1, x2) pair-chunk per thread and row, kept in registers between the reduction
+// and the rotation (one global read).  A CTA owns ROWS rows whose loads are all issued up front and whose sums of squares are
+// reduced together; the learned weight slice stays in registers; blockIdx.y selects the segment (q | k of the fused
+// projection: column offset seg * D, weight w0 / w1) so both norms are one launch.
 template <int ROWS>
 __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict__ x, int64_t ld, int M,
                                                                 const float* __restrict__ w0, const float* __restrict__ w1,
@@ -221,7 +269,7 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
                                                                 int rows_per_rope, float eps, bf16* __restrict__ bout0,
                                                                 bf16* __restrict__ bout1, int hpb, int64_t bstride,
                                                                 int64_t bld) {
-  __shared__ float red[33];
+  __shared__ float red[8 * ROWS];
   constexpr int D = 4096;
   const int seg = blockIdx.y;
   const float* w = seg == 0 ? w0 : w1;
@@ -238,12 +286,30 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
   griddep_launch();
   griddep_wait();   // the learned weights above are constants; x comes from the preceding GEMM
   const int row0 = blockIdx.x * ROWS;
+  uint4 u1[ROWS], u2[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const bf16* xr = x + static_cast<int64_t>(row0 + rr) * ld + static_cast<int64_t>(seg) * D;
+    u1[rr] = (row0 + rr < M) ? *reinterpret_cast<const uint4*>(xr + c1) : make_uint4(0u, 0u, 0u, 0u);
+    u2[rr] = (row0 + rr < M) ? *reinterpret_cast<const uint4*>(xr + c2) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float ss[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1[rr]);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2[rr]);
+    ss[rr] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = __bfloat1622float2(a2[t]), fb = __bfloat1622float2(b2[t]);
+      ss[rr] += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+    }
+  }
+  block_sum_multi<ROWS>(ss, red);
+#pragma unroll
   for (int rr = 0; rr < ROWS; ++rr) {
     const int row = row0 + rr;
     if (row >= M) break;
-    bf16* xr = x + static_cast<int64_t>(row) * ld + static_cast<int64_t>(seg) * D;
-    const uint4 u1 = *reinterpret_cast<const uint4*>(xr + c1);
-    const uint4 u2 = *reinterpret_cast<const uint4*>(xr + c2);
     float cs[8], sn[8];
     if (cosb) {
       const int64_t fo = static_cast<int64_t>(row % rows_per_rope) * (D >> 1) + hh * 64 + jc;
@@ -254,28 +320,27 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
         sn[t] = b.x; sn[t + 1] = b.y; sn[t + 2] = b.z; sn[t + 3] = b.w;
       }
     }
-    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1);
-    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2);
-    float x1[8], x2[8];
-    float ss = 0.f;
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1[rr]);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2[rr]);
+    const float rstd = rsqrtf(ss[rr] / D + eps);
+    float y1[8], y2[8];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const float2 fa = __bfloat1622float2(a2[t]), fb = __bfloat1622float2(b2[t]);
-      x1[2 * t] = fa.x; x1[2 * t + 1] = fa.y; x2[2 * t] = fb.x; x2[2 * t + 1] = fb.y;
-      ss += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
-    }
-    const float rstd = rsqrtf(block_sum(ss, red) / D + eps);
-    float y1[8], y2[8];
+      const float xa[2] = {fa.x, fa.y}, xb[2] = {fb.x, fb.y};
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float a = x1[t] * rstd * wa[t], b = x2[t] * rstd * wb[t];
-      if (cosb) {
-        y1[t] = a * cs[t] - b * sn[t];
-        y2[t] = b * cs[t] + a * sn[t];
-      } else {
-        y1[t] = a; y2[t] = b;
+      for (int e = 0; e < 2; ++e) {
+        const int i = 2 * t + e;
+        const float a = xa[e] * rstd * wa[i], b = xb[e] * rstd * wb[i];
+        if (cosb) {
+          y1[i] = a * cs[i] - b * sn[i];
+          y2[i] = b * cs[i] + a * sn[i];
+        } else {
+          y1[i] = a; y2[i] = b;
+        }
       }
     }
+    bf16* xr = x + static_cast<int64_t>(row) * ld + static_cast<int64_t>(seg) * D;
     bf16* o1 = xr + c1;
     bf16* o2 = xr + c2;
     if (bout) {
@@ -512,6 +577,12 @@ inline int grid_for(int64_t work, int threads) {
   return static_cast<int>(blocks);
 }
 
+// rows per CTA of the fast row kernels (LTX_ROWS_PER_CTA = 2 | 4)
+int rows_per_cta() {
+  static const int r = [] { const char* e = getenv("LTX_ROWS_PER_CTA"); const int v = e ? atoi(e) : 4; return v == 2 ? 2 : 4; }();
+  return r;
+}
+
 }  // namespace
 
 void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tbl_shift, const float* tbl_scale,
@@ -519,9 +590,13 @@ void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tb
                         int layernorm, cudaStream_t s) {
   LTX_CHECK(D % 4 == 0 && M > 0 && ada_ld % 4 == 0, 2, "rmsnorm_mod: D must be a multiple of 4");
   if (D == 4096) {
-    constexpr int ROWS = 4;
-    launch_pdl(rmsnorm_mod_fast_kernel<4, ROWS>, dim3((M + ROWS - 1) / ROWS), dim3(256), 0, s, x, out, M, tbl_shift, tbl_scale,
-               ada_shift, ada_scale, ada_ld, rows_per_mod > 0 ? rows_per_mod : 1, eps, layernorm);
+    const int rpm = rows_per_mod > 0 ? rows_per_mod : 1;
+    if (rows_per_cta() == 2)
+      launch_pdl(PDL_ROWS, rmsnorm_mod_fast_kernel<4, 2>, dim3((M + 1) / 2), dim3(256), 0, s, x, out, M, tbl_shift, tbl_scale, ada_shift,
+                 ada_scale, ada_ld, rpm, eps, layernorm);
+    else
+      launch_pdl(PDL_ROWS, rmsnorm_mod_fast_kernel<4, 4>, dim3((M + 3) / 4), dim3(256), 0, s, x, out, M, tbl_shift, tbl_scale, ada_shift,
+                 ada_scale, ada_ld, rpm, eps, layernorm);
     return;
   }
   rmsnorm_mod_kernel<<<M, 256, 0, s>>>(x, out, D, tbl_shift, tbl_scale, ada_shift, ada_scale, ada_ld,
@@ -540,10 +615,12 @@ void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const
   const int64_t bs = blocked ? blocked->block_stride : 0, bld = blocked ? blocked->ld : 0;
   LTX_CHECK(!blocked || (hpb > 0 && (D / 128) % hpb == 0 && b0 && (!w_second || b1)), 2, "qknorm_rope: bad blocked output");
   if (D == 4096) {
-    constexpr int ROWS = 4;
-    dim3 grid((M + ROWS - 1) / ROWS, w_second ? 2 : 1);
-    launch_pdl(qknorm_rope_fast_kernel<ROWS>, grid, dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs,
-               bld);
+    if (rows_per_cta() == 2)
+      launch_pdl(PDL_ROWS, qknorm_rope_fast_kernel<2>, dim3((M + 1) / 2, w_second ? 2 : 1), dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb,
+                 rpr, eps, b0, b1, hpb, bs, bld);
+    else
+      launch_pdl(PDL_ROWS, qknorm_rope_fast_kernel<4>, dim3((M + 3) / 4, w_second ? 2 : 1), dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb,
+                 rpr, eps, b0, b1, hpb, bs, bld);
     return;
   }
   qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps, b0, hpb, bs, bld);

@@ -169,7 +169,7 @@ void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, epi);
+  launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, epi);
 }
 
 // Tile width that minimises (waves x width): time ~ ceil(tiles / #SM) * (BN + c0), c0 = fixed per-tile cost in columns.

@@ -167,7 +167,7 @@ void launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K
   static const int dbg = [] { const char* e = getenv("LTX_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   GemmEpi ep2 = epi;
   ep2.debug = dbg;
-  launch_pdl(kern, dim3(grid), dim3(G2_THREADS), G2_SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, ep2);
+  launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(G2_THREADS), G2_SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, ep2);
 }
 
 }  // namespace

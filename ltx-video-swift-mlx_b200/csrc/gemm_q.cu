@@ -299,7 +299,7 @@ void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int 
   }
   const int tiles = ((M + QBM - 1) / QBM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  launch_pdl(kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, epi);
+  launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, epi);
   LTX_CUDA(cudaGetLastError());
 }
 

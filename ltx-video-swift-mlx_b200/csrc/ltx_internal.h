@@ -32,9 +32,10 @@ struct LtxError : public std::runtime_error {
 
 // ---------------------------------------------------------------- kernel launch with programmatic stream serialization
 // The kernel must call griddep_wait() (ptx.cuh) before touching dependent global memory.  LTX_PDL=0 launches normally.
-bool pdl_enabled();
+bool pdl_enabled(int cls = 0);   // cls: 0 GEMM, 1 row kernels, 2 attention, 3 VAE (LTX_PDL_MASK bit per class, debugging)
+enum { PDL_GEMM = 0, PDL_ROWS = 1, PDL_ATTN = 2, PDL_VAE = 3 };
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline void launch_pdl(int cls, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -44,7 +45,7 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(cls) ? 1 : 0;
   LTX_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }
 

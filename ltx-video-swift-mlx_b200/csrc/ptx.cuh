@@ -29,6 +29,9 @@ __device__ __forceinline__ bool elect_one() {
 // A kernel launched with launch_pdl() may become resident while its predecessor in the stream is still running (as SMs
 // free up).  It must call griddep_wait() before its first access to global memory the predecessor may write (and before
 // its own first global write); griddep_launch() lets ITS successor be scheduled the same way.
+// CAUTION: data produced by earlier kernels of the stream must not be read through `const T* __restrict__` pointers in
+// such a kernel: nvcc marks those loads invariant (LDG.CONSTANT) and hoists them ABOVE griddepcontrol.wait, memory clobber
+// or not (seen in SASS; it made rmsnorm read x before the producing GEMM had finished).  Constants (weights) are fine.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

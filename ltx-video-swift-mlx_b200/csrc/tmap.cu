@@ -7,9 +7,10 @@
 
 namespace ltx {
 
-bool pdl_enabled() {
+bool pdl_enabled(int cls) {
   static const bool on = [] { const char* e = getenv("LTX_PDL"); return e ? atoi(e) != 0 : true; }();
-  return on;
+  static const int mask = [] { const char* e = getenv("LTX_PDL_MASK"); return e ? atoi(e) : 0xFF; }();
+  return on && ((mask >> cls) & 1);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
