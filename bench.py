@@ -403,14 +403,14 @@ def run_ours(args, rank, world, local_rank):
     traffic, traffic_note = None, None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01_gemm_ffn_in_ncu_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01b_gemm_pair_ffn_in_ncu_raw.csv"))))
         hdr, units, last = rows[0], rows[1], rows[-1]
 
         def _bytes(k):
             v, u = float(last[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
-        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01_gemm_ffn_in_ncu_raw.csv"
+        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01b_gemm_pair_ffn_in_ncu_raw.csv"
     except Exception:
         pass
     gemm = prof["gemm"]
@@ -428,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
         e2e=dict(value=world * 1e3 / e2e_ms, unit="steps/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  path="ltx_dit_forward + ltx_guided_euler_step with pinned host buffers (text cached by context_key)"),
         gpu_launches=int(launches),
-        roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05 (all GEMM launches of one step)", achieved=achieved,
+        roofline=dict(bound="tensor", kernel="gemm_bf16_2cta / gemm_bf16_tcgen05 (all GEMM launches of one step)", achieved=achieved,
                       peak=pk["tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["tflops_sustained"], traffic=traffic,
                       traffic_note=traffic_note,
                       peak_source=pk["source"] + ", sustained bf16", launches=gemm["launches"], ms=gemm["ms"]),

@@ -72,6 +72,12 @@ int ltx_sync(ltx_ctx* ctx);
  * (VAE keys carry the prefix "vae.").  Matrices / conv kernels are stored as bf16 (the loader's fp32->bf16 cast,
  * :1005-1012), vectors and tables as fp32. */
 int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dtype dtype, const int64_t* shape, int ndim);
+/* Precision of the DiT path.  16 (default): the reference's "bf16" mode -- bf16 weights and tensor-core operands, fp32
+ * accumulation / residual stream / norms / softmax; velocity within rel-L2 1e-2 of the fp32 graph.  32: fp32 mode -- DiT
+ * matrices stay fp32, activations fp32, every Linear runs as a split-bf16 (3-term) tensor-core product that is exact to
+ * fp32 rounding, attention in fp32; velocity within rel-L2 1e-4 (the mode BASELINE config 0, "random-init fp32", is checked
+ * in).  Must be called before the DiT weights are loaded; single GPU, no quantisation; the VAE is unaffected. */
+int ltx_set_precision(ltx_ctx* ctx, int bits);
 /* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
  * which: 1 = DiT, 2 = VAE decoder, 3 = both. */
 int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);

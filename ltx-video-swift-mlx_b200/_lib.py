@@ -49,6 +49,7 @@ SIGNATURES = {
     "ltx_last_error": (C.c_char_p, [_P]),
     "ltx_sync": (_I, [_P]),
     "ltx_load_tensor": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_I64), _I]),
+    "ltx_set_precision": (_I, [_P, _I]),
     "ltx_init_random_weights": (_I, [_P, _I, _U64]),
     "ltx_finalize_weights": (_I, [_P, _I, _I]),
     "ltx_dit_forward": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(LtxDitFlags), _P]),

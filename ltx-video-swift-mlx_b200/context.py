@@ -170,6 +170,10 @@ class LtxContext:
         for k, v in weights.items():
             self.load_tensor(prefix + k, v)
 
+    def set_precision(self, bits: int):
+        """16 = bf16 mode (default), 32 = fp32 mode (fp32 DiT weights, split-bf16 tensor-core GEMMs); before loading weights."""
+        self._check(self.lib.ltx_set_precision(self.handle, int(bits)))
+
     def init_random_weights(self, which: int = 3, seed: int = 0):
         self._check(self.lib.ltx_init_random_weights(self.handle, which, seed))
 

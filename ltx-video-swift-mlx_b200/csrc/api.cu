@@ -103,7 +103,9 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
                     &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
-                    &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x, &c->s_ts};
+                    &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
+                    &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
+                    &c->f_bias};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
   cudaStreamDestroy(c->stream);
@@ -195,12 +197,23 @@ int ltx_init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
   return guarded(c, [&] { init_random_weights(c, which, seed); });
 }
 
+int ltx_set_precision(ltx_ctx* c, int bits) {
+  return guarded(c, [&] {
+    LTX_CHECK(bits == 16 || bits == 32, LTX_ERR_UNSUPPORTED, "precision must be 16 (bf16 mode) or 32 (fp32 mode)");
+    LTX_CHECK(!c->dit_ready && c->tensors.count("patchify_proj.weight") == 0, LTX_ERR_INVALID_ARGUMENT,
+              "ltx_set_precision must be called before the DiT weights are loaded");
+    c->precision = bits;
+  });
+}
+
 int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
   return guarded(c, [&] {
     LTX_CHECK(quant_bits == 16 || quant_bits == 8 || quant_bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");
     LTX_CHECK(quant_bits == 16 || group_size == 64, LTX_ERR_UNSUPPORTED, "only group_size 64 is implemented");
+    LTX_CHECK(quant_bits == 16 || c->precision == 16, LTX_ERR_UNSUPPORTED, "fp32 mode cannot be combined with quantised weights");
     if (c->tensors.count("patchify_proj.weight")) {
-      dit_finalize(c);
+      if (c->precision == 32) dit_finalize_f32(c);
+      else dit_finalize(c);
       if (quant_bits != 16) dit_quantize(c, quant_bits);
     }
     if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);

@@ -148,6 +148,10 @@ struct ltx_ctx {
   ltx::DevBuf snap_x;                           // residual-stream snapshot for the shared STG prefix
   int snap_rows = 0;
 
+  // ---- fp32 mode (dit_f32.cu): fp32 weights + activations, split-bf16 GEMM operands
+  int precision = 16;   // 16: bf16 weights (default), 32: DiT matrices stay fp32 and the forward runs in fp32 mode
+  ltx::DevBuf f_asplit, f_wsplit, f_h, f_q, f_k, f_v, f_att, f_ffh, f_ctx, f_c1, f_c2, f_tk, f_tv, f_lat, f_bias;
+
   // ---- resident denoise session
   ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma, s_ts;
   int s_F = 0, s_H = 0, s_W = 0, s_S = 0;
@@ -194,6 +198,12 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
                      int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev, int snapshot_block = -1,
                      int resume_block = -1);
 void dit_clear_caches(ltx_ctx* c);
+void dit_build_rope(ltx_ctx* c, int F, int H, int W);
+// dit_f32.cu
+void dit_finalize_f32(ltx_ctx* c);
+void dit_forward_f32(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
+                     const float* timesteps_dev, int ts_per_token, const int32_t* mask_dev, int B, int N, int S, int F, int H,
+                     int W, const ltx_dit_flags* flags, float* out_velocity_dev);
 // vae.cu
 void vae_finalize(ltx_ctx* c);
 void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,

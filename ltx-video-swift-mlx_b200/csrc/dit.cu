@@ -204,6 +204,8 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
 
 }  // namespace
 
+void dit_build_rope(ltx_ctx* c, int F, int H, int W) { build_rope(c, F, H, W); }
+
 void dit_clear_caches(ltx_ctx* c) {
   c->rope_f = c->rope_h = c->rope_w = 0;
   for (auto& t : c->text) { t.key = 0; t.B = t.S = 0; }
@@ -344,6 +346,11 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   LTX_CHECK(B >= 1 && B <= 4 && N >= 1 && S >= 1, LTX_ERR_INVALID_ARGUMENT, "bad B/N/S");
   LTX_CHECK(static_cast<int64_t>(F) * H * W == N, LTX_ERR_INVALID_ARGUMENT, "N must equal F*H*W");
   LTX_CHECK(latent && context && timesteps_dev && out_velocity_dev, LTX_ERR_INVALID_ARGUMENT, "null tensor");
+  if (c->precision == 32) {   // fp32 mode: no prefix sharing (a resumed pass is recomputed in full, same values)
+    dit_forward_f32(c, latent, latent_dtype, context, context_dtype, timesteps_dev, ts_per_token, mask_dev, B, N, S, F, H, W, flags,
+                    out_velocity_dev);
+    return;
+  }
   const ltx_config& g = c->cfg;
   const int D = g.num_heads * g.head_dim, FFD = g.ffn_mult * D, Hh = g.num_heads, L = g.num_layers;
   const int Cin = g.in_channels, Cout = g.out_channels;

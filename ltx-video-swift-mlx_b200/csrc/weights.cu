@@ -49,8 +49,11 @@ bool ends_with(const std::string& s, const std::string& suf) {
   return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
-int storage_dtype(const std::string& key, int ndim) {
-  return (ends_with(key, ".weight") && ndim >= 2) ? LTX_BF16 : LTX_F32;
+int storage_dtype(const ltx_ctx* c, const std::string& key, int ndim) {
+  if (!(ends_with(key, ".weight") && ndim >= 2)) return LTX_F32;
+  // fp32 mode keeps the DiT matrices in fp32; VAE conv kernels are always bf16
+  if (c->precision == 32 && key.compare(0, 4, "vae.") != 0) return LTX_F32;
+  return LTX_BF16;
 }
 
 DevTensor& alloc_tensor(ltx_ctx* c, const std::string& key, const std::vector<int64_t>& shape) {
@@ -61,7 +64,7 @@ DevTensor& alloc_tensor(ltx_ctx* c, const std::string& key, const std::vector<in
   }
   DevTensor t;
   t.shape = shape;
-  t.dtype = storage_dtype(key, static_cast<int>(shape.size()));
+  t.dtype = storage_dtype(c, key, static_cast<int>(shape.size()));
   size_t bytes = static_cast<size_t>(t.numel()) * dtype_size(t.dtype);
   LTX_CUDA(cudaMalloc(&t.ptr, bytes < 16 ? 16 : bytes));
   return c->tensors[key] = t;

@@ -152,3 +152,57 @@ def test_per_token_timesteps_and_i2v_loop():
     assert np.allclose(out_l[:, 0], init[0, :, 0].numpy(), atol=1e-6)
     assert rel_l2(out_l, ref_l[0]) <= 2e-2
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32 mode (ltx_set_precision(ctx, 32)): fp32 weights and activations, split-bf16 tensor-core GEMMs, fp32 attention.
+# north_star tolerance: per-step velocity rel-L2 <= 1e-4 against the fp32 graph; the oracle runs in fp64 here so that
+# its own rounding does not enter the comparison.
+# ---------------------------------------------------------------------------------------------------------------------
+TOL_F32 = 1e-4
+
+
+@pytest.mark.parametrize("layers,heads,fhw,S,B,mask_prefix", [
+    (2, 2, (2, 4, 6), 40, 1, 7), (3, 4, (2, 5, 7), 72, 2, 3),
+    (1, 32, (2, 16, 16), 128, 1, 0),   # BASELINE config 0: one LTX-2 block, random-init fp32, latent 512x512x9 + 128 text tokens
+])
+def test_dit_forward_fp32_mode(layers, heads, fhw, S, B, mask_prefix):
+    ocfg, pcfg = small_dit_config(layers, heads)
+    w = O.make_dit_weights(ocfg, seed=layers * 7 + heads, bf16=False)
+    ctx = product().LtxContext(pcfg, 0)
+    ctx.set_precision(32)
+    ctx.load_weights(w)
+    ctx.finalize_weights()
+    g = torch.Generator().manual_seed(99)
+    N = fhw[0] * fhw[1] * fhw[2]
+    lat = torch.randn(B, N, ocfg.in_channels, generator=g)
+    cx = torch.randn(B, S, ocfg.caption_channels, generator=g)
+    cx = cx / cx.pow(2).mean(-1, keepdim=True).sqrt()
+    mask = torch.ones(B, S, dtype=torch.int32)
+    if mask_prefix:
+        mask[:, :mask_prefix] = 0
+    sig = torch.tensor([0.7, 0.3][:B])
+    ref = O.dit_forward(w, ocfg, lat.double(), cx.double(), sig, mask if mask_prefix else None, fhw,
+                        dtype=torch.float64, mlx_bf16=False)
+    out = ctx.dit_forward(lat, cx, sig.numpy(), mask if mask_prefix else None, fhw)
+    assert np.isfinite(out).all()
+    err = rel_l2(out, ref)
+    assert err <= TOL_F32, err
+    # and the bf16-mode tolerance is not what makes this pass: the same weights rounded to bf16 differ by >> 1e-4
+    ctx.close()
+
+
+def test_fp32_mode_rejects_late_switch_and_quantisation():
+    ocfg, pcfg = small_dit_config(1, 1)
+    w = O.make_dit_weights(ocfg, seed=3, bf16=False)
+    ctx = product().LtxContext(pcfg, 0)
+    ctx.load_weights(w)
+    with pytest.raises(product().LtxError):
+        ctx.set_precision(32)             # too late: the DiT matrices were already stored as bf16
+    ctx.close()
+    ctx = product().LtxContext(pcfg, 0)
+    ctx.set_precision(32)
+    ctx.load_weights(w)
+    with pytest.raises(product().LtxError):
+        ctx.finalize_weights(quant_bits=8)
+    ctx.close()
