@@ -72,6 +72,16 @@ int ltx_sync(ltx_ctx* ctx);
  * (VAE keys carry the prefix "vae.").  Matrices / conv kernels are stored as bf16 (the loader's fp32->bf16 cast,
  * :1005-1012), vectors and tables as fp32. */
 int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dtype dtype, const int64_t* shape, int ndim);
+/* Reads a .safetensors checkpoint and loads the tensors of the hot path under their post-mapping names -- the counterpart of
+ * LTXWeightLoader.loadTransformerWeights / loadVAEWeights (Utils/ModelDownloader.swift:605-659) with the key mapping of
+ * mapTransformerKey (:756-803) and mapVAEWeights (:808-899).  which: 1 = video transformer (unified checkpoint: only the
+ * "model.diffusion_model." tensors; audio / cross-modal / connector tensors are skipped as with includeAudio:false),
+ * 2 = VAE decoder (stand-alone VAE file or the "vae." tensors of a unified checkpoint; encoder tensors are skipped).
+ * F32 / BF16 / F16 tensors are accepted.  n_loaded (nullable) receives the number of tensors taken.  Follow with
+ * ltx_finalize_weights.  ltx_map_weight_key exposes the name mapping alone (no context, no GPU): it writes the mapped name,
+ * or an empty string for a tensor the loader skips, into out[cap]. */
+int ltx_load_safetensors(ltx_ctx* ctx, const char* path, int which, int* n_loaded);
+int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap);
 /* Precision of the DiT path.  16 (default): the reference's "bf16" mode -- bf16 weights and tensor-core operands, fp32
  * accumulation / residual stream / norms / softmax; velocity within rel-L2 1e-2 of the fp32 graph.  32: fp32 mode -- DiT
  * matrices stay fp32, activations fp32, every Linear runs as a split-bf16 (3-term) tensor-core product that is exact to

@@ -88,6 +88,16 @@ def make_flags(stg_blocks: Sequence[int] = (), skip_self_attn: bool = False, ski
     return f
 
 
+def map_weight_key(which: int, file_key: str) -> Optional[str]:
+    """mapTransformerKey (which=1) / mapVAEWeights (which=2) for one checkpoint key; None = skipped by the loader."""
+    buf = C.create_string_buffer(512)
+    rc = _lib.load().ltx_map_weight_key(int(which), file_key.encode(), buf, 512)
+    if rc != 0:
+        raise LtxError(rc, "ltx_map_weight_key failed")
+    s = buf.value.decode()
+    return s or None
+
+
 class LtxContext:
     def __init__(self, config: Optional[LTXTransformerConfig] = None, device: int = 0):
         self.lib = _lib.load()
@@ -169,6 +179,13 @@ class LtxContext:
     def load_weights(self, weights: Dict[str, object], prefix: str = ""):
         for k, v in weights.items():
             self.load_tensor(prefix + k, v)
+
+    def load_safetensors(self, path: str, which: int) -> int:
+        """LTXWeightLoader.loadTransformerWeights (which=1) / loadVAEWeights (which=2): reads the checkpoint, maps the keys
+        (mapTransformerKey / mapVAEWeights) and uploads the tensors.  Returns the number of tensors taken."""
+        n = C.c_int(0)
+        self._check(self.lib.ltx_load_safetensors(self.handle, str(path).encode(), int(which), C.byref(n)))
+        return n.value
 
     def set_precision(self, bits: int):
         """16 = bf16 mode (default), 32 = fp32 mode (fp32 DiT weights, split-bf16 tensor-core GEMMs); before loading weights."""

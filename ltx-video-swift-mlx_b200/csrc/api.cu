@@ -193,6 +193,26 @@ int ltx_load_tensor(ltx_ctx* c, const char* key, const void* host_data, ltx_dtyp
   });
 }
 
+int ltx_load_safetensors(ltx_ctx* c, const char* path, int which, int* n_loaded) {
+  return guarded(c, [&] {
+    const int n = load_safetensors(c, path, which);
+    if (n_loaded) *n_loaded = n;
+    LTX_CHECK(n > 0, LTX_ERR_WEIGHTS, std::string("no ") + (which == 1 ? "transformer" : "VAE decoder") + " tensors found in '" + (path ? path : "") + "'");
+  });
+}
+
+int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap) {
+  if (!file_key || !out || cap == 0 || (which != 1 && which != 2)) return LTX_ERR_INVALID_ARGUMENT;
+  try {
+    const std::string m = which == 1 ? map_transformer_key(file_key) : map_vae_key(file_key);
+    if (m.size() + 1 > cap) return LTX_ERR_INVALID_ARGUMENT;
+    memcpy(out, m.c_str(), m.size() + 1);
+    return LTX_OK;
+  } catch (...) {
+    return LTX_ERR_WEIGHTS;
+  }
+}
+
 int ltx_init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
   return guarded(c, [&] { init_random_weights(c, which, seed); });
 }

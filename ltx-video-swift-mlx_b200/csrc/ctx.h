@@ -217,6 +217,10 @@ void dist_allgather_sp(ltx_ctx* c, const void* send, void* recv, size_t bytes_pe
 void dist_all_to_all_sp(ltx_ctx* c, const void* const* send, void* const* recv, int n_tensors, size_t bytes_per_peer);
 void dist_halo_exchange(ltx_ctx* c, const void* send_prev, void* recv_prev, const void* send_next, void* recv_next,
                         size_t bytes, int n_active);
+// safetensors.cu
+std::string map_transformer_key(const std::string& file_key);
+std::string map_vae_key(const std::string& file_key);
+int load_safetensors(ltx_ctx* c, const char* path, int which);
 // weights.cu
 const DevTensor& get_tensor(ltx_ctx* c, const std::string& key);
 void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int dtype, const int64_t* shape, int ndim);
