@@ -188,6 +188,12 @@ int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp
 int ltx_dist_get_unique_id(void* id_out_128);
 int ltx_dist_init(ltx_ctx* ctx, const void* unique_id_128, int rank, int world_size, int sp_size, int pass_groups);
 int ltx_dist_info(const ltx_ctx* ctx, int* rank, int* world_size, int* sp_size, int* pass_groups);
+/* 1 when the Ulysses exchange of this context runs over peer memory: every sp rank's receive buffer is mapped into its
+ * peers (CUDA IPC over NVLink / NVSwitch), the V-projection GEMM epilogue, the q/k norm+RoPE kernel and the attention
+ * epilogue store their head / token blocks straight into the destination rank's buffer, and a release/acquire flag barrier
+ * replaces the NCCL all-to-all.  Established lazily by the first sequence-parallel forward; 0 = NCCL all-to-all (mapping
+ * unavailable or LTX_P2P=0). */
+int ltx_dist_p2p_active(const ltx_ctx* ctx);
 /* Destroys the communicators (collective); the context can be re-initialised with a different layout afterwards. */
 int ltx_dist_shutdown(ltx_ctx* ctx);
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ltx_dist_get_unique_id": (_I, [_P]),
     "ltx_dist_init": (_I, [_P, _P, _I, _I, _I, _I]),
     "ltx_dist_shutdown": (_I, [_P]),
+    "ltx_dist_p2p_active": (_I, [_P]),
     "ltx_dist_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "ltx_launch_count": (_U64, [_P]),
     "ltx_get_stream": (_I, [_P, C.POINTER(_P)]),

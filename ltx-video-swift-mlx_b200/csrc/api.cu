@@ -155,6 +155,8 @@ int ltx_dist_info(const ltx_ctx* c, int* rank, int* world_size, int* sp_size, in
   return LTX_OK;
 }
 
+int ltx_dist_p2p_active(const ltx_ctx* c) { return (c && c->dist.p2p) ? 1 : 0; }
+
 int ltx_get_stream(ltx_ctx* c, void** stream) {
   return guarded(c, [&] {
     LTX_CHECK(stream != nullptr, LTX_ERR_INVALID_ARGUMENT, "null out pointer");

@@ -38,6 +38,8 @@ struct AttnParams {
   const float* key_bias;   // nullable, [B, Nk]
   bf16* O;
   int64_t ldo;
+  int o_rows_per_block;   // > 0: output row r goes to o_blocks.p[r / o_rows_per_block] (Ulysses over peer memory)
+  PeerTable o_blocks;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -262,23 +264,39 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_wait(&o_final[wg], 0);
     tc_fence_after();
     const float inv = 1.0f / l_run;
-    const int qi = (q_pair * 2 + wg) * TQ + r_in;
-    bf16* orow = p.O + (static_cast<int64_t>(b) * p.Nq + qi) * p.ldo + h * HD;
+    // O / l -> bf16, staged through this tile's P buffer (free now: o_final means every MMA has retired) so that the
+    // global stores are whole 256-byte rows (16 lanes x 16 B) -- full lines, also over NVLink when the row lives in a
+    // peer's buffer -- instead of 32 rows x 16 B per instruction.  Each warp reads back only the 32 rows it wrote.
+    // 16-byte chunk c of row r sits at chunk c ^ (r & 7): conflict-free for the row-per-thread writes and the reads.
+    uint8_t* otile = sP + wg * TILE_BYTES;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t r[32];
       tmem_ld32(o_addr + c * 32, r);
       tmem_ld_wait();
-      if (qi < p.Nq) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 pk = make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-                                pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-                                pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-                                pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
-          *reinterpret_cast<uint4*>(orow + c * 32 + i) = pk;
-        }
+      for (int i = 0; i < 32; i += 8) {
+        uint4 pk = make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                              pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                              pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                              pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+        const int chunk = c * 4 + (i >> 3);
+        *reinterpret_cast<uint4*>(otile + r_in * 256 + ((chunk ^ (r_in & 7)) << 4)) = pk;
       }
+    }
+    __syncwarp();
+    const int sub = lane >> 4, ch = lane & 15;   // 2 rows per instruction, 16 chunks of 16 B per row
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int rr = q * 32 + 2 * i + sub;        // row inside the tile (this warp's quarter)
+      const int qi = (q_pair * 2 + wg) * TQ + rr;
+      if (qi >= p.Nq) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(otile + rr * 256 + ((ch ^ (rr & 7)) << 4));
+      bf16* orow = p.O + (static_cast<int64_t>(b) * p.Nq + qi) * p.ldo + h * HD;
+      if (p.o_rows_per_block > 0)
+        orow = reinterpret_cast<bf16*>(p.o_blocks.p[qi / p.o_rows_per_block]) +
+               static_cast<int64_t>(qi % p.o_rows_per_block) * p.ldo + h * HD;
+      *reinterpret_cast<uint4*>(orow + ch * 8) = v;
     }
   }
   tc_fence_before();
@@ -294,7 +312,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                       const float* key_bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const PeerTable* o_blocks, int rows_per_block) {
   LTX_CHECK(D == H * HD, 2, "attention: head_dim must be 128");
   LTX_CHECK(Nq > 0 && Nk > 0 && B > 0, 2, "attention: empty problem");
   LTX_CHECK(ldvb % 8 == 0 && ldvb >= Nk, 2, "attention: V^T per-batch pitch must be a multiple of 8 and >= Nk");
@@ -313,6 +331,13 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
   p.key_bias = key_bias;
   p.O = O;
   p.ldo = ldo;
+  p.o_rows_per_block = 0;
+  p.o_blocks = PeerTable{};
+  if (o_blocks) {
+    LTX_CHECK(B == 1 && rows_per_block > 0, 2, "attention: peer-memory output needs B == 1");
+    p.o_rows_per_block = rows_per_block;
+    p.o_blocks = *o_blocks;
+  }
   dim3 grid((Nq + 2 * TQ - 1) / (2 * TQ), H, B);
   launch_pdl(PDL_ATTN, attention_fwd_tcgen05, grid, dim3(ATT_THREADS), ATT_SMEM, stream, tmQ, tmK, tmV, p);
   LTX_CUDA(cudaGetLastError());

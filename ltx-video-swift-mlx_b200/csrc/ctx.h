@@ -95,6 +95,13 @@ struct VaeWeights {
 
 namespace ltx {
 struct DistState {
+  // ---- Ulysses over peer memory (dist.cu: dist_p2p_*): every sp rank's receive buffer is mapped into its peers through
+  // CUDA IPC, producers store straight into it over NVLink, a flag barrier replaces the NCCL all-to-all
+  bool p2p_tried = false, p2p = false;
+  void* p2p_local = nullptr;          // this rank's exported allocation: [recv bytes | flags]
+  size_t p2p_bytes = 0;               // recv capacity (bytes) of every rank's allocation
+  void* p2p_peer[8] = {};             // base of rank r's allocation in this process (own pointer for r == sp_rank)
+  uint32_t p2p_epoch[2] = {0, 0};     // barrier generations: 0 = q/k/v landed, 1 = attention output landed
   void* comm_world = nullptr;  // ncclComm_t
   void* comm_sp = nullptr;     // sequence-parallel sub-communicator (== world when pass_groups == 1)
   bool sp_is_world = true;
@@ -215,6 +222,10 @@ void dist_destroy(ltx_ctx* c);
 void dist_broadcast(ltx_ctx* c, void* buf, size_t bytes, int root_world_rank);
 void dist_allgather_sp(ltx_ctx* c, const void* send, void* recv, size_t bytes_per_rank);
 void dist_all_to_all_sp(ltx_ctx* c, const void* const* send, void* const* recv, int n_tensors, size_t bytes_per_peer);
+// peer-memory Ulysses: (re)registers a receive buffer of >= bytes on every sp rank (collective); false = unavailable
+bool dist_p2p_ensure(ltx_ctx* c, size_t bytes);
+// all sp ranks: 'my stores of this phase have been issued' + wait for everyone's (kind 0: q/k/v, 1: attention output)
+void dist_p2p_barrier(ltx_ctx* c, int kind);
 void dist_halo_exchange(ltx_ctx* c, const void* send_prev, void* recv_prev, const void* send_next, void* recv_next,
                         size_t bytes, int n_active);
 // safetensors.cu

@@ -13,6 +13,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "ctx.h"
 
 namespace ltx {
@@ -104,8 +107,134 @@ void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ peer-memory Ulysses
+namespace {
+
+constexpr size_t P2P_FLAG_BYTES = 256;   // [2 kinds][8 source ranks] uint32 at the end of the exported allocation
+
+__global__ void p2p_barrier_kernel(PeerTable peers, size_t flag_off, int P, int me, int kind, uint32_t epoch) {
+  const int t = threadIdx.x;
+  if (t >= P) return;
+  // every store of the preceding kernels of this stream has completed (kernel boundary); publish that to rank t ...
+  __threadfence_system();
+  uint32_t* remote = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers.p[t]) + flag_off) + kind * LTX_MAX_PEERS + me;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+  // ... and wait until rank t has published the same for its stores into our buffer
+  const uint32_t* local = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(peers.p[me]) + flag_off) + kind * LTX_MAX_PEERS + t;
+  uint32_t v = 0;
+  unsigned long long spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
+    if (++spins > (1ull << 25)) {   // ~ tens of seconds: a peer died or the protocol is broken -> abort instead of hanging
+      printf("ltxcuda: peer barrier timeout (rank %d waiting for rank %d, kind %d, epoch %u, seen %u)\n", me, t, kind, epoch, v);
+      __trap();
+    }
+  } while (static_cast<int32_t>(v - epoch) < 0);
+}
+
+void p2p_release(ltx_ctx* c) {
+  DistState& d = c->dist;
+  for (int r = 0; r < d.sp; ++r)
+    if (d.p2p_peer[r] && r != d.sp_rank) cudaIpcCloseMemHandle(d.p2p_peer[r]);
+  for (auto& q : d.p2p_peer) q = nullptr;
+  if (d.p2p_local) cudaFree(d.p2p_local);
+  d.p2p_local = nullptr;
+  d.p2p_bytes = 0;
+  d.p2p = false;
+}
+
+}  // namespace
+
+bool dist_p2p_ensure(ltx_ctx* c, size_t bytes) {
+  DistState& d = c->dist;
+  if (d.sp <= 1 || d.sp > LTX_MAX_PEERS) return false;
+  static const bool enabled = [] { const char* e = getenv("LTX_P2P"); return e ? atoi(e) != 0 : true; }();
+  if (!enabled) return false;
+  if (d.p2p && d.p2p_bytes >= bytes) return true;
+  if (d.p2p_tried && !d.p2p) return false;   // mapping failed before (all ranks agree, see below): stay on NCCL
+  d.p2p_tried = true;
+  // (re)registration is collective: every rank of the sp group runs the same forward and gets here with the same size
+  LTX_CUDA(cudaStreamSynchronize(c->stream));
+  const int P = d.sp, me = d.sp_rank;
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+  static_assert(sizeof(Msg) == 128, "handle message is 128 bytes");
+  Msg* dev = nullptr;
+  LTX_CUDA(cudaMalloc(&dev, sizeof(Msg) * (P + 1)));
+  auto exchange = [&](Msg mine, std::vector<Msg>& all) {
+    LTX_CUDA(cudaMemcpyAsync(dev + P, &mine, sizeof(Msg), cudaMemcpyHostToDevice, c->stream));
+    LTX_NCCL(nccl().AllGather(dev + P, dev, sizeof(Msg), ncclChar, spc(c), c->stream));
+    all.resize(P);
+    LTX_CUDA(cudaMemcpyAsync(all.data(), dev, sizeof(Msg) * P, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  };
+  std::vector<Msg> all;
+  if (d.p2p_local) {   // growing: nobody may still be storing into the old buffers
+    Msg m = {};
+    exchange(m, all);
+    p2p_release(c);
+  }
+  Msg mine = {};
+  const size_t cap = (bytes + 1023) / 1024 * 1024;
+  void* local = nullptr;
+  mine.ok = cudaMalloc(&local, cap + P2P_FLAG_BYTES) == cudaSuccess && cudaMemset(local, 0, cap + P2P_FLAG_BYTES) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.h, local) == cudaSuccess;
+  cudaGetLastError();
+  exchange(mine, all);
+  bool ok = true;
+  for (int r = 0; r < P; ++r) ok = ok && all[r].ok;
+  void* peer[LTX_MAX_PEERS] = {};
+  if (ok) {
+    for (int r = 0; r < P && ok; ++r) {
+      if (r == me) { peer[r] = local; continue; }
+      ok = cudaIpcOpenMemHandle(&peer[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (!ok) cudaGetLastError();
+    }
+  }
+  // second round: everyone must have mapped everyone, otherwise all ranks fall back to NCCL together
+  Msg res = {};
+  res.ok = ok ? 1 : 0;
+  exchange(res, all);
+  bool all_ok = true;
+  for (int r = 0; r < P; ++r) all_ok = all_ok && all[r].ok;
+  cudaFree(dev);
+  if (!all_ok) {
+    for (int r = 0; r < P; ++r)
+      if (peer[r] && r != me) cudaIpcCloseMemHandle(peer[r]);
+    if (local) cudaFree(local);
+    d.p2p = false;
+    return false;
+  }
+  d.p2p_local = local;
+  d.p2p_bytes = cap;
+  for (int r = 0; r < P; ++r) d.p2p_peer[r] = peer[r];
+  d.p2p_epoch[0] = d.p2p_epoch[1] = 0;
+  d.p2p = true;
+  return true;
+}
+
+void dist_p2p_barrier(ltx_ctx* c, int kind) {
+  DistState& d = c->dist;
+  LTX_CHECK(d.p2p && (kind == 0 || kind == 1), LTX_ERR_INVALID_ARGUMENT, "peer barrier without peer memory");
+  PeerTable t = {};
+  for (int r = 0; r < d.sp; ++r) t.p[r] = d.p2p_peer[r];
+  const uint32_t epoch = ++d.p2p_epoch[kind];
+  p2p_barrier_kernel<<<1, 32, 0, c->stream>>>(t, d.p2p_bytes, d.sp, d.sp_rank, kind, epoch);
+  LTX_CUDA(cudaGetLastError());
+}
+
 void dist_destroy(ltx_ctx* c) {
   if (!c->dist.comm_world) return;
+  if (c->dist.p2p_local) {
+    // peers may still be storing into our buffer: drain the stream, meet at a collective, then unmap and free
+    cudaStreamSynchronize(c->stream);
+    char* one = nullptr;
+    if (cudaMalloc(&one, 2 * LTX_MAX_PEERS) == cudaSuccess) {
+      nccl().AllGather(one + LTX_MAX_PEERS, one, 1, ncclChar, spc(c), c->stream);
+      cudaStreamSynchronize(c->stream);
+      cudaFree(one);
+    }
+    p2p_release(c);
+  }
   if (c->dist.comm_sp && !c->dist.sp_is_world) nccl().CommDestroy(spc(c));
   nccl().CommDestroy(world(c));
   c->dist = DistState();

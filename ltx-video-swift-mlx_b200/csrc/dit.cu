@@ -44,10 +44,11 @@ void v_transposed(ltx_ctx* c, const bf16* wv, const float* bv, const bf16* hrows
   launch_transpose_bf16(tmp, D, rows, D, out, ld_out, c->stream);
 }
 void attention(ltx_ctx* c, const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
-               const float* bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale) {
+               const float* bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
+               const PeerTable* o_blocks = nullptr, int rows_per_block = 0) {
   ProfScope ps(c, PROF_ATTN, 4.0 * B * H * static_cast<double>(Nq) * Nk * 128.0,
                2.0 * B * (2.0 * Nq + 2.0 * Nk) * D);
-  launch_attention(Q, ldq, K, ldk, Vt, ldvb, bias, O, ldo, B, H, Nq, Nk, D, scale, c->stream);
+  launch_attention(Q, ldq, K, ldk, Vt, ldvb, bias, O, ldo, B, H, Nq, Nk, D, scale, c->stream, o_blocks, rows_per_block);
 }
 void norm_mod(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* ts, const float* tsc, const float* as,
               const float* asc, int64_t ada_ld, int rows_per_mod, float eps, int ln) {
@@ -401,16 +402,28 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
   const int64_t blk = static_cast<int64_t>(Nl) * Csp;   // elements one rank sends to one peer per tensor
   bf16 *qsend = nullptr, *ksend = nullptr, *vsend = nullptr, *qrecv = nullptr, *krecv = nullptr, *vrecv = nullptr,
        *osend = nullptr, *orecv = nullptr, *vt_sp = nullptr;
+  // Ulysses exchange buffers.  Preferred: every rank's receive buffer [q | k | v | o][P][Nl][Csp] is mapped into its peers
+  // (CUDA IPC over NVLink) and the producing kernels store straight into it; otherwise NCCL all-to-all through send buffers.
+  bool p2p = false;
+  bf16* peer_base[LTX_MAX_PEERS] = {};
+  const int me = c->dist.sp_rank;
   if (P > 1) {
-    c->sp_send.reserve(static_cast<size_t>(3) * P * blk * 2);
-    c->sp_recv.reserve(static_cast<size_t>(3) * P * blk * 2);
+    p2p = dist_p2p_ensure(c, static_cast<size_t>(4) * P * blk * 2);
     c->sp_vt.reserve(static_cast<size_t>(Csp) * ldv * 2);
     c->sp_vel.reserve(static_cast<size_t>(Nl) * Cout * 4);
-    qsend = c->sp_send.as<bf16>(); ksend = qsend + P * blk; vsend = ksend + P * blk;
-    qrecv = c->sp_recv.as<bf16>(); krecv = qrecv + P * blk; vrecv = krecv + P * blk;
-    osend = qsend;   // the attention output [N, Csp] reuses the q send buffer, its exchange lands in the q recv buffer
-    orecv = qrecv;
     vt_sp = c->sp_vt.as<bf16>();
+    if (p2p) {
+      for (int r = 0; r < P; ++r) peer_base[r] = reinterpret_cast<bf16*>(c->dist.p2p_peer[r]);
+      qrecv = peer_base[me]; krecv = qrecv + P * blk; vrecv = krecv + P * blk; orecv = vrecv + P * blk;
+      osend = orecv;   // placeholder (attention output rows go to the peers' o regions)
+    } else {
+      c->sp_send.reserve(static_cast<size_t>(3) * P * blk * 2);
+      c->sp_recv.reserve(static_cast<size_t>(3) * P * blk * 2);
+      qsend = c->sp_send.as<bf16>(); ksend = qsend + P * blk; vsend = ksend + P * blk;
+      qrecv = c->sp_recv.as<bf16>(); krecv = qrecv + P * blk; vrecv = krecv + P * blk;
+      osend = qsend;   // the attention output [N, Csp] reuses the q send buffer, its exchange lands in the q recv buffer
+      orecv = qrecv;
+    }
   }
 
   // ---- step-invariant pieces
@@ -509,12 +522,26 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
         // one all-to-all turns [Nl tokens, all heads] into [all tokens, Hl heads]; attention runs on the local heads;
         // a second all-to-all returns the output rows to their owners, K-blocked, straight into the to_out GEMM.
         GemmEpi ev;
-        ev.mode = EPI_BF16; ev.out = vsend; ev.ldo = Csp; ev.bias = bw.a1.bv; ev.col_block = Csp; ev.col_block_stride = blk;
-        gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
+        ev.mode = EPI_BF16; ev.out = p2p ? vrecv : vsend; ev.ldo = Csp; ev.bias = bw.a1.bv; ev.col_block = Csp; ev.col_block_stride = blk;
         QkOut qo;
         qo.out[0] = qsend; qo.out[1] = ksend; qo.heads_per_block = Hl; qo.block_stride = blk; qo.ld = Csp;
+        PeerTable ot = {};
+        if (p2p) {   // destination rank d receives this rank's block at [region][me] of its buffer
+          ev.use_col_ptrs = 1;
+          qo.use_peer = 1;
+          for (int d = 0; d < P; ++d) {
+            qo.peer[0].p[d] = peer_base[d] + static_cast<int64_t>(0 * P + me) * blk;
+            qo.peer[1].p[d] = peer_base[d] + static_cast<int64_t>(1 * P + me) * blk;
+            ev.col_ptrs.p[d] = peer_base[d] + static_cast<int64_t>(2 * P + me) * blk;
+            ot.p[d] = peer_base[d] + static_cast<int64_t>(3 * P + me) * blk;
+          }
+        }
+        gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
         qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rope_period, eps, bw.a1.k_norm, &qo);
-        {
+        if (p2p) {
+          ProfScope ps(c, PROF_COMM, 0.0, 3.0 * 2.0 * P * blk * 2.0);
+          dist_p2p_barrier(c, 0);   // everyone's q / k / v blocks have landed here, ours at the peers
+        } else {
           ProfScope ps(c, PROF_COMM, 0.0, 3.0 * 2.0 * P * blk * 2.0);
           const void* sb[3] = {qsend, ksend, vsend};
           void* rb[3] = {qrecv, krecv, vrecv};
@@ -524,8 +551,12 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
           ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * N * Csp);
           launch_transpose_bf16(vrecv, Csp, N, Csp, vt_sp, ldv, st);
         }
-        attention(c, qrecv, Csp, krecv, Csp, vt_sp, ldv, nullptr, osend, Csp, 1, Hl, N, N, Csp, att_scale);
-        {
+        if (p2p) {
+          attention(c, qrecv, Csp, krecv, Csp, vt_sp, ldv, nullptr, osend, Csp, 1, Hl, N, N, Csp, att_scale, &ot, Nl);
+          ProfScope ps(c, PROF_COMM, 0.0, 2.0 * P * blk * 2.0);
+          dist_p2p_barrier(c, 1);   // every rank's attention rows for our tokens have landed in the o region
+        } else {
+          attention(c, qrecv, Csp, krecv, Csp, vt_sp, ldv, nullptr, osend, Csp, 1, Hl, N, N, Csp, att_scale);
           ProfScope ps(c, PROF_COMM, 0.0, 2.0 * P * blk * 2.0);
           const void* sb[1] = {osend};
           void* rb[1] = {orecv};

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* x, b
 __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, int64_t ld, int D,
                                                            const float* __restrict__ w, const float* __restrict__ cosb,
                                                            const float* __restrict__ sinb, int rows_per_rope, float eps,
-                                                           bf16* __restrict__ bout, int hpb, int64_t bstride, int64_t bld) {
+                                                           bf16* __restrict__ bout, int hpb, int64_t bstride, int64_t bld,
+                                                           int use_peer, const PeerTable peer) {
   __shared__ float red[33];
   const int row = blockIdx.x;
   bf16* xr = x + static_cast<int64_t>(row) * ld;
@@ -246,7 +247,11 @@ __global__ void __launch_bounds__(256) qknorm_rope_kernel(bf16* __restrict__ x, 
     }
     bf16* o1 = xr + c1;
     bf16* o2 = xr + c2;
-    if (bout) {
+    if (use_peer) {
+      bf16* ob = reinterpret_cast<bf16*>(peer.p[hh / hpb]) + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+      o1 = ob;
+      o2 = ob + 64;
+    } else if (bout) {
       bf16* ob = bout + static_cast<int64_t>(hh / hpb) * bstride + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
       o1 = ob;
       o2 = ob + 64;
@@ -268,7 +273,8 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
                                                                 const float* __restrict__ cosb, const float* __restrict__ sinb,
                                                                 int rows_per_rope, float eps, bf16* __restrict__ bout0,
                                                                 bf16* __restrict__ bout1, int hpb, int64_t bstride,
-                                                                int64_t bld) {
+                                                                int64_t bld, int use_peer, const PeerTable peer0,
+                                                                const PeerTable peer1) {
   __shared__ float red[8 * ROWS];
   constexpr int D = 4096;
   const int seg = blockIdx.y;
@@ -343,7 +349,12 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
     bf16* xr = x + static_cast<int64_t>(row) * ld + static_cast<int64_t>(seg) * D;
     bf16* o1 = xr + c1;
     bf16* o2 = xr + c2;
-    if (bout) {
+    if (use_peer) {   // Ulysses over peer memory: head block hh / hpb lives in that rank's receive buffer
+      bf16* base = reinterpret_cast<bf16*>(seg == 0 ? peer0.p[hh / hpb] : peer1.p[hh / hpb]);
+      bf16* ob = base + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+      o1 = ob;
+      o2 = ob + 64;
+    } else if (bout) {
       bf16* ob = bout + static_cast<int64_t>(hh / hpb) * bstride + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
       o1 = ob;
       o2 = ob + 64;
@@ -613,20 +624,22 @@ void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const
   bf16* b1 = blocked ? blocked->out[1] : nullptr;
   const int hpb = blocked ? blocked->heads_per_block : 1;
   const int64_t bs = blocked ? blocked->block_stride : 0, bld = blocked ? blocked->ld : 0;
-  LTX_CHECK(!blocked || (hpb > 0 && (D / 128) % hpb == 0 && b0 && (!w_second || b1)), 2, "qknorm_rope: bad blocked output");
+  const int use_peer = blocked ? blocked->use_peer : 0;
+  const PeerTable pt0 = blocked ? blocked->peer[0] : PeerTable{}, pt1 = blocked ? blocked->peer[1] : PeerTable{};
+  LTX_CHECK(!blocked || (hpb > 0 && (D / 128) % hpb == 0 && (use_peer || (b0 && (!w_second || b1)))), 2, "qknorm_rope: bad blocked output");
   if (D == 4096) {
     if (rows_per_cta() == 2)
       launch_pdl(PDL_ROWS, qknorm_rope_fast_kernel<2>, dim3((M + 1) / 2, w_second ? 2 : 1), dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb,
-                 rpr, eps, b0, b1, hpb, bs, bld);
+                 rpr, eps, b0, b1, hpb, bs, bld, use_peer, pt0, pt1);
     else
       launch_pdl(PDL_ROWS, qknorm_rope_fast_kernel<4>, dim3((M + 3) / 4, w_second ? 2 : 1), dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb,
-                 rpr, eps, b0, b1, hpb, bs, bld);
+                 rpr, eps, b0, b1, hpb, bs, bld, use_peer, pt0, pt1);
     return;
   }
-  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps, b0, hpb, bs, bld);
+  qknorm_rope_kernel<<<M, 256, 0, s>>>(x, ld, D, w, cosb, sinb, rpr, eps, b0, hpb, bs, bld, use_peer, pt0);
   LTX_CUDA(cudaGetLastError());
   if (w_second) {
-    qknorm_rope_kernel<<<M, 256, 0, s>>>(x + D, ld, D, w_second, cosb, sinb, rpr, eps, b1, hpb, bs, bld);
+    qknorm_rope_kernel<<<M, 256, 0, s>>>(x + D, ld, D, w_second, cosb, sinb, rpr, eps, b1, hpb, bs, bld, use_peer, pt1);
     LTX_CUDA(cudaGetLastError());
   }
 }

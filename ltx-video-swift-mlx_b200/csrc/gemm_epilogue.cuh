@@ -108,8 +108,12 @@ __device__ __forceinline__ void epi_store_chunk(const float* stage, int lane, in
   } else {  // EPI_BF16 / EPI_GELU_BF16 / EPI_SILU_BF16
     // column-blocked destination (Ulysses send layout): a 4-column group never straddles a block (col_block % 32 == 0)
     bf16* obase = reinterpret_cast<bf16*>(ep.out) + c;
-    if (ep.col_block > 0)
-      obase = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(c / ep.col_block) * ep.col_block_stride + (c % ep.col_block);
+    if (ep.col_block > 0) {
+      if (ep.use_col_ptrs)   // one base per destination rank: the store goes over NVLink when the block is a peer's
+        obase = reinterpret_cast<bf16*>(ep.col_ptrs.p[c / ep.col_block]) + (c % ep.col_block);
+      else
+        obase = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(c / ep.col_block) * ep.col_block_stride + (c % ep.col_block);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rr = rs + 4 * i, row = row0 + rr;

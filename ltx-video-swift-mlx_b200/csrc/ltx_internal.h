@@ -70,6 +70,12 @@ enum EpiMode : int {
   EPI_SILU_BF16 = 4,   // out_bf16[m,n] = silu(acc + bias)
 };
 
+// up to 8 destination base pointers (own memory or NVLink-mapped peer memory), indexed by destination rank
+constexpr int LTX_MAX_PEERS = 8;
+struct PeerTable {
+  void* p[LTX_MAX_PEERS];
+};
+
 struct GemmEpi {
   int mode = EPI_BF16;
   void* out = nullptr;  // bf16 or f32, row pitch ldo (elements)
@@ -89,6 +95,10 @@ struct GemmEpi {
   // out[(n / col_block) * col_block_stride + m * ldo + n % col_block]; col_block = 0 -> plain row-major.
   int col_block = 0;
   int64_t col_block_stride = 0;
+  // column-blocked destination with one base pointer per block (Ulysses over peer memory: block d is written straight into
+  // rank d's receive buffer through NVLink): element (m, n) goes to col_ptrs.p[n / col_block][m * ldo + n % col_block]
+  int use_col_ptrs = 0;
+  PeerTable col_ptrs = {};
   int debug = 0;  // bit 0: skip the epilogue's global traffic (LTX_GEMM_DEBUG, timing experiments only)
 };
 
@@ -128,7 +138,8 @@ void launch_transpose_bf16(const bf16* in, int64_t ld_in, int R, int C, bf16* ou
 // b*ldvb + j, ldvb % 8 == 0); key_bias: optional fp32 [B, Nk] additive logits bias; O [B*Nq, D] bf16.
 void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb,
                       const float* key_bias, bf16* O, int64_t ldo, int B, int H, int Nq, int Nk, int D, float scale,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const PeerTable* o_blocks = nullptr, int rows_per_block = 0);
+// o_blocks != nullptr: output row r goes to o_blocks->p[r / rows_per_block] + (r % rows_per_block) * ldo (peer memory)
 
 // ---------------------------------------------------------------- elementwise / row kernels (elementwise.cu)
 // out_bf16[m,:] = norm(x[m,:]) * (1 + tbl_scale[n] + ada_scale[g*ada_ld + n]) + tbl_shift[n] + ada_shift[g*ada_ld + n],
@@ -144,6 +155,9 @@ struct QkOut {
   bf16* out[2] = {nullptr, nullptr};
   int heads_per_block = 0;
   int64_t block_stride = 0, ld = 0;
+  // use_peer: head block d of segment g goes to peer[g].p[d] + row * ld + ... instead (peer memory, no block_stride)
+  int use_peer = 0;
+  PeerTable peer[2] = {};
 };
 void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const float* cosb, const float* sinb,
                         int rows_per_rope, float eps, cudaStream_t s, const float* w_second = nullptr,

@@ -80,7 +80,10 @@ def main():
         for guided, ref in ((False, ref_plain), (True, ref_guided)):
             out = denoise(ctx, guided)
             err = O.rel_l2(torch.from_numpy(out), torch.from_numpy(ref))
-            print(f"[rank {rank}] Ulysses sp={world} guided={guided}: rel-L2 vs single GPU = {err:.3e}", flush=True)
+            p2p = ctx.lib.ltx_dist_p2p_active(ctx.handle)
+            print(f"[rank {rank}] Ulysses sp={world} guided={guided} peer-memory={p2p}: rel-L2 vs single GPU = {err:.3e}", flush=True)
+            if os.environ.get("LTX_P2P", "1") != "0" and os.environ.get("LTX_REQUIRE_P2P") == "1":
+                ok &= p2p == 1
             ok &= err <= 2e-3     # same arithmetic per element up to bf16 re-rounding of the exchanged tiles
         ctx.close()
     flag = torch.tensor([1 if ok else 0])
