@@ -171,7 +171,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     ctx = LtxContext(LTXTransformerConfig(), local_rank)
-    ctx.init_random_weights(3, seed=1234 + rank)
+    ctx.init_random_weights(3, seed=1234)   # one model; the replicas differ in noise and text
     ctx.finalize_weights()
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
@@ -386,12 +386,55 @@ def run_ours(args, rank, world, local_rank):
         extras["vae_121f_sharded"] = dict(desc=f"VAE decode 768x512x121f, {world} temporal shards + halo exchange",
                                           ms_per_decode=tv, frames_per_s=121e3 / tv)
         ctx.dist_shutdown()
-        # (2) pass-parallel guidance: cond / uncond / STG forwards on different GPU groups
-        ltxdist.init_context(ctx, sp_size=1, pass_groups=world)
+        # (2) pass-parallel guidance (BASELINE config 3): conditional (+ STG, sharing the prefix) on one GPU group, the
+        # unconditional pass on the other; each group runs its forwards sequence-parallel over world/2 GPUs
+        groups = 2
+        ltxdist.init_context(ctx, sp_size=world // groups, pass_groups=groups)
         tg = time_guided()
-        extras["guided_cfg3_pass_parallel"] = dict(desc=f"dev CFG 4.0 + STG 0.5, passes split over {world} GPU groups",
-                                                   ms_per_step=tg, steps_per_s=1e3 / tg)
+        extras["guided_cfg3_pass_parallel"] = dict(
+            desc=f"dev CFG 4.0 + STG 0.5, passes split over {groups} GPU groups x Ulysses sp={world // groups}",
+            ms_per_step=tg, steps_per_s=1e3 / tg)
         ctx.dist_shutdown()
+        # (3) BASELINE config 5, stage 2: 1536x1024x257 frames -> N = 33*32*48 = 50688 tokens, int8 weights, the 3-step
+        # refinement schedule, Ulysses over all GPUs (the upscaler is out of scope: seeded random latent of that shape)
+        if world >= 4 and not args.no_cfg5:
+            try:
+                from ltx_video_swift_mlx_b200.scheduler import STAGE_2_DISTILLED_SIGMA_VALUES as S2
+                ctx.close()
+                torch.cuda.empty_cache()
+                F5, H5, W5 = 33, 32, 48
+                cq = LtxContext(LTXTransformerConfig(), local_rank)
+                cq.init_random_weights(1, seed=99)          # same seed on every rank: sequence parallelism shards one model
+                cq.finalize_weights(quant_bits=8)
+                ltxdist.init_context(cq, sp_size=world, pass_groups=1)
+                sq = torch.cuda.ExternalStream(cq.stream, device=torch.device("cuda", local_rank))
+                n5 = torch.randn(CIN, F5, H5, W5, generator=torch.Generator().manual_seed(77))
+                cq.denoise_begin(n5.numpy(), (F5, H5, W5), S2[0], text, None)
+                cq.denoise_step(S2[0], S2[1], 0)                # builds the RoPE table, the text cache and the peer buffers
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(sq)
+                for i in range(3):
+                    cq.denoise_step(S2[i], S2[i + 1], i)
+                b.record(sq)
+                barrier()
+                t5 = torch.tensor([a.elapsed_time(b) / 3], device="cuda")
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+                cq.set_profiling(True)
+                cq.denoise_step(S2[0], S2[1], 0)
+                p5 = cq.get_profile()
+                cq.set_profiling(False)
+                fl5 = dit_flops_per_step(F5 * H5 * W5, S)
+                extras["cfg5_stage2_qint8_ulysses"] = dict(
+                    desc=f"two-stage refinement step at 1536x1024x257f (N={F5 * H5 * W5}), int8 weights, Ulysses sp={world}, "
+                         f"peer-memory exchange={bool(cq.lib.ltx_dist_p2p_active(cq.handle))}",
+                    ms_per_step=float(t5.item()), steps_per_s=1e3 / float(t5.item()),
+                    aggregate_tflops=fl5 / (float(t5.item()) * 1e-3) / 1e12,
+                    kernel_classes={k: v for k, v in p5.items() if v["launches"]})
+                cq.dist_shutdown()
+                cq.close()
+            except Exception as e:   # report, do not hide
+                extras["cfg5_stage2_qint8_ulysses"] = dict(error=str(e))
 
     if rank != 0:
         if dist is not None:
@@ -453,6 +496,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 50688-token int8 Ulysses extra of the >= 4-GPU runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -21,8 +21,7 @@ void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
   ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
   auto it = c->qw.empty() ? c->qw.end() : c->qw.find(B);
   if (it != c->qw.end()) {   // weight was replaced by int8 / int4 codes: dequant-fused kernel
-    LTX_CHECK(a_kblock == 0, LTX_ERR_UNSUPPORTED, "quantised weights are not supported together with sequence parallelism");
-    launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream);
+    launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
     return;
   }
   launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s,
 template <int MODE, int BITS>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ, int M, int N, int K, int BN,
-               const float* __restrict__ scales, const float* __restrict__ biases, const GemmEpi ep) {
+               const float* __restrict__ scales, const float* __restrict__ biases, int a_kblock, const GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -97,7 +97,10 @@ gemm_q_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_raw[stage], QA_BYTES + raw_bytes);
-          tma_load_2d(sA + stage * QA_BYTES, &tmA, &full_raw[stage], kb * QBK, m_blk * QBM);
+          if (a_kblock > 0)   // K-blocked A (Ulysses receive layout): 3-D map (k in block, row, block)
+            tma_load_3d(sA + stage * QA_BYTES, &tmA, &full_raw[stage], (kb * QBK) % a_kblock, m_blk * QBM, (kb * QBK) / a_kblock);
+          else
+            tma_load_2d(sA + stage * QA_BYTES, &tmA, &full_raw[stage], kb * QBK, m_blk * QBM);
           tma_load_2d(sR + stage * QR_STRIDE, &tmQ, &full_raw[stage], kb * ROW_BYTES, n_blk * BN);
           if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -290,7 +293,7 @@ __global__ void dequantize_kernel(const uint8_t* __restrict__ q, const float* __
 
 template <int MODE, int BITS>
 void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int K, int BN, const float* s, const float* b,
-              const GemmEpi& epi, cudaStream_t stream) {
+              int a_kblock, const GemmEpi& epi, cudaStream_t stream) {
   static bool configured = false;
   auto kern = gemm_q_tcgen05<MODE, BITS>;
   if (!configured) {
@@ -299,19 +302,19 @@ void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int 
   }
   const int tiles = ((M + QBM - 1) / QBM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, epi);
+  launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi);
   LTX_CUDA(cudaGetLastError());
 }
 
 template <int BITS>
 void launch_q_mode(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int K, int BN, const float* s, const float* b,
-                   const GemmEpi& epi, cudaStream_t stream) {
+                   int a_kblock, const GemmEpi& epi, cudaStream_t stream) {
   switch (epi.mode) {
-    case EPI_BF16: launch_q<EPI_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
-    case EPI_GELU_BF16: launch_q<EPI_GELU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
-    case EPI_GATE_RESID: launch_q<EPI_GATE_RESID, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
-    case EPI_F32: launch_q<EPI_F32, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
-    case EPI_SILU_BF16: launch_q<EPI_SILU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, epi, stream); break;
+    case EPI_BF16: launch_q<EPI_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi, stream); break;
+    case EPI_GELU_BF16: launch_q<EPI_GELU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi, stream); break;
+    case EPI_GATE_RESID: launch_q<EPI_GATE_RESID, BITS>(tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi, stream); break;
+    case EPI_F32: launch_q<EPI_F32, BITS>(tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi, stream); break;
+    case EPI_SILU_BF16: launch_q<EPI_SILU_BF16, BITS>(tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi, stream); break;
     default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
   }
 }
@@ -319,7 +322,7 @@ void launch_q_mode(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N,
 }  // namespace
 
 void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
-                   int force_bn) {
+                   int force_bn, int a_kblock, int64_t a_kblock_stride) {
   LTX_CHECK(M > 0 && N > 0 && K > 0 && K % 64 == 0, 2, "quantised GEMM: K must be a multiple of the group size 64");
   LTX_CHECK(W.bits == 8 || W.bits == 4, 2, "quantised GEMM: 8 or 4 bits");
   LTX_CHECK(W.n == N && W.k == K && W.q && W.scales && W.biases, 2, "quantised GEMM: weight shape mismatch");
@@ -327,12 +330,18 @@ void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, in
   int bn = force_bn ? force_bn : gemm_fit_tile_width(M, N);
   LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "quantised GEMM: bad tile width");
   const uint64_t row_bytes = W.bits == 8 ? K : K / 2;
-  CUtensorMap tmA = make_tmap_2d(A, M, K, lda, QBM);
+  CUtensorMap tmA;
+  if (a_kblock > 0) {
+    LTX_CHECK(a_kblock % QBK == 0 && K % a_kblock == 0 && lda == a_kblock, 2, "quantised GEMM: bad K-blocked A layout");
+    tmA = make_tmap_3d(A, a_kblock, M, K / a_kblock, lda, a_kblock_stride, 64, QBM);
+  } else {
+    tmA = make_tmap_2d(A, M, K, lda, QBM);
+  }
   CUtensorMap tmQ = make_tmap_u8(W.q, N, row_bytes, bn, W.bits == 8 ? 64 : 32);
   if (W.bits == 8)
-    launch_q_mode<8>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, epi, stream);
+    launch_q_mode<8>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, a_kblock, epi, stream);
   else
-    launch_q_mode<4>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, epi, stream);
+    launch_q_mode<4>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, a_kblock, epi, stream);
 }
 
 void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s) {

@@ -125,7 +125,7 @@ struct QuantW {
 };
 // C[M,N] = A[M,K] * (s*q + beta)[N,K]^T with the epilogues of launch_gemm (group size 64)
 void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
-                   int force_bn = 0);
+                   int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
 void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s);
 void launch_dequantize(const QuantW& W, bf16* w, cudaStream_t s);
 // uint8 matrix [rows, row_bytes], box [box_rows, box_bytes], no swizzle

@@ -31,7 +31,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # rendezvous only; the data path uses the library's own NCCL communicators
-    heads = 4
+    heads = max(4, world)                    # sp must divide the head count
     ocfg = O.DiTConfig(num_layers=3, num_heads=heads, head_dim=128, caption_channels=192)
     vcfg = O.VAEConfig(base_channels=512, blocks_per_stage=1)
     pcfg = ctxmod.LTXTransformerConfig(num_layers=3, num_attention_heads=heads, caption_channels=192, vae_base_channels=512,
@@ -86,6 +86,17 @@ def main():
                 ok &= p2p == 1
             ok &= err <= 2e-3     # same arithmetic per element up to bf16 re-rounding of the exchanged tiles
         ctx.close()
+        # int8 weights + sequence parallelism (BASELINE config 5): the dequant-fused GEMM reads the K-blocked exchange buffer
+        qs = ctxmod.LtxContext(pcfg, local); qs.load_weights(w); qs.finalize_weights(quant_bits=8)
+        ref_q = denoise(qs, False)
+        qs.close()
+        qd = ctxmod.LtxContext(pcfg, local); qd.load_weights(w); qd.finalize_weights(quant_bits=8)
+        ltxdist.init_context(qd, sp_size=world, pass_groups=1)
+        out = denoise(qd, False)
+        err = O.rel_l2(torch.from_numpy(out), torch.from_numpy(ref_q))
+        print(f"[rank {rank}] Ulysses sp={world} int8 weights: rel-L2 vs single GPU int8 = {err:.3e}", flush=True)
+        ok &= err <= 2e-3
+        qd.close()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
