@@ -349,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
             b.record(sq)
             cq.sync()
             tq = a.elapsed_time(b) / 6
-            extras["qint8"] = dict(desc="same step with int8 group-64 weights (dequant-fused tcgen05 GEMM)", ms_per_step=tq,
+            extras["qint8"] = dict(desc="same step with int8 group-64 weights (M > 256: weight converted once per GEMM into an L2-resident bf16 panel + bf16 pair kernel; M <= 256: dequant-fused tcgen05 GEMM)", ms_per_step=tq,
                                    steps_per_s=1e3 / tq)
             cq.close()
         except Exception as e:   # report, do not hide

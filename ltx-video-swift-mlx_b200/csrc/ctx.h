@@ -131,6 +131,7 @@ struct ltx_ctx {
   std::map<std::string, ltx::DevTensor> tensors;  // raw tensors by post-mapping key
   std::unordered_map<const void*, ltx::QuantW> qw;  // quantised replacements, keyed by the bf16 weight pointer they replace
   int quant_bits = 16;
+  ltx::DevBuf q_panel;                            // bf16 conversion panel of the large-M quantised GEMM path
   std::vector<void*> owned;                       // packed allocations made by finalize
   bool dit_ready = false;
   std::vector<ltx::BlockWeights> blocks;

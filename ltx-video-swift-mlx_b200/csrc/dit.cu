@@ -7,6 +7,7 @@
 //   h   bf16 [R, D]   AdaLN output             qk  bf16 [R, 2D] fused q|k projection (normed + RoPE'd in place)
 //   vt  bf16 [D, ldv] V^T (K-major for P V)    att bf16 [R, D]  attention output
 //   ffh bf16 [R, 4D]  GELU(FFN in)             text cache: per block K [B*S, D], V^T [D, ldv2] (step-invariant)
+#include <algorithm>
 #include <cmath>
 
 #include "ctx.h"
@@ -18,9 +19,11 @@ namespace {
 // profiled launch helpers (flop / byte counts are the algorithmic ones used by bench.py's roofline)
 void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e,
           int a_kblock = 0, int64_t a_kblock_stride = 0) {
-  ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
   auto it = c->qw.empty() ? c->qw.end() : c->qw.find(B);
-  if (it != c->qw.end()) {   // weight was replaced by int8 / int4 codes: dequant-fused kernel
+  const bool panel = it != c->qw.end() && it->second.scratch != nullptr && M >= 257;
+  ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N),
+               panel ? 2 : 1);
+  if (it != c->qw.end()) {   // weight was replaced by int8 / int4 codes: dequant-fused kernel, or panel + bf16 kernel for large M
     launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
     return;
   }
@@ -336,6 +339,11 @@ void dit_quantize(ltx_ctx* c, int bits) {
     qf(b.w_in, FF, D); qf(b.w_out, D, FF);
   }
   for (const void* p : to_free) release(p);
+  // one bf16 panel for the large-M path of launch_gemm_q, sized for the largest weight (the FFN matrices)
+  size_t max_elems = 0;
+  for (auto& kv : c->qw) max_elems = std::max(max_elems, static_cast<size_t>(kv.second.n) * kv.second.k);
+  c->q_panel.reserve(max_elems * 2);
+  for (auto& kv : c->qw) kv.second.scratch = c->q_panel.as<bf16>();
   c->quant_bits = bits;
 }
 

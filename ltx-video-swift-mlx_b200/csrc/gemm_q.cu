@@ -15,6 +15,8 @@
 //                                fence.proxy.async, arrive
 //   warp 1     : MMA issuer (tcgen05.mma, TMEM accumulators, two stages)      warps 2-5: epilogue
 // HBM / L2 traffic for weights drops 2x (int8) / 4x (int4); the tensor core still runs bf16 x bf16 -> fp32.
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "ltx_internal.h"
 #include "ptx.cuh"
@@ -40,7 +42,7 @@ __device__ __forceinline__ uint32_t deq2(uint32_t word, int i0, int i1, float s,
   const uint32_t sel0 = 0x7604u + (i0 << 4), sel1 = 0x7604u + (i1 << 4);
   const float f0 = __uint_as_float(__byte_perm(word, 0x47000000u, sel0));
   const float f1 = __uint_as_float(__byte_perm(word, 0x47000000u, sel1));
-  return pack_bf16(fmaf(f0, s, bm), fmaf(f1, s, bm));
+  return pack_bf16_alu(fmaf(f0, s, bm), fmaf(f1, s, bm));
 }
 
 template <int MODE, int BITS>
@@ -287,7 +289,53 @@ __global__ void dequantize_kernel(const uint8_t* __restrict__ q, const float* __
     const int g = k / 64;
     // identical arithmetic to the fused kernel's deq2(): (2^15 + q) * s + (beta - s * 2^15), one rounding each
     const float sv = scales[static_cast<int64_t>(g) * N + n], bv = biases[static_cast<int64_t>(g) * N + n];
-    w[i] = __float2bfloat16(fmaf(32768.0f + static_cast<float>(code), sv, fmaf(-32768.0f, sv, bv)));
+    // ... and the same fp32 -> bf16 rounding (pack_bf16_alu)
+    const float v = fmaf(32768.0f + static_cast<float>(code), sv, fmaf(-32768.0f, sv, bv));
+    const uint32_t pk = pack_bf16_alu(v, 0.f);
+    w[i] = __ushort_as_bfloat16(static_cast<unsigned short>(pk & 0xFFFFu));
+  }
+}
+
+// Whole-weight conversion into a bf16 panel [N, K]: one thread per 16 output values (16 int8 codes = one uint4, or 16 int4
+// codes = one uint2), 32-byte coalesced stores.  Same arithmetic and rounding as deq2().  Runs right before the bf16 GEMM
+// that consumes the panel; the panel is reused by every weight, so the kernel waits for its predecessor (the previous
+// consumer) before its first store.
+template <int BITS>
+__global__ void __launch_bounds__(256) dequantize_panel_kernel(const uint8_t* __restrict__ q, const float* __restrict__ scales,
+                                                                const float* __restrict__ biases, int N, int K, bf16* w) {
+  griddep_launch();
+  griddep_wait();
+  const int cpr = K >> 4;                                  // 16-value chunks per row
+  const int64_t total = static_cast<int64_t>(N) * cpr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / cpr), ch = static_cast<int>(i - static_cast<int64_t>(n) * cpr);
+    const int g = ch >> 2;                                 // 64-value group
+    const float sv = __ldg(scales + static_cast<int64_t>(g) * N + n), bv = __ldg(biases + static_cast<int64_t>(g) * N + n);
+    const float bm = fmaf(-32768.0f, sv, bv);
+    uint32_t o[8];
+    if (BITS == 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(q + static_cast<int64_t>(n) * K + ch * 16);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[2 * j] = deq2(wv[j], 0, 1, sv, bm);
+        o[2 * j + 1] = deq2(wv[j], 2, 3, sv, bm);
+      }
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(q + static_cast<int64_t>(n) * (K >> 1) + ch * 8);
+      const uint32_t wv[2] = {u.x, u.y};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t lo = wv[j] & 0x0F0F0F0Fu, hi = (wv[j] >> 4) & 0x0F0F0F0Fu;
+        const uint32_t e01 = __byte_perm(lo, hi, 0x5140), e23 = __byte_perm(lo, hi, 0x7362);
+        o[4 * j] = deq2(e01, 0, 1, sv, bm); o[4 * j + 1] = deq2(e01, 2, 3, sv, bm);
+        o[4 * j + 2] = deq2(e23, 0, 1, sv, bm); o[4 * j + 3] = deq2(e23, 2, 3, sv, bm);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(w + static_cast<int64_t>(n) * K + ch * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
   }
 }
 
@@ -327,6 +375,21 @@ void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, in
   LTX_CHECK(W.bits == 8 || W.bits == 4, 2, "quantised GEMM: 8 or 4 bits");
   LTX_CHECK(W.n == N && W.k == K && W.q && W.scales && W.biases, 2, "quantised GEMM: weight shape mismatch");
   LTX_CHECK(lda % 8 == 0, 2, "quantised GEMM: lda must be a multiple of 8");
+  // Large M: the fused kernels redo the code -> bf16 conversion once per 128 / 256-row M tile (12x / 6x at M = 1536) and are
+  // bound by its instruction issue (~450 TFLOP/s); converting the weight ONCE into the context's bf16 panel and running the
+  // bf16 pair kernel on it is ~2x faster there.  The fused kernels keep the small-M regime, where weight bytes dominate.
+  static const int panel_min_m = [] { const char* e = getenv("LTX_GEMMQ_PANEL_MIN_M"); return e ? atoi(e) : 257; }();
+  if (W.scratch != nullptr && force_bn == 0 && M >= panel_min_m) {
+    launch_dequantize_panel(W, W.scratch, stream);
+    launch_gemm(A, lda, W.scratch, K, M, N, K, epi, stream, 0, a_kblock, a_kblock_stride);
+    return;
+  }
+  // force_bn >= 1000 selects the pair kernel with width force_bn - 1000 (0 = fitted); LTX_GEMMQ_2CTA=1 makes it the default for M > 128
+  static const bool pair_default = [] { const char* e = getenv("LTX_GEMMQ_2CTA"); return e ? atoi(e) != 0 : false; }();  // measured slower than the 1-CTA kernel (profiles/r01b_gemm_q_experiments.txt)
+  if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {
+    launch_gemm_q_2cta(A, lda, W, M, N, K, epi, stream, force_bn >= 1000 ? force_bn - 1000 : 0, a_kblock, a_kblock_stride);
+    return;
+  }
   int bn = force_bn ? force_bn : gemm_fit_tile_width(M, N);
   LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "quantised GEMM: bad tile width");
   const uint64_t row_bytes = W.bits == 8 ? K : K / 2;
@@ -342,6 +405,18 @@ void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, in
     launch_q_mode<8>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, a_kblock, epi, stream);
   else
     launch_q_mode<4>(tmA, tmQ, M, N, K, bn, W.scales, W.biases, a_kblock, epi, stream);
+}
+
+void launch_dequantize_panel(const QuantW& W, bf16* w, cudaStream_t s) {
+  LTX_CHECK(W.k % 64 == 0 && (W.bits == 8 || W.bits == 4), 2, "dequantize: K % 64 == 0 and bits in {4, 8}");
+  const int64_t chunks = static_cast<int64_t>(W.n) * (W.k / 16);
+  int64_t blocks = (chunks + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (W.bits == 8)
+    launch_pdl(PDL_GEMM, dequantize_panel_kernel<8>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, W.q, W.scales, W.biases, W.n, W.k, w);
+  else
+    launch_pdl(PDL_GEMM, dequantize_panel_kernel<4>, dim3(static_cast<int>(blocks)), dim3(256), 0, s, W.q, W.scales, W.biases, W.n, W.k, w);
 }
 
 void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s) {

@@ -111,6 +111,7 @@ int gemm_fit_tile_width(int M, int N);
 // 2-CTA (cta_group::2) pair kernel, same contract as launch_gemm (gemm2.cu)
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
+int gemm2_fit_tile_width(int M, int N);
 // 4-CTA cluster kernel: two pairs side by side along N share A through TMA multicast (gemm4.cu), same contract
 void launch_gemm_4cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
@@ -122,12 +123,20 @@ struct QuantW {
   const float* scales = nullptr; // [K/64, N]
   const float* biases = nullptr; // [K/64, N]
   int bits = 0, n = 0, k = 0;
+  // optional bf16 [n, k] scratch panel shared by all quantised weights of a context: for M > 256 the weight is converted
+  // once per GEMM into it (it stays in the 126 MB L2 for the D x D projections) and the bf16 pair kernel runs on the panel
+  bf16* scratch = nullptr;
 };
 // C[M,N] = A[M,K] * (s*q + beta)[N,K]^T with the epilogues of launch_gemm (group size 64)
 void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
                    int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
+// 2-CTA pair variant: each CTA dequantises half of the B tile (gemm_q2.cu); default for M > 128 (LTX_GEMMQ_2CTA=0 disables)
+void launch_gemm_q_2cta(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
+                        int force_bn, int a_kblock, int64_t a_kblock_stride);
 void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s);
 void launch_dequantize(const QuantW& W, bf16* w, cudaStream_t s);
+// vectorised, PDL-aware conversion of the whole weight into a bf16 panel (same rounding as the fused kernels)
+void launch_dequantize_panel(const QuantW& W, bf16* w, cudaStream_t s);
 // uint8 matrix [rows, row_bytes], box [box_rows, box_bytes], no swizzle
 CUtensorMap make_tmap_u8(const void* base, uint64_t rows, uint64_t row_bytes, uint32_t box_rows, uint32_t box_bytes);
 // bf16 [R, C] (row pitch ld_in) -> [C, R] (row pitch ld_out)

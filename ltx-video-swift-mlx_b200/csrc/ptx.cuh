@@ -269,6 +269,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp32 pair -> packed bf16x2 on the integer ALU: round to nearest on the magnitude (ties away from zero; differs from
+// cvt.rn only on exact ties, 2^-16 of the values), then one PRMT takes the two upper halves.  cvt.rn.bf16x2.f32 (F2FP) runs
+// on the quarter-rate XU pipe on sm_100a: in the dequant stage of the quantised GEMM it was the limiter (XU pipe 93 % busy
+// in ncu, tensor pipe 24 %), the ALU form is not.
+__device__ __forceinline__ uint32_t pack_bf16_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

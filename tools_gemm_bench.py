@@ -9,7 +9,7 @@ stream = torch.cuda.ExternalStream(ctx.stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 shapes = [("qk", 1536, 8192, 4096, 0), ("vT", 4096, 1536, 4096, 0), ("out", 1536, 4096, 4096, 2), ("ffn_in", 1536, 16384, 4096, 1),
           ("ffn_out", 1536, 4096, 16384, 2), ("proj_out", 1536, 128, 4096, 3), ("big", 8192, 8192, 8192, 0)]
-def bench_q(name, M, N, K, bits):
+def bench_q(name, M, N, K, bits, bn=0):
     A = torch.randn(M, K, device="cuda").bfloat16()
     Wt = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     q = torch.empty(N, K * bits // 8, device="cuda", dtype=torch.uint8); s = torch.empty(K // 64, N, device="cuda"); b = torch.empty(K // 64, N, device="cuda")
@@ -17,7 +17,7 @@ def bench_q(name, M, N, K, bits):
     torch.cuda.synchronize()
     ctx._check(ctx.lib.ltx_op_quantize(ctx.handle, Wt.data_ptr(), N, K, bits, q.data_ptr(), s.data_ptr(), b.data_ptr()))
     def run():
-        ctx._check(ctx.lib.ltx_op_gemm_q(ctx.handle, A.data_ptr(), q.data_ptr(), s.data_ptr(), b.data_ptr(), bits, bias.data_ptr(), out.data_ptr(), M, N, K, 0, 0))
+        ctx._check(ctx.lib.ltx_op_gemm_q(ctx.handle, A.data_ptr(), q.data_ptr(), s.data_ptr(), b.data_ptr(), bits, bias.data_ptr(), out.data_ptr(), M, N, K, 0, bn))
     for _ in range(3): run()
     ctx.sync(); ts = []
     for _ in range(10):
@@ -25,11 +25,12 @@ def bench_q(name, M, N, K, bits):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream); run(); e1.record(stream); ctx.sync(); ts.append(e0.elapsed_time(e1))
     t = sorted(ts)[len(ts) // 2]
-    print(f"{name:9s} M={M} N={N} K={K} int{bits}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
+    print(f"{name:9s} M={M} N={N} K={K} int{bits} bn={bn:5d}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
 
 for nm, M, N, K in ([("qk", 1536, 8192, 4096), ("out", 1536, 4096, 4096), ("ffn_in", 1536, 16384, 4096), ("ffn_out", 1536, 4096, 16384)] if '--quant' in sys.argv else []):
     for bits in (8, 4):
-        bench_q(nm, M, N, K, bits)
+        for bn in (0, 1256, 1224, 1192, 1176, 256):    # 0 / 1xxx: pair kernel (fitted / forced width); 256: 1-CTA kernel
+            bench_q(nm, M, N, K, bits, bn)
 
 for name, M, N, K, mode in (shapes if '--bf16' in sys.argv else []):
     A = torch.randn(M, K, device="cuda").bfloat16()
