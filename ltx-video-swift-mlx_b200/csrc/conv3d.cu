@@ -11,6 +11,7 @@
 //   A tile (tap, k-chunk) = 4-D TMA box at (t0+dt, h0+dh, w0+dw, k0) of the padded volume -> [128 rows x 64 ch], 128B swizzle
 //   B tile               = rows [tap*Cout + n0, +BN) x cols [k0, +64) of the [27*Cout, Cin] weight matrix.
 // Warp roles and pipelines are those of gemm.cu (TMA producer / MMA issuer / 4 epilogue warps, 2 TMEM stages).
+#include "gemm_epilogue.cuh"
 #include "ltx_internal.h"
 #include "ptx.cuh"
 
@@ -26,7 +27,7 @@ struct ConvCfg {
   static constexpr uint32_t A_BYTES = CBM * CBK * 2;
   static constexpr uint32_t B_BYTES = BN * CBK * 2;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16;
+  static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
 };
 
 struct ConvGeom {
@@ -111,6 +112,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = g.nt * g.nh * g.nw;
@@ -196,12 +198,54 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      if (MODE == 0) {
+        // plain conv (+bias, +residual): the accumulator chunk is transposed through a warp-private smem tile (see
+        // gemm_epilogue.cuh) so that 8 lanes cover 128 contiguous bytes of one voxel's channels; the lane's 8 voxel
+        // offsets are computed once per tile, the residual values are fetched before the first store
+        float* stage = epi_stage + (warp - 2) * (EPI_STAGE_BYTES / 4);
+        const int cg = lane & 7, rsub = lane >> 3;
+        int64_t voff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = q * 32 + rsub + 4 * i;
+          const int w2 = iw * g.bw + mm % g.bw, h2 = ih * g.bh + (mm / g.bw) % g.bh, t2 = it * g.bt + mm / (g.bw * g.bh);
+          voff[i] = (w2 < g.W && h2 < g.H && t2 < g.T) ? ((static_cast<int64_t>(t2) * g.H + h2) * g.W + w2) * g.Cout : -1;
+        }
         uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (valid) conv_epilogue_chunk<MODE>(r, vt, vh, vw, n_blk * BN + c * 32, g, ep);
+        tmem_ld32(taddr, r);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld_wait();
+          epi_stage_write(stage, lane, r);
+          __syncwarp();
+          if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, r);
+          const int col = n_blk * BN + c * 32 + cg * 4;
+          if (col < g.Cout) {
+            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + col);
+            float4 xin[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              xin[i] = (ep.resid && voff[i] >= 0) ? *reinterpret_cast<const float4*>(ep.resid + voff[i] + col)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (voff[i] < 0) continue;
+              const int rr = rsub + 4 * i;
+              const float4 a = reinterpret_cast<const float4*>(stage)[rr * 8 + (cg ^ (rr & 7))];
+              *reinterpret_cast<float4*>(ep.out + voff[i] + col) =
+                  make_float4(a.x + bv.x + xin[i].x, a.y + bv.y + xin[i].y, a.z + bv.z + xin[i].z, a.w + bv.w + xin[i].w);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (valid) conv_epilogue_chunk<MODE>(r, vt, vh, vw, n_blk * BN + c * 32, g, ep);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -222,47 +266,84 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // mode 0: copy ; 1: x*a[c] + b[c] ; 2: silu(x / sqrt(mean_c x^2 + 1e-8) * (1 + a[c]) + b[c])
 // ---------------------------------------------------------------------------------------------
 // (x, a, b are produced by preceding kernels: no const __restrict__, see griddep_wait in ptx.cuh)
+// VPL = float4 per lane per voxel (C <= 128 * VPL); a warp keeps U = 8 / VPL voxels in flight so that 8 independent 16-byte
+// loads per lane are outstanding (one voxel per warp iteration was latency-bound at 1.8 TB/s), reads each voxel once
+// (registers between the channel reduction and the output) and reduces the U sums of squares together.
+template <int VPL>
 __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out, int T, int H, int W, int C, int mode,
                                                         const float* a, const float* b, int tshift) {
   griddep_launch();
   griddep_wait();
+  constexpr int U = 8 / VPL;
   const int lane = threadIdx.x & 31;
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
   const int64_t wid0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int nv = C >> 2;
-  for (int64_t pv = wid0; pv < nvox; pv += nwarps) {
-    const int pw = static_cast<int>(pv % (W + 2));
-    const int ph = static_cast<int>((pv / (W + 2)) % (H + 2));
-    const int pt = static_cast<int>(pv / (static_cast<int64_t>(W + 2) * (H + 2)));
-    int ws = pw - 1; ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);   // reflect (VideoConvolution.swift:257-266)
-    int hs = ph - 1; hs = hs < 0 ? -hs : (hs >= H ? 2 * H - 2 - hs : hs);
-    int ts = pt - tshift; ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);          // frame replication (:281-294)
-    const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<int64_t>(ts) * H + hs) * W + ws) * C);
-    uint2* dst = reinterpret_cast<uint2*>(out + pv * C);
-    float rs = 1.0f;
-    if (mode == 2) {
-      float ss = 0.f;
-      for (int i = lane; i < nv; i += 32) {
-        float4 v = src[i];
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  float4 av[VPL], bv[VPL];   // per-channel scale / shift: the same for every voxel
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    av[k] = bv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode != 0 && i < nv) { av[k] = reinterpret_cast<const float4*>(a)[i]; bv[k] = reinterpret_cast<const float4*>(b)[i]; }
+  }
+  for (int64_t pv0 = wid0 * U; pv0 < nvox; pv0 += nwarps * U) {
+    float4 v[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pv = pv0 + u;
+      const int pw = static_cast<int>(pv % (W + 2));
+      const int ph = static_cast<int>((pv / (W + 2)) % (H + 2));
+      const int pt = static_cast<int>(pv / (static_cast<int64_t>(W + 2) * (H + 2)));
+      int ws = pw - 1; ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);   // reflect (VideoConvolution.swift:257-266)
+      int hs = ph - 1; hs = hs < 0 ? -hs : (hs >= H ? 2 * H - 2 - hs : hs);
+      int ts = pt - tshift; ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);          // frame replication (:281-294)
+      const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<int64_t>(ts) * H + hs) * W + ws) * C);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k;
+        v[u][k] = (pv < nvox && i < nv) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      ss = warp_sum(ss);
-      rs = rsqrtf(ss / C + 1e-8f);
     }
-    for (int i = lane; i < nv; i += 32) {
-      float4 v = src[i];
-      if (mode == 1) {
-        float4 av = reinterpret_cast<const float4*>(a)[i], bv = reinterpret_cast<const float4*>(b)[i];
-        v.x = v.x * av.x + bv.x; v.y = v.y * av.y + bv.y; v.z = v.z * av.z + bv.z; v.w = v.w * av.w + bv.w;
-      } else if (mode == 2) {
-        float4 av = reinterpret_cast<const float4*>(a)[i], bv = reinterpret_cast<const float4*>(b)[i];
-        v.x = silu(v.x * rs * (1.f + av.x) + bv.x);
-        v.y = silu(v.y * rs * (1.f + av.y) + bv.y);
-        v.z = silu(v.z * rs * (1.f + av.z) + bv.z);
-        v.w = silu(v.w * rs * (1.f + av.w) + bv.w);
+    float rs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) rs[u] = 1.0f;
+    if (mode == 2) {
+      float ss[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ss[u] = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) ss[u] += v[u][k].x * v[u][k].x + v[u][k].y * v[u][k].y + v[u][k].z * v[u][k].z + v[u][k].w * v[u][k].w;
       }
-      dst[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) rs[u] = rsqrtf(ss[u] / C + 1e-8f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pv = pv0 + u;
+      if (pv >= nvox) break;
+      uint2* dst = reinterpret_cast<uint2*>(out + pv * C);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int i = lane + 32 * k;
+        if (i >= nv) break;
+        float4 o = v[u][k];
+        if (mode == 1) {
+          o.x = o.x * av[k].x + bv[k].x; o.y = o.y * av[k].y + bv[k].y; o.z = o.z * av[k].z + bv[k].z; o.w = o.w * av[k].w + bv[k].w;
+        } else if (mode == 2) {
+          o.x = silu(o.x * rs[u] * (1.f + av[k].x) + bv[k].x);
+          o.y = silu(o.y * rs[u] * (1.f + av[k].y) + bv[k].y);
+          o.z = silu(o.z * rs[u] * (1.f + av[k].z) + bv[k].z);
+          o.w = silu(o.w * rs[u] * (1.f + av[k].w) + bv[k].w);
+        }
+        dst[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
     }
   }
 }
@@ -329,12 +410,17 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
 
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
                      int causal, cudaStream_t s) {
-  LTX_CHECK(C % 4 == 0 && H > 1 && W > 1, 2, "vae_prep: bad shape");
+  LTX_CHECK(C % 4 == 0 && C <= 1024 && H > 1 && W > 1, 2, "vae_prep: bad shape (C must be a multiple of 4, at most 1024)");
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
   int64_t blocks = (nvox + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  launch_pdl(PDL_VAE, vae_prep_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, x, out, T, H, W, C, mode, a, b, causal ? 2 : 1);
+  const dim3 gr(static_cast<int>(blocks)), bl(256);
+  const int ts = causal ? 2 : 1;
+  if (C <= 128) launch_pdl(PDL_VAE, vae_prep_kernel<1>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
+  else if (C <= 256) launch_pdl(PDL_VAE, vae_prep_kernel<2>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
+  else if (C <= 512) launch_pdl(PDL_VAE, vae_prep_kernel<4>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
+  else launch_pdl(PDL_VAE, vae_prep_kernel<8>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
   LTX_CUDA(cudaGetLastError());
 }
 
