@@ -55,6 +55,12 @@ typedef struct {
   int32_t vae_base_channels;     /* 1024 */
   int32_t vae_blocks_per_stage;  /* 5 */
   int32_t vae_patch_size;        /* 4 */
+  /* used by ltx_init_random_weights only (loaded checkpoints carry their own shapes):
+   * VideoEncoder channel plan base (Models/VAE/VideoEncoder.swift:229-262) and SpatialUpscaler(midChannels:numBlocksPerStage:)
+   * (Models/Upscaler/SpatialUpscaler.swift:181-185) */
+  int32_t vae_encoder_base_channels; /* 128 */
+  int32_t upscaler_mid_channels;     /* 1024 */
+  int32_t upscaler_blocks;           /* 4 */
 } ltx_config;
 
 void ltx_config_default(ltx_config* cfg);
@@ -76,7 +82,10 @@ int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dt
  * LTXWeightLoader.loadTransformerWeights / loadVAEWeights (Utils/ModelDownloader.swift:605-659) with the key mapping of
  * mapTransformerKey (:756-803) and mapVAEWeights (:808-899).  which: 1 = video transformer (unified checkpoint: only the
  * "model.diffusion_model." tensors; audio / cross-modal / connector tensors are skipped as with includeAudio:false),
- * 2 = VAE decoder (stand-alone VAE file or the "vae." tensors of a unified checkpoint; encoder tensors are skipped).
+ * 2 = VAE decoder (stand-alone VAE file or the "vae." tensors of a unified checkpoint; encoder tensors are skipped),
+ * 3 = VAE encoder (the "encoder." tensors of the same files, mapVAEEncoderWeights :1224-1280, names prefixed "vae_encoder."),
+ * 4 = latent upscaler file (loadSpatialUpscaler, Models/Upscaler/SpatialUpscaler.swift:262-300, names prefixed "upscaler.";
+ * conv kernels are taken in the checkpoint's (O, I, kD, kH, kW) layout).
  * F32 / BF16 / F16 tensors are accepted.  n_loaded (nullable) receives the number of tensors taken.  Follow with
  * ltx_finalize_weights.  ltx_map_weight_key exposes the name mapping alone (no context, no GPU): it writes the mapped name,
  * or an empty string for a tensor the loader skips, into out[cap]. */
@@ -89,7 +98,7 @@ int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap);
  * in).  Must be called before the DiT weights are loaded; single GPU, no quantisation; the VAE is unaffected. */
 int ltx_set_precision(ltx_ctx* ctx, int bits);
 /* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
- * which: 1 = DiT, 2 = VAE decoder, 3 = both. */
+ * which: bit mask, 1 = DiT, 2 = VAE decoder, 4 = VAE encoder, 8 = latent upscaler. */
 int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);
 /* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16; 8 / 4 replace every GEMM weight of the DiT by
  * per-64-group affine codes (w ~= s*q + beta) consumed by the dequant-fused GEMM -- the counterpart of
@@ -173,6 +182,43 @@ int ltx_vae_decode(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, fl
                    int causal, float* out_frames);
 int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep,
                        const float* decode_noise, int causal, float* out_frames);
+
+/* VideoEncoder.callAsFunction (Models/VAE/VideoEncoder.swift:270-312), the encoder half of encodeImage
+ * (Pipeline/LTXPipeline.swift:1902-1932): pixels [3, T, H, W] fp32 (the reference feeds [-1, 1]), H and W multiples of 32
+ * -> latent mean [128, ceil(T/8), H/32, W/32] fp32 (T = 8k+1 frames -> k+1 latent frames; an image is T = 1).
+ * normalize != 0 applies (latent - mean_of_means) / std_of_means with the decoder's statistics, as encodeImage does
+ * (:1920-1926).  Weights: "vae_encoder.*" tensors (ltx_load_safetensors which = 3 or ltx_load_tensor). */
+int ltx_vae_encode(ltx_ctx* ctx, const float* pixels, int T, int H, int W, int normalize, float* latent_out);
+int ltx_vae_encode_dev(ltx_ctx* ctx, const float* pixels, int T, int H, int W, int normalize, float* latent_out);
+
+/* upsampleLatents(_:upscaler:latentMean:latentStd:) (Models/Upscaler/SpatialUpscaler.swift:360-383; inlined at
+ * Pipeline/LTXPipeline.swift:1694-1708, 2594-2619): latent [128, F, H, W] fp32 (normalised) -> denormalise ->
+ * SpatialUpscaler (:215-258) -> renormalise -> [128, F, 2H, 2W].  Weights: "upscaler.*" tensors. */
+int ltx_upscale_latent(ltx_ctx* ctx, const float* latent, int F, int H, int W, float* out);
+int ltx_upscale_latent_dev(ltx_ctx* ctx, const float* latent, int F, int H, int W, float* out);
+
+/* adainFilterLatent(_:reference:factor:) (Pipeline/LatentUtils.swift:201-227): per-channel statistics over (F, H, W) of
+ * latent [channels, n_per_channel] are replaced by those of reference [channels, n_ref_per_channel]; in place. */
+int ltx_adain_filter(ltx_ctx* ctx, float* latent, size_t n_per_channel, const float* reference, size_t n_ref_per_channel,
+                     int channels, float factor);
+int ltx_adain_filter_dev(ltx_ctx* ctx, float* latent, size_t n_per_channel, const float* reference, size_t n_ref_per_channel,
+                         int channels, float factor);
+
+/* Starts a resident denoise session from an existing latent instead of pure noise -- stage 2 of generateVideoTwoStage
+ * (Pipeline/LTXPipeline.swift:2636-2647): latent = noise_scale * noise + (1 - noise_scale) * latent.  latent and noise are
+ * [in_channels, F, H, W] fp32 host buffers; frame0_latent (nullable, [in_channels, 1, H, W]) overwrites the first latent
+ * frame afterwards (the full-resolution image latent of I2V stage 2, :2650-2657).  Text arguments as ltx_denoise_begin. */
+int ltx_denoise_begin_from_latent(ltx_ctx* ctx, const float* latent, const float* noise, float noise_scale,
+                                  const float* frame0_latent, int F, int H, int W, const void* context, ltx_dtype context_dtype,
+                                  const int32_t* mask, const void* neg_context, const int32_t* neg_mask, int S);
+/* Device-resident glue between the two stages (generateVideoTwoStage :2594-2647) without a host round trip: takes the
+ * current session latent [C, F, H, W] as the stage-1 output, upscales it 2x (ltx_upscale_latent), applies AdaIN against
+ * the stage-1 latent (factor adain_factor), mixes in noise [C, F, 2H, 2W] (host, fp32) with noise_scale and makes the
+ * result the session latent at (F, 2H, 2W); the text contexts of the session are kept. */
+int ltx_denoise_upscale_stage(ltx_ctx* ctx, const float* noise, float noise_scale, float adain_factor);
+/* latent[:, 0, :, :] = frame0_latent (host, [in_channels, 1, H, W] fp32): the clean conditioning frame of the
+ * image-to-video loops (Pipeline/LTXPipeline.swift:1132-1160, 2650-2657); combine with ltx_step_params.i2v_frame0_conditioned. */
+int ltx_denoise_set_frame0(ltx_ctx* ctx, const float* frame0_latent);
 
 /* ---- multi-GPU: one process and one context per GPU of an NVLink/NVSwitch box; NCCL communicators are owned by the context.
  * The reference has no multi-device code; correctness contract: N-GPU result == 1-GPU result.

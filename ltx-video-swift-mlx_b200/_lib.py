@@ -18,7 +18,8 @@ class LtxConfig(C.Structure):
         ("out_channels", C.c_int32), ("caption_channels", C.c_int32), ("ffn_mult", C.c_int32), ("rope_theta", C.c_float),
         ("max_pos", C.c_int32 * 3), ("timestep_scale_multiplier", C.c_float), ("norm_eps", C.c_float),
         ("vae_latent_channels", C.c_int32), ("vae_base_channels", C.c_int32), ("vae_blocks_per_stage", C.c_int32),
-        ("vae_patch_size", C.c_int32),
+        ("vae_patch_size", C.c_int32), ("vae_encoder_base_channels", C.c_int32), ("upscaler_mid_channels", C.c_int32),
+        ("upscaler_blocks", C.c_int32),
     ]
 
 
@@ -65,6 +66,15 @@ SIGNATURES = {
     "ltx_denoise_latent_dev": (_I, [_P, C.POINTER(_P)]),
     "ltx_vae_decode": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_decode_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
+    "ltx_vae_encode": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "ltx_vae_encode_dev": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "ltx_upscale_latent": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ltx_upscale_latent_dev": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ltx_adain_filter": (_I, [_P, _P, _SZ, _P, _SZ, _I, _F]),
+    "ltx_adain_filter_dev": (_I, [_P, _P, _SZ, _P, _SZ, _I, _F]),
+    "ltx_denoise_begin_from_latent": (_I, [_P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P, _P, _P, _I]),
+    "ltx_denoise_upscale_stage": (_I, [_P, _P, _F, _F]),
+    "ltx_denoise_set_frame0": (_I, [_P, _P]),
     "ltx_dist_get_unique_id": (_I, [_P]),
     "ltx_dist_init": (_I, [_P, _P, _I, _I, _I, _I]),
     "ltx_dist_shutdown": (_I, [_P]),

@@ -30,6 +30,9 @@ class LTXTransformerConfig:
     vae_base_channels: int = 1024
     vae_blocks_per_stage: int = 5
     vae_patch_size: int = 4
+    vae_encoder_base_channels: int = 128     # VideoEncoder channel plan (random init only)
+    upscaler_mid_channels: int = 1024        # SpatialUpscaler(midChannels:) (random init only)
+    upscaler_blocks: int = 4
 
     @property
     def inner_dim(self) -> int:
@@ -45,6 +48,8 @@ class LTXTransformerConfig:
         c.timestep_scale_multiplier, c.norm_eps = self.timestep_scale_multiplier, self.norm_eps
         c.vae_latent_channels, c.vae_base_channels = self.vae_latent_channels, self.vae_base_channels
         c.vae_blocks_per_stage, c.vae_patch_size = self.vae_blocks_per_stage, self.vae_patch_size
+        c.vae_encoder_base_channels, c.upscaler_mid_channels = self.vae_encoder_base_channels, self.upscaler_mid_channels
+        c.upscaler_blocks = self.upscaler_blocks
         return c
 
 
@@ -181,8 +186,8 @@ class LtxContext:
             self.load_tensor(prefix + k, v)
 
     def load_safetensors(self, path: str, which: int) -> int:
-        """LTXWeightLoader.loadTransformerWeights (which=1) / loadVAEWeights (which=2): reads the checkpoint, maps the keys
-        (mapTransformerKey / mapVAEWeights) and uploads the tensors.  Returns the number of tensors taken."""
+        """LTXWeightLoader.loadTransformerWeights (which=1) / loadVAEWeights (2) / loadVAEEncoderWeights (3) /
+        loadSpatialUpscaler (4): reads the checkpoint, maps the keys and uploads the tensors.  Returns the number taken."""
         n = C.c_int(0)
         self._check(self.lib.ltx_load_safetensors(self.handle, str(path).encode(), int(which), C.byref(n)))
         return n.value
@@ -254,6 +259,36 @@ class LtxContext:
                                                _ptr(nmk), S))
         self._session_shape = (self.config.in_channels, F, H, W)
 
+    def denoise_begin_from_latent(self, latent, noise, noise_scale: float, fhw, context, mask=None, neg_context=None,
+                                  neg_mask=None, frame0_latent=None):
+        """Stage-2 start point (P/LTXPipeline.swift:2636-2657): latent = noise_scale * noise + (1 - noise_scale) * latent."""
+        lt, nz = _host(latent, np.float32), _host(noise, np.float32)
+        f0 = None if frame0_latent is None else _host(frame0_latent, np.float32)
+        cc = _dtype_code(context)
+        ctx = _host(context)
+        S = ctx.shape[-2]
+        mk = None if mask is None else _host(mask, np.int32)
+        nctx = None if neg_context is None else _host(neg_context)
+        nmk = None if neg_mask is None else _host(neg_mask, np.int32)
+        F, H, W = fhw
+        self._check(self.lib.ltx_denoise_begin_from_latent(self.handle, _ptr(lt), _ptr(nz), float(noise_scale), _ptr(f0), F, H, W,
+                                                           _ptr(ctx), cc, _ptr(mk), _ptr(nctx), _ptr(nmk), S))
+        self._session_shape = (self.config.in_channels, F, H, W)
+
+    def denoise_upscale_stage(self, noise, noise_scale: float, adain_factor: float = 1.0):
+        """Device-resident stage switch of generateVideoTwoStage (:2594-2647): upscale 2x, AdaIN against stage 1, re-noise."""
+        Cc, F, H, W = self._session_shape
+        nz = _host(noise, np.float32)
+        assert nz.size == Cc * F * 4 * H * W, "noise must have the stage-2 shape [C, F, 2H, 2W]"
+        self._check(self.lib.ltx_denoise_upscale_stage(self.handle, _ptr(nz), float(noise_scale), float(adain_factor)))
+        self._session_shape = (Cc, F, 2 * H, 2 * W)
+
+    def denoise_set_frame0(self, frame0_latent):
+        f0 = _host(frame0_latent, np.float32)
+        Cc, F, H, W = self._session_shape
+        assert f0.size == Cc * H * W
+        self._check(self.lib.ltx_denoise_set_frame0(self.handle, _ptr(f0)))
+
     def denoise_step(self, sigma: float, sigma_next: float, step_index: int, cfg_scale: float = 1.0, rescale_phi: float = 0.0,
                      stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0,
                      share_stg_prefix: bool = True, i2v_frame0_conditioned: bool = False):
@@ -293,3 +328,40 @@ class LtxContext:
     def vae_decode_dev(self, latent_ptr: int, fhw, out_ptr: int, causal: bool = False):
         Fp, Hp, Wp = fhw
         self._check(self.lib.ltx_vae_decode_dev(self.handle, latent_ptr, Fp, Hp, Wp, -1.0, None, int(causal), out_ptr))
+
+    # ------------------------------------------------------------------ VAE encoder / latent upscaler / AdaIN
+    def vae_encode(self, pixels, normalize: bool = True) -> np.ndarray:
+        """pixels [3,T,H,W] (or [1,3,T,H,W]) fp32 -> latent [128, ceil(T/8), H/32, W/32] (VideoEncoder + encodeImage stats)."""
+        px = _host(pixels, np.float32)
+        if px.ndim == 5:
+            px = np.ascontiguousarray(px[0])
+        _, T, H, W = px.shape
+        out = np.empty((self.config.vae_latent_channels, (T + 7) // 8, H // 32, W // 32), dtype=np.float32)
+        self._check(self.lib.ltx_vae_encode(self.handle, _ptr(px), T, H, W, int(normalize), _ptr(out)))
+        return out
+
+    def vae_encode_dev(self, pixels_ptr: int, thw, out_ptr: int, normalize: bool = True):
+        T, H, W = thw
+        self._check(self.lib.ltx_vae_encode_dev(self.handle, pixels_ptr, T, H, W, int(normalize), out_ptr))
+
+    def upscale_latent(self, latent) -> np.ndarray:
+        """upsampleLatents: [128,F,H,W] (normalised) -> [128,F,2H,2W]."""
+        lat = _host(latent, np.float32)
+        if lat.ndim == 5:
+            lat = np.ascontiguousarray(lat[0])
+        Cc, F, H, W = lat.shape
+        out = np.empty((Cc, F, 2 * H, 2 * W), dtype=np.float32)
+        self._check(self.lib.ltx_upscale_latent(self.handle, _ptr(lat), F, H, W, _ptr(out)))
+        return out
+
+    def upscale_latent_dev(self, latent_ptr: int, fhw, out_ptr: int):
+        F, H, W = fhw
+        self._check(self.lib.ltx_upscale_latent_dev(self.handle, latent_ptr, F, H, W, out_ptr))
+
+    def adain_filter(self, latent, reference, factor: float = 1.0) -> np.ndarray:
+        """adainFilterLatent: latent [C,...] takes the per-channel mean/std of reference [C,...]; returns a new array."""
+        lat = np.array(_host(latent, np.float32), copy=True)
+        ref = _host(reference, np.float32)
+        Cc = lat.shape[0]
+        self._check(self.lib.ltx_adain_filter(self.handle, _ptr(lat), lat.size // Cc, _ptr(ref), ref.size // Cc, Cc, float(factor)))
+        return lat

@@ -58,6 +58,9 @@ void ltx_config_default(ltx_config* cfg) {
   cfg->vae_base_channels = 1024;
   cfg->vae_blocks_per_stage = 5;
   cfg->vae_patch_size = 4;
+  cfg->vae_encoder_base_channels = 128;
+  cfg->upscaler_mid_channels = 1024;
+  cfg->upscaler_blocks = 4;
 }
 
 int ltx_ctx_create(const ltx_config* cfg, int device, ltx_ctx** out) {
@@ -105,7 +108,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
                     &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
                     &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
-                    &c->f_bias, &c->q_panel};
+                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
   cudaStreamDestroy(c->stream);
@@ -199,14 +202,18 @@ int ltx_load_safetensors(ltx_ctx* c, const char* path, int which, int* n_loaded)
   return guarded(c, [&] {
     const int n = load_safetensors(c, path, which);
     if (n_loaded) *n_loaded = n;
-    LTX_CHECK(n > 0, LTX_ERR_WEIGHTS, std::string("no ") + (which == 1 ? "transformer" : "VAE decoder") + " tensors found in '" + (path ? path : "") + "'");
+    static const char* kWhat[] = {"", "transformer", "VAE decoder", "VAE encoder", "upscaler"};
+    LTX_CHECK(n > 0, LTX_ERR_WEIGHTS, std::string("no ") + kWhat[which] + " tensors found in '" + (path ? path : "") + "'");
   });
 }
 
 int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap) {
-  if (!file_key || !out || cap == 0 || (which != 1 && which != 2)) return LTX_ERR_INVALID_ARGUMENT;
+  if (!file_key || !out || cap == 0 || which < 1 || which > 4) return LTX_ERR_INVALID_ARGUMENT;
   try {
-    const std::string m = which == 1 ? map_transformer_key(file_key) : map_vae_key(file_key);
+    const std::string m = which == 1   ? map_transformer_key(file_key)
+                          : which == 2 ? map_vae_key(file_key)
+                          : which == 3 ? map_vae_encoder_key(file_key)
+                                       : map_upscaler_key(file_key);
     if (m.size() + 1 > cap) return LTX_ERR_INVALID_ARGUMENT;
     memcpy(out, m.c_str(), m.size() + 1);
     return LTX_OK;
@@ -239,7 +246,9 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
       if (quant_bits != 16) dit_quantize(c, quant_bits);
     }
     if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);
-    LTX_CHECK(c->dit_ready || c->vae.ready, LTX_ERR_WEIGHTS, "no weights loaded");
+    if (c->tensors.count("vae_encoder.conv_in.conv.weight")) vae_encoder_finalize(c);
+    if (c->tensors.count("upscaler.initial_conv.weight")) upscaler_finalize(c);
+    LTX_CHECK(c->dit_ready || c->vae.ready || c->enc.ready || c->ups.ready, LTX_ERR_WEIGHTS, "no weights loaded");
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
@@ -370,6 +379,75 @@ int ltx_denoise_begin(ltx_ctx* c, const float* noise, int F, int H, int W, float
   });
 }
 
+namespace {
+// (re)sizes the per-session work buffers for a [C, F, H, W] latent and records the geometry
+void session_resize(ltx_ctx* c, int F, int H, int W) {
+  const size_t n = static_cast<size_t>(c->cfg.in_channels) * F * H * W;
+  c->s_F = F; c->s_H = H; c->s_W = W;
+  c->s_tok.reserve(n * 2);
+  c->s_vc.reserve(n * 4);
+  c->s_vu.reserve(n * 4);
+  c->s_vs.reserve(n * 4);
+  c->s_vprev.reserve(n * 4);
+  c->vel.reserve(n * 4);
+  c->s_sigma.reserve(16);
+}
+// latent[:, 0, :, :] = frame0 (host [C, 1, H, W]): the clean conditioning frame of the image-to-video loops
+void session_set_frame0(ltx_ctx* c, const float* frame0_host) {
+  const size_t hw = static_cast<size_t>(c->s_H) * c->s_W;
+  LTX_CUDA(cudaMemcpy2DAsync(c->s_latent.ptr, static_cast<size_t>(c->s_F) * hw * 4, frame0_host, hw * 4, hw * 4,
+                             static_cast<size_t>(c->cfg.in_channels), cudaMemcpyHostToDevice, c->stream));
+}
+}  // namespace
+
+int ltx_denoise_begin_from_latent(ltx_ctx* c, const float* latent, const float* noise, float noise_scale,
+                                  const float* frame0_latent, int F, int H, int W, const void* context, ltx_dtype context_dtype,
+                                  const int32_t* mask, const void* neg_context, const int32_t* neg_mask, int S) {
+  // same session set-up as ltx_denoise_begin, then the stage-2 start point (P/LTXPipeline.swift:2636-2657)
+  int rc = ltx_denoise_begin(c, noise, F, H, W, 1.0f, context, context_dtype, mask, neg_context, neg_mask, S);
+  if (rc != LTX_OK) return rc;
+  return guarded(c, [&] {
+    LTX_CHECK(latent != nullptr, LTX_ERR_INVALID_ARGUMENT, "null latent");
+    const size_t n = static_cast<size_t>(c->cfg.in_channels) * F * H * W;
+    h2d(c, c->u_in, latent, n * 4);
+    // s_latent holds the noise: swap roles so that latent = s * noise + (1 - s) * latent lands in s_latent
+    renoise_dev(c, c->u_in.as<float>(), c->s_latent.as<float>(), static_cast<int64_t>(n), noise_scale);
+    LTX_CUDA(cudaMemcpyAsync(c->s_latent.ptr, c->u_in.ptr, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (frame0_latent) session_set_frame0(c, frame0_latent);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_denoise_set_frame0(ltx_ctx* c, const float* frame0_latent) {
+  return guarded(c, [&] {
+    LTX_CHECK(frame0_latent && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "no denoise session");
+    session_set_frame0(c, frame0_latent);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_denoise_upscale_stage(ltx_ctx* c, const float* noise, float noise_scale, float adain_factor) {
+  return guarded(c, [&] {
+    LTX_CHECK(noise && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "denoise_upscale_stage before denoise_begin");
+    const int C = c->cfg.in_channels, F = c->s_F, H = c->s_H, W = c->s_W;
+    const size_t n1 = static_cast<size_t>(C) * F * H * W, n2 = 4 * n1;
+    // the stage-1 output is both the upscaler input and the AdaIN reference (P/LTXPipeline.swift:2604-2624)
+    c->u_ref.reserve(n1 * 4);
+    LTX_CUDA(cudaMemcpyAsync(c->u_ref.ptr, c->s_latent.ptr, n1 * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->u_out.reserve(n2 * 4);
+    upscale_latent_dev(c, c->u_ref.as<float>(), F, H, W, c->u_out.as<float>());
+    adain_filter_dev(c, c->u_out.as<float>(), static_cast<int64_t>(4) * F * H * W, c->u_ref.as<float>(),
+                     static_cast<int64_t>(F) * H * W, C, adain_factor);
+    h2d(c, c->u_in, noise, n2 * 4);
+    renoise_dev(c, c->u_out.as<float>(), c->u_in.as<float>(), static_cast<int64_t>(n2), noise_scale);   // :2644-2647
+    LTX_CUDA(cudaStreamSynchronize(c->stream));   // s_latent is re-allocated below: nothing may still read it
+    c->s_latent.reserve(n2 * 4);
+    LTX_CUDA(cudaMemcpyAsync(c->s_latent.ptr, c->u_out.ptr, n2 * 4, cudaMemcpyDeviceToDevice, c->stream));
+    session_resize(c, F, 2 * H, 2 * W);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
   return guarded(c, [&] {
     LTX_CHECK(p != nullptr && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "denoise_step before denoise_begin");
@@ -492,6 +570,62 @@ int ltx_vae_decode(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, floa
     c->v_frames.reserve(fo * 4);
     vae_decode_dev(c, c->v_lat.as<float>(), Fp, Hp, Wp, timestep, nz, causal, c->v_frames.as<float>());
     LTX_CUDA(cudaMemcpyAsync(out_frames, c->v_frames.ptr, fo * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+// ---------------------------------------------------------------- VAE encoder, latent upscaler, AdaIN, re-noise
+int ltx_vae_encode_dev(ltx_ctx* c, const float* pixels, int T, int H, int W, int normalize, float* latent_out) {
+  return guarded(c, [&] { vae_encode_dev(c, pixels, T, H, W, normalize, latent_out); });
+}
+
+int ltx_vae_encode(ltx_ctx* c, const float* pixels, int T, int H, int W, int normalize, float* latent_out) {
+  return guarded(c, [&] {
+    LTX_CHECK(pixels && latent_out && T >= 1 && H >= 64 && W >= 64 && H % 32 == 0 && W % 32 == 0, LTX_ERR_INVALID_ARGUMENT,
+              "bad vae_encode arguments");
+    const size_t n_in = static_cast<size_t>(3) * T * H * W;
+    const size_t n_out = static_cast<size_t>(c->cfg.vae_latent_channels) * ((T + 7) / 8) * (H / 32) * (W / 32);
+    h2d(c, c->u_in, pixels, n_in * 4);
+    c->u_out.reserve(n_out * 4);
+    vae_encode_dev(c, c->u_in.as<float>(), T, H, W, normalize, c->u_out.as<float>());
+    LTX_CUDA(cudaMemcpyAsync(latent_out, c->u_out.ptr, n_out * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_upscale_latent_dev(ltx_ctx* c, const float* latent, int F, int H, int W, float* out) {
+  return guarded(c, [&] { upscale_latent_dev(c, latent, F, H, W, out); });
+}
+
+int ltx_upscale_latent(ltx_ctx* c, const float* latent, int F, int H, int W, float* out) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && out && F >= 1 && H > 1 && W > 1, LTX_ERR_INVALID_ARGUMENT, "bad upscale_latent arguments");
+    const size_t n = static_cast<size_t>(c->cfg.vae_latent_channels) * F * H * W;
+    h2d(c, c->u_in, latent, n * 4);
+    c->u_out.reserve(4 * n * 4);
+    upscale_latent_dev(c, c->u_in.as<float>(), F, H, W, c->u_out.as<float>());
+    LTX_CUDA(cudaMemcpyAsync(out, c->u_out.ptr, 4 * n * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_adain_filter_dev(ltx_ctx* c, float* latent, size_t n_per_channel, const float* reference, size_t n_ref_per_channel,
+                         int channels, float factor) {
+  return guarded(c, [&] {
+    adain_filter_dev(c, latent, static_cast<int64_t>(n_per_channel), reference, static_cast<int64_t>(n_ref_per_channel), channels,
+                     factor);
+  });
+}
+
+int ltx_adain_filter(ltx_ctx* c, float* latent, size_t n_per_channel, const float* reference, size_t n_ref_per_channel, int channels,
+                     float factor) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && reference && channels > 0, LTX_ERR_INVALID_ARGUMENT, "bad adain arguments");
+    h2d(c, c->u_in, latent, n_per_channel * channels * 4);
+    h2d(c, c->u_ref, reference, n_ref_per_channel * channels * 4);
+    adain_filter_dev(c, c->u_in.as<float>(), static_cast<int64_t>(n_per_channel), c->u_ref.as<float>(),
+                     static_cast<int64_t>(n_ref_per_channel), channels, factor);
+    LTX_CUDA(cudaMemcpyAsync(latent, c->u_in.ptr, n_per_channel * channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
 }

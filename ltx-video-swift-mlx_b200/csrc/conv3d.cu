@@ -34,6 +34,7 @@ struct ConvGeom {
   int T, H, W, Cin, Cout;
   int bt, bh, bw;     // voxel box of one M tile (bt*bh*bw == 128)
   int nt, nh, nw;     // tiles per axis
+  int tap0, ntaps;    // taps [tap0, tap0 + ntaps) of the 3x3x3 stencil (27: Conv3d; 9 starting at 9: per-frame Conv2d, dt = 1)
 };
 
 __device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
@@ -119,7 +120,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int num_n = (g.Cout + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int kchunks = g.Cin / CBK;
-  const int num_k = 27 * kchunks;
+  const int num_k = g.ntaps * kchunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -145,12 +146,13 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
         const int t0 = it * g.bt, h0 = ih * g.bh, w0 = iw * g.bw;
         for (int kb = 0; kb < num_k; ++kb) {
-          const int tap = kb / kchunks, kc = kb % kchunks;
+          const int wtap = kb / kchunks, kc = kb % kchunks;
+          const int tap = g.tap0 + wtap;
           const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           tma_load_4d(sA + stage * Cfg::A_BYTES, &tmX, &full[stage], kc * CBK, w0 + dw, h0 + dh, t0 + dt);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmW, &full[stage], kc * CBK, tap * g.Cout + n_blk * BN);
+          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmW, &full[stage], kc * CBK, wtap * g.Cout + n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -263,7 +265,10 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------
 // Padding prologue: one warp per padded voxel.
-// mode 0: copy ; 1: x*a[c] + b[c] ; 2: silu(x / sqrt(mean_c x^2 + 1e-8) * (1 + a[c]) + b[c])
+// mode 0: copy ; 1: x*a[c] + b[c] ; 2: silu(x / sqrt(mean_c x^2 + 1e-8) * (1 + a[c]) + b[c]) (a, b nullable: plain
+// pixel-norm + SiLU, the encoder's res block) ; 3: silu(x*a[c] + b[c]) (GroupNorm folded into a per-channel affine + SiLU)
+// pad: bit 0 causal (two leading frame copies instead of one leading + one trailing), bit 1 zero spatial padding instead
+// of reflect (the encoder, V/VideoEncoder.swift:226-227), bit 2 zero temporal padding (MLX Conv3d padding: 1, the upscaler)
 // ---------------------------------------------------------------------------------------------
 // (x, a, b are produced by preceding kernels: no const __restrict__, see griddep_wait in ptx.cuh)
 // VPL = float4 per lane per voxel (C <= 128 * VPL); a warp keeps U = 8 / VPL voxels in flight so that 8 independent 16-byte
@@ -271,10 +276,12 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // (registers between the channel reduction and the output) and reduces the U sums of squares together.
 template <int VPL>
 __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out, int T, int H, int W, int C, int mode,
-                                                        const float* a, const float* b, int tshift) {
+                                                        const float* a, const float* b, int pad) {
   griddep_launch();
   griddep_wait();
-  constexpr int U = 8 / VPL;
+  constexpr int U = VPL >= 8 ? 1 : 8 / VPL;
+  const int tshift = (pad & 1) ? 2 : 1;
+  const bool zero_hw = (pad & 2) != 0, zero_t = (pad & 4) != 0;
   const int lane = threadIdx.x & 31;
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
   const int64_t wid0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -285,24 +292,28 @@ __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out
   for (int k = 0; k < VPL; ++k) {
     const int i = lane + 32 * k;
     av[k] = bv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mode != 0 && i < nv) { av[k] = reinterpret_cast<const float4*>(a)[i]; bv[k] = reinterpret_cast<const float4*>(b)[i]; }
+    if (mode != 0 && a != nullptr && i < nv) { av[k] = reinterpret_cast<const float4*>(a)[i]; bv[k] = reinterpret_cast<const float4*>(b)[i]; }
   }
   for (int64_t pv0 = wid0 * U; pv0 < nvox; pv0 += nwarps * U) {
     float4 v[U][VPL];
+    bool zero[U];   // padding voxel of a zero-padded axis: written as 0 (after the activation, like the conv's own padding)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t pv = pv0 + u;
       const int pw = static_cast<int>(pv % (W + 2));
       const int ph = static_cast<int>((pv / (W + 2)) % (H + 2));
       const int pt = static_cast<int>(pv / (static_cast<int64_t>(W + 2) * (H + 2)));
-      int ws = pw - 1; ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);   // reflect (VideoConvolution.swift:257-266)
-      int hs = ph - 1; hs = hs < 0 ? -hs : (hs >= H ? 2 * H - 2 - hs : hs);
-      int ts = pt - tshift; ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);          // frame replication (:281-294)
+      int ws = pw - 1, hs = ph - 1, ts = pt - (zero_t ? 1 : tshift);
+      zero[u] = (zero_hw && (ws < 0 || ws >= W || hs < 0 || hs >= H)) || (zero_t && (ts < 0 || ts >= T));
+      ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);   // reflect (VideoConvolution.swift:257-266)
+      hs = hs < 0 ? -hs : (hs >= H ? 2 * H - 2 - hs : hs);
+      ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);              // frame replication (:281-294)
+      if (zero[u]) { ws = 0; hs = 0; ts = 0; }
       const float4* src = reinterpret_cast<const float4*>(x + ((static_cast<int64_t>(ts) * H + hs) * W + ws) * C);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int i = lane + 32 * k;
-        v[u][k] = (pv < nvox && i < nv) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u][k] = (pv < nvox && i < nv && !zero[u]) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     float rs[U];
@@ -341,7 +352,11 @@ __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out
           o.y = silu(o.y * rs[u] * (1.f + av[k].y) + bv[k].y);
           o.z = silu(o.z * rs[u] * (1.f + av[k].z) + bv[k].z);
           o.w = silu(o.w * rs[u] * (1.f + av[k].w) + bv[k].w);
+        } else if (mode == 3) {
+          o.x = silu(o.x * av[k].x + bv[k].x); o.y = silu(o.y * av[k].y + bv[k].y);
+          o.z = silu(o.z * av[k].z + bv[k].z); o.w = silu(o.w * av[k].w + bv[k].w);
         }
+        if (zero[u]) o = make_float4(0.f, 0.f, 0.f, 0.f);
         dst[i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
     }
@@ -388,8 +403,9 @@ void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
 }  // namespace
 
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
-                   cudaStream_t s) {
+                   cudaStream_t s, int ntaps) {
   LTX_CHECK(T > 0 && H > 1 && W > 1, 2, "conv3d: bad volume (reflect padding needs H, W >= 2)");
+  LTX_CHECK(ntaps == 27 || ntaps == 9, 2, "conv3d: 27 taps (3x3x3) or 9 taps (per-frame 3x3)");
   LTX_CHECK(Cin % 64 == 0, 2, "conv3d: Cin must be a multiple of 64");
   LTX_CHECK(epi.mode != 0 || Cout % 4 == 0, 2, "conv3d: Cout must be a multiple of 4");
   LTX_CHECK(epi.mode != 1 || (Cout % 32 == 0 && Cin % 8 == 0 && epi.resid != nullptr), 2, "conv3d: bad d2s configuration");
@@ -399,9 +415,10 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   g.bh = best_pow2(H, 128 / g.bw);
   g.bt = 128 / (g.bw * g.bh);
   g.nt = (T + g.bt - 1) / g.bt; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
+  g.ntaps = ntaps; g.tap0 = ntaps == 9 ? 9 : 0;
   const int bn = Cout >= 256 ? 256 : 128;
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
-  CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(27) * Cout, Cin, Cin, bn);
+  CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
   if (bn == 256)
     conv_launch_mode<256>(tmX, tmW, g, epi, s);
   else
@@ -409,18 +426,19 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
 }
 
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
-                     int causal, cudaStream_t s) {
-  LTX_CHECK(C % 4 == 0 && C <= 1024 && H > 1 && W > 1, 2, "vae_prep: bad shape (C must be a multiple of 4, at most 1024)");
+                     int pad, cudaStream_t s) {
+  LTX_CHECK(C % 4 == 0 && C <= 2048 && H > 1 && W > 1, 2, "vae_prep: bad shape (C must be a multiple of 4, at most 2048)");
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
   int64_t blocks = (nvox + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   const dim3 gr(static_cast<int>(blocks)), bl(256);
-  const int ts = causal ? 2 : 1;
+  const int ts = pad;
   if (C <= 128) launch_pdl(PDL_VAE, vae_prep_kernel<1>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
   else if (C <= 256) launch_pdl(PDL_VAE, vae_prep_kernel<2>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
   else if (C <= 512) launch_pdl(PDL_VAE, vae_prep_kernel<4>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
-  else launch_pdl(PDL_VAE, vae_prep_kernel<8>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
+  else if (C <= 1024) launch_pdl(PDL_VAE, vae_prep_kernel<8>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
+  else launch_pdl(PDL_VAE, vae_prep_kernel<16>, gr, bl, 0, s, x, out, T, H, W, C, mode, a, b, ts);
   LTX_CUDA(cudaGetLastError());
 }
 

@@ -69,6 +69,7 @@ struct ConvW {
   const bf16* w = nullptr;  // [27][Cout][Cin]
   const float* b = nullptr;
   int cin = 0, cout = 0;
+  int taps = 27;            // 27: 3x3x3 ; 9: per-frame 3x3 (upscaler Conv2d)
 };
 struct VaeResBlock {
   ConvW c1, c2;
@@ -89,6 +90,31 @@ struct VaeWeights {
   std::vector<std::vector<VaeResBlock>> stages;  // 4 stages x blocks_per_stage
   std::vector<ConvW> ups;                        // 3 depth-to-space convs
   const float* last_sst = nullptr;               // [2, C_last] rows shift, scale
+};
+
+// VAE encoder (V/VideoEncoder.swift:211-268): conv_in 48 -> base, 4 down blocks (res blocks + space-to-depth conv), mid block, conv_out
+struct EncResBlock { ConvW c1, c2; };
+struct EncStage {
+  std::vector<EncResBlock> res;
+  ConvW down;       // base_i -> cout / (ft*fh*fw)
+  int cout = 0;     // channels after space-to-depth
+};
+struct EncWeights {
+  bool ready = false;
+  int base = 0;
+  ConvW conv_in, conv_out;
+  EncStage stage[4];
+  std::vector<EncResBlock> mid;
+};
+// latent upscaler (Models/Upscaler/SpatialUpscaler.swift:167-258)
+struct GnW { const float *w = nullptr, *b = nullptr; };
+struct UpsBlock { ConvW c1, c2; GnW n1, n2; };
+struct UpsWeights {
+  bool ready = false;
+  int mid = 0, cin = 0;
+  ConvW initial, up2d, final_conv;
+  GnW initial_norm;
+  std::vector<UpsBlock> pre, post;
 };
 
 }  // namespace ltx
@@ -140,6 +166,8 @@ struct ltx_ctx {
   const float *b_patch = nullptr, *b_t1 = nullptr, *b_t2 = nullptr, *b_ada = nullptr, *b_c1 = nullptr, *b_c2 = nullptr,
               *b_out = nullptr, *sst_out = nullptr;
   ltx::VaeWeights vae;
+  ltx::EncWeights enc;
+  ltx::UpsWeights ups;
 
   // ---- DiT workspaces (grow-only)
   ltx::DevBuf lat_in, ctx_in, ts_in, mask_in;      // staged inputs
@@ -169,6 +197,7 @@ struct ltx_ctx {
 
   // ---- VAE workspaces
   ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te;
+  ltx::DevBuf u_part, u_ab, u_stats, u_in, u_out, u_ref;   // encoder / upscaler / AdaIN scratch and host-API staging
 };
 
 namespace ltx {
@@ -216,6 +245,19 @@ void dit_forward_f32(ltx_ctx* c, const void* latent, int latent_dtype, const voi
 void vae_finalize(ltx_ctx* c);
 void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
                     int causal, float* frames_dev);
+ConvW vae_pack_conv_keys(ltx_ctx* c, const std::string& wkey, const std::string& bkey, int64_t cout, int64_t cin,
+                         int64_t cout_use, int taps);
+const float* vae_vec(ltx_ctx* c, const std::string& key, int64_t n);
+void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
+              int pad, int epi_mode, float* out, const float* resid, int n_active = 1, int t_shift = 0);
+// vae_extra.cu: VAE encoder (V/VideoEncoder.swift), latent upscaler (Models/Upscaler/SpatialUpscaler.swift), AdaIN, re-noise
+void vae_encoder_finalize(ltx_ctx* c);
+void vae_encode_dev(ltx_ctx* c, const float* pixels_dev, int T, int H, int W, int normalize, float* latent_dev);
+void upscaler_finalize(ltx_ctx* c);
+void upscale_latent_dev(ltx_ctx* c, const float* latent_dev, int F, int H, int W, float* out_dev);
+void adain_filter_dev(ltx_ctx* c, float* latent_dev, int64_t n_per_channel, const float* ref_dev, int64_t n_ref_per_channel,
+                      int C, float factor);
+void renoise_dev(ltx_ctx* c, float* latent_dev, const float* noise_dev, int64_t n, float noise_scale);
 // dist.cu
 void dist_get_unique_id(void* out128);
 void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int sp_size, int pass_groups);
@@ -232,6 +274,8 @@ void dist_halo_exchange(ltx_ctx* c, const void* send_prev, void* recv_prev, cons
 // safetensors.cu
 std::string map_transformer_key(const std::string& file_key);
 std::string map_vae_key(const std::string& file_key);
+std::string map_vae_encoder_key(const std::string& file_key);
+std::string map_upscaler_key(const std::string& file_key);
 int load_safetensors(ltx_ctx* c, const char* path, int which);
 // weights.cu
 const DevTensor& get_tensor(ltx_ctx* c, const std::string& key);

@@ -215,12 +215,15 @@ struct ConvEpi {
   int t_shift = 0;          // mode 1: output frame = 2t + p1 - 1 + t_shift (1 on temporal shards other than the first,
                             // which keep the frame the first shard trims; frames < 0 are dropped)
 };
-// x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [27][Cout][Cin]; 3x3x3 cross-correlation.
+// x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [ntaps][Cout][Cin]; 3x3x3 cross-correlation (ntaps = 27) or a
+// per-frame 3x3 one (ntaps = 9: only the dt = 1 taps, the upscaler's Conv2d).
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
-                   cudaStream_t s);
+                   cudaStream_t s, int ntaps = 27);
 // pad (+ optional pixel-norm * (1+scale) + shift -> SiLU, or per-channel affine) from fp32 [T,H,W,C] into bf16 [T+2,H+2,W+2,C]
-// mode 0: copy ; 1: x*a[c]+b[c] (denormalise) ; 2: silu(pn(x)*(1+a[c])+b[c])
+// mode 0: copy ; 1: x*a[c]+b[c] (denormalise) ; 2: silu(pn(x)*(1+a[c])+b[c]) (a, b nullable) ; 3: silu(x*a[c]+b[c])
+// pad: VAE_PAD_* bits (0 = reflect H/W + one replicated frame each side: the decoder's non-causal convolution)
+enum { VAE_PAD_CAUSAL = 1, VAE_PAD_ZERO_HW = 2, VAE_PAD_ZERO_T = 4 };
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
-                     int causal, cudaStream_t s);
+                     int pad, cudaStream_t s);
 
 }  // namespace ltx

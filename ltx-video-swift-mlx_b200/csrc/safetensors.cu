@@ -247,9 +247,43 @@ std::string map_vae_key(const std::string& file_key) {
   return "vae." + k;
 }
 
-// which: 1 = transformer tensors (mapTransformerKey), 2 = VAE decoder tensors (mapVAEWeights).  Returns how many were loaded.
+// VAE-encoder key of the checkpoint -> "vae_encoder." + Swift module path (mapVAEEncoderWeights, U/ModelDownloader.swift:1224-1280),
+// or "" for everything that is not an "encoder." tensor.
+std::string map_vae_encoder_key(const std::string& file_key) {
+  std::string key = file_key;
+  if (starts_with(key, "vae.")) key = key.substr(4);
+  if (!starts_with(key, "encoder.")) return "";                           // :1233
+  std::string k = key.substr(strlen("encoder."));
+  for (int i = 0; i <= 3; ++i) {                                          // :1238-1244
+    const std::string src = "down_blocks." + std::to_string(i) + ".";
+    if (starts_with(k, src.c_str())) { k = "down_blocks_" + std::to_string(i) + "." + k.substr(src.size()); break; }
+  }
+  for (int i = 0; i <= 3; ++i) {                                          // :1253-1263: EncoderDownBlock.resnets -> group .resnets
+    const std::string rp = "down_blocks_" + std::to_string(i) + ".resnets.";
+    if (starts_with(k, rp.c_str())) {
+      const std::string suffix = k.substr(rp.size());
+      if (!starts_with(suffix, "resnets.")) k = rp + "resnets." + suffix;
+      break;
+    }
+  }
+  for (int i = 0; i <= 3; ++i) {                                          // :1266-1273
+    const std::string dp = "down_blocks_" + std::to_string(i) + ".downsamplers.0.";
+    if (starts_with(k, dp.c_str())) { k = "down_blocks_" + std::to_string(i) + ".downsamplers." + k.substr(dp.size()); break; }
+  }
+  return "vae_encoder." + k;
+}
+
+// Upscaler checkpoint key -> "upscaler." + key; the fixed blur kernel is skipped (loadSpatialUpscaler,
+// Models/Upscaler/SpatialUpscaler.swift:262-300).  Conv kernels stay in the checkpoint (PyTorch) layout, repacked at finalize.
+std::string map_upscaler_key(const std::string& file_key) {
+  if (contains(file_key, "blur_down")) return "";
+  return "upscaler." + file_key;
+}
+
+// which: 1 = transformer tensors (mapTransformerKey), 2 = VAE decoder tensors (mapVAEWeights), 3 = VAE encoder tensors
+// (mapVAEEncoderWeights), 4 = latent upscaler file.  Returns how many were loaded.
 int load_safetensors(ltx_ctx* c, const char* path, int which) {
-  LTX_CHECK(path != nullptr && (which == 1 || which == 2), LTX_ERR_INVALID_ARGUMENT, "load_safetensors: bad arguments");
+  LTX_CHECK(path != nullptr && which >= 1 && which <= 4, LTX_ERR_INVALID_ARGUMENT, "load_safetensors: bad arguments");
   MappedFile f(path);
   uint64_t hlen = 0;
   memcpy(&hlen, f.base, 8);
@@ -261,11 +295,15 @@ int load_safetensors(ltx_ctx* c, const char* path, int which) {
   // keys (:624) and the VAE tensors the "vae." keys; a stand-alone file carries no such prefix and is taken whole.
   const char* want = which == 1 ? "model.diffusion_model." : "vae.";
   bool unified = false;
-  for (const auto& kv : header) unified = unified || starts_with(kv.first, want);
+  if (which != 4)
+    for (const auto& kv : header) unified = unified || starts_with(kv.first, want);
   int loaded = 0;
   for (const auto& kv : header) {
     if (unified && !starts_with(kv.first, want)) continue;
-    const std::string name = which == 1 ? map_transformer_key(kv.first) : map_vae_key(kv.first);
+    const std::string name = which == 1   ? map_transformer_key(kv.first)
+                             : which == 2 ? map_vae_key(kv.first)
+                             : which == 3 ? map_vae_encoder_key(kv.first)
+                                          : map_upscaler_key(kv.first);
     if (name.empty()) continue;
     const TensorInfo& t = kv.second;
     int dtype;

@@ -10,15 +10,16 @@ namespace ltx {
 
 namespace {
 
-__global__ void permute_conv_weight_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int O, int I) {
-  // in [O][I][27] -> out [27][O][I]
-  const int64_t n = static_cast<int64_t>(O) * I * 27;
+__global__ void permute_conv_weight_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int O, int I, int taps,
+                                           int Ou, int Ip) {
+  // in [O][I][taps] -> out [taps][Ou][Ip]: the first Ou <= O output channels, input channels zero-padded to Ip >= I
+  const int64_t n = static_cast<int64_t>(Ou) * Ip * taps;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < n;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int i = static_cast<int>(idx % I);
-    const int o = static_cast<int>((idx / I) % O);
-    const int tap = static_cast<int>(idx / (static_cast<int64_t>(I) * O));
-    out[idx] = in[(static_cast<int64_t>(o) * I + i) * 27 + tap];
+    const int i = static_cast<int>(idx % Ip);
+    const int o = static_cast<int>((idx / Ip) % Ou);
+    const int tap = static_cast<int>(idx / (static_cast<int64_t>(Ip) * Ou));
+    out[idx] = i < I ? in[(static_cast<int64_t>(o) * I + i) * taps + tap] : __float2bfloat16(0.f);
   }
 }
 
@@ -33,60 +34,86 @@ __global__ void add_vec_kernel(float* __restrict__ out, const float* __restrict_
   if (i < n) out[i] = a[i] + b[i];
 }
 
-ConvW pack_conv(ltx_ctx* c, const std::string& name, int64_t cout, int64_t cin) {
-  const DevTensor& w = get_tensor(c, name + ".conv.weight");
-  LTX_CHECK(w.dtype == LTX_BF16 && w.shape.size() == 5 && w.shape[0] == cout && w.shape[1] == cin && w.shape[2] == 3 &&
-                w.shape[3] == 3 && w.shape[4] == 3,
-            LTX_ERR_WEIGHTS, "bad shape for '" + name + ".conv.weight'");
-  const DevTensor& b = get_tensor(c, name + ".conv.bias");
-  LTX_CHECK(b.dtype == LTX_F32 && b.numel() == cout, LTX_ERR_WEIGHTS, "bad shape for '" + name + ".conv.bias'");
+}  // namespace
+
+// Repacks a conv kernel stored in the checkpoint layout (O, I, 3, 3, 3) -- or (O, I, 3, 3) for the per-frame Conv2d of the
+// upscaler -- into the implicit GEMM's [taps][Cout][Cin] bf16 matrix.  cout_use < cout keeps the leading output channels
+// (encoder conv_out: 129 -> the 128 mean channels); cin is zero-padded to a multiple of 64 (encoder conv_in: 48 -> 64).
+ConvW vae_pack_conv_keys(ltx_ctx* c, const std::string& wkey, const std::string& bkey, int64_t cout, int64_t cin, int64_t cout_use,
+                         int taps) {
+  const DevTensor& w = get_tensor(c, wkey);
+  const bool ok3 = taps == 27 && w.shape.size() == 5 && w.shape[2] == 3 && w.shape[3] == 3 && w.shape[4] == 3;
+  const bool ok2 = taps == 9 && w.shape.size() == 4 && w.shape[2] == 3 && w.shape[3] == 3;
+  LTX_CHECK(w.dtype == LTX_BF16 && (ok3 || ok2) && w.shape[0] == cout && w.shape[1] == cin && cout_use <= cout, LTX_ERR_WEIGHTS,
+            "bad shape for '" + wkey + "'");
+  const DevTensor& b = get_tensor(c, bkey);
+  LTX_CHECK(b.dtype == LTX_F32 && b.numel() == cout, LTX_ERR_WEIGHTS, "bad shape for '" + bkey + "'");
+  const int64_t cin_pad = (cin + 63) / 64 * 64;
   bf16* packed = nullptr;
-  const int64_t n = cout * cin * 27;
+  const int64_t n = cout_use * cin_pad * taps;
   LTX_CUDA(cudaMalloc(&packed, static_cast<size_t>(n) * 2));
   c->owned.push_back(packed);
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8192) blocks = 8192;
-  permute_conv_weight_kernel<<<static_cast<int>(blocks), 256, 0, c->stream>>>(reinterpret_cast<const bf16*>(w.ptr), packed,
-                                                                             static_cast<int>(cout), static_cast<int>(cin));
+  permute_conv_weight_kernel<<<static_cast<int>(blocks), 256, 0, c->stream>>>(
+      reinterpret_cast<const bf16*>(w.ptr), packed, static_cast<int>(cout), static_cast<int>(cin), taps,
+      static_cast<int>(cout_use), static_cast<int>(cin_pad));
   LTX_CUDA(cudaGetLastError());
   LTX_CUDA(cudaStreamSynchronize(c->stream));
-  auto it = c->tensors.find(name + ".conv.weight");
+  auto it = c->tensors.find(wkey);
   cudaFree(it->second.ptr);
   c->tensors.erase(it);
   ConvW r;
-  r.w = packed; r.b = reinterpret_cast<const float*>(b.ptr); r.cin = static_cast<int>(cin); r.cout = static_cast<int>(cout);
+  r.w = packed; r.b = reinterpret_cast<const float*>(b.ptr); r.cin = static_cast<int>(cin_pad); r.cout = static_cast<int>(cout_use);
+  r.taps = taps;
   return r;
 }
 
-const float* vf(ltx_ctx* c, const std::string& k, int64_t n) {
+namespace {
+
+ConvW pack_conv(ltx_ctx* c, const std::string& name, int64_t cout, int64_t cin) {
+  return vae_pack_conv_keys(c, name + ".conv.weight", name + ".conv.bias", cout, cin, cout, 27);
+}
+
+}  // namespace
+
+const float* vae_vec(ltx_ctx* c, const std::string& k, int64_t n) {
   const DevTensor& t = get_tensor(c, k);
   LTX_CHECK(t.dtype == LTX_F32 && t.numel() == n, LTX_ERR_WEIGHTS, "bad shape for '" + k + "'");
   return reinterpret_cast<const float*>(t.ptr);
 }
 
-// n_active > 1: this rank holds a temporal slab; the two time-padding frames of the conv input come from the
-// neighbouring ranks (the global first / last slab keep the replicated frame the prologue wrote).
-void conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
-          int causal, int epi_mode, float* out, const float* resid, int n_active = 1, int t_shift = 0) {
+// One convolution = padding prologue (fp32 [T,H,W,Cin] -> activated bf16 [T+2,H+2,W+2,Cin]) + implicit-GEMM kernel.
+// pad: VAE_PAD_* bits.  n_active > 1: this rank holds a temporal slab; the two time-padding frames of the conv input come
+// from the neighbouring ranks (the global first / last slab keep the replicated frame the prologue wrote).
+void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
+              int pad, int epi_mode, float* out, const float* resid, int n_active, int t_shift) {
   c->v_pad.reserve(static_cast<size_t>(T + 2) * (H + 2) * (W + 2) * w.cin * 2);
   const double vox = static_cast<double>(T) * H * W;
   {
     ProfScope ps(c, PROF_PREP, 0.0, vox * w.cin * 4.0 + static_cast<double>(T + 2) * (H + 2) * (W + 2) * w.cin * 2.0);
-    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, causal, c->stream);
+    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, w.cin, prep_mode, a, b, pad, c->stream);
   }
   if (n_active > 1) {
     const size_t frame = static_cast<size_t>(H + 2) * (W + 2) * w.cin;  // one padded frame, contiguous in v_pad
-    bf16* pad = c->v_pad.as<bf16>();
+    bf16* padv = c->v_pad.as<bf16>();
     ProfScope ps(c, PROF_COMM, 0.0, 4.0 * frame * 2.0);
-    dist_halo_exchange(c, pad + frame, pad, pad + static_cast<size_t>(T) * frame, pad + static_cast<size_t>(T + 1) * frame,
+    dist_halo_exchange(c, padv + frame, padv, padv + static_cast<size_t>(T) * frame, padv + static_cast<size_t>(T + 1) * frame,
                        frame * 2, n_active);
   }
   ConvEpi e;
   e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin; e.t_shift = t_shift;
-  ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * w.cin * w.cout * vox, vox * (w.cin * 2.0 + w.cout * 4.0) + 27.0 * w.cin * w.cout * 2.0);
-  launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream);
+  ProfScope ps(c, PROF_CONV, 2.0 * w.taps * w.cin * w.cout * vox,
+               vox * (w.cin * 2.0 + w.cout * 4.0) + static_cast<double>(w.taps) * w.cin * w.cout * 2.0);
+  launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream, w.taps);
 }
 
+namespace {
+inline const float* vf(ltx_ctx* c, const std::string& k, int64_t n) { return vae_vec(c, k, n); }
+inline void conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const float* b, const ConvW& w, int T, int H, int W,
+                 int causal, int epi_mode, float* out, const float* resid, int n_active = 1, int t_shift = 0) {
+  vae_conv(c, x, prep_mode, a, b, w, T, H, W, causal ? VAE_PAD_CAUSAL : 0, epi_mode, out, resid, n_active, t_shift);
+}
 }  // namespace
 
 void vae_finalize(ltx_ctx* c) {

@@ -52,7 +52,9 @@ bool ends_with(const std::string& s, const std::string& suf) {
 int storage_dtype(const ltx_ctx* c, const std::string& key, int ndim) {
   if (!(ends_with(key, ".weight") && ndim >= 2)) return LTX_F32;
   // fp32 mode keeps the DiT matrices in fp32; VAE conv kernels are always bf16
-  if (c->precision == 32 && key.compare(0, 4, "vae.") != 0) return LTX_F32;
+  if (c->precision == 32 && key.compare(0, 4, "vae.") != 0 && key.compare(0, 12, "vae_encoder.") != 0 &&
+      key.compare(0, 9, "upscaler.") != 0)
+    return LTX_F32;
   return LTX_BF16;
 }
 
@@ -173,6 +175,54 @@ void init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
     lin("vae.last_time_embedder.timestep_embedder.linear_1", 256, 256);
     lin("vae.last_time_embedder.timestep_embedder.linear_2", 2 * ch, 256);
     conv("vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
+  }
+  if (which & 4) {   // VideoEncoder channel plan (Models/VAE/VideoEncoder.swift:222-268)
+    auto conv = [&](const std::string& name, int64_t cout, int64_t cin) {
+      fill(c, name + ".conv.weight", {cout, cin, 3, 3, 3}, 1.0f / sqrtf(27.0f * cin), 0.f, s);
+      fill(c, name + ".conv.bias", {cout}, 0.02f, 0.f, s);
+    };
+    static const int kRes[4] = {4, 6, 6, 2}, kProd[4] = {4, 2, 8, 8};
+    int64_t ch = g.vae_encoder_base_channels > 0 ? g.vae_encoder_base_channels : 128;
+    conv("vae_encoder.conv_in", ch, 48);
+    for (int i = 0; i < 4; ++i) {
+      const std::string blk = "vae_encoder.down_blocks_" + std::to_string(i);
+      for (int j = 0; j < kRes[i]; ++j) {
+        conv(blk + ".resnets.resnets." + std::to_string(j) + ".conv1", ch, ch);
+        conv(blk + ".resnets.resnets." + std::to_string(j) + ".conv2", ch, ch);
+      }
+      conv(blk + ".downsamplers.conv", 2 * ch / kProd[i], ch);
+      ch *= 2;
+    }
+    for (int j = 0; j < 2; ++j) {
+      conv("vae_encoder.mid_block.resnets." + std::to_string(j) + ".conv1", ch, ch);
+      conv("vae_encoder.mid_block.resnets." + std::to_string(j) + ".conv2", ch, ch);
+    }
+    conv("vae_encoder.conv_out", g.vae_latent_channels + 1, ch);
+  }
+  if (which & 8) {   // SpatialUpscaler (Models/Upscaler/SpatialUpscaler.swift:181-213), checkpoint layout
+    const int64_t mid = g.upscaler_mid_channels > 0 ? g.upscaler_mid_channels : 1024, cin = g.vae_latent_channels;
+    const int nb = g.upscaler_blocks > 0 ? g.upscaler_blocks : 4;
+    auto conv3 = [&](const std::string& name, int64_t cout, int64_t ci) {
+      fill(c, name + ".weight", {cout, ci, 3, 3, 3}, 1.0f / sqrtf(27.0f * ci), 0.f, s);
+      fill(c, name + ".bias", {cout}, 0.02f, 0.f, s);
+    };
+    auto norm = [&](const std::string& name) {
+      fill(c, name + ".weight", {mid}, 0.1f, 1.0f, s);
+      fill(c, name + ".bias", {mid}, 0.1f, 0.f, s);
+    };
+    conv3("upscaler.initial_conv", mid, cin);
+    norm("upscaler.initial_norm");
+    for (const char* grp : {"upscaler.res_blocks.", "upscaler.post_upsample_res_blocks."})
+      for (int i = 0; i < nb; ++i) {
+        const std::string b = std::string(grp) + std::to_string(i);
+        conv3(b + ".conv1", mid, mid);
+        norm(b + ".norm1");
+        conv3(b + ".conv2", mid, mid);
+        norm(b + ".norm2");
+      }
+    fill(c, "upscaler.upsampler.conv.weight", {4 * mid, mid, 3, 3}, 1.0f / sqrtf(9.0f * mid), 0.f, s);
+    fill(c, "upscaler.upsampler.conv.bias", {4 * mid}, 0.02f, 0.f, s);
+    conv3("upscaler.final_conv", cin, mid);
   }
   LTX_CUDA(cudaStreamSynchronize(c->stream));
 }

@@ -52,3 +52,24 @@ def denoise_resident(ctx: LtxContext, noise: np.ndarray, context, mask, sigmas: 
         ctx.denoise_step(float(sigmas[step]), float(sigmas[step + 1]), step, cfg_scale, guidance_rescale, stg_scale,
                          tuple(stg_blocks) if stg_scale > 0 else (), ge_gamma)
     return ctx.denoise_get_latent()[None] if fetch else None
+
+
+def generate_two_stage_resident(ctx: LtxContext, noise1: np.ndarray, noise2: np.ndarray, context, mask, sigmas1: Sequence[float],
+                                sigmas2: Sequence[float], adain_factor: float = 1.0, image_latent_half=None,
+                                image_latent_full=None) -> np.ndarray:
+    """generateVideoTwoStage (Pipeline/LTXPipeline.swift:2420-2720), denoising + latent glue only, device-resident:
+    stage 1 at half resolution (distilled schedule) -> upscale 2x + AdaIN + re-noise with sigmas2[0] (:2594-2647) ->
+    stage 2 refinement.  noise1 [1,C,F,H,W], noise2 [1,C,F,2H,2W].  The optional image latents condition frame 0 (I2V)."""
+    _, C, F, H, W = noise1.shape
+    i2v = image_latent_half is not None
+    ctx.denoise_begin(noise1[0], (F, H, W), float(sigmas1[0]), context, mask)
+    if i2v:
+        ctx.denoise_set_frame0(image_latent_half)
+    for i in range(len(sigmas1) - 1):
+        ctx.denoise_step(float(sigmas1[i]), float(sigmas1[i + 1]), i, i2v_frame0_conditioned=i2v)
+    ctx.denoise_upscale_stage(noise2[0], float(sigmas2[0]), adain_factor)
+    if i2v:
+        ctx.denoise_set_frame0(image_latent_full)
+    for i in range(len(sigmas2) - 1):
+        ctx.denoise_step(float(sigmas2[i]), float(sigmas2[i + 1]), i, i2v_frame0_conditioned=i2v)
+    return ctx.denoise_get_latent()[None]

@@ -28,3 +28,20 @@ def decode_video(latent, decoder: VideoDecoder, timestep: Optional[float] = None
     if temporal_tile_size > 0 and frames_lat > temporal_tile_size:
         raise LtxError(5, "temporal tiling (overlap-blend approximation) is not implemented; decode untiled")
     return decoder.ctx.vae_decode(lat, timestep, decode_noise, decoder.causal)
+
+
+class VideoEncoder:
+    """Handle on the encoder weights held by an LtxContext (VideoEncoder(causal: true), Models/VAE/VideoEncoder.swift:211)."""
+
+    def __init__(self, ctx: LtxContext):
+        self.ctx = ctx
+
+    def __call__(self, pixels) -> np.ndarray:
+        """VideoEncoder.callAsFunction (:270-312): [1,3,T,H,W] -> latent mean [1,128,T',H/32,W/32] (not normalised)."""
+        return self.ctx.vae_encode(pixels, normalize=False)[None]
+
+
+def encode_image(pixels, encoder: VideoEncoder) -> np.ndarray:
+    """encodeImage (Pipeline/LTXPipeline.swift:1902-1932) after the image has been loaded and resized: encode and
+    normalise with the decoder's per-channel statistics.  pixels [1,3,1,H,W] in [-1,1] -> [1,128,1,H/32,W/32]."""
+    return encoder.ctx.vae_encode(pixels, normalize=True)[None]

@@ -609,6 +609,197 @@ def decode_video(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float] = 
 
 
 # ----------------------------------------------------------------------------------------------
+# video VAE encoder (V/VideoEncoder.swift) -- SURVEY 8f-4: image / video -> latent for image-to-video conditioning
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class EncoderConfig:
+    """Channel plan of VideoEncoder.init (V/VideoEncoder.swift:222-268): conv_in 48->c0, four down blocks
+    (resnets, space-to-depth factor, output channels), mid block, conv_out -> latent_channels + 1."""
+    base_channels: int = 128
+    resnets: Tuple[int, ...] = (4, 6, 6, 2)
+    factors: Tuple[Tuple[int, int, int], ...] = ((1, 2, 2), (2, 1, 1), (2, 2, 2), (2, 2, 2))
+    mid_resnets: int = 2
+    latent_channels: int = 128
+    causal: bool = True
+
+    @property
+    def stage_channels(self) -> List[int]:
+        return [self.base_channels * (2 ** i) for i in range(5)]
+
+
+def make_encoder_weights(cfg: EncoderConfig, seed: int = 0) -> Dict[str, Tensor]:
+    """Random-init encoder weights under the post-mapping names of mapVAEEncoderWeights
+    (U/ModelDownloader.swift:1224-1280)."""
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, Tensor] = {}
+
+    def conv(name: str, cout: int, cin: int):
+        w[name + ".conv.weight"] = torch.randn(cout, cin, 3, 3, 3, generator=g) / math.sqrt(27 * cin)
+        w[name + ".conv.bias"] = torch.randn(cout, generator=g) * 0.02
+
+    ch = cfg.stage_channels
+    conv("conv_in", ch[0], 48)
+    for i in range(4):
+        for j in range(cfg.resnets[i]):
+            conv(f"down_blocks_{i}.resnets.resnets.{j}.conv1", ch[i], ch[i])
+            conv(f"down_blocks_{i}.resnets.resnets.{j}.conv2", ch[i], ch[i])
+        ft, fh, fw = cfg.factors[i]
+        conv(f"down_blocks_{i}.downsamplers.conv", ch[i + 1] // (ft * fh * fw), ch[i])
+    for j in range(cfg.mid_resnets):
+        conv(f"mid_block.resnets.{j}.conv1", ch[4], ch[4])
+        conv(f"mid_block.resnets.{j}.conv2", ch[4], ch[4])
+    conv("conv_out", cfg.latent_channels + 1, ch[4])
+    return w
+
+
+def encoder_patchify(x: Tensor) -> Tensor:                      # V/VideoEncoder.swift:13-32 (pW before pH)
+    B, C, T, H, W = x.shape
+    o = x.reshape(B, C, T, H // 4, 4, W // 4, 4).permute(0, 1, 6, 4, 2, 3, 5)
+    return o.reshape(B, C * 16, T, H // 4, W // 4)
+
+
+def space_to_depth(x: Tensor, factor: Tuple[int, int, int]) -> Tensor:   # :38-66 (front-pad T with the first frame)
+    ft, fh, fw = factor
+    B, C, T, H, W = x.shape
+    if T % ft != 0:
+        pad = ft - T % ft
+        x = torch.cat([x[:, :, :1].expand(B, C, pad, H, W), x], dim=2)
+        T = x.shape[2]
+    o = x.reshape(B, C, T // ft, ft, H // fh, fh, W // fw, fw).permute(0, 1, 3, 5, 7, 2, 4, 6)
+    return o.reshape(B, C * ft * fh * fw, T // ft, H // fh, W // fw)
+
+
+def encoder_resblock(w, prefix: str, x: Tensor, causal: bool) -> Tensor:       # :72-101
+    h = silu(pixel_norm(x))
+    h = conv3d_full(h, w[prefix + ".conv1.conv.weight"], w[prefix + ".conv1.conv.bias"], causal, "zeros")
+    h = silu(pixel_norm(h))
+    h = conv3d_full(h, w[prefix + ".conv2.conv.weight"], w[prefix + ".conv2.conv.bias"], causal, "zeros")
+    return h + x
+
+
+def encoder_downsample(w, prefix: str, x: Tensor, factor, out_channels: int, causal: bool) -> Tensor:   # :127-166
+    main = space_to_depth(conv3d_full(x, w[prefix + ".conv.conv.weight"], w[prefix + ".conv.conv.bias"], causal, "zeros"), factor)
+    r = space_to_depth(x, factor)
+    B, Cr, T2, H2, W2 = r.shape
+    r = r.reshape(B, out_channels, Cr // out_channels, T2, H2, W2).mean(dim=2)
+    return main + r
+
+
+def vae_encode(w, cfg: EncoderConfig, pixels: Tensor, dtype=torch.float32, return_stages: bool = False):
+    """VideoEncoder.callAsFunction (V/VideoEncoder.swift:270-312): pixels [B,3,T,H,W] -> latent mean
+    [B,128,T',H/32,W/32] (the log-variance channel is dropped)."""
+    w = {k: v.to(dtype) for k, v in w.items()}
+    ch = cfg.stage_channels
+    h = encoder_patchify(pixels.to(dtype))
+    h = conv3d_full(h, w["conv_in.conv.weight"], w["conv_in.conv.bias"], cfg.causal, "zeros")
+    stages = [h]
+    for i in range(4):
+        for j in range(cfg.resnets[i]):
+            h = encoder_resblock(w, f"down_blocks_{i}.resnets.resnets.{j}", h, cfg.causal)
+        h = encoder_downsample(w, f"down_blocks_{i}.downsamplers", h, cfg.factors[i], ch[i + 1], cfg.causal)
+        stages.append(h)
+    for j in range(cfg.mid_resnets):
+        h = encoder_resblock(w, f"mid_block.resnets.{j}", h, cfg.causal)
+    h = silu(pixel_norm(h))
+    h = conv3d_full(h, w["conv_out.conv.weight"], w["conv_out.conv.bias"], cfg.causal, "zeros")
+    h = h[:, :cfg.latent_channels]
+    return (h, stages) if return_stages else h
+
+
+def encode_image_latent(w, cfg: EncoderConfig, pixels: Tensor, mean: Tensor, std: Tensor) -> Tensor:
+    """encodeImage (P/LTXPipeline.swift:1902-1932): encode, then normalise with the decoder's per-channel statistics."""
+    z = vae_encode(w, cfg, pixels)
+    return (z - mean.view(1, -1, 1, 1, 1)) / std.view(1, -1, 1, 1, 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# latent spatial upscaler + AdaIN + re-noise (Models/Upscaler/SpatialUpscaler.swift, P/LatentUtils.swift:201-227,
+# P/LTXPipeline.swift:2594-2647) -- SURVEY 8f-3: the glue between the two stages of the two-stage pipeline
+# ----------------------------------------------------------------------------------------------
+def make_upscaler_weights(mid: int = 1024, in_ch: int = 128, blocks: int = 4, seed: int = 0) -> Dict[str, Tensor]:
+    """Random-init SpatialUpscaler weights in the checkpoint (PyTorch) layout the reference's loader reads
+    (SpatialUpscaler.swift:262-300): Conv3d (O,I,3,3,3), Conv2d (O,I,3,3)."""
+    g = torch.Generator().manual_seed(seed)
+    w: Dict[str, Tensor] = {}
+
+    def conv3(name, cout, cin):
+        w[name + ".weight"] = torch.randn(cout, cin, 3, 3, 3, generator=g) / math.sqrt(27 * cin)
+        w[name + ".bias"] = torch.randn(cout, generator=g) * 0.02
+
+    def norm(name, c):
+        w[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        w[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+
+    conv3("initial_conv", mid, in_ch)
+    norm("initial_norm", mid)
+    for grp in ("res_blocks", "post_upsample_res_blocks"):
+        for i in range(blocks):
+            conv3(f"{grp}.{i}.conv1", mid, mid)
+            norm(f"{grp}.{i}.norm1", mid)
+            conv3(f"{grp}.{i}.conv2", mid, mid)
+            norm(f"{grp}.{i}.norm2", mid)
+    w["upsampler.conv.weight"] = torch.randn(4 * mid, mid, 3, 3, generator=g) / math.sqrt(9 * mid)
+    w["upsampler.conv.bias"] = torch.randn(4 * mid, generator=g) * 0.02
+    conv3("final_conv", in_ch, mid)
+    return w
+
+
+def _group_norm(x: Tensor, weight: Tensor, bias: Tensor, groups: int = 32, eps: float = 1e-5) -> Tensor:
+    """UpscalerGroupNorm3D (SpatialUpscaler.swift:12-58): statistics over (D,H,W, C/groups), population variance."""
+    B, C = x.shape[:2]
+    y = x.reshape(B, groups, -1)
+    mu = y.mean(dim=2, keepdim=True)
+    var = y.var(dim=2, unbiased=False, keepdim=True)
+    y = ((y - mu) / torch.sqrt(var + eps)).reshape(x.shape)
+    return y * weight.view(1, C, 1, 1, 1) + bias.view(1, C, 1, 1, 1)
+
+
+def _upscaler_resblock(w, p: str, x: Tensor) -> Tensor:           # SpatialUpscaler.swift:62-107
+    h = torch.nn.functional.conv3d(x, w[p + ".conv1.weight"], w[p + ".conv1.bias"], padding=1)
+    h = silu(_group_norm(h, w[p + ".norm1.weight"], w[p + ".norm1.bias"]))
+    h = torch.nn.functional.conv3d(h, w[p + ".conv2.weight"], w[p + ".conv2.bias"], padding=1)
+    h = _group_norm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"])
+    return silu(h + x)
+
+
+def spatial_upscaler(w, x: Tensor, blocks: int = 4, dtype=torch.float32) -> Tensor:
+    """SpatialUpscaler.callAsFunction (SpatialUpscaler.swift:215-258): [B,128,F,H,W] -> [B,128,F,2H,2W].  Conv3d zero
+    padding 1; per-frame Conv2d + PixelShuffle(2) (:111-163: channel = c*4 + i*2 + j -> (2h+i, 2w+j))."""
+    w = {k: v.to(dtype) for k, v in w.items()}
+    h = torch.nn.functional.conv3d(x.to(dtype), w["initial_conv.weight"], w["initial_conv.bias"], padding=1)
+    h = silu(_group_norm(h, w["initial_norm.weight"], w["initial_norm.bias"]))
+    for i in range(blocks):
+        h = _upscaler_resblock(w, f"res_blocks.{i}", h)
+    B, C, D, H, W = h.shape
+    fr = h.permute(0, 2, 1, 3, 4).reshape(B * D, C, H, W)
+    fr = torch.nn.functional.conv2d(fr, w["upsampler.conv.weight"], w["upsampler.conv.bias"], padding=1)
+    fr = torch.nn.functional.pixel_shuffle(fr, 2)
+    h = fr.reshape(B, D, C, 2 * H, 2 * W).permute(0, 2, 1, 3, 4)
+    for i in range(blocks):
+        h = _upscaler_resblock(w, f"post_upsample_res_blocks.{i}", h)
+    return torch.nn.functional.conv3d(h, w["final_conv.weight"], w["final_conv.bias"], padding=1)
+
+
+def upsample_latents(w, latent: Tensor, mean: Tensor, std: Tensor, blocks: int = 4) -> Tensor:
+    """upsampleLatents (SpatialUpscaler.swift:360-383) / P/LTXPipeline.swift:2604-2619: denormalise, upscale, renormalise."""
+    m, s = mean.view(1, -1, 1, 1, 1), std.view(1, -1, 1, 1, 1)
+    return (spatial_upscaler(w, latent * s + m, blocks) - m) / s
+
+
+def adain_filter_latent(latent: Tensor, reference: Tensor, factor: float = 1.0) -> Tensor:   # P/LatentUtils.swift:201-227
+    if factor <= 0:
+        return latent
+    lm, ls = latent.mean(dim=(2, 3, 4), keepdim=True), latent.var(dim=(2, 3, 4), unbiased=False, keepdim=True).sqrt()
+    rm, rs = reference.mean(dim=(2, 3, 4), keepdim=True), reference.var(dim=(2, 3, 4), unbiased=False, keepdim=True).sqrt()
+    out = (latent - lm) / (ls + 1e-8) * rs + rm
+    return out if factor >= 1.0 else factor * out + (1.0 - factor) * latent
+
+
+def renoise(latent: Tensor, noise: Tensor, noise_scale: float) -> Tensor:    # P/LTXPipeline.swift:2644-2647
+    return noise_scale * noise + (1.0 - noise_scale) * latent
+
+
+# ----------------------------------------------------------------------------------------------
 # metrics used by the parity tests
 # ----------------------------------------------------------------------------------------------
 def rel_l2(a: Tensor, b: Tensor) -> float:

@@ -182,3 +182,31 @@ def test_load_safetensors_vae_matches_direct_load(tmp_path):
     fa, fb = a.vae_decode(lat), b.vae_decode(lat)
     assert np.array_equal(fa, fb)
     a.close(); b.close()
+
+
+def test_vae_encoder_and_upscaler_key_mapping():
+    """mapVAEEncoderWeights (Utils/ModelDownloader.swift:1224-1280) and loadSpatialUpscaler's key handling
+    (Models/Upscaler/SpatialUpscaler.swift:262-300)."""
+    enc = {
+        "encoder.conv_in.conv.weight": "vae_encoder.conv_in.conv.weight",
+        "encoder.down_blocks.0.resnets.3.conv1.conv.weight": "vae_encoder.down_blocks_0.resnets.resnets.3.conv1.conv.weight",
+        "encoder.down_blocks.2.downsamplers.0.conv.conv.bias": "vae_encoder.down_blocks_2.downsamplers.conv.conv.bias",
+        "encoder.mid_block.resnets.1.conv2.conv.weight": "vae_encoder.mid_block.resnets.1.conv2.conv.weight",
+        "encoder.conv_out.conv.bias": "vae_encoder.conv_out.conv.bias",
+        "vae.encoder.down_blocks.3.resnets.0.conv2.conv.bias": "vae_encoder.down_blocks_3.resnets.resnets.0.conv2.conv.bias",
+    }
+    for k, want in enc.items():
+        assert mk(3, k) == want, k
+    for k in ("decoder.conv_in.conv.weight", "latents_mean", "per_channel_statistics.mean-of-means"):
+        assert mk(3, k) is None, k
+    assert mk(2, "encoder.conv_in.conv.weight") is None          # the decoder loader still skips encoder tensors
+    ups = {
+        "initial_conv.weight": "upscaler.initial_conv.weight",
+        "res_blocks.2.norm1.bias": "upscaler.res_blocks.2.norm1.bias",
+        "upsampler.conv.weight": "upscaler.upsampler.conv.weight",
+        "post_upsample_res_blocks.0.conv2.weight": "upscaler.post_upsample_res_blocks.0.conv2.weight",
+        "final_conv.bias": "upscaler.final_conv.bias",
+    }
+    for k, want in ups.items():
+        assert mk(4, k) == want, k
+    assert mk(4, "upsampler.blur_down.kernel") is None

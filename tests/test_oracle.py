@@ -139,3 +139,51 @@ def test_vae_oracle_golden():
     # frame count formula and the causal switch
     cfg_c = O.VAEConfig(base_channels=512, blocks_per_stage=1, causal=True)
     assert O.psnr(O.decode_video(w, cfg_c, torch.from_numpy(g["latent"])), fr) < 50
+
+
+def test_encoder_shapes_and_space_to_depth():
+    """V/VideoEncoder.swift: 8k+1 frames -> k+1 latent frames, /32 spatially; space-to-depth front-pads odd T with frame 0
+    and is the inverse of the decoder's depth-to-space on even T."""
+    ecfg = O.EncoderConfig(base_channels=64)
+    w = O.make_encoder_weights(ecfg, 1)
+    assert w["conv_in.conv.weight"].shape == (64, 48, 3, 3, 3) and w["conv_out.conv.weight"].shape[0] == 129
+    assert w["down_blocks_0.downsamplers.conv.conv.weight"].shape[0] == 128 // 4
+    assert w["down_blocks_1.downsamplers.conv.conv.weight"].shape[0] == 256 // 2
+    for T, Tl in ((1, 1), (9, 2), (17, 3)):
+        z = O.vae_encode(w, ecfg, torch.randn(1, 3, T, 64, 64, generator=torch.Generator().manual_seed(T)))
+        assert z.shape == (1, 128, Tl, 2, 2)
+    x = torch.randn(1, 16, 4, 6, 8)
+    assert torch.equal(O.depth_to_space(O.space_to_depth(x, (2, 2, 2)), 16), x)
+    odd = torch.randn(1, 4, 3, 2, 2)
+    s = O.space_to_depth(odd, (2, 1, 1))
+    assert s.shape == (1, 8, 2, 2, 2)
+    assert torch.equal(s[:, 0::2, 0], odd[:, :, 0]) and torch.equal(s[:, 1::2, 0], odd[:, :, 0])   # (pad, frame 0)
+    assert torch.equal(s[:, 0::2, 1], odd[:, :, 1]) and torch.equal(s[:, 1::2, 1], odd[:, :, 2])
+    # patchify puts pW before pH in the channel index (:13-32)
+    img = torch.arange(3 * 8 * 8, dtype=torch.float32).view(1, 3, 1, 8, 8)
+    p = O.encoder_patchify(img)
+    assert p.shape == (1, 48, 1, 2, 2)
+    c, pw, ph = 1, 2, 3
+    assert p[0, (c * 4 + pw) * 4 + ph, 0, 1, 0] == img[0, c, 0, 4 + ph, pw]
+
+
+def test_upscaler_and_adain_properties():
+    """SpatialUpscaler doubles H and W only; GroupNorm statistics span (D,H,W,C/32); AdaIN transplants per-channel
+    mean / population std (P/LatentUtils.swift:201-227); re-noise is the stage-2 mix (:2644-2647)."""
+    uw = O.make_upscaler_weights(mid=64, blocks=1, seed=2)
+    lat = torch.randn(1, 128, 3, 4, 6, generator=torch.Generator().manual_seed(3))
+    up = O.spatial_upscaler(uw, lat, 1)
+    assert up.shape == (1, 128, 3, 8, 12)
+    x = torch.randn(1, 64, 2, 3, 3)
+    y = O._group_norm(x, torch.ones(64), torch.zeros(64))
+    g = y.reshape(1, 32, -1)
+    assert g.mean(-1).abs().max() < 1e-5 and (g.var(-1, unbiased=False) - 1).abs().max() < 1e-3
+    ref = torch.randn(1, 128, 3, 2, 3) * 0.5 + 1.0
+    a = O.adain_filter_latent(up, ref)
+    assert torch.allclose(a.mean((2, 3, 4)), ref.mean((2, 3, 4)), atol=1e-5)
+    assert torch.allclose(a.var((2, 3, 4), unbiased=False).sqrt(), ref.var((2, 3, 4), unbiased=False).sqrt(), atol=1e-4)
+    assert torch.equal(O.adain_filter_latent(up, ref, 0.0), up)
+    half = O.adain_filter_latent(up, ref, 0.5)
+    assert torch.allclose(half, 0.5 * a + 0.5 * up, atol=1e-6)
+    n = torch.randn_like(up)
+    assert torch.allclose(O.renoise(up, n, 0.909375), 0.909375 * n + (1 - 0.909375) * up)
