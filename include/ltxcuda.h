@@ -271,6 +271,10 @@ int ltx_op_gemm_q(ltx_ctx* ctx, const void* A, const void* q, const float* scale
  * columns [b*ldvb, b*ldvb + Nk), ldvb % 8 == 0), all bf16. */
 int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
                      int B, int H, int Nq, int Nk, float scale);
+/* the same with head_dim 128 or 64 (64: the audio / cross-modal attentions of the dual block, 32 heads x 64); Q, K [.., H*head_dim],
+ * Vt [H*head_dim, B*ldvb] */
+int ltx_op_attention_hd(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
+                        int B, int H, int head_dim, int Nq, int Nk, float scale);
 int ltx_op_rmsnorm_mod(ltx_ctx* ctx, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm);
 int ltx_op_qknorm_rope(ltx_ctx* ctx, void* x_bf16, int M, int D, const float* w, const float* cos_tab, const float* sin_tab,

@@ -694,6 +694,18 @@ int ltx_op_attention(ltx_ctx* c, const void* Q, const void* K, const void* Vt, i
   });
 }
 
+int ltx_op_attention_hd(ltx_ctx* c, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
+                        int B, int H, int head_dim, int Nq, int Nk, float scale) {
+  return guarded(c, [&] {
+    LTX_CHECK(head_dim == 128 || head_dim == 64, LTX_ERR_UNSUPPORTED, "head_dim must be 128 or 64");
+    const int D = H * head_dim;
+    launch_attention(reinterpret_cast<const bf16*>(Q), D, reinterpret_cast<const bf16*>(K), D,
+                     reinterpret_cast<const bf16*>(Vt), ldvb, key_bias, reinterpret_cast<bf16*>(O), D, B, H, Nq, Nk, D, scale,
+                     c->stream);
+    c->launches++;
+  });
+}
+
 int ltx_op_rmsnorm_mod(ltx_ctx* c, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm) {
   return guarded(c, [&] {

@@ -62,6 +62,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel aborts with an error) instead of hanging the GPU.
+// Non-blocking test (mbarrier.test_wait): for polling loops that watch several barriers -- try_wait may suspend the thread
+// for a hardware-defined time when the phase is not complete, which delays the other conditions of the loop.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -145,6 +160,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// The same with the A operand read from tensor memory ("TS" form): a_tmem addresses a [128 lanes x 8 columns] block holding,
+// per lane (= row of A), 16 bf16 of the K-slice packed two per 32-bit column (low half = lower k).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  const uint32_t zero = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum), "r"(zero)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05 op of this thread has completed.
