@@ -61,6 +61,11 @@ typedef struct {
   int32_t vae_encoder_base_channels; /* 128 */
   int32_t upscaler_mid_channels;     /* 1024 */
   int32_t upscaler_blocks;           /* 4 */
+  /* audio stream of the dual audio/video transformer (Configuration/LTXConfig.swift:134-173) */
+  int32_t audio_num_heads;           /* 32 */
+  int32_t audio_head_dim;            /* 64 */
+  int32_t audio_in_channels;         /* 128 (= audio_out_channels) */
+  int32_t audio_max_pos;             /* 20 */
 } ltx_config;
 
 void ltx_config_default(ltx_config* cfg);
@@ -85,7 +90,9 @@ int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dt
  * 2 = VAE decoder (stand-alone VAE file or the "vae." tensors of a unified checkpoint; encoder tensors are skipped),
  * 3 = VAE encoder (the "encoder." tensors of the same files, mapVAEEncoderWeights :1224-1280, names prefixed "vae_encoder."),
  * 4 = latent upscaler file (loadSpatialUpscaler, Models/Upscaler/SpatialUpscaler.swift:262-300, names prefixed "upscaler.";
- * conv kernels are taken in the checkpoint's (O, I, kD, kH, kW) layout).
+ * conv kernels are taken in the checkpoint's (O, I, kD, kH, kW) layout),
+ * 5 = dual audio/video transformer (loadTransformerWeights(includeAudio: true), :605-639: the audio_*, av_ca_* and
+ * cross-modal tensors are kept under their own names).
  * F32 / BF16 / F16 tensors are accepted.  n_loaded (nullable) receives the number of tensors taken.  Follow with
  * ltx_finalize_weights.  ltx_map_weight_key exposes the name mapping alone (no context, no GPU): it writes the mapped name,
  * or an empty string for a tensor the loader skips, into out[cap]. */
@@ -98,7 +105,8 @@ int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap);
  * in).  Must be called before the DiT weights are loaded; single GPU, no quantisation; the VAE is unaffected. */
 int ltx_set_precision(ltx_ctx* ctx, int bits);
 /* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
- * which: bit mask, 1 = DiT, 2 = VAE decoder, 4 = VAE encoder, 8 = latent upscaler. */
+ * which: bit mask, 1 = DiT, 2 = VAE decoder, 4 = VAE encoder, 8 = latent upscaler, 16 = the audio / cross-modal tensors of the
+ * dual audio/video transformer (use 17 for the whole LTX2Transformer). */
 int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);
 /* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16; 8 / 4 replace every GEMM weight of the DiT by
  * per-64-group affine codes (w ~= s*q + beta) consumed by the dequant-fused GEMM -- the counterpart of
@@ -134,6 +142,21 @@ int ltx_dit_forward(ltx_ctx* ctx, const void* latent, ltx_dtype latent_dtype, co
 int ltx_dit_forward_dev(ltx_ctx* ctx, const void* latent, ltx_dtype latent_dtype, const void* context,
                         ltx_dtype context_dtype, const float* timesteps, int ts_per_token, const int32_t* mask, int B, int N,
                         int S, int F, int H, int W, const ltx_dit_flags* flags, float* out_velocity);
+/* LTX2Transformer.callAsFunction(videoLatent:audioLatent:videoContext:audioContext:videoTimesteps:audioTimesteps:
+ * videoContextMask:audioContextMask:videoLatentShape:audioNumFrames:) (Models/Transformer/LTX2Transformer.swift:240-392): the dual
+ * audio/video ("19 B") model -- per block video and audio self-attention, text cross-attention on both streams, audio->video
+ * and video->audio cross-modal attention, both feed-forwards (Models/Transformer/LTX2TransformerBlock.swift:174-297).
+ *   video_latent [1, N, in_channels], audio_latent [1, Ta, audio_in_channels] (bf16 or fp32), contexts [1, S, caption_channels],
+ *   one sigma per stream, masks [1, S] int32 or NULL; out_video [1, N, out_channels], out_audio [1, Ta, audio_in_channels] fp32.
+ * context_key != 0 caches the text K / V of both streams.  This version: B = 1, bf16 weights, one GPU. */
+int ltx_av_forward(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent, ltx_dtype audio_dtype,
+                   const void* video_context, const void* audio_context, ltx_dtype context_dtype, float video_sigma,
+                   float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N, int Ta, int S, int F, int H,
+                   int W, uint64_t context_key, float* out_video, float* out_audio);
+int ltx_av_forward_dev(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                       ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                       const float* video_sigma, const float* audio_sigma, const int32_t* video_mask, const int32_t* audio_mask,
+                       int N, int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio);
 /* LTXTransformer.clearRoPECache (:202) + drops the cached text K/V. */
 int ltx_dit_clear_caches(ltx_ctx* ctx);
 

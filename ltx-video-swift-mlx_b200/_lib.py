@@ -19,7 +19,8 @@ class LtxConfig(C.Structure):
         ("max_pos", C.c_int32 * 3), ("timestep_scale_multiplier", C.c_float), ("norm_eps", C.c_float),
         ("vae_latent_channels", C.c_int32), ("vae_base_channels", C.c_int32), ("vae_blocks_per_stage", C.c_int32),
         ("vae_patch_size", C.c_int32), ("vae_encoder_base_channels", C.c_int32), ("upscaler_mid_channels", C.c_int32),
-        ("upscaler_blocks", C.c_int32),
+        ("upscaler_blocks", C.c_int32), ("audio_num_heads", C.c_int32), ("audio_head_dim", C.c_int32),
+        ("audio_in_channels", C.c_int32), ("audio_max_pos", C.c_int32),
     ]
 
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "ltx_finalize_weights": (_I, [_P, _I, _I]),
     "ltx_dit_forward": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(LtxDitFlags), _P]),
     "ltx_dit_forward_dev": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(LtxDitFlags), _P]),
+    "ltx_av_forward": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
+    "ltx_av_forward_dev": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
     "ltx_dit_clear_caches": (_I, [_P]),
     "ltx_guided_euler_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _SZ, _F, _F, _F, _F, _F, _F]),
     "ltx_guided_euler_step_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _SZ, _F, _F, _F, _F, _F, _F]),

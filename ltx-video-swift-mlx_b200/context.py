@@ -33,6 +33,10 @@ class LTXTransformerConfig:
     vae_encoder_base_channels: int = 128     # VideoEncoder channel plan (random init only)
     upscaler_mid_channels: int = 1024        # SpatialUpscaler(midChannels:) (random init only)
     upscaler_blocks: int = 4
+    audio_num_attention_heads: int = 32      # audio stream of LTX2Transformer (Configuration/LTXConfig.swift:134-173)
+    audio_attention_head_dim: int = 64
+    audio_in_channels: int = 128
+    audio_max_pos: int = 20
 
     @property
     def inner_dim(self) -> int:
@@ -50,6 +54,8 @@ class LTXTransformerConfig:
         c.vae_blocks_per_stage, c.vae_patch_size = self.vae_blocks_per_stage, self.vae_patch_size
         c.vae_encoder_base_channels, c.upscaler_mid_channels = self.vae_encoder_base_channels, self.upscaler_mid_channels
         c.upscaler_blocks = self.upscaler_blocks
+        c.audio_num_heads, c.audio_head_dim = self.audio_num_attention_heads, self.audio_attention_head_dim
+        c.audio_in_channels, c.audio_max_pos = self.audio_in_channels, self.audio_max_pos
         return c
 
 
@@ -225,6 +231,25 @@ class LtxContext:
         self._check(self.lib.ltx_dit_forward_dev(self.handle, latent_ptr, latent_dtype, context_ptr, context_dtype, ts_ptr, 0,
                                                  mask_ptr, B, N, S, F, H, W,
                                                  C.byref(flags) if flags is not None else None, out_ptr))
+
+    def av_forward(self, video_latent, audio_latent, video_context, audio_context, video_sigma: float, audio_sigma: float,
+                   fhw: Tuple[int, int, int], video_mask=None, audio_mask=None, context_key: int = 0):
+        """LTX2Transformer.callAsFunction: video_latent [1,N,C], audio_latent [1,Ta,Ca], contexts [1,S,Cc] ->
+        (video velocity [1,N,C], audio velocity [1,Ta,Ca]) fp32."""
+        vc, ac, cc = _dtype_code(video_latent), _dtype_code(audio_latent), _dtype_code(video_context)
+        assert _dtype_code(audio_context) == cc, "both contexts must have the same dtype"
+        vl, al, vx, axx = _host(video_latent), _host(audio_latent), _host(video_context), _host(audio_context)
+        assert vl.shape[0] == 1 and al.shape[0] == 1, "the dual model takes B = 1"
+        N, Ta, S = vl.shape[1], al.shape[1], vx.shape[1]
+        vm = None if video_mask is None else _host(video_mask, np.int32)
+        am = None if audio_mask is None else _host(audio_mask, np.int32)
+        ov = np.empty((1, N, self.config.out_channels), dtype=np.float32)
+        oa = np.empty((1, Ta, self.config.audio_in_channels), dtype=np.float32)
+        F, H, W = fhw
+        self._check(self.lib.ltx_av_forward(self.handle, _ptr(vl), vc, _ptr(al), ac, _ptr(vx), _ptr(axx), cc, float(video_sigma),
+                                            float(audio_sigma), _ptr(vm), _ptr(am), N, Ta, S, F, H, W, int(context_key),
+                                            _ptr(ov), _ptr(oa)))
+        return ov, oa
 
     def clear_caches(self):
         self._check(self.lib.ltx_dit_clear_caches(self.handle))

@@ -61,6 +61,10 @@ void ltx_config_default(ltx_config* cfg) {
   cfg->vae_encoder_base_channels = 128;
   cfg->upscaler_mid_channels = 1024;
   cfg->upscaler_blocks = 4;
+  cfg->audio_num_heads = 32;
+  cfg->audio_head_dim = 64;
+  cfg->audio_in_channels = 128;
+  cfg->audio_max_pos = 20;
 }
 
 int ltx_ctx_create(const ltx_config* cfg, int device, ltx_ctx** out) {
@@ -108,9 +112,10 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
                     &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
                     &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
-                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref};
+                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7]};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
+  for (auto& t : c->av.text) { t.k.release(); t.vt.release(); t.bias.release(); }
   cudaStreamDestroy(c->stream);
   delete c;
   return LTX_OK;
@@ -202,18 +207,19 @@ int ltx_load_safetensors(ltx_ctx* c, const char* path, int which, int* n_loaded)
   return guarded(c, [&] {
     const int n = load_safetensors(c, path, which);
     if (n_loaded) *n_loaded = n;
-    static const char* kWhat[] = {"", "transformer", "VAE decoder", "VAE encoder", "upscaler"};
+    static const char* kWhat[] = {"", "transformer", "VAE decoder", "VAE encoder", "upscaler", "audio/video transformer"};
     LTX_CHECK(n > 0, LTX_ERR_WEIGHTS, std::string("no ") + kWhat[which] + " tensors found in '" + (path ? path : "") + "'");
   });
 }
 
 int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap) {
-  if (!file_key || !out || cap == 0 || which < 1 || which > 4) return LTX_ERR_INVALID_ARGUMENT;
+  if (!file_key || !out || cap == 0 || which < 1 || which > 5) return LTX_ERR_INVALID_ARGUMENT;
   try {
     const std::string m = which == 1   ? map_transformer_key(file_key)
                           : which == 2 ? map_vae_key(file_key)
                           : which == 3 ? map_vae_encoder_key(file_key)
-                                       : map_upscaler_key(file_key);
+                          : which == 4 ? map_upscaler_key(file_key)
+                                       : map_transformer_key(file_key, true);
     if (m.size() + 1 > cap) return LTX_ERR_INVALID_ARGUMENT;
     memcpy(out, m.c_str(), m.size() + 1);
     return LTX_OK;
@@ -243,6 +249,10 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
     if (c->tensors.count("patchify_proj.weight")) {
       if (c->precision == 32) dit_finalize_f32(c);
       else dit_finalize(c);
+      if (c->tensors.count("audio_patchify_proj.weight")) {
+        LTX_CHECK(quant_bits == 16 && c->precision == 16, LTX_ERR_UNSUPPORTED, "the dual audio/video model runs with bf16 weights only");
+        dit_av_finalize(c);
+      }
       if (quant_bits != 16) dit_quantize(c, quant_bits);
     }
     if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);
@@ -289,6 +299,54 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
     dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), ts_per_token, mask_dev, B, N, S, F,
                     H, W, flags, c->vel.as<float>());
     LTX_CUDA(cudaMemcpyAsync(out_velocity, c->vel.ptr, R * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_av_forward_dev(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                       ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                       const float* video_sigma, const float* audio_sigma, const int32_t* video_mask, const int32_t* audio_mask,
+                       int N, int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio) {
+  return guarded(c, [&] {
+    dit_av_forward_dev(c, video_latent, video_dtype, audio_latent, audio_dtype, video_context, audio_context, context_dtype,
+                       video_sigma, audio_sigma, video_mask, audio_mask, 1, N, Ta, S, F, H, W, context_key, out_video, out_audio);
+  });
+}
+
+int ltx_av_forward(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent, ltx_dtype audio_dtype,
+                   const void* video_context, const void* audio_context, ltx_dtype context_dtype, float video_sigma,
+                   float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N, int Ta, int S, int F, int H,
+                   int W, uint64_t context_key, float* out_video, float* out_audio) {
+  return guarded(c, [&] {
+    LTX_CHECK(video_latent && audio_latent && video_context && audio_context && out_video && out_audio, LTX_ERR_INVALID_ARGUMENT,
+              "null tensor");
+    LTX_CHECK(N >= 1 && Ta >= 1 && S >= 1 && c->av.ready, LTX_ERR_INVALID_ARGUMENT, "bad sizes, or dual-model weights not finalized");
+    const ltx_config& g = c->cfg;
+    const int Ca = c->av.Cin;
+    DevBuf* b = c->av_in;   // staged host inputs: video latent, audio latent, contexts, sigmas, masks, outputs
+    h2d(c, b[0], video_latent, static_cast<size_t>(N) * g.in_channels * dsize(video_dtype));
+    h2d(c, b[1], audio_latent, static_cast<size_t>(Ta) * Ca * dsize(audio_dtype));
+    const size_t cbytes = static_cast<size_t>(S) * g.caption_channels * dsize(context_dtype);
+    h2d(c, b[2], video_context, cbytes);
+    h2d(c, b[3], audio_context, cbytes);
+    const float sig[2] = {video_sigma, audio_sigma};
+    h2d(c, b[4], sig, 8);
+    const int32_t *vm = nullptr, *am = nullptr;
+    b[5].reserve(static_cast<size_t>(2) * S * 4);
+    if (video_mask) {
+      LTX_CUDA(cudaMemcpyAsync(b[5].ptr, video_mask, static_cast<size_t>(S) * 4, cudaMemcpyHostToDevice, c->stream));
+      vm = b[5].as<int32_t>();
+    }
+    if (audio_mask) {
+      LTX_CUDA(cudaMemcpyAsync(b[5].as<int32_t>() + S, audio_mask, static_cast<size_t>(S) * 4, cudaMemcpyHostToDevice, c->stream));
+      am = b[5].as<int32_t>() + S;
+    }
+    b[6].reserve(static_cast<size_t>(N) * g.out_channels * 4);
+    b[7].reserve(static_cast<size_t>(Ta) * Ca * 4);
+    dit_av_forward_dev(c, b[0].ptr, video_dtype, b[1].ptr, audio_dtype, b[2].ptr, b[3].ptr, context_dtype, b[4].as<float>(),
+                       b[4].as<float>() + 1, vm, am, 1, N, Ta, S, F, H, W, context_key, b[6].as<float>(), b[7].as<float>());
+    LTX_CUDA(cudaMemcpyAsync(out_video, b[6].ptr, static_cast<size_t>(N) * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaMemcpyAsync(out_audio, b[7].ptr, static_cast<size_t>(Ta) * Ca * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
 }

@@ -65,6 +65,15 @@ struct TextCache {  // caption projection + per-block cross-attention K / V^T (s
   bool has_bias = false;
 };
 
+// what dit_prepare_text needs to build a stream's text cache: caption projection + per-block cross-attention K / V weights
+struct TextProjW {
+  const bf16 *w_c1 = nullptr, *w_c2 = nullptr;
+  const float *b_c1 = nullptr, *b_c2 = nullptr;
+  int D = 0;
+  const void* user = nullptr;
+  const AttnWeights& (*layer)(const void* user, int i) = nullptr;
+};
+
 struct ConvW {
   const bf16* w = nullptr;  // [27][Cout][Cin]
   const float* b = nullptr;
@@ -90,6 +99,37 @@ struct VaeWeights {
   std::vector<std::vector<VaeResBlock>> stages;  // 4 stages x blocks_per_stage
   std::vector<ConvW> ups;                        // 3 depth-to-space convs
   const float* last_sst = nullptr;               // [2, C_last] rows shift, scale
+};
+
+// dual audio / video model (T/LTX2Transformer.swift, T/LTX2TransformerBlock.swift): the audio stream, the learned norms and the
+// cross-modal attentions on top of the video weights held in ltx_ctx::blocks
+struct AdaLnW {   // AdaLayerNormSingle: Linear(256, dim) -> SiLU -> Linear(dim, dim) ; SiLU -> Linear(dim, n * dim)
+  const bf16 *w1 = nullptr, *w2 = nullptr, *wl = nullptr;
+  const float *b1 = nullptr, *b2 = nullptr, *bl = nullptr;
+  int dim = 0, n = 0;
+};
+struct AvBlockW {
+  const float *norm1 = nullptr, *norm2 = nullptr, *norm3 = nullptr, *a2v_norm = nullptr;        // video, [D]
+  const float *anorm1 = nullptr, *anorm2 = nullptr, *anorm3 = nullptr, *v2a_norm = nullptr;     // audio, [Da]
+  AttnWeights aa1, aa2, a2v, v2a;   // audio self / audio text-cross / audio->video / video->audio
+  const bf16 *w_in = nullptr, *w_out = nullptr;
+  const float *b_in = nullptr, *b_out = nullptr;
+  const float *asst = nullptr;      // audio_scale_shift_table [6, Da]
+  const float *sst_ca_v = nullptr;  // scale_shift_table_a2v_ca_video [5, D]
+  const float *sst_ca_a = nullptr;  // scale_shift_table_a2v_ca_audio [5, Da]
+};
+struct AvWeights {
+  bool ready = false;
+  int Da = 0, Ha = 0, hd = 0, Cin = 0;
+  const bf16 *w_patch = nullptr, *w_c1 = nullptr, *w_c2 = nullptr, *w_out = nullptr;
+  const float *b_patch = nullptr, *b_c1 = nullptr, *b_c2 = nullptr, *b_out = nullptr, *sst_out = nullptr;
+  AdaLnW ada_a, cv_ss, cv_g, ca_ss, ca_g;
+  std::vector<AvBlockW> blocks;
+  TextCache text[2];
+  int text_rr = 0;
+  DevBuf ws;                             // audio / cross-modal activations
+  DevBuf a_cos, a_sin, xv_cos, xv_sin;   // 1-D RoPE tables: audio frames [Ta, Da/2], video frames' temporal coordinate [N, Da/2]
+  int rope_ta = 0, rope_f = 0, rope_hw = 0;
 };
 
 // VAE encoder (V/VideoEncoder.swift:211-268): conv_in 48 -> base, 4 down blocks (res blocks + space-to-depth conv), mid block, conv_out
@@ -166,6 +206,7 @@ struct ltx_ctx {
   const float *b_patch = nullptr, *b_t1 = nullptr, *b_t2 = nullptr, *b_ada = nullptr, *b_c1 = nullptr, *b_c2 = nullptr,
               *b_out = nullptr, *sst_out = nullptr;
   ltx::VaeWeights vae;
+  ltx::AvWeights av;
   ltx::EncWeights enc;
   ltx::UpsWeights ups;
 
@@ -197,6 +238,7 @@ struct ltx_ctx {
 
   // ---- VAE workspaces
   ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te;
+  ltx::DevBuf av_in[8];   // host-API staging of the dual model's inputs / outputs
   ltx::DevBuf u_part, u_ab, u_stats, u_in, u_out, u_ref;   // encoder / upscaler / AdaIN scratch and host-API staging
 };
 
@@ -235,7 +277,15 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
                      int H, int W, const ltx_dit_flags* flags, float* out_velocity_dev, int snapshot_block = -1,
                      int resume_block = -1);
 void dit_clear_caches(ltx_ctx* c);
+TextCache& dit_prepare_text(ltx_ctx* c, TextCache* slots, int* rr, const TextProjW& src, const void* context, int context_dtype,
+                            const int32_t* mask_dev, int B, int S, uint64_t key);
 void dit_build_rope(ltx_ctx* c, int F, int H, int W);
+// dit_av.cu: dual audio / video model (LTX2Transformer)
+void dit_av_finalize(ltx_ctx* c);
+void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const void* a_latent, int a_dtype, const void* v_context,
+                        const void* a_context, int ctx_dtype, const float* v_ts_dev, const float* a_ts_dev, const int32_t* v_mask_dev,
+                        const int32_t* a_mask_dev, int B, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                        float* out_v_dev, float* out_a_dev);
 // dit_f32.cu
 void dit_finalize_f32(ltx_ctx* c);
 void dit_forward_f32(ltx_ctx* c, const void* latent, int latent_dtype, const void* context, int context_dtype,
@@ -272,7 +322,7 @@ void dist_p2p_barrier(ltx_ctx* c, int kind);
 void dist_halo_exchange(ltx_ctx* c, const void* send_prev, void* recv_prev, const void* send_next, void* recv_next,
                         size_t bytes, int n_active);
 // safetensors.cu
-std::string map_transformer_key(const std::string& file_key);
+std::string map_transformer_key(const std::string& file_key, bool include_audio = false);
 std::string map_vae_key(const std::string& file_key);
 std::string map_vae_encoder_key(const std::string& file_key);
 std::string map_upscaler_key(const std::string& file_key);

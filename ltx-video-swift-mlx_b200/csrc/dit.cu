@@ -136,19 +136,23 @@ bool in_list(int v, const int32_t* lst, int n) {
 }
 
 // caption projection + per-block text K / V^T (T/LTXTimestepEmbedding.swift:146-151, T/LTXAttention.swift:171-180)
-TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, const int32_t* mask_dev, int B, int S,
-                        uint64_t key) {
+}  // namespace
+
+// Generic over the stream: `src` names the caption-projection and per-block cross-attention K / V weights (the video stream
+// of both models, or the audio stream of the dual model), `slots` / `rr` the two-entry cache it fills.
+TextCache& dit_prepare_text(ltx_ctx* c, TextCache* slots, int* rr, const TextProjW& src, const void* context, int context_dtype,
+                            const int32_t* mask_dev, int B, int S, uint64_t key) {
   const ltx_config& g = c->cfg;
-  const int D = g.num_heads * g.head_dim, L = g.num_layers, Cc = g.caption_channels;
+  const int D = src.D, L = g.num_layers, Cc = g.caption_channels;
   if (key != 0)
-    for (auto& t : c->text)
-      if (t.key == key && t.B == B && t.S == S) return t;
+    for (int i = 0; i < 2; ++i)
+      if (slots[i].key == key && slots[i].B == B && slots[i].S == S) return slots[i];
   // miss: take an un-keyed slot if there is one, otherwise evict round-robin
   int slot = -1;
   for (int i = 0; i < 2; ++i)
-    if (c->text[i].key == 0) { slot = i; break; }
-  if (slot < 0) slot = (c->text_rr++) & 1;
-  TextCache& tc = c->text[slot];
+    if (slots[i].key == 0) { slot = i; break; }
+  if (slot < 0) slot = ((*rr)++) & 1;
+  TextCache& tc = slots[slot];
   const int64_t R = static_cast<int64_t>(B) * S;
   tc.key = key; tc.B = B; tc.S = S;
   tc.ldv = round_up(S, 8);  // per-batch pitch of V^T; row pitch is B * ldv
@@ -172,12 +176,12 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
   c->c1.reserve(static_cast<size_t>(R) * D * 2);
   c->c2.reserve(static_cast<size_t>(R) * D * 2);
   GemmEpi e;
-  e.mode = EPI_GELU_BF16; e.out = c->c1.ptr; e.ldo = D; e.bias = c->b_c1;
-  gemm(c, ctx_bf, Cc, c->w_c1, Cc, static_cast<int>(R), D, Cc, e);
-  e.mode = EPI_BF16; e.out = c->c2.ptr; e.bias = c->b_c2;
-  gemm(c, c->c1.as<bf16>(), D, c->w_c2, D, static_cast<int>(R), D, D, e);
+  e.mode = EPI_GELU_BF16; e.out = c->c1.ptr; e.ldo = D; e.bias = src.b_c1;
+  gemm(c, ctx_bf, Cc, src.w_c1, Cc, static_cast<int>(R), D, Cc, e);
+  e.mode = EPI_BF16; e.out = c->c2.ptr; e.bias = src.b_c2;
+  gemm(c, c->c1.as<bf16>(), D, src.w_c2, D, static_cast<int>(R), D, D, e);
   for (int i = 0; i < L; ++i) {
-    const AttnWeights& a = c->blocks[i].a2;
+    const AttnWeights& a = src.layer(src.user, i);
     bf16* kd = tc.k.as<bf16>() + static_cast<int64_t>(i) * R * D;
     bf16* vd = tc.vt.as<bf16>() + static_cast<int64_t>(i) * D * B * tc.ldv;
     GemmEpi ek;
@@ -205,6 +209,15 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
   return tc;
 }
 
+namespace {
+const AttnWeights& video_text_layer(const void* user, int i) { return static_cast<const ltx_ctx*>(user)->blocks[i].a2; }
+TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, const int32_t* mask_dev, int B, int S,
+                        uint64_t key) {
+  TextProjW src;
+  src.w_c1 = c->w_c1; src.w_c2 = c->w_c2; src.b_c1 = c->b_c1; src.b_c2 = c->b_c2;
+  src.D = c->cfg.num_heads * c->cfg.head_dim; src.user = c; src.layer = video_text_layer;
+  return dit_prepare_text(c, c->text, &c->text_rr, src, context, context_dtype, mask_dev, B, S, key);
+}
 }  // namespace
 
 void dit_build_rope(ltx_ctx* c, int F, int H, int W) { build_rope(c, F, H, W); }

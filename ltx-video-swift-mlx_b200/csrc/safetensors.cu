@@ -184,18 +184,19 @@ struct MappedFile {
 
 // Transformer key of the checkpoint -> name the context expects, or "" when the tensor is not part of the video-only DiT.
 // `key` is the name inside the file (with or without the "model.diffusion_model." prefix of the unified checkpoint).
-std::string map_transformer_key(const std::string& file_key) {
+std::string map_transformer_key(const std::string& file_key, bool include_audio) {
   std::string key = file_key;
   // loadTransformerWeights (:617-629): quantisation side tensors, audio / vocoder / cross-modal tensors, connectors
   if (ends_with(key, ".weight_scale") || ends_with(key, ".input_scale")) return "";
-  if (contains(key, "audio") || starts_with(key, "vocoder") || contains(key, "av_ca_")) return "";
+  if (!include_audio && (contains(key, "audio") || starts_with(key, "vocoder") || contains(key, "av_ca_"))) return "";
+  if (include_audio && starts_with(key, "vocoder")) return "";   // not under model.diffusion_model. (:624)
   static const char* kPrefix = "model.diffusion_model.";
   if (starts_with(key, kPrefix)) key = key.substr(strlen(kPrefix));
   if (starts_with(key, "video_embeddings_connector.") || starts_with(key, "audio_embeddings_connector.")) return "";
   // mapTransformerKey (:760-771): audio / cross-modal tensors of the dual model
-  if (starts_with(key, "audio_") || contains(key, ".audio_") || starts_with(key, "av_cross_attn_") ||
+  if (!include_audio && (starts_with(key, "audio_") || contains(key, ".audio_") || starts_with(key, "av_cross_attn_") ||
       contains(key, "video_to_audio") || contains(key, "video_a2v") || contains(key, "a2v_ca") ||
-      contains(key, "scale_shift_table_a2v"))
+      contains(key, "scale_shift_table_a2v")))
     return "";
   std::string k = key;
   if (starts_with(k, "proj_in.")) k = "patchify_proj." + k.substr(strlen("proj_in."));                       // :776-778
@@ -283,7 +284,7 @@ std::string map_upscaler_key(const std::string& file_key) {
 // which: 1 = transformer tensors (mapTransformerKey), 2 = VAE decoder tensors (mapVAEWeights), 3 = VAE encoder tensors
 // (mapVAEEncoderWeights), 4 = latent upscaler file.  Returns how many were loaded.
 int load_safetensors(ltx_ctx* c, const char* path, int which) {
-  LTX_CHECK(path != nullptr && which >= 1 && which <= 4, LTX_ERR_INVALID_ARGUMENT, "load_safetensors: bad arguments");
+  LTX_CHECK(path != nullptr && which >= 1 && which <= 5, LTX_ERR_INVALID_ARGUMENT, "load_safetensors: bad arguments");
   MappedFile f(path);
   uint64_t hlen = 0;
   memcpy(&hlen, f.base, 8);
@@ -293,7 +294,7 @@ int load_safetensors(ltx_ctx* c, const char* path, int which) {
   const uint64_t data_size = f.size - 8 - hlen;
   // A unified checkpoint holds every sub-model: there the transformer tensors are exactly the "model.diffusion_model."
   // keys (:624) and the VAE tensors the "vae." keys; a stand-alone file carries no such prefix and is taken whole.
-  const char* want = which == 1 ? "model.diffusion_model." : "vae.";
+  const char* want = (which == 1 || which == 5) ? "model.diffusion_model." : "vae.";
   bool unified = false;
   if (which != 4)
     for (const auto& kv : header) unified = unified || starts_with(kv.first, want);
@@ -303,7 +304,8 @@ int load_safetensors(ltx_ctx* c, const char* path, int which) {
     const std::string name = which == 1   ? map_transformer_key(kv.first)
                              : which == 2 ? map_vae_key(kv.first)
                              : which == 3 ? map_vae_encoder_key(kv.first)
-                                          : map_upscaler_key(kv.first);
+                             : which == 4 ? map_upscaler_key(kv.first)
+                                          : map_transformer_key(kv.first, true);
     if (name.empty()) continue;
     const TensorInfo& t = kv.second;
     int dtype;

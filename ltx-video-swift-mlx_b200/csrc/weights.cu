@@ -176,6 +176,47 @@ void init_random_weights(ltx_ctx* c, int which, uint64_t seed) {
     lin("vae.last_time_embedder.timestep_embedder.linear_2", 2 * ch, 256);
     conv("vae.conv_out", 3 * g.vae_patch_size * g.vae_patch_size, ch);
   }
+  if (which & 16) {   // audio / cross-modal tensors of LTX2Transformer (T/LTX2Transformer.swift:20-43, T/LTX2TransformerBlock.swift:44-72)
+    const int64_t Ha = g.audio_num_heads > 0 ? g.audio_num_heads : 32, hd = g.audio_head_dim > 0 ? g.audio_head_dim : 64;
+    const int64_t Da = Ha * hd, Ca = g.audio_in_channels > 0 ? g.audio_in_channels : 128;
+    auto adaln = [&](const std::string& name, int64_t dim, int n) {
+      lin(name + ".emb.linear_1", dim, 256);
+      lin(name + ".emb.linear_2", dim, dim);
+      lin(name + ".linear", n * dim, dim, 0.5f);
+    };
+    auto attn = [&](const std::string& name, int64_t qdim, int64_t cdim, int64_t inner) {
+      lin(name + ".to_q", inner, qdim);
+      lin(name + ".to_k", inner, cdim);
+      lin(name + ".to_v", inner, cdim);
+      lin(name + ".to_out", qdim, inner);
+      fill(c, name + ".q_norm.weight", {inner}, 0.1f, 1.0f, s);
+      fill(c, name + ".k_norm.weight", {inner}, 0.1f, 1.0f, s);
+    };
+    lin("audio_patchify_proj", Da, Ca);
+    adaln("audio_adaln_single", Da, 6);
+    lin("audio_caption_projection.linear_1", Da, g.caption_channels);
+    lin("audio_caption_projection.linear_2", Da, Da);
+    fill(c, "audio_scale_shift_table", {2, Da}, 0.1f, 0.f, s);
+    lin("audio_proj_out", Ca, Da);
+    adaln("av_ca_video_scale_shift_adaln_single", D, 4);
+    adaln("av_ca_a2v_gate_adaln_single", D, 1);
+    adaln("av_ca_audio_scale_shift_adaln_single", Da, 4);
+    adaln("av_ca_v2a_gate_adaln_single", Da, 1);
+    for (int i = 0; i < g.num_layers; ++i) {
+      const std::string p = "transformer_blocks." + std::to_string(i) + ".";
+      for (const char* n : {"norm1", "norm2", "norm3", "audio_to_video_norm"}) fill(c, p + n + ".weight", {D}, 0.1f, 1.0f, s);
+      for (const char* n : {"audio_norm1", "audio_norm2", "audio_norm3", "video_to_audio_norm"}) fill(c, p + n + ".weight", {Da}, 0.1f, 1.0f, s);
+      attn(p + "audio_attn1", Da, Da, Da);
+      attn(p + "audio_attn2", Da, Da, Da);
+      lin(p + "audio_ff.project_in.proj", g.ffn_mult * Da, Da);
+      lin(p + "audio_ff.project_out", Da, g.ffn_mult * Da);
+      fill(c, p + "audio_scale_shift_table", {6, Da}, 0.1f, 0.f, s);
+      attn(p + "audio_to_video_attn", D, Da, Da);
+      attn(p + "video_to_audio_attn", Da, D, Da);
+      fill(c, p + "scale_shift_table_a2v_ca_video", {5, D}, 0.1f, 0.f, s);
+      fill(c, p + "scale_shift_table_a2v_ca_audio", {5, Da}, 0.1f, 0.f, s);
+    }
+  }
   if (which & 4) {   // VideoEncoder channel plan (Models/VAE/VideoEncoder.swift:222-268)
     auto conv = [&](const std::string& name, int64_t cout, int64_t cin) {
       fill(c, name + ".conv.weight", {cout, cin, 3, 3, 3}, 1.0f / sqrtf(27.0f * cin), 0.f, s);

@@ -39,3 +39,24 @@ class LTXTransformer:
         `context_key` (extension): non-zero = the text embedding is step-invariant, cache its projections under this key."""
         flags = make_flags(self._stg_blocks, self._skip_self_attn, self._skip_ff, self._cas_blocks, self._cas, context_key)
         return self.ctx.dit_forward(latent, context, timesteps, context_mask, tuple(latent_shape), flags)
+
+
+class LTX2Transformer:
+    """Host mirror of LTX2Transformer (Models/Transformer/LTX2Transformer.swift): the dual audio / video model.  The call takes
+    the Swift argument list (videoLatent, audioLatent, videoContext, audioContext, videoTimesteps, audioTimesteps, masks,
+    videoLatentShape, audioNumFrames) and returns (video, audio) velocities."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def __call__(self, video_latent, audio_latent, video_context, audio_context, video_timesteps, audio_timesteps,
+                 video_context_mask=None, audio_context_mask=None, video_latent_shape=None, audio_num_frames=None,
+                 context_key: int = 0):
+        import numpy as np
+        vt, at = np.asarray(video_timesteps, dtype=np.float32).reshape(-1), np.asarray(audio_timesteps, dtype=np.float32).reshape(-1)
+        if vt.size != 1 or at.size != 1:
+            raise ValueError("one sigma per stream (per-token timesteps of the dual model are not implemented)")
+        if audio_num_frames is not None and audio_num_frames != np.asarray(audio_latent.shape)[1]:
+            raise ValueError("audio_num_frames must equal the audio latent length")
+        return self.ctx.av_forward(video_latent, audio_latent, video_context, audio_context, float(vt[0]), float(at[0]),
+                                   tuple(video_latent_shape), video_context_mask, audio_context_mask, context_key)

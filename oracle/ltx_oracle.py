@@ -367,6 +367,223 @@ def single_block_forward(w: Dict[str, Tensor], cfg: DiTConfig, x: Tensor, ctx: T
 
 
 # ----------------------------------------------------------------------------------------------
+# dual audio / video transformer (T/LTX2Transformer.swift, T/LTX2TransformerBlock.swift) -- SURVEY 8f-1
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class AVConfig:
+    """Audio-side constants of LTXTransformerConfig (C/LTXConfig.swift:134-173): 32 heads x 64, 128 latent channels,
+    1-D positions with max_pos [20]."""
+    audio_heads: int = 32
+    audio_head_dim: int = 64
+    audio_in_channels: int = 128
+    audio_out_channels: int = 128
+    audio_max_pos: int = 20
+
+    @property
+    def audio_dim(self) -> int:
+        return self.audio_heads * self.audio_head_dim
+
+
+def make_av_weights(cfg: DiTConfig, av: AVConfig, seed: int = 0, bf16: bool = True) -> Dict[str, Tensor]:
+    """Random-init LTX2Transformer weights under the Swift module keys (T/LTX2Transformer.swift:20-43,
+    T/LTX2TransformerBlock.swift:44-72).  The video-only keys are those of make_dit_weights plus the learned norms."""
+    w = make_dit_weights(cfg, seed, bf16=False)
+    g = torch.Generator().manual_seed(seed + 7919)
+    D, Da = cfg.inner_dim, av.audio_dim
+
+    def lin(name, out_f, in_f, wstd=None):
+        std = wstd if wstd is not None else 1.0 / math.sqrt(in_f)
+        w[name + ".weight"] = torch.randn(out_f, in_f, generator=g) * std
+        w[name + ".bias"] = torch.randn(out_f, generator=g) * 0.02
+
+    def adaln(name, dim, n):
+        lin(name + ".emb.linear_1", dim, 256)
+        lin(name + ".emb.linear_2", dim, dim)
+        lin(name + ".linear", n * dim, dim, wstd=0.5 / math.sqrt(dim))
+
+    def attn(name, qdim, cdim, inner):
+        lin(name + ".to_q", inner, qdim)
+        lin(name + ".to_k", inner, cdim)
+        lin(name + ".to_v", inner, cdim)
+        lin(name + ".to_out", qdim, inner)
+        w[name + ".q_norm.weight"] = 1.0 + 0.1 * torch.randn(inner, generator=g)
+        w[name + ".k_norm.weight"] = 1.0 + 0.1 * torch.randn(inner, generator=g)
+
+    def norm(name, dim):
+        w[name + ".weight"] = 1.0 + 0.1 * torch.randn(dim, generator=g)
+
+    lin("audio_patchify_proj", Da, av.audio_in_channels)
+    adaln("audio_adaln_single", Da, 6)
+    lin("audio_caption_projection.linear_1", Da, cfg.caption_channels)
+    lin("audio_caption_projection.linear_2", Da, Da)
+    w["audio_scale_shift_table"] = torch.randn(2, Da, generator=g) * 0.1
+    lin("audio_proj_out", av.audio_out_channels, Da)
+    adaln("av_ca_video_scale_shift_adaln_single", D, 4)
+    adaln("av_ca_a2v_gate_adaln_single", D, 1)
+    adaln("av_ca_audio_scale_shift_adaln_single", Da, 4)
+    adaln("av_ca_v2a_gate_adaln_single", Da, 1)
+    for i in range(cfg.num_layers):
+        p = f"transformer_blocks.{i}."
+        for n in ("norm1", "norm2", "norm3", "audio_to_video_norm"):
+            norm(p + n, D)
+        for n in ("audio_norm1", "audio_norm2", "audio_norm3", "video_to_audio_norm"):
+            norm(p + n, Da)
+        attn(p + "audio_attn1", Da, Da, Da)
+        attn(p + "audio_attn2", Da, Da, Da)            # context = audio caption projection (Da wide)
+        lin(p + "audio_ff.project_in.proj", cfg.ffn_mult * Da, Da)
+        lin(p + "audio_ff.project_out", Da, cfg.ffn_mult * Da)
+        w[p + "audio_scale_shift_table"] = torch.randn(6, Da, generator=g) * 0.1
+        attn(p + "audio_to_video_attn", D, Da, Da)     # Q from video, K/V from audio, audio head layout
+        attn(p + "video_to_audio_attn", Da, D, Da)     # Q from audio, K/V from video
+        w[p + "scale_shift_table_a2v_ca_video"] = torch.randn(5, D, generator=g) * 0.1
+        w[p + "scale_shift_table_a2v_ca_audio"] = torch.randn(5, Da, generator=g) * 0.1
+    if bf16:
+        w = {k: bf16_round(v) for k, v in w.items()}
+    return w
+
+
+def audio_position_grid(frames: int, hop: int = 160, sr: int = 16000, scale: int = 4, causal_offset: int = 1) -> Tensor:
+    """createAudioPositionGrid (T/LTXRoPE.swift:627-655): mid-point of the latent frame's mel span in seconds. [1, T]."""
+    f = torch.arange(frames, dtype=torch.float32)
+    start = torch.clamp(f * scale + causal_offset - scale, min=0)
+    end = torch.clamp((f + 1) * scale + causal_offset - scale, min=0)
+    return ((start + end) / 2.0 * hop / sr).view(1, -1)
+
+
+def rope_table_nd(grid: Tensor, dim: int, heads: int, theta: float, max_pos: Sequence[int]) -> Tuple[Tensor, Tensor]:
+    """precomputeFreqsCis, split type, doublePrecision (T/LTXRoPE.swift:375-488) for an [n_dims, T] position grid:
+    returns cos, sin [heads, T, dim / (2 heads)] fp32.  rope_table() is the n_dims = 3 video case."""
+    n_dims = grid.shape[0]
+    g64 = grid.to(torch.float64)
+    num_idx = max(1, dim // (2 * n_dims))
+    i = torch.arange(num_idx, dtype=torch.float64)
+    t = i / (num_idx - 1) if num_idx > 1 else torch.zeros(1, dtype=torch.float64)
+    idx = torch.pow(torch.tensor(theta, dtype=torch.float64), t) * (math.pi / 2.0)
+    mp = torch.tensor(list(max_pos), dtype=torch.float64).view(n_dims, 1)
+    scaled = (g64 / mp) * 2.0 - 1.0
+    freqs = (idx.view(1, num_idx, 1) * scaled.t().reshape(-1, 1, n_dims)).reshape(-1, num_idx * n_dims)
+    cos, sin = torch.cos(freqs), torch.sin(freqs)
+    pad = max(0, dim // 2 - num_idx * n_dims)
+    T = freqs.shape[0]
+    cos = torch.cat([torch.ones(T, pad, dtype=torch.float64), cos], 1).to(torch.float32)
+    sin = torch.cat([torch.zeros(T, pad, dtype=torch.float64), sin], 1).to(torch.float32)
+    hd2 = (dim // 2) // heads
+    return (cos.view(T, heads, hd2).permute(1, 0, 2).contiguous(), sin.view(T, heads, hd2).permute(1, 0, 2).contiguous())
+
+
+def _adaln_single(w, name: str, t_scaled: Tensor, dtype) -> Tuple[Tensor, Tensor]:
+    """AdaLayerNormSingle (T/LTXTimestepEmbedding.swift:96-124): returns (linear(silu(emb)), emb)."""
+    se = sinusoidal_embedding(t_scaled.reshape(-1)).to(dtype)
+    emb = linear(silu(linear(se, w, name + ".emb.linear_1")), w, name + ".emb.linear_2")
+    return linear(silu(emb), w, name + ".linear"), emb
+
+
+def _av_attention(w, prefix: str, x: Tensor, ctx: Optional[Tensor], heads: int, eps: float,
+                  q_rope=None, k_rope=None, bias=None, bf16_kv: bool = False) -> Tensor:
+    """LTXAttention.callAsFunction (T/LTXAttention.swift:160-218) with separate query / key RoPE (pe / kPe)."""
+    c = x if ctx is None else ctx
+    q, k, v = linear(x, w, prefix + ".to_q"), linear(c, w, prefix + ".to_k"), linear(c, w, prefix + ".to_v")
+    if bf16_kv:
+        k, v = bf16_round(k), bf16_round(v)
+    q = rms_norm(q, w[prefix + ".q_norm.weight"], eps)
+    k = rms_norm(k, w[prefix + ".k_norm.weight"], eps)
+    if bf16_kv:
+        k = bf16_round(k)
+    if q_rope is not None:
+        q = apply_split_rope(q, q_rope[0], q_rope[1], heads)
+        kr = k_rope if k_rope is not None else q_rope
+        k = apply_split_rope(k, kr[0], kr[1], heads)
+    return linear(sdpa(q, k, v, heads, bias), w, prefix + ".to_out")
+
+
+def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: Tensor, v_context: Tensor, a_context: Tensor,
+                   v_sigma: Tensor, a_sigma: Tensor, v_mask: Optional[Tensor], a_mask: Optional[Tensor],
+                   fhw: Tuple[int, int, int], audio_frames: int, dtype=torch.float32, mlx_bf16: bool = True):
+    """LTX2Transformer.callAsFunction (T/LTX2Transformer.swift:240-392) with LTX2TransformerBlock (:174-297).
+    v_latent [B,N,128], a_latent [B,Ta,128], contexts [B,S,3840], sigmas [B].  Returns (video velocity [B,N,128],
+    audio velocity [B,Ta,128])."""
+    F, H, W = fhw
+    D, Da, eps = cfg.inner_dim, av.audio_dim, cfg.norm_eps
+    B = v_latent.shape[0]
+    vl, al, vc, ac = v_latent.to(dtype), a_latent.to(dtype), v_context.to(dtype), a_context.to(dtype)
+    if mlx_bf16:
+        vl, al, vc, ac = bf16_round(vl), bf16_round(al), bf16_round(vc), bf16_round(ac)
+    vx = linear(vl, w, "patchify_proj")                                              # :255
+    ax = linear(al, w, "audio_patchify_proj")                                        # :262
+    if mlx_bf16:
+        vx, ax = bf16_round(vx), bf16_round(ax)
+    tv = v_sigma.to(torch.float32) * cfg.timestep_scale_multiplier                   # :256, 263
+    ta = a_sigma.to(torch.float32) * cfg.timestep_scale_multiplier
+    v_ada, v_emb = _adaln_single(w, "adaln_single", tv, dtype)
+    a_ada, a_emb = _adaln_single(w, "audio_adaln_single", ta, dtype)
+    v_ada, a_ada = v_ada.view(B, 1, 6, D), a_ada.view(B, 1, 6, Da)
+    pvc = caption_projection(w, vc, mlx_bf16)                                        # :259
+    h = linear(ac, w, "audio_caption_projection.linear_1")                           # :266
+    if mlx_bf16:
+        h = bf16_round(h)
+    h = gelu_tanh(h)
+    if mlx_bf16:
+        h = bf16_round(h)
+    pac = linear(h, w, "audio_caption_projection.linear_2")
+    if mlx_bf16:
+        pac = bf16_round(pac)
+    # cross-modal modulation: 4 scale/shift values + 1 gate per stream, from the stream's own timestep (:275-298)
+    cv_ss, _ = _adaln_single(w, "av_ca_video_scale_shift_adaln_single", tv, dtype)
+    cv_g, _ = _adaln_single(w, "av_ca_a2v_gate_adaln_single", tv, dtype)
+    ca_ss, _ = _adaln_single(w, "av_ca_audio_scale_shift_adaln_single", ta, dtype)
+    ca_g, _ = _adaln_single(w, "av_ca_v2a_gate_adaln_single", ta, dtype)
+    cv = torch.cat([cv_ss.view(B, 1, 4, D), cv_g.view(B, 1, 1, D)], dim=2)
+    ca = torch.cat([ca_ss.view(B, 1, 4, Da), ca_g.view(B, 1, 1, Da)], dim=2)
+    vbias = None if v_mask is None else ((1.0 - v_mask.to(dtype)) * -10000.0).view(B, 1, 1, -1)   # :394-403
+    abias = None if a_mask is None else ((1.0 - a_mask.to(dtype)) * -10000.0).view(B, 1, 1, -1)
+    v_rope = rope_table(cfg, F, H, W)                                                # :138-160
+    a_grid = audio_position_grid(audio_frames)
+    a_rope = rope_table_nd(a_grid, Da, av.audio_heads, cfg.rope_theta, [av.audio_max_pos])      # :162-186
+    v_tgrid = position_grid(F, H, W)[0:1]                                            # temporal coordinate only (:198-212)
+    xv_rope = rope_table_nd(v_tgrid, Da, av.audio_heads, cfg.rope_theta, [av.audio_max_pos])
+    xa_rope = rope_table_nd(a_grid, Da, av.audio_heads, cfg.rope_theta, [av.audio_max_pos])     # :216-229
+    Hv, Ha = cfg.num_heads, av.audio_heads
+    for i in range(cfg.num_layers):
+        p = f"transformer_blocks.{i}"
+        vs = w[p + ".scale_shift_table"].to(dtype).view(1, 1, 6, D) + v_ada          # T/LTX2TransformerBlock.swift:183-206
+        as_ = w[p + ".audio_scale_shift_table"].to(dtype).view(1, 1, 6, Da) + a_ada
+        # 1-2: self-attention on both streams (:208-216)
+        n = rms_norm(vx, w[p + ".norm1.weight"], eps) * (1 + vs[:, :, 1]) + vs[:, :, 0]
+        vx = vx + _av_attention(w, p + ".attn1", n, None, Hv, eps, v_rope) * vs[:, :, 2]
+        n = rms_norm(ax, w[p + ".audio_norm1.weight"], eps) * (1 + as_[:, :, 1]) + as_[:, :, 0]
+        ax = ax + _av_attention(w, p + ".audio_attn1", n, None, Ha, eps, a_rope) * as_[:, :, 2]
+        # 3-4: text cross-attention, learned RMSNorm in front, no RoPE, no gate (:218-226)
+        vx = vx + _av_attention(w, p + ".attn2", rms_norm(vx, w[p + ".norm2.weight"], eps), pvc, Hv, eps, bias=vbias,
+                                bf16_kv=mlx_bf16)
+        ax = ax + _av_attention(w, p + ".audio_attn2", rms_norm(ax, w[p + ".audio_norm2.weight"], eps), pac, Ha, eps, bias=abias,
+                                bf16_kv=mlx_bf16)
+        # 5-6: cross-modal attention; rows: a2v_scale, a2v_shift, v2a_scale, v2a_shift, gate (:228-271)
+        vca = w[p + ".scale_shift_table_a2v_ca_video"].to(dtype).view(1, 1, 5, D) + cv
+        aca = w[p + ".scale_shift_table_a2v_ca_audio"].to(dtype).view(1, 1, 5, Da) + ca
+        nv = rms_norm(vx, w[p + ".audio_to_video_norm.weight"], eps)
+        na = rms_norm(ax, w[p + ".video_to_audio_norm.weight"], eps)
+        a2v = _av_attention(w, p + ".audio_to_video_attn", nv * (1 + vca[:, :, 0]) + vca[:, :, 1],
+                            na * (1 + aca[:, :, 0]) + aca[:, :, 1], Ha, eps, xv_rope, xa_rope)
+        v2a = _av_attention(w, p + ".video_to_audio_attn", na * (1 + aca[:, :, 2]) + aca[:, :, 3],
+                            nv * (1 + vca[:, :, 2]) + vca[:, :, 3], Ha, eps, xa_rope, xv_rope)
+        vx = vx + a2v * vca[:, :, 4]
+        ax = ax + v2a * aca[:, :, 4]
+        # 7-8: feed-forward (:273-281)
+        n = rms_norm(vx, w[p + ".norm3.weight"], eps) * (1 + vs[:, :, 4]) + vs[:, :, 3]
+        vx = vx + linear(gelu_tanh(linear(n, w, p + ".ff.project_in.proj")), w, p + ".ff.project_out") * vs[:, :, 5]
+        n = rms_norm(ax, w[p + ".audio_norm3.weight"], eps) * (1 + as_[:, :, 4]) + as_[:, :, 3]
+        ax = ax + linear(gelu_tanh(linear(n, w, p + ".audio_ff.project_in.proj")), w, p + ".audio_ff.project_out") * as_[:, :, 5]
+
+    def head(x, table, emb, proj):                                                    # T/LTX2Transformer.swift:370-388
+        o = w[table].to(dtype).view(1, 1, 2, -1) + emb.view(B, 1, 1, -1)
+        mu = x.mean(-1, keepdim=True)
+        y = (x - mu) * torch.rsqrt((x - mu).pow(2).mean(-1, keepdim=True) + eps)
+        return linear(y * (1 + o[:, :, 1]) + o[:, :, 0], w, proj)
+
+    return head(vx, "scale_shift_table", v_emb, "proj_out"), head(ax, "audio_scale_shift_table", a_emb, "audio_proj_out")
+
+
+# ----------------------------------------------------------------------------------------------
 # latent utils, guidance, scheduler (P/LatentUtils.swift, S/LTXScheduler.swift, P/LTXPipeline.swift:800-956)
 # ----------------------------------------------------------------------------------------------
 def patchify(latent: Tensor) -> Tensor:                  # P/LatentUtils.swift:20-36  (B,C,F,H,W)->(B,N,C)

@@ -210,3 +210,26 @@ def test_vae_encoder_and_upscaler_key_mapping():
     for k, want in ups.items():
         assert mk(4, k) == want, k
     assert mk(4, "upsampler.blur_down.kernel") is None
+
+
+def test_audio_video_transformer_key_mapping():
+    """loadTransformerWeights(includeAudio: true) (Utils/ModelDownloader.swift:605-639, 756-803): audio / cross-modal tensors are
+    kept (with the general renames), vocoder and connector tensors are not transformer weights."""
+    P = "model.diffusion_model."
+    cases = {
+        P + "audio_patchify_proj.weight": "audio_patchify_proj.weight",
+        P + "audio_adaln_single.emb.timestep_embedder.linear_1.weight": "audio_adaln_single.emb.linear_1.weight",
+        P + "av_ca_a2v_gate_adaln_single.emb.timestep_embedder.linear_2.bias": "av_ca_a2v_gate_adaln_single.emb.linear_2.bias",
+        P + "transformer_blocks.3.audio_attn1.norm_q.weight": "transformer_blocks.3.audio_attn1.q_norm.weight",
+        P + "transformer_blocks.3.audio_to_video_attn.to_out.0.weight": "transformer_blocks.3.audio_to_video_attn.to_out.weight",
+        P + "transformer_blocks.3.audio_ff.net.0.proj.weight": "transformer_blocks.3.audio_ff.project_in.proj.weight",
+        P + "transformer_blocks.3.audio_ff.net.2.bias": "transformer_blocks.3.audio_ff.project_out.bias",
+        P + "transformer_blocks.3.scale_shift_table_a2v_ca_video": "transformer_blocks.3.scale_shift_table_a2v_ca_video",
+        P + "transformer_blocks.3.attn1.to_q.weight": "transformer_blocks.3.attn1.to_q.weight",
+        P + "proj_in.weight": "patchify_proj.weight",
+    }
+    for k, want in cases.items():
+        assert mk(5, k) == want, k
+    for k in ("vocoder.conv_pre.weight", P + "video_embeddings_connector.x", P + "audio_embeddings_connector.x",
+              P + "transformer_blocks.3.attn1.to_q.weight_scale"):
+        assert mk(5, k) is None, k
