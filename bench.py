@@ -354,6 +354,76 @@ def run_ours(args, rank, world, local_rank):
             cq.close()
         except Exception as e:   # report, do not hide
             extras["qint8"] = dict(error=str(e))
+        # ---- the rows either side of the denoise loop: dual audio/video model, VAE encoder, latent upscaler
+        def ev_time(fn, strm, reps=3, warm=1):
+            for _ in range(warm):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(strm)
+            for _ in range(reps):
+                fn()
+            b.record(strm)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        try:
+            ca = LtxContext(LTXTransformerConfig(), local_rank)
+            ca.init_random_weights(17, seed=101)          # video + audio / cross-modal tensors: the full LTX2Transformer
+            ca.finalize_weights()
+            sa = torch.cuda.ExternalStream(ca.stream, device=torch.device("cuda", local_rank))
+            Ta = 26                                       # 25 frames at 24 fps = 1.04 s of audio at 25 latent frames / s
+            vl = torch.randn(1, N, CIN, generator=g).bfloat16().cuda()
+            al = torch.randn(1, Ta, CIN, generator=g).bfloat16().cuda()
+            tx = text.cuda()
+            sg2 = torch.tensor([0.7, 0.7], device="cuda")
+            ov = torch.empty(1, N, CIN, device="cuda")
+            oa = torch.empty(1, Ta, CIN, device="cuda")
+            torch.cuda.synchronize()
+
+            def av_step():
+                ca._check(ca.lib.ltx_av_forward_dev(ca.handle, vl.data_ptr(), 1, al.data_ptr(), 1, tx.data_ptr(), tx.data_ptr(), 1,
+                                                    sg2.data_ptr(), sg2.data_ptr() + 4, None, None, N, Ta, S, F, H, W, 77,
+                                                    ov.data_ptr(), oa.data_ptr()))
+            av_step()
+            ta_ms = ev_time(av_step, sa, reps=4)
+            ca.set_profiling(True)
+            av_step()
+            pa = ca.get_profile()
+            ca.set_profiling(False)
+            extras["av_dual_forward"] = dict(
+                desc=f"LTX2Transformer (dual audio/video, 48 blocks, D=4096 + Da=2048) forward, N={N} video + {Ta} audio tokens, S={S}",
+                ms_per_forward=ta_ms, forwards_per_s=1e3 / ta_ms,
+                kernel_classes={k: v for k, v in pa.items() if v["launches"]})
+            ca.close()
+            del vl, al, tx, ov, oa
+        except Exception as e:
+            extras["av_dual_forward"] = dict(error=str(e))
+        try:
+            ce = LtxContext(LTXTransformerConfig(), local_rank)
+            ce.init_random_weights(2 | 4 | 8, seed=103)   # VAE decoder (latent statistics), encoder, upscaler
+            ce.finalize_weights()
+            se_ = torch.cuda.ExternalStream(ce.stream, device=torch.device("cuda", local_rank))
+            px = (torch.rand(3, 1, 32 * H, 32 * W, generator=g) * 2 - 1).cuda()
+            zl = torch.empty(CIN, 1, H, W, device="cuda")
+            px25 = (torch.rand(3, 8 * (F - 1) + 1, 32 * H, 32 * W, generator=g) * 2 - 1).cuda()
+            zl25 = torch.empty(CIN, F, H, W, device="cuda")
+            lat1 = torch.randn(CIN, 33, H, W, generator=g).cuda()     # stage-1 latent of BASELINE config 5 (768x512x257)
+            lat2 = torch.empty(CIN, 33, 2 * H, 2 * W, device="cuda")
+            torch.cuda.synchronize()
+            t_img = ev_time(lambda: ce.vae_encode_dev(px.data_ptr(), (1, 32 * H, 32 * W), zl.data_ptr()), se_)
+            t_clip = ev_time(lambda: ce.vae_encode_dev(px25.data_ptr(), (8 * (F - 1) + 1, 32 * H, 32 * W), zl25.data_ptr()), se_)
+            t_up = ev_time(lambda: ce.upscale_latent_dev(lat1.data_ptr(), (33, H, W), lat2.data_ptr()), se_)
+            ce.set_profiling(True)
+            ce.upscale_latent_dev(lat1.data_ptr(), (33, H, W), lat2.data_ptr())
+            pu = ce.get_profile()
+            ce.set_profiling(False)
+            extras["vae_encode"] = dict(desc="VideoEncoder + latent normalisation, 768x512", image_ms=t_img, clip_25f_ms=t_clip,
+                                        clip_frames_per_s=(8 * (F - 1) + 1) * 1e3 / t_clip)
+            extras["latent_upscale"] = dict(desc="upsampleLatents 33x16x24 -> 33x32x48 (stage switch of BASELINE config 5)",
+                                            ms=t_up, kernel_classes={k: v for k, v in pu.items() if v["launches"]})
+            ce.close()
+            del px, zl, px25, zl25, lat1, lat2
+        except Exception as e:
+            extras["vae_encode"] = dict(error=str(e))
         tg = time_guided()
         tv = time_vae121()
         extras["guided_cfg3"] = dict(desc="dev CFG 4.0 + STG 0.5 (3 forwards/step), 1 GPU", ms_per_step=tg, steps_per_s=1e3 / tg)

@@ -63,6 +63,82 @@ __global__ void __launch_bounds__(256) rmsnorm_w_mod_kernel(const float* x, bf16
   }
 }
 
+// Fast path of the same op for D == 4 * VPT * 256 (4096: video, 2048: audio): a CTA owns ROWS rows whose loads are all issued
+// up front and whose sums of squares are reduced together; the combined per-channel scale w * (1 + sc_t + sc_a) and shift are
+// formed once per CTA.  NOUT = 2 writes two differently modulated copies of the same normalised rows (the cross-modal
+// attentions use each stream once as query and once as context, T/LTX2TransformerBlock.swift:244-268): one read of x.
+struct ModSet {
+  const float *sc_t, *sc_a, *sh_t, *sh_a;
+  bf16* out;
+};
+template <int VPT, int ROWS, int NOUT>
+__global__ void __launch_bounds__(256) rmsnorm_w_mod_fast_kernel(const float* x, int M, const float* w, const ModSet m0,
+                                                                  const ModSet m1, float eps) {
+  __shared__ float red[8 * ROWS];
+  constexpr int D = 4 * VPT * 256;
+  const int row0 = blockIdx.x * ROWS;
+  griddep_launch();
+  griddep_wait();
+  float4 v[ROWS][VPT];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row0 + rr) * D);
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+      v[rr][k] = (row0 + rr < M) ? xr[threadIdx.x + k * 256] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s2[ROWS];
+#pragma unroll
+  for (int rr = 0; rr < ROWS; ++rr) {
+    s2[rr] = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+      s2[rr] += v[rr][k].x * v[rr][k].x + v[rr][k].y * v[rr][k].y + v[rr][k].z * v[rr][k].z + v[rr][k].w * v[rr][k].w;
+  }
+  {   // ROWS sums at once, fixed summation order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) s2[rr] = warp_sum(s2[rr]);
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) red[warp * ROWS + rr] = s2[rr];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      float t = 0.f;
+      for (int ww = 0; ww < 8; ++ww) t += red[ww * ROWS + rr];
+      s2[rr] = rsqrtf(t / D + eps);
+    }
+  }
+  auto ld4 = [](const float* p, int i, float dflt) {
+    return p ? reinterpret_cast<const float4*>(p)[i] : make_float4(dflt, dflt, dflt, dflt);
+  };
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    const ModSet& m = o == 0 ? m0 : m1;
+    float4 sc[VPT], sh[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const float4 ww = ld4(w, i, 1.f), a = ld4(m.sc_t, i, 0.f), b = ld4(m.sc_a, i, 0.f), cc = ld4(m.sh_t, i, 0.f), d = ld4(m.sh_a, i, 0.f);
+      sc[k] = make_float4(ww.x * (1.f + a.x + b.x), ww.y * (1.f + a.y + b.y), ww.z * (1.f + a.z + b.z), ww.w * (1.f + a.w + b.w));
+      sh[k] = make_float4(cc.x + d.x, cc.y + d.y, cc.z + d.z, cc.w + d.w);
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+      const int row = row0 + rr;
+      if (row >= M) break;
+      uint2* orow = reinterpret_cast<uint2*>(m.out + static_cast<int64_t>(row) * D);
+#pragma unroll
+      for (int k = 0; k < VPT; ++k)
+        orow[threadIdx.x + k * 256] =
+            make_uint2(pack_bf16(v[rr][k].x * s2[rr] * sc[k].x + sh[k].x, v[rr][k].y * s2[rr] * sc[k].y + sh[k].y),
+                       pack_bf16(v[rr][k].z * s2[rr] * sc[k].z + sh[k].z, v[rr][k].w * s2[rr] * sc[k].w + sh[k].w));
+    }
+  }
+}
+
 // q / k RMSNorm across all heads (learned weight) + split RoPE for any head_dim that is a multiple of 16, in place on bf16
 // rows (T/LTXAttention.swift:179-189, T/LTXRoPE.swift:84-149): head h holds (x1 | x2) halves of hd/2; cos / sin
 // [rows_per_rope, D/2] fp32 with index h * hd/2 + j.
@@ -158,8 +234,31 @@ void attention(ltx_ctx* c, const bf16* Q, const bf16* K, int64_t ldk, const bf16
 void normw(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* w, const float* sc_t, const float* sc_a,
            const float* sh_t, const float* sh_a, float eps) {
   ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * 6.0);
-  launch_pdl(PDL_ROWS, rmsnorm_w_mod_kernel, dim3(M), dim3(256), 0, c->stream, x, out, D, w, sc_t, sc_a, sh_t, sh_a, eps);
+  const ModSet m{sc_t, sc_a, sh_t, sh_a, out};
+  if (D == 4096)
+    launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<4, 4, 1>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m, m, eps);
+  else if (D == 2048)
+    launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<2, 4, 1>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m, m, eps);
+  else
+    launch_pdl(PDL_ROWS, rmsnorm_w_mod_kernel, dim3(M), dim3(256), 0, c->stream, x, out, D, w, sc_t, sc_a, sh_t, sh_a, eps);
   LTX_CUDA(cudaGetLastError());
+}
+// two modulations of the same normalised rows: out0 with (sc0, sh0), out1 with (sc1, sh1); tbl rows r*D of `tbl`, `ada`
+void normw2(ltx_ctx* c, const float* x, bf16* out0, bf16* out1, int M, int D, const float* w, const float* tbl, const float* ada,
+            float eps) {
+  // rows: 0 a2v scale, 1 a2v shift, 2 v2a scale, 3 v2a shift
+  const ModSet m0{tbl, ada, tbl + D, ada + D, out0}, m1{tbl + 2 * D, ada + 2 * D, tbl + 3 * D, ada + 3 * D, out1};
+  if (D == 4096 || D == 2048) {
+    ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * 8.0);
+    if (D == 4096)
+      launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<4, 4, 2>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m0, m1, eps);
+    else
+      launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<2, 4, 2>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m0, m1, eps);
+    LTX_CUDA(cudaGetLastError());
+    return;
+  }
+  normw(c, x, out0, M, D, w, m0.sc_t, m0.sc_a, m0.sh_t, m0.sh_a, eps);
+  normw(c, x, out1, M, D, w, m1.sc_t, m1.sc_a, m1.sh_t, m1.sh_a, eps);
 }
 void qknorm_hd(ltx_ctx* c, bf16* x, int M, int D, int hd, const float* w, const float* cs, const float* sn, int rpr, float eps) {
   ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)));
@@ -456,10 +555,8 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     linear_resid(c, aatt, Ta, Da, ba.aa2.wo, ba.aa2.bo, Da, ax, nullptr, nullptr);
     // ---- 5-6: cross-modal attention; both directions read the streams as they are here (:228-271).  Table / embedding
     // rows: 0 a2v scale, 1 a2v shift, 2 v2a scale, 3 v2a shift, 4 gate.
-    normw(c, x, h, N, D, ba.a2v_norm, ba.sst_ca_v, cv, ba.sst_ca_v + D, cv + D, eps);                         // video as a2v query
-    normw(c, x, h2, N, D, ba.a2v_norm, ba.sst_ca_v + 2 * D, cv + 2 * D, ba.sst_ca_v + 3 * D, cv + 3 * D, eps);  // video as v2a context
-    normw(c, ax, ah, Ta, Da, ba.v2a_norm, ba.sst_ca_a, ca, ba.sst_ca_a + Da, ca + Da, eps);                   // audio as a2v context
-    normw(c, ax, ah2, Ta, Da, ba.v2a_norm, ba.sst_ca_a + 2 * Da, ca + 2 * Da, ba.sst_ca_a + 3 * Da, ca + 3 * Da, eps);  // audio as v2a query
+    normw2(c, x, h, h2, N, D, ba.a2v_norm, ba.sst_ca_v, cv, eps);        // video as a2v query (h) and as v2a context (h2)
+    normw2(c, ax, ah, ah2, Ta, Da, ba.v2a_norm, ba.sst_ca_a, ca, eps);   // audio as a2v context (ah) and as v2a query (ah2)
     // A2V: Q from video (temporal RoPE of the video frames), K / V from audio
     linear(c, h, N, D, ba.a2v.wq, ba.a2v.bq, Da, cq);
     linear(c, ah, Ta, Da, ba.a2v.wk, ba.a2v.bk, Da, ak);

@@ -187,3 +187,38 @@ def test_upscaler_and_adain_properties():
     assert torch.allclose(half, 0.5 * a + 0.5 * up, atol=1e-6)
     n = torch.randn_like(up)
     assert torch.allclose(O.renoise(up, n, 0.909375), 0.909375 * n + (1 - 0.909375) * up)
+
+
+def test_av_oracle_structure():
+    """Dual audio/video restatement (T/LTX2Transformer.swift, T/LTX2TransformerBlock.swift): the generic RoPE builder
+    reproduces the video table, audio positions follow createAudioPositionGrid (T/LTXRoPE.swift:627-655), the two streams are
+    coupled only through the cross-modal attentions, and zero cross-modal gates decouple them exactly."""
+    cfg = O.DiTConfig(num_layers=1, num_heads=2, caption_channels=64)
+    av = O.AVConfig(audio_heads=2)
+    c1, s1 = O.rope_table(cfg, 2, 3, 4)
+    c2, s2 = O.rope_table_nd(O.position_grid(2, 3, 4), cfg.inner_dim, cfg.num_heads, cfg.rope_theta, cfg.max_pos)
+    assert torch.equal(c1, c2) and torch.equal(s1, s2)
+    g = O.audio_position_grid(4)
+    assert g.shape == (1, 4)
+    # frame 0 covers mel [0, 1), frame i >= 1 covers [4i-3, 4i+1): mid-points * hop / sr
+    want = torch.tensor([0.5, 3.0, 7.0, 11.0]) * 160.0 / 16000.0
+    assert torch.allclose(g[0], want)
+    w = O.make_av_weights(cfg, av, 4)
+    gen = torch.Generator().manual_seed(1)
+    fhw, Ta, S = (2, 2, 3), 5, 7
+    vl, al = torch.randn(1, 12, 128, generator=gen), torch.randn(1, Ta, 128, generator=gen)
+    vc, ac = torch.randn(1, S, 64, generator=gen), torch.randn(1, S, 64, generator=gen)
+    sg = torch.tensor([0.6])
+    v0, a0 = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, sg, sg, None, None, fhw, Ta)
+    v1, a1 = O.av_dit_forward(w, cfg, av, vl, al * 2.0, vc, ac, sg, sg, None, None, fhw, Ta)
+    assert v0.shape == (1, 12, 128) and a0.shape == (1, Ta, 128)
+    assert O.rel_l2(v1, v0) > 1e-4                     # audio reaches the video stream through a2v
+    # zero a2v gate (table row 4 and the gate embedder's output layer): the video stream no longer sees the audio
+    wz = dict(w)
+    wz["transformer_blocks.0.scale_shift_table_a2v_ca_video"] = w["transformer_blocks.0.scale_shift_table_a2v_ca_video"].clone()
+    wz["transformer_blocks.0.scale_shift_table_a2v_ca_video"][4] = 0
+    wz["av_ca_a2v_gate_adaln_single.linear.weight"] = torch.zeros_like(w["av_ca_a2v_gate_adaln_single.linear.weight"])
+    wz["av_ca_a2v_gate_adaln_single.linear.bias"] = torch.zeros_like(w["av_ca_a2v_gate_adaln_single.linear.bias"])
+    v2, _ = O.av_dit_forward(wz, cfg, av, vl, al, vc, ac, sg, sg, None, None, fhw, Ta)
+    v3, _ = O.av_dit_forward(wz, cfg, av, vl, al * 2.0, vc, ac, sg, sg, None, None, fhw, Ta)
+    assert torch.equal(v2, v3)
