@@ -266,6 +266,13 @@ int ltx_dist_p2p_active(const ltx_ctx* ctx);
 /* Destroys the communicators (collective); the context can be re-initialised with a different layout afterwards. */
 int ltx_dist_shutdown(ltx_ctx* ctx);
 
+/* Page-locked host memory for the caller's input / output buffers (frames, latents): the host-pointer entry points copy
+ * with cudaMemcpyAsync, which only reaches PCIe speed (and only overlaps) from pinned memory -- a pageable 118 MB frame
+ * buffer costs ~24 ms per 25-frame decode, a pinned one ~2 ms.  The Swift adapter wraps the pointer in an MLXArray / Data
+ * without copying. */
+int ltx_host_alloc(void** ptr, size_t bytes);
+int ltx_host_free(void* ptr);
+
 /* Number of kernels launched by this context so far (bench.py reports the per-step delta as gpu_launches). */
 uint64_t ltx_launch_count(const ltx_ctx* ctx);
 /* The CUDA stream (cudaStream_t) every kernel of this context is enqueued on -- for CUDA-event timing by the caller. */

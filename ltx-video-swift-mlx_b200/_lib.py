@@ -83,6 +83,8 @@ SIGNATURES = {
     "ltx_dist_shutdown": (_I, [_P]),
     "ltx_dist_p2p_active": (_I, [_P]),
     "ltx_dist_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "ltx_host_alloc": (_I, [C.POINTER(_P), _SZ]),
+    "ltx_host_free": (_I, [_P]),
     "ltx_launch_count": (_U64, [_P]),
     "ltx_get_stream": (_I, [_P, C.POINTER(_P)]),
     "ltx_set_profiling": (_I, [_P, _I]),

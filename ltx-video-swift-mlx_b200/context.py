@@ -338,14 +338,42 @@ class LtxContext:
         return p.value
 
     # ------------------------------------------------------------------ VAE
-    def vae_decode(self, latent, timestep: Optional[float] = None, decode_noise=None, causal: bool = False) -> np.ndarray:
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """ndarray over page-locked host memory (ltx_host_alloc), for buffers handed to the host-pointer entry points; the
+        memory is released when the array (and every view of it) is garbage-collected."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.lib.ltx_host_alloc(C.byref(p), max(n, 1))
+        if rc != 0:
+            raise LtxError(rc, "ltx_host_alloc failed")
+        lib = self.lib
+
+        class _Owner:
+            def __init__(self, addr):
+                self.addr = addr
+
+            def __del__(self):
+                lib.ltx_host_free(C.c_void_p(self.addr))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        owner = _Owner(p.value)
+        # keep the owner alive as long as the base buffer object is: numpy holds `buf`, `buf` holds the owner
+        buf._owner = owner
+        return arr
+
+    def vae_decode(self, latent, timestep: Optional[float] = None, decode_noise=None, causal: bool = False,
+                   out: Optional[np.ndarray] = None) -> np.ndarray:
         lat = _host(latent, np.float32)
         if lat.ndim == 5:
             lat = lat[0]
         Cc, Fp, Hp, Wp = lat.shape
         lat = np.ascontiguousarray(lat)
         nz = None if decode_noise is None else _host(decode_noise, np.float32)
-        out = np.empty((8 * (Fp - 1) + 1, 32 * Hp, 32 * Wp, 3), dtype=np.float32)
+        shape = (8 * (Fp - 1) + 1, 32 * Hp, 32 * Wp, 3)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        assert out.shape == shape and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
         self._check(self.lib.ltx_vae_decode(self.handle, _ptr(lat), Fp, Hp, Wp, -1.0 if timestep is None else float(timestep),
                                             _ptr(nz), int(causal), _ptr(out)))
         return out

@@ -129,6 +129,17 @@ int ltx_sync(ltx_ctx* c) {
 
 uint64_t ltx_launch_count(const ltx_ctx* c) { return c ? c->launches : 0; }
 
+int ltx_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return LTX_ERR_INVALID_ARGUMENT;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? LTX_OK : LTX_ERR_CUDA;
+}
+
+int ltx_host_free(void* ptr) {
+  if (!ptr) return LTX_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? LTX_OK : LTX_ERR_CUDA;
+}
+
 int ltx_dist_get_unique_id(void* id_out_128) {
   if (!id_out_128) return LTX_ERR_INVALID_ARGUMENT;
   try {
