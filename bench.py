@@ -518,14 +518,14 @@ def run_ours(args, rank, world, local_rank):
     traffic, traffic_note = None, None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01b_gemm_pair_ffn_in_ncu_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01c_gemm_pair_ffn_in_ncu_raw.csv"))))
         hdr, units, last = rows[0], rows[1], rows[-1]
 
         def _bytes(k):
             v, u = float(last[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
-        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01b_gemm_pair_ffn_in_ncu_raw.csv"
+        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01c_gemm_pair_ffn_in_ncu_raw.csv"
     except Exception:
         pass
     gemm = prof["gemm"]

@@ -23,7 +23,7 @@ constexpr int CBM = 128, CBK = 64, CONV_THREADS = 192;
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr uint32_t A_BYTES = CBM * CBK * 2;
   static constexpr uint32_t B_BYTES = BN * CBK * 2;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -416,13 +416,19 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   g.bt = 128 / (g.bw * g.bh);
   g.nt = (T + g.bt - 1) / g.bt; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
   g.ntaps = ntaps; g.tap0 = ntaps == 9 ? 9 : 0;
-  const int bn = Cout >= 256 ? 256 : 128;
+  // tile width: 256 when that still gives every SM a tile, else 128 (the 1024-channel stage of a 25-frame decode has only
+  // 12 voxel tiles: 48 tiles of 256 channels leave two thirds of the SMs idle); 64 for the narrow output conv (128 -> 48)
+  const int m_tiles = g.nt * g.nh * g.nw;
+  int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+  if (bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
   if (bn == 256)
     conv_launch_mode<256>(tmX, tmW, g, epi, s);
-  else
+  else if (bn == 128)
     conv_launch_mode<128>(tmX, tmW, g, epi, s);
+  else
+    conv_launch_mode<64>(tmX, tmW, g, epi, s);
 }
 
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
