@@ -305,6 +305,10 @@ int ltx_op_attention(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt,
  * Vt [H*head_dim, B*ldvb] */
 int ltx_op_attention_hd(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, const float* key_bias, void* O,
                         int B, int H, int head_dim, int Nq, int Nk, float scale);
+/* head_dim 128, B = 1, output rows scattered in blocks: row r goes to o_blocks[r / rows_per_block] + (r % rows_per_block) * H*128
+ * (the Ulysses epilogue that stores each destination rank's token block straight into that rank's buffer; here local pointers) */
+int ltx_op_attention_blocks(ltx_ctx* ctx, const void* Q, const void* K, const void* Vt, int64_t ldvb, int H, int Nq, int Nk,
+                            float scale, void* const* o_blocks, int n_blocks, int rows_per_block);
 int ltx_op_rmsnorm_mod(ltx_ctx* ctx, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm);
 int ltx_op_qknorm_rope(ltx_ctx* ctx, void* x_bf16, int M, int D, const float* w, const float* cos_tab, const float* sin_tab,

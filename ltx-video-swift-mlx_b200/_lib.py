@@ -96,6 +96,7 @@ SIGNATURES = {
     "ltx_op_gemm_q": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I]),
     "ltx_op_attention": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _F]),
     "ltx_op_attention_hd": (_I, [_P, _P, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _I, _F]),
+    "ltx_op_attention_blocks": (_I, [_P, _P, _P, _P, _I64, _I, _I, _I, _F, C.POINTER(_P), _I, _I]),
     "ltx_op_rmsnorm_mod": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _I]),
     "ltx_op_qknorm_rope": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _F]),
     "ltx_op_conv3d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),

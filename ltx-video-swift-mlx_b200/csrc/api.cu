@@ -775,6 +775,20 @@ int ltx_op_attention_hd(ltx_ctx* c, const void* Q, const void* K, const void* Vt
   });
 }
 
+int ltx_op_attention_blocks(ltx_ctx* c, const void* Q, const void* K, const void* Vt, int64_t ldvb, int H, int Nq, int Nk,
+                            float scale, void* const* o_blocks, int n_blocks, int rows_per_block) {
+  return guarded(c, [&] {
+    LTX_CHECK(o_blocks && n_blocks >= 1 && n_blocks <= LTX_MAX_PEERS && rows_per_block > 0 && n_blocks * rows_per_block >= Nq,
+              LTX_ERR_INVALID_ARGUMENT, "bad output blocks");
+    const int D = H * 128;
+    PeerTable t = {};
+    for (int i = 0; i < n_blocks; ++i) t.p[i] = o_blocks[i];
+    launch_attention(reinterpret_cast<const bf16*>(Q), D, reinterpret_cast<const bf16*>(K), D, reinterpret_cast<const bf16*>(Vt), ldvb,
+                     nullptr, reinterpret_cast<bf16*>(o_blocks[0]), D, 1, H, Nq, Nk, D, scale, c->stream, &t, rows_per_block);
+    c->launches++;
+  });
+}
+
 int ltx_op_rmsnorm_mod(ltx_ctx* c, const float* x, void* out_bf16, int M, int D, const float* tbl_shift,
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm) {
   return guarded(c, [&] {

@@ -377,6 +377,11 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
   p.ldo = ldo;
   p.o_rows_per_block = 0;
   p.o_blocks = PeerTable{};
+  if (o_blocks) {
+    LTX_CHECK(B == 1 && rows_per_block > 0, 2, "attention: peer-memory output needs B == 1");
+    p.o_rows_per_block = rows_per_block;
+    p.o_blocks = *o_blocks;
+  }
   if (D == H * 128)
     attention_launch<128>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
   else

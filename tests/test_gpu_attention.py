@@ -98,3 +98,25 @@ def test_attention_is_deterministic(ctx, H, HD, Nq, Nk):
         outs.append(o)
     for o in outs[1:]:
         assert torch.equal(o.view(torch.int16), outs[0].view(torch.int16))
+
+
+def test_attention_block_scattered_output(ctx):
+    """The Ulysses epilogue (output row blocks stored into per-destination buffers) equals the plain output, bit for bit."""
+    import ctypes
+    H, Nq, Nk, D = 4, 192, 320, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(Nq, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(Nk, D, device="cuda", generator=g).bfloat16()
+    vt = torch.randn(D, Nk, device="cuda", generator=g).bfloat16()
+    plain = torch.empty(Nq, D, device="cuda", dtype=torch.bfloat16)
+    rows = 64
+    blocks = [torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+    torch.cuda.synchronize()
+    ctx._check(ctx.lib.ltx_op_attention(ctx.handle, q.data_ptr(), k.data_ptr(), vt.data_ptr(), Nk, None, plain.data_ptr(), 1, H, Nq, Nk,
+                                        1 / math.sqrt(128)))
+    arr = (ctypes.c_void_p * 3)(*[b.data_ptr() for b in blocks])
+    ctx._check(ctx.lib.ltx_op_attention_blocks(ctx.handle, q.data_ptr(), k.data_ptr(), vt.data_ptr(), Nk, H, Nq, Nk, 1 / math.sqrt(128),
+                                               arr, 3, rows))
+    ctx.sync()
+    got = torch.cat(blocks, 0)
+    assert torch.equal(got.view(torch.int16), plain.view(torch.int16))
