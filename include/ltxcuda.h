@@ -92,12 +92,19 @@ int ltx_load_tensor(ltx_ctx* ctx, const char* key, const void* host_data, ltx_dt
  * 4 = latent upscaler file (loadSpatialUpscaler, Models/Upscaler/SpatialUpscaler.swift:262-300, names prefixed "upscaler.";
  * conv kernels are taken in the checkpoint's (O, I, kD, kH, kW) layout),
  * 5 = dual audio/video transformer (loadTransformerWeights(includeAudio: true), :605-639: the audio_*, av_ca_* and
- * cross-modal tensors are kept under their own names).
+ * cross-modal tensors are kept under their own names).  ltx_map_weight_key also accepts which = 6: a LoRA layer key ->
+ * the model weight it patches (LoRAKeyMapper.loraKeyToModelKey, LoRA/LoRALoader.swift:209-243).
  * F32 / BF16 / F16 tensors are accepted.  n_loaded (nullable) receives the number of tensors taken.  Follow with
  * ltx_finalize_weights.  ltx_map_weight_key exposes the name mapping alone (no context, no GPU): it writes the mapped name,
  * or an empty string for a tensor the loader skips, into out[cap]. */
 int ltx_load_safetensors(ltx_ctx* ctx, const char* path, int which, int* n_loaded);
 int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap);
+/* LoRA fuse at load time -- LoRAAdapter.fuseWeights (LoRA/LoRAAdapter.swift:64-166) with the delta of LoRAWeights.getDelta
+ * (LoRA/LoRALoader.swift:162-178): W[out, in] += scale * up[out, rank] @ down[rank, in] on the loaded tensor `key` (post-mapping
+ * name; ltx_map_weight_key(6, loraLayerKey) is LoRAKeyMapper.loraKeyToModelKey :209-243).  Call after loading the base weights
+ * and BEFORE ltx_finalize_weights: quantisation then sees the merged weight (the reference dequantises, merges, requantises).
+ * rank must be a multiple of 8; scale = user scale * alpha / rank as computed by the reference's loader. */
+int ltx_fuse_lora(ltx_ctx* ctx, const char* key, const void* down, const void* up, ltx_dtype dtype, int rank, float scale);
 /* Precision of the DiT path.  16 (default): the reference's "bf16" mode -- bf16 weights and tensor-core operands, fp32
  * accumulation / residual stream / norms / softmax; velocity within rel-L2 1e-2 of the fp32 graph.  32: fp32 mode -- DiT
  * matrices stay fp32, activations fp32, every Linear runs as a split-bf16 (3-term) tensor-core product that is exact to

@@ -198,6 +198,14 @@ class LtxContext:
         self._check(self.lib.ltx_load_safetensors(self.handle, str(path).encode(), int(which), C.byref(n)))
         return n.value
 
+    def fuse_lora(self, key: str, down, up, scale: float = 1.0):
+        """LoRAAdapter.fuseWeights for one layer: W[key] += scale * up @ down (down [r, in], up [out, r]); before finalize_weights."""
+        code = _dtype_code(down)
+        assert _dtype_code(up) == code
+        d, u = _host(down), _host(up)
+        assert d.ndim == 2 and u.ndim == 2 and d.shape[0] == u.shape[1]
+        self._check(self.lib.ltx_fuse_lora(self.handle, key.encode(), _ptr(d), _ptr(u), code, int(d.shape[0]), float(scale)))
+
     def set_precision(self, bits: int):
         """16 = bf16 mode (default), 32 = fp32 mode (fp32 DiT weights, split-bf16 tensor-core GEMMs); before loading weights."""
         self._check(self.lib.ltx_set_precision(self.handle, int(bits)))

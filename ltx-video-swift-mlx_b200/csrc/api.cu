@@ -224,19 +224,27 @@ int ltx_load_safetensors(ltx_ctx* c, const char* path, int which, int* n_loaded)
 }
 
 int ltx_map_weight_key(int which, const char* file_key, char* out, size_t cap) {
-  if (!file_key || !out || cap == 0 || which < 1 || which > 5) return LTX_ERR_INVALID_ARGUMENT;
+  if (!file_key || !out || cap == 0 || which < 1 || which > 6) return LTX_ERR_INVALID_ARGUMENT;
   try {
     const std::string m = which == 1   ? map_transformer_key(file_key)
                           : which == 2 ? map_vae_key(file_key)
                           : which == 3 ? map_vae_encoder_key(file_key)
                           : which == 4 ? map_upscaler_key(file_key)
-                                       : map_transformer_key(file_key, true);
+                          : which == 5 ? map_transformer_key(file_key, true)
+                                       : map_lora_key(file_key);
     if (m.size() + 1 > cap) return LTX_ERR_INVALID_ARGUMENT;
     memcpy(out, m.c_str(), m.size() + 1);
     return LTX_OK;
   } catch (...) {
     return LTX_ERR_WEIGHTS;
   }
+}
+
+int ltx_fuse_lora(ltx_ctx* c, const char* key, const void* down, const void* up, ltx_dtype dtype, int rank, float scale) {
+  return guarded(c, [&] {
+    LTX_CHECK(key != nullptr, LTX_ERR_INVALID_ARGUMENT, "null key");
+    fuse_lora(c, key, down, up, dtype, rank, scale);
+  });
 }
 
 int ltx_init_random_weights(ltx_ctx* c, int which, uint64_t seed) {

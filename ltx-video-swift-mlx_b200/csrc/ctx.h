@@ -331,4 +331,6 @@ int load_safetensors(ltx_ctx* c, const char* path, int which);
 const DevTensor& get_tensor(ltx_ctx* c, const std::string& key);
 void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int dtype, const int64_t* shape, int ndim);
 void init_random_weights(ltx_ctx* c, int which, uint64_t seed);
+void fuse_lora(ltx_ctx* c, const std::string& key, const void* down_host, const void* up_host, int dtype, int rank, float scale);
+std::string map_lora_key(const std::string& lora_key);
 }  // namespace ltx

@@ -281,6 +281,18 @@ std::string map_upscaler_key(const std::string& file_key) {
   return "upscaler." + file_key;
 }
 
+// LoRAKeyMapper.loraKeyToModelKey (LoRA/LoRALoader.swift:209-243): LoRA layer key (ComfyUI / Diffusers naming) -> the model weight
+// it patches, in the context's post-mapping names.
+std::string map_lora_key(const std::string& lora_key) {
+  std::string k = lora_key;
+  if (starts_with(k, "diffusion_model.")) k = k.substr(strlen("diffusion_model."));
+  replace_all(k, ".emb.timestep_embedder.", ".emb.");
+  replace_all(k, ".to_out.0", ".to_out");
+  replace_all(k, ".ff.net.0.proj", ".ff.project_in.proj");
+  replace_all(k, ".ff.net.2", ".ff.project_out");
+  return k + ".weight";
+}
+
 // which: 1 = transformer tensors (mapTransformerKey), 2 = VAE decoder tensors (mapVAEWeights), 3 = VAE encoder tensors
 // (mapVAEEncoderWeights), 4 = latent upscaler file.  Returns how many were loaded.
 int load_safetensors(ltx_ctx* c, const char* path, int which) {

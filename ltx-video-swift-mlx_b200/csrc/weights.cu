@@ -115,6 +115,67 @@ void load_tensor_host(ltx_ctx* c, const std::string& key, const void* host, int 
   LTX_CUDA(cudaFree(stage));
 }
 
+namespace {
+__global__ void lora_add_kernel(void* w, int w_is_bf16, const float* delta, float scale, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (w_is_bf16) {
+      bf16* p = reinterpret_cast<bf16*>(w);
+      p[i] = __float2bfloat16(__bfloat162float(p[i]) + scale * delta[i]);
+    } else {
+      float* p = reinterpret_cast<float*>(w);
+      p[i] += scale * delta[i];
+    }
+  }
+}
+}  // namespace
+
+// LoRA fuse at load time (LoRAAdapter.fuseWeights, LoRA/LoRAAdapter.swift:64-166, standard-Linear path; delta =
+// scale * up @ down, LoRA/LoRALoader.swift:162-178): W[out, in] += scale * up[out, r] @ down[r, in], on the raw tensor `key`
+// (post-mapping name, LoRAKeyMapper.loraKeyToModelKey :209-243) before ltx_finalize_weights packs / quantises it -- so a
+// quantised model is "merge, then quantise", the same result as the reference's dequantise -> merge -> requantise up to one
+// rounding.  The product runs on the tensor-core GEMM (bf16 operands, fp32 accumulation), the add in fp32.
+void fuse_lora(ltx_ctx* c, const std::string& key, const void* down_host, const void* up_host, int dtype, int rank, float scale) {
+  auto it = c->tensors.find(key);
+  LTX_CHECK(it != c->tensors.end(), LTX_ERR_WEIGHTS,
+            "LoRA target '" + key + "' is not loaded (fuse before ltx_finalize_weights, after loading the base weights)");
+  DevTensor& w = it->second;
+  LTX_CHECK(w.shape.size() == 2 && rank > 0 && rank % 8 == 0, LTX_ERR_INVALID_ARGUMENT, "LoRA: 2-D target and a rank that is a multiple of 8");
+  LTX_CHECK(down_host && up_host && (dtype == LTX_F32 || dtype == LTX_BF16 || dtype == LTX_F16), LTX_ERR_INVALID_ARGUMENT, "LoRA: bad factors");
+  const int64_t out = w.shape[0], in = w.shape[1];
+  // stage both factors as bf16 device tensors through the regular loader (temporary keys)
+  const int64_t ds[2] = {rank, in}, us[2] = {out, rank};
+  const int saved_precision = c->precision;
+  c->precision = 16;   // the factors are always staged as bf16, also in fp32 mode
+  load_tensor_host(c, "__lora.down.weight", down_host, dtype, ds, 2);
+  load_tensor_host(c, "__lora.up.weight", up_host, dtype, us, 2);
+  c->precision = saved_precision;
+  const bf16* down = reinterpret_cast<const bf16*>(c->tensors["__lora.down.weight"].ptr);
+  const bf16* up = reinterpret_cast<const bf16*>(c->tensors["__lora.up.weight"].ptr);
+  bf16* down_t = nullptr;   // [in, rank]: the GEMM's B operand is K-major
+  float* delta = nullptr;
+  LTX_CUDA(cudaMalloc(&down_t, static_cast<size_t>(in) * rank * 2));
+  LTX_CUDA(cudaMalloc(&delta, static_cast<size_t>(out) * in * 4));
+  launch_transpose_bf16(down, in, rank, static_cast<int>(in), down_t, rank, c->stream);
+  GemmEpi e;
+  e.mode = EPI_F32; e.out = delta; e.ldo = in;
+  launch_gemm(up, rank, down_t, rank, static_cast<int>(out), static_cast<int>(in), rank, e, c->stream);
+  const int64_t n = out * in;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  lora_add_kernel<<<static_cast<int>(blocks), 256, 0, c->stream>>>(w.ptr, w.dtype == LTX_BF16 ? 1 : 0, delta, scale, n);
+  LTX_CUDA(cudaGetLastError());
+  LTX_CUDA(cudaStreamSynchronize(c->stream));
+  c->launches += 3;
+  cudaFree(down_t);
+  cudaFree(delta);
+  for (const char* k : {"__lora.down.weight", "__lora.up.weight"}) {
+    auto t = c->tensors.find(k);
+    cudaFree(t->second.ptr);
+    c->tensors.erase(t);
+  }
+}
+
 // Random-init weights of the named architecture (SURVEY Appendix C shapes).  Scales keep activations O(1):
 // Linear N(0, 1/in), biases N(0, 0.02^2), scale-shift tables N(0, 0.1^2), q/k norm weights 1 + N(0, 0.1^2).
 void init_random_weights(ltx_ctx* c, int which, uint64_t seed) {

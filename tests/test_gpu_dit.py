@@ -206,3 +206,40 @@ def test_fp32_mode_rejects_late_switch_and_quantisation():
     with pytest.raises(product().LtxError):
         ctx.finalize_weights(quant_bits=8)
     ctx.close()
+
+
+def test_lora_fuse_matches_merged_weights():
+    """ltx_fuse_lora (LoRA/LoRAAdapter.swift:64-166): forward with fused factors == oracle forward on W + scale * up @ down, for
+    bf16 and for weights quantised after the merge; the key mapper follows LoRAKeyMapper.loraKeyToModelKey."""
+    ctxmod = product()
+    assert ctxmod.map_weight_key(6, "diffusion_model.transformer_blocks.0.attn1.to_out.0") == "transformer_blocks.0.attn1.to_out.weight"
+    assert ctxmod.map_weight_key(6, "diffusion_model.transformer_blocks.3.ff.net.0.proj") == "transformer_blocks.3.ff.project_in.proj.weight"
+    assert ctxmod.map_weight_key(6, "transformer_blocks.3.ff.net.2") == "transformer_blocks.3.ff.project_out.weight"
+    ocfg, pcfg = small_dit_config(2, 2)
+    w = O.make_dit_weights(ocfg, 21)
+    g = torch.Generator().manual_seed(4)
+    targets = ["transformer_blocks.0.attn1.to_q.weight", "transformer_blocks.0.attn1.to_out.weight",
+               "transformer_blocks.1.attn2.to_k.weight", "transformer_blocks.1.ff.project_in.proj.weight"]
+    rank, scale = 16, 0.7
+    merged = dict(w)
+    factors = {}
+    for k in targets:
+        out_f, in_f = w[k].shape
+        down = (torch.randn(rank, in_f, generator=g) / in_f ** 0.5).bfloat16()
+        up = (torch.randn(out_f, rank, generator=g) * 0.3).bfloat16()
+        factors[k] = (down, up)
+        merged[k] = O.bf16_round(w[k].float() + scale * (up.float() @ down.float()))
+    ctx = ctxmod.LtxContext(pcfg, 0)
+    ctx.load_weights(w)
+    for k, (down, up) in factors.items():
+        ctx.fuse_lora(k, down, up, scale)
+    ctx.finalize_weights()
+    fhw, S = (2, 4, 6), 40
+    lat, cx, _ = _inputs(ocfg, fhw, S, 5, 1, 0)
+    sig = torch.tensor([0.6])
+    ref = O.dit_forward(merged, ocfg, lat.float(), cx.float(), sig, None, fhw)
+    base = O.dit_forward(w, ocfg, lat.float(), cx.float(), sig, None, fhw)
+    out = ctx.dit_forward(lat, cx, sig.numpy(), None, fhw)
+    assert rel_l2(ref, base) > 5e-2            # the adapters matter
+    assert rel_l2(out, ref) <= TOL
+    ctx.close()
