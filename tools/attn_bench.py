@@ -1,6 +1,7 @@
 """Micro-benchmark of the attention kernel on the DiT shapes."""
+import os
 import math, sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ltx_video_swift_mlx_b200  # noqa
 from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
 ctx = LtxContext(LTXTransformerConfig(num_layers=1, num_attention_heads=1), 0)

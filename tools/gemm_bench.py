@@ -1,6 +1,7 @@
 """Micro-benchmark of the tcgen05 GEMM on the DiT shapes (device time via CUDA events on the library stream)."""
+import os
 import math, os, sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ltx_video_swift_mlx_b200  # noqa
 from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
 

@@ -2,9 +2,9 @@
 # ncu evidence for every hot kernel class: plain run first, then one `--set full` capture per kernel, then the launch list.
 mkdir -p gpurun_out
 R=${1:-r01b}
-timeout 300 python tools_ncu_target.py > gpurun_out/plain_ncu_target.log 2>&1 || { echo "plain target failed"; tail -5 gpurun_out/plain_ncu_target.log; exit 1; }
+timeout 300 python tools/ncu_target.py > gpurun_out/plain_ncu_target.log 2>&1 || { echo "plain target failed"; tail -5 gpurun_out/plain_ncu_target.log; exit 1; }
 cap() {  # name regex skip
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/${R}_$1 python tools_ncu_target.py > gpurun_out/ncu_$1.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/${R}_$1 python tools/ncu_target.py > gpurun_out/ncu_$1.log 2>&1
   echo "ncu $1 exit $?"
 }
 cap gemm_pair_ffn_in gemm_bf16_2cta 2

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-./tools_gpu_suite.sh "$@" > gpurun_out/suite.log 2>&1; grep -E "^===|passed|failed|exit|Error|error" gpurun_out/suite.log | head -40
-timeout 300 python tools_attn_bench.py 2>&1 | tee gpurun_out/attn_bench.log | tail -2
+tools/gpu_suite.sh "$@" > gpurun_out/suite.log 2>&1; grep -E "^===|passed|failed|exit|Error|error" gpurun_out/suite.log | head -40
+timeout 300 python tools/attn_bench.py 2>&1 | tee gpurun_out/attn_bench.log | tail -2
 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -2 gpurun_out/bench.err
 python -c "
 import json; b=json.load(open('gpurun_out/bench.json'))

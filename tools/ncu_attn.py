@@ -1,7 +1,8 @@
 """Short program for an `ncu --set full` capture of the attention kernel alone (self-attention, N = 6144: 48 key tiles per CTA,
 so the steady-state loop dominates the sampled stalls)."""
+import os
 import math, sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ltx_video_swift_mlx_b200  # noqa
 from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
 ctx = LtxContext(LTXTransformerConfig(num_layers=1, num_attention_heads=1), 0)
