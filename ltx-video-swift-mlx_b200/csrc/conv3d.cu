@@ -35,6 +35,8 @@ struct ConvGeom {
   int bt, bh, bw;     // voxel box of one M tile (bt*bh*bw == 128)
   int nt, nh, nw;     // tiles per axis
   int tap0, ntaps;    // taps [tap0, tap0 + ntaps) of the 3x3x3 stencil (27: Conv3d; 9 starting at 9: per-frame Conv2d, dt = 1)
+  int ksplit;         // > 1: the taps are split into ksplit groups, each an own work item writing raw partial sums to
+                      // out + ks * T*H*W*Cout (MODE 0, no bias / residual); conv_splitk_reduce_kernel adds them up in a fixed order
 };
 
 __device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
@@ -118,9 +120,11 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = g.nt * g.nh * g.nw;
   const int num_n = (g.Cout + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * g.ksplit;
   const int kchunks = g.Cin / CBK;
-  const int num_k = g.ntaps * kchunks;
+  const int taps_per_split = g.ntaps / g.ksplit;
+  const int num_k = taps_per_split * kchunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -142,11 +146,12 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int ks = tile / num_mn, mn = tile % num_mn;
+        const int m_blk = mn % num_m, n_blk = mn / num_m;
         const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
         const int t0 = it * g.bt, h0 = ih * g.bh, w0 = iw * g.bw;
         for (int kb = 0; kb < num_k; ++kb) {
-          const int wtap = kb / kchunks, kc = kb % kchunks;
+          const int wtap = ks * taps_per_split + kb / kchunks, kc = kb % kchunks;
           const int tap = g.tap0 + wtap;
           const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
           mbar_wait(&empty[stage], phase ^ 1);
@@ -188,7 +193,8 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int q = warp & 3;
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int ks = tile / num_mn, mn = tile % num_mn;
+      const int m_blk = mn % num_m, n_blk = mn / num_m;
       const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
       const int as = t & 1;
       const uint32_t aphase = (t >> 1) & 1;
@@ -206,6 +212,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // offsets are computed once per tile, the residual values are fetched before the first store
         float* stage = epi_stage + (warp - 2) * (EPI_STAGE_BYTES / 4);
         const int cg = lane & 7, rsub = lane >> 3;
+        float* outp = ep.out + static_cast<int64_t>(ks) * g.T * g.H * g.W * g.Cout;   // split-K: this group's partial slab
         int64_t voff[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -223,7 +230,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, r);
           const int col = n_blk * BN + c * 32 + cg * 4;
           if (col < g.Cout) {
-            const float4 bv = *reinterpret_cast<const float4*>(ep.bias + col);
+            const float4 bv = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 xin[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -234,7 +241,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               if (voff[i] < 0) continue;
               const int rr = rsub + 4 * i;
               const float4 a = reinterpret_cast<const float4*>(stage)[rr * 8 + (cg ^ (rr & 7))];
-              *reinterpret_cast<float4*>(ep.out + voff[i] + col) =
+              *reinterpret_cast<float4*>(outp + voff[i] + col) =
                   make_float4(a.x + bv.x + xin[i].x, a.y + bv.y + xin[i].y, a.z + bv.z + xin[i].z, a.w + bv.w + xin[i].w);
             }
           }
@@ -363,6 +370,28 @@ __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out
   }
 }
 
+// out = sum_ks partial[ks] + bias (+ resid), fixed summation order (deterministic); float4 over [V, Cout]
+__global__ void conv_splitk_reduce_kernel(const float* part, int ksplit, int64_t slab4, int C4, const float* bias, const float* resid,
+                                          float* out) {
+  griddep_launch();
+  griddep_wait();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < slab4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(part)[i];
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = reinterpret_cast<const float4*>(part)[k * slab4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float4 bv = reinterpret_cast<const float4*>(bias)[i % C4];
+    a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+    if (resid) {
+      const float4 r = reinterpret_cast<const float4*>(resid)[i];
+      a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+
 int best_pow2(int extent, int budget) {
   // power of two <= budget that wastes the least of `extent` when tiling; ties -> larger
   int best = 1;
@@ -384,7 +413,7 @@ void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom&
     LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM)));
     configured = true;
   }
-  const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN);
+  const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN) * g.ksplit;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
   LTX_CUDA(cudaGetLastError());
@@ -402,8 +431,13 @@ void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
 
 }  // namespace
 
-void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
-                   cudaStream_t s, int ntaps) {
+bool conv3d_wants_tap_split(int H, int W, int Cin, int Cout) {
+  return H * W <= 1024 && Cout >= 256 && Cout % 4 == 0 && static_cast<int64_t>(27) * Cin >= 8192;
+}
+
+void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi_in,
+                   cudaStream_t s, int ntaps, float* splitk_scratch, size_t splitk_scratch_bytes) {
+  ConvEpi epi = epi_in;
   LTX_CHECK(T > 0 && H > 1 && W > 1, 2, "conv3d: bad volume (reflect padding needs H, W >= 2)");
   LTX_CHECK(ntaps == 27 || ntaps == 9, 2, "conv3d: 27 taps (3x3x3) or 9 taps (per-frame 3x3)");
   LTX_CHECK(Cin % 64 == 0, 2, "conv3d: Cin must be a multiple of 64");
@@ -416,11 +450,26 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   g.bt = 128 / (g.bw * g.bh);
   g.nt = (T + g.bt - 1) / g.bt; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
   g.ntaps = ntaps; g.tap0 = ntaps == 9 ? 9 : 0;
+  g.ksplit = 1;
   // tile width: 256 when that still gives every SM a tile, else 128 (the 1024-channel stage of a 25-frame decode has only
   // 12 voxel tiles: 48 tiles of 256 channels leave two thirds of the SMs idle); 64 for the narrow output conv (128 -> 48)
   const int m_tiles = g.nt * g.nh * g.nw;
   int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
-  if (bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;
+  // Tile-starved convs (the 1024-channel stage of a 25-frame decode has 12 voxel tiles x 4 channel tiles for 148 SMs, each
+  // 27 x 1024 deep): split the taps into 3 groups (one per dt) -> 3x the work items at full tile width; the partial sums go to
+  // a scratch slab each and are added in a fixed order by a small reduction pass (+ bias, + residual).
+  // The rule looks at the frame geometry and the channel counts only -- never at T -- so that a temporal shard takes the same
+  // decision as the unsharded decode and multi-GPU results stay bit-identical.
+  const size_t slab = static_cast<size_t>(T) * H * W * Cout * 4;
+  const bool can_split = epi.mode == 0 && ntaps == 27 && splitk_scratch != nullptr && 3 * slab <= splitk_scratch_bytes &&
+                         conv3d_wants_tap_split(H, W, Cin, Cout);
+  if (can_split) g.ksplit = 3;
+  else if (bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
+  // cost ~0.7 of a 256-wide one, so they only pay when 256 leaves most SMs without a tile)
+  const float* final_bias = epi.bias;
+  const float* final_resid = epi.resid;
+  float* final_out = epi.out;
+  if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
   if (bn == 256)
@@ -429,6 +478,14 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
     conv_launch_mode<128>(tmX, tmW, g, epi, s);
   else
     conv_launch_mode<64>(tmX, tmW, g, epi, s);
+  if (g.ksplit > 1) {
+    const int64_t slab4 = static_cast<int64_t>(slab / 16);
+    int64_t blocks = (slab4 + 255) / 256;
+    if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+    launch_pdl(PDL_VAE, conv_splitk_reduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, splitk_scratch, g.ksplit, slab4,
+               Cout / 4, final_bias, final_resid, final_out);
+    LTX_CUDA(cudaGetLastError());
+  }
 }
 
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,

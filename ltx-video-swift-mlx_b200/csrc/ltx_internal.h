@@ -217,8 +217,10 @@ struct ConvEpi {
 };
 // x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [ntaps][Cout][Cin]; 3x3x3 cross-correlation (ntaps = 27) or a
 // per-frame 3x3 one (ntaps = 9: only the dt = 1 taps, the upscaler's Conv2d).
+bool conv3d_wants_tap_split(int H, int W, int Cin, int Cout);
+// splitk_scratch (optional, >= 3 * T*H*W*Cout fp32): lets tile-starved mode-0 convs split their taps over 3 work items.
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
-                   cudaStream_t s, int ntaps = 27);
+                   cudaStream_t s, int ntaps = 27, float* splitk_scratch = nullptr, size_t splitk_scratch_bytes = 0);
 // pad (+ optional pixel-norm * (1+scale) + shift -> SiLU, or per-channel affine) from fp32 [T,H,W,C] into bf16 [T+2,H+2,W+2,C]
 // mode 0: copy ; 1: x*a[c]+b[c] (denormalise) ; 2: silu(pn(x)*(1+a[c])+b[c]) (a, b nullable) ; 3: silu(x*a[c]+b[c])
 // pad: VAE_PAD_* bits (0 = reflect H/W + one replicated frame each side: the decoder's non-causal convolution)

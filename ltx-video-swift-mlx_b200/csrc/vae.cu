@@ -105,7 +105,14 @@ void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const f
   e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin; e.t_shift = t_shift;
   ProfScope ps(c, PROF_CONV, 2.0 * w.taps * w.cin * w.cout * vox,
                vox * (w.cin * 2.0 + w.cout * 4.0) + static_cast<double>(w.taps) * w.cin * w.cout * 2.0);
-  launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream, w.taps);
+  // scratch for the tap-split of tile-starved convs (three partial-sum slabs)
+  const size_t slab3 = static_cast<size_t>(3) * T * H * W * w.cout * 4;
+  float* scratch = nullptr;
+  if (epi_mode == 0 && w.taps == 27 && conv3d_wants_tap_split(H, W, w.cin, w.cout)) {
+    c->v_split.reserve(slab3);
+    scratch = c->v_split.as<float>();
+  }
+  launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream, w.taps, scratch, scratch ? slab3 : 0);
 }
 
 namespace {
