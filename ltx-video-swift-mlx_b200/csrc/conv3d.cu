@@ -247,6 +247,46 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           __syncwarp();
         }
+      } else if (MODE == 3) {
+        // fused prologue of the next conv (one tile holds all Cout channels of a voxel; thread = voxel): pass 1 sums the
+        // squares of (acc + bias) straight from TMEM, pass 2 re-reads TMEM, normalises, modulates, SiLU, packs to bf16 and
+        // stores 64 B per 32 channels into the interior of the next padded volume
+        const int nch = (g.Cout + 31) / 32;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]) + ep.bias[c * 32 + j];
+            ss += v * v;
+          }
+        }
+        const float rstd = rsqrtf(ss / g.Cout + 1e-8f);
+        bf16* dst = ep.next_pad + ((static_cast<int64_t>(vt + ep.next_tshift) * (g.H + 2) + (vh + 1)) * (g.W + 2) + (vw + 1)) * g.Cout;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (valid) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int col = c * 32 + j;
+              const float sc0 = ep.next_scale ? 1.f + ep.next_scale[col] : 1.f, sc1 = ep.next_scale ? 1.f + ep.next_scale[col + 1] : 1.f;
+              const float sh0 = ep.next_shift ? ep.next_shift[col] : 0.f, sh1 = ep.next_shift ? ep.next_shift[col + 1] : 0.f;
+              const float a = silu((__uint_as_float(r[j]) + ep.bias[col]) * rstd * sc0 + sh0);
+              const float b = silu((__uint_as_float(r[j + 1]) + ep.bias[col + 1]) * rstd * sc1 + sh1);
+              pk[j >> 1] = pack_bf16(a, b);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        }
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -392,6 +432,35 @@ __global__ void conv_splitk_reduce_kernel(const float* part, int ksplit, int64_t
   }
 }
 
+// Padding voxels of a bf16 padded volume from its interior (see launch_vae_halo_fill); one warp per padding voxel.
+__global__ void __launch_bounds__(256) vae_halo_fill_kernel(bf16* vol, int T, int H, int W, int C, int pad) {
+  griddep_launch();
+  griddep_wait();
+  const int tshift = (pad & 1) ? 2 : 1;
+  const bool zero_hw = (pad & 2) != 0, zero_t = (pad & 4) != 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
+  const int64_t wid0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = C >> 3;   // uint4 = 8 bf16
+  for (int64_t pv = wid0; pv < nvox; pv += nwarps) {
+    const int pw = static_cast<int>(pv % (W + 2));
+    const int ph = static_cast<int>((pv / (W + 2)) % (H + 2));
+    const int pt = static_cast<int>(pv / (static_cast<int64_t>(W + 2) * (H + 2)));
+    int ws = pw - 1, hs = ph - 1, ts = pt - (zero_t ? 1 : tshift);
+    const bool interior = ws >= 0 && ws < W && hs >= 0 && hs < H && ts >= 0 && ts < T;
+    if (interior) continue;
+    const bool zero = (zero_hw && (ws < 0 || ws >= W || hs < 0 || hs >= H)) || (zero_t && (ts < 0 || ts >= T));
+    ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);
+    hs = hs < 0 ? -hs : (hs >= H ? 2 * H - 2 - hs : hs);
+    ts = ts < 0 ? 0 : (ts >= T ? T - 1 : ts);
+    const int tpad = ts + (zero_t ? 1 : tshift);
+    const uint4* src = reinterpret_cast<const uint4*>(vol + ((static_cast<int64_t>(tpad) * (H + 2) + hs + 1) * (W + 2) + ws + 1) * C);
+    uint4* dst = reinterpret_cast<uint4*>(vol + pv * C);
+    for (int i = lane; i < nv; i += 32) dst[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : src[i];
+  }
+}
+
 int best_pow2(int extent, int budget) {
   // power of two <= budget that wastes the least of `extent` when tiling; ties -> larger
   int best = 1;
@@ -425,6 +494,7 @@ void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
     case 0: conv_launch<BN, 0>(tmX, tmW, g, ep, s); break;
     case 1: conv_launch<BN, 1>(tmX, tmW, g, ep, s); break;
     case 2: conv_launch<BN, 2>(tmX, tmW, g, ep, s); break;
+    case 3: conv_launch<BN, 3>(tmX, tmW, g, ep, s); break;
     default: LTX_CHECK(false, 2, "bad conv epilogue mode");
   }
 }
@@ -443,6 +513,8 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   LTX_CHECK(Cin % 64 == 0, 2, "conv3d: Cin must be a multiple of 64");
   LTX_CHECK(epi.mode != 0 || Cout % 4 == 0, 2, "conv3d: Cout must be a multiple of 4");
   LTX_CHECK(epi.mode != 1 || (Cout % 32 == 0 && Cin % 8 == 0 && epi.resid != nullptr), 2, "conv3d: bad d2s configuration");
+  LTX_CHECK(epi.mode != 3 || (Cout % 32 == 0 && Cout <= 256 && Cout > 64 && epi.next_pad != nullptr && ntaps == 27), 2,
+            "conv3d: the fused-prologue epilogue needs 64 < Cout <= 256 (one tile = all channels of a voxel)");
   ConvGeom g;
   g.T = T; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
   g.bw = best_pow2(W, 128);
@@ -464,12 +536,13 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   const bool can_split = epi.mode == 0 && ntaps == 27 && splitk_scratch != nullptr && 3 * slab <= splitk_scratch_bytes &&
                          conv3d_wants_tap_split(H, W, Cin, Cout);
   if (can_split) g.ksplit = 3;
-  else if (bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
+  else if (epi.mode != 3 && bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
   // cost ~0.7 of a 256-wide one, so they only pay when 256 leaves most SMs without a tile)
   const float* final_bias = epi.bias;
   const float* final_resid = epi.resid;
   float* final_out = epi.out;
   if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
+  LTX_CHECK(epi.mode != 3 || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
   if (bn == 256)
@@ -486,6 +559,17 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
                Cout / 4, final_bias, final_resid, final_out);
     LTX_CUDA(cudaGetLastError());
   }
+}
+
+void launch_vae_halo_fill(bf16* vol, int T, int H, int W, int C, int pad, cudaStream_t s) {
+  LTX_CHECK(C % 8 == 0 && H > 1 && W > 1, 2, "vae_halo_fill: bad shape");
+  // work ~ padded voxels (interior ones exit at once); a warp per voxel
+  const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
+  int64_t blocks = (nvox + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  launch_pdl(PDL_VAE, vae_halo_fill_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, vol, T, H, W, C, pad);
+  LTX_CUDA(cudaGetLastError());
 }
 
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,

@@ -237,7 +237,7 @@ struct ltx_ctx {
   uint64_t s_serial = 0;
 
   // ---- VAE workspaces
-  ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te, v_split;
+  ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te, v_split, v_pad2;
   ltx::DevBuf av_in[8];   // host-API staging of the dual model's inputs / outputs
   ltx::DevBuf u_part, u_ab, u_stats, u_in, u_out, u_ref;   // encoder / upscaler / AdaIN scratch and host-API staging
 };

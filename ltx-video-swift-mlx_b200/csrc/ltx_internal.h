@@ -214,6 +214,14 @@ struct ConvEpi {
   int Cin;
   int t_shift = 0;          // mode 1: output frame = 2t + p1 - 1 + t_shift (1 on temporal shards other than the first,
                             // which keep the frame the first shard trims; frames < 0 are dropped)
+  // mode 3 (Cout <= tile width): the epilogue is the NEXT conv's padding prologue -- pixel-norm over the voxel's Cout channels
+  // of (acc + bias), * (1 + next_scale) + next_shift, SiLU, bf16, stored into the interior of the next conv's padded volume
+  // [T+2, H+2, W+2, Cout] (frame offset next_tshift: 1, or 2 when causal); launch_vae_halo_fill completes the padding.
+  // The fp32 tensor is never written (VAEResBlock3d conv1 -> conv2, V/VideoDecoder.swift:118-127).
+  bf16* next_pad = nullptr;
+  const float* next_scale = nullptr;
+  const float* next_shift = nullptr;
+  int next_tshift = 1;
 };
 // x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [ntaps][Cout][Cin]; 3x3x3 cross-correlation (ntaps = 27) or a
 // per-frame 3x3 one (ntaps = 9: only the dt = 1 taps, the upscaler's Conv2d).
@@ -225,6 +233,9 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
 // mode 0: copy ; 1: x*a[c]+b[c] (denormalise) ; 2: silu(pn(x)*(1+a[c])+b[c]) (a, b nullable) ; 3: silu(x*a[c]+b[c])
 // pad: VAE_PAD_* bits (0 = reflect H/W + one replicated frame each side: the decoder's non-causal convolution)
 enum { VAE_PAD_CAUSAL = 1, VAE_PAD_ZERO_HW = 2, VAE_PAD_ZERO_T = 4 };
+// fills the padding voxels of a bf16 padded volume [T+2,H+2,W+2,C] whose interior has been written (conv epilogue mode 3):
+// reflect / zero in H, W and frame replication / zero in T, as launch_vae_prep would have produced
+void launch_vae_halo_fill(bf16* pad_vol, int T, int H, int W, int C, int pad, cudaStream_t s);
 void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int mode, const float* a, const float* b,
                      int pad, cudaStream_t s);
 

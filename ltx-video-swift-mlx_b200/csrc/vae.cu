@@ -4,6 +4,8 @@
 // HBM layout: every activation is channels-last fp32 [T, H, W, C] (the residual stream stays fp32); each conv reads a
 // bf16 padded copy produced by the fused pixel-norm/scale-shift/SiLU prologue and writes fp32 through its epilogue
 // (+bias, +residual, depth-to-space scatter, or unpatchify+clip straight into the [F, H, W, 3] frame buffer).
+#include <cstdlib>
+
 #include "ctx.h"
 
 namespace ltx {
@@ -113,6 +115,46 @@ void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const f
     scratch = c->v_split.as<float>();
   }
   launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream, w.taps, scratch, scratch ? slab3 : 0);
+}
+
+// VAEResBlock3d's conv1 -> conv2 hand-over without the fp32 round trip (V/VideoDecoder.swift:118-127): conv1's epilogue
+// normalises, modulates (scale2 / shift2), activates and stores the bf16 interior of conv2's padded volume (conv3d.cu mode 3), a
+// halo pass completes the padding (+ the neighbour exchange on temporal shards), conv2 runs straight from it.
+// Requires 64 < C <= 256 (one tile = all channels of a voxel).
+void vae_resblock_fused(ltx_ctx* c, float* x, const float* sc1, const float* sh1, const float* sc2, const float* sh2, const ConvW& c1,
+                        const ConvW& c2, int T, int H, int W, int pad, int n_active) {
+  const int C = c1.cout;
+  const size_t padded = static_cast<size_t>(T + 2) * (H + 2) * (W + 2);
+  c->v_pad.reserve(padded * c1.cin * 2);
+  c->v_pad2.reserve(padded * C * 2);
+  const double vox = static_cast<double>(T) * H * W;
+  {
+    ProfScope ps(c, PROF_PREP, 0.0, vox * c1.cin * 4.0 + static_cast<double>(padded) * c1.cin * 2.0);
+    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, c1.cin, 2, sc1, sh1, pad, c->stream);
+  }
+  auto exchange = [&](bf16* pv, int ch) {
+    if (n_active <= 1) return;
+    const size_t frame = static_cast<size_t>(H + 2) * (W + 2) * ch;
+    ProfScope ps(c, PROF_COMM, 0.0, 4.0 * frame * 2.0);
+    dist_halo_exchange(c, pv + frame, pv, pv + static_cast<size_t>(T) * frame, pv + static_cast<size_t>(T + 1) * frame, frame * 2, n_active);
+  };
+  exchange(c->v_pad.as<bf16>(), c1.cin);
+  {
+    ConvEpi e;
+    e.mode = 3; e.out = nullptr; e.bias = c1.b; e.resid = nullptr; e.Cin = c1.cin;
+    e.next_pad = c->v_pad2.as<bf16>(); e.next_scale = sc2; e.next_shift = sh2; e.next_tshift = (pad & VAE_PAD_CAUSAL) ? 2 : 1;
+    ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * c1.cin * C * vox, vox * (c1.cin * 2.0 + C * 2.0) + 27.0 * c1.cin * C * 2.0);
+    launch_conv3d(c->v_pad.as<bf16>(), c1.w, T, H, W, c1.cin, C, e, c->stream, 27);
+  }
+  {
+    ProfScope ps(c, PROF_PREP, 0.0, static_cast<double>(padded - vox) * C * 4.0);
+    launch_vae_halo_fill(c->v_pad2.as<bf16>(), T, H, W, C, pad, c->stream);
+  }
+  exchange(c->v_pad2.as<bf16>(), C);
+  ConvEpi e;
+  e.mode = 0; e.out = x; e.bias = c2.b; e.resid = x; e.Cin = c2.cin;
+  ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * c2.cin * c2.cout * vox, vox * (c2.cin * 2.0 + c2.cout * 8.0) + 27.0 * c2.cin * c2.cout * 2.0);
+  launch_conv3d(c->v_pad2.as<bf16>(), c2.w, T, H, W, c2.cin, c2.cout, e, c->stream, 27);
 }
 
 namespace {
@@ -280,11 +322,16 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
     // denormalise (x*std + mean, :379-381) fused into conv_in's padding prologue
     conv(c, hbuf, 1, v.std, v.mean, v.conv_in, T, H, W, causal, 0, x, nullptr, n_active);
     int64_t ch = g.vae_base_channels;
+    static const bool fuse_ok = []() { const char* e = getenv("LTX_VAE_FUSE"); return !(e && e[0] == '0'); }();   // LTX_VAE_FUSE=0: A/B switch
     for (int s = 0; s < 4; ++s) {
       if (timed) time_emb(v.stage_te[s], te_stage);   // one embedding per res-block group (:152-160)
       for (const VaeResBlock& rb : v.stages[s]) {
         // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
         const float* tb = eff_table(rb.sst, static_cast<int>(4 * ch));
+        if (ch > 64 && ch <= 256 && ch % 32 == 0 && fuse_ok) {
+          vae_resblock_fused(c, x, tb + ch, tb, tb + 3 * ch, tb + 2 * ch, rb.c1, rb.c2, T, H, W, causal ? VAE_PAD_CAUSAL : 0, n_active);
+          continue;
+        }
         conv(c, x, 2, tb + ch, tb, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
         conv(c, hbuf, 2, tb + 3 * ch, tb + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
       }

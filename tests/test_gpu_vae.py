@@ -37,3 +37,18 @@ def test_vae_decode_timestep_conditioned():
     plain = ctx.vae_decode(z[0].numpy())
     assert O.psnr(torch.from_numpy(plain), ref) < 35.0      # the conditioning really changes the frames
     ctx.close()
+
+
+def test_vae_decode_causal():
+    """causal: true -- two leading frame copies instead of one leading + one trailing (V/VideoConvolution.swift:281-294); covers the
+    fused conv1 -> conv2 hand-over and the halo fill with the causal frame offset."""
+    ocfg, pcfg = small_vae_config(512, 2)
+    ocfg.causal = True
+    ctx, w = make_ctx_with_vae(ocfg, pcfg, seed=51)
+    z = torch.randn(1, 128, 3, 3, 4, generator=torch.Generator().manual_seed(53))
+    ref = O.decode_video(w, ocfg, z)
+    out = ctx.vae_decode(z[0].numpy(), causal=True)
+    assert O.psnr(torch.from_numpy(out), ref) >= 40.0
+    noncausal = ctx.vae_decode(z[0].numpy(), causal=False)
+    assert O.psnr(torch.from_numpy(noncausal), ref) < 35.0
+    ctx.close()
