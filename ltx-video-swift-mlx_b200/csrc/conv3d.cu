@@ -287,6 +287,60 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
           }
         }
+      } else if (MODE == 4) {
+        // conv2 of a res block handing over to the next block's conv1: x_new = acc + bias + x_old is stored as fp32 (the
+        // residual stream) AND, normalised / modulated / SiLU'd with the NEXT block's (scale1, shift1), as the bf16 interior of
+        // the next conv's padded volume.  thread = voxel: the row segments it touches are whole 128-byte lines.
+        const int nch = (g.Cout + 31) / 32;
+        const int64_t vox = (static_cast<int64_t>(vt) * g.H + vh) * g.W + vw;
+        const float* xin = ep.resid + vox * g.Cout;
+        float* xout = ep.out + vox * g.Cout;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          float4 xr[8];
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[j] = *reinterpret_cast<const float4*>(xin + c * 32 + 4 * j);
+          }
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = *reinterpret_cast<const float4*>(ep.bias + c * 32 + 4 * j);
+              float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x + xr[j].x, __uint_as_float(r[4 * j + 1]) + bv.y + xr[j].y,
+                                     __uint_as_float(r[4 * j + 2]) + bv.z + xr[j].z, __uint_as_float(r[4 * j + 3]) + bv.w + xr[j].w);
+              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              *reinterpret_cast<float4*>(xout + c * 32 + 4 * j) = v;
+            }
+          }
+        }
+        if (valid) {
+          const float rstd = rsqrtf(ss / g.Cout + 1e-8f);
+          bf16* dst = ep.next_pad + ((static_cast<int64_t>(vt + ep.next_tshift) * (g.H + 2) + (vh + 1)) * (g.W + 2) + (vw + 1)) * g.Cout;
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = *reinterpret_cast<const float4*>(xout + c * 32 + 4 * j);   // this thread's own stores
+              const int col = c * 32 + 4 * j;
+              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ep.next_scale) {
+                const float4 t = *reinterpret_cast<const float4*>(ep.next_scale + col);
+                sc = make_float4(1.f + t.x, 1.f + t.y, 1.f + t.z, 1.f + t.w);
+                sh = *reinterpret_cast<const float4*>(ep.next_shift + col);
+              }
+              pk[2 * j] = pack_bf16(silu(v.x * rstd * sc.x + sh.x), silu(v.y * rstd * sc.y + sh.y));
+              pk[2 * j + 1] = pack_bf16(silu(v.z * rstd * sc.z + sh.z), silu(v.w * rstd * sc.w + sh.w));
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        }
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -495,6 +549,7 @@ void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
     case 1: conv_launch<BN, 1>(tmX, tmW, g, ep, s); break;
     case 2: conv_launch<BN, 2>(tmX, tmW, g, ep, s); break;
     case 3: conv_launch<BN, 3>(tmX, tmW, g, ep, s); break;
+    case 4: conv_launch<BN, 4>(tmX, tmW, g, ep, s); break;
     default: LTX_CHECK(false, 2, "bad conv epilogue mode");
   }
 }
@@ -513,7 +568,8 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   LTX_CHECK(Cin % 64 == 0, 2, "conv3d: Cin must be a multiple of 64");
   LTX_CHECK(epi.mode != 0 || Cout % 4 == 0, 2, "conv3d: Cout must be a multiple of 4");
   LTX_CHECK(epi.mode != 1 || (Cout % 32 == 0 && Cin % 8 == 0 && epi.resid != nullptr), 2, "conv3d: bad d2s configuration");
-  LTX_CHECK(epi.mode != 3 || (Cout % 32 == 0 && Cout <= 256 && Cout > 64 && epi.next_pad != nullptr && ntaps == 27), 2,
+  LTX_CHECK(epi.mode != 4 || (epi.resid != nullptr && epi.out != nullptr), 2, "conv3d: mode 4 needs the residual stream");
+  LTX_CHECK((epi.mode != 3 && epi.mode != 4) || (Cout % 32 == 0 && Cout <= 256 && Cout > 64 && epi.next_pad != nullptr && ntaps == 27), 2,
             "conv3d: the fused-prologue epilogue needs 64 < Cout <= 256 (one tile = all channels of a voxel)");
   ConvGeom g;
   g.T = T; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
@@ -536,13 +592,13 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   const bool can_split = epi.mode == 0 && ntaps == 27 && splitk_scratch != nullptr && 3 * slab <= splitk_scratch_bytes &&
                          conv3d_wants_tap_split(H, W, Cin, Cout);
   if (can_split) g.ksplit = 3;
-  else if (epi.mode != 3 && bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
+  else if (epi.mode != 3 && epi.mode != 4 && bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
   // cost ~0.7 of a 256-wide one, so they only pay when 256 leaves most SMs without a tile)
   const float* final_bias = epi.bias;
   const float* final_resid = epi.resid;
   float* final_out = epi.out;
   if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
-  LTX_CHECK(epi.mode != 3 || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
+  LTX_CHECK((epi.mode != 3 && epi.mode != 4) || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
   if (bn == 256)

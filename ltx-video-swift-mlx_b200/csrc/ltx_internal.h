@@ -218,6 +218,8 @@ struct ConvEpi {
   // of (acc + bias), * (1 + next_scale) + next_shift, SiLU, bf16, stored into the interior of the next conv's padded volume
   // [T+2, H+2, W+2, Cout] (frame offset next_tshift: 1, or 2 when causal); launch_vae_halo_fill completes the padding.
   // The fp32 tensor is never written (VAEResBlock3d conv1 -> conv2, V/VideoDecoder.swift:118-127).
+  // mode 4: the same hand-over from conv2 to the NEXT res block's conv1: out = acc + bias + resid is stored as fp32 (the residual
+  // stream) and its normalised / modulated / activated bf16 copy goes into next_pad.
   bf16* next_pad = nullptr;
   const float* next_scale = nullptr;
   const float* next_shift = nullptr;

@@ -117,44 +117,74 @@ void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const f
   launch_conv3d(c->v_pad.as<bf16>(), w.w, T, H, W, w.cin, w.cout, e, c->stream, w.taps, scratch, scratch ? slab3 : 0);
 }
 
-// VAEResBlock3d's conv1 -> conv2 hand-over without the fp32 round trip (V/VideoDecoder.swift:118-127): conv1's epilogue
-// normalises, modulates (scale2 / shift2), activates and stores the bf16 interior of conv2's padded volume (conv3d.cu mode 3), a
-// halo pass completes the padding (+ the neighbour exchange on temporal shards), conv2 runs straight from it.
-// Requires 64 < C <= 256 (one tile = all channels of a voxel).
-void vae_resblock_fused(ltx_ctx* c, float* x, const float* sc1, const float* sh1, const float* sc2, const float* sh2, const ConvW& c1,
-                        const ConvW& c2, int T, int H, int W, int pad, int n_active) {
-  const int C = c1.cout;
+// A group of VAEResBlock3d (V/VideoDecoder.swift:93-130, 152-167) with both hand-overs fused into the producing conv's epilogue
+// (conv3d.cu modes 3 and 4): only the first conv1 of the group runs the padding prologue kernel; afterwards
+//   conv1 epilogue -> bf16 interior of conv2's padded volume (pixel-norm, scale2/shift2, SiLU; the fp32 h is never written)
+//   conv2 epilogue -> x += ... as fp32 AND the bf16 interior of the next block's conv1 input (scale1/shift1 of that block)
+// a halo-fill pass completes each padded volume (+ the neighbour exchange on temporal shards).  tables[j] = block j's
+// [shift1 | scale1 | shift2 | scale2] rows.  Requires 64 < C <= 256 (one tile = all channels of a voxel).
+void vae_resgroup_fused(ltx_ctx* c, float* x, const std::vector<VaeResBlock>& blocks, const std::vector<const float*>& tables, int T,
+                        int H, int W, int pad, int n_active) {
+  const int C = blocks[0].c1.cout;
   const size_t padded = static_cast<size_t>(T + 2) * (H + 2) * (W + 2);
-  c->v_pad.reserve(padded * c1.cin * 2);
+  c->v_pad.reserve(padded * C * 2);
   c->v_pad2.reserve(padded * C * 2);
+  bf16* padA = c->v_pad.as<bf16>();
+  bf16* padB = c->v_pad2.as<bf16>();
   const double vox = static_cast<double>(T) * H * W;
-  {
-    ProfScope ps(c, PROF_PREP, 0.0, vox * c1.cin * 4.0 + static_cast<double>(padded) * c1.cin * 2.0);
-    launch_vae_prep(x, c->v_pad.as<bf16>(), T, H, W, c1.cin, 2, sc1, sh1, pad, c->stream);
-  }
-  auto exchange = [&](bf16* pv, int ch) {
+  const int tshift = (pad & VAE_PAD_CAUSAL) ? 2 : 1;
+  auto exchange = [&](bf16* pv) {
     if (n_active <= 1) return;
-    const size_t frame = static_cast<size_t>(H + 2) * (W + 2) * ch;
+    const size_t frame = static_cast<size_t>(H + 2) * (W + 2) * C;
     ProfScope ps(c, PROF_COMM, 0.0, 4.0 * frame * 2.0);
     dist_halo_exchange(c, pv + frame, pv, pv + static_cast<size_t>(T) * frame, pv + static_cast<size_t>(T + 1) * frame, frame * 2, n_active);
   };
-  exchange(c->v_pad.as<bf16>(), c1.cin);
+  auto halo = [&](bf16* pv) {
+    {
+      ProfScope ps(c, PROF_PREP, 0.0, static_cast<double>(padded - vox) * C * 4.0);
+      launch_vae_halo_fill(pv, T, H, W, C, pad, c->stream);
+    }
+    exchange(pv);
+  };
   {
+    ProfScope ps(c, PROF_PREP, 0.0, vox * C * 4.0 + static_cast<double>(padded) * C * 2.0);
+    launch_vae_prep(x, padA, T, H, W, C, 2, tables[0] + C, tables[0], pad, c->stream);
+  }
+  exchange(padA);
+  const double cflops = 2.0 * 27.0 * C * C * vox, wbytes = 27.0 * C * C * 2.0;
+  // The conv2 -> next conv1 hand-over (mode 4) is off by default: its thread-per-voxel epilogue (fp32 residual read + write,
+  // re-read for the normalised copy) costs more than the prologue kernel it replaces (measured, 25-frame decode: prologue
+  // 3.1 -> 2.2 ms but convs 13.6 -> 15.7 ms).  LTX_VAE_FUSE2=1 enables it for experiments.
+  static const bool fuse2 = []() { const char* e = getenv("LTX_VAE_FUSE2"); return e && e[0] == '1'; }();
+  for (size_t j = 0; j < blocks.size(); ++j) {
+    const VaeResBlock& rb = blocks[j];
+    const float* tb = tables[j];
+    {
+      ConvEpi e;
+      e.mode = 3; e.out = nullptr; e.bias = rb.c1.b; e.resid = nullptr; e.Cin = C;
+      e.next_pad = padB; e.next_scale = tb + 3 * C; e.next_shift = tb + 2 * C; e.next_tshift = tshift;
+      ProfScope ps(c, PROF_CONV, cflops, vox * C * 4.0 + wbytes);
+      launch_conv3d(padA, rb.c1.w, T, H, W, C, C, e, c->stream, 27);
+    }
+    halo(padB);
+    const bool last = j + 1 == blocks.size() || !fuse2;
     ConvEpi e;
-    e.mode = 3; e.out = nullptr; e.bias = c1.b; e.resid = nullptr; e.Cin = c1.cin;
-    e.next_pad = c->v_pad2.as<bf16>(); e.next_scale = sc2; e.next_shift = sh2; e.next_tshift = (pad & VAE_PAD_CAUSAL) ? 2 : 1;
-    ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * c1.cin * C * vox, vox * (c1.cin * 2.0 + C * 2.0) + 27.0 * c1.cin * C * 2.0);
-    launch_conv3d(c->v_pad.as<bf16>(), c1.w, T, H, W, c1.cin, C, e, c->stream, 27);
+    e.mode = last ? 0 : 4; e.out = x; e.bias = rb.c2.b; e.resid = x; e.Cin = C;
+    if (!last) { e.next_pad = padA; e.next_scale = tables[j + 1] + C; e.next_shift = tables[j + 1]; e.next_tshift = tshift; }
+    {
+      ProfScope ps(c, PROF_CONV, cflops, vox * C * (last ? 10.0 : 12.0) + wbytes);
+      launch_conv3d(padB, rb.c2.w, T, H, W, C, C, e, c->stream, 27);
+    }
+    if (!last) {
+      halo(padA);
+    } else if (j + 1 < blocks.size()) {   // next block's conv1 input through the prologue kernel
+      {
+        ProfScope ps(c, PROF_PREP, 0.0, vox * C * 4.0 + static_cast<double>(padded) * C * 2.0);
+        launch_vae_prep(x, padA, T, H, W, C, 2, tables[j + 1] + C, tables[j + 1], pad, c->stream);
+      }
+      exchange(padA);
+    }
   }
-  {
-    ProfScope ps(c, PROF_PREP, 0.0, static_cast<double>(padded - vox) * C * 4.0);
-    launch_vae_halo_fill(c->v_pad2.as<bf16>(), T, H, W, C, pad, c->stream);
-  }
-  exchange(c->v_pad2.as<bf16>(), C);
-  ConvEpi e;
-  e.mode = 0; e.out = x; e.bias = c2.b; e.resid = x; e.Cin = c2.cin;
-  ProfScope ps(c, PROF_CONV, 2.0 * 27.0 * c2.cin * c2.cout * vox, vox * (c2.cin * 2.0 + c2.cout * 8.0) + 27.0 * c2.cin * c2.cout * 2.0);
-  launch_conv3d(c->v_pad2.as<bf16>(), c2.w, T, H, W, c2.cin, c2.cout, e, c->stream, 27);
 }
 
 namespace {
@@ -257,7 +287,7 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
       LTX_CUDA(cudaGetLastError());
     }
     latent_in = c->v_mix.as<float>();
-    c->v_te.reserve((1 + 256 + 256 + 4 * static_cast<size_t>(g.vae_base_channels) * 2 + 64) * 4);
+    c->v_te.reserve((1 + 256 + 256 + 4 * static_cast<size_t>(g.vae_base_channels) * (1 + std::max(1, g.vae_blocks_per_stage)) + 64) * 4);
     te_base = c->v_te.as<float>();
     const float ts_host = timestep;
     LTX_CUDA(cudaMemcpyAsync(te_base, &ts_host, 4, cudaMemcpyHostToDevice, st));
@@ -325,15 +355,27 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
     static const bool fuse_ok = []() { const char* e = getenv("LTX_VAE_FUSE"); return !(e && e[0] == '0'); }();   // LTX_VAE_FUSE=0: A/B switch
     for (int s = 0; s < 4; ++s) {
       if (timed) time_emb(v.stage_te[s], te_stage);   // one embedding per res-block group (:152-160)
-      for (const VaeResBlock& rb : v.stages[s]) {
-        // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
-        const float* tb = eff_table(rb.sst, static_cast<int>(4 * ch));
-        if (ch > 64 && ch <= 256 && ch % 32 == 0 && fuse_ok) {
-          vae_resblock_fused(c, x, tb + ch, tb, tb + 3 * ch, tb + 2 * ch, rb.c1, rb.c2, T, H, W, causal ? VAE_PAD_CAUSAL : 0, n_active);
-          continue;
+      const bool fuse = ch > 64 && ch <= 256 && ch % 32 == 0 && fuse_ok && !v.stages[s].empty();
+      if (fuse) {
+        // every block's effective table is needed at once: a conv2 epilogue applies the NEXT block's scale1 / shift1
+        std::vector<const float*> tabs;
+        for (size_t j = 0; j < v.stages[s].size(); ++j) {
+          const VaeResBlock& rb = v.stages[s][j];
+          if (!timed) { tabs.push_back(rb.sst); continue; }
+          float* dstt = tbl_eff + j * 4 * ch;
+          ProfScope ps(c, PROF_OTHER, 0.0, 12.0 * 4 * ch);
+          add_vec_kernel<<<static_cast<int>((4 * ch + 255) / 256), 256, 0, st>>>(dstt, rb.sst, te_stage, static_cast<int>(4 * ch));
+          LTX_CUDA(cudaGetLastError());
+          tabs.push_back(dstt);
         }
-        conv(c, x, 2, tb + ch, tb, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
-        conv(c, hbuf, 2, tb + 3 * ch, tb + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
+        vae_resgroup_fused(c, x, v.stages[s], tabs, T, H, W, causal ? VAE_PAD_CAUSAL : 0, n_active);
+      } else {
+        for (const VaeResBlock& rb : v.stages[s]) {
+          // h = conv1(silu(pn(x) * (1 + scale1) + shift1)) ; x = x + conv2(silu(pn(h) * (1 + scale2) + shift2))   (:93-130)
+          const float* tb = eff_table(rb.sst, static_cast<int>(4 * ch));
+          conv(c, x, 2, tb + ch, tb, rb.c1, T, H, W, causal, 0, hbuf, nullptr, n_active);
+          conv(c, hbuf, 2, tb + 3 * ch, tb + 2 * ch, rb.c2, T, H, W, causal, 0, x, x, n_active);
+        }
       }
       if (s < 3) {
         // conv -> d2s -> drop frame 0 (first slab only) -> + tiled d2s(x)
