@@ -118,7 +118,9 @@ int ltx_init_random_weights(ltx_ctx* ctx, int which, uint64_t seed);
 /* Packs the loaded tensors into kernel layouts.  quant_bits: 16 = bf16; 8 / 4 replace every GEMM weight of the DiT by
  * per-64-group affine codes (w ~= s*q + beta) consumed by the dequant-fused GEMM -- the counterpart of
  * quantize(model:groupSize:64,bits:) (Pipeline/LTXPipeline.swift:323-333).  The exact MLX rounding rule is not in the
- * reference tree; ours is plain min/max affine with bf16 scales. */
+ * reference tree; ours is plain min/max affine with bf16 scales.  Each component (DiT, VAE decoder, VAE encoder,
+ * upscaler) is packed once: the call may be repeated after loading a further component (loadVAEEncoder on demand,
+ * Pipeline/LTXPipeline.swift:1870-1884). */
 int ltx_finalize_weights(ltx_ctx* ctx, int quant_bits, int group_size);
 
 /* Per-forward runtime flags: setSTGSkipFlags / clearSTGSkipFlags / setCrossAttentionScale

@@ -265,7 +265,8 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
     LTX_CHECK(quant_bits == 16 || quant_bits == 8 || quant_bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");
     LTX_CHECK(quant_bits == 16 || group_size == 64, LTX_ERR_UNSUPPORTED, "only group_size 64 is implemented");
     LTX_CHECK(quant_bits == 16 || c->precision == 16, LTX_ERR_UNSUPPORTED, "fp32 mode cannot be combined with quantised weights");
-    if (c->tensors.count("patchify_proj.weight")) {
+    // each component is packed once; a later call (after loading another component) only packs what is new
+    if (c->tensors.count("patchify_proj.weight") && !c->dit_ready) {
       if (c->precision == 32) dit_finalize_f32(c);
       else dit_finalize(c);
       if (c->tensors.count("audio_patchify_proj.weight")) {
@@ -274,9 +275,9 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
       }
       if (quant_bits != 16) dit_quantize(c, quant_bits);
     }
-    if (c->tensors.count("vae.conv_in.conv.weight")) vae_finalize(c);
-    if (c->tensors.count("vae_encoder.conv_in.conv.weight")) vae_encoder_finalize(c);
-    if (c->tensors.count("upscaler.initial_conv.weight")) upscaler_finalize(c);
+    if (c->tensors.count("vae.conv_in.conv.weight") && !c->vae.ready) vae_finalize(c);
+    if (c->tensors.count("vae_encoder.conv_in.conv.weight") && !c->enc.ready) vae_encoder_finalize(c);
+    if (c->tensors.count("upscaler.initial_conv.weight") && !c->ups.ready) upscaler_finalize(c);
     LTX_CHECK(c->dit_ready || c->vae.ready || c->enc.ready || c->ups.ready, LTX_ERR_WEIGHTS, "no weights loaded");
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });

@@ -127,3 +127,23 @@ def test_two_stage_resident_matches_oracle():
     ctx.denoise_begin_from_latent(O.adain_filter_latent(up, z1)[0].numpy(), n2[0].numpy(), s2[0], (F, 2 * H, 2 * W), text)
     assert rel_l2(ctx.denoise_get_latent(), z[0]) <= 1e-5
     ctx.close()
+
+
+def test_components_can_be_loaded_and_finalized_incrementally():
+    """loadVAEEncoder() runs on demand, after loadModels() (P/LTXPipeline.swift:1870-1884): a second ltx_finalize_weights packs
+    only the new component and leaves the finalized ones working."""
+    vcfg = O.VAEConfig(base_channels=512, blocks_per_stage=1)
+    vw = _bf16_weights(O.make_vae_weights(vcfg, 61))
+    ctx = _ctx(vae_base_channels=512, vae_blocks_per_stage=1)
+    ctx.load_weights(vw, prefix="vae.")
+    ctx.finalize_weights()
+    z = torch.randn(1, 128, 2, 2, 3, generator=torch.Generator().manual_seed(2))
+    before = ctx.vae_decode(z[0].numpy())
+    ecfg = O.EncoderConfig(base_channels=64)
+    we = _bf16_weights(O.make_encoder_weights(ecfg, 62))
+    ctx.load_weights(we, prefix="vae_encoder.")
+    ctx.finalize_weights()
+    px = torch.rand(1, 3, 1, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    assert rel_l2(ctx.vae_encode(px.numpy(), normalize=False), O.vae_encode(we, ecfg, px)[0]) <= 1e-2
+    assert np.array_equal(ctx.vae_decode(z[0].numpy()), before)
+    ctx.close()
