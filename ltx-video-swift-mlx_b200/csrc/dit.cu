@@ -255,33 +255,37 @@ void dit_finalize(ltx_ctx* c) {
     const std::string p = "transformer_blocks." + std::to_string(i) + ".";
     BlockWeights& b = c->blocks[i];
     b.sst = wf(c, p + "scale_shift_table", 6 * D);
-    // attn1: pack q|k
+    // attn1: pack q|k|v into one [3D, D] operand: the three projections of the block run as ONE GEMM (N = 3D; V leaves its
+    // epilogue transposed); the Ulysses / quantised paths address the q|k rows and the v rows of the same buffer separately
     {
       const bf16* wq = wbf(c, p + "attn1.to_q.weight", D, D);
       const bf16* wk = wbf(c, p + "attn1.to_k.weight", D, D);
+      const bf16* wv = wbf(c, p + "attn1.to_v.weight", D, D);
       const float* bq = wf(c, p + "attn1.to_q.bias", D);
       const float* bk = wf(c, p + "attn1.to_k.bias", D);
-      bf16* wqk = nullptr;
-      float* bqk = nullptr;
-      LTX_CUDA(cudaMalloc(&wqk, static_cast<size_t>(2) * D * D * 2));
-      c->owned.push_back(wqk);
-      LTX_CUDA(cudaMalloc(&bqk, static_cast<size_t>(2) * D * 4));
-      c->owned.push_back(bqk);
-      LTX_CUDA(cudaMemcpyAsync(wqk, wq, static_cast<size_t>(D) * D * 2, cudaMemcpyDeviceToDevice, c->stream));
-      LTX_CUDA(cudaMemcpyAsync(wqk + D * D, wk, static_cast<size_t>(D) * D * 2, cudaMemcpyDeviceToDevice, c->stream));
-      LTX_CUDA(cudaMemcpyAsync(bqk, bq, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, c->stream));
-      LTX_CUDA(cudaMemcpyAsync(bqk + D, bk, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, c->stream));
+      const float* bvv = wf(c, p + "attn1.to_v.bias", D);
+      bf16* wqkv = nullptr;
+      float* bqkv = nullptr;
+      LTX_CUDA(cudaMalloc(&wqkv, static_cast<size_t>(3) * D * D * 2));
+      c->owned.push_back(wqkv);
+      LTX_CUDA(cudaMalloc(&bqkv, static_cast<size_t>(3) * D * 4));
+      c->owned.push_back(bqkv);
+      const bf16* ws[3] = {wq, wk, wv};
+      const float* bs[3] = {bq, bk, bvv};
+      for (int t = 0; t < 3; ++t) {
+        LTX_CUDA(cudaMemcpyAsync(wqkv + static_cast<size_t>(t) * D * D, ws[t], static_cast<size_t>(D) * D * 2, cudaMemcpyDeviceToDevice, c->stream));
+        LTX_CUDA(cudaMemcpyAsync(bqkv + static_cast<size_t>(t) * D, bs[t], static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, c->stream));
+      }
       LTX_CUDA(cudaStreamSynchronize(c->stream));
       // the unpacked copies are no longer needed
-      for (const char* k : {"attn1.to_q.weight", "attn1.to_k.weight"}) {
+      for (const char* k : {"attn1.to_q.weight", "attn1.to_k.weight", "attn1.to_v.weight"}) {
         auto it = c->tensors.find(p + k);
         cudaFree(it->second.ptr);
         c->tensors.erase(it);
       }
-      b.a1.wq = wqk; b.a1.wk = wqk + D * D; b.a1.bq = bqk; b.a1.bk = bqk + D;
+      b.a1.wq = wqkv; b.a1.wk = wqkv + D * D; b.a1.wv = wqkv + 2 * D * D;
+      b.a1.bq = bqkv; b.a1.bk = bqkv + D; b.a1.bv = bqkv + 2 * D;
     }
-    b.a1.wv = wbf(c, p + "attn1.to_v.weight", D, D);
-    b.a1.bv = wf(c, p + "attn1.to_v.bias", D);
     b.a1.wo = wbf(c, p + "attn1.to_out.weight", D, D);
     b.a1.bo = wf(c, p + "attn1.to_out.bias", D);
     b.a1.q_norm = wf(c, p + "attn1.q_norm.weight", D);
@@ -529,11 +533,20 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     if (!skip_sa) {
       // h = rms(x) * (1 + scale_msa) + shift_msa      (T/LTXTransformerBlock.swift:72-83, rows 0/1 of table+ada)
       norm_mod(c, x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, rows_per_b, eps, 0);
+      // q|k|v in one GEMM (N = 3D, 256-wide tiles: 288 tiles = 3.9 rounds of 74 CTA pairs at M = 1536), the V columns stored
+      // transposed by the epilogue; separate q|k and V^T GEMMs for batches, sequence parallelism and quantised weights
+      const bool fused_qkv = P == 1 && B == 1 && c->qw.empty() && D % 32 == 0;
       GemmEpi e;
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
-      gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
+      if (fused_qkv) {
+        e.tsplit_col = 2 * D; e.out_t = vt; e.ldt = ldv;
+        ProfScope ps(c, PROF_GEMM, 2.0 * R * 3.0 * D * D, 2.0 * (static_cast<double>(R) * D + 3.0 * D * D + 3.0 * R * D));
+        launch_gemm(h, D, bw.a1.wq, D, R, 3 * D, D, e, st, R > 128 ? 1256 : 256);
+      } else {
+        gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
+      }
       if (P == 1) {
-        for (int b = 0; b < B; ++b)  // V^T, one column block per batch
+        for (int b = 0; b < B && !fused_qkv; ++b)  // V^T, one column block per batch
           v_transposed(c, bw.a1.wv, bw.a1.bv, h + static_cast<int64_t>(b) * N * D, N, D, vt + b * ldv, B * ldv, q2);
         qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rope_period, eps, bw.a1.k_norm);
         attention(c, qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, B, Hh, N, N, D, att_scale);

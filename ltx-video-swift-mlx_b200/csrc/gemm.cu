@@ -226,6 +226,9 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   int bn = force_bn;
   if (bn == 0) bn = fit_tile_width(M, N, device_sm_count());
   LTX_CHECK(bn >= 32 && bn <= 256 && bn % 16 == 0, 2, "GEMM: tile width must be a multiple of 16 in [32, 256]");
+  LTX_CHECK(epi.tsplit_col == 0 || (epi.mode == EPI_BF16 && bn % 32 == 0 && epi.tsplit_col % 32 == 0 && epi.out_t != nullptr &&
+                                    epi.ldt % 8 == 0 && epi.col_block == 0),
+            2, "GEMM: transposed-column output needs the bf16 epilogue, a tile width and split column that are multiples of 32");
   LTX_CHECK(epi.col_block == 0 || ((epi.mode == EPI_BF16 || epi.mode == EPI_GELU_BF16 || epi.mode == EPI_SILU_BF16) && epi.col_block % 32 == 0 &&
                                    N % epi.col_block == 0),
             2, "GEMM: column-blocked output needs a bf16 epilogue and col_block % 32 == 0");

@@ -194,6 +194,9 @@ void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride) {
   int bn = force_bn ? force_bn : gemm2_fit_tile_width(M, N);
   LTX_CHECK(bn >= 64 && bn <= 256 && bn % 16 == 0, 2, "2-CTA GEMM: tile width must be a multiple of 16 in [64, 256]");
+  LTX_CHECK(epi.tsplit_col == 0 || (epi.mode == EPI_BF16 && bn % 32 == 0 && epi.tsplit_col % 32 == 0 && epi.out_t != nullptr &&
+                                    epi.ldt % 8 == 0 && epi.col_block == 0),
+            2, "GEMM: transposed-column output needs the bf16 epilogue, a tile width and split column that are multiples of 32");
   CUtensorMap tmA;
   if (a_kblock > 0) {
     LTX_CHECK(a_kblock % BK2 == 0 && K % a_kblock == 0 && lda == a_kblock, 2, "GEMM: bad K-blocked A layout");

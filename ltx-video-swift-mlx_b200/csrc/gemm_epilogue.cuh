@@ -139,6 +139,30 @@ __device__ __forceinline__ void epi_store_chunk(const float* stage, int lane, in
   }
 }
 
+// Transposed store of one staged chunk (bf16): lane l owns column col0 + l and gathers its 32 rows from the staging tile
+// (bank = ((l >> 2) ^ (rr & 7)) * 4 + (l & 3): a permutation of the 32 banks for every rr), adds the bias, and writes 64
+// contiguous bytes of row (n - tsplit_col) of the transposed output.
+__device__ __forceinline__ void epi_store_chunk_t(const float* stage, int lane, int row0, int col0, int ncols, int M, int N,
+                                                  const GemmEpi& ep) {
+  if (ep.debug & 1) return;
+  const int n = col0 + lane;
+  if (lane >= ncols || n >= N || row0 >= M) return;
+  const float b = (ep.bias && !ep.bias_per_row) ? ep.bias[n] : 0.f;
+  bf16* dst = ep.out_t + static_cast<int64_t>(n - ep.tsplit_col) * ep.ldt + row0;
+  const int nrows = (M - row0 < 32) ? M - row0 : 32;
+  float v[32];
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) v[rr] = stage[(rr * 8 + ((lane >> 2) ^ (rr & 7))) * 4 + (lane & 3)] + b;
+  if (nrows == 32) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      *reinterpret_cast<uint4*>(dst + q4 * 8) = make_uint4(pack_bf16(v[q4 * 8], v[q4 * 8 + 1]), pack_bf16(v[q4 * 8 + 2], v[q4 * 8 + 3]),
+                                                           pack_bf16(v[q4 * 8 + 4], v[q4 * 8 + 5]), pack_bf16(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+  } else {
+    for (int rr = 0; rr < nrows; ++rr) dst[rr] = __float2bfloat16(v[rr]);
+  }
+}
+
 // EPI_GATE_RESID: fetch this lane's 8 residual float4 of chunk [row0, +32) x [col0, +ncols) (same ownership as above)
 __device__ __forceinline__ void epi_prefetch_resid(float4 (&xin)[8], int lane, int row0, int col0, int ncols, int M, int N,
                                                    const GemmEpi& ep) {
@@ -177,7 +201,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int BN, float* sta
       if (MODE == EPI_GATE_RESID)
         epi_prefetch_resid(xnext, lane, row0, col_base + (c + 1) * 32, (c + 1 < nfull) ? 32 : 16, M, N, ep);
     }
-    epi_store_chunk<MODE>(stage, lane, row0, col_base + c * 32, (c < nfull) ? 32 : 16, M, N, ep, xcur);
+    if (MODE == EPI_BF16 && ep.tsplit_col > 0 && col_base + c * 32 >= ep.tsplit_col)
+      epi_store_chunk_t(stage, lane, row0, col_base + c * 32, (c < nfull) ? 32 : 16, M, N, ep);
+    else
+      epi_store_chunk<MODE>(stage, lane, row0, col_base + c * 32, (c < nfull) ? 32 : 16, M, N, ep, xcur);
     __syncwarp();
     if (MODE == EPI_GATE_RESID) {
 #pragma unroll

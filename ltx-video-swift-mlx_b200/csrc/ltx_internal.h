@@ -99,6 +99,12 @@ struct GemmEpi {
   // rank d's receive buffer through NVLink): element (m, n) goes to col_ptrs.p[n / col_block][m * ldo + n % col_block]
   int use_col_ptrs = 0;
   PeerTable col_ptrs = {};
+  // EPI_BF16 only: columns n >= tsplit_col are stored TRANSPOSED: element (m, n) -> out_t[(n - tsplit_col) * ldt + m].
+  // Used by the fused q|k|v projection: q|k land row-major in `out`, V lands as V^T (K-major for the PV MMA).  Needs
+  // tsplit_col % 32 == 0, a tile width that is a multiple of 32, ldt % 8 == 0.  0 = off.
+  int tsplit_col = 0;
+  bf16* out_t = nullptr;
+  int64_t ldt = 0;
   int debug = 0;  // bit 0: skip the epilogue's global traffic (LTX_GEMM_DEBUG, timing experiments only)
 };
 
