@@ -93,3 +93,28 @@ def test_av_random_init_full_width_block():
     assert np.isfinite(ov).all() and np.isfinite(oa).all() and ov.std() > 0.05 and oa.std() > 0.05
     assert np.array_equal(ov, ov2) and np.array_equal(oa, oa2)
     ctx.close()
+
+
+def test_av_restrictions_fail_loudly():
+    """The dual model runs with bf16 weights only: asking for int8 is LTX_ERR_UNSUPPORTED (5), not a silent fallback; calling
+    it without the audio tensors is a weight error (2 / 4)."""
+    from ltx_video_swift_mlx_b200._lib import LtxError
+    ctxmod = product()
+    ocfg = O.DiTConfig(num_layers=1, num_heads=2, head_dim=128, caption_channels=192)
+    av = O.AVConfig(audio_heads=2)
+    pcfg = ctxmod.LTXTransformerConfig(num_layers=1, num_attention_heads=2, caption_channels=192, audio_num_attention_heads=2)
+    w = O.make_av_weights(ocfg, av, 3)
+    ctx = ctxmod.LtxContext(pcfg, 0)
+    ctx.load_weights(w)
+    with pytest.raises(LtxError) as e:
+        ctx.finalize_weights(quant_bits=8)
+    assert e.value.code == 5
+    ctx.close()
+    ctx = ctxmod.LtxContext(pcfg, 0)
+    ctx.load_weights({k: v for k, v in w.items() if k in O.make_dit_weights(ocfg, 3)})   # video-only weights
+    ctx.finalize_weights()
+    vl, al, vc, ac, _ = _inputs((2, 4, 6), 11, 24, 192, 1)
+    with pytest.raises(LtxError) as e:
+        ctx.av_forward(vl, al, vc, ac, 0.5, 0.5, (2, 4, 6))
+    assert e.value.code in (2, 4)
+    ctx.close()

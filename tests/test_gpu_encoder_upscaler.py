@@ -147,3 +147,32 @@ def test_components_can_be_loaded_and_finalized_incrementally():
     assert rel_l2(ctx.vae_encode(px.numpy(), normalize=False), O.vae_encode(we, ecfg, px)[0]) <= 1e-2
     assert np.array_equal(ctx.vae_decode(z[0].numpy()), before)
     ctx.close()
+
+
+def test_error_paths_map_to_ltx_error_codes():
+    """Bad shapes / missing weights fail loudly with the LTXError-equivalent codes (LTXVideo.swift:66-107): 2 = generationFailed
+    (invalid argument), 4 = weightLoadingFailed, 5 = unsupported; nothing falls back to a CPU path."""
+    from ltx_video_swift_mlx_b200._lib import LtxError
+    ctx = _ctx()
+    with pytest.raises(LtxError) as e:                       # encoder weights were never loaded
+        ctx.vae_encode(np.zeros((3, 1, 64, 64), dtype=np.float32), normalize=False)
+    assert e.value.code == 4
+    with pytest.raises(LtxError) as e:                       # upscaler weights were never loaded
+        ctx.upscale_latent(np.zeros((128, 1, 4, 4), dtype=np.float32))
+    assert e.value.code == 4
+    ecfg = O.EncoderConfig(base_channels=64)
+    ctx.load_weights(_bf16_weights(O.make_encoder_weights(ecfg, 71)), prefix="vae_encoder.")
+    ctx.finalize_weights()
+    with pytest.raises(LtxError) as e:                       # H, W must be multiples of 32
+        ctx.lib.ltx_vae_encode  # noqa: B018 (symbol exists)
+        px = np.zeros((3, 1, 72, 64), dtype=np.float32)
+        out = np.zeros((128, 1, 2, 2), dtype=np.float32)
+        ctx._check(ctx.lib.ltx_vae_encode(ctx.handle, px.ctypes.data, 1, 72, 64, 0, out.ctypes.data))
+    assert e.value.code == 2
+    with pytest.raises(LtxError) as e:                       # normalisation needs the decoder's latent statistics
+        ctx.vae_encode(np.zeros((3, 1, 64, 64), dtype=np.float32), normalize=True)
+    assert e.value.code == 4
+    with pytest.raises(LtxError) as e:                       # LoRA target must be loaded and not yet packed
+        ctx.fuse_lora("transformer_blocks.0.attn1.to_q.weight", torch.zeros(8, 256).bfloat16(), torch.zeros(256, 8).bfloat16())
+    assert e.value.code == 4
+    ctx.close()
