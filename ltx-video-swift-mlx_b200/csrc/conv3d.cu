@@ -206,7 +206,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 4) {
         // plain conv (+bias, +residual): the accumulator chunk is transposed through a warp-private smem tile (see
         // gemm_epilogue.cuh) so that 8 lanes cover 128 contiguous bytes of one voxel's channels; the lane's 8 voxel
         // offsets are computed once per tile, the residual values are fetched before the first store
@@ -214,11 +214,15 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int cg = lane & 7, rsub = lane >> 3;
         float* outp = ep.out + static_cast<int64_t>(ks) * g.T * g.H * g.W * g.Cout;   // split-K: this group's partial slab
         int64_t voff[8];
+        int64_t poff[8];     // MODE 4: the voxel's place in the next conv's padded volume
+        float ssv[8];        // MODE 4: running sum of squares of x_new over this lane's channels
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int mm = q * 32 + rsub + 4 * i;
           const int w2 = iw * g.bw + mm % g.bw, h2 = ih * g.bh + (mm / g.bw) % g.bh, t2 = it * g.bt + mm / (g.bw * g.bh);
           voff[i] = (w2 < g.W && h2 < g.H && t2 < g.T) ? ((static_cast<int64_t>(t2) * g.H + h2) * g.W + w2) * g.Cout : -1;
+          poff[i] = ((static_cast<int64_t>(t2 + ep.next_tshift) * (g.H + 2) + (h2 + 1)) * (g.W + 2) + (w2 + 1)) * g.Cout;
+          ssv[i] = 0.f;
         }
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -241,11 +245,50 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               if (voff[i] < 0) continue;
               const int rr = rsub + 4 * i;
               const float4 a = reinterpret_cast<const float4*>(stage)[rr * 8 + (cg ^ (rr & 7))];
-              *reinterpret_cast<float4*>(outp + voff[i] + col) =
-                  make_float4(a.x + bv.x + xin[i].x, a.y + bv.y + xin[i].y, a.z + bv.z + xin[i].z, a.w + bv.w + xin[i].w);
+              const float4 v = make_float4(a.x + bv.x + xin[i].x, a.y + bv.y + xin[i].y, a.z + bv.z + xin[i].z, a.w + bv.w + xin[i].w);
+              *reinterpret_cast<float4*>(outp + voff[i] + col) = v;
+              if (MODE == 4) ssv[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             }
           }
           __syncwarp();
+        }
+        if (MODE == 4) {
+          // conv2 of a res block handing over to the next block's conv1: x_new (just stored as fp32, the residual stream)
+          // also goes, pixel-normalised / modulated with the NEXT block's (scale1, shift1) / SiLU'd, as bf16 into the
+          // interior of the next conv's padded volume.  The 8 lanes that share a voxel combine their partial sums; each lane
+          // then re-reads exactly the float4 it stored above (same thread: program order) and writes 8 bytes, 64 contiguous
+          // bytes per voxel and chunk.
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float t = ssv[i];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            ssv[i] = rsqrtf(t / g.Cout + 1e-8f);
+          }
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col = c * 32 + cg * 4;
+            if (col >= g.Cout) break;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.next_scale) {
+              const float4 t = *reinterpret_cast<const float4*>(ep.next_scale + col);
+              sc = make_float4(1.f + t.x, 1.f + t.y, 1.f + t.z, 1.f + t.w);
+              sh = *reinterpret_cast<const float4*>(ep.next_shift + col);
+            }
+            float4 xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              xv[i] = voff[i] >= 0 ? *reinterpret_cast<const float4*>(outp + voff[i] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (voff[i] < 0) continue;
+              const float r0 = ssv[i];
+              *reinterpret_cast<uint2*>(ep.next_pad + poff[i] + col) =
+                  make_uint2(pack_bf16(silu(xv[i].x * r0 * sc.x + sh.x), silu(xv[i].y * r0 * sc.y + sh.y)),
+                             pack_bf16(silu(xv[i].z * r0 * sc.z + sh.z), silu(xv[i].w * r0 * sc.w + sh.w)));
+            }
+          }
         }
       } else if (MODE == 3) {
         // fused prologue of the next conv (one tile holds all Cout channels of a voxel; thread = voxel): pass 1 sums the
@@ -281,60 +324,6 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               const float a = silu((__uint_as_float(r[j]) + ep.bias[col]) * rstd * sc0 + sh0);
               const float b = silu((__uint_as_float(r[j + 1]) + ep.bias[col + 1]) * rstd * sc1 + sh1);
               pk[j >> 1] = pack_bf16(a, b);
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-          }
-        }
-      } else if (MODE == 4) {
-        // conv2 of a res block handing over to the next block's conv1: x_new = acc + bias + x_old is stored as fp32 (the
-        // residual stream) AND, normalised / modulated / SiLU'd with the NEXT block's (scale1, shift1), as the bf16 interior of
-        // the next conv's padded volume.  thread = voxel: the row segments it touches are whole 128-byte lines.
-        const int nch = (g.Cout + 31) / 32;
-        const int64_t vox = (static_cast<int64_t>(vt) * g.H + vh) * g.W + vw;
-        const float* xin = ep.resid + vox * g.Cout;
-        float* xout = ep.out + vox * g.Cout;
-        float ss = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          float4 xr[8];
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xr[j] = *reinterpret_cast<const float4*>(xin + c * 32 + 4 * j);
-          }
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = *reinterpret_cast<const float4*>(ep.bias + c * 32 + 4 * j);
-              float4 v = make_float4(__uint_as_float(r[4 * j]) + bv.x + xr[j].x, __uint_as_float(r[4 * j + 1]) + bv.y + xr[j].y,
-                                     __uint_as_float(r[4 * j + 2]) + bv.z + xr[j].z, __uint_as_float(r[4 * j + 3]) + bv.w + xr[j].w);
-              ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-              *reinterpret_cast<float4*>(xout + c * 32 + 4 * j) = v;
-            }
-          }
-        }
-        if (valid) {
-          const float rstd = rsqrtf(ss / g.Cout + 1e-8f);
-          bf16* dst = ep.next_pad + ((static_cast<int64_t>(vt + ep.next_tshift) * (g.H + 2) + (vh + 1)) * (g.W + 2) + (vw + 1)) * g.Cout;
-#pragma unroll 1
-          for (int c = 0; c < nch; ++c) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 v = *reinterpret_cast<const float4*>(xout + c * 32 + 4 * j);   // this thread's own stores
-              const int col = c * 32 + 4 * j;
-              float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ep.next_scale) {
-                const float4 t = *reinterpret_cast<const float4*>(ep.next_scale + col);
-                sc = make_float4(1.f + t.x, 1.f + t.y, 1.f + t.z, 1.f + t.w);
-                sh = *reinterpret_cast<const float4*>(ep.next_shift + col);
-              }
-              pk[2 * j] = pack_bf16(silu(v.x * rstd * sc.x + sh.x), silu(v.y * rstd * sc.y + sh.y));
-              pk[2 * j + 1] = pack_bf16(silu(v.z * rstd * sc.z + sh.z), silu(v.w * rstd * sc.w + sh.w));
             }
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)

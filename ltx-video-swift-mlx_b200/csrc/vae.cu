@@ -152,10 +152,10 @@ void vae_resgroup_fused(ltx_ctx* c, float* x, const std::vector<VaeResBlock>& bl
   }
   exchange(padA);
   const double cflops = 2.0 * 27.0 * C * C * vox, wbytes = 27.0 * C * C * 2.0;
-  // The conv2 -> next conv1 hand-over (mode 4) is off by default: its thread-per-voxel epilogue (fp32 residual read + write,
-  // re-read for the normalised copy) costs more than the prologue kernel it replaces (measured, 25-frame decode: prologue
-  // 3.1 -> 2.2 ms but convs 13.6 -> 15.7 ms).  LTX_VAE_FUSE2=1 enables it for experiments.
-  static const bool fuse2 = []() { const char* e = getenv("LTX_VAE_FUSE2"); return e && e[0] == '1'; }();
+  // conv2 -> next conv1 hand-over (mode 4, in the coalesced epilogue domain).  Measured: 25-frame decode 16.26 -> 16.14 ms
+  // (prologue 3.1 -> 2.3 ms, convs +1.5 ms: the second epilogue pass is exposed at the short 128-channel main loops), 121 frames
+  // 76.7 -> 72.3 ms.  LTX_VAE_FUSE2=0 switches it off.
+  static const bool fuse2 = []() { const char* e = getenv("LTX_VAE_FUSE2"); return !(e && e[0] == '0'); }();
   for (size_t j = 0; j < blocks.size(); ++j) {
     const VaeResBlock& rb = blocks[j];
     const float* tb = tables[j];
