@@ -583,6 +583,37 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
     return head(vx, "scale_shift_table", v_emb, "proj_out"), head(ax, "audio_scale_shift_table", a_emb, "audio_proj_out")
 
 
+def av_denoise_loop(w, cfg: DiTConfig, av: AVConfig, v_noise: Tensor, a_noise: Tensor, v_ctx: Tensor, a_ctx: Tensor,
+                    mask: Optional[Tensor], sigmas: Sequence[float], neg_v_ctx: Optional[Tensor] = None,
+                    neg_a_ctx: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None, cfg_scale: float = 1.0,
+                    phi: float = 0.0):
+    """Audio + video denoise loop (P/LTXPipeline.swift:1277-1404, text-to-video branch): v_noise [1,C,F,H,W], a_noise [1,Ta,128]
+    (packed audio latent).  Per step: one dual forward (two with CFG), video = CFG (+ rescale) + scheduler.step, audio = CFG +
+    plain Euler a += (sigma' - sigma) v (:1402).  Returns (video latent [1,C,F,H,W], audio latent [1,Ta,128])."""
+    fhw = tuple(v_noise.shape[2:])
+    Ta = a_noise.shape[1]
+    v_lat = v_noise.float() * sigmas[0]                                   # :1255-1259
+    a_lat = a_noise.float() * sigmas[0]
+    use_cfg = cfg_scale > 1.0 and neg_v_ctx is not None
+    for step in range(len(sigmas) - 1):
+        sg, sn = sigmas[step], sigmas[step + 1]
+        ts = torch.tensor([sg], dtype=torch.float32)
+        tok = patchify(v_lat)
+        pv, pa = av_dit_forward(w, cfg, av, tok, a_lat, v_ctx, a_ctx, ts, ts, mask, mask, fhw, Ta)
+        vv, va = unpatchify(pv, fhw).float(), pa.float()
+        if use_cfg:
+            nv, na = av_dit_forward(w, cfg, av, tok, a_lat, neg_v_ctx, neg_a_ctx, ts, ts, neg_mask, neg_mask, fhw, Ta)
+            nvv = unpatchify(nv, fhw).float()
+            cond_v = vv
+            vv = apply_cfg(nvv, cond_v, cfg_scale)
+            va = apply_cfg(na.float(), va, cfg_scale)
+            if phi > 0:
+                vv = guidance_rescale(vv, cond_v, phi)
+        v_lat = euler_step(v_lat, vv, sg, sn)
+        a_lat = a_lat + (sn - sg) * va
+    return v_lat, a_lat
+
+
 # ----------------------------------------------------------------------------------------------
 # latent utils, guidance, scheduler (P/LatentUtils.swift, S/LTXScheduler.swift, P/LTXPipeline.swift:800-956)
 # ----------------------------------------------------------------------------------------------

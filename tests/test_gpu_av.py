@@ -118,3 +118,23 @@ def test_av_restrictions_fail_loudly():
         ctx.av_forward(vl, al, vc, ac, 0.5, 0.5, (2, 4, 6))
     assert e.value.code in (2, 4)
     ctx.close()
+
+
+def test_av_denoise_loop_matches_oracle():
+    """generateVideoWithAudio's step loop (P/LTXPipeline.swift:1277-1404) at the host seams, with CFG + rescale: both final
+    latents within the multi-step bf16 bound of the oracle loop."""
+    from ltx_video_swift_mlx_b200.pipeline import denoise_av_host_seam
+    ocfg, av, w, ctx = _setup(2, 2, 2, seed=77)
+    fhw, Ta, S = (2, 4, 6), 11, 40
+    g = torch.Generator().manual_seed(5)
+    vn, an = torch.randn(1, 128, *fhw, generator=g), torch.randn(1, Ta, 128, generator=g)
+
+    def text():
+        t = torch.randn(1, S, 192, generator=g)
+        return (t / t.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
+    vc, ac, nvc, nac = text(), text(), text(), text()
+    sig = O.set_timesteps(8, True, 48)[4:8]
+    rv, ra = O.av_denoise_loop(w, ocfg, av, vn, an, vc.float(), ac.float(), None, sig, nvc.float(), nac.float(), None, cfg_scale=3.0, phi=0.5)
+    ov, oa = denoise_av_host_seam(ctx, vn.numpy(), an.numpy(), vc, ac, None, sig, nvc, nac, None, cfg_scale=3.0, guidance_rescale=0.5)
+    assert rel_l2(ov, rv) <= 2e-2 and rel_l2(oa, ra) <= 2e-2, (rel_l2(ov, rv), rel_l2(oa, ra))
+    ctx.close()
