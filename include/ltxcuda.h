@@ -166,6 +166,19 @@ int ltx_av_forward_dev(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_d
                        ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
                        const float* video_sigma, const float* audio_sigma, const int32_t* video_mask, const int32_t* audio_mask,
                        int N, int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio);
+/* The same call with videoTimesteps of shape [1, N] -- one sigma per video token: the image-to-video branch of
+ * generateVideoWithAudio feeds sigma * (1 - conditioningMask) (Pipeline/LTXPipeline.swift:1293-1298), and the main video
+ * AdaLN-single, both cross-modal video embedders and the output head's embedded timestep are then evaluated per token
+ * (Models/Transformer/LTX2Transformer.swift:273-298, 370-377).  video_sigmas [N] fp32; the audio stream keeps one sigma. */
+int ltx_av_forward_tokens(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                          ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                          const float* video_sigmas, float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N,
+                          int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio);
+int ltx_av_forward_tokens_dev(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                              ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                              const float* video_sigmas, const float* audio_sigma, const int32_t* video_mask,
+                              const int32_t* audio_mask, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                              float* out_video, float* out_audio);
 /* LTXTransformer.clearRoPECache (:202) + drops the cached text K/V. */
 int ltx_dit_clear_caches(ltx_ctx* ctx);
 

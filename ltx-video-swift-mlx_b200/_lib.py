@@ -61,6 +61,8 @@ SIGNATURES = {
     "ltx_dit_forward_dev": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(LtxDitFlags), _P]),
     "ltx_av_forward": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
     "ltx_av_forward_dev": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
+    "ltx_av_forward_tokens": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
+    "ltx_av_forward_tokens_dev": (_I, [_P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _U64, _P, _P]),
     "ltx_dit_clear_caches": (_I, [_P]),
     "ltx_guided_euler_step": (_I, [_P, _P, _P, _P, _P, _P, _I, _SZ, _F, _F, _F, _F, _F, _F]),
     "ltx_guided_euler_step_dev": (_I, [_P, _P, _P, _P, _P, _P, _I, _SZ, _F, _F, _F, _F, _F, _F]),

@@ -240,10 +240,11 @@ class LtxContext:
                                                  mask_ptr, B, N, S, F, H, W,
                                                  C.byref(flags) if flags is not None else None, out_ptr))
 
-    def av_forward(self, video_latent, audio_latent, video_context, audio_context, video_sigma: float, audio_sigma: float,
+    def av_forward(self, video_latent, audio_latent, video_context, audio_context, video_sigma, audio_sigma: float,
                    fhw: Tuple[int, int, int], video_mask=None, audio_mask=None, context_key: int = 0):
         """LTX2Transformer.callAsFunction: video_latent [1,N,C], audio_latent [1,Ta,Ca], contexts [1,S,Cc] ->
-        (video velocity [1,N,C], audio velocity [1,Ta,Ca]) fp32."""
+        (video velocity [1,N,C], audio velocity [1,Ta,Ca]) fp32.  video_sigma: a float, or an array [1,N] / [N] of per-token
+        sigmas (videoTimesteps of the image-to-video mode)."""
         vc, ac, cc = _dtype_code(video_latent), _dtype_code(audio_latent), _dtype_code(video_context)
         assert _dtype_code(audio_context) == cc, "both contexts must have the same dtype"
         vl, al, vx, axx = _host(video_latent), _host(audio_latent), _host(video_context), _host(audio_context)
@@ -254,6 +255,14 @@ class LtxContext:
         ov = np.empty((1, N, self.config.out_channels), dtype=np.float32)
         oa = np.empty((1, Ta, self.config.audio_in_channels), dtype=np.float32)
         F, H, W = fhw
+        if not np.isscalar(video_sigma) and np.asarray(video_sigma).size > 1:
+            vs = np.ascontiguousarray(_host(video_sigma, np.float32).reshape(-1))
+            assert vs.size == N, "per-token video sigmas must have N entries"
+            self._check(self.lib.ltx_av_forward_tokens(self.handle, _ptr(vl), vc, _ptr(al), ac, _ptr(vx), _ptr(axx), cc, _ptr(vs),
+                                                       float(audio_sigma), _ptr(vm), _ptr(am), N, Ta, S, F, H, W,
+                                                       int(context_key), _ptr(ov), _ptr(oa)))
+            return ov, oa
+        video_sigma = float(np.asarray(video_sigma).reshape(-1)[0])
         self._check(self.lib.ltx_av_forward(self.handle, _ptr(vl), vc, _ptr(al), ac, _ptr(vx), _ptr(axx), cc, float(video_sigma),
                                             float(audio_sigma), _ptr(vm), _ptr(am), N, Ta, S, F, H, W, int(context_key),
                                             _ptr(ov), _ptr(oa)))

@@ -329,16 +329,29 @@ int ltx_av_forward_dev(ltx_ctx* c, const void* video_latent, ltx_dtype video_dty
                        int N, int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio) {
   return guarded(c, [&] {
     dit_av_forward_dev(c, video_latent, video_dtype, audio_latent, audio_dtype, video_context, audio_context, context_dtype,
-                       video_sigma, audio_sigma, video_mask, audio_mask, 1, N, Ta, S, F, H, W, context_key, out_video, out_audio);
+                       video_sigma, 0, audio_sigma, video_mask, audio_mask, 1, N, Ta, S, F, H, W, context_key, out_video, out_audio);
   });
 }
 
-int ltx_av_forward(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent, ltx_dtype audio_dtype,
-                   const void* video_context, const void* audio_context, ltx_dtype context_dtype, float video_sigma,
-                   float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N, int Ta, int S, int F, int H,
-                   int W, uint64_t context_key, float* out_video, float* out_audio) {
+int ltx_av_forward_tokens_dev(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                              ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                              const float* video_sigmas, const float* audio_sigma, const int32_t* video_mask,
+                              const int32_t* audio_mask, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                              float* out_video, float* out_audio) {
   return guarded(c, [&] {
-    LTX_CHECK(video_latent && audio_latent && video_context && audio_context && out_video && out_audio, LTX_ERR_INVALID_ARGUMENT,
+    dit_av_forward_dev(c, video_latent, video_dtype, audio_latent, audio_dtype, video_context, audio_context, context_dtype,
+                       video_sigmas, 1, audio_sigma, video_mask, audio_mask, 1, N, Ta, S, F, H, W, context_key, out_video, out_audio);
+  });
+}
+
+// host-buffer form of the dual forward; video_sigmas holds one value, or N when per_token
+static int av_forward_host(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                           ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                           const float* video_sigmas, int per_token, float audio_sigma, const int32_t* video_mask,
+                           const int32_t* audio_mask, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                           float* out_video, float* out_audio) {
+  return guarded(c, [&] {
+    LTX_CHECK(video_latent && audio_latent && video_context && audio_context && video_sigmas && out_video && out_audio, LTX_ERR_INVALID_ARGUMENT,
               "null tensor");
     LTX_CHECK(N >= 1 && Ta >= 1 && S >= 1 && c->av.ready, LTX_ERR_INVALID_ARGUMENT, "bad sizes, or dual-model weights not finalized");
     const ltx_config& g = c->cfg;
@@ -349,8 +362,11 @@ int ltx_av_forward(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, 
     const size_t cbytes = static_cast<size_t>(S) * g.caption_channels * dsize(context_dtype);
     h2d(c, b[2], video_context, cbytes);
     h2d(c, b[3], audio_context, cbytes);
-    const float sig[2] = {video_sigma, audio_sigma};
-    h2d(c, b[4], sig, 8);
+    // sigmas: [audio, video...] so the video values start 4-byte aligned right behind the audio one
+    const size_t nvs = per_token ? static_cast<size_t>(N) : 1;
+    b[4].reserve((1 + nvs) * 4);
+    LTX_CUDA(cudaMemcpyAsync(b[4].ptr, &audio_sigma, 4, cudaMemcpyHostToDevice, c->stream));
+    LTX_CUDA(cudaMemcpyAsync(b[4].as<float>() + 1, video_sigmas, nvs * 4, cudaMemcpyHostToDevice, c->stream));
     const int32_t *vm = nullptr, *am = nullptr;
     b[5].reserve(static_cast<size_t>(2) * S * 4);
     if (video_mask) {
@@ -363,12 +379,28 @@ int ltx_av_forward(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, 
     }
     b[6].reserve(static_cast<size_t>(N) * g.out_channels * 4);
     b[7].reserve(static_cast<size_t>(Ta) * Ca * 4);
-    dit_av_forward_dev(c, b[0].ptr, video_dtype, b[1].ptr, audio_dtype, b[2].ptr, b[3].ptr, context_dtype, b[4].as<float>(),
-                       b[4].as<float>() + 1, vm, am, 1, N, Ta, S, F, H, W, context_key, b[6].as<float>(), b[7].as<float>());
+    dit_av_forward_dev(c, b[0].ptr, video_dtype, b[1].ptr, audio_dtype, b[2].ptr, b[3].ptr, context_dtype, b[4].as<float>() + 1,
+                       per_token, b[4].as<float>(), vm, am, 1, N, Ta, S, F, H, W, context_key, b[6].as<float>(), b[7].as<float>());
     LTX_CUDA(cudaMemcpyAsync(out_video, b[6].ptr, static_cast<size_t>(N) * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaMemcpyAsync(out_audio, b[7].ptr, static_cast<size_t>(Ta) * Ca * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
+}
+
+int ltx_av_forward(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent, ltx_dtype audio_dtype,
+                   const void* video_context, const void* audio_context, ltx_dtype context_dtype, float video_sigma,
+                   float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N, int Ta, int S, int F, int H,
+                   int W, uint64_t context_key, float* out_video, float* out_audio) {
+  return av_forward_host(c, video_latent, video_dtype, audio_latent, audio_dtype, video_context, audio_context, context_dtype,
+                         &video_sigma, 0, audio_sigma, video_mask, audio_mask, N, Ta, S, F, H, W, context_key, out_video, out_audio);
+}
+
+int ltx_av_forward_tokens(ltx_ctx* c, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent,
+                          ltx_dtype audio_dtype, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                          const float* video_sigmas, float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N,
+                          int Ta, int S, int F, int H, int W, uint64_t context_key, float* out_video, float* out_audio) {
+  return av_forward_host(c, video_latent, video_dtype, audio_latent, audio_dtype, video_context, audio_context, context_dtype,
+                         video_sigmas, 1, audio_sigma, video_mask, audio_mask, N, Ta, S, F, H, W, context_key, out_video, out_audio);
 }
 
 int ltx_dit_clear_caches(ltx_ctx* c) {

@@ -283,8 +283,8 @@ void dit_build_rope(ltx_ctx* c, int F, int H, int W);
 // dit_av.cu: dual audio / video model (LTX2Transformer)
 void dit_av_finalize(ltx_ctx* c);
 void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const void* a_latent, int a_dtype, const void* v_context,
-                        const void* a_context, int ctx_dtype, const float* v_ts_dev, const float* a_ts_dev, const int32_t* v_mask_dev,
-                        const int32_t* a_mask_dev, int B, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                        const void* a_context, int ctx_dtype, const float* v_ts_dev, int v_ts_per_token, const float* a_ts_dev,
+                        const int32_t* v_mask_dev, const int32_t* a_mask_dev, int B, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
                         float* out_v_dev, float* out_a_dev);
 // dit_f32.cu
 void dit_finalize_f32(ltx_ctx* c);

@@ -8,8 +8,9 @@
 // Everything GEMM-shaped runs on gemm_bf16_tcgen05 / gemm_bf16_2cta, every attention on attention_fwd_tcgen05 (head_dim 128
 // for the video stream, 64 for audio and cross-modal); the learned-weight norm + modulation and the head_dim-generic q/k
 // norm + RoPE are the two row kernels below.  Text K / V of both streams are step-invariant and cached like the video-only
-// model's.  Restrictions of this first version: B = 1, one sigma per stream (the reference feeds per-token sigmas to the
-// cross-modal embedders only in its image-to-video mode), bf16 weights (no int8 / int4), single GPU.
+// model's.  The video sigma is one scalar, or one value per video token (the image-to-video mode feeds sigma * (1 - mask),
+// Pipeline/LTXPipeline.swift:1293-1298; every video-side embedder then runs per token, LTX2Transformer.swift:273-298).
+// Restrictions of this version: B = 1, bf16 weights (no int8 / int4), single GPU.
 #include <algorithm>
 #include <cmath>
 
@@ -35,11 +36,13 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // RMSNorm(dims:eps:) with a learned weight (T/LTXAttention.swift:12-25) followed by the AdaLN modulation of
 // T/LTX2TransformerBlock.swift:208-281; one row per CTA.
 __global__ void __launch_bounds__(256) rmsnorm_w_mod_kernel(const float* x, bf16* out, int D, const float* w, const float* sc_t,
-                                                             const float* sc_a, const float* sh_t, const float* sh_a, float eps) {
+                                                             const float* sc_a, const float* sh_t, const float* sh_a, int64_t a_ld,
+                                                             float eps) {
   __shared__ float red[8];
   griddep_launch();
   griddep_wait();
   const int row = blockIdx.x;
+  if (sc_a) { sc_a += row * a_ld; sh_a += row * a_ld; }   // a_ld > 0: one modulation row per token (per-token sigmas)
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<int64_t>(row) * D);
   const int nv = D >> 2;
   float ss = 0.f;
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(256) rmsnorm_w_mod_kernel(const float* x, bf16
 struct ModSet {
   const float *sc_t, *sc_a, *sh_t, *sh_a;
   bf16* out;
+  int64_t a_ld;   // 0: sc_a / sh_a are one vector shared by all rows; > 0: row r uses sc_a + r * a_ld (per-token sigmas)
 };
 template <int VPT, int ROWS, int NOUT>
 __global__ void __launch_bounds__(256) rmsnorm_w_mod_fast_kernel(const float* x, int M, const float* w, const ModSet m0,
@@ -118,17 +122,22 @@ __global__ void __launch_bounds__(256) rmsnorm_w_mod_fast_kernel(const float* x,
   for (int o = 0; o < NOUT; ++o) {
     const ModSet& m = o == 0 ? m0 : m1;
     float4 sc[VPT], sh[VPT];
+    auto combine = [&](int64_t aoff) {
 #pragma unroll
-    for (int k = 0; k < VPT; ++k) {
-      const int i = threadIdx.x + k * 256;
-      const float4 ww = ld4(w, i, 1.f), a = ld4(m.sc_t, i, 0.f), b = ld4(m.sc_a, i, 0.f), cc = ld4(m.sh_t, i, 0.f), d = ld4(m.sh_a, i, 0.f);
-      sc[k] = make_float4(ww.x * (1.f + a.x + b.x), ww.y * (1.f + a.y + b.y), ww.z * (1.f + a.z + b.z), ww.w * (1.f + a.w + b.w));
-      sh[k] = make_float4(cc.x + d.x, cc.y + d.y, cc.z + d.z, cc.w + d.w);
-    }
+      for (int k = 0; k < VPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const float4 ww = ld4(w, i, 1.f), a = ld4(m.sc_t, i, 0.f), b = ld4(m.sc_a ? m.sc_a + aoff : nullptr, i, 0.f),
+                     cc = ld4(m.sh_t, i, 0.f), d = ld4(m.sh_a ? m.sh_a + aoff : nullptr, i, 0.f);
+        sc[k] = make_float4(ww.x * (1.f + a.x + b.x), ww.y * (1.f + a.y + b.y), ww.z * (1.f + a.z + b.z), ww.w * (1.f + a.w + b.w));
+        sh[k] = make_float4(cc.x + d.x, cc.y + d.y, cc.z + d.z, cc.w + d.w);
+      }
+    };
+    if (m.a_ld == 0) combine(0);
 #pragma unroll
     for (int rr = 0; rr < ROWS; ++rr) {
       const int row = row0 + rr;
       if (row >= M) break;
+      if (m.a_ld != 0) combine(static_cast<int64_t>(row) * m.a_ld);
       uint2* orow = reinterpret_cast<uint2*>(m.out + static_cast<int64_t>(row) * D);
 #pragma unroll
       for (int k = 0; k < VPT; ++k)
@@ -213,10 +222,10 @@ void linear(ltx_ctx* c, const bf16* A, int M, int K, const bf16* W, const float*
 }
 // x[M, N] (fp32) += (A W^T + b) * (gate_a[n] + gate_b[n])   (null gates: 1)
 void linear_resid(ltx_ctx* c, const bf16* A, int M, int K, const bf16* W, const float* b, int N, float* x, const float* gate_a,
-                  const float* gate_b) {
+                  const float* gate_b, int64_t gate_ld = 0) {
   GemmEpi e;
-  e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = b; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = 0;
-  e.rows_per_gate = M > 0 ? M : 1;
+  e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = b; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = gate_ld;
+  e.rows_per_gate = gate_ld > 0 ? 1 : (M > 0 ? M : 1);   // gate_ld > 0: one gate row per token
   gemm(c, A, K, W, K, M, N, K, e);
 }
 // V^T [Nout, rows] (row pitch ld_out) = (h W^T + b)^T: the weight is the A operand, so the product lands transposed
@@ -232,22 +241,22 @@ void attention(ltx_ctx* c, const bf16* Q, const bf16* K, int64_t ldk, const bf16
   launch_attention(Q, D, K, ldk, Vt, ldv, bias, O, D, 1, H, Nq, Nk, D, 1.0f / sqrtf(static_cast<float>(hd)), c->stream);
 }
 void normw(ltx_ctx* c, const float* x, bf16* out, int M, int D, const float* w, const float* sc_t, const float* sc_a,
-           const float* sh_t, const float* sh_a, float eps) {
+           const float* sh_t, const float* sh_a, float eps, int64_t a_ld = 0) {
   ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * 6.0);
-  const ModSet m{sc_t, sc_a, sh_t, sh_a, out};
+  const ModSet m{sc_t, sc_a, sh_t, sh_a, out, a_ld};
   if (D == 4096)
     launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<4, 4, 1>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m, m, eps);
   else if (D == 2048)
     launch_pdl(PDL_ROWS, rmsnorm_w_mod_fast_kernel<2, 4, 1>, dim3((M + 3) / 4), dim3(256), 0, c->stream, x, M, w, m, m, eps);
   else
-    launch_pdl(PDL_ROWS, rmsnorm_w_mod_kernel, dim3(M), dim3(256), 0, c->stream, x, out, D, w, sc_t, sc_a, sh_t, sh_a, eps);
+    launch_pdl(PDL_ROWS, rmsnorm_w_mod_kernel, dim3(M), dim3(256), 0, c->stream, x, out, D, w, sc_t, sc_a, sh_t, sh_a, a_ld, eps);
   LTX_CUDA(cudaGetLastError());
 }
 // two modulations of the same normalised rows: out0 with (sc0, sh0), out1 with (sc1, sh1); tbl rows r*D of `tbl`, `ada`
 void normw2(ltx_ctx* c, const float* x, bf16* out0, bf16* out1, int M, int D, const float* w, const float* tbl, const float* ada,
-            float eps) {
+            float eps, int64_t a_ld = 0) {
   // rows: 0 a2v scale, 1 a2v shift, 2 v2a scale, 3 v2a shift
-  const ModSet m0{tbl, ada, tbl + D, ada + D, out0}, m1{tbl + 2 * D, ada + 2 * D, tbl + 3 * D, ada + 3 * D, out1};
+  const ModSet m0{tbl, ada, tbl + D, ada + D, out0, a_ld}, m1{tbl + 2 * D, ada + 2 * D, tbl + 3 * D, ada + 3 * D, out1, a_ld};
   if (D == 4096 || D == 2048) {
     ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * 8.0);
     if (D == 4096)
@@ -257,8 +266,8 @@ void normw2(ltx_ctx* c, const float* x, bf16* out0, bf16* out1, int M, int D, co
     LTX_CUDA(cudaGetLastError());
     return;
   }
-  normw(c, x, out0, M, D, w, m0.sc_t, m0.sc_a, m0.sh_t, m0.sh_a, eps);
-  normw(c, x, out1, M, D, w, m1.sc_t, m1.sc_a, m1.sh_t, m1.sh_a, eps);
+  normw(c, x, out0, M, D, w, m0.sc_t, m0.sc_a, m0.sh_t, m0.sh_a, eps, a_ld);
+  normw(c, x, out1, M, D, w, m1.sc_t, m1.sc_a, m1.sh_t, m1.sh_a, eps, a_ld);
 }
 void qknorm_hd(ltx_ctx* c, bf16* x, int M, int D, int hd, const float* w, const float* cs, const float* sn, int rpr, float eps) {
   ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(M) * D * (4.0 + (cs ? 4.0 : 0.0)));
@@ -304,6 +313,25 @@ void adaln_single(ltx_ctx* c, const AdaLnW& a, const float* se, float* t1, float
   launch_gemv(a.w1, a.b1, se, t1, 1, a.dim, 256, 0, c->stream);
   launch_gemv(a.w2, a.b2, t1, emb, 1, a.dim, a.dim, 1, c->stream);
   launch_gemv(a.wl, a.bl, emb, lin, 1, a.n * a.dim, a.dim, 1, c->stream);
+}
+
+// The same for R sigmas (one per video token): the three Linears as tensor-core GEMMs over the R rows, bf16 operands, the
+// SiLUs in the first epilogue / a cast pass (the video-only model's per-token path, dit.cu).  se_bf [R, 256] bf16;
+// t1_bf [R, dim] bf16 scratch; emb [R, dim] fp32; lin [R, n * dim] fp32 with row pitch ld_lin.
+void adaln_single_rows(ltx_ctx* c, const AdaLnW& a, const bf16* se_bf, int R, bf16* t1_bf, float* emb, float* lin, int64_t ld_lin) {
+  GemmEpi e1;
+  e1.mode = EPI_SILU_BF16; e1.out = t1_bf; e1.ldo = a.dim; e1.bias = a.b1;
+  gemm(c, se_bf, 256, a.w1, 256, R, a.dim, 256, e1);
+  GemmEpi e2;
+  e2.mode = EPI_F32; e2.out = emb; e2.ldo = a.dim; e2.bias = a.b2;
+  gemm(c, t1_bf, a.dim, a.w2, a.dim, R, a.dim, a.dim, e2);
+  {
+    ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * R * a.dim);
+    launch_silu_cast(emb, t1_bf, static_cast<int64_t>(R) * a.dim, c->stream);
+  }
+  GemmEpi e3;
+  e3.mode = EPI_F32; e3.out = lin; e3.ldo = ld_lin; e3.bias = a.bl;
+  gemm(c, t1_bf, a.dim, a.wl, a.dim, R, a.n * a.dim, a.dim, e3);
 }
 
 // 1-D RoPE table, token-major [T, dim/2] (precomputeFreqsCis with a [1, T] grid, T/LTXRoPE.swift:375-488): all dim/2
@@ -381,8 +409,8 @@ void dit_av_finalize(ltx_ctx* c) {
 }
 
 void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const void* a_latent, int a_dtype, const void* v_context,
-                        const void* a_context, int ctx_dtype, const float* v_ts_dev, const float* a_ts_dev, const int32_t* v_mask_dev,
-                        const int32_t* a_mask_dev, int B, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
+                        const void* a_context, int ctx_dtype, const float* v_ts_dev, int v_ts_per_token, const float* a_ts_dev,
+                        const int32_t* v_mask_dev, const int32_t* a_mask_dev, int B, int N, int Ta, int S, int F, int H, int W, uint64_t context_key,
                         float* out_v_dev, float* out_a_dev) {
   AvWeights& av = c->av;
   LTX_CHECK(av.ready, LTX_ERR_WEIGHTS, "dual audio/video weights not loaded / finalized");
@@ -411,6 +439,9 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
   c->ffh.reserve(static_cast<size_t>(N) * FFD * 2);
   c->xb.reserve(static_cast<size_t>(N) * D * 2);
   DevBuf& wsb = av.ws;
+  // rows of the video-side modulation tensors: one, or one per token (per-token sigmas); their row pitches
+  const int VR = v_ts_per_token ? N : 1;
+  const int64_t vada_ld = v_ts_per_token ? 6 * static_cast<int64_t>(D) : 0, cv_ld = v_ts_per_token ? 5 * static_cast<int64_t>(D) : 0;
   // audio / cross-modal workspace carved out of one allocation
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -421,10 +452,12 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
                o_cq = carve(static_cast<size_t>(N) * Da * 2), o_catt = carve(static_cast<size_t>(N) * Da * 2),
                o_vt2 = carve(static_cast<size_t>(Da) * ldv * 2), o_lat = carve(static_cast<size_t>(std::max(N * Cv, Ta * Ca)) * 2),
                o_se = carve(2 * 256 * 4), o_t1 = carve(static_cast<size_t>(D) * 4),
-               o_vemb = carve(static_cast<size_t>(D) * 4), o_aemb = carve(static_cast<size_t>(Da) * 4),
-               o_vada = carve(static_cast<size_t>(6) * D * 4), o_aada = carve(static_cast<size_t>(6) * Da * 4),
-               o_cv = carve(static_cast<size_t>(5) * D * 4), o_ca = carve(static_cast<size_t>(5) * Da * 4),
-               o_scr = carve(static_cast<size_t>(D) * 4);
+               o_vemb = carve(static_cast<size_t>(VR) * D * 4), o_aemb = carve(static_cast<size_t>(Da) * 4),
+               o_vada = carve(static_cast<size_t>(VR) * 6 * D * 4), o_aada = carve(static_cast<size_t>(6) * Da * 4),
+               o_cv = carve(static_cast<size_t>(VR) * 5 * D * 4), o_ca = carve(static_cast<size_t>(5) * Da * 4),
+               o_scr = carve(static_cast<size_t>(VR) * D * 4),
+               o_sev = carve(v_ts_per_token ? static_cast<size_t>(N) * 256 * 2 : 0),
+               o_t1v = carve(v_ts_per_token ? static_cast<size_t>(N) * D * 2 : 0);
   wsb.reserve(off);
   uint8_t* wbase = wsb.as<uint8_t>();
   float* x = c->x.as<float>();
@@ -503,10 +536,21 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
   AdaLnW vmain;
   vmain.w1 = c->w_t1; vmain.b1 = c->b_t1; vmain.w2 = c->w_t2; vmain.b2 = c->b_t2; vmain.wl = c->w_ada; vmain.bl = c->b_ada;
   vmain.dim = D; vmain.n = 6;
-  adaln_single(c, vmain, se, t1, vemb, vada);
+  if (!v_ts_per_token) {
+    adaln_single(c, vmain, se, t1, vemb, vada);
+    adaln_single(c, av.cv_ss, se, t1, scr, cv);                 // rows 0-3: a2v scale, a2v shift, v2a scale, v2a shift
+    adaln_single(c, av.cv_g, se, t1, scr, cv + 4 * D);          // row 4: a2v gate
+  } else {
+    bf16 *sev = reinterpret_cast<bf16*>(wbase + o_sev), *t1v = reinterpret_cast<bf16*>(wbase + o_t1v);
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * N + 512.0 * N);
+      launch_sincos_embed(v_ts_dev, g.timestep_scale_multiplier, nullptr, N, 256, st, sev);
+    }
+    adaln_single_rows(c, vmain, sev, N, t1v, vemb, vada, vada_ld);
+    adaln_single_rows(c, av.cv_ss, sev, N, t1v, scr, cv, cv_ld);            // [N, 5, D]: rows 0-3 of every token
+    adaln_single_rows(c, av.cv_g, sev, N, t1v, scr, cv + 4 * D, cv_ld);     // row 4 of every token
+  }
   adaln_single(c, av.ada_a, se + 256, t1, aemb, aada);
-  adaln_single(c, av.cv_ss, se, t1, scr, cv);                 // rows 0-3: a2v scale, a2v shift, v2a scale, v2a shift
-  adaln_single(c, av.cv_g, se, t1, scr, cv + 4 * D);          // row 4: a2v gate
   adaln_single(c, av.ca_ss, se + 256, t1, scr, ca);
   adaln_single(c, av.ca_g, se + 256, t1, scr, ca + 4 * Da);
 
@@ -514,7 +558,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     const BlockWeights& bv = c->blocks[i];
     const AvBlockW& ba = av.blocks[i];
     // ---- 1: video self-attention (T/LTX2TransformerBlock.swift:208-211)
-    normw(c, x, h, N, D, ba.norm1, bv.sst + D, vada + D, bv.sst, vada, eps);
+    normw(c, x, h, N, D, ba.norm1, bv.sst + D, vada + D, bv.sst, vada, eps, vada_ld);
     {
       GemmEpi e;
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bv.a1.bq;
@@ -529,7 +573,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
       ProfScope ps(c, PROF_ATTN, 4.0 * Hv * static_cast<double>(N) * N * hdv, 2.0 * 4.0 * N * D);
       launch_attention(qk, 2 * D, qk + D, 2 * D, vt, ldv, nullptr, att, D, 1, Hv, N, N, D, 1.0f / sqrtf(static_cast<float>(hdv)), st);
     }
-    linear_resid(c, att, N, D, bv.a1.wo, bv.a1.bo, D, x, vada + 2 * D, bv.sst + 2 * D);
+    linear_resid(c, att, N, D, bv.a1.wo, bv.a1.bo, D, x, vada + 2 * D, bv.sst + 2 * D, vada_ld);
     // ---- 2: audio self-attention (:213-216)
     normw(c, ax, ah, Ta, Da, ba.anorm1, ba.asst + Da, aada + Da, ba.asst, aada, eps);
     linear(c, ah, Ta, Da, ba.aa1.wq, ba.aa1.bq, Da, aq);
@@ -555,7 +599,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     linear_resid(c, aatt, Ta, Da, ba.aa2.wo, ba.aa2.bo, Da, ax, nullptr, nullptr);
     // ---- 5-6: cross-modal attention; both directions read the streams as they are here (:228-271).  Table / embedding
     // rows: 0 a2v scale, 1 a2v shift, 2 v2a scale, 3 v2a shift, 4 gate.
-    normw2(c, x, h, h2, N, D, ba.a2v_norm, ba.sst_ca_v, cv, eps);        // video as a2v query (h) and as v2a context (h2)
+    normw2(c, x, h, h2, N, D, ba.a2v_norm, ba.sst_ca_v, cv, eps, cv_ld);      // video as a2v query (h) and as v2a context (h2)
     normw2(c, ax, ah, ah2, Ta, Da, ba.v2a_norm, ba.sst_ca_a, ca, eps);   // audio as a2v context (ah) and as v2a query (ah2)
     // A2V: Q from video (temporal RoPE of the video frames), K / V from audio
     linear(c, h, N, D, ba.a2v.wq, ba.a2v.bq, Da, cq);
@@ -571,29 +615,29 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     qknorm_hd(c, aq, Ta, Da, hda, ba.v2a.q_norm, cos_a, sin_a, Ta, eps);
     qknorm_hd(c, cq, N, Da, hda, ba.v2a.k_norm, cos_xv, sin_xv, N, eps);
     attention(c, aq, cq, Da, vt2, ldv, nullptr, aatt, Ha, hda, Ta, N);
-    linear_resid(c, catt, N, Da, ba.a2v.wo, ba.a2v.bo, D, x, cv + 4 * D, ba.sst_ca_v + 4 * D);
+    linear_resid(c, catt, N, Da, ba.a2v.wo, ba.a2v.bo, D, x, cv + 4 * D, ba.sst_ca_v + 4 * D, cv_ld);
     linear_resid(c, aatt, Ta, Da, ba.v2a.wo, ba.v2a.bo, Da, ax, ca + 4 * Da, ba.sst_ca_a + 4 * Da);
     // ---- 7-8: feed-forward on both streams (:273-281)
-    normw(c, x, h, N, D, ba.norm3, bv.sst + 4 * D, vada + 4 * D, bv.sst + 3 * D, vada + 3 * D, eps);
+    normw(c, x, h, N, D, ba.norm3, bv.sst + 4 * D, vada + 4 * D, bv.sst + 3 * D, vada + 3 * D, eps, vada_ld);
     linear(c, h, N, D, bv.w_in, bv.b_in, FFD, ffh, EPI_GELU_BF16);
-    linear_resid(c, ffh, N, FFD, bv.w_out, bv.b_out, D, x, vada + 5 * D, bv.sst + 5 * D);
+    linear_resid(c, ffh, N, FFD, bv.w_out, bv.b_out, D, x, vada + 5 * D, bv.sst + 5 * D, vada_ld);
     normw(c, ax, ah, Ta, Da, ba.anorm3, ba.asst + 4 * Da, aada + 4 * Da, ba.asst + 3 * Da, aada + 3 * Da, eps);
     linear(c, ah, Ta, Da, ba.w_in, ba.b_in, FFa, affh, EPI_GELU_BF16);
     linear_resid(c, affh, Ta, FFa, ba.w_out, ba.b_out, Da, ax, aada + 5 * Da, ba.asst + 5 * Da);
   }
   // ---- output heads (T/LTX2Transformer.swift:370-388): LayerNorm(no affine) * (1 + scale) + shift ; proj_out
-  auto head = [&](const float* xs, int rows, int Dx, const float* sst, const float* emb, bf16* tmp, const bf16* w, const float* b,
-                  int Cout, float* out) {
+  auto head = [&](const float* xs, int rows, int Dx, const float* sst, const float* emb, int emb_per_row, bf16* tmp, const bf16* w,
+                  const float* b, int Cout, float* out) {
     {
       ProfScope ps(c, PROF_ROW, 0.0, static_cast<double>(rows) * Dx * 6.0);
-      launch_rmsnorm_mod(xs, tmp, rows, Dx, sst, sst + Dx, emb, emb, Dx, rows, eps, 1, st);
+      launch_rmsnorm_mod(xs, tmp, rows, Dx, sst, sst + Dx, emb, emb, Dx, emb_per_row ? 1 : rows, eps, 1, st);
     }
     GemmEpi e;
     e.mode = EPI_F32; e.out = out; e.ldo = Cout; e.bias = b;
     gemm(c, tmp, Dx, w, Dx, rows, Cout, Dx, e);
   };
-  head(x, N, D, c->sst_out, vemb, h, c->w_out, c->b_out, g.out_channels, out_v_dev);
-  head(ax, Ta, Da, av.sst_out, aemb, ah, av.w_out, av.b_out, Ca, out_a_dev);
+  head(x, N, D, c->sst_out, vemb, v_ts_per_token, h, c->w_out, c->b_out, g.out_channels, out_v_dev);
+  head(ax, Ta, Da, av.sst_out, aemb, 0, ah, av.w_out, av.b_out, Ca, out_a_dev);
 }
 
 }  // namespace ltx

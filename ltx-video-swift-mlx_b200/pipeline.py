@@ -77,29 +77,45 @@ def generate_two_stage_resident(ctx: LtxContext, noise1: np.ndarray, noise2: np.
 
 def denoise_av_host_seam(ctx: LtxContext, video_noise: np.ndarray, audio_noise: np.ndarray, video_context, audio_context, mask,
                          sigmas: Sequence[float], neg_video_context=None, neg_audio_context=None, neg_mask=None,
-                         cfg_scale: float = 1.0, guidance_rescale: float = 0.0, cache_text: bool = True):
-    """The audio + video denoise loop of generateVideoWithAudio (Pipeline/LTXPipeline.swift:1277-1404, text-to-video branch) at
-    the Swift seams: one LTX2Transformer call per step (two with CFG), CFG / rescale / scheduler.step on the video latent through
+                         cfg_scale: float = 1.0, guidance_rescale: float = 0.0, cache_text: bool = True,
+                         image_latent: Optional[np.ndarray] = None, inject_noise: Optional[Sequence[np.ndarray]] = None,
+                         image_cond_noise_scale: float = 0.0):
+    """The audio + video denoise loop of generateVideoWithAudio (Pipeline/LTXPipeline.swift:1277-1404) at the Swift seams: one
+    LTX2Transformer call per step (two with CFG), CFG / rescale / scheduler.step on the video latent through
     ltx_guided_euler_step, CFG + plain Euler on the packed audio latent.  video_noise [1,C,F,H,W], audio_noise [1,Ta,Ca] fp32.
-    Returns (video latent, audio latent)."""
+    image_latent [1,C,1,H,W] selects the image-to-video branch (:1262-1298, 1381-1391): frame 0 holds the image latent
+    (optionally re-noised per step with the caller's draws, inject_noise[step] * scale * sigma^2), the video timesteps are per
+    token (0 on frame 0), and the Euler update leaves frame 0 untouched.  Returns (video latent, audio latent)."""
     _, C, F, H, W = video_noise.shape
     shape = VideoLatentShape(1, C, F, H, W)
     v_lat = np.ascontiguousarray(video_noise.astype(np.float32) * np.float32(sigmas[0]))       # :1255-1259
     a_lat = np.ascontiguousarray(audio_noise.astype(np.float32) * np.float32(sigmas[0]))
+    cond_mask = None
+    if image_latent is not None:
+        v_lat[:, :, 0:1] = np.asarray(image_latent, dtype=np.float32)
+        cond_mask = np.zeros((1, F * H * W), dtype=np.float32)
+        cond_mask[:, :H * W] = 1.0
     use_cfg = cfg_scale > 1.0 and neg_video_context is not None
     for step in range(len(sigmas) - 1):
         sg, sn = float(sigmas[step]), float(sigmas[step + 1])
+        if image_latent is not None and image_cond_noise_scale > 0 and sg > 0 and inject_noise is not None:
+            v_lat[:, :, 0:1] = (np.asarray(image_latent, dtype=np.float32) + np.float32(image_cond_noise_scale)
+                                * np.asarray(inject_noise[step], dtype=np.float32) * np.float32(sg * sg))
         tok = patchify(v_lat)
-        pv, pa = ctx.av_forward(tok, a_lat, video_context, audio_context, sg, sg, shape.fhw, mask, mask,
+        vsg = sg if cond_mask is None else np.float32(sg) * (1.0 - cond_mask)                  # :1294-1298
+        pv, pa = ctx.av_forward(tok, a_lat, video_context, audio_context, vsg, sg, shape.fhw, mask, mask,
                                 context_key=11 if cache_text else 0)
         vc, vu = unpatchify(pv, shape), None
         va = pa
         if use_cfg:                                                                            # :1310-1362
-            nv, na = ctx.av_forward(tok, a_lat, neg_video_context, neg_audio_context, sg, sg, shape.fhw, neg_mask, neg_mask,
+            nv, na = ctx.av_forward(tok, a_lat, neg_video_context, neg_audio_context, vsg, sg, shape.fhw, neg_mask, neg_mask,
                                     context_key=12 if cache_text else 0)
             vu = unpatchify(nv, shape)
             va = pa + np.float32(cfg_scale - 1.0) * (pa - na)                                  # applyCFG on the audio velocity
+        frame0 = v_lat[:, :, 0:1].copy() if image_latent is not None else None
         ctx.guided_euler_step(v_lat, vc, vu, None, None, cfg_scale=cfg_scale if use_cfg else 1.0,
                               rescale_phi=guidance_rescale if use_cfg else 0.0, sigma=sg, sigma_next=sn)
+        if frame0 is not None:                    # :1381-1391: the element-wise Euler update is discarded on frame 0
+            v_lat[:, :, 0:1] = frame0
         a_lat = a_lat + np.float32(sn - sg) * va                                               # :1402
     return v_lat, a_lat

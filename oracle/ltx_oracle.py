@@ -500,8 +500,9 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
                    v_sigma: Tensor, a_sigma: Tensor, v_mask: Optional[Tensor], a_mask: Optional[Tensor],
                    fhw: Tuple[int, int, int], audio_frames: int, dtype=torch.float32, mlx_bf16: bool = True):
     """LTX2Transformer.callAsFunction (T/LTX2Transformer.swift:240-392) with LTX2TransformerBlock (:174-297).
-    v_latent [B,N,128], a_latent [B,Ta,128], contexts [B,S,3840], sigmas [B].  Returns (video velocity [B,N,128],
-    audio velocity [B,Ta,128])."""
+    v_latent [B,N,128], a_latent [B,Ta,128], contexts [B,S,3840], sigmas [B] (v_sigma may be [B,N]: the image-to-video mode
+    feeds sigma * (1 - mask) per video token, P/LTXPipeline.swift:1293-1298, and every video-side embedder then works per
+    token).  Returns (video velocity [B,N,128], audio velocity [B,Ta,128])."""
     F, H, W = fhw
     D, Da, eps = cfg.inner_dim, av.audio_dim, cfg.norm_eps
     B = v_latent.shape[0]
@@ -516,7 +517,7 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
     ta = a_sigma.to(torch.float32) * cfg.timestep_scale_multiplier
     v_ada, v_emb = _adaln_single(w, "adaln_single", tv, dtype)
     a_ada, a_emb = _adaln_single(w, "audio_adaln_single", ta, dtype)
-    v_ada, a_ada = v_ada.view(B, 1, 6, D), a_ada.view(B, 1, 6, Da)
+    v_ada, a_ada = v_ada.view(B, -1, 6, D), a_ada.view(B, -1, 6, Da)      # [B, 1 | N, 6, D]: per-token sigmas in I2V mode (:275-283)
     pvc = caption_projection(w, vc, mlx_bf16)                                        # :259
     h = linear(ac, w, "audio_caption_projection.linear_1")                           # :266
     if mlx_bf16:
@@ -532,8 +533,8 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
     cv_g, _ = _adaln_single(w, "av_ca_a2v_gate_adaln_single", tv, dtype)
     ca_ss, _ = _adaln_single(w, "av_ca_audio_scale_shift_adaln_single", ta, dtype)
     ca_g, _ = _adaln_single(w, "av_ca_v2a_gate_adaln_single", ta, dtype)
-    cv = torch.cat([cv_ss.view(B, 1, 4, D), cv_g.view(B, 1, 1, D)], dim=2)
-    ca = torch.cat([ca_ss.view(B, 1, 4, Da), ca_g.view(B, 1, 1, Da)], dim=2)
+    cv = torch.cat([cv_ss.view(B, -1, 4, D), cv_g.view(B, -1, 1, D)], dim=2)
+    ca = torch.cat([ca_ss.view(B, -1, 4, Da), ca_g.view(B, -1, 1, Da)], dim=2)
     vbias = None if v_mask is None else ((1.0 - v_mask.to(dtype)) * -10000.0).view(B, 1, 1, -1)   # :394-403
     abias = None if a_mask is None else ((1.0 - a_mask.to(dtype)) * -10000.0).view(B, 1, 1, -1)
     v_rope = rope_table(cfg, F, H, W)                                                # :138-160
@@ -575,7 +576,7 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
         ax = ax + linear(gelu_tanh(linear(n, w, p + ".audio_ff.project_in.proj")), w, p + ".audio_ff.project_out") * as_[:, :, 5]
 
     def head(x, table, emb, proj):                                                    # T/LTX2Transformer.swift:370-388
-        o = w[table].to(dtype).view(1, 1, 2, -1) + emb.view(B, 1, 1, -1)
+        o = w[table].to(dtype).view(1, 1, 2, -1) + emb.view(B, -1, 1, x.shape[-1])
         mu = x.mean(-1, keepdim=True)
         y = (x - mu) * torch.rsqrt((x - mu).pow(2).mean(-1, keepdim=True) + eps)
         return linear(y * (1 + o[:, :, 1]) + o[:, :, 0], w, proj)
@@ -586,30 +587,46 @@ def av_dit_forward(w, cfg: DiTConfig, av: AVConfig, v_latent: Tensor, a_latent: 
 def av_denoise_loop(w, cfg: DiTConfig, av: AVConfig, v_noise: Tensor, a_noise: Tensor, v_ctx: Tensor, a_ctx: Tensor,
                     mask: Optional[Tensor], sigmas: Sequence[float], neg_v_ctx: Optional[Tensor] = None,
                     neg_a_ctx: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None, cfg_scale: float = 1.0,
-                    phi: float = 0.0):
-    """Audio + video denoise loop (P/LTXPipeline.swift:1277-1404, text-to-video branch): v_noise [1,C,F,H,W], a_noise [1,Ta,128]
-    (packed audio latent).  Per step: one dual forward (two with CFG), video = CFG (+ rescale) + scheduler.step, audio = CFG +
-    plain Euler a += (sigma' - sigma) v (:1402).  Returns (video latent [1,C,F,H,W], audio latent [1,Ta,128])."""
+                    phi: float = 0.0, image_latent: Optional[Tensor] = None, inject_noise: Optional[Sequence[Tensor]] = None,
+                    image_cond_noise_scale: float = 0.0):
+    """Audio + video denoise loop (P/LTXPipeline.swift:1277-1404): v_noise [1,C,F,H,W], a_noise [1,Ta,128] (packed audio
+    latent).  Per step: one dual forward (two with CFG), video = CFG (+ rescale) + scheduler.step, audio = CFG + plain Euler
+    a += (sigma' - sigma) v (:1402).  image_latent [1,C,1,H,W] selects the image-to-video branch: frame 0 := image latent
+    (:1262-1274), optionally re-noised every step with inject_noise[step] * scale * sigma^2 (:1288-1292; the draws are passed in
+    as data), video timesteps = sigma * (1 - mask) per token (:1294-1298), Euler only on frames 1+ (:1381-1391).
+    Returns (video latent [1,C,F,H,W], audio latent [1,Ta,128])."""
     fhw = tuple(v_noise.shape[2:])
     Ta = a_noise.shape[1]
     v_lat = v_noise.float() * sigmas[0]                                   # :1255-1259
     a_lat = a_noise.float() * sigmas[0]
+    cond_mask = None
+    if image_latent is not None:
+        v_lat = v_lat.clone()
+        v_lat[:, :, 0:1] = image_latent.float()
+        cond_mask = torch.zeros(1, fhw[0] * fhw[1] * fhw[2])
+        cond_mask[:, :fhw[1] * fhw[2]] = 1.0
     use_cfg = cfg_scale > 1.0 and neg_v_ctx is not None
     for step in range(len(sigmas) - 1):
         sg, sn = sigmas[step], sigmas[step + 1]
         ts = torch.tensor([sg], dtype=torch.float32)
+        if image_latent is not None and image_cond_noise_scale > 0 and sg > 0 and inject_noise is not None:
+            v_lat[:, :, 0:1] = image_latent.float() + image_cond_noise_scale * inject_noise[step].float() * (sg * sg)
+        tsv = ts if cond_mask is None else torch.tensor(sg, dtype=torch.float32) * (1 - cond_mask)
         tok = patchify(v_lat)
-        pv, pa = av_dit_forward(w, cfg, av, tok, a_lat, v_ctx, a_ctx, ts, ts, mask, mask, fhw, Ta)
+        pv, pa = av_dit_forward(w, cfg, av, tok, a_lat, v_ctx, a_ctx, tsv, ts, mask, mask, fhw, Ta)
         vv, va = unpatchify(pv, fhw).float(), pa.float()
         if use_cfg:
-            nv, na = av_dit_forward(w, cfg, av, tok, a_lat, neg_v_ctx, neg_a_ctx, ts, ts, neg_mask, neg_mask, fhw, Ta)
+            nv, na = av_dit_forward(w, cfg, av, tok, a_lat, neg_v_ctx, neg_a_ctx, tsv, ts, neg_mask, neg_mask, fhw, Ta)
             nvv = unpatchify(nv, fhw).float()
             cond_v = vv
             vv = apply_cfg(nvv, cond_v, cfg_scale)
             va = apply_cfg(na.float(), va, cfg_scale)
             if phi > 0:
                 vv = guidance_rescale(vv, cond_v, phi)
-        v_lat = euler_step(v_lat, vv, sg, sn)
+        if image_latent is not None:                                      # :1381-1391: frame 0 stays as it is
+            v_lat = torch.cat([v_lat[:, :, 0:1], euler_step(v_lat[:, :, 1:], vv[:, :, 1:], sg, sn)], dim=2)
+        else:
+            v_lat = euler_step(v_lat, vv, sg, sn)
         a_lat = a_lat + (sn - sg) * va
     return v_lat, a_lat
 

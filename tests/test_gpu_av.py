@@ -62,6 +62,36 @@ def test_av_forward_matches_oracle(layers, heads, aheads, fhw, Ta, S, mask_prefi
     ctx.close()
 
 
+@pytest.mark.parametrize("layers,heads,aheads,fhw,Ta,S", [
+    (2, 2, 2, (3, 4, 6), 11, 40),
+    (1, 4, 2, (2, 8, 10), 130, 150),
+])
+def test_av_forward_per_token_sigmas_match_oracle(layers, heads, aheads, fhw, Ta, S):
+    """videoTimesteps [1, N] (image-to-video: sigma * (1 - conditioningMask), P/LTXPipeline.swift:1293-1298): the main video
+    AdaLN-single, the two cross-modal video embedders and the head's embedded timestep are per token
+    (T/LTX2Transformer.swift:273-298).  Frame 0 at sigma 0, a ramp elsewhere so every token has its own modulation row."""
+    ocfg, av, w, ctx = _setup(layers, heads, aheads, seed=layers * 100 + heads * 10 + aheads + 1)
+    vl, al, vc, ac, _ = _inputs(fhw, Ta, S, 192, 4)
+    N = fhw[0] * fhw[1] * fhw[2]
+    ts = torch.linspace(0.35, 0.85, N).view(1, N)
+    ts[:, :fhw[1] * fhw[2]] = 0.0
+    rv, ra = O.av_dit_forward(w, ocfg, av, vl.float(), al.float(), vc.float(), ac.float(), ts, torch.tensor([0.55]), None, None,
+                              fhw, Ta)
+    ov, oa = ctx.av_forward(vl, al, vc, ac, ts.numpy(), 0.55, fhw)
+    assert np.isfinite(ov).all() and np.isfinite(oa).all()
+    assert rel_l2(ov, rv) <= TOL, rel_l2(ov, rv)
+    assert rel_l2(oa, ra) <= TOL, rel_l2(oa, ra)
+    ov2, oa2 = ctx.av_forward(vl, al, vc, ac, ts.numpy(), 0.55, fhw)
+    assert np.array_equal(ov2, ov) and np.array_equal(oa2, oa)
+    # a constant per-token vector is the scalar call up to the embedders' arithmetic (tensor-core GEMM vs fp32 GEMV)
+    us, ua = ctx.av_forward(vl, al, vc, ac, 0.7, 0.55, fhw)
+    ut, uat = ctx.av_forward(vl, al, vc, ac, np.full((1, N), 0.7, dtype=np.float32), 0.55, fhw)
+    assert rel_l2(ut, us) <= 5e-3 and rel_l2(uat, ua) <= 5e-3, (rel_l2(ut, us), rel_l2(uat, ua))
+    # the per-token values matter: the scalar result is far from the image-conditioned one
+    assert rel_l2(us, ov) > 1e-2
+    ctx.close()
+
+
 def test_av_streams_are_coupled_and_video_only_model_still_works():
     """Changing the audio latent changes the video velocity (the a2v attention is live), and the same context still serves
     the video-only forward (LTXTransformer) from the shared video weights."""
@@ -92,6 +122,16 @@ def test_av_random_init_full_width_block():
     ov2, oa2 = ctx.av_forward(vl, al, vc, ac, 0.8, 0.8, fhw)
     assert np.isfinite(ov).all() and np.isfinite(oa).all() and ov.std() > 0.05 and oa.std() > 0.05
     assert np.array_equal(ov, ov2) and np.array_equal(oa, oa2)
+    # per-token sigmas on the D = 4096 / 2048 row kernels: a constant vector reproduces the scalar call, a frame-0 mask does not
+    N = fhw[0] * fhw[1] * fhw[2]
+    ts = np.full((1, N), 0.8, dtype=np.float32)
+    pv, pa = ctx.av_forward(vl, al, vc, ac, ts, 0.8, fhw)
+    assert rel_l2(pv, ov) <= 5e-3 and rel_l2(pa, oa) <= 5e-3, (rel_l2(pv, ov), rel_l2(pa, oa))
+    ts[:, :fhw[1] * fhw[2]] = 0.0
+    qv, qa = ctx.av_forward(vl, al, vc, ac, ts, 0.8, fhw)
+    qv2, _ = ctx.av_forward(vl, al, vc, ac, ts, 0.8, fhw)
+    assert np.isfinite(qv).all() and np.isfinite(qa).all() and np.array_equal(qv, qv2)
+    assert rel_l2(qv[:, :fhw[1] * fhw[2]], ov[:, :fhw[1] * fhw[2]]) > 1e-2
     ctx.close()
 
 
@@ -137,4 +177,32 @@ def test_av_denoise_loop_matches_oracle():
     rv, ra = O.av_denoise_loop(w, ocfg, av, vn, an, vc.float(), ac.float(), None, sig, nvc.float(), nac.float(), None, cfg_scale=3.0, phi=0.5)
     ov, oa = denoise_av_host_seam(ctx, vn.numpy(), an.numpy(), vc, ac, None, sig, nvc, nac, None, cfg_scale=3.0, guidance_rescale=0.5)
     assert rel_l2(ov, rv) <= 2e-2 and rel_l2(oa, ra) <= 2e-2, (rel_l2(ov, rv), rel_l2(oa, ra))
+    ctx.close()
+
+
+def test_av_image_conditioned_denoise_loop_matches_oracle():
+    """The image-to-video branch of generateVideoWithAudio (P/LTXPipeline.swift:1262-1298, 1381-1391): frame 0 = image latent
+    (+ per-step injected noise passed in as data), per-token video timesteps, Euler on frames 1+ only."""
+    from ltx_video_swift_mlx_b200.pipeline import denoise_av_host_seam
+    ocfg, av, w, ctx = _setup(2, 2, 2, seed=78)
+    fhw, Ta, S = (3, 4, 6), 11, 40
+    g = torch.Generator().manual_seed(6)
+    vn, an = torch.randn(1, 128, *fhw, generator=g), torch.randn(1, Ta, 128, generator=g)
+    img = torch.randn(1, 128, 1, fhw[1], fhw[2], generator=g)
+
+    def text():
+        t = torch.randn(1, S, 192, generator=g)
+        return (t / t.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
+    vc, ac = text(), text()
+    sig = O.set_timesteps(8, True, 72)[3:7]
+    inj = [torch.randn(1, 128, 1, fhw[1], fhw[2], generator=g) for _ in range(len(sig) - 1)]
+    rv, ra = O.av_denoise_loop(w, ocfg, av, vn, an, vc.float(), ac.float(), None, sig, image_latent=img, inject_noise=inj,
+                               image_cond_noise_scale=0.15)
+    ov, oa = denoise_av_host_seam(ctx, vn.numpy(), an.numpy(), vc, ac, None, sig, image_latent=img.numpy(),
+                                  inject_noise=[t.numpy() for t in inj], image_cond_noise_scale=0.15)
+    assert rel_l2(ov, rv) <= 2e-2 and rel_l2(oa, ra) <= 2e-2, (rel_l2(ov, rv), rel_l2(oa, ra))
+    # frame 0 left the loop as the (last) conditioned frame, untouched by the Euler update
+    sg_last = float(sig[-2])
+    expect0 = img + 0.15 * inj[-1] * (sg_last * sg_last) if sg_last > 0 else img
+    assert np.allclose(ov[:, :, 0:1], expect0.numpy(), atol=1e-6)
     ctx.close()

@@ -222,3 +222,33 @@ def test_av_oracle_structure():
     v2, _ = O.av_dit_forward(wz, cfg, av, vl, al, vc, ac, sg, sg, None, None, fhw, Ta)
     v3, _ = O.av_dit_forward(wz, cfg, av, vl, al * 2.0, vc, ac, sg, sg, None, None, fhw, Ta)
     assert torch.equal(v2, v3)
+
+
+def test_av_oracle_per_token_sigmas_and_image_conditioned_loop():
+    """videoTimesteps [1, N] (T/LTX2Transformer.swift:273-298): a constant per-token vector equals the scalar call; in the
+    image-to-video loop (P/LTXPipeline.swift:1262-1298, 1381-1391) frame 0 keeps the image latent and the other frames move."""
+    cfg = O.DiTConfig(num_layers=1, num_heads=2, caption_channels=64)
+    av = O.AVConfig(audio_heads=2)
+    w = O.make_av_weights(cfg, av, 6)
+    gen = torch.Generator().manual_seed(2)
+    fhw, Ta, S = (2, 2, 3), 5, 7
+    N = 12
+    vl, al = torch.randn(1, N, 128, generator=gen), torch.randn(1, Ta, 128, generator=gen)
+    vc, ac = torch.randn(1, S, 64, generator=gen), torch.randn(1, S, 64, generator=gen)
+    sg = torch.tensor([0.6])
+    v0, a0 = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, sg, sg, None, None, fhw, Ta)
+    v1, a1 = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, torch.full((1, N), 0.6), sg, None, None, fhw, Ta)
+    assert O.rel_l2(v1, v0) < 1e-5 and O.rel_l2(a1, a0) < 1e-5
+    ts = torch.full((1, N), 0.6)
+    ts[:, :6] = 0.0
+    v2, _ = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, ts, sg, None, None, fhw, Ta)
+    assert O.rel_l2(v2[:, :6], v0[:, :6]) > 1e-3
+    vn, an = torch.randn(1, 128, *fhw, generator=gen), torch.randn(1, Ta, 128, generator=gen)
+    img = torch.randn(1, 128, 1, 2, 3, generator=gen)
+    sig = [1.0, 0.7, 0.3, 0.0]
+    lv, la = O.av_denoise_loop(w, cfg, av, vn, an, vc, ac, None, sig, image_latent=img)
+    assert torch.equal(lv[:, :, 0:1], img) and lv.shape == vn.shape and la.shape == an.shape
+    assert not torch.allclose(lv[:, :, 1:], vn[:, :, 1:])
+    inj = [torch.randn(1, 128, 1, 2, 3, generator=gen) for _ in range(3)]
+    lv2, _ = O.av_denoise_loop(w, cfg, av, vn, an, vc, ac, None, sig, image_latent=img, inject_noise=inj, image_cond_noise_scale=0.1)
+    assert torch.allclose(lv2[:, :, 0:1], img + 0.1 * inj[2] * 0.3 * 0.3, atol=1e-6)
