@@ -227,6 +227,19 @@ int ltx_vae_decode(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, fl
                    int causal, float* out_frames);
 int ltx_vae_decode_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep,
                        const float* decode_noise, int causal, float* out_frames);
+/* decodeVideo with temporalTileSize > 0 and more latent frames than one tile (Models/VAE/VideoDecoder.swift:482-494 ->
+ * decodeWithTemporalTiling :517-602): chunks of tile_size latent frames at stride tile_size - tile_overlap are decoded
+ * independently, the 8 * tile_overlap frames they share are cross-faded linearly (weight j / (8 overlap) on the later chunk),
+ * and the result is normalised and clipped.  This is the reference's memory-saving approximation (Fp <= tile_size, or
+ * tile_size <= 0, is the exact single pass); its frame count follows the chunk arithmetic -- ltx_vae_tiled_frames gives it
+ * (-1 for an invalid tile / overlap pair) so that the caller can size out_frames [frames, 32H', 32W', 3].  With
+ * timestep >= 0 each chunk mixes in its own slice of decode_noise. */
+int ltx_vae_tiled_frames(int Fp, int tile_size, int tile_overlap);
+int ltx_vae_decode_tiled(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                         int causal, int tile_size, int tile_overlap, float* out_frames, int* out_num_frames);
+int ltx_vae_decode_tiled_dev(ltx_ctx* ctx, const float* latent, int Fp, int Hp, int Wp, float timestep,
+                             const float* decode_noise, int causal, int tile_size, int tile_overlap, float* out_frames,
+                             int* out_num_frames);
 
 /* VideoEncoder.callAsFunction (Models/VAE/VideoEncoder.swift:270-312), the encoder half of encodeImage
  * (Pipeline/LTXPipeline.swift:1902-1932): pixels [3, T, H, W] fp32 (the reference feeds [-1, 1]), H and W multiples of 32

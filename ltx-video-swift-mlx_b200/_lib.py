@@ -72,6 +72,9 @@ SIGNATURES = {
     "ltx_denoise_latent_dev": (_I, [_P, C.POINTER(_P)]),
     "ltx_vae_decode": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_decode_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
+    "ltx_vae_tiled_frames": (_I, [_I, _I, _I]),
+    "ltx_vae_decode_tiled": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
+    "ltx_vae_decode_tiled_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _I, _I, _P, _P]),
     "ltx_vae_encode": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ltx_vae_encode_dev": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ltx_upscale_latent": (_I, [_P, _P, _I, _I, _I, _P]),

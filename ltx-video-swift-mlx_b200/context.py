@@ -395,6 +395,26 @@ class LtxContext:
                                             _ptr(nz), int(causal), _ptr(out)))
         return out
 
+    def vae_decode_tiled(self, latent, tile_size: int, tile_overlap: int = 1, timestep: Optional[float] = None,
+                         decode_noise=None, causal: bool = False) -> np.ndarray:
+        """decodeVideo's temporally tiled branch (decodeWithTemporalTiling, Models/VAE/VideoDecoder.swift:517-602)."""
+        lat = _host(latent, np.float32)
+        if lat.ndim == 5:
+            lat = lat[0]
+        Cc, Fp, Hp, Wp = lat.shape
+        lat = np.ascontiguousarray(lat)
+        nz = None if decode_noise is None else np.ascontiguousarray(_host(decode_noise, np.float32).reshape(lat.shape))
+        nf = self.lib.ltx_vae_tiled_frames(Fp, int(tile_size), int(tile_overlap))
+        if nf <= 0:
+            raise LtxError(2, "temporal tile overlap must be in [0, tile size)")
+        out = np.empty((nf, 32 * Hp, 32 * Wp, 3), dtype=np.float32)
+        got = C.c_int(0)
+        self._check(self.lib.ltx_vae_decode_tiled(self.handle, _ptr(lat), Fp, Hp, Wp, -1.0 if timestep is None else float(timestep),
+                                                  _ptr(nz), int(causal), int(tile_size), int(tile_overlap), _ptr(out),
+                                                  C.byref(got)))
+        assert got.value == nf
+        return out
+
     def vae_decode_dev(self, latent_ptr: int, fhw, out_ptr: int, causal: bool = False):
         Fp, Hp, Wp = fhw
         self._check(self.lib.ltx_vae_decode_dev(self.handle, latent_ptr, Fp, Hp, Wp, -1.0, None, int(causal), out_ptr))

@@ -684,6 +684,44 @@ int ltx_vae_decode(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, floa
   });
 }
 
+int ltx_vae_tiled_frames(int Fp, int tile_size, int tile_overlap) {
+  if (Fp <= 0 || (tile_size > 0 && Fp > tile_size && (tile_overlap < 0 || tile_overlap >= tile_size))) return -1;
+  return vae_tiled_frames(Fp, tile_size, tile_overlap);
+}
+
+int ltx_vae_decode_tiled_dev(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                             int causal, int tile_size, int tile_overlap, float* out_frames, int* out_num_frames) {
+  return guarded(c, [&] {
+    const int n = vae_decode_tiled_dev(c, latent, Fp, Hp, Wp, timestep, decode_noise, causal, tile_size, tile_overlap, out_frames);
+    if (out_num_frames) *out_num_frames = n;
+  });
+}
+
+int ltx_vae_decode_tiled(ltx_ctx* c, const float* latent, int Fp, int Hp, int Wp, float timestep, const float* decode_noise,
+                         int causal, int tile_size, int tile_overlap, float* out_frames, int* out_num_frames) {
+  return guarded(c, [&] {
+    LTX_CHECK(latent && out_frames && Fp > 0 && Hp > 0 && Wp > 0, LTX_ERR_INVALID_ARGUMENT, "bad vae_decode arguments");
+    const int nf = ltx_vae_tiled_frames(Fp, tile_size, tile_overlap);
+    LTX_CHECK(nf > 0, LTX_ERR_INVALID_ARGUMENT, "temporal tile overlap must be in [0, tile size)");
+    const size_t n = static_cast<size_t>(c->cfg.vae_latent_channels) * Fp * Hp * Wp;
+    h2d(c, c->v_lat, latent, n * 4);
+    const float* nz = nullptr;
+    if (timestep >= 0.f) {
+      LTX_CHECK(decode_noise != nullptr, LTX_ERR_INVALID_ARGUMENT, "decode_noise is required when timestep >= 0");
+      h2d(c, c->v_noise, decode_noise, n * 4);
+      nz = c->v_noise.as<float>();
+    }
+    const size_t fe = static_cast<size_t>(32 * Hp) * (32 * Wp) * 3;
+    c->v_frames.reserve(static_cast<size_t>(nf) * fe * 4);
+    const int got = vae_decode_tiled_dev(c, c->v_lat.as<float>(), Fp, Hp, Wp, timestep, nz, causal, tile_size, tile_overlap,
+                                         c->v_frames.as<float>());
+    LTX_CHECK(got == nf, LTX_ERR_CUDA, "tiled decode frame count mismatch");
+    if (out_num_frames) *out_num_frames = got;
+    LTX_CUDA(cudaMemcpyAsync(out_frames, c->v_frames.ptr, static_cast<size_t>(got) * fe * 4, cudaMemcpyDeviceToHost, c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
 // ---------------------------------------------------------------- VAE encoder, latent upscaler, AdaIN, re-noise
 int ltx_vae_encode_dev(ltx_ctx* c, const float* pixels, int T, int H, int W, int normalize, float* latent_out) {
   return guarded(c, [&] { vae_encode_dev(c, pixels, T, H, W, normalize, latent_out); });

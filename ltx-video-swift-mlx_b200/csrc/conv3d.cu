@@ -95,7 +95,7 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
       const int co = col0 + j;
       const int c = co >> 4, pa = (co >> 2) & 3, pb = co & 3;
       const float v = (__uint_as_float(r[j]) + ep.bias[co] + 1.0f) * 0.5f;
-      ep.out[((static_cast<int64_t>(t) * Ho + (4 * h + pb)) * Wo + (4 * w + pa)) * 3 + c] = clip01(v);
+      ep.out[((static_cast<int64_t>(t) * Ho + (4 * h + pb)) * Wo + (4 * w + pa)) * 3 + c] = ep.no_clip ? v : clip01(v);
     }
   }
 }

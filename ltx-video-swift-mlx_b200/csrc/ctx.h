@@ -238,6 +238,8 @@ struct ltx_ctx {
 
   // ---- VAE workspaces
   ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te, v_split, v_pad2;
+  ltx::DevBuf v_tile_lat, v_tile_noise, v_tile_frames;   // temporally tiled decode: one gathered chunk and its frames
+  int vae_no_clip = 0;                                    // conv_out stores (x+1)/2 unclipped (tiles are clipped after blending)
   ltx::DevBuf av_in[8];   // host-API staging of the dual model's inputs / outputs
   ltx::DevBuf u_part, u_ab, u_stats, u_in, u_out, u_ref;   // encoder / upscaler / AdaIN scratch and host-API staging
 };
@@ -293,6 +295,10 @@ void dit_forward_f32(ltx_ctx* c, const void* latent, int latent_dtype, const voi
                      int W, const ltx_dit_flags* flags, float* out_velocity_dev);
 // vae.cu
 void vae_finalize(ltx_ctx* c);
+int vae_tiled_frames(int Fp, int tile_size, int overlap);
+// returns the number of frames written
+int vae_decode_tiled_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
+                         int causal, int tile_size, int tile_overlap, float* frames_dev);
 void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
                     int causal, float* frames_dev);
 ConvW vae_pack_conv_keys(ltx_ctx* c, const std::string& wkey, const std::string& bkey, int64_t cout, int64_t cin,

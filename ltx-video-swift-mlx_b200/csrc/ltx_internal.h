@@ -230,6 +230,7 @@ struct ConvEpi {
   const float* next_scale = nullptr;
   const float* next_shift = nullptr;
   int next_tshift = 1;
+  int no_clip = 0;          // mode 2: store (x+1)/2 unclipped (temporal tiles are blended before the clip)
 };
 // x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [ntaps][Cout][Cin]; 3x3x3 cross-correlation (ntaps = 27) or a
 // per-frame 3x3 one (ntaps = 9: only the dt = 1 taps, the upscaler's Conv2d).

@@ -35,6 +35,28 @@ __global__ void add_vec_kernel(float* __restrict__ out, const float* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b[i];
 }
+// temporal tiling (V/VideoDecoder.swift:560-585): the first `po` frames of the next tile are cross-faded into the last `po`
+// frames of the result, weight j / po on the next tile
+__global__ void tile_blend_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t frame_elems, int po) {
+  const int64_t n4 = frame_elems * po / 4, fe4 = frame_elems / 4;
+  const float inv = 1.0f / static_cast<float>(po);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float w = static_cast<float>(i / fe4) * inv;
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x = a.x * (1.f - w) + b.x * w; a.y = a.y * (1.f - w) + b.y * w;
+    a.z = a.z * (1.f - w) + b.z * w; a.w = a.w * (1.f - w) + b.w * w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+__global__ void clip01_kernel(float* __restrict__ x, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(x)[i];
+    a.x = fminf(fmaxf(a.x, 0.f), 1.f); a.y = fminf(fmaxf(a.y, 0.f), 1.f);
+    a.z = fminf(fmaxf(a.z, 0.f), 1.f); a.w = fminf(fmaxf(a.w, 0.f), 1.f);
+    reinterpret_cast<float4*>(x)[i] = a;
+  }
+}
 
 }  // namespace
 
@@ -105,6 +127,7 @@ void vae_conv(ltx_ctx* c, const float* x, int prep_mode, const float* a, const f
   }
   ConvEpi e;
   e.mode = epi_mode; e.out = out; e.bias = w.b; e.resid = resid; e.Cin = w.cin; e.t_shift = t_shift;
+  e.no_clip = c->vae_no_clip;
   ProfScope ps(c, PROF_CONV, 2.0 * w.taps * w.cin * w.cout * vox,
                vox * (w.cin * 2.0 + w.cout * 4.0) + static_cast<double>(w.taps) * w.cin * w.cout * 2.0);
   // scratch for the tap-split of tile-starved convs (three partial-sum slabs)
@@ -401,6 +424,86 @@ void vae_decode_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp,
       dist_broadcast(c, frames_dev + static_cast<size_t>(o0) * frame_elems, static_cast<size_t>(o1 - o0) * frame_elems * 4, r);
     }
   }
+}
+
+// decodeWithTemporalTiling (V/VideoDecoder.swift:517-602): overlapping chunks of `tile_size` latent frames (stride
+// tile_size - overlap) are decoded independently and their 8 * overlap boundary frames cross-faded; the result is clipped
+// afterwards.  The chunk decodes store (x + 1) / 2 unclipped -- the blend is linear, so blending those equals blending x.
+// Returns the number of frames written (the reference's chunk arithmetic, not 8 (F' - 1) + 1 in general).
+int vae_tiled_frames(int Fp, int tile_size, int overlap) {
+  if (tile_size <= 0 || Fp <= tile_size) return 8 * (Fp - 1) + 1;
+  const int stride = tile_size - overlap, po = 8 * overlap;
+  int total = 0;
+  for (int start = 0;; start += stride) {
+    const int end = std::min(start + tile_size, Fp), nf = 8 * (end - start - 1) + 1;
+    if (total == 0) total = nf;
+    else total += (po > 0 && po < total && po < nf) ? nf - po : nf;
+    if (end >= Fp) break;
+  }
+  return total;
+}
+
+int vae_decode_tiled_dev(ltx_ctx* c, const float* latent_dev, int Fp, int Hp, int Wp, float timestep, const float* noise_dev,
+                         int causal, int tile_size, int overlap, float* frames_dev) {
+  LTX_CHECK(latent_dev && frames_dev && Fp > 0 && Hp > 1 && Wp > 1, LTX_ERR_INVALID_ARGUMENT, "bad vae_decode arguments");
+  if (tile_size <= 0 || Fp <= tile_size) {   // decodeVideo's single-pass branch (:482, 496)
+    vae_decode_dev(c, latent_dev, Fp, Hp, Wp, timestep, noise_dev, causal, frames_dev);
+    return 8 * (Fp - 1) + 1;
+  }
+  LTX_CHECK(overlap >= 0 && overlap < tile_size, LTX_ERR_INVALID_ARGUMENT, "temporal tile overlap must be in [0, tile size)");
+  const bool timed = timestep >= 0.f;
+  LTX_CHECK(!timed || noise_dev != nullptr, LTX_ERR_INVALID_ARGUMENT, "decode_noise is required when timestep >= 0");
+  const int C0 = c->cfg.vae_latent_channels, stride = tile_size - overlap, po = 8 * overlap;
+  const size_t hw = static_cast<size_t>(Hp) * Wp, fe = static_cast<size_t>(32 * Hp) * (32 * Wp) * 3;
+  cudaStream_t st = c->stream;
+  c->v_tile_lat.reserve(static_cast<size_t>(C0) * tile_size * hw * 4);
+  if (timed) c->v_tile_noise.reserve(static_cast<size_t>(C0) * tile_size * hw * 4);
+  c->v_tile_frames.reserve(static_cast<size_t>(8 * (tile_size - 1) + 1) * fe * 4);
+  struct NoClip {   // the chunk decodes leave the clip to the end; restored on every exit path
+    ltx_ctx* c;
+    explicit NoClip(ltx_ctx* cc) : c(cc) { c->vae_no_clip = 1; }
+    ~NoClip() { c->vae_no_clip = 0; }
+  } guard(c);
+  auto grid_for = [](int64_t n4) { return static_cast<int>(std::min<int64_t>((n4 + 255) / 256, 148 * 16)); };
+  int total = 0;
+  for (int start = 0;; start += stride) {
+    const int end = std::min(start + tile_size, Fp), Fc = end - start, nf = 8 * (Fc - 1) + 1;
+    // gather frames [start, end) of every channel: [C, F', H'W'] -> [C, Fc, H'W']
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * C0 * Fc * hw * (timed ? 2 : 1), timed ? 2 : 1);
+      LTX_CUDA(cudaMemcpy2DAsync(c->v_tile_lat.ptr, Fc * hw * 4, latent_dev + start * hw, static_cast<size_t>(Fp) * hw * 4, Fc * hw * 4,
+                                 C0, cudaMemcpyDeviceToDevice, st));
+      if (timed)
+        LTX_CUDA(cudaMemcpy2DAsync(c->v_tile_noise.ptr, Fc * hw * 4, noise_dev + start * hw, static_cast<size_t>(Fp) * hw * 4,
+                                   Fc * hw * 4, C0, cudaMemcpyDeviceToDevice, st));
+    }
+    float* dst = total == 0 ? frames_dev : c->v_tile_frames.as<float>();
+    vae_decode_dev(c, c->v_tile_lat.as<float>(), Fc, Hp, Wp, timestep, timed ? c->v_tile_noise.as<float>() : nullptr, causal, dst);
+    if (total == 0) {
+      total = nf;
+    } else if (po > 0 && po < total && po < nf) {
+      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * fe * (3.0 * po + 2.0 * (nf - po)), 2);
+      tile_blend_kernel<<<grid_for(static_cast<int64_t>(fe) * po / 4), 256, 0, st>>>(frames_dev + static_cast<size_t>(total - po) * fe,
+                                                                                   dst, static_cast<int64_t>(fe), po);
+      LTX_CUDA(cudaGetLastError());
+      LTX_CUDA(cudaMemcpyAsync(frames_dev + static_cast<size_t>(total) * fe, dst + static_cast<size_t>(po) * fe,
+                               static_cast<size_t>(nf - po) * fe * 4, cudaMemcpyDeviceToDevice, st));
+      total += nf - po;
+    } else {
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * fe * nf);
+      LTX_CUDA(cudaMemcpyAsync(frames_dev + static_cast<size_t>(total) * fe, dst, static_cast<size_t>(nf) * fe * 4,
+                               cudaMemcpyDeviceToDevice, st));
+      total += nf;
+    }
+    if (end >= Fp) break;
+  }
+  {
+    const int64_t n4 = static_cast<int64_t>(total) * fe / 4;
+    ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * fe * total);
+    clip01_kernel<<<grid_for(n4), 256, 0, st>>>(frames_dev, n4);
+    LTX_CUDA(cudaGetLastError());
+  }
+  return total;
 }
 
 }  // namespace ltx

@@ -5,7 +5,6 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import LtxError
 from .context import LtxContext
 
 
@@ -21,12 +20,13 @@ class VideoDecoder:
 def decode_video(latent, decoder: VideoDecoder, timestep: Optional[float] = None, temporal_tile_size: int = 0,
                  temporal_tile_overlap: int = 1, decode_noise=None) -> np.ndarray:
     """latent [1,128,F',H',W'] or [128,F',H',W'] fp32 -> frames [F,H,W,3] fp32 in [0,1].
-    The reference's temporal tiling (:517-602) is an approximation that is off by default (vaeTemporalTileSize 0,
-    Configuration/MemoryOptimizationConfig.swift:78-84); only the exact untiled decode is provided."""
+    temporal_tile_size > 0 with more latent frames than one tile takes the reference's overlap-blend tiling (:482-494,
+    517-602; off by default there: vaeTemporalTileSize 0, Configuration/MemoryOptimizationConfig.swift:78-84) -- an
+    approximation kept for drop-in behaviour; on B200 the exact single pass (or the exact multi-GPU temporal sharding) fits."""
     lat = np.asarray(latent, dtype=np.float32)
     frames_lat = lat.shape[-3]
     if temporal_tile_size > 0 and frames_lat > temporal_tile_size:
-        raise LtxError(5, "temporal tiling (overlap-blend approximation) is not implemented; decode untiled")
+        return decoder.ctx.vae_decode_tiled(lat, temporal_tile_size, temporal_tile_overlap, timestep, decode_noise, decoder.causal)
     return decoder.ctx.vae_decode(lat, timestep, decode_noise, decoder.causal)
 
 

@@ -864,13 +864,51 @@ def vae_decode(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float] = No
 
 
 def decode_video(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float] = None,
-                 decode_noise: Optional[Tensor] = None, dtype=torch.float32) -> Tensor:
-    """V/VideoDecoder.swift:466-508 (untiled): frames [F,H,W,3] in [0,1]."""
+                 decode_noise: Optional[Tensor] = None, dtype=torch.float32, temporal_tile_size: int = 0,
+                 temporal_tile_overlap: int = 1) -> Tensor:
+    """V/VideoDecoder.swift:466-508: frames [F,H,W,3] in [0,1]; temporal tiling (:482-494) when the latent has more frames
+    than one tile."""
     if latent.ndim == 4:
         latent = latent.unsqueeze(0)
-    x = vae_decode(w, cfg, latent, timestep, decode_noise, dtype)
+    if decode_noise is not None and decode_noise.ndim == 4:
+        decode_noise = decode_noise.unsqueeze(0)
+    if temporal_tile_size > 0 and latent.shape[2] > temporal_tile_size:
+        x = decode_with_temporal_tiling(w, cfg, latent, timestep, decode_noise, temporal_tile_size, temporal_tile_overlap, dtype)
+    else:
+        x = vae_decode(w, cfg, latent, timestep, decode_noise, dtype)
     x = torch.clamp((x + 1.0) / 2.0, 0.0, 1.0)
     return x[0].permute(1, 2, 3, 0).contiguous()
+
+
+def decode_with_temporal_tiling(w, cfg: VAEConfig, latent: Tensor, timestep: Optional[float], decode_noise: Optional[Tensor],
+                                tile_size: int, overlap: int, dtype=torch.float32) -> Tensor:
+    """decodeWithTemporalTiling (V/VideoDecoder.swift:517-602): chunks [start, start + tile) at stride tile - overlap decoded
+    independently (:534-551); each next chunk's first 8 * overlap frames are cross-faded into the result's last ones with
+    weights j / (8 * overlap) when both sides are longer than the overlap (:572-585), else concatenated (:586-589).  Raw
+    decoder output [1,3,F,H,W] (the caller normalises and clips, :595-599).  The reference draws fresh decode noise per chunk;
+    here each chunk takes its slice of the caller's noise (noise is data)."""
+    total = latent.shape[2]
+    stride = tile_size - overlap
+    po = 8 * overlap
+    chunks = []
+    start = 0
+    while start < total:
+        end = min(start + tile_size, total)
+        nz = None if decode_noise is None else decode_noise[:, :, start:end]
+        chunks.append(vae_decode(w, cfg, latent[:, :, start:end], timestep, nz, dtype))
+        if end >= total:
+            break
+        start += stride
+    result = chunks[0]
+    for nxt in chunks[1:]:
+        rf, nf = result.shape[2], nxt.shape[2]
+        if 0 < po < rf and po < nf:
+            wts = (torch.arange(po, dtype=torch.float32) / float(po)).to(dtype).view(1, 1, po, 1, 1)
+            blended = result[:, :, rf - po:] * (1 - wts) + nxt[:, :, :po] * wts
+            result = torch.cat([result[:, :, :rf - po], blended, nxt[:, :, po:]], dim=2)
+        else:
+            result = torch.cat([result, nxt], dim=2)
+    return result
 
 
 # ----------------------------------------------------------------------------------------------

@@ -252,3 +252,20 @@ def test_av_oracle_per_token_sigmas_and_image_conditioned_loop():
     inj = [torch.randn(1, 128, 1, 2, 3, generator=gen) for _ in range(3)]
     lv2, _ = O.av_denoise_loop(w, cfg, av, vn, an, vc, ac, None, sig, image_latent=img, inject_noise=inj, image_cond_noise_scale=0.1)
     assert torch.allclose(lv2[:, :, 0:1], img + 0.1 * inj[2] * 0.3 * 0.3, atol=1e-6)
+
+
+def test_vae_temporal_tiling_oracle():
+    """decodeWithTemporalTiling (V/VideoDecoder.swift:517-602): frame count follows the chunk arithmetic, frames outside every
+    cross-fade equal the chunk's own decode, the first cross-faded frame (weight 0) is still the earlier chunk's."""
+    cfg = O.VAEConfig(base_channels=64, blocks_per_stage=1)
+    w = O.make_vae_weights(cfg, 3)
+    z = torch.randn(1, 128, 5, 2, 2, generator=torch.Generator().manual_seed(4))
+    tiled = O.decode_video(w, cfg, z, temporal_tile_size=3, temporal_tile_overlap=1)      # chunks [0,3) and [2,5): 17 + 17 - 8
+    assert tiled.shape == (26, 64, 64, 3)
+    a = O.decode_video(w, cfg, z[:, :, 0:3])
+    b = O.decode_video(w, cfg, z[:, :, 2:5])
+    assert torch.allclose(tiled[:10], a[:10], atol=1e-6) and torch.allclose(tiled[17:], b[8:], atol=1e-6)
+    mid = torch.clamp((a[13] * 0.5 + b[4] * 0.5), 0, 1)                                   # frame 9 + 4: weight 4 / 8
+    inside = (a[13] > 1e-3) & (a[13] < 1 - 1e-3) & (b[4] > 1e-3) & (b[4] < 1 - 1e-3)
+    assert torch.allclose(tiled[13][inside], mid[inside], atol=1e-6)
+    assert torch.equal(O.decode_video(w, cfg, z, temporal_tile_size=8), O.decode_video(w, cfg, z))   # fits one tile
