@@ -219,6 +219,24 @@ int ltx_denoise_get_latent(ltx_ctx* ctx, float* latent_out);
 /* device pointer of the resident latent (for chaining into ltx_vae_decode_dev). */
 int ltx_denoise_latent_dev(ltx_ctx* ctx, float** latent_dev);
 
+/* The step loop of generateVideoWithAudio (Pipeline/LTXPipeline.swift:1255-1404), device resident: both latents, the text K / V
+ * of both streams and the velocities stay in HBM; one call per step.
+ *   begin : video_noise [in_channels, F, H, W], audio_noise [Ta, audio_in_channels] (the packed audio latent) fp32 host; both
+ *           are scaled by sigma0 (:1255-1259); contexts [S, caption_channels]; one mask serves both streams (textMask); the
+ *           negative contexts (a pair, or both NULL) enable CFG.
+ *   step  : per pass one LTX2Transformer forward (two with CFG, :1300-1362); video = applyCFG (+ rescale) + scheduler.step,
+ *           audio = applyCFG + latent += (sigma_next - sigma) * velocity (:1402).  Reads sigma, sigma_next, cfg_scale,
+ *           rescale_phi and i2v_frame0_conditioned of ltx_step_params (per-token video timesteps sigma * (1 - mask) and an
+ *           untouched frame 0, :1293-1298, 1381-1391; set the frame with ltx_denoise_set_frame0); STG / GE are not part of
+ *           this loop (LTX_ERR_UNSUPPORTED).
+ *   get   : either output may be NULL.  ltx_denoise_latent_dev / ltx_denoise_set_frame0 act on the video latent. */
+int ltx_av_denoise_begin(ltx_ctx* ctx, const float* video_noise, const float* audio_noise, int F, int H, int W, int Ta,
+                         float sigma0, const void* video_context, const void* audio_context, ltx_dtype context_dtype,
+                         const int32_t* mask, const void* neg_video_context, const void* neg_audio_context,
+                         const int32_t* neg_mask, int S);
+int ltx_av_denoise_step(ltx_ctx* ctx, const ltx_step_params* p);
+int ltx_av_denoise_get_latents(ltx_ctx* ctx, float* video_latent_out, float* audio_latent_out);
+
 /* decodeVideo(latent:decoder:timestep:temporalTileSize:temporalTileOverlap:) untiled
  * (Models/VAE/VideoDecoder.swift:466-508 -> VideoDecoder.callAsFunction :358-449).
  *   latent [128, F', H', W'] fp32 ; timestep < 0 = none ; decode_noise (same shape) required when timestep >= 0;

@@ -70,6 +70,9 @@ SIGNATURES = {
     "ltx_denoise_step": (_I, [_P, C.POINTER(LtxStepParams)]),
     "ltx_denoise_get_latent": (_I, [_P, _P]),
     "ltx_denoise_latent_dev": (_I, [_P, C.POINTER(_P)]),
+    "ltx_av_denoise_begin": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P, _P, _P, _I]),
+    "ltx_av_denoise_step": (_I, [_P, C.POINTER(LtxStepParams)]),
+    "ltx_av_denoise_get_latents": (_I, [_P, _P, _P]),
     "ltx_vae_decode": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_decode_dev": (_I, [_P, _P, _I, _I, _I, _F, _P, _I, _P]),
     "ltx_vae_tiled_frames": (_I, [_I, _I, _I]),

@@ -344,6 +344,39 @@ class LtxContext:
             p.stg_blocks[i] = int(b)
         self._check(self.lib.ltx_denoise_step(self.handle, C.byref(p)))
 
+    # ------------------------------------------------------------------ resident audio + video denoise session
+    def av_denoise_begin(self, video_noise, audio_noise, fhw, sigma0: float, video_context, audio_context, mask=None,
+                         neg_video_context=None, neg_audio_context=None, neg_mask=None):
+        """video_noise [C,F,H,W], audio_noise [Ta,Ca] fp32 (generateVideoWithAudio, Pipeline/LTXPipeline.swift:1255-1259)."""
+        vn, an = _host(video_noise, np.float32), _host(audio_noise, np.float32)
+        cc = _dtype_code(video_context)
+        assert _dtype_code(audio_context) == cc, "both contexts must have the same dtype"
+        vx, ax = _host(video_context), _host(audio_context)
+        S = vx.shape[-2]
+        mk = None if mask is None else _host(mask, np.int32)
+        nvx = None if neg_video_context is None else _host(neg_video_context)
+        nax = None if neg_audio_context is None else _host(neg_audio_context)
+        nmk = None if neg_mask is None else _host(neg_mask, np.int32)
+        F, H, W = fhw
+        Ta = an.shape[-2]
+        self._check(self.lib.ltx_av_denoise_begin(self.handle, _ptr(vn), _ptr(an), F, H, W, Ta, sigma0, _ptr(vx), _ptr(ax), cc,
+                                                  _ptr(mk), _ptr(nvx), _ptr(nax), _ptr(nmk), S))
+        self._session_shape = (self.config.in_channels, F, H, W)
+        self._av_session_audio_shape = (Ta, self.config.audio_in_channels)
+
+    def av_denoise_step(self, sigma: float, sigma_next: float, step_index: int = 0, cfg_scale: float = 1.0,
+                        rescale_phi: float = 0.0, i2v_frame0_conditioned: bool = False):
+        p = LtxStepParams()
+        p.i2v_frame0_conditioned = int(i2v_frame0_conditioned)
+        p.sigma, p.sigma_next, p.cfg_scale, p.rescale_phi, p.step_index = sigma, sigma_next, cfg_scale, rescale_phi, step_index
+        self._check(self.lib.ltx_av_denoise_step(self.handle, C.byref(p)))
+
+    def av_denoise_get_latents(self):
+        ov = np.empty(self._session_shape, dtype=np.float32)
+        oa = np.empty(self._av_session_audio_shape, dtype=np.float32)
+        self._check(self.lib.ltx_av_denoise_get_latents(self.handle, _ptr(ov), _ptr(oa)))
+        return ov, oa
+
     def denoise_get_latent(self) -> np.ndarray:
         out = np.empty(self._session_shape, dtype=np.float32)
         self._check(self.lib.ltx_denoise_get_latent(self.handle, _ptr(out)))

@@ -112,7 +112,8 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
                     &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->v_split, &c->v_pad2, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
                     &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
-                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7]};
+                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7],
+                    &c->v_tile_lat, &c->v_tile_noise, &c->v_tile_frames, &c->s_alat, &c->s_avc, &c->s_avu, &c->s_actx_pos, &c->s_actx_neg};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
   for (auto& t : c->av.text) { t.k.release(); t.vt.release(); t.bias.release(); }
@@ -655,6 +656,118 @@ int ltx_denoise_latent_dev(ltx_ctx* c, float** p) {
   return guarded(c, [&] {
     LTX_CHECK(p && c->s_F > 0, LTX_ERR_INVALID_ARGUMENT, "no denoise session");
     *p = c->s_latent.as<float>();
+  });
+}
+
+// ---------------------------------------------------------------- resident audio + video denoise session
+int ltx_av_denoise_begin(ltx_ctx* c, const float* video_noise, const float* audio_noise, int F, int H, int W, int Ta, float sigma0,
+                         const void* video_context, const void* audio_context, ltx_dtype context_dtype, const int32_t* mask,
+                         const void* neg_video_context, const void* neg_audio_context, const int32_t* neg_mask, int S) {
+  return guarded(c, [&] {
+    LTX_CHECK(video_noise && audio_noise && video_context && audio_context && F > 0 && H > 0 && W > 0 && Ta > 0 && S > 0,
+              LTX_ERR_INVALID_ARGUMENT, "bad av_denoise_begin arguments");
+    LTX_CHECK((neg_video_context == nullptr) == (neg_audio_context == nullptr), LTX_ERR_INVALID_ARGUMENT,
+              "the negative contexts come as a pair");
+    LTX_CHECK(c->av.ready, LTX_ERR_WEIGHTS, "dual audio/video weights not loaded / finalized");
+    const ltx_config& g = c->cfg;
+    LTX_CHECK(g.in_channels == g.out_channels, LTX_ERR_INVALID_CONFIGURATION, "in/out channels must match");
+    const size_t n = static_cast<size_t>(g.in_channels) * F * H * W, na = static_cast<size_t>(Ta) * c->av.Cin;
+    session_resize(c, F, H, W);
+    c->s_S = S; c->s_Ta = Ta;
+    c->s_ctx_dtype = context_dtype;
+    h2d(c, c->s_latent, video_noise, n * 4);
+    h2d(c, c->s_alat, audio_noise, na * 4);
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * (n + na), 2);
+      launch_scale_f32(c->s_latent.as<float>(), sigma0, static_cast<int64_t>(n), c->stream);   // P/LTXPipeline.swift:1255-1259
+      launch_scale_f32(c->s_alat.as<float>(), sigma0, static_cast<int64_t>(na), c->stream);
+    }
+    const size_t cbytes = static_cast<size_t>(S) * g.caption_channels * dsize(context_dtype);
+    h2d(c, c->s_ctx_pos, video_context, cbytes);
+    h2d(c, c->s_actx_pos, audio_context, cbytes);
+    c->s_has_mask_pos = mask != nullptr;
+    if (mask) h2d(c, c->s_mask_pos, mask, static_cast<size_t>(S) * 4);
+    c->s_has_neg = neg_video_context != nullptr;
+    if (c->s_has_neg) {
+      h2d(c, c->s_ctx_neg, neg_video_context, cbytes);
+      h2d(c, c->s_actx_neg, neg_audio_context, cbytes);
+      c->s_has_mask_neg = neg_mask != nullptr;
+      if (neg_mask) h2d(c, c->s_mask_neg, neg_mask, static_cast<size_t>(S) * 4);
+    }
+    c->s_avc.reserve(na * 4);
+    c->s_avu.reserve(na * 4);
+    c->scratch.reserve(64 * sizeof(double));
+    c->s_serial += 2;
+    dit_clear_caches(c);
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ltx_av_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
+  return guarded(c, [&] {
+    LTX_CHECK(p != nullptr && c->s_F > 0 && c->s_Ta > 0, LTX_ERR_INVALID_ARGUMENT, "av_denoise_step before av_denoise_begin");
+    LTX_CHECK(p->sigma > 0.f, LTX_ERR_INVALID_ARGUMENT, "sigma must be > 0");
+    LTX_CHECK(p->stg_scale == 0.f && p->ge_gamma == 0.f, LTX_ERR_UNSUPPORTED,
+              "the audio + video loop has no STG / GE terms (Pipeline/LTXPipeline.swift:1300-1404)");
+    const ltx_config& g = c->cfg;
+    const int C = g.in_channels, F = c->s_F, H = c->s_H, W = c->s_W, S = c->s_S, Ta = c->s_Ta;
+    const int T = F * H * W;
+    const size_t n = static_cast<size_t>(C) * T, na = static_cast<size_t>(Ta) * c->av.Cin;
+    cudaStream_t st = c->stream;
+    {
+      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * n);
+      launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
+    }
+    LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
+    // image-to-video (:1293-1298): video timesteps sigma * (1 - conditioningMask) per token; the audio stream keeps sigma
+    const bool i2v = p->i2v_frame0_conditioned != 0;
+    const float* ts_dev = c->s_sigma.as<float>();
+    if (i2v) {
+      c->s_ts.reserve(static_cast<size_t>(T) * 4);
+      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * T);
+      launch_fill_token_timesteps(c->s_ts.as<float>(), T, T, H * W, c->s_sigma.as<float>(), st);
+      ts_dev = c->s_ts.as<float>();
+    }
+    const uint64_t key_pos = 0x6000000000000000ull + c->s_serial, key_neg = key_pos + 1;
+    auto pass = [&](bool neg, float* v_lat, float* a_vel) {
+      const int32_t* mk = neg ? (c->s_has_mask_neg ? c->s_mask_neg.as<int32_t>() : nullptr)
+                              : (c->s_has_mask_pos ? c->s_mask_pos.as<int32_t>() : nullptr);
+      dit_av_forward_dev(c, c->s_tok.ptr, LTX_BF16, c->s_alat.ptr, LTX_F32, neg ? c->s_ctx_neg.ptr : c->s_ctx_pos.ptr,
+                         neg ? c->s_actx_neg.ptr : c->s_actx_pos.ptr, c->s_ctx_dtype, ts_dev, i2v ? 1 : 0, c->s_sigma.as<float>(), mk,
+                         mk, 1, T, Ta, S, F, H, W, neg ? key_neg : key_pos, c->vel.as<float>(), a_vel);
+      ProfScope ps(c, PROF_OTHER, 0.0, 8.0 * n);
+      launch_unpatchify(c->vel.as<float>(), v_lat, C, T, st);
+    };
+    const bool use_cfg = p->cfg_scale > 1.0f && c->s_has_neg;
+    pass(false, c->s_vc.as<float>(), c->s_avc.as<float>());
+    if (use_cfg) pass(true, c->s_vu.as<float>(), c->s_avu.as<float>());
+    // video: applyCFG (+ rescale) + scheduler.step, frame 0 untouched in the image-to-video mode (:1364-1391)
+    GuidedEulerArgs a;
+    a.latent = c->s_latent.as<float>(); a.v_cond = c->s_vc.as<float>();
+    a.v_uncond = use_cfg ? c->s_vu.as<float>() : nullptr;
+    a.v_stg = nullptr; a.v_prev = nullptr; a.use_prev = 0;
+    a.v_out = nullptr; a.n = n; a.cfg = use_cfg ? p->cfg_scale : 1.0f; a.phi = use_cfg ? p->rescale_phi : 0.0f; a.stg = 0.f;
+    a.ge_gamma = 0.f; a.sigma = p->sigma; a.sigma_next = p->sigma_next; a.scratch = c->scratch.as<double>();
+    if (i2v) { a.period = static_cast<size_t>(T); a.frozen = static_cast<size_t>(H) * W; }
+    ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * n * (3.0 + (use_cfg ? 1.0 : 0.0)) + 4.0 * na * (3.0 + (use_cfg ? 1.0 : 0.0)),
+                 ((use_cfg && p->rescale_phi > 0.f) ? 2 : 1) + 1);
+    launch_guided_euler(a, st);
+    // audio: applyCFG + a += (sigma' - sigma) v (:1402)
+    const float dt = static_cast<float>(static_cast<double>(p->sigma_next) - static_cast<double>(p->sigma));
+    launch_audio_cfg_euler(c->s_alat.as<float>(), c->s_avc.as<float>(), use_cfg ? c->s_avu.as<float>() : nullptr, p->cfg_scale, dt,
+                           static_cast<int64_t>(na), st);
+  });
+}
+
+int ltx_av_denoise_get_latents(ltx_ctx* c, float* video_out, float* audio_out) {
+  return guarded(c, [&] {
+    LTX_CHECK(c->s_F > 0 && c->s_Ta > 0, LTX_ERR_INVALID_ARGUMENT, "no audio + video denoise session");
+    const size_t n = static_cast<size_t>(c->cfg.in_channels) * c->s_F * c->s_H * c->s_W;
+    if (video_out) LTX_CUDA(cudaMemcpyAsync(video_out, c->s_latent.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (audio_out)
+      LTX_CUDA(cudaMemcpyAsync(audio_out, c->s_alat.ptr, static_cast<size_t>(c->s_Ta) * c->av.Cin * 4, cudaMemcpyDeviceToHost,
+                               c->stream));
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
 

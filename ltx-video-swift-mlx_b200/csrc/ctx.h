@@ -235,6 +235,9 @@ struct ltx_ctx {
   bool s_has_neg = false, s_has_mask_pos = false, s_has_mask_neg = false;
   int s_ctx_dtype = LTX_BF16;
   uint64_t s_serial = 0;
+  // audio + video session (ltx_av_denoise_*): audio latent / velocities [Ta, Ca] fp32, audio contexts
+  ltx::DevBuf s_alat, s_avc, s_avu, s_actx_pos, s_actx_neg;
+  int s_Ta = 0;
 
   // ---- VAE workspaces
   ltx::DevBuf v_a, v_b, v_h, v_pad, v_lat, v_noise, v_frames, v_mix, v_te, v_split, v_pad2;

@@ -692,6 +692,24 @@ __global__ void scale_f32_kernel(float* __restrict__ x, float a, int64_t n) {
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     x[i] *= a;
 }
+// audio latent of the audio + video loop: applyCFG on the audio velocity, then a += dt * v (P/LTXPipeline.swift:1340-1362,
+// 1402); separate roundings (no FMA contraction) so the result equals the reference's op-by-op fp32 arithmetic
+__global__ void audio_cfg_euler_kernel(float* __restrict__ lat, const float* __restrict__ vc, const float* __restrict__ vu,
+                                       float cfg_m1, float dt, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = vc[i];
+    if (vu) v = __fadd_rn(v, __fmul_rn(cfg_m1, __fsub_rn(v, vu[i])));
+    lat[i] = __fadd_rn(lat[i], __fmul_rn(dt, v));
+  }
+}
+void launch_audio_cfg_euler(float* lat, const float* v_cond, const float* v_uncond, float cfg_scale, float dt, int64_t n,
+                            cudaStream_t s) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  audio_cfg_euler_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(lat, v_cond, v_uncond, cfg_scale - 1.0f, dt, n);
+  LTX_CUDA(cudaGetLastError());
+}
 void launch_mask_to_bias(const int32_t* mask, float* bias, int n, cudaStream_t s) {
   mask_to_bias_kernel<<<(n + 255) / 256, 256, 0, s>>>(mask, bias, n);
   LTX_CUDA(cudaGetLastError());

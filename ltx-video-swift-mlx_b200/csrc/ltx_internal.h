@@ -184,6 +184,9 @@ void launch_gemv(const bf16* W, const float* bias, const float* x, float* y, int
                  cudaStream_t s);
 void launch_mask_to_bias(const int32_t* mask, float* bias, int n, cudaStream_t s);
 void launch_scale_f32(float* x, float a, int64_t n, cudaStream_t s);
+// lat += dt * (v_cond + (cfg_scale - 1) * (v_cond - v_uncond))   (v_uncond nullable: lat += dt * v_cond)
+void launch_audio_cfg_euler(float* lat, const float* v_cond, const float* v_uncond, float cfg_scale, float dt, int64_t n,
+                            cudaStream_t s);
 void launch_sincos_embed(const float* sigma, float mult, float* out, int M, int dim, cudaStream_t s, bf16* out_bf16 = nullptr);
 // out_bf16 = silu(in) (fp32 in)
 void launch_silu_cast(const float* in, bf16* out, int64_t n, cudaStream_t s);

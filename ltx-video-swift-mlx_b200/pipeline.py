@@ -119,3 +119,26 @@ def denoise_av_host_seam(ctx: LtxContext, video_noise: np.ndarray, audio_noise: 
             v_lat[:, :, 0:1] = frame0
         a_lat = a_lat + np.float32(sn - sg) * va                                               # :1402
     return v_lat, a_lat
+
+
+def denoise_av_resident(ctx: LtxContext, video_noise: np.ndarray, audio_noise: np.ndarray, video_context, audio_context, mask,
+                        sigmas: Sequence[float], neg_video_context=None, neg_audio_context=None, neg_mask=None,
+                        cfg_scale: float = 1.0, guidance_rescale: float = 0.0, image_latent: Optional[np.ndarray] = None,
+                        inject_noise: Optional[Sequence[np.ndarray]] = None, image_cond_noise_scale: float = 0.0):
+    """The same loop on the device-resident session (ltx_av_denoise_begin / _step): latents, text caches and velocities stay
+    in HBM, the only per-step host traffic is the optional re-noised conditioning frame.  Returns (video latent [1,C,F,H,W],
+    audio latent [1,Ta,Ca])."""
+    _, C, F, H, W = video_noise.shape
+    ctx.av_denoise_begin(video_noise[0], audio_noise[0], (F, H, W), float(sigmas[0]), video_context, audio_context, mask,
+                         neg_video_context, neg_audio_context, neg_mask)
+    i2v = image_latent is not None
+    if i2v:
+        ctx.denoise_set_frame0(np.asarray(image_latent, dtype=np.float32))
+    for step in range(len(sigmas) - 1):
+        sg, sn = float(sigmas[step]), float(sigmas[step + 1])
+        if i2v and image_cond_noise_scale > 0 and sg > 0 and inject_noise is not None:
+            ctx.denoise_set_frame0(np.asarray(image_latent, dtype=np.float32) + np.float32(image_cond_noise_scale)
+                                   * np.asarray(inject_noise[step], dtype=np.float32) * np.float32(sg * sg))
+        ctx.av_denoise_step(sg, sn, step, cfg_scale, guidance_rescale, i2v_frame0_conditioned=i2v)
+    v, a = ctx.av_denoise_get_latents()
+    return v[None], a[None]

@@ -206,3 +206,48 @@ def test_av_image_conditioned_denoise_loop_matches_oracle():
     expect0 = img + 0.15 * inj[-1] * (sg_last * sg_last) if sg_last > 0 else img
     assert np.allclose(ov[:, :, 0:1], expect0.numpy(), atol=1e-6)
     ctx.close()
+
+
+@pytest.mark.parametrize("i2v,cfg", [(False, 3.0), (True, 1.0), (True, 2.5)])
+def test_av_resident_session_matches_host_seam_loop_and_oracle(i2v, cfg):
+    """ltx_av_denoise_begin / _step (latents resident in HBM) against the host-seam loop -- the same kernels behind both, so the
+    video latent is bit-identical and the audio latent equal to fp32 rounding of (sigma' - sigma) -- and against the oracle."""
+    from ltx_video_swift_mlx_b200.pipeline import denoise_av_host_seam, denoise_av_resident
+    from ltx_video_swift_mlx_b200._lib import LtxError
+    ocfg, av, w, ctx = _setup(2, 2, 2, seed=79)
+    fhw, Ta, S = (3, 4, 6), 11, 40
+    g = torch.Generator().manual_seed(8)
+    vn, an = torch.randn(1, 128, *fhw, generator=g), torch.randn(1, Ta, 128, generator=g)
+    img = torch.randn(1, 128, 1, fhw[1], fhw[2], generator=g) if i2v else None
+
+    def text():
+        t = torch.randn(1, S, 192, generator=g)
+        return (t / t.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
+    vc, ac, nvc, nac = text(), text(), text(), text()
+    mask = torch.ones(1, S, dtype=torch.int32)
+    mask[:, :3] = 0
+    use_neg = cfg > 1.0
+    sig = O.set_timesteps(8, True, 72)[3:7]
+    inj = [torch.randn(1, 128, 1, fhw[1], fhw[2], generator=g) for _ in range(len(sig) - 1)] if i2v else None
+    kw = dict(cfg_scale=cfg, guidance_rescale=0.4 if use_neg else 0.0,
+              image_latent=None if img is None else img.numpy(), inject_noise=None if inj is None else [t.numpy() for t in inj],
+              image_cond_noise_scale=0.15 if i2v else 0.0)
+    negs = (nvc, nac, mask) if use_neg else (None, None, None)
+    hv, ha = denoise_av_host_seam(ctx, vn.numpy(), an.numpy(), vc, ac, mask, sig, *negs, **kw)
+    rv, ra = denoise_av_resident(ctx, vn.numpy(), an.numpy(), vc, ac, mask, sig, *negs, **kw)
+    assert np.array_equal(rv, hv)
+    assert np.allclose(ra, ha, rtol=0, atol=1e-5)
+    ov, oa = O.av_denoise_loop(w, ocfg, av, vn, an, vc.float(), ac.float(), mask, sig, nvc.float() if use_neg else None,
+                               nac.float() if use_neg else None, mask if use_neg else None, cfg_scale=cfg,
+                               phi=0.4 if use_neg else 0.0, image_latent=img, inject_noise=inj,
+                               image_cond_noise_scale=0.15 if i2v else 0.0)
+    assert rel_l2(rv, ov) <= 2e-2 and rel_l2(ra, oa) <= 2e-2, (rel_l2(rv, ov), rel_l2(ra, oa))
+    with pytest.raises(LtxError) as e:                      # no STG / GE in this loop: refused, not ignored
+        p = ctx.lib  # noqa: F841
+        from ltx_video_swift_mlx_b200._lib import LtxStepParams
+        import ctypes as C
+        sp = LtxStepParams()
+        sp.sigma, sp.sigma_next, sp.cfg_scale, sp.stg_scale = 0.5, 0.4, 1.0, 0.5
+        ctx._check(ctx.lib.ltx_av_denoise_step(ctx.handle, C.byref(sp)))
+    assert e.value.code == 5
+    ctx.close()
