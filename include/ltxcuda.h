@@ -157,7 +157,8 @@ int ltx_dit_forward_dev(ltx_ctx* ctx, const void* latent, ltx_dtype latent_dtype
  * and video->audio cross-modal attention, both feed-forwards (Models/Transformer/LTX2TransformerBlock.swift:174-297).
  *   video_latent [1, N, in_channels], audio_latent [1, Ta, audio_in_channels] (bf16 or fp32), contexts [1, S, caption_channels],
  *   one sigma per stream, masks [1, S] int32 or NULL; out_video [1, N, out_channels], out_audio [1, Ta, audio_in_channels] fp32.
- * context_key != 0 caches the text K / V of both streams.  This version: B = 1, bf16 weights, one GPU. */
+ * context_key != 0 caches the text K / V of both streams.  Weights: bf16, or int8 / int4 after ltx_finalize_weights(ctx, 8 | 4, 64)
+ * (quantize(model: ltx2, groupSize: 64, bits:), Pipeline/LTXPipeline.swift:491).  This version: B = 1, one GPU. */
 int ltx_av_forward(ltx_ctx* ctx, const void* video_latent, ltx_dtype video_dtype, const void* audio_latent, ltx_dtype audio_dtype,
                    const void* video_context, const void* audio_context, ltx_dtype context_dtype, float video_sigma,
                    float audio_sigma, const int32_t* video_mask, const int32_t* audio_mask, int N, int Ta, int S, int F, int H,

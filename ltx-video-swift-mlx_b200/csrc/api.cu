@@ -271,7 +271,7 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
       if (c->precision == 32) dit_finalize_f32(c);
       else dit_finalize(c);
       if (c->tensors.count("audio_patchify_proj.weight")) {
-        LTX_CHECK(quant_bits == 16 && c->precision == 16, LTX_ERR_UNSUPPORTED, "the dual audio/video model runs with bf16 weights only");
+        LTX_CHECK(c->precision == 16, LTX_ERR_UNSUPPORTED, "the dual audio/video model has no fp32 mode");
         dit_av_finalize(c);
       }
       if (quant_bits != 16) dit_quantize(c, quant_bits);

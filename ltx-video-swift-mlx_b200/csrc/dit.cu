@@ -355,6 +355,26 @@ void dit_quantize(ltx_ctx* c, int bits) {
     qf(b.a2.wq, D, D); qf(b.a2.wk, D, D); qf(b.a2.wv, D, D); qf(b.a2.wo, D, D);
     qf(b.w_in, FF, D); qf(b.w_out, D, FF);
   }
+  if (c->av.ready) {
+    // the dual model's Linears (quantize(model: ltx2, groupSize: 64, bits:), Pipeline/LTXPipeline.swift:491); the AdaLN-single
+    // embedders stay bf16 like the video model's timestep MLP
+    AvWeights& a = c->av;
+    const int Da = a.Da, FFa = g.ffn_mult * Da, Ca = a.Cin;
+    qf(a.w_patch, Da, Ca);
+    qf(a.w_c1, Da, g.caption_channels);
+    qf(a.w_c2, Da, Da);
+    qf(a.w_out, Ca, Da);
+    auto qattn = [&](AttnWeights& w, int qdim, int cdim, int inner) {
+      qf(w.wq, inner, qdim); qf(w.wk, inner, cdim); qf(w.wv, inner, cdim); qf(w.wo, qdim, inner);
+    };
+    for (auto& b : a.blocks) {
+      qattn(b.aa1, Da, Da, Da);
+      qattn(b.aa2, Da, Da, Da);
+      qattn(b.a2v, D, Da, Da);
+      qattn(b.v2a, Da, D, Da);
+      qf(b.w_in, FFa, Da); qf(b.w_out, Da, FFa);
+    }
+  }
   for (const void* p : to_free) release(p);
   // one bf16 panel for the large-M path of launch_gemm_q, sized for the largest weight (the FFN matrices)
   size_t max_elems = 0;

@@ -10,7 +10,8 @@
 // norm + RoPE are the two row kernels below.  Text K / V of both streams are step-invariant and cached like the video-only
 // model's.  The video sigma is one scalar, or one value per video token (the image-to-video mode feeds sigma * (1 - mask),
 // Pipeline/LTXPipeline.swift:1293-1298; every video-side embedder then runs per token, LTX2Transformer.swift:273-298).
-// Restrictions of this version: B = 1, bf16 weights (no int8 / int4), single GPU.
+// Weights: bf16, or int8 / int4 codes through the dequant-fused GEMM (quantize(model: ltx2, ...), Pipeline/LTXPipeline.swift:491).
+// Restrictions of this version: B = 1, single GPU.
 #include <algorithm>
 #include <cmath>
 
@@ -211,7 +212,14 @@ __global__ void __launch_bounds__(256) qknorm_rope_hd_kernel(bf16* x, int64_t ld
 
 // ---------------------------------------------------------------- profiled launch helpers
 void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& e) {
-  ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N));
+  auto it = c->qw.empty() ? c->qw.end() : c->qw.find(B);
+  const bool panel = it != c->qw.end() && it->second.scratch != nullptr && M >= 257;
+  ProfScope ps(c, PROF_GEMM, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K + static_cast<double>(M) * N),
+               panel ? 2 : 1);
+  if (it != c->qw.end()) {   // int8 / int4 codes (quantize(model: ltx2, ...), Pipeline/LTXPipeline.swift:491): dequant-fused kernel
+    launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream);
+    return;
+  }
   launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream);
 }
 // out_bf16[M, N] = A W^T + b
@@ -228,11 +236,21 @@ void linear_resid(ltx_ctx* c, const bf16* A, int M, int K, const bf16* W, const 
   e.rows_per_gate = gate_ld > 0 ? 1 : (M > 0 ? M : 1);   // gate_ld > 0: one gate row per token
   gemm(c, A, K, W, K, M, N, K, e);
 }
-// V^T [Nout, rows] (row pitch ld_out) = (h W^T + b)^T: the weight is the A operand, so the product lands transposed
-void linear_t(ltx_ctx* c, const bf16* W, const float* b, int Nout, int K, const bf16* hrows, int rows, bf16* out, int64_t ld_out) {
+// V^T [Nout, rows] (row pitch ld_out) = (h W^T + b)^T: the weight is the A operand, so the product lands transposed.
+// Quantised weights must be the B operand: project into `tmp` [rows, Nout], then transpose.
+void linear_t(ltx_ctx* c, const bf16* W, const float* b, int Nout, int K, const bf16* hrows, int rows, bf16* out, int64_t ld_out,
+              bf16* tmp) {
+  if (c->qw.empty() || c->qw.find(W) == c->qw.end()) {
+    GemmEpi e;
+    e.mode = EPI_BF16; e.out = out; e.ldo = ld_out; e.bias = b; e.bias_per_row = 1;
+    gemm(c, W, K, hrows, K, Nout, rows, K, e);
+    return;
+  }
   GemmEpi e;
-  e.mode = EPI_BF16; e.out = out; e.ldo = ld_out; e.bias = b; e.bias_per_row = 1;
-  gemm(c, W, K, hrows, K, Nout, rows, K, e);
+  e.mode = EPI_BF16; e.out = tmp; e.ldo = Nout; e.bias = b;
+  gemm(c, hrows, K, W, K, rows, Nout, K, e);
+  ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * rows * Nout);
+  launch_transpose_bf16(tmp, Nout, rows, Nout, out, ld_out, c->stream);
 }
 void attention(ltx_ctx* c, const bf16* Q, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldv, const float* bias, bf16* O, int H,
                int hd, int Nq, int Nk) {
@@ -366,7 +384,8 @@ int64_t round_up8(int64_t v) { return (v + 7) / 8 * 8; }
 
 void dit_av_finalize(ltx_ctx* c) {
   const ltx_config& g = c->cfg;
-  LTX_CHECK(c->dit_ready && c->precision == 16, LTX_ERR_WEIGHTS, "the dual model needs the finalized bf16 video weights");
+  LTX_CHECK(c->dit_ready && c->precision == 16 && c->qw.empty(), LTX_ERR_WEIGHTS,
+            "the dual model is finalized on the bf16 video weights (quantisation follows)");
   AvWeights& a = c->av;
   const int64_t D = static_cast<int64_t>(g.num_heads) * g.head_dim;
   const int Ha = g.audio_num_heads > 0 ? g.audio_num_heads : 32, hd = g.audio_head_dim > 0 ? g.audio_head_dim : 64;
@@ -414,7 +433,6 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
                         float* out_v_dev, float* out_a_dev) {
   AvWeights& av = c->av;
   LTX_CHECK(av.ready, LTX_ERR_WEIGHTS, "dual audio/video weights not loaded / finalized");
-  LTX_CHECK(c->qw.empty(), LTX_ERR_UNSUPPORTED, "the dual model runs with bf16 weights only");
   LTX_CHECK(!(c->dist.comm_world && c->dist.sp > 1), LTX_ERR_UNSUPPORTED, "the dual model is single-GPU in this version");
   LTX_CHECK(B == 1 && N >= 1 && Ta >= 1 && S >= 1 && static_cast<int64_t>(F) * H * W == N, LTX_ERR_INVALID_ARGUMENT,
             "dual forward: B must be 1 and N = F*H*W");
@@ -456,6 +474,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
                o_vada = carve(static_cast<size_t>(VR) * 6 * D * 4), o_aada = carve(static_cast<size_t>(6) * Da * 4),
                o_cv = carve(static_cast<size_t>(VR) * 5 * D * 4), o_ca = carve(static_cast<size_t>(5) * Da * 4),
                o_scr = carve(static_cast<size_t>(VR) * D * 4),
+               o_tq = carve(c->qw.empty() ? 0 : static_cast<size_t>(std::max(N, Ta)) * D * 2),   // projection before the V^T transpose
                o_sev = carve(v_ts_per_token ? static_cast<size_t>(N) * 256 * 2 : 0),
                o_t1v = carve(v_ts_per_token ? static_cast<size_t>(N) * D * 2 : 0);
   wsb.reserve(off);
@@ -469,7 +488,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
        *avt = reinterpret_cast<bf16*>(wbase + o_avt), *aatt = reinterpret_cast<bf16*>(wbase + o_aatt),
        *affh = reinterpret_cast<bf16*>(wbase + o_affh), *cq = reinterpret_cast<bf16*>(wbase + o_cq),
        *catt = reinterpret_cast<bf16*>(wbase + o_catt), *vt2 = reinterpret_cast<bf16*>(wbase + o_vt2),
-       *lat_bf = reinterpret_cast<bf16*>(wbase + o_lat);
+       *lat_bf = reinterpret_cast<bf16*>(wbase + o_lat), *tq = reinterpret_cast<bf16*>(wbase + o_tq);
   float *se = reinterpret_cast<float*>(wbase + o_se), *t1 = reinterpret_cast<float*>(wbase + o_t1),
         *vemb = reinterpret_cast<float*>(wbase + o_vemb), *aemb = reinterpret_cast<float*>(wbase + o_aemb),
         *vada = reinterpret_cast<float*>(wbase + o_vada), *aada = reinterpret_cast<float*>(wbase + o_aada),
@@ -564,7 +583,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bv.a1.bq;
       gemm(c, h, D, bv.a1.wq, D, N, 2 * D, D, e);   // packed q|k projection
     }
-    linear_t(c, bv.a1.wv, bv.a1.bv, D, D, h, N, vt, ldv);
+    linear_t(c, bv.a1.wv, bv.a1.bv, D, D, h, N, vt, ldv, tq);
     {
       ProfScope ps(c, PROF_ROW, 0.0, 2.0 * N * D * 8.0, (D == 4096) ? 1 : 2);
       launch_qknorm_rope(qk, 2 * D, N, D, bv.a1.q_norm, cos_v, sin_v, N, eps, st, bv.a1.k_norm);
@@ -578,7 +597,7 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     normw(c, ax, ah, Ta, Da, ba.anorm1, ba.asst + Da, aada + Da, ba.asst, aada, eps);
     linear(c, ah, Ta, Da, ba.aa1.wq, ba.aa1.bq, Da, aq);
     linear(c, ah, Ta, Da, ba.aa1.wk, ba.aa1.bk, Da, ak);
-    linear_t(c, ba.aa1.wv, ba.aa1.bv, Da, Da, ah, Ta, avt, lda);
+    linear_t(c, ba.aa1.wv, ba.aa1.bv, Da, Da, ah, Ta, avt, lda, tq);
     qknorm_hd(c, aq, Ta, Da, hda, ba.aa1.q_norm, cos_a, sin_a, Ta, eps);
     qknorm_hd(c, ak, Ta, Da, hda, ba.aa1.k_norm, cos_a, sin_a, Ta, eps);
     attention(c, aq, ak, Da, avt, lda, nullptr, aatt, Ha, hda, Ta, Ta);
@@ -604,14 +623,14 @@ void dit_av_forward_dev(ltx_ctx* c, const void* v_latent, int v_dtype, const voi
     // A2V: Q from video (temporal RoPE of the video frames), K / V from audio
     linear(c, h, N, D, ba.a2v.wq, ba.a2v.bq, Da, cq);
     linear(c, ah, Ta, Da, ba.a2v.wk, ba.a2v.bk, Da, ak);
-    linear_t(c, ba.a2v.wv, ba.a2v.bv, Da, Da, ah, Ta, avt, lda);
+    linear_t(c, ba.a2v.wv, ba.a2v.bv, Da, Da, ah, Ta, avt, lda, tq);
     qknorm_hd(c, cq, N, Da, hda, ba.a2v.q_norm, cos_xv, sin_xv, N, eps);
     qknorm_hd(c, ak, Ta, Da, hda, ba.a2v.k_norm, cos_a, sin_a, Ta, eps);
     attention(c, cq, ak, Da, avt, lda, nullptr, catt, Ha, hda, N, Ta);
     // V2A: Q from audio, K / V from video (projected before the a2v update lands in x: h2 was taken above)
     linear(c, ah2, Ta, Da, ba.v2a.wq, ba.v2a.bq, Da, aq);
     linear(c, h2, N, D, ba.v2a.wk, ba.v2a.bk, Da, cq);
-    linear_t(c, ba.v2a.wv, ba.v2a.bv, Da, D, h2, N, vt2, ldv);
+    linear_t(c, ba.v2a.wv, ba.v2a.bv, Da, D, h2, N, vt2, ldv, tq);
     qknorm_hd(c, aq, Ta, Da, hda, ba.v2a.q_norm, cos_a, sin_a, Ta, eps);
     qknorm_hd(c, cq, N, Da, hda, ba.v2a.k_norm, cos_xv, sin_xv, N, eps);
     attention(c, aq, cq, Da, vt2, ldv, nullptr, aatt, Ha, hda, Ta, N);

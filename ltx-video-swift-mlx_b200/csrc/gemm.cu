@@ -30,29 +30,37 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 
 struct GemmCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES_MIN = 4;                   // ring depth at the widest tile
+  static constexpr int STAGES_MAX = 9;                   // ... and at the narrowest (the ring's bytes are fixed, see ring_stages)
   static constexpr int BN_MAX = 256;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_STRIDE = BN_MAX * BK * 2;  // smem stage pitch of the B ring (a stage holds bn <= 256 rows)
+  static constexpr uint32_t RING_BYTES = STAGES_MIN * (A_BYTES + BN_MAX * BK * 2);   // 192 KB of operand stages
   static constexpr uint32_t TMEM_COLS = 512;             // two accumulator stages of up to 256 columns
-  static constexpr size_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_STRIDE) + (2 * STAGES + 4) * 8 + 16 + 128 +
+  static constexpr size_t SMEM = 1024 /*align slack*/ + RING_BYTES + (2 * STAGES_MAX + 4) * 8 + 16 + 128 +
                                  4 * EPI_STAGE_BYTES;  // + per-warp epilogue staging tiles
 };
+// A stage holds one A tile (16 KB) and one B tile of bn rows (bn * 128 B, a multiple of the 1024-B swizzle atom): narrow
+// tiles get a deeper ring out of the same bytes.  The small-M GEMMs that pick them (the dual model's audio stream: M = 26
+// rows against 2048..8192-wide weights) are bound by TMA latency x bytes in flight, not by the tensor pipe.
+__host__ __device__ inline int ring_stages(int bn) {
+  const int s = static_cast<int>(GemmCfg::RING_BYTES / (GemmCfg::A_BYTES + static_cast<uint32_t>(bn) * BK * 2));
+  return s > GemmCfg::STAGES_MAX ? GemmCfg::STAGES_MAX : s;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                   int BN, int a_kblock, const GemmEpi ep) {
   using Cfg = GemmCfg;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = ring_stages(BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t b_bytes = static_cast<uint32_t>(BN) * BK * 2;   // B stage pitch = the tile itself
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STRIDE);
-  const uint32_t b_bytes = static_cast<uint32_t>(BN) * BK * 2;
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::RING_BYTES);
+  uint64_t* empty = full + Cfg::STAGES_MAX;
+  uint64_t* tfull = empty + Cfg::STAGES_MAX;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
@@ -99,7 +107,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_3d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], (kb * BK) % a_kblock, m_blk * BM, (kb * BK) / a_kblock);
           else
             tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sB + stage * Cfg::B_STRIDE, &tmB, &full[stage], kb * BK, n_blk * BN);
+          tma_load_2d(sB + stage * b_bytes, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -120,7 +128,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STRIDE);
+          const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
