@@ -31,5 +31,16 @@ for _ in range(int(os.environ.get("AV_REPS", "2"))):
                                           sg.data_ptr(), sg.data_ptr() + 4, None, None, N, Ta, S, F, H, W, 77,
                                           ov.data_ptr(), oa.data_ptr()))
 ctx.sync()
+if os.environ.get("AV_TIME"):   # plain timing of the forward (not under ncu): AV_TIME=1 AV_LAYERS=48 python tools/ncu_av.py
+    st = torch.cuda.ExternalStream(ctx.stream)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(5):
+        ctx._check(ctx.lib.ltx_av_forward_dev(ctx.handle, vl.data_ptr(), 1, al.data_ptr(), 1, tx.data_ptr(), tx.data_ptr(), 1,
+                                              sg.data_ptr(), sg.data_ptr() + 4, None, None, N, Ta, S, F, H, W, 77,
+                                              ov.data_ptr(), oa.data_ptr()))
+    b.record(st)
+    torch.cuda.synchronize()
+    print("ms_per_forward", a.elapsed_time(b) / 5, "layers", L)
 print("ok", float(ov.float().std()), float(oa.float().std()))
 ctx.close()
