@@ -339,7 +339,8 @@ int ltx_set_profiling(ltx_ctx* ctx, int enabled);
 int ltx_get_profile(ltx_ctx* ctx, double* ms, double* flops, double* bytes, uint64_t* counts, int n_classes);
 
 /* ---- diagnostic single-kernel entry points (device pointers; used by the parity tests and the profiler) ---- */
-/* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) ; mode: 0 bf16 out, 1 gelu bf16 out, 3 fp32 out; force_bn: 0 auto, 128, 256. */
+/* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) ; mode: 0 bf16 out, 1 gelu bf16 out, 3 fp32 out, 4 silu bf16 out; force_bn: 0 auto, a tile
+ * width, or -1 = the weight-streaming kernel for M <= 32 (error if the shape is not eligible). */
 int ltx_op_gemm(ltx_ctx* ctx, const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int mode,
                 int force_bn);
 /* x[M,N] (fp32) += (A B^T + bias) * (gate_a[n] + gate_b[n]) * scale ; shadow (bf16, nullable) = new x. */

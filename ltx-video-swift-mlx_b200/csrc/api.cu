@@ -895,10 +895,15 @@ int ltx_adain_filter(ltx_ctx* c, float* latent, size_t n_per_channel, const floa
 int ltx_op_gemm(ltx_ctx* c, const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int mode,
                 int force_bn) {
   return guarded(c, [&] {
-    LTX_CHECK(mode == EPI_BF16 || mode == EPI_GELU_BF16 || mode == EPI_F32, LTX_ERR_INVALID_ARGUMENT, "bad mode");
     GemmEpi e;
     e.mode = mode; e.out = C; e.ldo = N; e.bias = bias;
-    launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);
+    LTX_CHECK(mode == EPI_BF16 || mode == EPI_GELU_BF16 || mode == EPI_F32 || mode == EPI_SILU_BF16, LTX_ERR_INVALID_ARGUMENT, "bad mode");
+    if (force_bn == -1) {   // the weight-streaming kernel for M <= 32, or an error: never a silent switch to the tile kernel
+      LTX_CHECK(gemm_skinny_eligible(K, K, M, N, K, e, 0), LTX_ERR_INVALID_ARGUMENT, "shape not eligible for the skinny GEMM");
+      launch_gemm_skinny(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    } else {
+      launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);
+    }
     c->launches++;
   });
 }
@@ -909,7 +914,8 @@ int ltx_op_gemm_resid(ltx_ctx* c, const void* A, const void* B, const float* bia
     GemmEpi e;
     e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = bias; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = 0;
     e.rows_per_gate = M > 0 ? M : 1; e.shadow = reinterpret_cast<bf16*>(shadow); e.lds = N; e.scale = scale;
-    launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, 0, 0, 0,
+                1 /* M <= 32: the weight-streaming kernel, as on the dual model's audio stream */);
     c->launches++;
   });
 }

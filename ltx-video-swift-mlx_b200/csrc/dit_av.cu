@@ -220,7 +220,7 @@ void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
     launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream);
     return;
   }
-  launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream);
+  launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream, 0, 0, 0, 1);   // the audio stream's M <= 32 Linears stream their weights
 }
 // out_bf16[M, N] = A W^T + b
 void linear(ltx_ctx* c, const bf16* A, int M, int K, const bf16* W, const float* b, int N, bf16* out, int mode = EPI_BF16) {

@@ -202,7 +202,7 @@ int fit_tile_width(int M, int N, int sms) {
 int gemm_fit_tile_width(int M, int N) { return fit_tile_width(M, N, device_sm_count()); }
 
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
-                 cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride) {
+                 cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride, int allow_skinny) {
   LTX_CHECK(M > 0 && N > 0 && K > 0, 2, "GEMM: empty problem");
   LTX_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, 2, "GEMM: K and leading dims must be multiples of 8");
   if (epi.mode == EPI_GATE_RESID) {
@@ -217,6 +217,10 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
   if (force_bn == 0) {  // experiment hook: LTX_GEMM_FORCE_BN is re-read on every call
     const char* e = getenv("LTX_GEMM_FORCE_BN");
     if (e) force_bn = atoi(e);
+  }
+  if (allow_skinny && force_bn == 0 && gemm_skinny_eligible(lda, ldb, M, N, K, epi, a_kblock)) {
+    launch_gemm_skinny(A, lda, B, ldb, M, N, K, epi, stream);
+    return;
   }
   // force_bn >= 2000 selects the 4-CTA multicast kernel (gemm4.cu) with width force_bn - 2000 (0 = fitted); LTX_GEMM_4CTA=1
   // makes it the default for problems with more than one 128-row tile and at least two column tiles

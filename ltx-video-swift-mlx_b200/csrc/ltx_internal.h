@@ -111,8 +111,14 @@ struct GemmEpi {
 // C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 K-major (row pitch lda / ldb elements, multiples of 8).
 // a_kblock > 0: A is K-blocked (Ulysses receive layout): element (m, k) lives at A[(k / a_kblock) * a_kblock_stride +
 // m * lda + k % a_kblock] (a_kblock % 64 == 0, lda = a_kblock).
+// allow_skinny: M <= 32 problems may take the weight-streaming kernel (gemm_skinny.cu) -- opt-in, because its summation
+// order differs from the tile kernels' and the sequence-parallel path promises results bit-identical to one GPU.
 void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
-                 cudaStream_t stream, int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
+                 cudaStream_t stream, int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0, int allow_skinny = 0);
+// weight-streaming Linear for M <= 32 (gemm_skinny.cu): HBM-bound, mma.sync on 16-byte coalesced weight rows
+bool gemm_skinny_eligible(int64_t lda, int64_t ldb, int M, int N, int K, const GemmEpi& epi, int a_kblock);
+void launch_gemm_skinny(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                        cudaStream_t stream);
 int gemm_fit_tile_width(int M, int N);
 // 2-CTA (cta_group::2) pair kernel, same contract as launch_gemm (gemm2.cu)
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,

@@ -56,7 +56,57 @@ def test_gemm(ctx, M, N, K, bn, mode):
     assert rel_l2(out.float(), ref) <= tol
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 264, 128), (1536, 4096, 4096), (1536, 4096, 16384)])
+SKINNY = [(26, 2048, 2048), (26, 8192, 2048), (26, 2048, 8192), (11, 128, 128), (32, 48, 96), (17, 16, 32), (16, 2048, 4096),
+          (1, 128, 4096), (5, 4096, 64), (24, 256, 192), (31, 272, 1056)]
+
+
+@pytest.mark.parametrize("M,N,K", SKINNY)
+@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+def test_gemm_skinny(ctx, M, N, K, mode):
+    """The weight-streaming kernel for M <= 32 (gemm_skinny.cu, the dual model's audio-stream Linears), forced with bn = -1:
+    same contract and tolerances as the tile kernels, and the two agree with each other to accumulation-order noise."""
+    g = torch.Generator(device="cuda").manual_seed(M * 11 + N * 5 + K + mode)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    dt = torch.float32 if mode == 3 else torch.bfloat16
+    out = torch.full((M + 1, N), float("nan"), device="cuda", dtype=dt)      # one guard row: nothing may be written past M
+    tile = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+    torch.cuda.synchronize()
+    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, -1))
+    if N % 8 == 0 or mode == 3:
+        ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), tile.data_ptr(), M, N, K, mode, 0))
+    ctx.sync()
+    ref = A.float() @ B.float().t() + bias
+    if mode == 1:
+        ref = _gelu_tanh(ref)
+    if mode == 4:
+        ref = ref * torch.sigmoid(ref)
+    tol = 2e-5 if mode == 3 else 4e-3
+    assert torch.isfinite(out[:M].float()).all() and torch.isnan(out[M].float()).all()
+    assert rel_l2(out[:M].float(), ref) <= tol
+    if N % 8 == 0 or mode == 3:
+        assert rel_l2(out[:M].float(), tile.float()) <= (2e-5 if mode == 3 else 3e-3)
+    # deterministic
+    out2 = torch.empty_like(out)
+    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out2.data_ptr(), M, N, K, mode, -1))
+    ctx.sync()
+    assert torch.equal(out[:M], out2[:M])
+
+
+def test_gemm_skinny_refuses_ineligible_shapes(ctx):
+    from ltx_video_swift_mlx_b200._lib import LtxError
+    A = torch.zeros(40, 64, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(32, 64, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(40, 32, device="cuda", dtype=torch.bfloat16)
+    for M, N, K in [(40, 32, 64), (8, 24, 64), (8, 32, 48)]:      # too many rows, N % 16, K % 32
+        with pytest.raises(LtxError) as e:
+            ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), None, out.data_ptr(), M, N, K, 0, -1))
+        assert e.value.code == 2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 264, 128), (1536, 4096, 4096), (1536, 4096, 16384),
+                                   (26, 2048, 2048), (11, 128, 128), (32, 2048, 8192)])      # M <= 32: weight-streaming kernel
 def test_gemm_gate_residual(ctx, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
