@@ -242,7 +242,13 @@ void linear_t(ltx_ctx* c, const bf16* W, const float* b, int Nout, int K, const 
               bf16* tmp) {
   if (c->qw.empty() || c->qw.find(W) == c->qw.end()) {
     GemmEpi e;
-    e.mode = EPI_BF16; e.out = out; e.ldo = ld_out; e.bias = b; e.bias_per_row = 1;
+    e.mode = EPI_BF16; e.out = out; e.ldo = ld_out; e.bias = b;
+    if (rows <= 32 && gemm_skinny_eligible(K, K, rows, Nout, K, e, 0)) {   // audio rows: stream the weight, store transposed
+      e.transpose_out = 1;
+      gemm(c, hrows, K, W, K, rows, Nout, K, e);
+      return;
+    }
+    e.bias_per_row = 1;
     gemm(c, W, K, hrows, K, Nout, rows, K, e);
     return;
   }

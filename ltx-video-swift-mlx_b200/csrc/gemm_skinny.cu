@@ -15,7 +15,8 @@
 //   dependent launch they overlap the producer's tail.  Partial sums of the 8 warps meet in shared memory and are added in
 //   warp order (deterministic); 256 threads then apply bias / GELU / SiLU / gate * residual and store two columns each.
 //
-// Supported: a_kblock = 0, row-major outputs (no column blocking, no transposed columns), K % 32 == 0, N % 16 == 0.
+// Supported: a_kblock = 0, row-major outputs (no column blocking, no split transposed columns) or, for the bf16 epilogue, the
+// whole output transposed (V^T), K % 32 == 0, N % 16 == 0.
 // launch_gemm falls back to the tensor-core kernels otherwise (and for M > 32).
 #include "ltx_internal.h"
 #include "ptx.cuh"
@@ -163,9 +164,15 @@ gemm_skinny_kernel(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M
   } else {
     if (MODE == EPI_GELU_BF16) { v[0] = gelu_tanh(v[0]); v[1] = gelu_tanh(v[1]); }
     if (MODE == EPI_SILU_BF16) { v[0] = silu(v[0]); v[1] = silu(v[1]); }
-    bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + n;
-    o[0] = __float2bfloat16(v[0]);
-    o[1] = __float2bfloat16(v[1]);
+    if (MODE == EPI_BF16 && ep.transpose_out) {
+      bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(n) * ep.ldo + row;
+      o[0] = __float2bfloat16(v[0]);
+      o[ep.ldo] = __float2bfloat16(v[1]);
+    } else {
+      bf16* o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(row) * ep.ldo + n;
+      o[0] = __float2bfloat16(v[0]);
+      o[1] = __float2bfloat16(v[1]);
+    }
   }
 }
 
@@ -180,7 +187,8 @@ void launch_impl(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M, 
 bool gemm_skinny_eligible(int64_t lda, int64_t ldb, int M, int N, int K, const GemmEpi& epi, int a_kblock) {
   static const bool enabled = []() { const char* e = getenv("LTX_GEMM_SKINNY"); return !(e && e[0] == '0'); }();   // A/B switch
   return enabled && M >= 1 && M <= 32 && a_kblock == 0 && K % 32 == 0 && N % SK_COLS == 0 && lda % 8 == 0 && ldb % 8 == 0 &&
-         epi.col_block == 0 && epi.tsplit_col == 0 && epi.mode >= EPI_BF16 && epi.mode <= EPI_SILU_BF16;
+         epi.col_block == 0 && epi.tsplit_col == 0 && epi.mode >= EPI_BF16 && epi.mode <= EPI_SILU_BF16 &&
+         (epi.transpose_out == 0 || epi.mode == EPI_BF16);
 }
 
 void launch_gemm_skinny(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M, int N, int K, const GemmEpi& epi,

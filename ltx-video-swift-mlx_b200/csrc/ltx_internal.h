@@ -105,6 +105,8 @@ struct GemmEpi {
   int tsplit_col = 0;
   bf16* out_t = nullptr;
   int64_t ldt = 0;
+  // weight-streaming kernel only (gemm_skinny.cu), EPI_BF16: element (m, n) is stored at out[n * ldo + m] -- V^T for the PV MMA
+  int transpose_out = 0;
   int debug = 0;  // bit 0: skip the epilogue's global traffic (LTX_GEMM_DEBUG, timing experiments only)
 };
 
