@@ -55,3 +55,33 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.LtxError) as e:
         LtxContext(LTXTransformerConfig(), 0)
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
+
+
+def test_pure_host_entry_points_without_a_gpu():
+    """ltx_vae_tiled_frames is pure chunk arithmetic (decodeWithTemporalTiling, V/VideoDecoder.swift:525-589): checked here, on the
+    GPU-less host, against the same loop written out and against the untiled 8 (F' - 1) + 1."""
+    lib = _lib.load()
+
+    def frames(total, tile, overlap):      # the reference's loop, frame counts only
+        if tile <= 0 or total <= tile:
+            return 8 * (total - 1) + 1
+        stride, po, chunks, start = tile - overlap, 8 * overlap, [], 0
+        while start < total:
+            end = min(start + tile, total)
+            chunks.append(8 * (end - start - 1) + 1)
+            if end >= total:
+                break
+            start += stride
+        res = chunks[0]
+        for nf in chunks[1:]:
+            res = res + nf - po if 0 < po < res and po < nf else res + nf
+        return res
+    for total in (1, 2, 5, 8, 9, 16, 33):
+        for tile in (0, 1, 2, 3, 4, 8, 16):
+            for overlap in (0, 1, 2, 3):
+                got = lib.ltx_vae_tiled_frames(total, tile, overlap)
+                if 0 < tile < total and overlap >= tile:
+                    assert got == -1, (total, tile, overlap, got)        # the stride would not advance
+                else:
+                    assert got == frames(total, tile, overlap), (total, tile, overlap, got)
+    assert lib.ltx_vae_tiled_frames(16, 8, 1) == 107 and lib.ltx_vae_tiled_frames(0, 8, 1) == -1
