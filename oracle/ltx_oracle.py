@@ -15,7 +15,9 @@ its primitives are the published ones:
   geluApproximate = 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)));  variance = population (ddof 0)
   type promotion bf16 (x) f32 -> f32.
 The only in-source known-answer data are the sigma tables (S/LTXScheduler.swift:18-36) and the shape
-formulae; those are checked in tests/test_oracle.py.
+formulae; those are checked in tests/test_oracle.py.  Each assumed primitive is additionally checked
+against a second, code-independent implementation (torch.nn.functional / einops / complex arithmetic)
+in tests/test_oracle_primitives.py -- that pins the DEFINITIONS, not MLX's bits: parity stays unpinned.
 
 File:line citations are relative to /root/reference/Sources/LTXVideo/ (T/ = Models/Transformer,
 V/ = Models/VAE, P/ = Pipeline, S/ = Scheduler, C/ = Configuration).
