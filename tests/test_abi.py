@@ -85,3 +85,16 @@ def test_pure_host_entry_points_without_a_gpu():
                 else:
                     assert got == frames(total, tile, overlap), (total, tile, overlap, got)
     assert lib.ltx_vae_tiled_frames(16, 8, 1) == 107 and lib.ltx_vae_tiled_frames(0, 8, 1) == -1
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ltxcuda.h compiled as C99 with -Wall -Werror -pedantic by gcc, linked against the in-tree library and run:
+    the boundary a SwiftPM C target would import."""
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-l:libltxcuda.so",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert ("no CPU fallback" in r.stdout) != torch.cuda.is_available()
