@@ -54,9 +54,12 @@ class LTX2Transformer:
                  context_key: int = 0):
         import numpy as np
         vt, at = np.asarray(video_timesteps, dtype=np.float32).reshape(-1), np.asarray(audio_timesteps, dtype=np.float32).reshape(-1)
-        if vt.size != 1 or at.size != 1:
-            raise ValueError("one sigma per stream (per-token timesteps of the dual model are not implemented)")
+        n_video = int(np.asarray(video_latent.shape)[1])
+        if vt.size not in (1, n_video) or at.size != 1:
+            # videoTimesteps is [B] or [B, N] (image-to-video, Pipeline/LTXPipeline.swift:1293-1298); audioTimesteps is [B]
+            raise ValueError("videoTimesteps must hold one sigma or one per video token, audioTimesteps one sigma")
         if audio_num_frames is not None and audio_num_frames != np.asarray(audio_latent.shape)[1]:
             raise ValueError("audio_num_frames must equal the audio latent length")
-        return self.ctx.av_forward(video_latent, audio_latent, video_context, audio_context, float(vt[0]), float(at[0]),
+        return self.ctx.av_forward(video_latent, audio_latent, video_context, audio_context,
+                                   float(vt[0]) if vt.size == 1 else vt.reshape(1, -1), float(at[0]),
                                    tuple(video_latent_shape), video_context_mask, audio_context_mask, context_key)

@@ -57,10 +57,48 @@ def guidance_case():
     return dict(x=x.numpy(), vc=vc.numpy(), vu=vu.numpy(), vs=vs.numpy(), vp=vp.numpy(), out=out.numpy(), v=v.numpy())
 
 
+def av_case():
+    """Dual audio / video forward (T/LTX2Transformer.swift:240-392): scalar sigmas, and per-token video sigmas (image-to-video)."""
+    cfg = O.DiTConfig(num_layers=2, num_heads=2, head_dim=128, caption_channels=192)
+    av = O.AVConfig(audio_heads=2)
+    w = O.make_av_weights(cfg, av, 2468)
+    g = torch.Generator().manual_seed(8642)
+    fhw, Ta, S = (2, 4, 6), 11, 40
+    vl = torch.randn(1, 48, 128, generator=g).bfloat16().float()
+    al = torch.randn(1, Ta, 128, generator=g).bfloat16().float()
+
+    def text():
+        t = torch.randn(1, S, 192, generator=g)
+        return (t / t.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16().float()
+    vc, ac = text(), text()
+    mask = torch.ones(1, S, dtype=torch.int32)
+    mask[:, :5] = 0
+    sv, sa = torch.tensor([0.7]), torch.tensor([0.55])
+    v, a = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, sv, sa, mask, mask, fhw, Ta)
+    ts = torch.full((1, 48), 0.7)
+    ts[:, :24] = 0.0
+    v_tok, a_tok = O.av_dit_forward(w, cfg, av, vl, al, vc, ac, ts, sa, mask, mask, fhw, Ta)
+    return dict(video_latent=vl.numpy(), audio_latent=al.numpy(), video_context=vc.numpy(), audio_context=ac.numpy(),
+                mask=mask.numpy(), video_velocity=v.numpy(), audio_velocity=a.numpy(), video_sigmas_tok=ts.numpy(),
+                video_velocity_tok=v_tok.numpy(), audio_velocity_tok=a_tok.numpy())
+
+
+def vae_tiled_case():
+    """decodeWithTemporalTiling (V/VideoDecoder.swift:517-602) on the vae_small weights: 5 latent frames, tile 3, overlap 1."""
+    cfg = O.VAEConfig(base_channels=512, blocks_per_stage=1)
+    w = O.make_vae_weights(cfg, 99)
+    w = {k: (O.bf16_round(v) if k.endswith("conv.weight") else v) for k, v in w.items()}
+    z = torch.randn(1, 128, 5, 2, 2, generator=torch.Generator().manual_seed(97))
+    frames = O.decode_video(w, cfg, z, temporal_tile_size=3, temporal_tile_overlap=1)
+    return dict(latent=z.numpy(), frames=frames.numpy().astype(np.float16))
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "dit_small.npz"), **dit_case())
     np.savez_compressed(os.path.join(HERE, "vae_small.npz"), **vae_case())
     np.savez_compressed(os.path.join(HERE, "sigmas.npz"), **sigma_case())
     np.savez_compressed(os.path.join(HERE, "guidance.npz"), **guidance_case())
+    np.savez_compressed(os.path.join(HERE, "av_small.npz"), **av_case())
+    np.savez_compressed(os.path.join(HERE, "vae_tiled_small.npz"), **vae_tiled_case())
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -269,3 +269,24 @@ def test_vae_temporal_tiling_oracle():
     inside = (a[13] > 1e-3) & (a[13] < 1 - 1e-3) & (b[4] > 1e-3) & (b[4] < 1 - 1e-3)
     assert torch.allclose(tiled[13][inside], mid[inside], atol=1e-6)
     assert torch.equal(O.decode_video(w, cfg, z, temporal_tile_size=8), O.decode_video(w, cfg, z))   # fits one tile
+
+
+def test_av_and_tiled_vae_golden():
+    """Committed vectors of the dual forward (scalar and per-token video sigmas) and of the temporally tiled decode."""
+    g = np.load(os.path.join(GOLD, "av_small.npz"))
+    cfg = O.DiTConfig(num_layers=2, num_heads=2, head_dim=128, caption_channels=192)
+    av = O.AVConfig(audio_heads=2)
+    w = O.make_av_weights(cfg, av, 2468)
+    t = lambda k: torch.from_numpy(g[k])                                     # noqa: E731
+    args = (t("video_latent"), t("audio_latent"), t("video_context"), t("audio_context"))
+    v, a = O.av_dit_forward(w, cfg, av, *args, torch.tensor([0.7]), torch.tensor([0.55]), t("mask"), t("mask"), (2, 4, 6), 11)
+    assert O.rel_l2(v, t("video_velocity")) < 1e-5 and O.rel_l2(a, t("audio_velocity")) < 1e-5
+    v, a = O.av_dit_forward(w, cfg, av, *args, t("video_sigmas_tok"), torch.tensor([0.55]), t("mask"), t("mask"), (2, 4, 6), 11)
+    assert O.rel_l2(v, t("video_velocity_tok")) < 1e-5 and O.rel_l2(a, t("audio_velocity_tok")) < 1e-5
+    g2 = np.load(os.path.join(GOLD, "vae_tiled_small.npz"))
+    vcfg = O.VAEConfig(base_channels=512, blocks_per_stage=1)
+    vw = O.make_vae_weights(vcfg, 99)
+    vw = {k: (O.bf16_round(x) if k.endswith("conv.weight") else x) for k, x in vw.items()}
+    fr = O.decode_video(vw, vcfg, torch.from_numpy(g2["latent"]), temporal_tile_size=3, temporal_tile_overlap=1)
+    assert fr.shape == (26, 64, 64, 3)
+    assert O.psnr(fr, torch.from_numpy(g2["frames"].astype(np.float32))) > 55
