@@ -461,6 +461,7 @@ int ltx_denoise_begin(ltx_ctx* c, const float* noise, int F, int H, int W, float
     LTX_CHECK(g.in_channels == g.out_channels, LTX_ERR_INVALID_CONFIGURATION, "in/out channels must match");
     const size_t n = static_cast<size_t>(g.in_channels) * F * H * W;
     c->s_F = F; c->s_H = H; c->s_W = W; c->s_S = S;
+    c->s_Ta = 0;   // a video-only session: ltx_av_denoise_step is refused until ltx_av_denoise_begin
     c->s_ctx_dtype = context_dtype;
     h2d(c, c->s_latent, noise, n * 4);
     {
