@@ -290,3 +290,26 @@ def test_av_and_tiled_vae_golden():
     fr = O.decode_video(vw, vcfg, torch.from_numpy(g2["latent"]), temporal_tile_size=3, temporal_tile_overlap=1)
     assert fr.shape == (26, 64, 64, 3)
     assert O.psnr(fr, torch.from_numpy(g2["frames"].astype(np.float32))) > 55
+
+
+def test_parameter_inventory_matches_the_reference_constructors():
+    """Parameter count per block as a function of the width, from the constructors (T/LTXAttention.swift:117-157,
+    T/LTXFeedForward.swift:39-52, T/LTXTransformerBlock.swift:140-160): 8 Linears (D x D + D) in the two attentions, four
+    RMSNorm weights, the 4x FFN and the 6 x D table.  At D = 4096 that is 268 529 664 per block and, with the global tensors,
+    13.04 B for the 48-block video model (26.1 GB bf16, the measured 27 GB mean RAM of the reference)."""
+    def per_block(D, mult=4):
+        return 8 * (D * D + D) + 4 * D + (D * mult * D + mult * D) + (mult * D * D + D) + 6 * D
+    assert per_block(4096) == 268_529_664
+    cfg = O.DiTConfig(num_layers=3, num_heads=2, head_dim=128, caption_channels=192)
+    w = O.make_dit_weights(cfg, 0)
+    D = cfg.inner_dim
+    blk = sum(v.numel() for k, v in w.items() if k.startswith("transformer_blocks.1."))
+    assert blk == per_block(D)
+    glob = sum(v.numel() for k, v in w.items() if not k.startswith("transformer_blocks."))
+    # patchify_proj, adaln_single (256 -> D -> D, D -> 6D), caption_projection (Cc -> D -> D), proj_out, scale_shift_table
+    want = (128 * D + D) + (256 * D + D) + (D * D + D) + (D * 6 * D + 6 * D) + (192 * D + D) + (D * D + D) + (D * 128 + 128) + 2 * D
+    assert glob == want
+    full_glob = (128 * 4096 + 4096) + (256 * 4096 + 4096) + (4096 ** 2 + 4096) + (6 * 4096 ** 2 + 6 * 4096) + \
+                (3840 * 4096 + 4096) + (4096 ** 2 + 4096) + (4096 * 128 + 128) + 2 * 4096
+    total = 48 * per_block(4096) + full_glob
+    assert abs(total / 1e9 - 13.04) < 0.01 and abs(full_glob / 1e6 - 152.1) < 0.1
