@@ -122,3 +122,34 @@ def test_linear_layernorm_and_adain_match_torch():
     # AdaIN: per-channel statistics of the result equal the reference's (P/LatentUtils.swift:201-227)
     assert torch.allclose(out.flatten(2).mean(-1), ref.flatten(2).mean(-1), atol=1e-10)
     assert torch.allclose(out.flatten(2).std(-1, unbiased=False), ref.flatten(2).std(-1, unbiased=False), rtol=1e-4)
+
+
+@pytest.mark.parametrize("heads,head_dim,fhw", [(2, 16, (2, 2, 3)), (4, 32, (3, 2, 2)), (2, 128, (2, 3, 2))])
+def test_rope_table_against_scalar_loops(heads, head_dim, fhw):
+    """precomputeFreqsCis (doublePrecision, split; T/LTXRoPE.swift:375-488) written out as the reference's own scalar loops --
+    a second derivation of the vectorised oracle table, including the left identity padding and the head split."""
+    cfg = O.DiTConfig(num_layers=1, num_heads=heads, head_dim=head_dim)
+    cos, sin = O.rope_table(cfg, *fhw)
+    D, theta, max_pos = heads * head_dim, cfg.rope_theta, cfg.max_pos
+    F, H, W = fhw
+    grid = []                                    # createPositionGrid (:552-610): (t, h, w) mid-points per token, fp32
+    for f in range(F):
+        s0, e0 = max(f * 8 + (1 - 8), 0), max((f + 1) * 8 + (1 - 8), 0)
+        for h in range(H):
+            for w in range(W):
+                grid.append((np.float32((np.float32(s0) + np.float32(e0)) / np.float32(2.0)) / np.float32(24.0),
+                             np.float32(h * 32 + 16.0), np.float32(w * 32 + 16.0)))
+    n_idx = max(1, D // 6)
+    idx = [theta ** ((i / (n_idx - 1)) if n_idx > 1 else 0.0) * (math.pi / 2.0) for i in range(n_idx)]
+    pad = max(0, D // 2 - n_idx * 3)
+    hd2 = (D // 2) // heads
+    for t, pos in enumerate(grid):
+        row_c, row_s = [1.0] * pad, [0.0] * pad
+        for fi in range(n_idx):
+            for d in range(3):
+                a = idx[fi] * (float(pos[d]) / max_pos[d] * 2.0 - 1.0)
+                row_c.append(math.cos(a))
+                row_s.append(math.sin(a))
+        for hh in range(heads):
+            assert np.allclose(cos[hh, t].numpy(), np.float32(row_c[hh * hd2:(hh + 1) * hd2]), atol=1e-7)
+            assert np.allclose(sin[hh, t].numpy(), np.float32(row_s[hh * hd2:(hh + 1) * hd2]), atol=1e-7)
