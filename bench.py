@@ -5,17 +5,22 @@ One "step" = one denoise step of the distilled LTX-2 video DiT at 768x512x25 fra
 tokens, S = 1024 text tokens, 48 blocks, D = 4096, bf16 weights, random-init on the device, synthetic inputs):
 patchify -> 48-block forward -> unpatchify -> Euler update.  Step-invariant text projections are cached by the warm-up.
 
-  value        steps/s, whole job, latent resident in HBM (ltx_denoise_step), CUDA events on the library's stream
+  value        steps/s of ONE video (latent resident in HBM, ltx_denoise_step), CUDA events on the library's stream.
+               --gpus N > 1: the SAME video strong-scaled over N GPUs by Ulysses sequence parallelism (`scaling: "strong"`);
+               N independent replicas (the trivial weak-scaling mode) are reported under extras.replicas
   e2e          steps/s through the host-buffer C ABI the Swift pipeline binds (ltx_dit_forward + ltx_guided_euler_step):
                pinned-host -> device copies of latent/timestep (+ text on a cache miss) and device -> host copies of the
                velocity and the new latent are inside the timed region
+  parity       what the timed code computes, checked in the same process: a 2-block prefix of the model at the config-2
+               shapes against the CPU oracle (rel-L2 <= 1e-2), the timed 48-block latent finite, the decoder on the real
+               channel plan against the oracle (PSNR >= 40 dB); N > 1: the N-GPU latent / frames against this rank's own
+               1-GPU run of the same inputs
   roofline     tensor-pipe roofline of the dominant kernel class (the tcgen05 GEMM): algorithmic FLOPs of the GEMM launches
                of one step / their summed device time (CUDA events around every launch, separate profiled pass)
   cpu_baseline the CPU oracle (a port of the reference's algorithm) on this box's host cores, bounded sample
   vae          secondary metric: frames/s of the video-VAE decode of the same clip (25 frames, 768x512)
 
 `--impl reference` times the CPU port only (the Swift/MLX reference cannot be built in this image).
-Multi-GPU (torchrun, one rank per GPU): independent replicas (whole-video data parallel), weak scaling.
 """
 import argparse
 import json
@@ -34,6 +39,8 @@ sys.path.insert(0, ROOT)
 
 CFG2 = dict(width=768, height=512, frames=25, F=4, H=16, W=24, N=1536, S=1024)
 D, L, HEADS, CAP, CIN = 4096, 48, 32, 3840, 128
+WORKLOAD = ("LTX-2 distilled 13B-video DiT denoise step (BASELINE config 2): 768x512x25f -> N=1536 tokens, S=1024 text tokens, "
+            "48 blocks, D=4096, 32 heads")
 
 
 def dit_flops_per_step(N, S, cached_text=True):
@@ -90,10 +97,48 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU port arm
+_CPU_CACHE = {}
+
+
+def _cpu_port_inputs(O, cfg):
+    """One transformer block's weights at the LTX-2 width plus the global (embedding / head) weights; the full-step timing
+    re-uses the block for all 48 layers (same arithmetic, 1/48 of the 52 GB an fp32 copy of the model would need)."""
+    g = torch.Generator().manual_seed(0)
+    w = {}
+
+    def lin(name, out_f, in_f):
+        w[name + ".weight"] = torch.randn(out_f, in_f, generator=g) / math.sqrt(in_f)
+        w[name + ".bias"] = torch.zeros(out_f)
+    p = "transformer_blocks.0."
+    w[p + "scale_shift_table"] = torch.randn(6, D, generator=g) * 0.1
+    for a in ("attn1", "attn2"):
+        for l in ("to_q", "to_k", "to_v", "to_out"):
+            lin(p + f"{a}.{l}", D, D)
+        w[p + f"{a}.q_norm.weight"] = torch.ones(D)
+        w[p + f"{a}.k_norm.weight"] = torch.ones(D)
+    lin(p + "ff.project_in.proj", 4 * D, D)
+    lin(p + "ff.project_out", D, 4 * D)
+    lin("patchify_proj", D, CIN)
+    lin("adaln_single.emb.linear_1", D, 256)
+    lin("adaln_single.emb.linear_2", D, D)
+    lin("adaln_single.linear", 6 * D, D)
+    lin("caption_projection.linear_1", D, CAP)
+    lin("caption_projection.linear_2", D, D)
+    w["scale_shift_table"] = torch.randn(2, D, generator=g) * 0.1
+    lin("proj_out", CIN, D)
+    x = torch.randn(1, CFG2["N"], D, generator=g)
+    ctx = torch.randn(1, CFG2["S"], D, generator=g)
+    ada = torch.randn(1, 1, 6, D, generator=g) * 0.1
+    lat = torch.randn(1, CFG2["N"], CIN, generator=g)
+    text = torch.randn(1, CFG2["S"], CAP, generator=g)
+    rope = O.rope_table(cfg, CFG2["F"], CFG2["H"], CFG2["W"])
+    return dict(w=w, x=x, ctx=ctx, ada=ada, rope=rope, lat=lat, text=text)
+
+
 def cpu_port_step_seconds(sample_blocks=1, repeats=1):
     """Times the oracle (CPU port of the reference algorithm) on a bounded sample of the config-2 step: `sample_blocks`
-    transformer blocks at the full shapes (N=1536, S=1024, D=4096, fp32) plus the embedding / head work measured once,
-    extrapolated to 48 blocks.  Returns (seconds per full step, cores, description)."""
+    transformer blocks at the full shapes (N=1536, S=1024, D=4096, fp32), extrapolated to 48 blocks.
+    Returns (seconds per full step, cores, description)."""
     from oracle import ltx_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = O.DiTConfig()
@@ -113,29 +158,28 @@ def cpu_port_step_seconds(sample_blocks=1, repeats=1):
     return best * L, os.cpu_count() or 1, f"{sample_blocks} of {L} blocks at N=1536,S=1024,D=4096 fp32 (torch CPU), x{L}"
 
 
-_CPU_CACHE = {}
+def cpu_port_full_step_seconds():
+    """ONE true full step of the CPU port, not extrapolated: patchify projection, timestep MLPs, caption projection, RoPE
+    table, all 48 block forwards (block 0's weights stand in for every layer), output head, Euler update.  ~26 s on 16 cores."""
+    from oracle import ltx_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.DiTConfig()
+    if not _CPU_CACHE:
+        _CPU_CACHE.update(_cpu_port_inputs(O, cfg))
+    base = _CPU_CACHE["w"]
 
-
-def _cpu_port_inputs(O, cfg):
-    g = torch.Generator().manual_seed(0)
-    w = {}
-    p = "transformer_blocks.0."
-    w[p + "scale_shift_table"] = torch.randn(6, D, generator=g) * 0.1
-    for a in ("attn1", "attn2"):
-        for l in ("to_q", "to_k", "to_v", "to_out"):
-            w[p + f"{a}.{l}.weight"] = torch.randn(D, D, generator=g) / math.sqrt(D)
-            w[p + f"{a}.{l}.bias"] = torch.zeros(D)
-        w[p + f"{a}.q_norm.weight"] = torch.ones(D)
-        w[p + f"{a}.k_norm.weight"] = torch.ones(D)
-    w[p + "ff.project_in.proj.weight"] = torch.randn(4 * D, D, generator=g) / math.sqrt(D)
-    w[p + "ff.project_in.proj.bias"] = torch.zeros(4 * D)
-    w[p + "ff.project_out.weight"] = torch.randn(D, 4 * D, generator=g) / math.sqrt(4 * D)
-    w[p + "ff.project_out.bias"] = torch.zeros(D)
-    x = torch.randn(1, CFG2["N"], D, generator=g)
-    ctx = torch.randn(1, CFG2["S"], D, generator=g)
-    ada = torch.randn(1, 1, 6, D, generator=g) * 0.1
-    rope = O.rope_table(cfg, CFG2["F"], CFG2["H"], CFG2["W"])
-    return dict(w=w, x=x, ctx=ctx, ada=ada, rope=rope)
+    class Shared(dict):      # transformer_blocks.i.* -> transformer_blocks.0.*
+        def __missing__(self, k):
+            if k.startswith("transformer_blocks."):
+                return base["transformer_blocks.0." + k.split(".", 2)[2]]
+            raise KeyError(k)
+    w = Shared(base)
+    lat, text = _CPU_CACHE["lat"], _CPU_CACHE["text"]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        v = O.dit_forward(w, cfg, lat, text, torch.tensor([0.7]), None, (CFG2["F"], CFG2["H"], CFG2["W"]))
+        _ = lat + (0.5 - 0.7) * v
+        return time.perf_counter() - t0
 
 
 def run_reference(args, rank):
@@ -147,21 +191,85 @@ def run_reference(args, rank):
         if i >= args.warmup:
             times.append(t)
     sec = float(np.mean(times))
+    full = None
+    if not args.no_cpu_full_step:
+        try:
+            full = cpu_port_full_step_seconds()
+        except Exception as e:   # report, do not hide
+            full = f"failed: {e}"
     line = dict(metric="dit_steps_per_s", value=1.0 / sec, unit="steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                impl="reference",
-                config=dict(workload="LTX-2 distilled DiT denoise step, 768x512x25f (N=1536 tokens, S=1024 text), 48 blocks",
-                            note="CPU port of the reference algorithm (oracle/); the Swift+MLX reference cannot be built here"),
-                cpu_baseline=dict(value=1.0 / sec, unit="steps/s", cores=cores, kind="port", sample=desc),
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", extrapolated=True,
+                sample_ms_per_step=sec * 1e3 / L,
+                config=dict(workload=WORKLOAD,
+                            note="CPU port of the reference algorithm (oracle/); the Swift+MLX reference cannot be built here. Each "
+                                 "timed step is ONE of the 48 blocks at the full shapes; value = 1 / (48 x that) -- extrapolated, so "
+                                 "ms_per_step x steps exceeds the wall time of this run by design; full_step_s is one true 48-block step"),
+                cpu_baseline=dict(value=1.0 / sec, unit="steps/s", cores=cores, kind="port", sample=desc, extrapolated=True,
+                                  full_step_s=full, full_step_steps_per_s=(1.0 / full) if isinstance(full, float) else None),
                 e2e=dict(value=1.0 / sec, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def _unit_rms(t):
+    return (t / t.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def parity_vs_oracle(local_rank):
+    """The kernels the benchmark times, checked against the CPU oracle inside the benchmark process: (i) a 2-block prefix of
+    the model at the config-2 shapes (N=1536, S=1024, D=4096 -- same tile fits, fused q|k|v, attention shapes as the timed
+    48-block run), (ii) the decoder's real channel plan (base 1024, 5 blocks per stage) on a small latent."""
+    from oracle import ltx_oracle as O   # checker only
+    from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
+    out = {}
+    torch.set_num_threads(os.cpu_count() or 1)
+    F, H, W, N, S = CFG2["F"], CFG2["H"], CFG2["W"], CFG2["N"], CFG2["S"]
+    ocfg = O.DiTConfig(num_layers=2)
+    w = O.make_dit_weights(ocfg, 77)
+    g = torch.Generator().manual_seed(78)
+    lat = torch.randn(1, N, CIN, generator=g).bfloat16()
+    text = _unit_rms(torch.randn(1, S, CAP, generator=g))
+    sig = torch.tensor([0.725])
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = O.dit_forward(w, ocfg, lat.float(), text.float(), sig, None, (F, H, W))
+    t_oracle = time.perf_counter() - t0
+    c = LtxContext(LTXTransformerConfig(num_layers=2), local_rank)
+    c.load_weights(w)
+    c.finalize_weights()
+    got = c.dit_forward(lat, text, sig.numpy(), None, (F, H, W))
+    c.close()
+    err = _rel_l2(got, ref.numpy())
+    out["dit_prefix_2_blocks_cfg2_shape"] = dict(rel_l2_vs_oracle=err, tol=1e-2, ok=bool(err <= 1e-2 and np.isfinite(got).all()),
+                                                 oracle_cpu_s=t_oracle)
+    del w
+    vcfg = O.VAEConfig()
+    vw = O.make_vae_weights(vcfg, 79)
+    vw = {k: (O.bf16_round(v) if (k.endswith(".weight") and v.ndim >= 2) else v) for k, v in vw.items()}
+    z = torch.randn(1, 128, 2, 4, 6, generator=g)
+    with torch.no_grad():
+        fref = O.decode_video(vw, vcfg, z)
+    c = LtxContext(LTXTransformerConfig(num_layers=1, num_attention_heads=1), local_rank)
+    c.load_weights(vw, prefix="vae.")
+    c.finalize_weights()
+    fr = c.vae_decode(z[0].numpy())
+    c.close()
+    p = float(O.psnr(torch.from_numpy(fr), fref))
+    out["vae_full_channel_plan"] = dict(psnr_db_vs_oracle=p, bound_db=40.0, ok=bool(p >= 40.0), latent="2x4x6 (9 frames of 128x192)")
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import ltx_video_swift_mlx_b200  # noqa: F401
     from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig, make_flags
     from ltx_video_swift_mlx_b200.scheduler import LTXScheduler
+    from ltx_video_swift_mlx_b200 import dist as ltxdist
 
     torch.cuda.set_device(local_rank)
     dist = None
@@ -171,24 +279,84 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
     ctx = LtxContext(LTXTransformerConfig(), local_rank)
-    ctx.init_random_weights(3, seed=1234)   # one model; the replicas differ in noise and text
+    ctx.init_random_weights(3, seed=1234)   # one model on every rank: sequence parallelism shards one video's tokens
     ctx.finalize_weights()
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     F, H, W, N, S = CFG2["F"], CFG2["H"], CFG2["W"], CFG2["N"], CFG2["S"]
-    g = torch.Generator().manual_seed(1236 + rank)
+    g = torch.Generator().manual_seed(1236)          # same video on every rank
     noise = torch.randn(1, CIN, F, H, W, generator=g)
-    text = torch.randn(1, S, CAP, generator=g)
-    text = (text / text.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()          # unit-RMS rows, mask all ones
+    text = _unit_rms(torch.randn(1, S, CAP, generator=g))          # unit-RMS rows, mask all ones
+    ntext = _unit_rms(torch.randn(1, S, CAP, generator=g))
     sigmas = LTXScheduler().set_timesteps(8, distilled=True, latent_token_count=N)
     pairs = [(sigmas[i], sigmas[i + 1]) for i in range(len(sigmas) - 1)]
+    dev_sig = LTXScheduler().set_timesteps(40, distilled=False, latent_token_count=N)
+    parity = {}
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- resident path (value)
+    def max_over_ranks(v):
+        if dist is None:
+            return float(v)
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(flag):
+        if dist is None:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def ev_time(c, strm, fn, reps, warm=0):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(strm)
+        for i in range(reps):
+            fn()
+        b.record(strm)
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    def full_denoise(c, guided=False, n_steps=None):
+        """The whole schedule from the seeded noise; returns the final latent (host)."""
+        if guided:
+            c.denoise_begin(noise[0].numpy(), (F, H, W), dev_sig[0], text, None, ntext, None)
+            for i in range(n_steps or 3):
+                c.denoise_step(dev_sig[i], dev_sig[i + 1], i, cfg_scale=4.0, stg_scale=0.5, stg_blocks=(29,))
+        else:
+            c.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
+            for i, (sg, sn) in enumerate(pairs[:n_steps] if n_steps else pairs):
+                c.denoise_step(sg, sn, i)
+        return c.denoise_get_latent()
+
+    # ---------------- N > 1: the single-GPU answers this rank will hold the multi-GPU modes to (same inputs, same device)
+    if world > 1:
+        single_plain = full_denoise(ctx)
+        single_guided = full_denoise(ctx, guided=True)
+        # replicas: N independent videos, one per GPU (weak scaling, no communication) -- reported as an extra
+        ctx.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
+        rep_no = [0]
+
+        def rep_step():
+            sg, sn = pairs[rep_no[0] % len(pairs)]
+            ctx.denoise_step(sg, sn, rep_no[0] % len(pairs))
+            rep_no[0] += 1
+        t_rep = ev_time(ctx, stream, rep_step, max(4, min(args.steps, 8)), warm=3)
+        ltxdist.init_context(ctx, sp_size=world, pass_groups=1)
+        dist_plain = full_denoise(ctx)
+        err = _rel_l2(dist_plain, single_plain)
+        parity["ulysses_vs_single_gpu"] = dict(rel_l2=err, bit_identical=bool(np.array_equal(dist_plain, single_plain)), tol=1e-3,
+                                               ok=all_ok(err <= 1e-3 and np.isfinite(dist_plain).all()), steps=len(pairs),
+                                               peer_memory=bool(ctx.lib.ltx_dist_p2p_active(ctx.handle)))
+
+    # ---------------- resident path (value): one video; Ulysses over all ranks when world > 1
     ctx.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
     step_no = [0]
 
@@ -211,14 +379,11 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     launches = (ctx.launch_count - l0) // args.steps
-    ms = e0.elapsed_time(e1)
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
-    value = world * 1e3 / ms_per_step
+    value = 1e3 / ms_per_step
+    timed_latent = ctx.denoise_get_latent()
+    parity["timed_latent_finite"] = all_ok(bool(np.isfinite(timed_latent).all() and np.abs(timed_latent).max() > 0))
 
     # ---------------- profiled pass: per-kernel-class device time of one step (not part of the timed value)
     ctx.set_profiling(True)
@@ -234,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
     ts = torch.zeros(1).pin_memory()
     from ltx_video_swift_mlx_b200 import latent_utils
     shape = latent_utils.VideoLatentShape(1, CIN, F, H, W)
-    flags = make_flags(context_key=4242)
+    flags = make_flags(context_key=ctx.new_context_key())
 
     def host_step(i):
         sg, sn = pairs[i % len(pairs)]
@@ -251,113 +416,144 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.steps):
         host_step(i)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     h2d = N * CIN * 2 + 4 + 2 * N * CIN * 4          # bf16 tokens + sigma ; latent + velocity for the Euler call
     d2h = N * CIN * 4 + N * CIN * 4                  # velocity ; updated latent
+    parity["e2e_latent_finite"] = all_ok(bool(torch.isfinite(lat32).all()))
 
-    # ---------------- VAE decode (secondary metric), resident + host ABI
-    lat_dev = torch.randn(CIN, F, H, W, device="cuda")
-    frames_dev = torch.empty(8 * (F - 1) + 1, 32 * H, 32 * W, 3, device="cuda")
+    extras = {}
+    if world > 1:
+        extras["replicas"] = dict(desc=f"{world} independent videos, one per GPU (weak scaling, no communication)",
+                                  ms_per_step=t_rep, steps_per_s=world * 1e3 / t_rep)
+        extras["ulysses"] = dict(desc=f"the headline: one video, sequence-parallel sp={world}", ms_per_step=ms_per_step,
+                                 kernel_classes={k: v for k, v in prof.items() if v["launches"]})
+
+    # ---------------- VAE decode (secondary metric), resident + host ABI; temporally sharded over the ranks when world > 1
+    n_frames = 8 * (F - 1) + 1
+    lat_dev = torch.randn(CIN, F, H, W, generator=torch.Generator().manual_seed(55)).cuda()
+    frames_dev = torch.empty(n_frames, 32 * H, 32 * W, 3, device="cuda")
     torch.cuda.synchronize()
-    for _ in range(3):
-        ctx.vae_decode_dev(lat_dev.data_ptr(), (F, H, W), frames_dev.data_ptr())
-    barrier()
-    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(3, min(args.steps, 10))
-    v0.record(stream)
-    for _ in range(reps):
-        ctx.vae_decode_dev(lat_dev.data_ptr(), (F, H, W), frames_dev.data_ptr())
-    v1.record(stream)
-    barrier()
-    vae_ms = v0.elapsed_time(v1) / reps
+    vae_ms = ev_time(ctx, stream, lambda: ctx.vae_decode_dev(lat_dev.data_ptr(), (F, H, W), frames_dev.data_ptr()),
+                     max(3, min(args.steps, 10)), warm=3)
     ctx.set_profiling(True)
     ctx.vae_decode_dev(lat_dev.data_ptr(), (F, H, W), frames_dev.data_ptr())
     vprof = ctx.get_profile()
     ctx.set_profiling(False)
+    torch.cuda.synchronize()
+    frames_multi = frames_dev.cpu().numpy() if world > 1 else None
     lat_cpu = lat_dev.cpu().numpy()
-    frames_host = ctx.pinned_empty((8 * (F - 1) + 1, 32 * H, 32 * W, 3))      # page-locked output buffer (ltx_host_alloc)
+    frames_host = ctx.pinned_empty((n_frames, 32 * H, 32 * W, 3))      # page-locked output buffer (ltx_host_alloc)
     ctx.vae_decode(lat_cpu, out=frames_host)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(3):
         ctx.vae_decode(lat_cpu, out=frames_host)
-    vae_e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
-    n_frames = 8 * (F - 1) + 1
+    vae_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 3)
+    parity["vae_frames_in_range"] = all_ok(bool(np.isfinite(frames_host).all() and frames_host.min() >= 0 and frames_host.max() <= 1
+                                                and frames_host.std() > 0))
 
-    # ---------------- extra single-GPU reference points for the multi-GPU modes (guided step, 121-frame decode)
-    extras = {}
-    _, ntext = None, torch.randn(1, S, CAP, generator=g)
-    ntext = (ntext / ntext.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
-    dev_sig = LTXScheduler().set_timesteps(40, distilled=False, latent_token_count=N)
-
-    def time_guided(nsteps=3):
+    def time_guided(c, strm, nsteps=3):
         """BASELINE config 3: dev schedule, CFG 4.0 + STG 0.5 at block 29 -> 3 forwards per step."""
-        ctx.denoise_begin(noise[0].numpy(), (F, H, W), dev_sig[0], text, None, ntext, None)
+        c.denoise_begin(noise[0].numpy(), (F, H, W), dev_sig[0], text, None, ntext, None)
         for i in range(2):
-            ctx.denoise_step(dev_sig[i], dev_sig[i + 1], i, cfg_scale=4.0, stg_scale=0.5, stg_blocks=(29,))
+            c.denoise_step(dev_sig[i], dev_sig[i + 1], i, cfg_scale=4.0, stg_scale=0.5, stg_blocks=(29,))
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
+        a.record(strm)
         for i in range(2, 2 + nsteps):
-            ctx.denoise_step(dev_sig[i], dev_sig[i + 1], i, cfg_scale=4.0, stg_scale=0.5, stg_blocks=(29,))
-        b.record(stream)
+            c.denoise_step(dev_sig[i], dev_sig[i + 1], i, cfg_scale=4.0, stg_scale=0.5, stg_blocks=(29,))
+        b.record(strm)
         barrier()
-        t = a.elapsed_time(b) / nsteps
-        if dist is not None:
-            tt = torch.tensor([t], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t = float(tt.item())
-        return t
+        return max_over_ranks(a.elapsed_time(b) / nsteps)
 
-    def time_vae121(reps=2):
+    lat121 = torch.randn(CIN, 16, H, W, generator=torch.Generator().manual_seed(77))
+
+    def time_vae121(c, strm, reps=2, fetch=False):
         """BASELINE config 4: 768x512x121 frames (latent 16x16x24)."""
-        lat = torch.randn(CIN, 16, H, W, generator=torch.Generator().manual_seed(77)).cuda()
+        lat = lat121.cuda()
         out = torch.empty(121, 32 * H, 32 * W, 3, device="cuda")
         torch.cuda.synchronize()
-        ctx.vae_decode_dev(lat.data_ptr(), (16, H, W), out.data_ptr())
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(reps):
-            ctx.vae_decode_dev(lat.data_ptr(), (16, H, W), out.data_ptr())
-        b.record(stream)
-        barrier()
-        t = a.elapsed_time(b) / reps
-        if dist is not None:
-            tt = torch.tensor([t], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t = float(tt.item())
+        t = ev_time(c, strm, lambda: c.vae_decode_dev(lat.data_ptr(), (16, H, W), out.data_ptr()), reps, warm=1)
+        fr = out.cpu().numpy() if fetch else None
         del lat, out
-        return t
+        return t, fr
+
+    def cfg5_two_stage(sp):
+        """BASELINE config 5 (generateVideoTwoStage, P/LTXPipeline.swift:2420-2709), int8 group-64 weights: stage 1 at
+        768x512x257 (N = 12 672, 8 distilled steps) -> latent upscale 2x + AdaIN + re-noise on the device -> stage 2 at
+        1536x1024x257 (N = 50 688, 3 refinement steps).  sp > 1: Ulysses over all ranks, the stage switch replicated."""
+        from ltx_video_swift_mlx_b200.scheduler import STAGE_2_DISTILLED_SIGMA_VALUES as S2
+        F5, H5, W5 = 33, 16, 24
+        cq = LtxContext(LTXTransformerConfig(), local_rank)
+        cq.init_random_weights(1 | 2 | 8, seed=99)   # DiT + VAE (latent statistics) + latent upscaler; same seed on every rank
+        cq.finalize_weights(quant_bits=8)
+        if sp > 1:
+            ltxdist.init_context(cq, sp_size=sp, pass_groups=1)
+        sq = torch.cuda.ExternalStream(cq.stream, device=torch.device("cuda", local_rank))
+        g5 = torch.Generator().manual_seed(177)
+        n1 = torch.randn(CIN, F5, H5, W5, generator=g5)
+        n2 = torch.randn(CIN, F5, 2 * H5, 2 * W5, generator=g5)
+        s1 = LTXScheduler().set_timesteps(8, distilled=True, latent_token_count=F5 * H5 * W5)
+        res = {}
+
+        def timed(fn):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(sq)
+            fn()
+            b.record(sq)
+            barrier()
+            return max_over_ranks(a.elapsed_time(b))
+        cq.denoise_begin(n1.numpy(), (F5, H5, W5), s1[0], text, None)
+        cq.denoise_step(s1[0], s1[1], 0)       # untimed: builds the RoPE table, the text cache and the peer buffers
+        t1 = timed(lambda: [cq.denoise_step(s1[i], s1[i + 1], i) for i in range(1, 8)]) / 7
+        tu = timed(lambda: cq.denoise_upscale_stage(n2.numpy(), S2[0], 1.0))
+        cq.denoise_step(S2[0], S2[1], 0)       # first stage-2 step builds the stage-2 RoPE table and buffers
+        t2 = timed(lambda: [cq.denoise_step(S2[i], S2[i + 1], i) for i in range(1, 3)]) / 2
+        cq.set_profiling(True)
+        cq.denoise_step(S2[1], S2[2], 1)
+        p5 = cq.get_profile()
+        cq.set_profiling(False)
+        lat = cq.denoise_get_latent()
+        fl1, fl2 = dit_flops_per_step(F5 * H5 * W5, S), dit_flops_per_step(4 * F5 * H5 * W5, S)
+        res.update(stage1_ms_per_step=t1, stage1_tokens=F5 * H5 * W5, stage1_tflops=fl1 / (t1 * 1e-3) / 1e12,
+                   upscale_switch_ms=tu, stage2_ms_per_step=t2, stage2_tokens=4 * F5 * H5 * W5,
+                   stage2_tflops=fl2 / (t2 * 1e-3) / 1e12, total_ms_8_plus_3_steps=8 * t1 + tu + 3 * t2,
+                   final_latent_finite=all_ok(bool(np.isfinite(lat).all() and lat.std() > 0)),
+                   peer_memory=bool(cq.lib.ltx_dist_p2p_active(cq.handle)) if sp > 1 else None,
+                   stage2_kernel_classes={k: v for k, v in p5.items() if v["launches"]})
+        if sp > 1:
+            cq.dist_shutdown()
+        cq.close()
+        return res
 
     if world == 1:
-        # qint8 weights (the reference's --transformer-quant qint8 path): same step, dequant-fused GEMMs
+        # qint8 weights (the reference's --transformer-quant qint8 path): same step on int8 group-64 weights
         try:
             cq = LtxContext(LTXTransformerConfig(), local_rank)
             cq.init_random_weights(1, seed=99)
             cq.finalize_weights(quant_bits=8)
             sq = torch.cuda.ExternalStream(cq.stream, device=torch.device("cuda", local_rank))
             cq.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
-            for i in range(3):
-                cq.denoise_step(pairs[i][0], pairs[i][1], i)
-            cq.sync()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(sq)
-            for i in range(6):
-                cq.denoise_step(pairs[i][0], pairs[i][1], i)
-            b.record(sq)
-            cq.sync()
-            tq = a.elapsed_time(b) / 6
-            extras["qint8"] = dict(desc="same step with int8 group-64 weights (M > 256: weight converted once per GEMM into an L2-resident bf16 panel + bf16 pair kernel; M <= 256: dequant-fused tcgen05 GEMM)", ms_per_step=tq,
-                                   steps_per_s=1e3 / tq)
+            qn = [0]
+
+            def qstep():
+                cq.denoise_step(pairs[qn[0] % len(pairs)][0], pairs[qn[0] % len(pairs)][1], qn[0] % len(pairs))
+                qn[0] += 1
+            tq = ev_time(cq, sq, qstep, 6, warm=3)
+            cq.set_profiling(True)
+            qstep()
+            pq = cq.get_profile()
+            cq.set_profiling(False)
+            lq = cq.denoise_get_latent()
+            extras["qint8"] = dict(desc="same step with int8 group-64 weights (dequant-fused tcgen05 GEMMs)", ms_per_step=tq,
+                                   steps_per_s=1e3 / tq, latent_finite=bool(np.isfinite(lq).all()),
+                                   kernel_classes={k: v for k, v in pq.items() if v["launches"]})
             cq.close()
         except Exception as e:   # report, do not hide
             extras["qint8"] = dict(error=str(e))
         # ---- the rows either side of the denoise loop (SURVEY 8f): dual audio/video model, VAE encoder, latent upscaler
-        def ev_time(fn, strm, reps=3, warm=1):
+        def ev1(fn, strm, reps=3, warm=1):
             for _ in range(warm):
                 fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -386,14 +582,14 @@ def run_ours(args, rank, world, local_rank):
                                                     sg2.data_ptr(), sg2.data_ptr() + 4, None, None, N, Ta, S, F, H, W, 77,
                                                     ov.data_ptr(), oa.data_ptr()))
             av_step()
-            ta_ms = ev_time(av_step, sa, reps=4)
+            ta_ms = ev1(av_step, sa, reps=4)
             ca.set_profiling(True)
             av_step()
             pa = ca.get_profile()
             ca.set_profiling(False)
             extras["av_dual_forward"] = dict(
                 desc=f"LTX2Transformer (dual audio/video, 48 blocks, D=4096 + Da=2048) forward, N={N} video + {Ta} audio tokens, S={S}",
-                ms_per_forward=ta_ms, forwards_per_s=1e3 / ta_ms,
+                ms_per_forward=ta_ms, forwards_per_s=1e3 / ta_ms, outputs_finite=bool(torch.isfinite(ov).all() and torch.isfinite(oa).all()),
                 kernel_classes={k: v for k, v in pa.items() if v["launches"]})
             ca.close()
             del vl, al, tx, ov, oa
@@ -411,9 +607,9 @@ def run_ours(args, rank, world, local_rank):
             lat1 = torch.randn(CIN, 33, H, W, generator=g).cuda()     # stage-1 latent of BASELINE config 5 (768x512x257)
             lat2 = torch.empty(CIN, 33, 2 * H, 2 * W, device="cuda")
             torch.cuda.synchronize()
-            t_img = ev_time(lambda: ce.vae_encode_dev(px.data_ptr(), (1, 32 * H, 32 * W), zl.data_ptr()), se_)
-            t_clip = ev_time(lambda: ce.vae_encode_dev(px25.data_ptr(), (8 * (F - 1) + 1, 32 * H, 32 * W), zl25.data_ptr()), se_)
-            t_up = ev_time(lambda: ce.upscale_latent_dev(lat1.data_ptr(), (33, H, W), lat2.data_ptr()), se_)
+            t_img = ev1(lambda: ce.vae_encode_dev(px.data_ptr(), (1, 32 * H, 32 * W), zl.data_ptr()), se_)
+            t_clip = ev1(lambda: ce.vae_encode_dev(px25.data_ptr(), (8 * (F - 1) + 1, 32 * H, 32 * W), zl25.data_ptr()), se_)
+            t_up = ev1(lambda: ce.upscale_latent_dev(lat1.data_ptr(), (33, H, W), lat2.data_ptr()), se_)
             ce.set_profiling(True)
             ce.upscale_latent_dev(lat1.data_ptr(), (33, H, W), lat2.data_ptr())
             pu = ce.get_profile()
@@ -426,87 +622,75 @@ def run_ours(args, rank, world, local_rank):
             del px, zl, px25, zl25, lat1, lat2
         except Exception as e:
             extras["vae_encode"] = dict(error=str(e))
-        tg = time_guided()
-        tv = time_vae121()
+        tg = time_guided(ctx, stream)
+        tv, _ = time_vae121(ctx, stream)
         extras["guided_cfg3"] = dict(desc="dev CFG 4.0 + STG 0.5 (3 forwards/step), 1 GPU", ms_per_step=tg, steps_per_s=1e3 / tg)
         extras["vae_121f"] = dict(desc="VAE decode 768x512x121f, 1 GPU", ms_per_decode=tv, frames_per_s=121e3 / tv)
+        if not args.no_parity:
+            try:
+                parity.update(parity_vs_oracle(local_rank))
+            except Exception as e:   # report, do not hide
+                parity["oracle_check_error"] = str(e)
+        if not args.no_cfg5:
+            ctx.close()
+            torch.cuda.empty_cache()
+            try:
+                extras["cfg5_two_stage"] = dict(desc="BASELINE config 5, int8 weights, 1 GPU: stage 1 N=12672 x 8 steps, device-resident "
+                                                     "upscale + AdaIN + re-noise, stage 2 N=50688 x 3 steps", **cfg5_two_stage(1))
+            except Exception as e:
+                extras["cfg5_two_stage"] = dict(error=str(e))
     else:
-        from ltx_video_swift_mlx_b200 import dist as ltxdist
-        # (1) Ulysses: ONE video's step strong-scaled over all ranks
-        ltxdist.init_context(ctx, sp_size=world, pass_groups=1)
-        ctx.denoise_begin(noise[0].numpy(), (F, H, W), sigmas[0], text, None)
-        for i in range(3):
-            ctx.denoise_step(pairs[i][0], pairs[i][1], i)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for i in range(args.steps):
-            sg, sn = pairs[i % len(pairs)]
-            ctx.denoise_step(sg, sn, i % len(pairs))
-        b.record(stream)
-        barrier()
-        t = torch.tensor([a.elapsed_time(b) / args.steps], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ctx.set_profiling(True)
-        ctx.denoise_step(pairs[0][0], pairs[0][1], 0)
-        sp_prof = ctx.get_profile()
-        ctx.set_profiling(False)
-        extras["ulysses"] = dict(desc=f"one video, sequence-parallel sp={world} (strong scaling)", ms_per_step=float(t.item()),
-                                 steps_per_s=1e3 / float(t.item()), kernel_classes={k: v for k, v in sp_prof.items() if v["launches"]})
-        # temporally sharded VAE decode of the 121-frame clip on the same communicator
-        tv = time_vae121()
+        # sharded VAE on the same communicator: 25 frames (above, `vae`) and the 121-frame clip, both against this rank's 1-GPU decode
+        tv, fr121 = time_vae121(ctx, stream, fetch=True)
+        ctx.dist_shutdown()
+        single = torch.empty(n_frames, 32 * H, 32 * W, 3, device="cuda")
+        ctx.vae_decode_dev(lat_dev.data_ptr(), (F, H, W), single.data_ptr())
+        torch.cuda.synchronize()
+        s25 = single.cpu().numpy()
+        _, s121 = time_vae121(ctx, stream, reps=1, fetch=True)
+        d25, d121 = float(np.abs(frames_multi - s25).max()), float(np.abs(fr121 - s121).max())
+        parity["vae_sharded_vs_single_gpu"] = dict(max_abs_diff_25f=d25, max_abs_diff_121f=d121,
+                                                   bit_identical=bool(d25 == 0.0 and d121 == 0.0), tol=1e-4,
+                                                   ok=all_ok(d25 <= 1e-4 and d121 <= 1e-4))
+        del single, s25, s121, fr121
         extras["vae_121f_sharded"] = dict(desc=f"VAE decode 768x512x121f, {world} temporal shards + halo exchange",
                                           ms_per_decode=tv, frames_per_s=121e3 / tv)
+        # pass-parallel guidance (BASELINE config 3): the conditional / unconditional / STG forwards on different GPU groups,
+        # each group sequence-parallel over world / groups GPUs; best grouping reported, every grouping checked
+        best = None
+        for groups in (2, 3):
+            if world % groups or HEADS % (world // groups):
+                continue
+            ltxdist.init_context(ctx, sp_size=world // groups, pass_groups=groups)
+            out_g = full_denoise(ctx, guided=True)
+            err = _rel_l2(out_g, single_guided)
+            tg = time_guided(ctx, stream)
+            ctx.dist_shutdown()
+            rec = dict(groups=groups, sp=world // groups, ms_per_step=tg, steps_per_s=1e3 / tg, rel_l2_vs_single_gpu=err,
+                       ok=all_ok(err <= 1e-3))
+            extras.setdefault("guided_cfg3_groupings", []).append(rec)
+            if best is None or tg < best["ms_per_step"]:
+                best = rec
+        ltxdist.init_context(ctx, sp_size=world, pass_groups=1)     # all passes sequentially, each over all GPUs
+        out_g = full_denoise(ctx, guided=True)
+        err = _rel_l2(out_g, single_guided)
+        tg = time_guided(ctx, stream)
         ctx.dist_shutdown()
-        # (2) pass-parallel guidance (BASELINE config 3): conditional (+ STG, sharing the prefix) on one GPU group, the
-        # unconditional pass on the other; each group runs its forwards sequence-parallel over world/2 GPUs
-        groups = 2
-        ltxdist.init_context(ctx, sp_size=world // groups, pass_groups=groups)
-        tg = time_guided()
-        extras["guided_cfg3_pass_parallel"] = dict(
-            desc=f"dev CFG 4.0 + STG 0.5, passes split over {groups} GPU groups x Ulysses sp={world // groups}",
-            ms_per_step=tg, steps_per_s=1e3 / tg)
-        ctx.dist_shutdown()
-        # (3) BASELINE config 5, stage 2: 1536x1024x257 frames -> N = 33*32*48 = 50688 tokens, int8 weights, the 3-step
-        # refinement schedule, Ulysses over all GPUs (the upscaler is out of scope: seeded random latent of that shape)
+        rec = dict(groups=1, sp=world, ms_per_step=tg, steps_per_s=1e3 / tg, rel_l2_vs_single_gpu=err, ok=all_ok(err <= 1e-3))
+        extras.setdefault("guided_cfg3_groupings", []).append(rec)
+        if best is None or tg < best["ms_per_step"]:
+            best = rec
+        extras["guided_cfg3_pass_parallel"] = dict(desc="dev CFG 4.0 + STG 0.5 (BASELINE config 3), best grouping of passes x Ulysses", **best)
+        parity["guided_pass_groups_vs_single_gpu"] = dict(ok=all(r["ok"] for r in extras["guided_cfg3_groupings"]), tol=1e-3,
+                                                          worst_rel_l2=max(r["rel_l2_vs_single_gpu"] for r in extras["guided_cfg3_groupings"]))
         if world >= 4 and not args.no_cfg5:
+            ctx.close()
+            torch.cuda.empty_cache()
             try:
-                from ltx_video_swift_mlx_b200.scheduler import STAGE_2_DISTILLED_SIGMA_VALUES as S2
-                ctx.close()
-                torch.cuda.empty_cache()
-                F5, H5, W5 = 33, 32, 48
-                cq = LtxContext(LTXTransformerConfig(), local_rank)
-                cq.init_random_weights(1, seed=99)          # same seed on every rank: sequence parallelism shards one model
-                cq.finalize_weights(quant_bits=8)
-                ltxdist.init_context(cq, sp_size=world, pass_groups=1)
-                sq = torch.cuda.ExternalStream(cq.stream, device=torch.device("cuda", local_rank))
-                n5 = torch.randn(CIN, F5, H5, W5, generator=torch.Generator().manual_seed(77))
-                cq.denoise_begin(n5.numpy(), (F5, H5, W5), S2[0], text, None)
-                cq.denoise_step(S2[0], S2[1], 0)                # builds the RoPE table, the text cache and the peer buffers
-                barrier()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(sq)
-                for i in range(3):
-                    cq.denoise_step(S2[i], S2[i + 1], i)
-                b.record(sq)
-                barrier()
-                t5 = torch.tensor([a.elapsed_time(b) / 3], device="cuda")
-                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
-                cq.set_profiling(True)
-                cq.denoise_step(S2[0], S2[1], 0)
-                p5 = cq.get_profile()
-                cq.set_profiling(False)
-                fl5 = dit_flops_per_step(F5 * H5 * W5, S)
-                extras["cfg5_stage2_qint8_ulysses"] = dict(
-                    desc=f"two-stage refinement step at 1536x1024x257f (N={F5 * H5 * W5}), int8 weights, Ulysses sp={world}, "
-                         f"peer-memory exchange={bool(cq.lib.ltx_dist_p2p_active(cq.handle))}",
-                    ms_per_step=float(t5.item()), steps_per_s=1e3 / float(t5.item()),
-                    aggregate_tflops=fl5 / (float(t5.item()) * 1e-3) / 1e12,
-                    kernel_classes={k: v for k, v in p5.items() if v["launches"]})
-                cq.dist_shutdown()
-                cq.close()
+                extras["cfg5_two_stage"] = dict(desc=f"BASELINE config 5, int8 weights, Ulysses sp={world}: stage 1 N=12672 x 8 steps, "
+                                                     "upscale + AdaIN + re-noise, stage 2 N=50688 x 3 steps", **cfg5_two_stage(world))
             except Exception as e:   # report, do not hide
-                extras["cfg5_stage2_qint8_ulysses"] = dict(error=str(e))
+                extras["cfg5_two_stage"] = dict(error=str(e))
 
     if rank != 0:
         if dist is not None:
@@ -514,43 +698,59 @@ def run_ours(args, rank, world, local_rank):
         return
 
     pk = peaks()
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (FFN-in launch), if present
+    # DRAM traffic of the dominant kernel: bytes of ONE FFN-in launch from the newest committed `ncu --set full` capture
     traffic, traffic_note = None, None
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r01c_gemm_pair_ffn_in_ncu_raw.csv"))))
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_gemm*ffn_in_ncu_raw.csv")))
+        src = cands[-1]
+        rows = list(csv.reader(open(src)))
         hdr, units, last = rows[0], rows[1], rows[-1]
 
         def _bytes(k):
             v, u = float(last[hdr.index(k)].replace(",", "")), units[hdr.index(k)]
             return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         traffic = _bytes("dram__bytes_read.sum") + _bytes("dram__bytes_write.sum")
-        traffic_note = "bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6) from profiles/r01c_gemm_pair_ffn_in_ncu_raw.csv"
+        traffic_note = ("bytes of ONE FFN-in launch (M=1536,N=16384,K=4096; algorithmic 197.1e6), read from the committed capture "
+                        f"profiles/{os.path.basename(src)} -- a citation of that capture's tree, not measured in this run")
     except Exception:
         pass
     gemm = prof["gemm"]
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     conv = vprof["conv3d"]
     cpu_sec, cores, desc = cpu_port_step_seconds(1, 1) if not args.no_cpu_baseline else (float("nan"), 0, "skipped")
+    cpu_full = None
+    if world == 1 and not args.no_cpu_baseline and not args.no_cpu_full_step:
+        try:
+            cpu_full = cpu_port_full_step_seconds()
+        except Exception as e:
+            cpu_full = f"failed: {e}"
+    class_ms = sum(v["ms"] for v in prof.values())
+    parity["all_ok"] = all((v if isinstance(v, bool) else v.get("ok", True)) for v in parity.values() if isinstance(v, (bool, dict)))
     line = dict(
         metric="dit_steps_per_s", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload="LTX-2 distilled 13B-video DiT denoise step (BASELINE config 2): 768x512x25f -> N=1536 tokens, "
-                             "S=1024 text tokens, 48 blocks, D=4096, 32 heads, bf16 weights random-init, fp32 residual stream",
-                    global_batch=world, l2="weights per step (26 GB) >> 126 MB L2; no flush needed",
-                    parallelism="replicas" if world > 1 else "single",
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload=WORKLOAD, weights="bf16 random-init on the device, fp32 residual stream",
+                    global_batch=1, l2="weights per step (26 GB) >> 126 MB L2; no flush needed",
+                    parallelism=f"ulysses sp={world} (one video, tokens sharded, heads sharded inside self-attention)" if world > 1 else "single",
                     flops_per_step=dit_flops_per_step(N, S), step_tflops=dit_flops_per_step(N, S) / (ms_per_step * 1e-3) / 1e12),
-        e2e=dict(value=world * 1e3 / e2e_ms, unit="steps/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+        e2e=dict(value=1e3 / e2e_ms, unit="steps/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  path="ltx_dit_forward + ltx_guided_euler_step with pinned host buffers (text cached by context_key)"),
         gpu_launches=int(launches),
-        roofline=dict(bound="tensor", kernel="gemm_bf16_2cta / gemm_bf16_tcgen05 (all GEMM launches of one step)", achieved=achieved,
+        parity=parity,
+        roofline=dict(bound="tensor", kernel="gemm_bf16_2cta / gemm_bf16_tcgen05 / gemm_swapab (all GEMM launches of one step)", achieved=achieved,
                       peak=pk["tflops_sustained"], unit="TFLOP/s", frac=achieved / pk["tflops_sustained"], traffic=traffic,
                       traffic_note=traffic_note,
                       peak_source=pk["source"] + ", sustained bf16", launches=gemm["launches"], ms=gemm["ms"]),
         kernel_classes={k: v for k, v in prof.items() if v["launches"]},
-        cpu_baseline=dict(value=1.0 / cpu_sec if cpu_sec == cpu_sec else None, unit="steps/s", cores=cores, kind="port", sample=desc),
-        vae=dict(metric="vae_frames_per_s", value=world * n_frames / (vae_ms * 1e-3), unit="frames/s", ms_per_decode=vae_ms,
+        step_minus_class_sum_ms=ms_per_step - class_ms,
+        cpu_baseline=dict(value=1.0 / cpu_sec if cpu_sec == cpu_sec else None, unit="steps/s", cores=cores, kind="port", sample=desc,
+                          extrapolated=True, full_step_s=cpu_full,
+                          full_step_steps_per_s=(1.0 / cpu_full) if isinstance(cpu_full, float) else None),
+        vae=dict(metric="vae_frames_per_s", value=n_frames / (vae_ms * 1e-3), unit="frames/s", ms_per_decode=vae_ms,
                  frames=n_frames, e2e_value=n_frames / (vae_e2e_ms * 1e-3), e2e_ms=vae_e2e_ms,
+                 parallelism=f"{min(world, F)} temporal shards + per-conv halo exchange" if world > 1 else "single",
                  conv_tflops=conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else None,
                  conv_frac_of_peak=(conv["flops"] / (conv["ms"] * 1e-3) / 1e12) / pk["tflops_sustained"] if conv["ms"] > 0 else None,
                  kernel_classes={k: v for k, v in vprof.items() if v["launches"]}),
@@ -568,8 +768,10 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cfg5", action="store_true", help="skip the 50688-token int8 Ulysses extra of the >= 4-GPU runs")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the two-stage 1536x1024x257 extra")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full-step", action="store_true", help="skip the one true 48-block CPU step (~26 s)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-process oracle checks (N = 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

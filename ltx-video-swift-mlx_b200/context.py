@@ -269,7 +269,14 @@ class LtxContext:
         return ov, oa
 
     def clear_caches(self):
+        """clearRoPECache + the text-projection caches of both streams (video and, in the dual model, audio)."""
         self._check(self.lib.ltx_dit_clear_caches(self.handle))
+
+    def new_context_key(self) -> int:
+        """A context_key no earlier call on this context has used: the host-seam loops take one per prompt per generation, so a
+        second generation never finds the first one's projected text under its key."""
+        self._key_serial = getattr(self, "_key_serial", 0) + 1
+        return 0x6000000000000000 + self._key_serial
 
     # ------------------------------------------------------------------ guidance + Euler
     def guided_euler_step(self, latent: np.ndarray, v_cond, v_uncond=None, v_stg=None, v_prev=None, use_prev: bool = False,

@@ -33,6 +33,43 @@ void h2d(ltx_ctx* c, DevBuf& buf, const void* host, size_t bytes) {
   LTX_CUDA(cudaMemcpyAsync(buf.ptr, host, bytes, cudaMemcpyHostToDevice, c->stream));
 }
 
+// A context_key promises "same text as last time under this key".  The host-buffer entry points can check that promise
+// cheaply: a sampled 64-bit hash of the embedding (512 strided 8-byte words + both ends) and of the whole mask is recorded
+// with the cache entry; a later call whose buffers hash differently under the same key rebuilds the entry instead of silently
+// reusing another prompt's K / V (the device-pointer entry points cannot look at their inputs and trust the key).
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+uint64_t host_text_fingerprint(const void* ctx, size_t bytes, const int32_t* mask, size_t mask_n) {
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, &bytes, sizeof bytes);
+  const uint8_t* p = static_cast<const uint8_t*>(ctx);
+  if (bytes <= 8192) {
+    h = fnv1a(h, p, bytes);
+  } else {
+    h = fnv1a(h, p, 64);
+    h = fnv1a(h, p + bytes - 64, 64);
+    const size_t words = bytes / 8, step = words / 512;
+    for (size_t i = 0; i < 512; ++i) h = fnv1a(h, p + (i * step) * 8, 8);
+  }
+  if (mask) h = fnv1a(h, mask, mask_n * 4);
+  else h = fnv1a(h, &mask_n, 1);
+  return h ? h : 1;
+}
+// drop the entry cached under `key` if it was built from different host buffers
+void text_cache_guard(TextCache* slots, uint64_t key, uint64_t fp) {
+  if (key == 0) return;
+  for (int i = 0; i < 2; ++i)
+    if (slots[i].key == key && slots[i].fingerprint != 0 && slots[i].fingerprint != fp) { slots[i].key = 0; slots[i].fingerprint = 0; }
+}
+void text_cache_stamp(TextCache* slots, uint64_t key, uint64_t fp) {
+  if (key == 0) return;
+  for (int i = 0; i < 2; ++i)
+    if (slots[i].key == key) slots[i].fingerprint = fp;
+}
+
 }  // namespace
 
 extern "C" {
@@ -306,10 +343,14 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
     DevBuf& lat = c->api_lat;
     DevBuf& ctx = c->api_ctx;
     h2d(c, lat, latent, R * g.in_channels * dsize(latent_dtype));
+    const uint64_t key = flags ? flags->context_key : 0;
+    const size_t ctx_bytes = static_cast<size_t>(B) * S * g.caption_channels * dsize(context_dtype);
+    const uint64_t fp = key ? host_text_fingerprint(context, ctx_bytes, mask, static_cast<size_t>(B) * S) : 0;
+    text_cache_guard(c->text, key, fp);
     const bool cached = flags && flags->context_key != 0 &&
                         ((c->text[0].key == flags->context_key && c->text[0].B == B && c->text[0].S == S) ||
                          (c->text[1].key == flags->context_key && c->text[1].B == B && c->text[1].S == S));
-    if (!cached) h2d(c, ctx, context, static_cast<size_t>(B) * S * g.caption_channels * dsize(context_dtype));
+    if (!cached) h2d(c, ctx, context, ctx_bytes);
     h2d(c, c->ts_in, timesteps, (ts_per_token ? R : static_cast<size_t>(B)) * 4);
     const int32_t* mask_dev = nullptr;
     if (mask) {
@@ -319,6 +360,7 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
     c->vel.reserve(R * g.out_channels * 4);
     dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), ts_per_token, mask_dev, B, N, S, F,
                     H, W, flags, c->vel.as<float>());
+    text_cache_stamp(c->text, key, fp);
     LTX_CUDA(cudaMemcpyAsync(out_velocity, c->vel.ptr, R * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
   });
@@ -380,8 +422,14 @@ static int av_forward_host(ltx_ctx* c, const void* video_latent, ltx_dtype video
     }
     b[6].reserve(static_cast<size_t>(N) * g.out_channels * 4);
     b[7].reserve(static_cast<size_t>(Ta) * Ca * 4);
+    const uint64_t fpv = context_key ? host_text_fingerprint(video_context, cbytes, video_mask, static_cast<size_t>(S)) : 0;
+    const uint64_t fpa = context_key ? host_text_fingerprint(audio_context, cbytes, audio_mask, static_cast<size_t>(S)) : 0;
+    text_cache_guard(c->text, context_key, fpv);
+    text_cache_guard(c->av.text, context_key, fpa);
     dit_av_forward_dev(c, b[0].ptr, video_dtype, b[1].ptr, audio_dtype, b[2].ptr, b[3].ptr, context_dtype, b[4].as<float>() + 1,
                        per_token, b[4].as<float>(), vm, am, 1, N, Ta, S, F, H, W, context_key, b[6].as<float>(), b[7].as<float>());
+    text_cache_stamp(c->text, context_key, fpv);
+    text_cache_stamp(c->av.text, context_key, fpa);
     LTX_CUDA(cudaMemcpyAsync(out_video, b[6].ptr, static_cast<size_t>(N) * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaMemcpyAsync(out_audio, b[7].ptr, static_cast<size_t>(Ta) * Ca * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));

@@ -347,12 +347,7 @@ template <int HD>
 void attention_launch(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb, const AttnParams& p,
                       int D, cudaStream_t stream) {
   using Cfg = AttCfg<HD>;
-  static bool configured = false;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(Cfg::SMEM)));
-    configured = true;
-  }
+  ensure_dyn_smem(attention_fwd_tcgen05<HD>, Cfg::SMEM);
   CUtensorMap tmQ = make_tmap_2d(Q, static_cast<uint64_t>(p.B) * p.Nq, D, ldq, 128);
   CUtensorMap tmK = make_tmap_2d(K, static_cast<uint64_t>(p.B) * p.Nk, D, ldk, TK);
   CUtensorMap tmV = make_tmap_3d(Vt, p.Nk, D, p.B, static_cast<uint64_t>(p.B) * ldvb, ldvb, TK, HD);

@@ -532,12 +532,8 @@ int best_pow2(int extent, int budget) {
 template <int BN, int MODE>
 void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
   using Cfg = ConvCfg<BN>;
-  static bool configured = false;
   auto kern = conv3d_tcgen05<BN, MODE>;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM)));
-    configured = true;
-  }
+  ensure_dyn_smem(kern, Cfg::SMEM);
   const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN) * g.ksplit;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);

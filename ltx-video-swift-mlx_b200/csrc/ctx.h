@@ -57,6 +57,7 @@ struct BlockWeights {
 
 struct TextCache {  // caption projection + per-block cross-attention K / V^T (step-invariant)
   uint64_t key = 0;
+  uint64_t fingerprint = 0;   // host-buffer entry points: sampled hash of the embedding + mask the entry was built from (0 = not recorded)
   int B = 0, S = 0;
   int64_t ldv = 0;
   DevBuf k;    // [L][B*S, D] bf16

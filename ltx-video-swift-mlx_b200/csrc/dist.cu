@@ -37,9 +37,7 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
-NcclApi& nccl() {
-  static NcclApi api;
-  if (api.handle) return api;
+NcclApi& nccl_load(NcclApi& api) {
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
     api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -63,6 +61,13 @@ NcclApi& nccl() {
   api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   return api;
+}
+// loaded once per process, on first use, from any thread (function-local static initialisation is thread-safe; a failed
+// load throws and is retried by the next caller)
+NcclApi& nccl() {
+  static NcclApi api;
+  static NcclApi& ready = nccl_load(api);
+  return ready;
 }
 
 #define LTX_NCCL(expr)                                                                                          \

@@ -154,7 +154,7 @@ TextCache& dit_prepare_text(ltx_ctx* c, TextCache* slots, int* rr, const TextPro
   if (slot < 0) slot = ((*rr)++) & 1;
   TextCache& tc = slots[slot];
   const int64_t R = static_cast<int64_t>(B) * S;
-  tc.key = key; tc.B = B; tc.S = S;
+  tc.key = key; tc.fingerprint = 0; tc.B = B; tc.S = S;
   tc.ldv = round_up(S, 8);  // per-batch pitch of V^T; row pitch is B * ldv
   tc.k.reserve(static_cast<size_t>(L) * R * D * 2);
   tc.vt.reserve(static_cast<size_t>(L) * D * B * tc.ldv * 2);
@@ -224,7 +224,9 @@ void dit_build_rope(ltx_ctx* c, int F, int H, int W) { build_rope(c, F, H, W); }
 
 void dit_clear_caches(ltx_ctx* c) {
   c->rope_f = c->rope_h = c->rope_w = 0;
-  for (auto& t : c->text) { t.key = 0; t.B = t.S = 0; }
+  for (auto& t : c->text) { t.key = 0; t.fingerprint = 0; t.B = t.S = 0; }
+  for (auto& t : c->av.text) { t.key = 0; t.fingerprint = 0; t.B = t.S = 0; }   // the dual model's audio-stream text cache
+  c->av.rope_ta = c->av.rope_f = c->av.rope_hw = 0;
 }
 
 // Pack raw tensors into kernel-ready pointers.  attn1 to_q|to_k are concatenated into one [2D, D] operand so the

@@ -258,11 +258,7 @@ void attention_f32(ltx_ctx* c, const float* Q, int64_t ldq, const float* K, int6
   ProfScope ps(c, PROF_ATTN, 4.0 * B * H * static_cast<double>(Nq) * Nk * 128.0, 4.0 * B * (2.0 * Nq + 2.0 * Nk) * H * 128.0);
   dim3 grid((Nq + AF_WARPS * AF_QPW - 1) / (AF_WARPS * AF_QPW), H, B);
   constexpr size_t smem = (AF_TK * AF_LD + AF_TK * 128 + AF_WARPS * AF_QPW * 128) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
-  }
+  ensure_dyn_smem(attention_f32_kernel, smem);
   attention_f32_kernel<<<grid, 256, smem, c->stream>>>(Q, ldq, K, ldk, V, ldv, bias, O, ldo, Nq, Nk, scale);
   LTX_CUDA(cudaGetLastError());
 }

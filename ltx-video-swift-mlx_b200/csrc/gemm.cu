@@ -169,12 +169,8 @@ template <int MODE>
 void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, int a_kblock,
                  const GemmEpi& epi, cudaStream_t stream) {
   using Cfg = GemmCfg;
-  static bool configured = false;
   auto kern = gemm_bf16_tcgen05<MODE>;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::SMEM)));
-    configured = true;
-  }
+  ensure_dyn_smem(kern, Cfg::SMEM);
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM, stream, tmA, tmB, M, N, K, BN, a_kblock, epi);
@@ -222,13 +218,6 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
             "GEMM: transpose_out is served by the weight-streaming kernel only");
   if (allow_skinny && force_bn == 0 && gemm_skinny_eligible(lda, ldb, M, N, K, epi, a_kblock)) {
     launch_gemm_skinny(A, lda, B, ldb, M, N, K, epi, stream);
-    return;
-  }
-  // force_bn >= 2000 selects the 4-CTA multicast kernel (gemm4.cu) with width force_bn - 2000 (0 = fitted); LTX_GEMM_4CTA=1
-  // makes it the default for problems with more than one 128-row tile and at least two column tiles
-  static const bool quad_default = [] { const char* e = getenv("LTX_GEMM_4CTA"); return e ? atoi(e) != 0 : false; }();
-  if (force_bn >= 2000 || (force_bn == 0 && quad_default && M > 128 && N >= 512)) {
-    launch_gemm_4cta(A, lda, B, ldb, M, N, K, epi, stream, force_bn >= 2000 ? force_bn - 2000 : 0, a_kblock, a_kblock_stride);
     return;
   }
   static const bool pair_default = [] { const char* e = getenv("LTX_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();

@@ -155,12 +155,8 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int MODE>
 void launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, int a_kblock, const GemmEpi& epi,
              cudaStream_t stream) {
-  static bool configured = false;
   auto kern = gemm_bf16_2cta<MODE>;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G2_SMEM)));
-    configured = true;
-  }
+  ensure_dyn_smem(kern, G2_SMEM);
   const int tiles = ((M + 2 * BM2 - 1) / (2 * BM2)) * ((N + BN - 1) / BN);
   const int clusters = device_sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);

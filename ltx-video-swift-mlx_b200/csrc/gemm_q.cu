@@ -342,12 +342,8 @@ __global__ void __launch_bounds__(256) dequantize_panel_kernel(const uint8_t* __
 template <int MODE, int BITS>
 void launch_q(const CUtensorMap& tmA, const CUtensorMap& tmQ, int M, int N, int K, int BN, const float* s, const float* b,
               int a_kblock, const GemmEpi& epi, cudaStream_t stream) {
-  static bool configured = false;
   auto kern = gemm_q_tcgen05<MODE, BITS>;
-  if (!configured) {
-    LTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Q_SMEM)));
-    configured = true;
-  }
+  ensure_dyn_smem(kern, Q_SMEM);
   const int tiles = ((M + QBM - 1) / QBM) * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(Q_THREADS), Q_SMEM, stream, tmA, tmQ, M, N, K, BN, s, b, a_kblock, epi);
@@ -382,12 +378,6 @@ void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, in
   if (W.scratch != nullptr && force_bn == 0 && M >= panel_min_m) {
     launch_dequantize_panel(W, W.scratch, stream);
     launch_gemm(A, lda, W.scratch, K, M, N, K, epi, stream, 0, a_kblock, a_kblock_stride);
-    return;
-  }
-  // force_bn >= 1000 selects the pair kernel with width force_bn - 1000 (0 = fitted); LTX_GEMMQ_2CTA=1 makes it the default for M > 128
-  static const bool pair_default = [] { const char* e = getenv("LTX_GEMMQ_2CTA"); return e ? atoi(e) != 0 : false; }();  // measured slower than the 1-CTA kernel (profiles/r01b_gemm_q_experiments.txt)
-  if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {
-    launch_gemm_q_2cta(A, lda, W, M, N, K, epi, stream, force_bn >= 1000 ? force_bn - 1000 : 0, a_kblock, a_kblock_stride);
     return;
   }
   int bn = force_bn ? force_bn : gemm_fit_tile_width(M, N);

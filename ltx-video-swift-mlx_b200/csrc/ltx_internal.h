@@ -59,7 +59,11 @@ CUtensorMap make_tmap_thwc(const void* base, uint64_t T, uint64_t H, uint64_t W,
 // 3-D bf16 tensor (d0 fastest); strides in elements; box = [box0 (64), box1, 1].
 CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1, uint64_t stride2,
                          uint32_t box0, uint32_t box1);
-int device_sm_count();
+int device_sm_count();   // of the calling thread's current device (cached per device)
+// opt a kernel in to `bytes` of dynamic shared memory on the current device, once per (kernel, device); thread-safe
+void ensure_dyn_smem(const void* kernel, size_t bytes);
+template <typename K>
+inline void ensure_dyn_smem(K* kernel, size_t bytes) { ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
 
 // ---------------------------------------------------------------- GEMM (gemm.cu)
 enum EpiMode : int {
@@ -126,11 +130,6 @@ int gemm_fit_tile_width(int M, int N);
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
 int gemm2_fit_tile_width(int M, int N);
-// 4-CTA cluster kernel: two pairs side by side along N share A through TMA multicast (gemm4.cu), same contract
-void launch_gemm_4cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
-                      cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);
-int gemm4_max_clusters();
-int gemm4_fit_tile_width(int M, int N);
 // ---------------------------------------------------------------- quantised weights (gemm_q.cu)
 struct QuantW {
   const uint8_t* q = nullptr;    // [N, K] codes (8-bit) or [N, K/2] packed nibbles (4-bit)
@@ -144,9 +143,6 @@ struct QuantW {
 // C[M,N] = A[M,K] * (s*q + beta)[N,K]^T with the epilogues of launch_gemm (group size 64)
 void launch_gemm_q(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
                    int force_bn = 0, int a_kblock = 0, int64_t a_kblock_stride = 0);
-// 2-CTA pair variant: each CTA dequantises half of the B tile (gemm_q2.cu); default for M > 128 (LTX_GEMMQ_2CTA=0 disables)
-void launch_gemm_q_2cta(const bf16* A, int64_t lda, const QuantW& W, int M, int N, int K, const GemmEpi& epi, cudaStream_t stream,
-                        int force_bn, int a_kblock, int64_t a_kblock_stride);
 void launch_quantize(const bf16* w, int N, int K, int bits, uint8_t* q, float* scales, float* biases, cudaStream_t s);
 void launch_dequantize(const QuantW& W, bf16* w, cudaStream_t s);
 // vectorised, PDL-aware conversion of the whole weight into a bf16 panel (same rounding as the fused kernels)

@@ -140,9 +140,9 @@ std::map<std::string, TensorInfo> parse_header(const char* json, size_t n) {
           j.expect(']');
         } else if (k == "data_offsets") {
           j.expect('[');
-          t.begin = static_cast<uint64_t>(j.integer());
+          { const int64_t v = j.integer(); LTX_CHECK(v >= 0, LTX_ERR_WEIGHTS, "safetensors header: negative data offset"); t.begin = static_cast<uint64_t>(v); }
           j.expect(',');
-          t.end = static_cast<uint64_t>(j.integer());
+          { const int64_t v = j.integer(); LTX_CHECK(v >= 0, LTX_ERR_WEIGHTS, "safetensors header: negative data offset"); t.end = static_cast<uint64_t>(v); }
           j.expect(']');
         } else {
           j.skip_value();
@@ -326,10 +326,22 @@ int load_safetensors(ltx_ctx* c, const char* path, int which) {
     else if (t.dtype == "BF16") { dtype = LTX_BF16; esz = 2; }
     else if (t.dtype == "F16") { dtype = LTX_F16; esz = 2; }
     else LTX_CHECK(false, LTX_ERR_WEIGHTS, "tensor '" + kv.first + "' has unsupported dtype " + t.dtype);
-    int64_t n = 1;
-    for (int64_t d : t.shape) n *= d;
-    LTX_CHECK(t.end >= t.begin && t.end <= data_size && static_cast<uint64_t>(n) * esz == t.end - t.begin, LTX_ERR_WEIGHTS,
+    // the header is untrusted input: bound the rank, reject negative dims and an element count that overflows, and only then
+    // compare the byte count with the (already range-checked) data offsets
+    LTX_CHECK(t.shape.size() <= 8, LTX_ERR_WEIGHTS, "tensor '" + kv.first + "': more than 8 dimensions");
+    LTX_CHECK(t.begin <= t.end && t.end <= data_size, LTX_ERR_WEIGHTS, "tensor '" + kv.first + "': data_offsets outside the file");
+    const uint64_t span = t.end - t.begin;
+    uint64_t n_u = 1;
+    for (int64_t d : t.shape) {
+      LTX_CHECK(d >= 0, LTX_ERR_WEIGHTS, "tensor '" + kv.first + "': negative dimension");
+      LTX_CHECK(d == 0 || n_u <= UINT64_MAX / static_cast<uint64_t>(d), LTX_ERR_WEIGHTS,
+                "tensor '" + kv.first + "': element count overflows");
+      n_u *= static_cast<uint64_t>(d);
+    }
+    LTX_CHECK(n_u <= span / esz && n_u * esz == span, LTX_ERR_WEIGHTS,
               "tensor '" + kv.first + "': data_offsets do not match its shape");
+    if (n_u == 0) continue;   // empty tensor: nothing to load
+    const int64_t n = static_cast<int64_t>(n_u);
     std::vector<int64_t> shape = t.shape;
     if (name == "vae.mean_of_means" || name == "vae.std_of_means") shape.assign(1, n);   // .squeezed() (:833, :837)
     if (shape.empty()) shape.assign(1, 1);                                                  // scalars (timestep_scale_multiplier)

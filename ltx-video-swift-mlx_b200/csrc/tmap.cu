@@ -1,7 +1,9 @@
 // Host-side TMA descriptor construction.  cuTensorMapEncodeTiled is fetched through the runtime's driver entry
 // point lookup so that libltxcuda.so has no link-time dependency on libcuda.so (it must build on a GPU-less box).
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
+#include <set>
 
 #include "ltx_internal.h"
 
@@ -97,14 +99,37 @@ CUtensorMap make_tmap_u8(const void* base, uint64_t rows, uint64_t row_bytes, ui
   return m;
 }
 
+// Per-device caches (one process may hold contexts on several GPUs, each driven by its own host thread): the SM count and the
+// set of kernels that already opted in to more than 48 KB of dynamic shared memory -- cudaFuncSetAttribute is per device.
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_attr_mutex;
+std::set<const void*> g_smem_done[kMaxDevices];
+std::atomic<int> g_sm_count[kMaxDevices];
+int current_device() {
+  int dev = 0;
+  LTX_CUDA(cudaGetDevice(&dev));
+  LTX_CHECK(dev >= 0 && dev < kMaxDevices, 3, "device index out of range");
+  return dev;
+}
+}  // namespace
+
 int device_sm_count() {
-  static int n = 0;
+  const int dev = current_device();
+  int n = g_sm_count[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    LTX_CUDA(cudaGetDevice(&dev));
     LTX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    g_sm_count[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+void ensure_dyn_smem(const void* kernel, size_t bytes) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  if (g_smem_done[dev].count(kernel)) return;
+  LTX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  g_smem_done[dev].insert(kernel);
 }
 
 }  // namespace ltx

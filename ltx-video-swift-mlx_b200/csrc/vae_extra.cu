@@ -427,11 +427,7 @@ void upscale_latent_dev(ltx_ctx* c, const float* latent_dev, int F, int H, int W
     gn_apply_kernel<<<grid_for(n4), 256, 0, st>>>(vol, ga, gb, resid, out, n4, C / 4);
     LTX_CUDA(cudaGetLastError());
   };
-  static bool smem_set = false;
-  if (!smem_set) {
-    LTX_CUDA(cudaFuncSetAttribute(gn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    smem_set = true;
-  }
+  ensure_dyn_smem(gn_partial_kernel, 64 * 1024);
   int h = H, w = W;
   int64_t V = static_cast<int64_t>(F) * h * w;
   // [C, F*H*W] -> channels-last; denormalise (x * std + mean, SpatialUpscaler.swift:370-371) inside the first padding prologue

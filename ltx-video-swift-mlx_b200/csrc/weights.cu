@@ -135,31 +135,80 @@ __global__ void lora_add_kernel(void* w, int w_is_bf16, const float* delta, floa
 // (post-mapping name, LoRAKeyMapper.loraKeyToModelKey :209-243) before ltx_finalize_weights packs / quantises it -- so a
 // quantised model is "merge, then quantise", the same result as the reference's dequantise -> merge -> requantise up to one
 // rounding.  The product runs on the tensor-core GEMM (bf16 operands, fp32 accumulation), the add in fp32.
+namespace {
+// fuse_lora's temporaries: the staged factors live in c->tensors under reserved keys, the scratch in plain allocations, and
+// the context is switched to bf16 storage while the factors are staged.  All of it is undone on every exit path.
+struct LoraScope {
+  ltx_ctx* c;
+  int saved_precision;
+  std::vector<void*> scratch;
+  explicit LoraScope(ltx_ctx* ctx) : c(ctx), saved_precision(ctx->precision) {}
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    LTX_CUDA(cudaMalloc(&p, bytes));
+    scratch.push_back(p);
+    return p;
+  }
+  ~LoraScope() {
+    c->precision = saved_precision;
+    cudaStreamSynchronize(c->stream);
+    for (void* p : scratch) cudaFree(p);
+    for (const char* k : {"__lora.down.weight", "__lora.up.weight"}) {
+      auto t = c->tensors.find(k);
+      if (t == c->tensors.end()) continue;
+      if (t->second.ptr) cudaFree(t->second.ptr);
+      c->tensors.erase(t);
+    }
+  }
+};
+float lora_host_value(const void* p, int dtype, int64_t i) {
+  if (dtype == LTX_F32) return static_cast<const float*>(p)[i];
+  const uint16_t h = static_cast<const uint16_t*>(p)[i];
+  if (dtype == LTX_BF16) {
+    const uint32_t u = static_cast<uint32_t>(h) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  return __half2float(__ushort_as_half(h));
+}
+}  // namespace
+
 void fuse_lora(ltx_ctx* c, const std::string& key, const void* down_host, const void* up_host, int dtype, int rank, float scale) {
   auto it = c->tensors.find(key);
   LTX_CHECK(it != c->tensors.end(), LTX_ERR_WEIGHTS,
             "LoRA target '" + key + "' is not loaded (fuse before ltx_finalize_weights, after loading the base weights)");
   DevTensor& w = it->second;
-  LTX_CHECK(w.shape.size() == 2 && rank > 0 && rank % 8 == 0, LTX_ERR_INVALID_ARGUMENT, "LoRA: 2-D target and a rank that is a multiple of 8");
+  LTX_CHECK(w.shape.size() == 2 && rank > 0, LTX_ERR_INVALID_ARGUMENT, "LoRA: 2-D target and a positive rank");
   LTX_CHECK(down_host && up_host && (dtype == LTX_F32 || dtype == LTX_BF16 || dtype == LTX_F16), LTX_ERR_INVALID_ARGUMENT, "LoRA: bad factors");
   const int64_t out = w.shape[0], in = w.shape[1];
-  // stage both factors as bf16 device tensors through the regular loader (temporary keys)
-  const int64_t ds[2] = {rank, in}, us[2] = {out, rank};
-  const int saved_precision = c->precision;
-  c->precision = 16;   // the factors are always staged as bf16, also in fp32 mode
+  // the tensor-core GEMM wants K (= rank) to be a multiple of 8: ranks such as 4 are zero-padded, which adds exact zeros
+  const int64_t rpad = (static_cast<int64_t>(rank) + 7) / 8 * 8;
+  std::vector<float> down_pad, up_pad;
+  if (rpad != rank) {
+    down_pad.assign(static_cast<size_t>(rpad) * in, 0.f);
+    up_pad.assign(static_cast<size_t>(out) * rpad, 0.f);
+    for (int64_t r = 0; r < rank; ++r)
+      for (int64_t i = 0; i < in; ++i) down_pad[r * in + i] = lora_host_value(down_host, dtype, r * in + i);
+    for (int64_t o = 0; o < out; ++o)
+      for (int64_t r = 0; r < rank; ++r) up_pad[o * rpad + r] = lora_host_value(up_host, dtype, o * rank + r);
+    down_host = down_pad.data(); up_host = up_pad.data(); dtype = LTX_F32;
+  }
+  LoraScope scope(c);
+  // stage both factors as bf16 device tensors through the regular loader (temporary keys), also in fp32 mode
+  const int64_t ds[2] = {rpad, in}, us[2] = {out, rpad};
+  c->precision = 16;
   load_tensor_host(c, "__lora.down.weight", down_host, dtype, ds, 2);
   load_tensor_host(c, "__lora.up.weight", up_host, dtype, us, 2);
-  c->precision = saved_precision;
+  c->precision = scope.saved_precision;
   const bf16* down = reinterpret_cast<const bf16*>(c->tensors["__lora.down.weight"].ptr);
   const bf16* up = reinterpret_cast<const bf16*>(c->tensors["__lora.up.weight"].ptr);
-  bf16* down_t = nullptr;   // [in, rank]: the GEMM's B operand is K-major
-  float* delta = nullptr;
-  LTX_CUDA(cudaMalloc(&down_t, static_cast<size_t>(in) * rank * 2));
-  LTX_CUDA(cudaMalloc(&delta, static_cast<size_t>(out) * in * 4));
-  launch_transpose_bf16(down, in, rank, static_cast<int>(in), down_t, rank, c->stream);
+  bf16* down_t = static_cast<bf16*>(scope.alloc(static_cast<size_t>(in) * rpad * 2));   // [in, rank]: the GEMM's B operand is K-major
+  float* delta = static_cast<float*>(scope.alloc(static_cast<size_t>(out) * in * 4));
+  launch_transpose_bf16(down, in, static_cast<int>(rpad), static_cast<int>(in), down_t, rpad, c->stream);
   GemmEpi e;
   e.mode = EPI_F32; e.out = delta; e.ldo = in;
-  launch_gemm(up, rank, down_t, rank, static_cast<int>(out), static_cast<int>(in), rank, e, c->stream);
+  launch_gemm(up, rpad, down_t, rpad, static_cast<int>(out), static_cast<int>(in), static_cast<int>(rpad), e, c->stream);
   const int64_t n = out * in;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 8192) blocks = 8192;
@@ -167,13 +216,6 @@ void fuse_lora(ltx_ctx* c, const std::string& key, const void* down_host, const 
   LTX_CUDA(cudaGetLastError());
   LTX_CUDA(cudaStreamSynchronize(c->stream));
   c->launches += 3;
-  cudaFree(down_t);
-  cudaFree(delta);
-  for (const char* k : {"__lora.down.weight", "__lora.up.weight"}) {
-    auto t = c->tensors.find(k);
-    cudaFree(t->second.ptr);
-    c->tensors.erase(t);
-  }
 }
 
 // Random-init weights of the named architecture (SURVEY Appendix C shapes).  Scales keep activations O(1):

@@ -26,17 +26,20 @@ def denoise_host_seam(ctx: LtxContext, noise: np.ndarray, context, mask, sigmas:
     latent = np.ascontiguousarray(noise.astype(np.float32) * np.float32(sigmas[0]))      # :793
     v_prev = np.zeros_like(latent)
     use_cfg = cfg_scale > 1.0 and neg_context is not None
+    # one fresh cache key per prompt per generation: the projected text is step-invariant inside this loop only
+    key_pos = ctx.new_context_key() if cache_text else 0
+    key_neg = ctx.new_context_key() if cache_text else 0
     for step in range(len(sigmas) - 1):
         sg, sn = float(sigmas[step]), float(sigmas[step + 1])
         tok = patchify(latent)                                                            # :815 (cast to bf16 on device)
         ts = np.array([sg], dtype=np.float32)
-        vc = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=1 if cache_text else 0), shape)
+        vc = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=key_pos), shape)
         vu = vs = None
         if use_cfg:                                                                       # :829-848
-            vu = unpatchify(tr(tok, neg_context, ts, neg_mask, shape.fhw, context_key=2 if cache_text else 0), shape)
+            vu = unpatchify(tr(tok, neg_context, ts, neg_mask, shape.fhw, context_key=key_neg), shape)
         if stg_scale > 0:                                                                 # :897-921
             tr.set_stg_skip_flags(True, False, stg_blocks)
-            vs = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=1 if cache_text else 0), shape)
+            vs = unpatchify(tr(tok, context, ts, mask, shape.fhw, context_key=key_pos), shape)
             tr.clear_stg_skip_flags()
         ctx.guided_euler_step(latent, vc, vu, vs, v_prev, use_prev=step > 0, cfg_scale=cfg_scale,
                               rescale_phi=guidance_rescale, stg_scale=stg_scale, ge_gamma=ge_gamma, sigma=sg, sigma_next=sn)
@@ -96,6 +99,8 @@ def denoise_av_host_seam(ctx: LtxContext, video_noise: np.ndarray, audio_noise: 
         cond_mask = np.zeros((1, F * H * W), dtype=np.float32)
         cond_mask[:, :H * W] = 1.0
     use_cfg = cfg_scale > 1.0 and neg_video_context is not None
+    key_pos = ctx.new_context_key() if cache_text else 0
+    key_neg = ctx.new_context_key() if cache_text else 0
     for step in range(len(sigmas) - 1):
         sg, sn = float(sigmas[step]), float(sigmas[step + 1])
         if image_latent is not None and image_cond_noise_scale > 0 and sg > 0 and inject_noise is not None:
@@ -104,12 +109,12 @@ def denoise_av_host_seam(ctx: LtxContext, video_noise: np.ndarray, audio_noise: 
         tok = patchify(v_lat)
         vsg = sg if cond_mask is None else np.float32(sg) * (1.0 - cond_mask)                  # :1294-1298
         pv, pa = ctx.av_forward(tok, a_lat, video_context, audio_context, vsg, sg, shape.fhw, mask, mask,
-                                context_key=11 if cache_text else 0)
+                                context_key=key_pos)
         vc, vu = unpatchify(pv, shape), None
         va = pa
         if use_cfg:                                                                            # :1310-1362
             nv, na = ctx.av_forward(tok, a_lat, neg_video_context, neg_audio_context, vsg, sg, shape.fhw, neg_mask, neg_mask,
-                                    context_key=12 if cache_text else 0)
+                                    context_key=key_neg)
             vu = unpatchify(nv, shape)
             va = pa + np.float32(cfg_scale - 1.0) * (pa - na)                                  # applyCFG on the audio velocity
         frame0 = v_lat[:, :, 0:1].copy() if image_latent is not None else None

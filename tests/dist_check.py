@@ -1,6 +1,7 @@
 """Multi-GPU parity check, run as  torchrun --nproc-per-node N tests/dist_check.py [what...]
 Each rank compares the distributed result with a single-GPU run of the same inputs on its own device.
-what: pass (pass-parallel guidance), vae (temporal shards + halo exchange), sp (Ulysses sequence parallel)."""
+what: pass (pass-parallel guidance), vae (temporal shards + halo exchange), sp (Ulysses sequence parallel), hybrid (>= 4 ranks:
+pass groups x Ulysses, the ncclCommSplit sub-communicators and the non-zero broadcast roots)."""
 import os
 import sys
 
@@ -27,7 +28,7 @@ def make_ctx(ocfg, pcfg, w, vw, device):
 
 
 def main():
-    what = sys.argv[1:] or ["pass", "vae", "sp"]
+    what = sys.argv[1:] or ["pass", "vae", "sp", "hybrid"]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # rendezvous only; the data path uses the library's own NCCL communicators
@@ -97,6 +98,14 @@ def main():
         print(f"[rank {rank}] Ulysses sp={world} int8 weights: rel-L2 vs single GPU int8 = {err:.3e}", flush=True)
         ok &= err <= 2e-3
         qd.close()
+    if "hybrid" in what and world >= 4 and world % 2 == 0:
+        ctx = make_ctx(ocfg, pcfg, w, None, local)
+        ltxdist.init_context(ctx, sp_size=world // 2, pass_groups=2)
+        out = denoise(ctx, True)
+        err = O.rel_l2(torch.from_numpy(out), torch.from_numpy(ref_guided))
+        print(f"[rank {rank}] 2 pass groups x Ulysses sp={world // 2}: rel-L2 vs single GPU = {err:.3e}", flush=True)
+        ok &= err <= 2e-3
+        ctx.close()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -27,10 +27,6 @@ SHAPES = [
     (1536, 4096, 4096, 176), (1536, 4096, 4096, 240), (300, 1000, 256, 48), (1536, 8192, 4096, 0), (4096, 1536, 4096, 0), (1536, 16384, 512, 0), (2000, 2304, 1024, 0),
     (1536, 128, 4096, 128), (19000, 256, 128, 0), (1536, 4096, 4096, 1192), (300, 1000, 256, 1064), (256, 256, 64, 1256),
     (1536, 16384, 4096, 1000), (130, 264, 128, 1128), (1536, 4096, 4096, 1176), (4096, 1536, 4096, 1176),
-    # 4-CTA cluster kernel (A multicast between two pairs): fitted / forced widths, ragged M, N, K, odd column-tile counts
-    (1536, 4096, 4096, 2000), (1536, 4096, 4096, 2192), (1536, 8192, 4096, 2256), (4096, 1536, 4096, 2000), (256, 512, 64, 2256),
-    (300, 1000, 256, 2064), (130, 264, 128, 2128), (1000, 1000, 512, 2176), (2000, 2304, 1024, 2000), (1536, 16384, 512, 2000),
-    (520, 776, 192, 2256), (19000, 512, 128, 2000),
 ]
 
 

@@ -53,10 +53,7 @@ def test_quantiser_error_bound_and_layout(ctx, bits):
 
 @pytest.mark.parametrize("bits", [8, 4])
 @pytest.mark.parametrize("M,N,K,mode,bn", [(128, 128, 64, 3, 0), (300, 264, 256, 0, 0), (1536, 4096, 4096, 3, 0),
-                                           (1536, 8192, 4096, 1, 0), (1536, 4096, 16384, 0, 0), (200, 520, 128, 3, 48),
-                                           # 2-CTA pair kernel (each CTA dequantises half of the B tile): forced widths, ragged shapes
-                                           (1536, 4096, 4096, 3, 1256), (300, 264, 256, 0, 1064), (1000, 1000, 512, 3, 1176),
-                                           (1536, 16384, 4096, 1, 1224), (130, 8192, 320, 0, 1128), (2000, 2304, 1024, 3, 1000)])
+                                           (1536, 8192, 4096, 1, 0), (1536, 4096, 16384, 0, 0), (200, 520, 128, 3, 48)])
 def test_dequant_fused_gemm_equals_gemm_on_dequantised_weights(ctx, bits, M, N, K, mode, bn):
     g = torch.Generator(device="cuda").manual_seed(M + N + K + bits)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()

@@ -71,6 +71,10 @@ class _OracleBackedContext:
                             tuple(fhw), stg_blocks=stg, skip_self_attn=bool(flags.skip_self_attn) if flags is not None else False)
         return out.numpy()
 
+    def new_context_key(self):
+        self.keys = getattr(self, "keys", 0) + 1
+        return 100 + self.keys
+
     def av_forward(self, vl, al, vc, ac, vs, a_s, fhw, vm=None, am=None, context_key=0):
         t = self.torch
         self.calls.append(("av", np.size(vs), context_key))
@@ -111,7 +115,13 @@ def test_host_seam_loops_follow_the_reference_order():
                                      guidance_rescale=0.5, stg_scale=0.4, stg_blocks=(1,), ge_gamma=0.2)
     ref = O.denoise_loop(w, cfg, noise, cx, None, sig, ncx, None, 3.0, 0.5, 0.4, (1,), 0.2)
     assert O.rel_l2(torch.from_numpy(out), ref) < 1e-5
-    assert ctx.calls[:3] == [("dit", (), 1), ("dit", (), 2), ("dit", (1,), 1)] and len(ctx.calls) == 9
+    kp, kn = ctx.calls[0][2], ctx.calls[1][2]
+    assert kp != 0 and kn != 0 and kp != kn
+    assert ctx.calls[:3] == [("dit", (), kp), ("dit", (), kn), ("dit", (1,), kp)] and len(ctx.calls) == 9
+    assert all(c[2] == (kn if i % 3 == 1 else kp) for i, c in enumerate(ctx.calls))     # one key per prompt for the whole loop
+    # a second generation on the same context must not reuse the first one's keys (stale text K/V under constant keys)
+    pipeline.denoise_host_seam(ctx, noise.numpy(), ncx.numpy(), None, sig[:2])
+    assert ctx.calls[-1][2] not in (0, kp, kn)
 
     av = O.AVConfig(audio_heads=2)
     wav = O.make_av_weights(cfg, av, 5)
