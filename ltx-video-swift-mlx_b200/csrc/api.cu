@@ -149,7 +149,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
                     &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
                     &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->v_split, &c->v_pad2, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
                     &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
-                    &c->f_bias, &c->q_panel, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7],
+                    &c->f_bias, &c->q_panel, &c->gemm_ws, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7],
                     &c->v_tile_lat, &c->v_tile_noise, &c->v_tile_frames, &c->s_alat, &c->s_avc, &c->s_avu, &c->s_actx_pos, &c->s_actx_neg};
   for (DevBuf* b : bufs) b->release();
   for (auto& t : c->text) { t.k.release(); t.vt.release(); t.bias.release(); }
@@ -950,6 +950,10 @@ int ltx_op_gemm(ltx_ctx* c, const void* A, const void* B, const float* bias, voi
     if (force_bn == -1) {   // the weight-streaming kernel for M <= 32, or an error: never a silent switch to the tile kernel
       LTX_CHECK(gemm_skinny_eligible(K, K, M, N, K, e, 0), LTX_ERR_INVALID_ARGUMENT, "shape not eligible for the skinny GEMM");
       launch_gemm_skinny(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    } else if (force_bn == -2 || force_bn == -3) {   // the swap-AB weight-streaming kernel (M <= 512): -2 with split-K workspace, -3 without
+      LTX_CHECK(gemm_swapab_eligible(K, K, M, N, K, e), LTX_ERR_INVALID_ARGUMENT, "shape not eligible for the swap-AB GEMM");
+      if (force_bn == -2) gemm_attach_workspace(c, e);
+      launch_gemm_swapab(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
     } else {
       launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);
     }
@@ -963,6 +967,7 @@ int ltx_op_gemm_resid(ltx_ctx* c, const void* A, const void* B, const float* bia
     GemmEpi e;
     e.mode = EPI_GATE_RESID; e.resid = x; e.ldr = N; e.bias = bias; e.gate_a = gate_a; e.gate_b = gate_b; e.gate_ld = 0;
     e.rows_per_gate = M > 0 ? M : 1; e.shadow = reinterpret_cast<bf16*>(shadow); e.lds = N; e.scale = scale;
+    if (M > 32 && M <= 512) gemm_attach_workspace(c, e);   // as the DiT forward does for few-row problems (swap-AB kernel)
     launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, 0, 0, 0,
                 1 /* M <= 32: the weight-streaming kernel, as on the dual model's audio stream */);
     c->launches++;

@@ -199,6 +199,7 @@ struct ltx_ctx {
   std::unordered_map<const void*, ltx::QuantW> qw;  // quantised replacements, keyed by the bf16 weight pointer they replace
   int quant_bits = 16;
   ltx::DevBuf q_panel;                            // bf16 conversion panel of the large-M quantised GEMM path
+  ltx::DevBuf gemm_ws;                            // split-K workspace of the weight-streaming GEMM: [counters 64 KB | fp32 partials]
   std::vector<void*> owned;                       // packed allocations made by finalize
   bool dit_ready = false;
   std::vector<ltx::BlockWeights> blocks;
@@ -249,6 +250,9 @@ struct ltx_ctx {
 };
 
 namespace ltx {
+// split-K workspace of the swap-AB GEMM (gemm_swapab.cu), one per context = per stream: 16 K zeroed arrival counters followed by
+// 40 MB of fp32 partial tiles (74 CTA pairs x 256 x 512 x 4 B is the most a launch can use)
+void gemm_attach_workspace(ltx_ctx* c, GemmEpi& e);
 // RAII scope: times the launches issued inside it when profiling is on, and counts them.
 struct ProfScope {
   ltx_ctx* c;

@@ -27,6 +27,12 @@ void gemm(ltx_ctx* c, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
     launch_gemm_q(A, lda, it->second, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
     return;
   }
+  if (M <= 512) {   // few rows (an Ulysses shard, a small clip): opt in to the weight-streaming kernel
+    GemmEpi ew = e;
+    gemm_attach_workspace(c, ew);
+    launch_gemm(A, lda, B, ldb, M, N, K, ew, c->stream, 0, a_kblock, a_kblock_stride);
+    return;
+  }
   launch_gemm(A, lda, B, ldb, M, N, K, e, c->stream, 0, a_kblock, a_kblock_stride);
 }
 // V^T [D, ncols] (row pitch ld_out) = (h Wv^T + bv)^T for one batch.  bf16 weights: run the projection with the weight as
@@ -221,6 +227,18 @@ TextCache& prepare_text(ltx_ctx* c, const void* context, int context_dtype, cons
 }  // namespace
 
 void dit_build_rope(ltx_ctx* c, int F, int H, int W) { build_rope(c, F, H, W); }
+
+void gemm_attach_workspace(ltx_ctx* c, GemmEpi& e) {
+  constexpr size_t kCounters = 16384, kPartials = static_cast<size_t>(40) << 20;
+  if (!c->gemm_ws.ptr) {
+    c->gemm_ws.reserve(kCounters * 4 + kPartials);
+    LTX_CUDA(cudaMemsetAsync(c->gemm_ws.ptr, 0, kCounters * 4, c->stream));
+  }
+  e.ws_counters = c->gemm_ws.as<unsigned int>();
+  e.ws_counter_count = kCounters;
+  e.ws = reinterpret_cast<float*>(c->gemm_ws.as<uint8_t>() + kCounters * 4);
+  e.ws_bytes = kPartials;
+}
 
 void dit_clear_caches(ltx_ctx* c) {
   c->rope_f = c->rope_h = c->rope_w = 0;

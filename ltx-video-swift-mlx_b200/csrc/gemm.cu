@@ -220,6 +220,12 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
     launch_gemm_skinny(A, lda, B, ldb, M, N, K, epi, stream);
     return;
   }
+  // few activation rows (Ulysses shards, small clips): stream the weights through the swap-AB kernel when the caller opted in
+  // by passing a split-K workspace; force_bn == -2 forces it (tests)
+  if ((force_bn == 0 && epi.ws != nullptr && gemm_swapab_eligible(lda, ldb, M, N, K, epi)) || force_bn == -2) {
+    launch_gemm_swapab(A, lda, B, ldb, M, N, K, epi, stream, a_kblock, a_kblock_stride);
+    return;
+  }
   static const bool pair_default = [] { const char* e = getenv("LTX_GEMM_2CTA"); return e ? atoi(e) != 0 : true; }();
   if (force_bn >= 1000 || (force_bn == 0 && pair_default && M > 128)) {
     launch_gemm_2cta(A, lda, B, ldb, M, N, K, epi, stream, force_bn >= 1000 ? force_bn - 1000 : 0, a_kblock, a_kblock_stride);

@@ -112,6 +112,13 @@ struct GemmEpi {
   // weight-streaming kernel only (gemm_skinny.cu), EPI_BF16: element (m, n) is stored at out[n * ldo + m] -- V^T for the PV MMA
   int transpose_out = 0;
   int debug = 0;  // bit 0: skip the epilogue's global traffic (LTX_GEMM_DEBUG, timing experiments only)
+  // Optional split-K workspace of the weight-streaming kernel for M <= 512 (gemm_swapab.cu): fp32 partial tiles + one zeroed
+  // arrival counter per (weight tile, CTA).  Owned by the caller's context (one per stream); giving it is also the opt-in to
+  // that kernel -- its summation order differs from the tile kernels' when K is split.
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  unsigned int* ws_counters = nullptr;
+  size_t ws_counter_count = 0;
 };
 
 // C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 K-major (row pitch lda / ldb elements, multiples of 8).
@@ -126,6 +133,11 @@ bool gemm_skinny_eligible(int64_t lda, int64_t ldb, int M, int N, int K, const G
 void launch_gemm_skinny(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                         cudaStream_t stream);
 int gemm_fit_tile_width(int M, int N);
+// weight-streaming kernel for M <= 512 (gemm_swapab.cu): the weight tile rides the TMEM lanes, the activation rows are the MMA's
+// N dimension; split-K with a deterministic last-arriver reduction when epi.ws is given.  Same contract as launch_gemm.
+bool gemm_swapab_eligible(int64_t lda, int64_t ldb, int M, int N, int K, const GemmEpi& epi);
+void launch_gemm_swapab(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
+                        cudaStream_t stream, int a_kblock = 0, int64_t a_kblock_stride = 0);
 // 2-CTA (cta_group::2) pair kernel, same contract as launch_gemm (gemm2.cu)
 void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, int N, int K, const GemmEpi& epi,
                       cudaStream_t stream, int force_bn, int a_kblock, int64_t a_kblock_stride);

@@ -101,7 +101,45 @@ def test_gemm_skinny_refuses_ineligible_shapes(ctx):
         assert e.value.code == 2
 
 
+SWAPAB = [(192, 4096, 4096), (192, 16384, 4096), (192, 4096, 16384), (384, 4096, 4096), (384, 8192, 4096), (512, 1024, 512),
+          (1, 128, 64), (16, 256, 64), (48, 520, 192), (130, 264, 320), (200, 1000, 1024), (300, 264, 128), (257, 4096, 2048),
+          (96, 128, 4096), (64, 48, 256), (192, 12288, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", SWAPAB)
+@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("bn", [-2, -3])
+def test_gemm_swapab(ctx, M, N, K, mode, bn):
+    """The weight-streaming kernel for M <= 512 (gemm_swapab.cu: weights on the TMEM lanes, activation rows as the MMA's N),
+    forced with bn = -2 (split-K workspace attached, as the DiT forward does) / -3 (no split): same contract and tolerances as
+    the tile kernels, nothing written past row M or into neighbouring columns, and bit-reproducible run to run although the
+    split-K partials arrive in any order."""
+    if mode != 3 and N % 8 != 0:
+        pytest.skip("bf16 output needs N % 8 == 0")
+    g = torch.Generator(device="cuda").manual_seed(M * 13 + N * 7 + K + mode)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    dt = torch.float32 if mode == 3 else torch.bfloat16
+    out = torch.full((M + 1, N), float("nan"), device="cuda", dtype=dt)      # one guard row
+    torch.cuda.synchronize()
+    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn))
+    ctx.sync()
+    ref = A.float() @ B.float().t() + bias
+    if mode == 1:
+        ref = _gelu_tanh(ref)
+    if mode == 4:
+        ref = ref * torch.sigmoid(ref)
+    assert torch.isfinite(out[:M].float()).all() and torch.isnan(out[M].float()).all()
+    assert rel_l2(out[:M].float(), ref) <= (2e-5 if mode == 3 else 4e-3)
+    out2 = torch.full_like(out, float("nan"))
+    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out2.data_ptr(), M, N, K, mode, bn))
+    ctx.sync()
+    assert torch.equal(out[:M], out2[:M])
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 264, 128), (1536, 4096, 4096), (1536, 4096, 16384),
+                                   (192, 4096, 4096), (384, 4096, 16384), (64, 4096, 4096), (33, 520, 192),   # 32 < M <= 512: swap-AB kernel
                                    (26, 2048, 2048), (11, 128, 128), (32, 2048, 8192)])      # M <= 32: weight-streaming kernel
 def test_gemm_gate_residual(ctx, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)

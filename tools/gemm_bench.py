@@ -63,3 +63,41 @@ for name, M, N, K, mode in (shapes if '--bf16' in sys.argv else []):
         t = sorted(ts)[len(ts) // 2]
         os.environ.pop("LTX_GEMM_FORCE_BN", None)
         print(f"{name:9s} M={M} N={N} K={K} mode={mode} bn={bn:5d}: {t*1e3:8.1f} us  {2*M*N*K/t/1e9:8.1f} TFLOP/s", flush=True)
+
+
+# few activation rows (an Ulysses shard of the config-2 video: 192 rows at sp = 8, 384 at sp = 4): tile kernels (bn = 0) against
+# the swap-AB weight-streaming kernel with (-2) / without (-3) split-K; GB/s = weight bytes / time
+small = [("qk", 8192, 4096, 0), ("v/q2", 4096, 4096, 0), ("out", 4096, 4096, 2), ("ffn_in", 16384, 4096, 1), ("ffn_out", 4096, 16384, 2)]
+for M in ([192, 384, 96, 512] if '--small' in sys.argv else []):
+    for name, N, K, mode in small:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        B = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+        bias = torch.randn(max(M, N), device="cuda")
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        x = torch.zeros(M, N, device="cuda")
+        g = torch.ones(N, device="cuda")
+        for bn in ([0, -2, -3] if mode != 2 else [0, -2]):
+            def run():
+                if mode == 2:   # gate * residual epilogue: ltx_op_gemm_resid attaches the workspace itself (swap-AB for 32 < M <= 512)
+                    ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                                         g.data_ptr(), g.data_ptr(), None, M, N, K, 0.5))
+                else:
+                    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A.data_ptr(), B.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, mode, bn))
+            if mode == 2:
+                os.environ["LTX_GEMM_SWAPAB"] = "1"
+                if bn == 0: os.environ["LTX_GEMM_FORCE_BN"] = "1000"    # force the pair tile kernel (fitted width) for the comparison
+                else: os.environ.pop("LTX_GEMM_FORCE_BN", None)
+            for _ in range(3):
+                run()
+            ctx.sync()
+            ts = []
+            for _ in range(10):
+                flush.zero_()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); run(); e1.record(stream); ctx.sync(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[len(ts) // 2]
+            os.environ.pop("LTX_GEMM_FORCE_BN", None)
+            print(f"{name:8s} M={M:4d} N={N:5d} K={K:5d} mode={mode} kernel={'tile' if bn == 0 else ('swapab+splitK' if bn == -2 else 'swapab')}: "
+                  f"{t*1e3:8.1f} us  {2*M*N*K/t/1e9:7.1f} TFLOP/s  {N*K*2/t/1e6:7.1f} GB/s of weights", flush=True)
