@@ -336,6 +336,13 @@ int ltx_get_stream(ltx_ctx* ctx, void** stream);
  * elapsed ms / algorithmic flops / algorithmic bytes / launch counts per class and clears the records.
  * Classes: 0 GEMM, 1 attention, 2 norm/RoPE rows, 3 conv3d, 4 VAE prologue, 5 other; n_classes must be >= 8. */
 int ltx_set_profiling(ltx_ctx* ctx, int enabled);
+/* Captured steps.  In the steady state of a denoise loop (text projections cached, RoPE table built) ltx_denoise_step and
+ * ltx_dit_forward issue a fixed sequence of ~600 launches on fixed buffers; the library runs the sequence eagerly once per
+ * (shape, flags, buffers), captures it into a CUDA graph on the second occurrence and replays the graph afterwards -- the
+ * B200 counterpart of MLX's lazy graph + eval() (Pipeline/LTXPipeline.swift:950-952).  Same results bit for bit.
+ * ltx_set_graphs(ctx, 0) turns it off (and drops the captured graphs); ltx_graph_stats reports captures / replays so far. */
+int ltx_set_graphs(ltx_ctx* ctx, int enabled);
+int ltx_graph_stats(const ltx_ctx* ctx, uint64_t* captures, uint64_t* replays);
 int ltx_get_profile(ltx_ctx* ctx, double* ms, double* flops, double* bytes, uint64_t* counts, int n_classes);
 
 /* ---- diagnostic single-kernel entry points (device pointers; used by the parity tests and the profiler) ---- */

@@ -97,6 +97,8 @@ SIGNATURES = {
     "ltx_launch_count": (_U64, [_P]),
     "ltx_get_stream": (_I, [_P, C.POINTER(_P)]),
     "ltx_set_profiling": (_I, [_P, _I]),
+    "ltx_set_graphs": (_I, [_P, _I]),
+    "ltx_graph_stats": (_I, [_P, _P, _P]),
     "ltx_get_profile": (_I, [_P, _P, _P, _P, _P, _I]),
     "ltx_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
     "ltx_op_gemm_resid": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F]),

@@ -150,6 +150,16 @@ class LtxContext:
         self._check(self.lib.ltx_get_stream(self.handle, C.byref(p)))
         return p.value or 0
 
+    def set_graphs(self, enabled: bool):
+        """Captured-step replay (CUDA graphs) on / off; off also drops what was captured."""
+        self._check(self.lib.ltx_set_graphs(self.handle, int(enabled)))
+
+    def graph_stats(self) -> Tuple[int, int]:
+        """(captures, replays) so far."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.ltx_graph_stats(self.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_profiling(self, enabled: bool):
         self._check(self.lib.ltx_set_profiling(self.handle, int(enabled)))
 

@@ -70,7 +70,109 @@ void text_cache_stamp(TextCache* slots, uint64_t key, uint64_t fp) {
     if (slots[i].key == key) slots[i].fingerprint = fp;
 }
 
+// ---------------------------------------------------------------- captured step graphs
+// A denoise step is ~600 kernel launches whose sequence depends only on shapes, flags and buffer addresses.  run_graphed
+// runs `body` -- code that only ENQUEUES work on c->stream -- eagerly the first time a key is seen (so every grow-only
+// workspace reaches its final size), captures it into a CUDA graph the second time, and replays the graph from then on: no
+// per-launch host work (tensor-map encoding, argument marshalling), and launch gaps handled by the graph executor.  A graph
+// is dropped when any workspace was (re)allocated since its capture; anything that cannot be captured falls back to eager.
+struct KeyBuilder {
+  std::string s;
+  template <typename T>
+  KeyBuilder& add(const T& v) {
+    s.append(reinterpret_cast<const char*>(&v), sizeof v);
+    return *this;
+  }
+};
+
+void graph_destroy(StepGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  g.exec = nullptr;
+}
+
+template <typename Fn>
+void run_graphed(ltx_ctx* c, const std::string& key, bool eligible, Fn&& body) {
+  static const bool env_on = [] { const char* e = getenv("LTX_GRAPH"); return e ? atoi(e) != 0 : true; }();
+  if (!eligible || !env_on || !c->graphs_enabled || c->prof_on) { body(); return; }
+  auto it = c->graphs.find(key);
+  if (it != c->graphs.end() && it->second.state == 1 && it->second.generation != devbuf_generation().load()) {
+    graph_destroy(it->second);   // a workspace moved since the capture
+    c->graphs.erase(it);
+    it = c->graphs.end();
+  }
+  if (it == c->graphs.end()) {   // first sighting: eager, so that every workspace reaches its final size
+    if (c->graphs.size() >= 8) {
+      auto lru = c->graphs.begin();
+      for (auto j = c->graphs.begin(); j != c->graphs.end(); ++j)
+        if (j->second.last_use < lru->second.last_use) lru = j;
+      graph_destroy(lru->second);
+      c->graphs.erase(lru);
+    }
+    StepGraph g;
+    g.last_use = ++c->graph_clock;
+    c->graphs[key] = g;
+    body();
+    return;
+  }
+  StepGraph& g = it->second;
+  g.last_use = ++c->graph_clock;
+  if (g.state < 0) { body(); return; }   // capture failed before: stay eager
+  if (g.state == 0) {
+    const uint64_t gen = devbuf_generation().load();
+    const uint64_t l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      try {
+        body();
+      } catch (...) {
+        cudaStreamEndCapture(c->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        g.state = -1;
+        throw;
+      }
+      ok = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && graph != nullptr;
+    }
+    const uint64_t n_launch = c->launches - l0;
+    if (ok && devbuf_generation().load() == gen) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+    else ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {   // nothing has run yet: do the step eagerly and do not try again for this key
+      cudaGetLastError();
+      graph_destroy(g);
+      g.state = -1;
+      c->launches = l0;
+      body();
+      return;
+    }
+    g.state = 1;
+    g.generation = gen;
+    g.launches = n_launch;
+    c->graph_captures++;
+    LTX_CUDA(cudaGraphLaunch(g.exec, c->stream));
+    return;
+  }
+  c->launches += g.launches;
+  c->graph_replays++;
+  LTX_CUDA(cudaGraphLaunch(g.exec, c->stream));
+}
+
+const TextCache* find_text(const TextCache* slots, uint64_t key, int B, int S) {
+  if (key == 0) return nullptr;
+  for (int i = 0; i < 2; ++i)
+    if (slots[i].key == key && slots[i].B == B && slots[i].S == S) return &slots[i];
+  return nullptr;
+}
+
 }  // namespace
+
+namespace ltx {
+void graphs_clear(ltx_ctx* c) {
+  for (auto& kv : c->graphs) graph_destroy(kv.second);
+  c->graphs.clear();
+}
+}  // namespace ltx
 
 extern "C" {
 
@@ -139,6 +241,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
   if (!c) return LTX_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  graphs_clear(c);
   try { dist_destroy(c); } catch (...) {}
   for (auto& kv : c->tensors)
     if (kv.second.ptr) cudaFree(kv.second.ptr);
@@ -191,6 +294,7 @@ int ltx_dist_get_unique_id(void* id_out_128) {
 
 int ltx_dist_init(ltx_ctx* c, const void* unique_id_128, int rank, int world_size, int sp_size, int pass_groups) {
   return guarded(c, [&] {
+    graphs_clear(c);
     LTX_CHECK(unique_id_128 != nullptr, LTX_ERR_INVALID_ARGUMENT, "null unique id");
     dist_init(c, unique_id_128, rank, world_size, sp_size, pass_groups);
   });
@@ -198,6 +302,7 @@ int ltx_dist_init(ltx_ctx* c, const void* unique_id_128, int rank, int world_siz
 
 int ltx_dist_shutdown(ltx_ctx* c) {
   return guarded(c, [&] {
+    graphs_clear(c);
     LTX_CUDA(cudaStreamSynchronize(c->stream));
     dist_destroy(c);
   });
@@ -219,6 +324,20 @@ int ltx_get_stream(ltx_ctx* c, void** stream) {
     LTX_CHECK(stream != nullptr, LTX_ERR_INVALID_ARGUMENT, "null out pointer");
     *stream = reinterpret_cast<void*>(c->stream);
   });
+}
+
+int ltx_set_graphs(ltx_ctx* c, int enabled) {
+  return guarded(c, [&] {
+    c->graphs_enabled = enabled ? 1 : 0;
+    if (!enabled) graphs_clear(c);
+  });
+}
+
+int ltx_graph_stats(const ltx_ctx* c, uint64_t* captures, uint64_t* replays) {
+  if (!c) return LTX_ERR_INVALID_ARGUMENT;
+  if (captures) *captures = c->graph_captures;
+  if (replays) *replays = c->graph_replays;
+  return LTX_OK;
 }
 
 int ltx_set_profiling(ltx_ctx* c, int enabled) {
@@ -303,6 +422,7 @@ int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
     LTX_CHECK(quant_bits == 16 || quant_bits == 8 || quant_bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");
     LTX_CHECK(quant_bits == 16 || group_size == 64, LTX_ERR_UNSUPPORTED, "only group_size 64 is implemented");
     LTX_CHECK(quant_bits == 16 || c->precision == 16, LTX_ERR_UNSUPPORTED, "fp32 mode cannot be combined with quantised weights");
+    graphs_clear(c);
     // each component is packed once; a later call (after loading another component) only packs what is new
     if (c->tensors.count("patchify_proj.weight") && !c->dit_ready) {
       if (c->precision == 32) dit_finalize_f32(c);
@@ -358,8 +478,23 @@ int ltx_dit_forward(ltx_ctx* c, const void* latent, ltx_dtype latent_dtype, cons
       mask_dev = c->mask_in.as<int32_t>();
     }
     c->vel.reserve(R * g.out_channels * 4);
-    dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), ts_per_token, mask_dev, B, N, S, F,
-                    H, W, flags, c->vel.as<float>());
+    // steady state of a denoise loop at this seam (text cached under the key, RoPE table built): the forward is a fixed launch
+    // sequence on fixed buffers -> replay it as a graph
+    const TextCache* tcache = find_text(c->text, key, B, S);
+    const bool steady = tcache != nullptr && c->precision == 16 && c->rope_f == F && c->rope_h == H && c->rope_w == W && c->rope_cos.ptr;
+    KeyBuilder kb;
+    if (steady) {
+      kb.add('F').add(B).add(N).add(S).add(F).add(H).add(W).add(static_cast<int>(latent_dtype)).add(static_cast<int>(context_dtype))
+          .add(ts_per_token).add(mask_dev).add(lat.ptr).add(ctx.ptr).add(c->ts_in.ptr).add(c->vel.ptr).add(tcache->k.ptr).add(tcache->vt.ptr)
+          .add(tcache->has_bias).add(c->rope_cos.ptr).add(c->dist.sp).add(c->dist.sp_rank).add(c->dist.p2p).add(c->quant_bits);
+      kb.add(flags->n_stg_blocks).add(flags->skip_self_attn).add(flags->skip_ff).add(flags->n_cas_blocks).add(flags->cross_attn_scale);
+      for (int i = 0; i < flags->n_stg_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i) kb.add(flags->stg_blocks[i]);
+      for (int i = 0; i < flags->n_cas_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i) kb.add(flags->cas_blocks[i]);
+    }
+    run_graphed(c, kb.s, steady, [&] {
+      dit_forward_dev(c, lat.ptr, latent_dtype, ctx.ptr, context_dtype, c->ts_in.as<float>(), ts_per_token, mask_dev, B, N, S, F,
+                      H, W, flags, c->vel.as<float>());
+    });
     text_cache_stamp(c->text, key, fp);
     LTX_CUDA(cudaMemcpyAsync(out_velocity, c->vel.ptr, R * g.out_channels * 4, cudaMemcpyDeviceToHost, c->stream));
     LTX_CUDA(cudaStreamSynchronize(c->stream));
@@ -617,22 +752,11 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     const int T = F * H * W;
     const size_t n = static_cast<size_t>(C) * T;
     cudaStream_t st = c->stream;
-    // patchify(latent).asType(.bfloat16)  (P/LTXPipeline.swift:815)
-    {
-      ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * n);
-      launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
-    }
+    // the only per-step scalar the forward passes read lives in device memory (the captured step re-reads it on replay)
     LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
-    // image-conditioned loop (denoise(), P/LTXPipeline.swift:2237-2252, 2344-2357): frame-0 tokens are clean -> per-token
-    // timesteps sigma * (1 - mask), and the Euler update leaves frame 0 untouched
     const bool i2v = p->i2v_frame0_conditioned != 0;
-    const float* ts_dev = c->s_sigma.as<float>();
-    if (i2v) {
-      c->s_ts.reserve(static_cast<size_t>(T) * 4);
-      ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * T);
-      launch_fill_token_timesteps(c->s_ts.as<float>(), T, T, H * W, c->s_sigma.as<float>(), st);
-      ts_dev = c->s_ts.as<float>();
-    }
+    if (i2v) c->s_ts.reserve(static_cast<size_t>(T) * 4);
+    const float* ts_dev = i2v ? c->s_ts.as<float>() : c->s_sigma.as<float>();
     const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
     // the STG pass differs from the conditional pass only from its first perturbed block on; when both run
     // on this rank the conditional pass saves the stream there and the STG pass resumes from it (bit-identical result).
@@ -670,13 +794,42 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     const int stg_idx = use_stg ? n_pass - 1 : -1;
     const bool share = use_stg && !p->disable_stg_prefix_sharing && first_stg > 0 && first_stg < g.num_layers &&
                        (groups == 1 || (stg_idx % groups) == 0);   // conditional pass (index 0) and STG pass on the same group
-    for (int i = 0; i < n_pass; ++i)
-      if (groups == 1 || (i % groups) == c->dist.group)
-        pass(passes[i].neg, passes[i].stg, passes[i].v, (share && i == 0) ? first_stg : -1, (share && passes[i].stg) ? first_stg : -1);
-    if (groups > 1) {
-      ProfScope ps(c, PROF_COMM, 0.0, 4.0 * n * n_pass, n_pass);
-      for (int i = 0; i < n_pass; ++i) dist_broadcast(c, passes[i].v, n * 4, (i % groups) * c->dist.sp);
+    // everything up to the guided Euler update: patchify, the forward passes of this rank's group, velocity exchange
+    auto forwards = [&] {
+      {
+        // patchify(latent).asType(.bfloat16)  (P/LTXPipeline.swift:815)
+        ProfScope ps(c, PROF_OTHER, 0.0, 6.0 * n);
+        launch_patchify(c->s_latent.as<float>(), c->s_tok.as<bf16>(), nullptr, C, T, st);
+      }
+      // image-conditioned loop (denoise(), P/LTXPipeline.swift:2237-2252, 2344-2357): frame-0 tokens are clean -> per-token
+      // timesteps sigma * (1 - mask), and the Euler update leaves frame 0 untouched
+      if (i2v) {
+        ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * T);
+        launch_fill_token_timesteps(c->s_ts.as<float>(), T, T, H * W, c->s_sigma.as<float>(), st);
+      }
+      for (int i = 0; i < n_pass; ++i)
+        if (groups == 1 || (i % groups) == c->dist.group)
+          pass(passes[i].neg, passes[i].stg, passes[i].v, (share && i == 0) ? first_stg : -1, (share && passes[i].stg) ? first_stg : -1);
+      if (groups > 1) {
+        ProfScope ps(c, PROF_COMM, 0.0, 4.0 * n * n_pass, n_pass);
+        for (int i = 0; i < n_pass; ++i) dist_broadcast(c, passes[i].v, n * 4, (i % groups) * c->dist.sp);
+      }
+    };
+    // Steady state (every step of a session but the first): the projected text of each prompt this rank needs is cached and
+    // the RoPE table is built, so the step is a fixed launch sequence on fixed buffers -> captured once, then replayed.
+    bool steady = c->precision == 16 && c->rope_f == F && c->rope_h == H && c->rope_w == W && c->rope_cos.ptr != nullptr;
+    KeyBuilder kb;
+    kb.add('S').add(F).add(H).add(W).add(S).add(i2v).add(use_cfg).add(use_stg).add(share).add(first_stg).add(p->n_stg_blocks)
+        .add(c->dist.world).add(c->dist.rank).add(c->dist.sp).add(groups).add(c->dist.p2p).add(c->quant_bits).add(c->s_ctx_dtype)
+        .add(c->s_latent.ptr).add(c->s_tok.ptr).add(c->s_sigma.ptr).add(c->s_ts.ptr).add(c->vel.ptr).add(c->rope_cos.ptr);
+    for (int i = 0; i < p->n_stg_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i) kb.add(p->stg_blocks[i]);
+    for (int i = 0; i < n_pass && steady; ++i) {
+      if (!(groups == 1 || (i % groups) == c->dist.group)) continue;
+      const TextCache* tcache = find_text(c->text, passes[i].neg ? key_neg : key_pos, 1, S);
+      if (!tcache) { steady = false; break; }
+      kb.add(i).add(tcache->k.ptr).add(tcache->vt.ptr).add(tcache->has_bias).add(passes[i].v);
     }
+    run_graphed(c, kb.s, steady, forwards);
     GuidedEulerArgs a;
     a.latent = c->s_latent.as<float>(); a.v_cond = c->s_vc.as<float>();
     a.v_uncond = use_cfg ? c->s_vu.as<float>() : nullptr;

@@ -1,5 +1,6 @@
 // libltxcuda context: device weights, workspaces and caches for one GPU.
 #pragma once
+#include <atomic>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -21,12 +22,20 @@ struct DevTensor {
   }
 };
 
+// Bumped whenever a DevBuf (re)allocates or frees: captured CUDA graphs hold raw workspace pointers and are only replayed
+// while the generation they were captured at is still current.
+inline std::atomic<uint64_t>& devbuf_generation() {
+  static std::atomic<uint64_t> g{1};
+  return g;
+}
+
 // Grow-only device buffer.
 struct DevBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
   void reserve(size_t n) {
     if (n <= bytes) return;
+    devbuf_generation().fetch_add(1, std::memory_order_relaxed);
     if (ptr) LTX_CUDA(cudaFree(ptr));
     ptr = nullptr;
     bytes = 0;
@@ -34,7 +43,7 @@ struct DevBuf {
     bytes = n;
   }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) { devbuf_generation().fetch_add(1, std::memory_order_relaxed); cudaFree(ptr); }
     ptr = nullptr;
     bytes = 0;
   }
@@ -168,11 +177,20 @@ struct DistState {
   void* p2p_local = nullptr;          // this rank's exported allocation: [recv bytes | flags]
   size_t p2p_bytes = 0;               // recv capacity (bytes) of every rank's allocation
   void* p2p_peer[8] = {};             // base of rank r's allocation in this process (own pointer for r == sp_rank)
-  uint32_t p2p_epoch[2] = {0, 0};     // barrier generations: 0 = q/k/v landed, 1 = attention output landed
+                                      // barrier generations (0 = q/k/v landed, 1 = attention output landed) are counted on the
+                                      // device, next to the flags, so that a captured step replays with fresh epochs
   void* comm_world = nullptr;  // ncclComm_t
   void* comm_sp = nullptr;     // sequence-parallel sub-communicator (== world when pass_groups == 1)
   bool sp_is_world = true;
   int rank = 0, world = 1, sp = 1, groups = 1, group = 0, sp_rank = 0;
+};
+// One captured denoise step / forward (api.cu: run_graphed).  state 0: seen once (ran eagerly, buffers are sized), 1: captured.
+struct StepGraph {
+  int state = 0;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches = 0;     // kernel launches one replay stands for
+  uint64_t generation = 0;   // devbuf_generation() at capture
+  uint64_t last_use = 0;
 };
 enum ProfClass { PROF_GEMM = 0, PROF_ATTN = 1, PROF_ROW = 2, PROF_CONV = 3, PROF_PREP = 4, PROF_OTHER = 5, PROF_COMM = 6, PROF_NCLASS = 8 };
 struct ProfRec {
@@ -189,6 +207,11 @@ struct ltx_ctx {
   bool prof_on = false;
   std::vector<ltx::ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
+
+  // ---- captured step graphs (keyed by everything that shapes the launch sequence; see run_graphed in api.cu)
+  std::map<std::string, ltx::StepGraph> graphs;
+  uint64_t graph_clock = 0, graph_replays = 0, graph_captures = 0;
+  int graphs_enabled = 1;
 
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -276,6 +299,8 @@ struct ProfScope {
     c->prof_recs.push_back(r);
   }
 };
+// api.cu: drop every captured graph (weights, communicators or precision changed)
+void graphs_clear(ltx_ctx* c);
 // dit.cu
 void dit_finalize(ltx_ctx* c);
 void dit_quantize(ltx_ctx* c, int bits);

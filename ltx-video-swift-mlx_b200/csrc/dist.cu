@@ -115,10 +115,21 @@ void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int 
 // ------------------------------------------------------------------------------------------------ peer-memory Ulysses
 namespace {
 
-constexpr size_t P2P_FLAG_BYTES = 256;   // [2 kinds][8 source ranks] uint32 at the end of the exported allocation
+constexpr size_t P2P_FLAG_BYTES = 256;   // [2 kinds][8 source ranks] uint32 flags + [2] local epoch counters, at the end of the exported allocation
 
-__global__ void p2p_barrier_kernel(PeerTable peers, size_t flag_off, int P, int me, int kind, uint32_t epoch) {
+// The epoch of barrier `kind` lives in this rank's own allocation (behind the flags) and is advanced by the kernel itself:
+// every rank runs the same sequence of barriers, so the counters agree, and a CUDA-graph replay of a captured step gets
+// fresh epochs without any host-side argument.
+__global__ void p2p_barrier_kernel(PeerTable peers, size_t flag_off, int P, int me, int kind) {
   const int t = threadIdx.x;
+  __shared__ uint32_t epoch_s;
+  if (t == 0) {
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(peers.p[me]) + flag_off) + 2 * LTX_MAX_PEERS + kind;
+    epoch_s = *ctr + 1;
+    *ctr = epoch_s;
+  }
+  __syncthreads();
+  const uint32_t epoch = epoch_s;
   if (t >= P) return;
   // every store of the preceding kernels of this stream has completed (kernel boundary); publish that to rank t ...
   __threadfence_system();
@@ -212,7 +223,6 @@ bool dist_p2p_ensure(ltx_ctx* c, size_t bytes) {
   d.p2p_local = local;
   d.p2p_bytes = cap;
   for (int r = 0; r < P; ++r) d.p2p_peer[r] = peer[r];
-  d.p2p_epoch[0] = d.p2p_epoch[1] = 0;
   d.p2p = true;
   return true;
 }
@@ -222,8 +232,7 @@ void dist_p2p_barrier(ltx_ctx* c, int kind) {
   LTX_CHECK(d.p2p && (kind == 0 || kind == 1), LTX_ERR_INVALID_ARGUMENT, "peer barrier without peer memory");
   PeerTable t = {};
   for (int r = 0; r < d.sp; ++r) t.p[r] = d.p2p_peer[r];
-  const uint32_t epoch = ++d.p2p_epoch[kind];
-  p2p_barrier_kernel<<<1, 32, 0, c->stream>>>(t, d.p2p_bytes, d.sp, d.sp_rank, kind, epoch);
+  p2p_barrier_kernel<<<1, 32, 0, c->stream>>>(t, d.p2p_bytes, d.sp, d.sp_rank, kind);
   LTX_CUDA(cudaGetLastError());
 }
 

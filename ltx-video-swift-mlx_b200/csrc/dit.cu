@@ -582,7 +582,7 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
         e.tsplit_col = 2 * D; e.out_t = vt; e.ldt = ldv;
         ProfScope ps(c, PROF_GEMM, 2.0 * R * 3.0 * D * D, 2.0 * (static_cast<double>(R) * D + 3.0 * D * D + 3.0 * R * D));
         launch_gemm(h, D, bw.a1.wq, D, R, 3 * D, D, e, st, R > 128 ? 1256 : 256);
-      } else {
+      } else if (P == 1) {
         gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
       }
       if (P == 1) {
@@ -609,7 +609,18 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
             ot.p[d] = peer_base[d] + static_cast<int64_t>(3 * P + me) * blk;
           }
         }
-        gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
+        if (c->qw.empty()) {
+          // bf16 weights: q | k | v as ONE projection over the packed [3D, D] operand (one launch instead of two at a row count
+          // where every launch is latency-bound): q | k stay local (row-major, pitch 2D), the v columns go column-blocked to
+          // their destination ranks
+          GemmEpi eqkv = ev;
+          eqkv.out = qk; eqkv.ldo = 2 * D; eqkv.bias = bw.a1.bq;
+          eqkv.col_block_from = 2 * D; eqkv.blocked_out = ev.out; eqkv.blocked_ld = Csp;
+          gemm(c, h, D, bw.a1.wq, D, R, 3 * D, D, eqkv);
+        } else {
+          gemm(c, h, D, bw.a1.wq, D, R, 2 * D, D, e);  // fused q|k projection
+          gemm(c, h, D, bw.a1.wv, D, R, D, D, ev);
+        }
         qknorm(c, qk, 2 * D, R, D, bw.a1.q_norm, cos_l, sin_l, rope_period, eps, bw.a1.k_norm, &qo);
         if (p2p) {
           ProfScope ps(c, PROF_COMM, 0.0, 3.0 * 2.0 * P * blk * 2.0);

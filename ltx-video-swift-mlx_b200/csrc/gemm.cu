@@ -239,7 +239,7 @@ void launch_gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int M, 
                                     epi.ldt % 8 == 0 && epi.col_block == 0),
             2, "GEMM: transposed-column output needs the bf16 epilogue, a tile width and split column that are multiples of 32");
   LTX_CHECK(epi.col_block == 0 || ((epi.mode == EPI_BF16 || epi.mode == EPI_GELU_BF16 || epi.mode == EPI_SILU_BF16) && epi.col_block % 32 == 0 &&
-                                   N % epi.col_block == 0),
+                                   epi.col_block_from % 32 == 0 && (N - epi.col_block_from) % epi.col_block == 0),
             2, "GEMM: column-blocked output needs a bf16 epilogue and col_block % 32 == 0");
   CUtensorMap tmA;
   if (a_kblock > 0) {

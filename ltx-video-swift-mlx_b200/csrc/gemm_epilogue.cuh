@@ -108,11 +108,15 @@ __device__ __forceinline__ void epi_store_chunk(const float* stage, int lane, in
   } else {  // EPI_BF16 / EPI_GELU_BF16 / EPI_SILU_BF16
     // column-blocked destination (Ulysses send layout): a 4-column group never straddles a block (col_block % 32 == 0)
     bf16* obase = reinterpret_cast<bf16*>(ep.out) + c;
-    if (ep.col_block > 0) {
+    int64_t old = ep.ldo;
+    if (ep.col_block > 0 && c >= ep.col_block_from) {
+      const int cb = c - ep.col_block_from;
+      if (ep.blocked_ld) old = ep.blocked_ld;
       if (ep.use_col_ptrs)   // one base per destination rank: the store goes over NVLink when the block is a peer's
-        obase = reinterpret_cast<bf16*>(ep.col_ptrs.p[c / ep.col_block]) + (c % ep.col_block);
+        obase = reinterpret_cast<bf16*>(ep.col_ptrs.p[cb / ep.col_block]) + (cb % ep.col_block);
       else
-        obase = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(c / ep.col_block) * ep.col_block_stride + (c % ep.col_block);
+        obase = reinterpret_cast<bf16*>(ep.blocked_out ? ep.blocked_out : ep.out) + static_cast<int64_t>(cb / ep.col_block) * ep.col_block_stride +
+                (cb % ep.col_block);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -129,7 +133,7 @@ __device__ __forceinline__ void epi_store_chunk(const float* stage, int lane, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = silu(v[j]);
       }
-      bf16* o = obase + static_cast<int64_t>(row) * ep.ldo;
+      bf16* o = obase + static_cast<int64_t>(row) * old;
       if (nvalid >= 4) {
         *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
       } else {

@@ -7,13 +7,17 @@
 // step for 4.3 TFLOP).  Here the operands trade places: the WEIGHT tile is the UMMA "A" operand -- 256 rows per CTA pair, 128 TMEM
 // lanes each -- and the activation rows are the UMMA "N" dimension (one 256 x MC x 16 tcgen05.mma.cta_group::2 per k-step,
 // MC = the row count rounded up to 16, at most 256), split between the two CTAs.  Per k-block a CTA now moves 16 KB of weights
-// + MC/2 x 128 B of activations: 1.75 bytes per weight byte at M = 192, so HBM, not L2, is the limit again.
+// + MC/2 x 128 B of activations: 1.75 bytes per weight byte at M = 192.  (Measured: without the K split this alone buys nothing --
+// both kernels sit at ~60 GB/s of ingest per SM and the tile kernel uses more SMs; the K split below is what pays.)
 //
 //   * unit of work = (256-row weight tile, K split, activation chunk); persistent CTA pairs, units dealt round-robin with the
 //     chunks / splits of one weight tile adjacent, so they run at the same time and the tile's second read hits L2
-//   * weight tiles are few when N is small (4096 / 256 = 16): K is split so that ~all 74 pairs stream; every split stores its
-//     fp32 partial tile to an L2-resident workspace, takes a ticket on the tile's counter, and the LAST arriver adds the
-//     partials in split order (a fixed order: bit-reproducible whatever the arrival order) and runs the fused epilogue
+//   * weight tiles are few when N is small (4096 / 256 = 16): K is split so that ~all 74 pairs stream.  Every split stores its
+//     fp32 partial tile to an L2-resident workspace ([row][128 features]: 128-byte lines per warp access) and takes a ticket on
+//     the tile's counter.  When all units of the launch are resident at once (units <= CTA pairs, the usual case) the S splits
+//     of a tile wait for each other and each one reduces and finishes 1/S of the rows; otherwise the LAST arriver reduces the
+//     whole tile.  Either way the partials are added in split order: bit-reproducible whatever the arrival order.
+//     Measured (B200, M = 192, cold weights): D x D 26.0 -> 20.4 us, FFN-out (K = 16384) 82.8 -> 39.8 us against the tile kernel
 //   * TMEM lane = output feature n, column = activation row m: for a fixed m a warp's 32 lanes own 32 consecutive n, so the
 //     epilogue stores straight from registers, 128 B (fp32) / 64 B (bf16) per instruction, no shared-memory transpose
 //   * 8-stage TMA ring (224 KB), double-buffered accumulators, PDL prologue overlap, TMA zero-fill for ragged M / N / K
@@ -37,17 +41,12 @@ constexpr int SW_MAX_STAGES = 8;
 constexpr size_t SW_SMEM_LIMIT = 227 * 1024;
 constexpr size_t SW_SMEM_FIXED = 1024 + (2 * SW_MAX_STAGES + 4) * 8 + 64;
 
-__device__ __forceinline__ float ld_cg(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Fused epilogue of 32 activation rows [m0, m0 + 32) of output feature n (one thread): v[i] = accumulator of (m0 + i, n).
+// Fused epilogue of `lim` (<= 32) activation rows [m0, m0 + lim) of output feature n (one thread): v[i] = accumulator of (m0 + i, n).
+// lim < 32 on the 16-column tail of a chunk: the rows behind it belong to the next activation chunk (another unit).
 template <int MODE>
-__device__ __forceinline__ void swap_epilogue32(const float (&v)[32], int m0, int n, int M, int N, const GemmEpi& ep) {
+__device__ __forceinline__ void swap_epilogue32(const float (&v)[32], int m0, int lim, int n, int M, int N, const GemmEpi& ep) {
   if (n >= N || m0 >= M) return;
-  const int cnt = (M - m0 < 32) ? M - m0 : 32;
+  const int cnt = (M - m0 < lim) ? M - m0 : lim;
   const float bn = (ep.bias && !ep.bias_per_row) ? __ldg(ep.bias + n) : 0.f;
   if (MODE == EPI_GATE_RESID) {
     float x[32];
@@ -79,9 +78,13 @@ __device__ __forceinline__ void swap_epilogue32(const float (&v)[32], int m0, in
     }
   } else {
     bf16* o = reinterpret_cast<bf16*>(ep.out) + n;
-    if (ep.col_block > 0) {
-      if (ep.use_col_ptrs) o = reinterpret_cast<bf16*>(ep.col_ptrs.p[n / ep.col_block]) + (n % ep.col_block);
-      else o = reinterpret_cast<bf16*>(ep.out) + static_cast<int64_t>(n / ep.col_block) * ep.col_block_stride + (n % ep.col_block);
+    int64_t old = ep.ldo;
+    if (ep.col_block > 0 && n >= ep.col_block_from) {
+      const int nb = n - ep.col_block_from;
+      if (ep.blocked_ld) old = ep.blocked_ld;
+      if (ep.use_col_ptrs) o = reinterpret_cast<bf16*>(ep.col_ptrs.p[nb / ep.col_block]) + (nb % ep.col_block);
+      else o = reinterpret_cast<bf16*>(ep.blocked_out ? ep.blocked_out : ep.out) + static_cast<int64_t>(nb / ep.col_block) * ep.col_block_stride +
+               (nb % ep.col_block);
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -91,7 +94,7 @@ __device__ __forceinline__ void swap_epilogue32(const float (&v)[32], int m0, in
       float a = v[i] + bn + rb;
       if (MODE == EPI_GELU_BF16) a = gelu_tanh(a);
       if (MODE == EPI_SILU_BF16) a = silu(a);
-      o[static_cast<int64_t>(m) * ep.ldo] = __float2bfloat16(a);
+      o[static_cast<int64_t>(m) * old] = __float2bfloat16(a);
     }
   }
 }
@@ -104,6 +107,7 @@ struct SwapParams {
   int kps;       // k-blocks per split
   int stages;
   int a_kblock;
+  int spin;      // every unit is resident at once (units <= CTA pairs): the S splits of a tile wait for each other and share the reduction
   float* ws;             // [tile][rank][split][MC * num_mc... see slot()] fp32 partial tiles (S > 1)
   unsigned int* counters;
 };
@@ -228,16 +232,20 @@ gemm_swapab_2cta(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          swap_epilogue32<MODE>(v, mbase + c * 32, n, p.M, p.N, ep);
+          swap_epilogue32<MODE>(v, mbase + c * 32, min(32, p.MC - c * 32), n, p.M, p.N, ep);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tempty[as], 0);
       } else {
-        // ---- split-K: park this split's partial tile [MC][128 features] in the workspace, take a ticket
+        // ---- split-K: park this split's partial tile in the workspace, [activation row][128 features] so that a warp's
+        // store / load of one row is one 128-byte line, then take a ticket on the tile's arrival counter
         const int tile_slot = (nt * p.num_mc + mc) * 2 + static_cast<int>(rank);
-        float* slot0 = p.ws + static_cast<size_t>(tile_slot) * p.S * (SW_WROWS * p.MC);
-        float* mine = slot0 + static_cast<size_t>(s) * (SW_WROWS * p.MC);
+        const size_t slot_sz = static_cast<size_t>(SW_WROWS) * p.MC;
+        float* slot0 = p.ws + static_cast<size_t>(tile_slot) * p.S * slot_sz;
+        float* mine = slot0 + static_cast<size_t>(s) * slot_sz + n_loc;
+        unsigned int* arrived = p.counters + 2 * tile_slot;
+        unsigned int* finished = arrived + 1;
         uint32_t r[32];
 #pragma unroll 1
         for (int c = 0; c < nch; ++c) {
@@ -247,34 +255,69 @@ gemm_swapab_2cta(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           const int lim = min(32, p.MC - c * 32);
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < lim) __stcg(mine + static_cast<size_t>(c * 32 + i) * SW_WROWS + n_loc, __uint_as_float(r[i]));
+            if (i < lim) __stcg(mine + static_cast<size_t>(c * 32 + i) * SW_WROWS, __uint_as_float(r[i]));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(&tempty[as], 0);   // the accumulator buffer is free again
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) *ticket = atomicAdd(p.counters + tile_slot, 1u);
+        if (et == 0) {
+          uint32_t tk = atomicAdd(arrived, 1u);
+          if (p.spin) {
+            // every split of this tile is resident right now (one unit per CTA pair): wait for all of them, then each split
+            // reduces and finishes ITS share of the rows -- the reduction reads are spread over S CTAs instead of one
+            unsigned long long spins = 0;
+            while (tk + 1 < static_cast<uint32_t>(p.S)) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(tk) : "l"(arrived) : "memory");
+              tk -= 1;
+              if (++spins > (1ull << 24)) {
+                printf("ltxcuda: split-K partner timeout block %d tile %d split %d\n", blockIdx.x, tile_slot, s);
+                __trap();
+              }
+            }
+          }
+          *ticket = tk;
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const bool last = (*ticket == static_cast<uint32_t>(p.S - 1));
+        const uint32_t tk = *ticket;
         asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone has read the ticket before the next unit overwrites it
-        if (last) {
+        // rows this CTA reduces: all of them if it is the last arriver (no partner guaranteed to be resident), its 1/S share
+        // when all splits are known to be there
+        int row_lo = 0, row_hi = 0;
+        if (p.spin) {
+          const int share = ((p.MC + p.S - 1) / p.S + 15) & ~15;
+          row_lo = min(p.MC, s * share);
+          row_hi = min(p.MC, row_lo + share);
+        } else if (tk == static_cast<uint32_t>(p.S - 1)) {
+          row_hi = p.MC;
+        }
+        if (row_hi > row_lo) {
           __threadfence();
 #pragma unroll 1
-          for (int c = 0; c < nch; ++c) {
-            const int lim = min(32, p.MC - c * 32);
+          for (int c0 = row_lo; c0 < row_hi; c0 += 32) {
+            const int lim = min(32, row_hi - c0);
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            for (int ss = 0; ss < p.S; ++ss) {   // fixed order: the sum does not depend on who arrived last
-              const float* src = slot0 + static_cast<size_t>(ss) * (SW_WROWS * p.MC) + static_cast<size_t>(c * 32) * SW_WROWS + n_loc;
+#pragma unroll 1
+            for (int ss = 0; ss < p.S; ++ss) {   // fixed order: the sum does not depend on the arrival order
+              const float* src = slot0 + static_cast<size_t>(ss) * slot_sz + static_cast<size_t>(c0) * SW_WROWS + n_loc;
+              float t[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < lim) v[i] += ld_cg(src + static_cast<size_t>(i) * SW_WROWS);
+              for (int i = 0; i < 32; ++i) t[i] = (i < lim) ? __ldcg(src + static_cast<size_t>(i) * SW_WROWS) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += t[i];
             }
-            swap_epilogue32<MODE>(v, mbase + c * 32, n, p.M, p.N, ep);
+            swap_epilogue32<MODE>(v, mbase + c0, lim, n, p.M, p.N, ep);
           }
-          if (et == 0) p.counters[tile_slot] = 0;   // ready for the next launch (kernel boundary orders it)
+        }
+        // the last CTA to finish with the tile's partials re-arms its counters for the next launch
+        if (p.spin) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0 && atomicAdd(finished, 1u) == static_cast<uint32_t>(p.S - 1)) { *arrived = 0; *finished = 0; }
+        } else if (et == 0 && tk == static_cast<uint32_t>(p.S - 1)) {
+          *arrived = 0;
         }
       }
     }
@@ -326,7 +369,7 @@ void launch_gemm_swapab(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, 
     while (S > 1 && num_k / S < 8) --S;
     const size_t per_split = static_cast<size_t>(base_units) * 2 * SW_WROWS * p.MC * 4;
     while (S > 1 && per_split * S > epi.ws_bytes) --S;
-    if (static_cast<size_t>(base_units) * 2 > epi.ws_counter_count) S = 1;
+    if (static_cast<size_t>(base_units) * 4 > epi.ws_counter_count) S = 1;
   }
   p.S = S;
   p.kps = (num_k + S - 1) / S;
@@ -349,6 +392,7 @@ void launch_gemm_swapab(const bf16* A, int64_t lda, const bf16* W, int64_t ldb, 
     tmA = make_tmap_2d(A, M, K, lda, p.MC / 2);
   }
   const int units = num_nt * p.S * p.num_mc;
+  p.spin = (p.S > 1 && units <= clusters) ? 1 : 0;
   switch (epi.mode) {
     case EPI_BF16: launch_sw<EPI_BF16>(tmW, tmA, p, smem, units, epi, stream); break;
     case EPI_GELU_BF16: launch_sw<EPI_GELU_BF16>(tmW, tmA, p, smem, units, epi, stream); break;

@@ -103,6 +103,13 @@ struct GemmEpi {
   // rank d's receive buffer through NVLink): element (m, n) goes to col_ptrs.p[n / col_block][m * ldo + n % col_block]
   int use_col_ptrs = 0;
   PeerTable col_ptrs = {};
+  // col_block_from > 0: only columns n >= col_block_from are column-blocked (block index (n - col_block_from) / col_block, base
+  // blocked_out -- or col_ptrs -- and row pitch blocked_ld); the columns before it go row-major to `out` / ldo.  Lets the
+  // sequence-parallel path run q | k | v as ONE projection: q | k stay local, the v columns leave for their destination ranks.
+  // col_block_from % 32 == 0.
+  int col_block_from = 0;
+  void* blocked_out = nullptr;   // nullptr -> out
+  int64_t blocked_ld = 0;        // 0 -> ldo
   // EPI_BF16 only: columns n >= tsplit_col are stored TRANSPOSED: element (m, n) -> out_t[(n - tsplit_col) * ldt + m].
   // Used by the fused q|k|v projection: q|k land row-major in `out`, V lands as V^T (K-major for the PV MMA).  Needs
   // tsplit_col % 32 == 0, a tile width that is a multiple of 32, ldt % 8 == 0.  0 = off.

@@ -243,3 +243,60 @@ def test_lora_fuse_matches_merged_weights():
     assert rel_l2(ref, base) > 5e-2            # the adapters matter
     assert rel_l2(out, ref) <= TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("guided", [False, True])
+def test_captured_step_replay_is_bit_identical(guided):
+    """ltx_denoise_step runs eagerly until its launch sequence has been seen once with final buffer sizes, captures it into a
+    CUDA graph and replays it afterwards (api.cu: run_graphed).  The replayed loop must equal the eager loop bit for bit, also
+    across two sessions on one context (the second session's steps replay the first one's graph with fresh text caches)."""
+    ocfg, pcfg = small_dit_config(3, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=16)
+    fhw, S = (2, 4, 6), 40
+    g = torch.Generator().manual_seed(23)
+    noise = torch.randn(1, 128, *fhw, generator=g)
+    _, cx, _ = _inputs(ocfg, fhw, S, 27)
+    _, cx2, _ = _inputs(ocfg, fhw, S, 28)
+    _, ncx, _ = _inputs(ocfg, fhw, S, 29)
+    sigmas = O.set_timesteps(6, False, 48)
+
+    def loop(context):
+        ctx.denoise_begin(noise[0].numpy(), fhw, sigmas[0], context, None, ncx if guided else None, None)
+        for i in range(len(sigmas) - 1):
+            ctx.denoise_step(sigmas[i], sigmas[i + 1], i, cfg_scale=3.0 if guided else 1.0, rescale_phi=0.5 if guided else 0.0,
+                             stg_scale=0.4 if guided else 0.0, stg_blocks=(1,) if guided else (), ge_gamma=0.1 if guided else 0.0)
+        return ctx.denoise_get_latent()
+
+    ctx.set_graphs(False)
+    eager1, eager2 = loop(cx), loop(cx2)
+    assert ctx.graph_stats() == (0, 0)
+    ctx.set_graphs(True)
+    graphed1, graphed2 = loop(cx), loop(cx2)
+    captures, replays = ctx.graph_stats()
+    assert captures >= 1 and replays >= 4, (captures, replays)
+    np.testing.assert_array_equal(graphed1, eager1)
+    np.testing.assert_array_equal(graphed2, eager2)
+    assert rel_l2(eager1, eager2) > 1e-3                 # the two prompts really differ
+    ctx.close()
+
+
+def test_captured_forward_at_the_host_seam():
+    """ltx_dit_forward with a context_key: from the third call on the device part is a graph replay; results stay identical and
+    follow the inputs (latent and timestep are re-uploaded into the same staging buffers before every replay)."""
+    ocfg, pcfg = small_dit_config(2, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=18)
+    fhw, S = (2, 4, 6), 40
+    lat, cx, mask = _inputs(ocfg, fhw, S, 31, mask_prefix=4)
+    lat2, _, _ = _inputs(ocfg, fhw, S, 32)
+    ctxmod = product()
+    fl = ctxmod.make_flags(context_key=ctx.new_context_key())
+    ref_a = ctx.dit_forward(lat, cx, np.array([0.6], dtype=np.float32), mask, fhw)          # un-keyed: always eager
+    ref_b = ctx.dit_forward(lat2, cx, np.array([0.3], dtype=np.float32), mask, fhw)
+    outs = [ctx.dit_forward(lat, cx, np.array([0.6], dtype=np.float32), mask, fhw, fl) for _ in range(4)]
+    out_b = ctx.dit_forward(lat2, cx, np.array([0.3], dtype=np.float32), mask, fhw, fl)
+    captures, replays = ctx.graph_stats()
+    assert captures == 1 and replays >= 2, (captures, replays)
+    for o in outs:
+        np.testing.assert_array_equal(o, ref_a)
+    np.testing.assert_array_equal(out_b, ref_b)
+    ctx.close()
