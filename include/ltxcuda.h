@@ -317,6 +317,11 @@ int ltx_dist_info(const ltx_ctx* ctx, int* rank, int* world_size, int* sp_size, 
  * replaces the NCCL all-to-all.  Established lazily by the first sequence-parallel forward; 0 = NCCL all-to-all (mapping
  * unavailable or LTX_P2P=0). */
 int ltx_dist_p2p_active(const ltx_ctx* ctx);
+/* The same wiring for contexts that all live in ONE process (one per device; contexts[i] becomes rank i): the shape a Swift
+ * host needs, whose pipeline is a single actor in a single process (Pipeline/LTXPipeline.swift:117) and has no launcher.
+ * Afterwards the collective entry points must be called concurrently, one host thread per context.  Peer memory between
+ * same-process ranks is plain peer access (no IPC handles). */
+int ltx_dist_init_local(ltx_ctx** contexts, int n, int sp_size, int pass_groups);
 /* Destroys the communicators (collective); the context can be re-initialised with a different layout afterwards. */
 int ltx_dist_shutdown(ltx_ctx* ctx);
 
@@ -347,9 +352,15 @@ int ltx_get_profile(ltx_ctx* ctx, double* ms, double* flops, double* bytes, uint
 
 /* ---- diagnostic single-kernel entry points (device pointers; used by the parity tests and the profiler) ---- */
 /* C[M,N] = A[M,K] B[N,K]^T (+bias[N]) ; mode: 0 bf16 out, 1 gelu bf16 out, 3 fp32 out, 4 silu bf16 out; force_bn: 0 auto, a tile
- * width, or -1 = the weight-streaming kernel for M <= 32 (error if the shape is not eligible). */
+ * width, -1 = the weight-streaming kernel for M <= 32 (error if the shape is not eligible), -2 / -3 = the few-row (M <= 512)
+ * swap-AB weight-streaming kernel with / without its split-K workspace. */
 int ltx_op_gemm(ltx_ctx* ctx, const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int mode,
                 int force_bn);
+/* The sequence-parallel send layout of the fused q|k|v projection: columns < col_from of A B^T + bias go row-major (pitch col_from)
+ * to plain_out, the others leave in blocks of col_block columns, block j to blocks_out + j * block_stride (row pitch col_block);
+ * force_bn as above, -2 = the few-row weight-streaming kernel. */
+int ltx_op_gemm_blocked(ltx_ctx* ctx, const void* A, const void* B, const float* bias, void* plain_out, void* blocks_out, int M, int N,
+                        int K, int col_from, int col_block, int64_t block_stride, int force_bn);
 /* x[M,N] (fp32) += (A B^T + bias) * (gate_a[n] + gate_b[n]) * scale ; shadow (bf16, nullable) = new x. */
 int ltx_op_gemm_resid(ltx_ctx* ctx, const void* A, const void* B, const float* bias, float* x, const float* gate_a,
                       const float* gate_b, void* shadow, int M, int N, int K, float scale);

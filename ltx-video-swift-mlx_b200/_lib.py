@@ -89,6 +89,7 @@ SIGNATURES = {
     "ltx_denoise_set_frame0": (_I, [_P, _P]),
     "ltx_dist_get_unique_id": (_I, [_P]),
     "ltx_dist_init": (_I, [_P, _P, _I, _I, _I, _I]),
+    "ltx_dist_init_local": (_I, [_P, _I, _I, _I]),
     "ltx_dist_shutdown": (_I, [_P]),
     "ltx_dist_p2p_active": (_I, [_P]),
     "ltx_dist_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "ltx_graph_stats": (_I, [_P, _P, _P]),
     "ltx_get_profile": (_I, [_P, _P, _P, _P, _P, _I]),
     "ltx_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I]),
+    "ltx_op_gemm_blocked": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_int64, _I]),
     "ltx_op_gemm_resid": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F]),
     "ltx_op_quantize": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "ltx_op_dequantize": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),

@@ -187,6 +187,16 @@ class LtxContext:
         assert len(unique_id) == 128
         self._check(self.lib.ltx_dist_init(self.handle, unique_id, rank, world_size, sp_size, pass_groups))
 
+    @staticmethod
+    def dist_init_local(contexts: Sequence["LtxContext"], sp_size: int = 1, pass_groups: Optional[int] = None):
+        """All ranks in this process: contexts[i] (one per device) becomes rank i.  Collective calls must then be issued
+        concurrently, one host thread per context (ctypes releases the GIL while a call runs)."""
+        n = len(contexts)
+        if pass_groups is None:
+            pass_groups = n // sp_size
+        arr = (C.c_void_p * n)(*[c.handle for c in contexts])
+        contexts[0]._check(contexts[0].lib.ltx_dist_init_local(arr, n, int(sp_size), int(pass_groups)))
+
     def dist_shutdown(self):
         self._check(self.lib.ltx_dist_shutdown(self.handle))
 

@@ -300,6 +300,15 @@ int ltx_dist_init(ltx_ctx* c, const void* unique_id_128, int rank, int world_siz
   });
 }
 
+int ltx_dist_init_local(ltx_ctx** contexts, int n, int sp_size, int pass_groups) {
+  if (!contexts || n < 1 || !contexts[0]) return LTX_ERR_INVALID_ARGUMENT;
+  return guarded(contexts[0], [&] {
+    for (int i = 0; i < n; ++i)
+      if (contexts[i]) graphs_clear(contexts[i]);
+    dist_init_local(contexts, n, sp_size, pass_groups);
+  });
+}
+
 int ltx_dist_shutdown(ltx_ctx* c) {
   return guarded(c, [&] {
     graphs_clear(c);
@@ -1106,6 +1115,26 @@ int ltx_op_gemm(ltx_ctx* c, const void* A, const void* B, const float* bias, voi
     } else if (force_bn == -2 || force_bn == -3) {   // the swap-AB weight-streaming kernel (M <= 512): -2 with split-K workspace, -3 without
       LTX_CHECK(gemm_swapab_eligible(K, K, M, N, K, e), LTX_ERR_INVALID_ARGUMENT, "shape not eligible for the swap-AB GEMM");
       if (force_bn == -2) gemm_attach_workspace(c, e);
+      launch_gemm_swapab(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
+    } else {
+      launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);
+    }
+    c->launches++;
+  });
+}
+
+int ltx_op_gemm_blocked(ltx_ctx* c, const void* A, const void* B, const float* bias, void* plain_out, void* blocks_out, int M, int N,
+                        int K, int col_from, int col_block, int64_t block_stride, int force_bn) {
+  return guarded(c, [&] {
+    LTX_CHECK(col_block > 0 && col_from >= 0 && col_from < N && (N - col_from) % col_block == 0 && (N - col_from) / col_block <= LTX_MAX_PEERS,
+              LTX_ERR_INVALID_ARGUMENT, "bad column blocking");
+    GemmEpi e;
+    e.mode = EPI_BF16; e.out = plain_out; e.ldo = col_from > 0 ? col_from : col_block; e.bias = bias;
+    e.col_block = col_block; e.col_block_from = col_from; e.blocked_ld = col_block; e.use_col_ptrs = 1;
+    for (int j = 0; j < (N - col_from) / col_block; ++j)   // one base per block, as the peer-memory path hands out one per rank
+      e.col_ptrs.p[j] = reinterpret_cast<bf16*>(blocks_out) + static_cast<int64_t>(j) * block_stride;
+    if (force_bn == -2) {
+      gemm_attach_workspace(c, e);
       launch_gemm_swapab(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream);
     } else {
       launch_gemm(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), K, M, N, K, e, c->stream, force_bn);

@@ -177,6 +177,8 @@ struct DistState {
   void* p2p_local = nullptr;          // this rank's exported allocation: [recv bytes | flags]
   size_t p2p_bytes = 0;               // recv capacity (bytes) of every rank's allocation
   void* p2p_peer[8] = {};             // base of rank r's allocation in this process (own pointer for r == sp_rank)
+  bool p2p_ipc[8] = {};               // mapped through CUDA IPC (another process) rather than a same-process pointer
+  void* p2p_pool = nullptr;           // cudaMemPool_t the local buffer comes from when every sp rank lives in this process
                                       // barrier generations (0 = q/k/v landed, 1 = attention output landed) are counted on the
                                       // device, next to the flags, so that a captured step replays with fresh epochs
   void* comm_world = nullptr;  // ncclComm_t
@@ -350,6 +352,7 @@ void renoise_dev(ltx_ctx* c, float* latent_dev, const float* noise_dev, int64_t 
 // dist.cu
 void dist_get_unique_id(void* out128);
 void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int sp_size, int pass_groups);
+void dist_init_local(ltx_ctx** contexts, int n, int sp_size, int pass_groups);
 void dist_destroy(ltx_ctx* c);
 void dist_broadcast(ltx_ctx* c, void* buf, size_t bytes, int root_world_rank);
 void dist_allgather_sp(ltx_ctx* c, const void* send, void* recv, size_t bytes_per_rank);

@@ -11,6 +11,7 @@
 //   * VAE           -- latent frames are sharded in contiguous temporal slabs over all ranks; every conv exchanges one
 //                      boundary frame with each temporal neighbour (vae.cu).
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <cstdlib>
@@ -112,6 +113,47 @@ void dist_init(ltx_ctx* c, const void* unique_id, int rank, int world_size, int 
   }
 }
 
+// All ranks in ONE process (the drop-in surface is a single `actor LTXPipeline`, Pipeline/LTXPipeline.swift:117, so a Swift host
+// has no launcher): contexts[i] becomes rank i.  One thread creates every communicator inside an NCCL group; afterwards the
+// collective entry points (ltx_denoise_step, ltx_dit_forward, ltx_vae_decode, ...) must be called concurrently, one host thread
+// per context -- the same contract torchrun's one-process-per-GPU gives, minus the processes.
+void dist_init_local(ltx_ctx** cs, int n, int sp_size, int pass_groups) {
+  LTX_CHECK(cs != nullptr && n >= 1 && n <= 64, LTX_ERR_INVALID_ARGUMENT, "bad context list");
+  LTX_CHECK(sp_size >= 1 && pass_groups >= 1 && sp_size * pass_groups == n, LTX_ERR_INVALID_CONFIGURATION,
+            "sp_size * pass_groups must equal the number of contexts");
+  for (int i = 0; i < n; ++i) {
+    LTX_CHECK(cs[i] != nullptr && cs[i]->dist.comm_world == nullptr, LTX_ERR_INVALID_ARGUMENT, "context missing or already distributed");
+    LTX_CHECK(cs[i]->cfg.num_heads % sp_size == 0, LTX_ERR_INVALID_CONFIGURATION, "sp_size must divide num_heads");
+    for (int j = 0; j < i; ++j) LTX_CHECK(cs[j]->device != cs[i]->device, LTX_ERR_INVALID_ARGUMENT, "one context per device");
+  }
+  ncclUniqueId id;
+  LTX_NCCL(nccl().GetUniqueId(&id));
+  std::vector<ncclComm_t> w(n, nullptr), s(n, nullptr);
+  LTX_NCCL(nccl().GroupStart());
+  for (int i = 0; i < n; ++i) {
+    LTX_CUDA(cudaSetDevice(cs[i]->device));
+    LTX_NCCL(nccl().CommInitRank(&w[i], n, id, i));
+  }
+  LTX_NCCL(nccl().GroupEnd());
+  const bool split = sp_size > 1 && pass_groups > 1;
+  if (split) {
+    LTX_NCCL(nccl().GroupStart());
+    for (int i = 0; i < n; ++i) {
+      LTX_CUDA(cudaSetDevice(cs[i]->device));
+      LTX_NCCL(nccl().CommSplit(w[i], i / sp_size, i % sp_size, &s[i], nullptr));
+    }
+    LTX_NCCL(nccl().GroupEnd());
+  }
+  for (int i = 0; i < n; ++i) {
+    DistState& d = cs[i]->dist;
+    d.comm_world = w[i];
+    d.rank = i; d.world = n; d.sp = sp_size; d.groups = pass_groups;
+    d.group = i / sp_size; d.sp_rank = i % sp_size;
+    d.comm_sp = split ? s[i] : w[i];
+    d.sp_is_world = !split;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ peer-memory Ulysses
 namespace {
 
@@ -151,9 +193,15 @@ __global__ void p2p_barrier_kernel(PeerTable peers, size_t flag_off, int P, int 
 void p2p_release(ltx_ctx* c) {
   DistState& d = c->dist;
   for (int r = 0; r < d.sp; ++r)
-    if (d.p2p_peer[r] && r != d.sp_rank) cudaIpcCloseMemHandle(d.p2p_peer[r]);
+    if (d.p2p_peer[r] && r != d.sp_rank && d.p2p_ipc[r]) cudaIpcCloseMemHandle(d.p2p_peer[r]);
   for (auto& q : d.p2p_peer) q = nullptr;
-  if (d.p2p_local) cudaFree(d.p2p_local);
+  if (d.p2p_pool) {   // same-process mode: the buffer came from the context's peer-visible pool
+    if (d.p2p_local) { cudaFreeAsync(d.p2p_local, c->stream); cudaStreamSynchronize(c->stream); }
+    cudaMemPoolDestroy(reinterpret_cast<cudaMemPool_t>(d.p2p_pool));
+    d.p2p_pool = nullptr;
+  } else if (d.p2p_local) {
+    cudaFree(d.p2p_local);
+  }
   d.p2p_local = nullptr;
   d.p2p_bytes = 0;
   d.p2p = false;
@@ -172,7 +220,12 @@ bool dist_p2p_ensure(ltx_ctx* c, size_t bytes) {
   // (re)registration is collective: every rank of the sp group runs the same forward and gets here with the same size
   LTX_CUDA(cudaStreamSynchronize(c->stream));
   const int P = d.sp, me = d.sp_rank;
-  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+  // Ranks of the same process (ltx_dist_init_local) cannot open each other's IPC handles -- and do not need to: they share an
+  // address space.  Their buffers come from a per-context memory pool whose access list names the peer devices
+  // (cudaMemPoolSetAccess), so a peer's pointer is usable as it is.  NOT cudaDeviceEnablePeerAccess: with blanket peer access
+  // every later cudaMalloc on one device has to be mapped into the other and waits for it to go idle -- which it never does
+  // while its barrier kernel spins for a flag this rank has yet to write (seen as a peer-barrier timeout).
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pid; int device; int pad0; void* ptr; int pad[10]; };
   static_assert(sizeof(Msg) == 128, "handle message is 128 bytes");
   Msg* dev = nullptr;
   LTX_CUDA(cudaMalloc(&dev, sizeof(Msg) * (P + 1)));
@@ -189,20 +242,64 @@ bool dist_p2p_ensure(ltx_ctx* c, size_t bytes) {
     exchange(m, all);
     p2p_release(c);
   }
+  // round 0: who lives where
   Msg mine = {};
+  mine.pid = static_cast<int>(getpid());
+  mine.device = c->device;
+  exchange(mine, all);
+  bool inproc = true;
+  for (int r = 0; r < P; ++r) inproc = inproc && all[r].pid == mine.pid;
   const size_t cap = (bytes + 1023) / 1024 * 1024;
   void* local = nullptr;
-  mine.ok = cudaMalloc(&local, cap + P2P_FLAG_BYTES) == cudaSuccess && cudaMemset(local, 0, cap + P2P_FLAG_BYTES) == cudaSuccess &&
-            cudaIpcGetMemHandle(&mine.h, local) == cudaSuccess;
-  cudaGetLastError();
+  if (inproc) {
+    cudaMemPool_t pool = nullptr;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = c->device;
+    bool ok = cudaMemPoolCreate(&pool, &props) == cudaSuccess;
+    std::vector<cudaMemAccessDesc> acc;
+    for (int r = 0; r < P && ok; ++r) {
+      if (r == me) continue;
+      int can = 0;
+      ok = cudaDeviceCanAccessPeer(&can, all[r].device, c->device) == cudaSuccess && can;
+      cudaMemAccessDesc a = {};
+      a.location.type = cudaMemLocationTypeDevice;
+      a.location.id = all[r].device;
+      a.flags = cudaMemAccessFlagsProtReadWrite;
+      acc.push_back(a);
+    }
+    ok = ok && (acc.empty() || cudaMemPoolSetAccess(pool, acc.data(), acc.size()) == cudaSuccess);
+    ok = ok && cudaMallocFromPoolAsync(&local, cap + P2P_FLAG_BYTES, pool, c->stream) == cudaSuccess &&
+         cudaMemsetAsync(local, 0, cap + P2P_FLAG_BYTES, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (!ok) {
+      cudaGetLastError();
+      if (local) { cudaFreeAsync(local, c->stream); cudaStreamSynchronize(c->stream); local = nullptr; }
+      if (pool) cudaMemPoolDestroy(pool);
+      pool = nullptr;
+    }
+    d.p2p_pool = pool;
+    mine.ok = ok ? 1 : 0;
+  } else {
+    mine.ok = cudaMalloc(&local, cap + P2P_FLAG_BYTES) == cudaSuccess && cudaMemset(local, 0, cap + P2P_FLAG_BYTES) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.h, local) == cudaSuccess;
+    cudaGetLastError();
+  }
+  mine.ptr = local;
   exchange(mine, all);
   bool ok = true;
   for (int r = 0; r < P; ++r) ok = ok && all[r].ok;
   void* peer[LTX_MAX_PEERS] = {};
+  bool via_ipc[LTX_MAX_PEERS] = {};
   if (ok) {
     for (int r = 0; r < P && ok; ++r) {
       if (r == me) { peer[r] = local; continue; }
-      ok = cudaIpcOpenMemHandle(&peer[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (inproc) {
+        peer[r] = all[r].ptr;   // same address space, access granted by the owner's pool
+      } else {
+        ok = cudaIpcOpenMemHandle(&peer[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        via_ipc[r] = ok;
+      }
       if (!ok) cudaGetLastError();
     }
   }
@@ -215,14 +312,14 @@ bool dist_p2p_ensure(ltx_ctx* c, size_t bytes) {
   cudaFree(dev);
   if (!all_ok) {
     for (int r = 0; r < P; ++r)
-      if (peer[r] && r != me) cudaIpcCloseMemHandle(peer[r]);
-    if (local) cudaFree(local);
-    d.p2p = false;
+      if (peer[r] && r != me && via_ipc[r]) cudaIpcCloseMemHandle(peer[r]);
+    d.p2p_local = local;
+    p2p_release(c);   // frees `local` the way it was allocated
     return false;
   }
   d.p2p_local = local;
   d.p2p_bytes = cap;
-  for (int r = 0; r < P; ++r) d.p2p_peer[r] = peer[r];
+  for (int r = 0; r < P; ++r) { d.p2p_peer[r] = peer[r]; d.p2p_ipc[r] = via_ipc[r]; }
   d.p2p = true;
   return true;
 }
