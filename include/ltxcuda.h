@@ -210,6 +210,9 @@ typedef struct {
                                      (per-token timesteps sigma * (1 - mask)) and the Euler update skips it */
   int32_t disable_stg_prefix_sharing; /* 0 (default): the STG pass reuses the conditional pass's blocks before the first
                                          perturbed block (identical inputs -> identical values); 1: recompute them */
+  int32_t disable_batched_cfg;        /* 0 (default): on one GPU the conditional and unconditional passes run as ONE B = 2
+                                         forward, as denoise() batches them (Pipeline/LTXPipeline.swift:2234-2269); 1: as two
+                                         B = 1 forwards, the way generateVideo issues them (:829-848).  Same values per pass. */
 } ltx_step_params;
 /* noise [in_channels, F, H, W] fp32 host; latent = noise * sigma0 (:793).  neg_context may be NULL. */
 int ltx_denoise_begin(ltx_ctx* ctx, const float* noise, int F, int H, int W, float sigma0, const void* context,

@@ -37,7 +37,7 @@ class LtxStepParams(C.Structure):
         ("sigma", C.c_float), ("sigma_next", C.c_float), ("cfg_scale", C.c_float), ("rescale_phi", C.c_float),
         ("stg_scale", C.c_float), ("ge_gamma", C.c_float), ("n_stg_blocks", C.c_int32),
         ("stg_blocks", C.c_int32 * LTX_MAX_FLAG_BLOCKS), ("step_index", C.c_int32),
-        ("i2v_frame0_conditioned", C.c_int32), ("disable_stg_prefix_sharing", C.c_int32),
+        ("i2v_frame0_conditioned", C.c_int32), ("disable_stg_prefix_sharing", C.c_int32), ("disable_batched_cfg", C.c_int32),
     ]
 
 

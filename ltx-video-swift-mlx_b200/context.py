@@ -360,10 +360,11 @@ class LtxContext:
 
     def denoise_step(self, sigma: float, sigma_next: float, step_index: int, cfg_scale: float = 1.0, rescale_phi: float = 0.0,
                      stg_scale: float = 0.0, stg_blocks: Sequence[int] = (), ge_gamma: float = 0.0,
-                     share_stg_prefix: bool = True, i2v_frame0_conditioned: bool = False):
+                     share_stg_prefix: bool = True, i2v_frame0_conditioned: bool = False, batched_cfg: bool = True):
         p = LtxStepParams()
         p.i2v_frame0_conditioned = int(i2v_frame0_conditioned)
         p.disable_stg_prefix_sharing = 0 if share_stg_prefix else 1
+        p.disable_batched_cfg = 0 if batched_cfg else 1
         p.sigma, p.sigma_next, p.cfg_scale, p.rescale_phi = sigma, sigma_next, cfg_scale, rescale_phi
         p.stg_scale, p.ge_gamma, p.step_index = stg_scale, ge_gamma, step_index
         p.n_stg_blocks = len(stg_blocks)

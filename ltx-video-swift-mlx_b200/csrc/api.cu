@@ -249,7 +249,7 @@ int ltx_ctx_destroy(ltx_ctx* c) {
   DevBuf* bufs[] = {&c->sp_send, &c->sp_recv, &c->sp_vt, &c->sp_vel, &c->api_lat, &c->api_ctx, &c->lat_in, &c->ctx_in, &c->ts_in, &c->mask_in, &c->x, &c->xb, &c->h, &c->qk, &c->vt, &c->att, &c->q2,
                     &c->ffh, &c->vel, &c->se, &c->t1, &c->emb, &c->ada, &c->c1, &c->c2, &c->rope_cos, &c->rope_sin,
                     &c->scratch, &c->s_latent, &c->s_tok, &c->s_vc, &c->s_vu, &c->s_vs, &c->s_vprev, &c->s_ctx_pos,
-                    &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
+                    &c->s_ctx_neg, &c->s_mask_pos, &c->s_mask_neg, &c->s_ctx_pair, &c->s_mask_pair, &c->s_sigma, &c->v_a, &c->v_b, &c->v_h, &c->v_pad,
                     &c->v_lat, &c->v_noise, &c->v_frames, &c->v_mix, &c->v_te, &c->v_split, &c->v_pad2, &c->snap_x, &c->s_ts, &c->f_asplit, &c->f_wsplit, &c->f_h,
                     &c->f_q, &c->f_k, &c->f_v, &c->f_att, &c->f_ffh, &c->f_ctx, &c->f_c1, &c->f_c2, &c->f_tk, &c->f_tv, &c->f_lat,
                     &c->f_bias, &c->q_panel, &c->gemm_ws, &c->u_part, &c->u_ab, &c->u_stats, &c->u_in, &c->u_out, &c->u_ref, &c->av.ws, &c->av.a_cos, &c->av.a_sin, &c->av.xv_cos, &c->av.xv_sin, &c->av_in[0], &c->av_in[1], &c->av_in[2], &c->av_in[3], &c->av_in[4], &c->av_in[5], &c->av_in[6], &c->av_in[7],
@@ -669,13 +669,26 @@ int ltx_denoise_begin(ltx_ctx* c, const float* noise, int F, int H, int W, float
       h2d(c, c->s_ctx_neg, neg_context, cbytes);
       c->s_has_mask_neg = neg_mask != nullptr;
       if (neg_mask) h2d(c, c->s_mask_neg, neg_mask, static_cast<size_t>(S) * 4);
+      // batched guidance (denoise(), P/LTXPipeline.swift:2234-2269: latent doubled, one B = 2 forward): both prompts in one
+      // [2, S, Cc] buffer, and one [2, S] mask when either prompt has one (all ones for the other)
+      c->s_ctx_pair.reserve(2 * cbytes);
+      LTX_CUDA(cudaMemcpyAsync(c->s_ctx_pair.ptr, c->s_ctx_pos.ptr, cbytes, cudaMemcpyDeviceToDevice, c->stream));
+      LTX_CUDA(cudaMemcpyAsync(c->s_ctx_pair.as<uint8_t>() + cbytes, c->s_ctx_neg.ptr, cbytes, cudaMemcpyDeviceToDevice, c->stream));
+      if (mask || neg_mask) {
+        std::vector<int32_t> pm(static_cast<size_t>(2) * S, 1);
+        if (mask) memcpy(pm.data(), mask, static_cast<size_t>(S) * 4);
+        if (neg_mask) memcpy(pm.data() + S, neg_mask, static_cast<size_t>(S) * 4);
+        h2d(c, c->s_mask_pair, pm.data(), pm.size() * 4);
+        LTX_CUDA(cudaStreamSynchronize(c->stream));   // pm goes out of scope
+      }
     }
-    c->s_tok.reserve(n * 2);
+    const size_t nb = neg_context ? 2 : 1;   // rows of the batched conditional + unconditional forward
+    c->s_tok.reserve(nb * n * 2);
     c->s_vc.reserve(n * 4);
     c->s_vu.reserve(n * 4);
     c->s_vs.reserve(n * 4);
     c->s_vprev.reserve(n * 4);
-    c->vel.reserve(n * 4);
+    c->vel.reserve(nb * n * 4);
     c->s_sigma.reserve(16);
     c->s_serial += 2;  // fresh context-cache keys for this session
     dit_clear_caches(c);
@@ -688,12 +701,13 @@ namespace {
 void session_resize(ltx_ctx* c, int F, int H, int W) {
   const size_t n = static_cast<size_t>(c->cfg.in_channels) * F * H * W;
   c->s_F = F; c->s_H = H; c->s_W = W;
-  c->s_tok.reserve(n * 2);
+  const size_t nb = c->s_has_neg ? 2 : 1;
+  c->s_tok.reserve(nb * n * 2);
   c->s_vc.reserve(n * 4);
   c->s_vu.reserve(n * 4);
   c->s_vs.reserve(n * 4);
   c->s_vprev.reserve(n * 4);
-  c->vel.reserve(n * 4);
+  c->vel.reserve(nb * n * 4);
   c->s_sigma.reserve(16);
 }
 // latent[:, 0, :, :] = frame0 (host [C, 1, H, W]): the clean conditioning frame of the image-to-video loops
@@ -761,12 +775,15 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     const int T = F * H * W;
     const size_t n = static_cast<size_t>(C) * T;
     cudaStream_t st = c->stream;
-    // the only per-step scalar the forward passes read lives in device memory (the captured step re-reads it on replay)
-    LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, &p->sigma, 4, cudaMemcpyHostToDevice, st));
+    // the only per-step scalar the forward passes read lives in device memory (the captured step re-reads it on replay);
+    // twice: the batched forward takes one timestep per batch row
+    const float sig2[2] = {p->sigma, p->sigma};
+    LTX_CUDA(cudaMemcpyAsync(c->s_sigma.ptr, sig2, 8, cudaMemcpyHostToDevice, st));
     const bool i2v = p->i2v_frame0_conditioned != 0;
-    if (i2v) c->s_ts.reserve(static_cast<size_t>(T) * 4);
+    if (i2v) c->s_ts.reserve(static_cast<size_t>(2) * T * 4);
     const float* ts_dev = i2v ? c->s_ts.as<float>() : c->s_sigma.as<float>();
     const uint64_t key_pos = 0x5000000000000000ull + c->s_serial, key_neg = key_pos + 1;
+    const uint64_t key_pair = 0x5800000000000000ull + c->s_serial;
     // the STG pass differs from the conditional pass only from its first perturbed block on; when both run
     // on this rank the conditional pass saves the stream there and the STG pass resumes from it (bit-identical result).
     int first_stg = -1;
@@ -800,6 +817,13 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     if (use_cfg) passes[n_pass++] = {true, false, c->s_vu.as<float>()};
     if (use_stg) passes[n_pass++] = {false, true, c->s_vs.as<float>()};
     const int groups = c->dist.groups;
+    // Conditional + unconditional as ONE B = 2 forward when both run on this GPU alone: M = 3072 rows fill the tile waves
+    // better (N = 4096 GEMMs: 192 tiles instead of 2 x 96 on 74 CTA pairs; attention: 768 CTAs instead of 2 x 384 on 296
+    // slots) and the weights are read once.  Batch row 0 is the conditional pass, so the STG pass can still resume from its
+    // stream.  Per batch row the arithmetic is that of the separate passes.
+    static const bool batched_on = [] { const char* e = getenv("LTX_BATCHED_CFG"); return e ? atoi(e) != 0 : true; }();
+    const bool batched = batched_on && use_cfg && groups == 1 && !(c->dist.comm_world && c->dist.sp > 1) && c->precision == 16 &&
+                         !p->disable_batched_cfg;
     const int stg_idx = use_stg ? n_pass - 1 : -1;
     const bool share = use_stg && !p->disable_stg_prefix_sharing && first_stg > 0 && first_stg < g.num_layers &&
                        (groups == 1 || (stg_idx % groups) == 0);   // conditional pass (index 0) and STG pass on the same group
@@ -814,11 +838,26 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
       // timesteps sigma * (1 - mask), and the Euler update leaves frame 0 untouched
       if (i2v) {
         ProfScope ps(c, PROF_OTHER, 0.0, 4.0 * T);
-        launch_fill_token_timesteps(c->s_ts.as<float>(), T, T, H * W, c->s_sigma.as<float>(), st);
+        launch_fill_token_timesteps(c->s_ts.as<float>(), batched ? 2 * T : T, T, H * W, c->s_sigma.as<float>(), st);
       }
-      for (int i = 0; i < n_pass; ++i)
+      if (batched) {
+        bf16* tok = c->s_tok.as<bf16>();
+        LTX_CUDA(cudaMemcpyAsync(tok + n, tok, n * 2, cudaMemcpyDeviceToDevice, st));   // the same latent under both prompts
+        ltx_dit_flags fl = {};
+        fl.cross_attn_scale = 1.0f;
+        fl.context_key = key_pair;
+        const int32_t* mk = (c->s_has_mask_pos || c->s_has_mask_neg) ? c->s_mask_pair.as<int32_t>() : nullptr;
+        dit_forward_dev(c, tok, LTX_BF16, c->s_ctx_pair.ptr, c->s_ctx_dtype, ts_dev, i2v ? 1 : 0, mk, 2, T, S, F, H, W, &fl,
+                        c->vel.as<float>(), share ? first_stg : -1, -1);
+        ProfScope ps(c, PROF_OTHER, 0.0, 16.0 * n, 2);
+        launch_unpatchify(c->vel.as<float>(), c->s_vc.as<float>(), C, T, st);
+        launch_unpatchify(c->vel.as<float>() + n, c->s_vu.as<float>(), C, T, st);
+      }
+      for (int i = 0; i < n_pass; ++i) {
+        if (batched && !passes[i].stg) continue;   // done above
         if (groups == 1 || (i % groups) == c->dist.group)
           pass(passes[i].neg, passes[i].stg, passes[i].v, (share && i == 0) ? first_stg : -1, (share && passes[i].stg) ? first_stg : -1);
+      }
       if (groups > 1) {
         ProfScope ps(c, PROF_COMM, 0.0, 4.0 * n * n_pass, n_pass);
         for (int i = 0; i < n_pass; ++i) dist_broadcast(c, passes[i].v, n * 4, (i % groups) * c->dist.sp);
@@ -828,11 +867,17 @@ int ltx_denoise_step(ltx_ctx* c, const ltx_step_params* p) {
     // the RoPE table is built, so the step is a fixed launch sequence on fixed buffers -> captured once, then replayed.
     bool steady = c->precision == 16 && c->rope_f == F && c->rope_h == H && c->rope_w == W && c->rope_cos.ptr != nullptr;
     KeyBuilder kb;
-    kb.add('S').add(F).add(H).add(W).add(S).add(i2v).add(use_cfg).add(use_stg).add(share).add(first_stg).add(p->n_stg_blocks)
+    kb.add('S').add(F).add(H).add(W).add(S).add(i2v).add(use_cfg).add(use_stg).add(share).add(first_stg).add(p->n_stg_blocks).add(batched)
         .add(c->dist.world).add(c->dist.rank).add(c->dist.sp).add(groups).add(c->dist.p2p).add(c->quant_bits).add(c->s_ctx_dtype)
         .add(c->s_latent.ptr).add(c->s_tok.ptr).add(c->s_sigma.ptr).add(c->s_ts.ptr).add(c->vel.ptr).add(c->rope_cos.ptr);
     for (int i = 0; i < p->n_stg_blocks && i < LTX_MAX_FLAG_BLOCKS; ++i) kb.add(p->stg_blocks[i]);
+    if (batched) {
+      const TextCache* tcache = find_text(c->text, key_pair, 2, S);
+      if (!tcache) steady = false;
+      else kb.add(tcache->k.ptr).add(tcache->vt.ptr).add(tcache->has_bias).add(c->s_ctx_pair.ptr);
+    }
     for (int i = 0; i < n_pass && steady; ++i) {
+      if (batched && !passes[i].stg) continue;
       if (!(groups == 1 || (i % groups) == c->dist.group)) continue;
       const TextCache* tcache = find_text(c->text, passes[i].neg ? key_neg : key_pos, 1, S);
       if (!tcache) { steady = false; break; }

@@ -258,6 +258,7 @@ struct ltx_ctx {
 
   // ---- resident denoise session
   ltx::DevBuf s_latent, s_tok, s_vc, s_vu, s_vs, s_vprev, s_ctx_pos, s_ctx_neg, s_mask_pos, s_mask_neg, s_sigma, s_ts;
+  ltx::DevBuf s_ctx_pair, s_mask_pair;   // [2, S, Cc] / [2, S]: positive | negative prompt, for the batched guidance forward
   int s_F = 0, s_H = 0, s_W = 0, s_S = 0;
   bool s_has_neg = false, s_has_mask_pos = false, s_has_mask_neg = false;
   int s_ctx_dtype = LTX_BF16;

@@ -521,7 +521,8 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
     launch_cast_bf16_f32(xb, x, static_cast<int64_t>(R) * D, st);
   } else {
     // resume from the stream saved at the entry of block `resume_block` by an identical-input pass
-    LTX_CHECK(resume_block < L && c->snap_x.ptr && c->snap_rows == R, LTX_ERR_INVALID_ARGUMENT, "no matching snapshot to resume from");
+    // (a snapshot taken by a batched pass holds the rows of every batch entry; entry 0 -- the first R rows -- is the pass resumed)
+    LTX_CHECK(resume_block < L && c->snap_x.ptr && c->snap_rows >= R, LTX_ERR_INVALID_ARGUMENT, "no matching snapshot to resume from");
     ProfScope ps(c, PROF_OTHER, 0.0, 14.0 * R * D, 2);
     LTX_CUDA(cudaMemcpyAsync(x, c->snap_x.ptr, static_cast<size_t>(R) * D * 4, cudaMemcpyDeviceToDevice, st));
     launch_cast_f32_bf16(x, xb, static_cast<int64_t>(R) * D, st);
@@ -575,11 +576,12 @@ void dit_forward_dev(ltx_ctx* c, const void* latent, int latent_dtype, const voi
       norm_mod(c, x, h, R, D, bw.sst, bw.sst + D, ada, ada + D, ada_ld, rows_per_b, eps, 0);
       // q|k|v in one GEMM (N = 3D, 256-wide tiles: 288 tiles = 3.9 rounds of 74 CTA pairs at M = 1536), the V columns stored
       // transposed by the epilogue; separate q|k and V^T GEMMs for batches, sequence parallelism and quantised weights
-      const bool fused_qkv = P == 1 && B == 1 && c->qw.empty() && D % 32 == 0;
+      // (batches: V^T row = feature, column = b * ldv + token -- the same as the GEMM row b * N + token when ldv == N)
+      const bool fused_qkv = P == 1 && (B == 1 || ldv == N) && c->qw.empty() && D % 32 == 0;
       GemmEpi e;
       e.mode = EPI_BF16; e.out = qk; e.ldo = 2 * D; e.bias = bw.a1.bq;
       if (fused_qkv) {
-        e.tsplit_col = 2 * D; e.out_t = vt; e.ldt = ldv;
+        e.tsplit_col = 2 * D; e.out_t = vt; e.ldt = B * ldv;
         ProfScope ps(c, PROF_GEMM, 2.0 * R * 3.0 * D * D, 2.0 * (static_cast<double>(R) * D + 3.0 * D * D + 3.0 * R * D));
         launch_gemm(h, D, bw.a1.wq, D, R, 3 * D, D, e, st, R > 128 ? 1256 : 256);
       } else if (P == 1) {

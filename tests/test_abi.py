@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     assert (cfg.num_layers, cfg.num_heads, cfg.head_dim, cfg.caption_channels) == (48, 32, 128, 3840)
     assert list(cfg.max_pos) == [20, 2048, 2048] and cfg.vae_patch_size == 4 and abs(cfg.norm_eps - 1e-6) < 1e-12
     assert ctypes.sizeof(_lib.LtxDitFlags) == 4 * (1 + 64 + 2 + 1 + 64 + 1) + 4 + 8   # incl. padding before the u64
-    assert ctypes.sizeof(_lib.LtxStepParams) == 4 * (6 + 1 + 64 + 3)
+    assert ctypes.sizeof(_lib.LtxStepParams) == 4 * (6 + 1 + 64 + 4)
 
 
 def test_only_sm100_sass_in_library():

@@ -300,3 +300,36 @@ def test_captured_forward_at_the_host_seam():
         np.testing.assert_array_equal(o, ref_a)
     np.testing.assert_array_equal(out_b, ref_b)
     ctx.close()
+
+
+@pytest.mark.parametrize("i2v,masked,stg", [(False, False, True), (True, False, False), (False, True, True), (True, True, True)])
+def test_batched_guidance_equals_separate_passes(i2v, masked, stg):
+    """ltx_denoise_step runs the conditional and unconditional passes as ONE B = 2 forward on a single GPU (denoise() batches
+    them the same way, P/LTXPipeline.swift:2234-2269; generateVideo issues two B = 1 calls, :829-848).  Per batch row the
+    arithmetic is that of the separate passes: the two loops agree to bf16 round-off (bit-identical in practice), with masks
+    on one or both prompts, per-token timesteps (image-to-video) and the STG pass resumed from batch row 0 of the shared prefix."""
+    ocfg, pcfg = small_dit_config(3, 2)
+    ctx, w = make_ctx_with_dit(ocfg, pcfg, seed=26)
+    fhw, S = (3, 4, 8), 40          # 96 tokens: a multiple of 8, so the batched pass also takes the fused q|k|v projection
+    g = torch.Generator().manual_seed(41)
+    noise = torch.randn(1, 128, *fhw, generator=g)
+    _, cx, mk = _inputs(ocfg, fhw, S, 43, mask_prefix=6)
+    _, ncx, _ = _inputs(ocfg, fhw, S, 44)
+    sigmas = O.set_timesteps(4, False, 96)
+
+    def loop(batched):
+        ctx.denoise_begin(noise[0].numpy(), fhw, sigmas[0], cx, mk if masked else None, ncx, None)
+        for i in range(len(sigmas) - 1):
+            ctx.denoise_step(sigmas[i], sigmas[i + 1], i, cfg_scale=3.0, rescale_phi=0.5, stg_scale=0.4 if stg else 0.0,
+                             stg_blocks=(1,) if stg else (), ge_gamma=0.1, i2v_frame0_conditioned=i2v, batched_cfg=batched)
+        return ctx.denoise_get_latent()
+
+    sep = loop(False)
+    bat = loop(True)
+    assert np.isfinite(bat).all()
+    assert rel_l2(bat, sep) <= 1e-5, rel_l2(bat, sep)
+    if not i2v:
+        kw = dict(neg_context=ncx.float(), cfg_scale=3.0, phi=0.5, stg_scale=0.4 if stg else 0.0, stg_blocks=(1,), ge_gamma=0.1)
+        ref = O.denoise_loop(w, ocfg, noise, cx.float(), mk if masked else None, sigmas, **kw)
+        assert rel_l2(bat, ref[0]) <= 2e-2
+    ctx.close()
