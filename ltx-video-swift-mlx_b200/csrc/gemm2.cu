@@ -31,15 +31,19 @@ constexpr uint32_t G2_A_BYTES = BM2 * BK2 * 2;                 // 16 KB
 constexpr uint32_t G2_B_STRIDE = (G2_BN_MAX / 2) * BK2 * 2;    // 16 KB: half of the B tile
 constexpr size_t G2_SMEM = 1024 + G2_STAGES * (G2_A_BYTES + G2_B_STRIDE) + (2 * G2_STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
 
-template <int MODE>
+// KS = 64-wide k sub-blocks per pipeline stage.  KS = 2: a stage holds 128 k (two swizzle atoms per operand), so the issuing
+// thread waits on / commits to half as many barriers per k and has 8 MMAs in flight per wait; 3 stages of 64 KB.
+template <int MODE, int KS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, int BN,
                int a_kblock, const GemmEpi ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int STAGES = G2_STAGES / KS;
+  constexpr uint32_t A_STAGE = KS * G2_A_BYTES, B_STAGE = KS * G2_B_STRIDE;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + G2_STAGES * G2_B_STRIDE);
+  uint8_t* sB = smem + STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
   uint64_t* empty = full + G2_STAGES;
   uint64_t* tfull = empty + G2_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -53,14 +57,14 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_mp = (M + 2 * BM2 - 1) / (2 * BM2);   // 256-row pair tiles
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_mp * num_n;
-  const int num_k = (K + BK2 - 1) / BK2;
+  const int num_k = (K + KS * BK2 - 1) / (KS * BK2);   // pipeline steps of KS * 64 k
   const int half_bn = BN >> 1;
   const uint32_t b_bytes = static_cast<uint32_t>(half_bn) * BK2 * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < G2_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 2);    // leader's expect_tx arrive + the peer's remote arrive (only the leader's copy is used)
       mbar_init(&empty[i], 1);   // multicast tcgen05.commit
     }
@@ -89,14 +93,18 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = n_blk * BN + static_cast<int>(rank) * half_bn;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (G2_A_BYTES + b_bytes));
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * KS * (G2_A_BYTES + b_bytes));
           else mbar_arrive_remote(&full[stage], 0);
-          if (a_kblock > 0)
-            tma_load_3d_2sm(sA + stage * G2_A_BYTES, &tmA, &full[stage], (kb * BK2) % a_kblock, m0, (kb * BK2) / a_kblock);
-          else
-            tma_load_2d_2sm(sA + stage * G2_A_BYTES, &tmA, &full[stage], kb * BK2, m0);
-          tma_load_2d_2sm(sB + stage * G2_B_STRIDE, &tmB, &full[stage], kb * BK2, n0);
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {   // k past K (a ragged tail) is zero-filled by TMA
+            const int k0 = (kb * KS + ks) * BK2;
+            if (a_kblock > 0)
+              tma_load_3d_2sm(sA + stage * A_STAGE + ks * G2_A_BYTES, &tmA, &full[stage], k0 % a_kblock, m0, k0 / a_kblock);
+            else
+              tma_load_2d_2sm(sA + stage * A_STAGE + ks * G2_A_BYTES, &tmA, &full[stage], k0, m0);
+            tma_load_2d_2sm(sB + stage * B_STAGE + ks * G2_B_STRIDE, &tmB, &full[stage], k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -115,14 +123,16 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * G2_A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * G2_B_STRIDE);
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
-          for (int k = 0; k < BK2 / 16; ++k)
-            umma_bf16_2cta(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int k = 0; k < BK2 / 16; ++k)
+              umma_bf16_2cta(d_tmem, umma_desc_sw128(a_addr + ks * G2_A_BYTES + k * 32), umma_desc_sw128(b_addr + ks * G2_B_STRIDE + k * 32),
+                             idesc, (kb | ks | k) != 0 ? 1u : 0u);
           umma_commit_2cta(&empty[stage]);
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_2cta(&tfull[as]);
       }
@@ -152,10 +162,10 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int MODE>
+template <int MODE, int KS>
 void launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int BN, int a_kblock, const GemmEpi& epi,
              cudaStream_t stream) {
-  auto kern = gemm_bf16_2cta<MODE>;
+  auto kern = gemm_bf16_2cta<MODE, KS>;
   ensure_dyn_smem(kern, G2_SMEM);
   const int tiles = ((M + 2 * BM2 - 1) / (2 * BM2)) * ((N + BN - 1) / BN);
   const int clusters = device_sm_count() / 2;
@@ -178,9 +188,10 @@ int gemm2_fit_tile_width(int M, int N) {
   for (int bn = 256; bn >= 64; bn -= 16) {
     const long long tiles = static_cast<long long>(num_mp) * ((N + bn - 1) / bn);
     const long long waves = (tiles + clusters - 1) / clusters;
-    // per-tile time is bound by operand delivery L2 -> SM, ~ (16 KB of A + 64 B x bn of B) per k-block at ~42 B/clk/SM:
-    // proportional to bn + 257 (fits the measured width sweep within 5 %); narrow tiles pay for re-reading A
-    const double cost = static_cast<double>(waves) * (bn + 257.0);
+    // per-tile time = a fixed part per k step (operand delivery of the 16 KB A block, barrier round trips of the issuing
+    // thread) + a part proportional to the width: ~ bn + 100 with 128-wide k stages (round-2 sweep: 256 / 224 / 176 columns
+    // take 27.1 / 23.4 / 20.6 us per wave at K = 4096); it was bn + 257 with 64-wide stages
+    const double cost = static_cast<double>(waves) * (bn + 100.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -201,14 +212,22 @@ void launch_gemm_2cta(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, in
     tmA = make_tmap_2d(A, M, K, lda, BM2);
   }
   CUtensorMap tmB = make_tmap_2d(B, N, K, ldb, bn / 2);
+  // 128-wide k stages by default: -4..7 % on every DiT GEMM shape at M = 1536 against 64-wide ones on the same box
+  // (profiles/r02_gemm_kstage_sweep.txt); LTX_GEMM_KS=1 selects the 64-wide pipeline
+  static const int ks_env = [] { const char* e = getenv("LTX_GEMM_KS"); return e ? atoi(e) : 2; }();
+  const bool ks2 = ks_env == 2;
+#define LTX_G2_LAUNCH(MODE_)                                                            \
+  if (ks2) launch2<MODE_, 2>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream);             \
+  else launch2<MODE_, 1>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream)
   switch (epi.mode) {
-    case EPI_BF16: launch2<EPI_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
-    case EPI_GELU_BF16: launch2<EPI_GELU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
-    case EPI_GATE_RESID: launch2<EPI_GATE_RESID>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
-    case EPI_F32: launch2<EPI_F32>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
-    case EPI_SILU_BF16: launch2<EPI_SILU_BF16>(tmA, tmB, M, N, K, bn, a_kblock, epi, stream); break;
+    case EPI_BF16: LTX_G2_LAUNCH(EPI_BF16); break;
+    case EPI_GELU_BF16: LTX_G2_LAUNCH(EPI_GELU_BF16); break;
+    case EPI_GATE_RESID: LTX_G2_LAUNCH(EPI_GATE_RESID); break;
+    case EPI_F32: LTX_G2_LAUNCH(EPI_F32); break;
+    case EPI_SILU_BF16: LTX_G2_LAUNCH(EPI_SILU_BF16); break;
     default: LTX_CHECK(false, 2, "bad GEMM epilogue mode");
   }
+#undef LTX_G2_LAUNCH
 }
 
 }  // namespace ltx
