@@ -11,6 +11,8 @@
 //   A tile (tap, k-chunk) = 4-D TMA box at (t0+dt, h0+dh, w0+dw, k0) of the padded volume -> [128 rows x 64 ch], 128B swizzle
 //   B tile               = rows [tap*Cout + n0, +BN) x cols [k0, +64) of the [27*Cout, Cin] weight matrix.
 // Warp roles and pipelines are those of gemm.cu (TMA producer / MMA issuer / 4 epilogue warps, 2 TMEM stages).
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 #include "ltx_internal.h"
 #include "ptx.cuh"
@@ -21,13 +23,17 @@ namespace {
 
 constexpr int CBM = 128, CBK = 64, CONV_THREADS = 192;
 
-template <int BN>
+// KS = 64-channel k chunks per pipeline stage.  KS = 2 (tiles up to 128 columns, Cin a multiple of 128): a stage holds both
+// halves of a 128-channel slice of one tap, so the issuing thread waits on / commits to half as many barriers per k -- the
+// same change that bought 4-7 % on the DiT GEMMs (profiles/r02_gemm_kstage_sweep.txt).
+template <int BN, int KS = 1>
 struct ConvCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) / KS;
   static constexpr uint32_t A_BYTES = CBM * CBK * 2;
   static constexpr uint32_t B_BYTES = BN * CBK * 2;
+  static constexpr uint32_t A_STAGE = KS * A_BYTES, B_STAGE = KS * B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
-  static constexpr size_t SMEM = 1024 + STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
+  static constexpr size_t SMEM = 1024 + STAGES * (A_STAGE + B_STAGE) + (2 * STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
 };
 
 struct ConvGeom {
@@ -100,17 +106,17 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int KS>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
                const ConvEpi ep) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, KS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint8_t* sB = smem + STAGES * Cfg::A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_STAGE);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -122,7 +128,7 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int num_n = (g.Cout + BN - 1) / BN;
   const int num_mn = num_m * num_n;
   const int num_tiles = num_mn * g.ksplit;
-  const int kchunks = g.Cin / CBK;
+  const int kchunks = g.Cin / (CBK * KS);   // pipeline steps per tap (KS * 64 channels each)
   const int taps_per_split = g.ntaps / g.ksplit;
   const int num_k = taps_per_split * kchunks;
 
@@ -155,9 +161,12 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const int tap = g.tap0 + wtap;
           const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmX, &full[stage], kc * CBK, w0 + dw, h0 + dh, t0 + dt);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmW, &full[stage], kc * CBK, wtap * g.Cout + n_blk * BN);
+          mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE + Cfg::B_STAGE);
+#pragma unroll
+          for (int s2 = 0; s2 < KS; ++s2) {
+            tma_load_4d(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
+            tma_load_2d(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wtap * g.Cout + n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -177,12 +186,14 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE);
 #pragma unroll
-          for (int k = 0; k < CBK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int s2 = 0; s2 < KS; ++s2)
+#pragma unroll
+            for (int k = 0; k < CBK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128(a_addr + s2 * Cfg::A_BYTES + k * 32), umma_desc_sw128(b_addr + s2 * Cfg::B_BYTES + k * 32),
+                        idesc, (kb | s2 | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -529,15 +540,23 @@ int best_pow2(int extent, int budget) {
   return best;
 }
 
-template <int BN, int MODE>
-void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
-  using Cfg = ConvCfg<BN>;
-  auto kern = conv3d_tcgen05<BN, MODE>;
+template <int BN, int MODE, int KS>
+void conv_launch_ks(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+  using Cfg = ConvCfg<BN, KS>;
+  auto kern = conv3d_tcgen05<BN, MODE, KS>;
   ensure_dyn_smem(kern, Cfg::SMEM);
   const int tiles = g.nt * g.nh * g.nw * ((g.Cout + BN - 1) / BN) * g.ksplit;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
   LTX_CUDA(cudaGetLastError());
+}
+
+template <int BN, int MODE>
+void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+  // 128-channel stages where they fit: tiles up to 128 columns (3 / 4 stages of 64 / 48 KB stay in flight) and whole pairs of chunks
+  static const int ks_env = [] { const char* e = getenv("LTX_CONV_KS"); return e ? atoi(e) : 2; }();
+  if (BN <= 128 && ks_env == 2 && g.Cin % (2 * CBK) == 0) conv_launch_ks<BN, MODE, (BN <= 128 ? 2 : 1)>(tmX, tmW, g, ep, s);
+  else conv_launch_ks<BN, MODE, 1>(tmX, tmW, g, ep, s);
 }
 
 template <int BN>
