@@ -36,5 +36,11 @@ for _ in range(3):
     ctx._check(ctx.lib.ltx_op_rmsnorm_mod(ctx.handle, xr.data_ptr(), hr.data_ptr(), M, D, tb[0].data_ptr(), tb[1].data_ptr(), tb[2].data_ptr(), tb[3].data_ptr(), 1e-6, 0))
     ctx._check(ctx.lib.ltx_op_qknorm_rope(ctx.handle, qkr.data_ptr(), M, D, wn.data_ptr(), cs.data_ptr(), sn.data_ptr(), M, 1e-6))
     ctx._check(ctx.lib.ltx_guided_euler_step_dev(ctx.handle, lat.data_ptr(), vc.data_ptr(), vu.data_ptr(), vs.data_ptr(), vp.data_ptr(), 1, n, 4.0, 0.0, 0.5, 0.0, 0.7, 0.5))
+# few-row GEMMs of an Ulysses sp = 8 shard (M = 192): split-K weight-streaming kernel, D x D and FFN-out shapes
+A192 = torch.randn(192, 16384, device="cuda").bfloat16(); x192 = torch.randn(192, 4096, device="cuda")
+Bfo = (torch.randn(4096, 16384, device="cuda") / 128).bfloat16(); o192 = torch.empty(192, 4096, device="cuda", dtype=torch.bfloat16)
+for _ in range(2):
+    ctx._check(ctx.lib.ltx_op_gemm(ctx.handle, A192.data_ptr(), Bo.data_ptr(), bias.data_ptr(), o192.data_ptr(), 192, 4096, 4096, 0, -2))
+    ctx._check(ctx.lib.ltx_op_gemm_resid(ctx.handle, A192.data_ptr(), Bfo.data_ptr(), bias.data_ptr(), x192.data_ptr(), gate.data_ptr(), gate.data_ptr(), None, 192, 4096, 16384, 0.5))
 ctx.sync()
 print("ok")

@@ -12,8 +12,8 @@ for r in rows[hi + 1:]:
 skip = ("fill_normal", "permute_conv_weight", "quantize_kernel")
 tot = sum(v[1] for k, v in agg.items() if not any(s in k[0] for s in skip))
 with open(f"profiles/{R}_launches_dit_step_summary.md", "w") as f:
-    f.write(f"# ncu launch list, `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (B200, first 2400 launches)\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 2400`; per-launch times are cold-cache and serialised -- compare SHARES.\n"
+    f.write(f"# ncu launch list, `LTX_GRAPH=0 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity --no-cfg5` (B200, first 2600 launches)\n\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -c 2600`; per-launch times are cold-cache and serialised -- compare SHARES.\n"
             "Weight-init kernels (`fill_normal_kernel`, `permute_conv_weight_kernel`) are excluded. The window covers model init, the text-cache build and ~4 denoise steps.\n\n"
             "| kernel | grid | block | launches | total us | avg us | share |\n|---|---|---|---|---|---|---|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
