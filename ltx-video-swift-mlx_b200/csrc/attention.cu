@@ -18,6 +18,15 @@
 //               running max / sum in fp32 (exp2 domain, ex2.approx); the output accumulator in TMEM is rescaled only when
 //               the row max grows by more than 2^8 (lazy rescale, exact after the final 1/l normalisation); P is packed to
 //               bf16x2 and stored over the first 32 columns of the S buffer it came from.
+// PAIR = true (Nq > 128): two CTAs of a cluster -- adjacent 128-query tiles of one head, on the two SMs of a TPC -- share every
+// K / V^T tile: each CTA loads HALF of it (32 of the 64 keys of K, 64 of the 128 feature rows of V^T) and the leader issues
+// tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in the leader's tensor memory, 128-255 in the peer's).  Why: the
+// one-CTA form is bound by shared-memory traffic (profiles/r02_attention_experiments.txt) -- per 64-key step an SM reads
+// 8 x (4 KB Q + 2 KB K) + 4 x 4 KB V^T and takes 32 KB of TMA writes; in pair mode the B halves and the TMA writes halve: 96 -> 64 KB.
+// Protocol as in gemm2.cu: 2-SM TMA loads report to the LEADER's full barriers (armed for both CTAs' bytes, the peer adds a remote
+// arrive), tcgen05.commit multicasts to both CTAs (S landed, K / V stage free, PV retired), each CTA's softmax warps work on their
+// own 128 rows and arrive -- one elected lane per warp -- on the leader's p_full.
+//
 // tcgen05.commit tracks every earlier MMA of the issuing thread: "S(j+2) landed" implies "PV(j) retired", i.e. the buffer's
 // previous P has been consumed.  TMEM: S|P buffers [0,64) [64,128), O [128, 128 + HD).
 // V is consumed as V^T [head_dim, keys] (K-major for the PV product); the V-projection GEMM writes it in that layout.
@@ -37,13 +46,15 @@ constexpr int TQ = 128, TK = 64;
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
-template <int HD>
+template <int HD, bool PAIR>
 struct AttCfg {
+  static constexpr int KROWS = PAIR ? TK / 2 : TK;       // keys of a K tile held by one CTA
+  static constexpr int VROWS = PAIR ? HD / 2 : HD;       // feature rows of a V^T tile held by one CTA
   static constexpr uint32_t Q_TILE = 128 * HD * 2;       // [128 rows x HD]: HD/64 swizzled halves of 16 KB
   static constexpr uint32_t Q_HALF = 128 * 64 * 2;
-  static constexpr uint32_t K_TILE = TK * HD * 2;        // [64 keys x HD]: HD/64 halves of 8 KB
-  static constexpr uint32_t K_HALF = TK * 64 * 2;
-  static constexpr uint32_t V_TILE = HD * TK * 2;        // [HD rows x 64 keys]
+  static constexpr uint32_t K_TILE = KROWS * HD * 2;     // [keys x HD]: HD/64 halves
+  static constexpr uint32_t K_HALF = KROWS * 64 * 2;
+  static constexpr uint32_t V_TILE = VROWS * TK * 2;     // [feature rows x 64 keys]
   static constexpr size_t SMEM = 1024 + Q_TILE + 2 * K_TILE + 2 * V_TILE + 16 * 8 + 16;
 };
 
@@ -63,11 +74,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int HD>
+template <int HD, bool PAIR>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using Cfg = AttCfg<HD>;
+  using Cfg = AttCfg<HD, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
@@ -90,38 +101,67 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.Nk + TK - 1) / TK;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;   // pair mode: CTAs 2i, 2i+1 of the x dimension = adjacent query tiles
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
+    // pair mode: the full barriers that count are the leader's (its expect_tx arrive + the peer's remote arrive); p_full takes one
+    // arrive per softmax warp of both CTAs; everything a tcgen05.commit signals is multicast to both CTAs' copies
+    mbar_init(q_full, PAIR ? 2 : 1);
     mbar_init(pv_done, 1);
     mbar_init(o_final, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
+      mbar_init(&k_full[i], PAIR ? 2 : 1);
       mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
+      mbar_init(&v_full[i], PAIR ? 2 : 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], PAIR ? 8 : 128);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta<ATT_TMEM_COLS>(tmem_slot);
+    else tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (PAIR && !leader && threadIdx.x == 0) {
+    // the leader's MMAs address both CTAs' tensor memory with ONE address: the paired allocation must have landed on the same
+    // columns in both (it does -- cta_group::2 allocations are symmetric; this check makes a violation loud instead of wrong)
+    uint32_t remote_addr, theirs;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote_addr) : "r"(smem_u32(tmem_slot)));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(theirs) : "r"(remote_addr) : "memory");
+    if (theirs != tmem_base) {
+      printf("ltxcuda: attention pair got asymmetric tensor-memory columns (%u vs %u)\n", theirs, tmem_base);
+      __trap();
+    }
+  }
   griddep_launch();
   griddep_wait();   // PDL: the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Cfg::Q_TILE);
+      // pair mode: the leader arms the barrier for both CTAs' bytes, the peer adds its arrive; 2-SM loads report to the leader
+      auto arm = [&](uint64_t* bar, uint32_t bytes) {
+        if (!PAIR) mbar_arrive_expect_tx(bar, bytes);
+        else if (leader) mbar_arrive_expect_tx(bar, 2 * bytes);
+        else mbar_arrive_remote(bar, 0);
+      };
+      auto load2 = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+        if (PAIR) tma_load_2d_2sm(dst, m, bar, c0, c1);
+        else tma_load_2d(dst, m, bar, c0, c1);
+      };
+      arm(q_full, Cfg::Q_TILE);
 #pragma unroll
       for (int hh = 0; hh < HD / 64; ++hh)
-        tma_load_2d(sQ + hh * Cfg::Q_HALF, &tmQ, q_full, h * HD + hh * 64, b * p.Nq + q_tile * TQ);
+        load2(sQ + hh * Cfg::Q_HALF, &tmQ, q_full, h * HD + hh * 64, b * p.Nq + q_tile * TQ);
       // K and V^T tiles are fetched independently, each as soon as one of its two buffers is free
       int nk = 0, nv = 0;
       uint32_t spins = 0;
@@ -129,17 +169,20 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         bool progress = false;
         if (nk < n_kv && mbar_test(&k_empty[nk & 1], ((nk >> 1) & 1) ^ 1)) {
           uint8_t* dst = sK + (nk & 1) * Cfg::K_TILE;
-          mbar_arrive_expect_tx(&k_full[nk & 1], Cfg::K_TILE);
+          arm(&k_full[nk & 1], Cfg::K_TILE);
 #pragma unroll
-          for (int hh = 0; hh < HD / 64; ++hh)
-            tma_load_2d(dst + hh * Cfg::K_HALF, &tmK, &k_full[nk & 1], h * HD + hh * 64, b * p.Nk + nk * TK);
+          for (int hh = 0; hh < HD / 64; ++hh)   // pair mode: this CTA's half of the tile's keys
+            load2(dst + hh * Cfg::K_HALF, &tmK, &k_full[nk & 1], h * HD + hh * 64, b * p.Nk + nk * TK + static_cast<int>(rank) * Cfg::KROWS);
           ++nk;
           progress = true;
         }
         if (nv < n_kv && mbar_test(&v_empty[nv & 1], ((nv >> 1) & 1) ^ 1)) {
           // V^T is a 3-D map (keys, features, batch): keys past Nk are zero-filled, never another batch's columns
-          mbar_arrive_expect_tx(&v_full[nv & 1], Cfg::V_TILE);
-          tma_load_3d(sV + (nv & 1) * Cfg::V_TILE, &tmV, &v_full[nv & 1], nv * TK, h * HD, b);
+          arm(&v_full[nv & 1], Cfg::V_TILE);
+          if (PAIR)   // this CTA's half of the feature rows
+            tma_load_3d_2sm(sV + (nv & 1) * Cfg::V_TILE, &tmV, &v_full[nv & 1], nv * TK, h * HD + static_cast<int>(rank) * Cfg::VROWS, b);
+          else
+            tma_load_3d(sV + (nv & 1) * Cfg::V_TILE, &tmV, &v_full[nv & 1], nv * TK, h * HD, b);
           ++nv;
           progress = true;
         }
@@ -152,42 +195,66 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, TK);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(PAIR ? 256 : 128, TK);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(PAIR ? 256 : 128, HD);
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_2cta(bar);   // both CTAs' copies
+        else umma_commit(bar);
+      };
+      // every operand descriptor of the loop is a constant of the CTA: build them once, so that the issuing thread's
+      // instruction stream per MMA is the tcgen05.mma itself (it is one thread; its issue rate is part of the step)
       const uint32_t q_addr = smem_u32(sQ);
-      auto issue_S = [&](int j) {
-        const int st = j & 1;
+      uint64_t qd[HD / 16], kd[2][HD / 16], vd[2][TK / 16];
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        qd[kk] = umma_desc_sw128(q_addr + (kk >> 2) * Cfg::Q_HALF + (kk & 3) * 32);
+#pragma unroll
+        for (int st = 0; st < 2; ++st)
+          kd[st][kk] = umma_desc_sw128(smem_u32(sK + st * Cfg::K_TILE) + (kk >> 2) * Cfg::K_HALF + (kk & 3) * 32);
+      }
+#pragma unroll
+      for (int kk = 0; kk < TK / 16; ++kk)
+#pragma unroll
+        for (int st = 0; st < 2; ++st) vd[st][kk] = umma_desc_sw128(smem_u32(sV + st * Cfg::V_TILE) + kk * 32);
+      auto issue_S = [&](int j, auto st_tag) {
+        constexpr int st = decltype(st_tag)::value;
         mbar_wait(&k_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::K_TILE);
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk)
-          umma_bf16(tmem_base + st * TK, umma_desc_sw128(q_addr + (kk >> 2) * Cfg::Q_HALF + (kk & 3) * 32),
-                    umma_desc_sw128(k_addr + (kk >> 2) * Cfg::K_HALF + (kk & 3) * 32), idesc_s, kk != 0);
-        umma_commit(&s_full[st]);    // also covers PV(j-2): the buffer's previous P has been consumed
-        umma_commit(&k_empty[st]);
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          if (PAIR) umma_bf16_2cta(tmem_base + st * TK, qd[kk], kd[st][kk], idesc_s, kk != 0);
+          else umma_bf16(tmem_base + st * TK, qd[kk], kd[st][kk], idesc_s, kk != 0);
+        }
+        commit(&s_full[st]);    // also covers PV(j-2): the buffer's previous P has been consumed
+        commit(&k_empty[st]);
       };
-      auto issue_PV = [&](int j) {
-        const int st = j & 1;
+      auto issue_PV = [&](int j, auto st_tag) {
+        constexpr int st = decltype(st_tag)::value;
         mbar_wait(&v_full[st], (j >> 1) & 1);
         mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * Cfg::V_TILE);
 #pragma unroll
-        for (int kk = 0; kk < TK / 16; ++kk)   // A = P(j) from tensor memory: 16 keys = 8 packed columns per k-step
-          umma_bf16_ts(tmem_base + 2 * TK, tmem_base + st * TK + kk * 8, umma_desc_sw128(v_addr + kk * 32), idesc_o,
-                       (j | kk) != 0);
-        umma_commit(pv_done);
-        umma_commit(&v_empty[st]);
-        if (j == n_kv - 1) umma_commit(o_final);
+        for (int kk = 0; kk < TK / 16; ++kk) {  // A = P(j) from tensor memory: 16 keys = 8 packed columns per k-step
+          if (PAIR) umma_bf16_ts_2cta(tmem_base + 2 * TK, tmem_base + st * TK + kk * 8, vd[st][kk], idesc_o, (j | kk) != 0);
+          else umma_bf16_ts(tmem_base + 2 * TK, tmem_base + st * TK + kk * 8, vd[st][kk], idesc_o, (j | kk) != 0);
+        }
+        commit(pv_done);
+        commit(&v_empty[st]);
+        if (j == n_kv - 1) commit(o_final);
       };
+      using S0 = std::integral_constant<int, 0>;
+      using S1 = std::integral_constant<int, 1>;
       mbar_wait(q_full, 0);
-      issue_S(0);
-      if (n_kv > 1) issue_S(1);
-      for (int j = 0; j < n_kv; ++j) {
-        issue_PV(j);
-        if (j + 2 < n_kv) issue_S(j + 2);   // into the S buffer PV(j) has just read P from (in-order tensor pipe)
+      issue_S(0, S0{});
+      if (n_kv > 1) issue_S(1, S1{});
+      for (int j = 0; j < n_kv; j += 2) {   // two steps per trip: the stage index is a compile-time constant
+        issue_PV(j, S0{});
+        if (j + 2 < n_kv) issue_S(j + 2, S0{});   // into the S buffer PV(j) has just read P from (in-order tensor pipe)
+        if (j + 1 < n_kv) {
+          issue_PV(j + 1, S1{});
+          if (j + 3 < n_kv) issue_S(j + 3, S1{});
+        }
       }
     }
   } else {
@@ -281,7 +348,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       l_run += rs0 + rs1;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[st]);
+      if (PAIR) {   // one arrive per warp on the LEADER's barrier
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&p_full[st], 0);
+      } else {
+        mbar_arrive(&p_full[st]);
+      }
     };
     {
       const bool ragged = (p.Nk % TK) != 0;
@@ -335,25 +407,48 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_2cta<ATT_TMEM_COLS>(tmem_base);
+    else tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
   }
 }
 
-template <int HD>
+template <int HD, bool PAIR>
 void attention_launch(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, const bf16* Vt, int64_t ldvb, const AttnParams& p,
                       int D, cudaStream_t stream) {
-  using Cfg = AttCfg<HD>;
-  ensure_dyn_smem(attention_fwd_tcgen05<HD>, Cfg::SMEM);
+  using Cfg = AttCfg<HD, PAIR>;
+  auto kern = attention_fwd_tcgen05<HD, PAIR>;
+  ensure_dyn_smem(kern, Cfg::SMEM);
   CUtensorMap tmQ = make_tmap_2d(Q, static_cast<uint64_t>(p.B) * p.Nq, D, ldq, 128);
-  CUtensorMap tmK = make_tmap_2d(K, static_cast<uint64_t>(p.B) * p.Nk, D, ldk, TK);
-  CUtensorMap tmV = make_tmap_3d(Vt, p.Nk, D, p.B, static_cast<uint64_t>(p.B) * ldvb, ldvb, TK, HD);
-  dim3 grid((p.Nq + TQ - 1) / TQ, p.H, p.B);
-  launch_pdl(PDL_ATTN, attention_fwd_tcgen05<HD>, grid, dim3(ATT_THREADS), Cfg::SMEM, stream, tmQ, tmK, tmV, p);
-  LTX_CUDA(cudaGetLastError());
+  CUtensorMap tmK = make_tmap_2d(K, static_cast<uint64_t>(p.B) * p.Nk, D, ldk, Cfg::KROWS);
+  CUtensorMap tmV = make_tmap_3d(Vt, p.Nk, D, p.B, static_cast<uint64_t>(p.B) * ldvb, ldvb, TK, Cfg::VROWS);
+  int tiles = (p.Nq + TQ - 1) / TQ;
+  if (PAIR) tiles = (tiles + 1) & ~1;   // whole pairs: an odd last tile gets a partner whose rows are all past Nq (never stored)
+  dim3 grid(tiles, p.H, p.B);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (pdl_enabled(PDL_ATTN)) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (PAIR) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  LTX_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, p));
 }
 
 }  // namespace
@@ -377,10 +472,16 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
     p.o_rows_per_block = rows_per_block;
     p.o_blocks = *o_blocks;
   }
-  if (D == H * 128)
-    attention_launch<128>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
-  else
-    attention_launch<64>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
+  // CTA pairs sharing the K / V tiles whenever there are at least two query tiles (LTX_ATT_PAIR=0: one CTA per tile everywhere)
+  static const bool pair_on = [] { const char* e = getenv("LTX_ATT_PAIR"); return e ? atoi(e) != 0 : true; }();
+  const bool pair = pair_on && Nq > TQ;
+  if (D == H * 128) {
+    if (pair) attention_launch<128, true>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
+    else attention_launch<128, false>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
+  } else {
+    if (pair) attention_launch<64, true>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
+    else attention_launch<64, false>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
+  }
 }
 
 }  // namespace ltx

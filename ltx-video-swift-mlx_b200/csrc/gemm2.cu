@@ -111,6 +111,7 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (leader && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(2 * BM2, BN);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA)), b_desc0 = umma_desc_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -123,13 +124,15 @@ gemm_bf16_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
-          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
+          // descriptors: stage base + a compile-time offset (the start-address field counts 16-byte units and cannot carry
+          // out of its 14 bits: all operand buffers sit below 256 KB) -- the issuing thread spends one add per operand
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage) * (A_STAGE >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(stage) * (B_STAGE >> 4);
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
             for (int k = 0; k < BK2 / 16; ++k)
-              umma_bf16_2cta(d_tmem, umma_desc_sw128(a_addr + ks * G2_A_BYTES + k * 32), umma_desc_sw128(b_addr + ks * G2_B_STRIDE + k * 32),
+              umma_bf16_2cta(d_tmem, a_desc + ((ks * G2_A_BYTES + k * 32) >> 4), b_desc + ((ks * G2_B_STRIDE + k * 32) >> 4),
                              idesc, (kb | ks | k) != 0 ? 1u : 0u);
           umma_commit_2cta(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -225,6 +225,18 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// cta_group::2 with the A operand of each CTA read from ITS tensor memory (TS form): a_tmem addresses, in both CTAs, a
+// [128 lanes x 8 columns] block holding 16 bf16 of the K slice per row, packed two per column
+__device__ __forceinline__ void umma_bf16_ts_2cta(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // arrive (once all earlier MMAs of this thread completed) on the barrier at this smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask = 0x3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
