@@ -111,6 +111,13 @@ int ltx_fuse_lora(ltx_ctx* ctx, const char* key, const void* down, const void* u
  * fp32 rounding, attention in fp32; velocity within rel-L2 1e-4 (the mode BASELINE config 0, "random-init fp32", is checked
  * in).  Must be called before the DiT weights are loaded; single GPU, no quantisation; the VAE is unaffected. */
 int ltx_set_precision(ltx_ctx* ctx, int bits);
+/* Where quantised weights live (takes effect at the next ltx_finalize_weights with quant_bits 8 / 4).  0 (default): as codes --
+ * 13 GB (int8) / 6.5 GB (int4) for the video DiT; every GEMM dequantises on the fly (fused kernel for M <= 256, a per-GEMM bf16
+ * panel above).  1: materialised -- every Linear is quantised exactly as in mode 0 and its dequantised values (s * q + beta,
+ * rounded to bf16: the operand values the fused kernels feed the tensor cores) replace the bf16 weight once, at load time; the
+ * codes are dropped.  Same results bit for bit as mode 0 at the speed and footprint of the bf16 model: the reference quantises to
+ * fit 32 GB of unified memory (Pipeline/LTXPipeline.swift:323-333), which a 180 GB B200 does not need. */
+int ltx_set_quant_storage(ltx_ctx* ctx, int materialise);
 /* Random-init weights of the configured architecture, generated on the device (no checkpoints in this environment).
  * which: bit mask, 1 = DiT, 2 = VAE decoder, 4 = VAE encoder, 8 = latent upscaler, 16 = the audio / cross-modal tensors of the
  * dual audio/video transformer (use 17 for the whole LTX2Transformer). */

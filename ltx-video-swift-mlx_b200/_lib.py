@@ -55,6 +55,7 @@ SIGNATURES = {
     "ltx_map_weight_key": (_I, [_I, C.c_char_p, C.c_char_p, _SZ]),
     "ltx_fuse_lora": (_I, [_P, C.c_char_p, _P, _P, _I, _I, _F]),
     "ltx_set_precision": (_I, [_P, _I]),
+    "ltx_set_quant_storage": (_I, [_P, _I]),
     "ltx_init_random_weights": (_I, [_P, _I, _U64]),
     "ltx_finalize_weights": (_I, [_P, _I, _I]),
     "ltx_dit_forward": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, C.POINTER(LtxDitFlags), _P]),

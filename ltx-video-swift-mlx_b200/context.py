@@ -230,6 +230,11 @@ class LtxContext:
         """16 = bf16 mode (default), 32 = fp32 mode (fp32 DiT weights, split-bf16 tensor-core GEMMs); before loading weights."""
         self._check(self.lib.ltx_set_precision(self.handle, int(bits)))
 
+    def set_quant_storage(self, materialise: bool):
+        """False (default): quantised weights stay as codes; True: their dequantised bf16 values replace the weights at
+        finalize time (same results, bf16 speed and footprint).  Before finalize_weights(quant_bits=8 | 4)."""
+        self._check(self.lib.ltx_set_quant_storage(self.handle, int(materialise)))
+
     def init_random_weights(self, which: int = 3, seed: int = 0):
         self._check(self.lib.ltx_init_random_weights(self.handle, which, seed))
 

@@ -426,6 +426,10 @@ int ltx_set_precision(ltx_ctx* c, int bits) {
   });
 }
 
+int ltx_set_quant_storage(ltx_ctx* c, int materialise) {
+  return guarded(c, [&] { c->quant_materialise = materialise ? 1 : 0; });
+}
+
 int ltx_finalize_weights(ltx_ctx* c, int quant_bits, int group_size) {
   return guarded(c, [&] {
     LTX_CHECK(quant_bits == 16 || quant_bits == 8 || quant_bits == 4, LTX_ERR_UNSUPPORTED, "quant_bits must be 16, 8 or 4");

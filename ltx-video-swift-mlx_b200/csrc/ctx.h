@@ -223,6 +223,7 @@ struct ltx_ctx {
   std::map<std::string, ltx::DevTensor> tensors;  // raw tensors by post-mapping key
   std::unordered_map<const void*, ltx::QuantW> qw;  // quantised replacements, keyed by the bf16 weight pointer they replace
   int quant_bits = 16;
+  int quant_materialise = 0;                      // 1: dequantised bf16 values replace the weights at finalize (ltx_set_quant_storage)
   ltx::DevBuf q_panel;                            // bf16 conversion panel of the large-M quantised GEMM path
   ltx::DevBuf gemm_ws;                            // split-K workspace of the weight-streaming GEMM: [counters 64 KB | fp32 partials]
   std::vector<void*> owned;                       // packed allocations made by finalize

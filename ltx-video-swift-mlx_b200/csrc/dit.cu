@@ -357,20 +357,32 @@ void dit_quantize(ltx_ctx* c, int bits) {
     LTX_CUDA(cudaMalloc(&handle, 16));
     c->owned.push_back(q); c->owned.push_back(s); c->owned.push_back(b); c->owned.push_back(handle);
     launch_quantize(w, N, K, bits, q, s, b, c->stream);
-    LTX_CUDA(cudaStreamSynchronize(c->stream));
     QuantW r;
     r.q = q; r.scales = s; r.biases = b; r.bits = bits; r.n = N; r.k = K;
+    if (c->quant_materialise) {
+      // materialised storage: the weight keeps its place and dtype, its values become s * q + beta (the panel conversion's
+      // arithmetic and rounding, i.e. exactly what the fused kernels would feed the tensor cores); the codes are dropped
+      launch_dequantize_panel(r, const_cast<bf16*>(w), c->stream);
+      LTX_CUDA(cudaStreamSynchronize(c->stream));
+      for (void* ptr : {static_cast<void*>(q), static_cast<void*>(s), static_cast<void*>(b), handle}) {
+        cudaFree(ptr);
+        c->owned.erase(std::find(c->owned.begin(), c->owned.end(), ptr));
+      }
+      return;
+    }
+    LTX_CUDA(cudaStreamSynchronize(c->stream));
     c->qw[handle] = r;
     to_free.push_back(w);
     w = reinterpret_cast<const bf16*>(handle);
   };
+  const bool codes = !c->quant_materialise;
   qf(c->w_patch, D, g.in_channels);
   qf(c->w_c1, D, g.caption_channels);
   qf(c->w_c2, D, D);
   qf(c->w_out, g.out_channels, D);
   for (auto& b : c->blocks) {
-    qf(b.a1.wq, 2 * D, D);            // packed q|k
-    b.a1.wk = nullptr;
+    qf(b.a1.wq, 2 * D, D);            // packed q|k (the v rows behind them are quantised by the next call: rows are independent)
+    if (codes) b.a1.wk = nullptr;
     qf(b.a1.wv, D, D); qf(b.a1.wo, D, D);
     qf(b.a2.wq, D, D); qf(b.a2.wk, D, D); qf(b.a2.wv, D, D); qf(b.a2.wo, D, D);
     qf(b.w_in, FF, D); qf(b.w_out, D, FF);
@@ -395,6 +407,7 @@ void dit_quantize(ltx_ctx* c, int bits) {
       qf(b.w_in, FFa, Da); qf(b.w_out, Da, FFa);
     }
   }
+  if (!codes) { c->quant_bits = bits; return; }   // materialised: the structs still point at (now dequantised) bf16 weights
   for (const void* p : to_free) release(p);
   // one bf16 panel for the large-M path of launch_gemm_q, sized for the largest weight (the FFN matrices)
   size_t max_elems = 0;

@@ -98,3 +98,35 @@ def test_quantised_dit_drift(bits, tol):
     assert err > 1e-5               # and the quantised path really ran
     ctx16.close()
     ctxq.close()
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+def test_materialised_quant_storage_equals_codes(bits):
+    """ltx_set_quant_storage(ctx, 1): the weights are quantised exactly as in the default mode, but their dequantised bf16 values
+    replace them once at load time instead of being rebuilt inside every GEMM.  Same operand values into the same tensor-core
+    products: the two contexts must agree bit for bit (token counts on both sides of the fused-kernel / panel switch at M = 256),
+    and both must differ from the unquantised model."""
+    ocfg, pcfg = small_dit_config(2, 2)
+    ctx16, w = make_ctx_with_dit(ocfg, pcfg, seed=14)
+    ctxc = product().LtxContext(pcfg, 0)
+    ctxc.load_weights(w)
+    ctxc.finalize_weights(quant_bits=bits)
+    ctxm = product().LtxContext(pcfg, 0)
+    ctxm.set_quant_storage(True)
+    ctxm.load_weights(w)
+    ctxm.finalize_weights(quant_bits=bits)
+    gq = torch.Generator().manual_seed(5)
+    for fhw in ((2, 4, 6), (3, 10, 12)):            # 48 and 360 tokens
+        N, S = fhw[0] * fhw[1] * fhw[2], 40
+        lat = torch.randn(1, N, 128, generator=gq).bfloat16()
+        cx = torch.randn(1, S, ocfg.caption_channels, generator=gq)
+        cx = (cx / cx.pow(2).mean(-1, keepdim=True).sqrt()).bfloat16()
+        sig = np.array([0.6], dtype=np.float32)
+        a = ctxc.dit_forward(lat, cx, sig, None, fhw)
+        b = ctxm.dit_forward(lat, cx, sig, None, fhw)
+        ref = ctx16.dit_forward(lat, cx, sig, None, fhw)
+        assert np.isfinite(b).all()
+        assert rel_l2(b, a) <= 2e-3, rel_l2(b, a)     # same operand values; the GEMM kernels (and their summation order) may differ
+        assert rel_l2(b, ref) > 1e-5                  # the quantisation is really in the weights
+    for c in (ctx16, ctxc, ctxm):
+        c.close()
