@@ -18,7 +18,7 @@
 //               running max / sum in fp32 (exp2 domain, ex2.approx); the output accumulator in TMEM is rescaled only when
 //               the row max grows by more than 2^8 (lazy rescale, exact after the final 1/l normalisation); P is packed to
 //               bf16x2 and stored over the first 32 columns of the S buffer it came from.
-// PAIR = true (Nq > 128): two CTAs of a cluster -- adjacent 128-query tiles of one head, on the two SMs of a TPC -- share every
+// PAIR = true (Nq >= 3072, see the dispatch at the bottom): two CTAs of a cluster -- adjacent 128-query tiles of one head, on the two SMs of a TPC -- share every
 // K / V^T tile: each CTA loads HALF of it (32 of the 64 keys of K, 64 of the 128 feature rows of V^T) and the leader issues
 // tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in the leader's tensor memory, 128-255 in the peer's).  Why: the
 // one-CTA form is bound by shared-memory traffic (profiles/r02_attention_experiments.txt) -- per 64-key step an SM reads
@@ -87,14 +87,13 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * Cfg::V_TILE);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
   uint64_t* v_full = bars + 5;    // [2]
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2] per S buffer
   uint64_t* p_full = bars + 11;   // [2] per S buffer
-  uint64_t* pv_done = bars + 13;  // phase j completes when PV(j) has retired (lazy rescale: at step j the count is j-1 or j)
-  uint64_t* o_final = bars + 14;  // the last PV has retired.  Not a phase of pv_done: the softmax warps run up to two PVs ahead
-                                  // of the tensor pipe, and a parity wait cannot tell "two phases behind" from "done"
+  // one tcgen05.commit per MMA group does all the signalling: s_full[st] = 'S(j) landed' = 'the K stage is free' (producer) =
+  // 'PV(j-2) retired'; v_empty[st] = 'PV(j) retired' = 'the V stage is free' (producer) = 'O is stable up to step j' (rescale, epilogue).
+  // No waiter can fall two phases behind on either (each phase needs a tile / probabilities the waiter itself has to supply first).
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
@@ -111,15 +110,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // pair mode: the full barriers that count are the leader's (its expect_tx arrive + the peer's remote arrive); p_full takes one
     // arrive per softmax warp of both CTAs; everything a tcgen05.commit signals is multicast to both CTAs' copies
     mbar_init(q_full, PAIR ? 2 : 1);
-    mbar_init(pv_done, 1);
-    mbar_init(o_final, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], PAIR ? 2 : 1);
-      mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], PAIR ? 2 : 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], PAIR ? 8 : 128);
+      mbar_init(&p_full[i], PAIR ? 8 : 4);   // one arrive per softmax warp
     }
     fence_mbar_init();
   }
@@ -167,7 +163,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       uint32_t spins = 0;
       while (nk < n_kv || nv < n_kv) {
         bool progress = false;
-        if (nk < n_kv && mbar_test(&k_empty[nk & 1], ((nk >> 1) & 1) ^ 1)) {
+        if (nk < n_kv && mbar_test(&s_full[nk & 1], ((nk >> 1) & 1) ^ 1)) {   // the stage is free once the S MMAs that read it have landed
           uint8_t* dst = sK + (nk & 1) * Cfg::K_TILE;
           arm(&k_full[nk & 1], Cfg::K_TILE);
 #pragma unroll
@@ -226,8 +222,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (PAIR) umma_bf16_2cta(tmem_base + st * TK, qd[kk], kd[st][kk], idesc_s, kk != 0);
           else umma_bf16(tmem_base + st * TK, qd[kk], kd[st][kk], idesc_s, kk != 0);
         }
-        commit(&s_full[st]);    // also covers PV(j-2): the buffer's previous P has been consumed
-        commit(&k_empty[st]);
+        commit(&s_full[st]);    // S(j) landed; also: PV(j-2) retired (the buffer's previous P has been consumed) and the K stage is free
       };
       auto issue_PV = [&](int j, auto st_tag) {
         constexpr int st = decltype(st_tag)::value;
@@ -239,9 +234,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (PAIR) umma_bf16_ts_2cta(tmem_base + 2 * TK, tmem_base + st * TK + kk * 8, vd[st][kk], idesc_o, (j | kk) != 0);
           else umma_bf16_ts(tmem_base + 2 * TK, tmem_base + st * TK + kk * 8, vd[st][kk], idesc_o, (j | kk) != 0);
         }
-        commit(pv_done);
-        commit(&v_empty[st]);
-        if (j == n_kv - 1) commit(o_final);
+        commit(&v_empty[st]);   // PV(j) retired: the V stage is free, O is stable up to step j (the softmax warps' rescale and the epilogue wait on it)
       };
       using S0 = std::integral_constant<int, 0>;
       using S1 = std::integral_constant<int, 1>;
@@ -318,7 +311,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
         if (j > 0) {
-          mbar_wait(pv_done, (j - 1) & 1);   // O must be stable: PV(j-1) retired (PV(j) cannot start before P(j) below)
+          mbar_wait(&v_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O must be stable: PV(j-1) retired (PV(j) cannot start before P(j) below)
           tc_fence_after();
           uint32_t r[32];
 #pragma unroll 1
@@ -348,11 +341,10 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       l_run += rs0 + rs1;
       tmem_st_wait();
       tc_fence_before();
-      if (PAIR) {   // one arrive per warp on the LEADER's barrier
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&p_full[st], 0);
-      } else {
-        mbar_arrive(&p_full[st]);
+      __syncwarp();   // every lane's P columns are stored and fenced: one arrive per warp (pair mode: on the LEADER's barrier)
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(&p_full[st], 0);
+        else mbar_arrive(&p_full[st]);
       }
     };
     {
@@ -366,7 +358,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
     // epilogue: O / l -> bf16
-    mbar_wait(o_final, 0);
+    mbar_wait(&v_empty[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);   // the last PV has retired
     tc_fence_after();
     const float inv = 1.0f / l_run;
     // O / l -> bf16, staged through the Q buffer (free now: every MMA has retired) so that the global stores are whole rows
@@ -472,9 +464,12 @@ void launch_attention(const bf16* Q, int64_t ldq, const bf16* K, int64_t ldk, co
     p.o_rows_per_block = rows_per_block;
     p.o_blocks = *o_blocks;
   }
-  // CTA pairs sharing the K / V tiles whenever there are at least two query tiles (LTX_ATT_PAIR=0: one CTA per tile everywhere)
-  static const bool pair_on = [] { const char* e = getenv("LTX_ATT_PAIR"); return e ? atoi(e) != 0 : true; }();
-  const bool pair = pair_on && Nq > TQ;
+  // CTA pairs sharing the K / V tiles on LONG sequences.  Measured after the commits were merged (profiles/r02_attention_experiments.txt
+  // (6)): one CTA per tile is 2-5 % faster at N = 1536 (56.2 vs 57.5 us self, 39.4 vs 41.6 cross), the pair 2-4 % faster from
+  // N = 6144 up (569 vs 581 us; 12672: 2142 vs 2233 us).  LTX_ATT_PAIR=0 / 1: never / whenever there are two query tiles.
+  const char* pair_str = getenv("LTX_ATT_PAIR");   // read per call: the parity tests run every case in both forms
+  const int pair_env = pair_str ? atoi(pair_str) : -1;
+  const bool pair = pair_env < 0 ? Nq >= 3072 : (pair_env != 0 && Nq > TQ);
   if (D == H * 128) {
     if (pair) attention_launch<128, true>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);
     else attention_launch<128, false>(Q, ldq, K, ldk, Vt, ldvb, p, D, stream);

@@ -27,6 +27,26 @@ def test_attention(ctx, B, H, Nq, Nk, masked):
     _run(ctx, B, H, Nq, Nk, masked, 128)
 
 
+@pytest.fixture(params=["0", "1"])
+def pair_mode(request, monkeypatch):
+    """LTX_ATT_PAIR (read by the launcher on every call): 0 = one CTA per query tile, 1 = CTA pairs sharing the K / V tiles
+    whenever there are two query tiles.  The default picks pairs from Nq = 3072 up."""
+    monkeypatch.setenv("LTX_ATT_PAIR", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,masked,HD", [(1, 2, 300, 300, False, 128), (2, 2, 130, 70, True, 128), (1, 4, 1536, 1024, True, 128),
+                                                 (3, 1, 257, 129, False, 128), (1, 4, 1536, 126, False, 64), (2, 2, 300, 70, True, 64)])
+def test_attention_both_forms(ctx, pair_mode, B, H, Nq, Nk, masked, HD):
+    _run(ctx, B, H, Nq, Nk, masked, HD)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,masked,HD", [(1, 2, 3072, 3072, False, 128), (1, 2, 3100, 1030, True, 128), (1, 2, 3200, 200, False, 64)])
+def test_attention_long_sequences_default_form(ctx, B, H, Nq, Nk, masked, HD):
+    """Nq >= 3072: the default dispatch takes the pair form (odd tile counts and a ragged last tile included)."""
+    _run(ctx, B, H, Nq, Nk, masked, HD)
+
+
 # head_dim 64: audio self-attention and the audio<->video cross-modal attentions of the dual block (32 heads x 64)
 @pytest.mark.parametrize("B,H,Nq,Nk,masked", [(1, 2, 126, 126, False), (1, 4, 1536, 126, False), (1, 4, 126, 1536, False),
                                               (2, 2, 300, 70, True), (1, 32, 256, 384, False)])
