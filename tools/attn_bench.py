@@ -12,6 +12,8 @@ for name, B, H, Nq, Nk, masked in [("self1536", 1, 32, 1536, 1536, False), ("cro
                                    ("cfg_self", 2, 32, 1536, 1536, False), ("cfg_cross", 2, 32, 1536, 1024, False),
                                    ("sp8_self", 1, 4, 1536, 1536, False), ("sp8_cross", 1, 32, 192, 1024, False),
                                    ("self6144", 1, 32, 6144, 6144, False), ("self12672", 1, 32, 12672, 12672, False)]:
+    if os.environ.get("ATT_SHAPES") and name not in os.environ["ATT_SHAPES"].split(","):
+        continue
     D = H * 128
     R = 8 if Nq <= 6144 else 3
     q = torch.randn(B * Nq, D, device="cuda").bfloat16(); k = torch.randn(B * Nk, D, device="cuda").bfloat16()
