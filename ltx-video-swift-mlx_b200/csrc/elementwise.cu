@@ -1,6 +1,7 @@
 // HBM-bound row / elementwise kernels of the DiT step: AdaLN-modulated RMSNorm / LayerNorm, q/k RMSNorm-across-heads
 // fused with split RoPE, the timestep-embedding GEMV chain, patchify / unpatchify, and the fused
 // CFG + rescale + STG + GE + Euler update.  All vectorised 16-byte accesses, fp32 math.
+#include <algorithm>
 #include <cstdlib>
 
 #include "ltx_internal.h"
@@ -189,6 +190,110 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fast_kernel(const float* x, b
   }
 }
 
+
+// Streaming form (default for D = 4096): persistent CTAs, three per SM, each with a ring of NST row buffers in shared memory
+// that ONE thread fills with 16 KB bulk copies (cp.async.bulk + mbarrier) -- every row a CTA will ever touch is requested
+// before the first one is reduced, at no register cost: 3 x NST x 16 KB in flight per SM against 64 KB for the register form
+// above (146 registers -> one CTA per SM: load phase, reduce phase, store phase in turn: 2.9 TB/s at M = 1536).  The
+// modulation vectors stay in registers for the CTA's whole life (one L2 read per CTA, not one per 4 rows).
+// Reduction scratch alternates between two slots, so one __syncthreads per reduction is enough; the same barrier tells
+// the filling thread that every thread has taken its part of the stage out of shared memory.
+__device__ __forceinline__ float block_sum_256(float v, float* red, int& slot) {
+  v = warp_sum(v);
+  float* r = red + (slot & 1) * 8;
+  ++slot;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+}
+
+template <int NST>
+__global__ void __launch_bounds__(256, 3) rmsnorm_mod_stream_kernel(const float* x, bf16* out, int M,
+                                                                     const float* __restrict__ tbl_shift,
+                                                                     const float* __restrict__ tbl_scale,
+                                                                     const float* ada_shift, const float* ada_scale,
+                                                                     int64_t ada_ld, int rows_per_mod, float eps, int layernorm) {
+  constexpr int D = 4096, ROW_BYTES = D * 4;
+  extern __shared__ __align__(128) uint8_t smem_rows[];
+  const float4* stage = reinterpret_cast<const float4*>(smem_rows);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_rows + NST * ROW_BYTES);
+  float* red = reinterpret_cast<float*>(full + NST);   // 2 x 8 floats
+  const int t = threadIdx.x;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = (M - first + stride - 1) / stride;   // first < M: the launcher never starts more CTAs than rows
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  griddep_launch();
+  griddep_wait();   // x and the ada vectors come from preceding kernels
+  if (t == 0) {
+    for (int i = 0; i < NST && i < n_my; ++i) {
+      mbar_arrive_expect_tx(&full[i], ROW_BYTES);
+      bulk_load_1d(smem_rows + i * ROW_BYTES, x + static_cast<int64_t>(first + i * stride) * D, ROW_BYTES, &full[i]);
+    }
+  }
+  int cur_mod = -1, slot = 0;
+  float4 sc[4], sh[4];
+  for (int i = 0; i < n_my; ++i) {
+    const int s = i % NST;
+    const int row = first + i * stride;
+    const int mod = row / rows_per_mod;
+    if (mod != cur_mod) {   // while the row is in flight
+      cur_mod = mod;
+      const int64_t aoff = static_cast<int64_t>(mod) * ada_ld;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = t + k * 256;
+        const float4 a = reinterpret_cast<const float4*>(tbl_scale)[c], b = reinterpret_cast<const float4*>(ada_scale + aoff)[c];
+        const float4 e = reinterpret_cast<const float4*>(tbl_shift)[c], f = reinterpret_cast<const float4*>(ada_shift + aoff)[c];
+        sc[k] = make_float4(1.f + a.x + b.x, 1.f + a.y + b.y, 1.f + a.z + b.z, 1.f + a.w + b.w);
+        sh[k] = make_float4(e.x + f.x, e.y + f.y, e.z + f.z, e.w + f.w);
+      }
+    }
+    mbar_wait(&full[s], (i / NST) & 1);
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = stage[s * (D / 4) + t + k * 256];
+    float mean = 0.f, part = 0.f;
+    if (layernorm) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) part += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) part += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+    float tot = block_sum_256(part, red, slot);
+    // every thread holds its part of the stage in registers: refill it with the row NST steps ahead
+    if (t == 0 && i + NST < n_my) {
+      mbar_arrive_expect_tx(&full[s], ROW_BYTES);
+      bulk_load_1d(smem_rows + s * ROW_BYTES, x + static_cast<int64_t>(row + NST * stride) * D, ROW_BYTES, &full[s]);
+    }
+    if (layernorm) {
+      mean = tot / D;
+      part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        part += (a * a + b * b) + (c * c + d * d);
+      }
+      tot = block_sum_256(part, red, slot);
+    }
+    const float rstd = rsqrtf(tot / D + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(row) * D);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float y0 = (v[k].x - mean) * rstd * sc[k].x + sh[k].x;
+      const float y1 = (v[k].y - mean) * rstd * sc[k].y + sh[k].y;
+      const float y2 = (v[k].z - mean) * rstd * sc[k].z + sh[k].z;
+      const float y3 = (v[k].w - mean) * rstd * sc[k].w + sh[k].w;
+      orow[t + k * 256] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // q/k RMSNorm across all heads (learned weight) + split RoPE, in place on bf16 rows.
 // T/LTXAttention.swift:179-189, T/LTXRoPE.swift:84-149.  cos/sin: [rows_per_rope, D/2] fp32, index h*64 + j.
@@ -363,6 +468,150 @@ __global__ void __launch_bounds__(256) qknorm_rope_fast_kernel(bf16* __restrict_
         make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
     *reinterpret_cast<uint4*>(o2) =
         make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
+  }
+}
+
+// Streaming form of the q/k norm (default for D = 4096): as rmsnorm_mod_stream_kernel.  A stage holds one row: the nseg
+// (1 | 2) bf16 segments -- contiguous in the fused q|k projection output -- and, with RoPE, its cos and sin rows, so the
+// rotation tables are fetched once per row for both segments.  Two CTAs per SM, STAGES_BYTES of bulk copies in flight each.
+constexpr int QK_STREAM_BYTES = 96 * 1024;
+
+template <bool ROPE>
+__global__ void __launch_bounds__(256, 2) qknorm_rope_stream_kernel(bf16* x, int64_t ld, int M, int nseg,
+                                                                     const float* __restrict__ w0, const float* __restrict__ w1,
+                                                                     const float* __restrict__ cosb, const float* __restrict__ sinb,
+                                                                     int rows_per_rope, float eps, bf16* bout0, bf16* bout1, int hpb,
+                                                                     int64_t bstride, int64_t bld, int use_peer,
+                                                                     const PeerTable peer0, const PeerTable peer1) {
+  constexpr int D = 4096, SEG_BYTES = D * 2, TAB_BYTES = (D / 2) * 4;
+  extern __shared__ __align__(128) uint8_t smem_rows[];
+  const int x_bytes = nseg * SEG_BYTES;
+  const int stage_bytes = x_bytes + (ROPE ? 2 * TAB_BYTES : 0);
+  const int nst = min(8, QK_STREAM_BYTES / stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_rows + QK_STREAM_BYTES);
+  float* red = reinterpret_cast<float*>(full + 8);   // 2 slots x 2 segments x 8 warps
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_my = (M - first + stride - 1) / stride;
+  const int hh = t >> 3, jc = (t & 7) * 8;
+  const int c1 = hh * 128 + jc, c2 = c1 + 64;
+  float wa[2][8], wb[2][8];
+#pragma unroll
+  for (int sg = 0; sg < 2; ++sg) {
+    const float* w = sg == 0 ? w0 : w1;
+    if (sg < nseg) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(w + c1 + e), b = *reinterpret_cast<const float4*>(w + c2 + e);
+        wa[sg][e] = a.x; wa[sg][e + 1] = a.y; wa[sg][e + 2] = a.z; wa[sg][e + 3] = a.w;
+        wb[sg][e] = b.x; wb[sg][e + 1] = b.y; wb[sg][e + 2] = b.z; wb[sg][e + 3] = b.w;
+      }
+    }
+  }
+  if (t == 0) {
+    for (int s = 0; s < nst; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  griddep_launch();
+  griddep_wait();   // x comes from the preceding GEMM
+  auto fill = [&](int s, int row) {
+    uint8_t* dst = smem_rows + s * stage_bytes;
+    mbar_arrive_expect_tx(&full[s], stage_bytes);
+    bulk_load_1d(dst, x + static_cast<int64_t>(row) * ld, x_bytes, &full[s]);
+    if (ROPE) {
+      const int64_t fo = static_cast<int64_t>(row % rows_per_rope) * (D / 2);
+      bulk_load_1d(dst + x_bytes, cosb + fo, TAB_BYTES, &full[s]);
+      bulk_load_1d(dst + x_bytes + TAB_BYTES, sinb + fo, TAB_BYTES, &full[s]);
+    }
+  };
+  if (t == 0)
+    for (int i = 0; i < nst && i < n_my; ++i) fill(i, first + i * stride);
+  int slot = 0;
+  for (int i = 0; i < n_my; ++i) {
+    const int s = i % nst;
+    const int row = first + i * stride;
+    const uint8_t* src = smem_rows + s * stage_bytes;
+    mbar_wait(&full[s], (i / nst) & 1);
+    uint4 u1[2], u2[2];
+    float ss[2] = {0.f, 0.f};
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      if (sg < nseg) {
+        u1[sg] = *reinterpret_cast<const uint4*>(src + sg * SEG_BYTES + c1 * 2);
+        u2[sg] = *reinterpret_cast<const uint4*>(src + sg * SEG_BYTES + c2 * 2);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1[sg]);
+        const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2[sg]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+          ss[sg] += fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+        }
+      }
+    }
+    float cs[8], sn[8];
+    if (ROPE) {
+      const float* ct = reinterpret_cast<const float*>(src + x_bytes) + hh * 64 + jc;
+      const float* stb = ct + D / 2;
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(ct + e), b = *reinterpret_cast<const float4*>(stb + e);
+        cs[e] = a.x; cs[e + 1] = a.y; cs[e + 2] = a.z; cs[e + 3] = a.w;
+        sn[e] = b.x; sn[e + 1] = b.y; sn[e + 2] = b.z; sn[e + 3] = b.w;
+      }
+    }
+    // both segments' sums of squares in one barrier; scratch alternates between two slots
+    ss[0] = warp_sum(ss[0]);
+    ss[1] = warp_sum(ss[1]);
+    float* r = red + (slot & 1) * 16;
+    ++slot;
+    if (lane == 0) { r[warp] = ss[0]; r[8 + warp] = ss[1]; }
+    __syncthreads();
+    if (t == 0 && i + nst < n_my) fill(s, row + nst * stride);   // the stage is in registers everywhere
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      if (sg >= nseg) break;
+      const float* rr = r + sg * 8;
+      const float tot = ((rr[0] + rr[1]) + (rr[2] + rr[3])) + ((rr[4] + rr[5]) + (rr[6] + rr[7]));
+      const float rstd = rsqrtf(tot / D + eps);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&u1[sg]);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u2[sg]);
+      float y1[8], y2[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __bfloat1622float2(a2[e]), fb = __bfloat1622float2(b2[e]);
+        const float xa[2] = {fa.x, fa.y}, xb[2] = {fb.x, fb.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * e + h;
+          const float a = xa[h] * rstd * wa[sg][j], b = xb[h] * rstd * wb[sg][j];
+          if (ROPE) {
+            y1[j] = a * cs[j] - b * sn[j];
+            y2[j] = b * cs[j] + a * sn[j];
+          } else {
+            y1[j] = a; y2[j] = b;
+          }
+        }
+      }
+      bf16* xr = x + static_cast<int64_t>(row) * ld + static_cast<int64_t>(sg) * D;
+      bf16* o1 = xr + c1;
+      bf16* o2 = xr + c2;
+      bf16* bout = sg == 0 ? bout0 : bout1;
+      if (use_peer) {   // Ulysses over peer memory: head block hh / hpb lives in that rank's receive buffer
+        bf16* base = reinterpret_cast<bf16*>(sg == 0 ? peer0.p[hh / hpb] : peer1.p[hh / hpb]);
+        bf16* ob = base + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+        o1 = ob;
+        o2 = ob + 64;
+      } else if (bout) {
+        bf16* ob = bout + static_cast<int64_t>(hh / hpb) * bstride + static_cast<int64_t>(row) * bld + (hh % hpb) * 128 + jc;
+        o1 = ob;
+        o2 = ob + 64;
+      }
+      *reinterpret_cast<uint4*>(o1) =
+          make_uint4(pack_bf16(y1[0], y1[1]), pack_bf16(y1[2], y1[3]), pack_bf16(y1[4], y1[5]), pack_bf16(y1[6], y1[7]));
+      *reinterpret_cast<uint4*>(o2) =
+          make_uint4(pack_bf16(y2[0], y2[1]), pack_bf16(y2[2], y2[3]), pack_bf16(y2[4], y2[5]), pack_bf16(y2[6], y2[7]));
+    }
   }
 }
 
@@ -594,12 +843,27 @@ int rows_per_cta() {
   return r;
 }
 
+// LTX_ROWS_STREAM=0: the register-staged row kernels instead of the bulk-copy streaming ones
+bool rows_stream() {
+  static const bool on = [] { const char* e = getenv("LTX_ROWS_STREAM"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 }  // namespace
 
 void launch_rmsnorm_mod(const float* x, bf16* out, int M, int D, const float* tbl_shift, const float* tbl_scale,
                         const float* ada_shift, const float* ada_scale, int64_t ada_ld, int rows_per_mod, float eps,
                         int layernorm, cudaStream_t s) {
   LTX_CHECK(D % 4 == 0 && M > 0 && ada_ld % 4 == 0, 2, "rmsnorm_mod: D must be a multiple of 4");
+  if (D == 4096 && rows_stream() && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    constexpr int NST = 4;
+    const size_t smem = NST * 4096 * 4 + NST * 8 + 64;
+    auto kern = rmsnorm_mod_stream_kernel<NST>;
+    ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+    launch_pdl(PDL_ROWS, kern, dim3(std::min(M, 3 * device_sm_count())), dim3(256), smem, s, x, out, M, tbl_shift, tbl_scale,
+               ada_shift, ada_scale, ada_ld, rows_per_mod > 0 ? rows_per_mod : 1, eps, layernorm);
+    return;
+  }
   if (D == 4096) {
     const int rpm = rows_per_mod > 0 ? rows_per_mod : 1;
     if (rows_per_cta() == 2)
@@ -627,6 +891,24 @@ void launch_qknorm_rope(bf16* x, int64_t ld, int M, int D, const float* w, const
   const int use_peer = blocked ? blocked->use_peer : 0;
   const PeerTable pt0 = blocked ? blocked->peer[0] : PeerTable{}, pt1 = blocked ? blocked->peer[1] : PeerTable{};
   LTX_CHECK(!blocked || (hpb > 0 && (D / 128) % hpb == 0 && (use_peer || (b0 && (!w_second || b1)))), 2, "qknorm_rope: bad blocked output");
+  // streaming form: the segments of a row must be one contiguous, 16-byte aligned piece
+  if (D == 4096 && rows_stream() && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!cosb || ((reinterpret_cast<uintptr_t>(cosb) | reinterpret_cast<uintptr_t>(sinb)) & 15) == 0)) {
+    const size_t smem = QK_STREAM_BYTES + 8 * 8 + 128;
+    const int nseg = w_second ? 2 : 1;
+    const dim3 grid(std::min(M, 2 * device_sm_count()));
+    if (cosb) {
+      auto kern = qknorm_rope_stream_kernel<true>;
+      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      launch_pdl(PDL_ROWS, kern, grid, dim3(256), smem, s, x, ld, M, nseg, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs, bld,
+                 use_peer, pt0, pt1);
+    } else {
+      auto kern = qknorm_rope_stream_kernel<false>;
+      ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+      launch_pdl(PDL_ROWS, kern, grid, dim3(256), smem, s, x, ld, M, nseg, w, w_second, cosb, sinb, rpr, eps, b0, b1, hpb, bs, bld,
+                 use_peer, pt0, pt1);
+    }
+    return;
+  }
   if (D == 4096) {
     if (rows_per_cta() == 2)
       launch_pdl(PDL_ROWS, qknorm_rope_fast_kernel<2>, dim3((M + 1) / 2, w_second ? 2 : 1), dim3(256), 0, s, x, ld, M, w, w_second, cosb, sinb,

@@ -120,6 +120,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (the TMA engine without a tensor map): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM alloc
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

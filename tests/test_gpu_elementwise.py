@@ -15,7 +15,9 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("M,D,layernorm", [(5, 256, 0), (48, 4096, 0), (48, 4096, 1), (1536, 4096, 0), (7, 512, 1)])
+@pytest.mark.parametrize("M,D,layernorm", [(5, 256, 0), (48, 4096, 0), (48, 4096, 1), (1536, 4096, 0), (7, 512, 1),
+                                                # streaming form: fewer rows than CTAs, ring refills (rows > 3 x 148 x 4), ragged last round
+                                                (1, 4096, 0), (445, 4096, 1), (3077, 4096, 0), (3077, 4096, 1)])
 def test_rmsnorm_mod(ctx, M, D, layernorm):
     g = torch.Generator(device="cuda").manual_seed(M + D)
     x = torch.randn(M, D, device="cuda", generator=g) * 3 + 0.5
@@ -34,7 +36,9 @@ def test_rmsnorm_mod(ctx, M, D, layernorm):
     assert rel_l2(out.float(), ref) <= 4e-3
 
 
-@pytest.mark.parametrize("heads,fhw,rope", [(2, (2, 4, 6), True), (32, (4, 16, 24), True), (4, (1, 3, 5), False)])
+@pytest.mark.parametrize("heads,fhw,rope", [(2, (2, 4, 6), True), (32, (4, 16, 24), True), (4, (1, 3, 5), False),
+                                               # streaming form at D = 4096: ring refills with and without the rotation tables
+                                               (32, (1, 1, 3), True), (32, (2, 40, 41), True), (32, (1, 50, 53), False)])
 def test_qknorm_rope(ctx, heads, fhw, rope):
     cfg = O.DiTConfig(num_heads=heads)
     D = cfg.inner_dim

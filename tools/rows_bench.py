@@ -1,36 +1,45 @@
-"""Micro-benchmark of the HBM-bound row kernels at the DiT shapes (device time via CUDA events on the library stream)."""
+"""Micro-benchmark of the HBM-bound row kernels of a DiT block (AdaLN RMSNorm, q/k RMSNorm + RoPE) at D = 4096.
+R launches queued behind a 1 GB memset on the library's stream, cycling over NBUF distinct buffers (> L2 in total) so every
+launch reads its rows from HBM; CUDA events around the R.  GB/s counts x read + written and the RoPE tables once per launch."""
 import os
-import sys, torch
+import sys
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ltx_video_swift_mlx_b200  # noqa
 from ltx_video_swift_mlx_b200.context import LtxContext, LTXTransformerConfig
 ctx = LtxContext(LTXTransformerConfig(num_layers=1, num_attention_heads=1), 0)
 stream = torch.cuda.ExternalStream(ctx.stream)
-M, D = 1536, 4096
-x = torch.randn(M, D, device="cuda"); out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+big = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+D, NBUF, R = 4096, 8, 16
 tb = torch.randn(4, D, device="cuda") * 0.1
-qk = torch.randn(M, D, device="cuda").bfloat16(); w = torch.randn(D, device="cuda")
-cs = torch.randn(M, D // 2, device="cuda"); sn = torch.randn(M, D // 2, device="cuda")
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-torch.cuda.synchronize()
-def t_norm():
-    ctx._check(ctx.lib.ltx_op_rmsnorm_mod(ctx.handle, x.data_ptr(), out.data_ptr(), M, D, tb[0].data_ptr(), tb[1].data_ptr(), tb[2].data_ptr(), tb[3].data_ptr(), 1e-6, 0))
-def t_qk():
-    ctx._check(ctx.lib.ltx_op_qknorm_rope(ctx.handle, qk.data_ptr(), M, D, w.data_ptr(), cs.data_ptr(), sn.data_ptr(), M, 1e-6))
-for name, fn, nbytes in [("rmsnorm_mod", t_norm, M * D * 6), ("qknorm_rope(1 seg)", t_qk, M * D * 4 + M * D * 4)]:
-    for cold in (True, False):
-        for _ in range(3): fn()
-        ctx.sync(); ts = []
-        for _ in range(20):
-            if cold: flush.zero_()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); fn(); e1.record(stream); ctx.sync(); ts.append(e0.elapsed_time(e1))
-        t = sorted(ts)[len(ts) // 2]
-        # 10 back-to-back launches: amortises the event/launch overhead
+wn = torch.randn(D, device="cuda")
+
+
+def timed(run):
+    run(0); ctx.sync(); ts = []
+    for _ in range(5):
         torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            big.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(10): fn()
-        e1.record(stream); ctx.sync(); t10 = e0.elapsed_time(e1) / 10
-        print(f"{name:20s} {'cold(L2 flushed)' if cold else 'warm':17s}: single {t*1e3:7.1f} us ({nbytes/t/1e6:7.0f} GB/s)  x10 avg {t10*1e3:7.1f} us ({nbytes/t10/1e6:7.0f} GB/s)", flush=True)
+        for i in range(R):
+            run(i % NBUF)
+        e1.record(stream); ctx.sync(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / R)
+    return sorted(ts)[len(ts) // 2]
+
+
+for M in (1536, 3072):
+    xs = [torch.randn(M, D, device="cuda") for _ in range(NBUF)]
+    hs = [torch.empty(M, D, device="cuda", dtype=torch.bfloat16) for _ in range(NBUF)]
+    t = timed(lambda i: ctx._check(ctx.lib.ltx_op_rmsnorm_mod(ctx.handle, xs[i].data_ptr(), hs[i].data_ptr(), M, D, tb[0].data_ptr(),
+                                                              tb[1].data_ptr(), tb[2].data_ptr(), tb[3].data_ptr(), 1e-6, 0)))
+    print(f"rmsnorm_mod   M={M}: {t*1e3:7.1f} us  {6.0*M*D/t/1e6:7.0f} GB/s", flush=True)
+    qs = [torch.randn(M, D, device="cuda").bfloat16() for _ in range(NBUF)]
+    t = timed(lambda i: ctx._check(ctx.lib.ltx_op_qknorm_rope(ctx.handle, qs[i].data_ptr(), M, D, wn.data_ptr(), None, None, 1, 1e-6)))
+    print(f"qknorm        M={M}: {t*1e3:7.1f} us  {4.0*M*D/t/1e6:7.0f} GB/s", flush=True)
+    cs = [torch.randn(1536, D // 2, device="cuda") for _ in range(NBUF)]
+    sn = [torch.randn(1536, D // 2, device="cuda") for _ in range(NBUF)]
+    t = timed(lambda i: ctx._check(ctx.lib.ltx_op_qknorm_rope(ctx.handle, qs[i].data_ptr(), M, D, wn.data_ptr(), cs[i].data_ptr(),
+                                                              sn[i].data_ptr(), 1536, 1e-6)))
+    print(f"qknorm_rope   M={M}: {t*1e3:7.1f} us  {(4.0*M*D + 4.0*1536*D)/t/1e6:7.0f} GB/s", flush=True)
