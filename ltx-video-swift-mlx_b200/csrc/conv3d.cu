@@ -23,14 +23,19 @@ namespace {
 
 constexpr int CBM = 128, CBK = 64, CONV_THREADS = 192;
 
-// KS = 64-channel k chunks per pipeline stage.  KS = 2 (tiles up to 128 columns, Cin a multiple of 128): a stage holds both
-// halves of a 128-channel slice of one tap, so the issuing thread waits on / commits to half as many barriers per k -- the
-// same change that bought 4-7 % on the DiT GEMMs (profiles/r02_gemm_kstage_sweep.txt).
-template <int BN, int KS = 1>
+// KS = 64-channel k chunks per pipeline stage.  KS = 2 (Cin a multiple of 128): a stage holds both halves of a 128-channel
+// slice of one tap, so the issuing thread waits on / commits to half as many barriers per k -- the same change that bought
+// 4-7 % on the DiT GEMMs (profiles/r02_gemm_kstage_sweep.txt).
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) compute two adjacent voxel tiles against the same weight tile with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA loads its own A tile and HALF of the weight tile.  Why: one CTA per tile is bound
+// by shared-memory traffic -- per 128-channel stage of the 128 -> 128 convs 64 KB of TMA writes + 64 KB of operand reads against
+// 512 clk x 128 B/clk of port bandwidth; in a pair the B half drops out of both: 96 KB.
+template <int BN, int KS = 1, bool PAIR = false>
 struct ConvCfg {
-  static constexpr int STAGES = ((BN == 256) ? 4 : (BN == 128 ? 6 : 8)) / KS;
+  static constexpr int BROWS = PAIR ? BN / 2 : BN;   // weight rows this CTA stages
+  static constexpr int STAGES = (PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8))) / KS;
   static constexpr uint32_t A_BYTES = CBM * CBK * 2;
-  static constexpr uint32_t B_BYTES = BN * CBK * 2;
+  static constexpr uint32_t B_BYTES = BROWS * CBK * 2;
   static constexpr uint32_t A_STAGE = KS * A_BYTES, B_STAGE = KS * B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr size_t SMEM = 1024 + STAGES * (A_STAGE + B_STAGE) + (2 * STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
@@ -106,11 +111,9 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
   }
 }
 
-template <int BN, int MODE, int KS>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
-               const ConvEpi ep) {
-  using Cfg = ConvCfg<BN, KS>;
+template <int BN, int MODE, int KS, bool PAIR>
+__device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep) {
+  using Cfg = ConvCfg<BN, KS, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -124,7 +127,14 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   float* epi_stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~static_cast<uintptr_t>(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m = g.nt * g.nh * g.nw;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int worker = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_workers = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_vox_tiles = g.nt * g.nh * g.nw;
+  // PAIR: a work item covers voxel tiles 2 * mp and 2 * mp + 1 (the second may lie past the volume when the count is odd: its
+  // TMA boxes are zero-filled, its rows masked by the epilogue)
+  const int num_m = PAIR ? (num_vox_tiles + 1) / 2 : num_vox_tiles;
   const int num_n = (g.Cout + BN - 1) / BN;
   const int num_mn = num_m * num_n;
   const int num_tiles = num_mn * g.ksplit;
@@ -135,13 +145,20 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    // PAIR (protocol of gemm2.cu): full = the leader's expect_tx arrive + the peer's remote arrive, the 2-SM TMA loads of both
+    // CTAs report their bytes to the leader's copy; empty / tfull are released in BOTH CTAs by the multicast tcgen05.commit;
+    // tempty (leader's copy) collects the 4 epilogue warps of each CTA
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], PAIR ? 2 : 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], PAIR ? 8 : 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();
@@ -151,9 +168,9 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int ks = tile / num_mn, mn = tile % num_mn;
-        const int m_blk = mn % num_m, n_blk = mn / num_m;
+        const int m_blk = PAIR ? 2 * (mn % num_m) + static_cast<int>(rank) : mn % num_m, n_blk = mn / num_m;
         const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
         const int t0 = it * g.bt, h0 = ih * g.bh, w0 = iw * g.bw;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -161,23 +178,31 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const int tap = g.tap0 + wtap;
           const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE + Cfg::B_STAGE);
+          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE + Cfg::B_STAGE);
+          else if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_STAGE + Cfg::B_STAGE));
+          else mbar_arrive_remote(&full[stage], 0);
+          const int wrow = wtap * g.Cout + n_blk * BN + static_cast<int>(rank) * Cfg::BROWS;   // PAIR: this CTA's half of the weight tile
 #pragma unroll
           for (int s2 = 0; s2 < KS; ++s2) {
-            tma_load_4d(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
-            tma_load_2d(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wtap * g.Cout + n_blk * BN);
+            if (PAIR) {
+              tma_load_4d_2sm(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
+              tma_load_2d_2sm(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wrow);
+            } else {
+              tma_load_4d(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
+              tma_load_2d(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wrow);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(CBM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * CBM : CBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
         const int as = t & 1;
         const uint32_t aphase = (t >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -191,21 +216,25 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int s2 = 0; s2 < KS; ++s2)
 #pragma unroll
-            for (int k = 0; k < CBK / 16; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128(a_addr + s2 * Cfg::A_BYTES + k * 32), umma_desc_sw128(b_addr + s2 * Cfg::B_BYTES + k * 32),
-                        idesc, (kb | s2 | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+            for (int k = 0; k < CBK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(a_addr + s2 * Cfg::A_BYTES + k * 32), bd = umma_desc_sw128(b_addr + s2 * Cfg::B_BYTES + k * 32);
+              if (PAIR) umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
+            }
+          if (PAIR) umma_commit_2cta(&empty[stage]);
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (PAIR) umma_commit_2cta(&tfull[as]);
+        else umma_commit(&tfull[as]);
       }
     }
   } else {
     const int q = warp & 3;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++t) {
       const int ks = tile / num_mn, mn = tile % num_mn;
-      const int m_blk = mn % num_m, n_blk = mn / num_m;
+      const int m_blk = PAIR ? 2 * (mn % num_m) + static_cast<int>(rank) : mn % num_m, n_blk = mn / num_m;
       const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
       const int as = t & 1;
       const uint32_t aphase = (t >> 1) & 1;
@@ -352,16 +381,35 @@ conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(&tempty[as], 0);
+        else mbar_arrive(&tempty[as]);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+}
+
+template <int BN, int MODE, int KS>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
+               const ConvEpi ep) {
+  conv3d_body<BN, MODE, KS, false>(tmX, tmW, g, ep);
+}
+
+template <int BN, int MODE, int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3d_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
+                    const ConvEpi ep) {
+  conv3d_body<BN, MODE, KS, true>(tmX, tmW, g, ep);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,12 +446,18 @@ __global__ void __launch_bounds__(256) vae_prep_kernel(const float* x, bf16* out
   for (int64_t pv0 = wid0 * U; pv0 < nvox; pv0 += nwarps * U) {
     float4 v[U][VPL];
     bool zero[U];   // padding voxel of a zero-padded axis: written as 0 (after the activation, like the conv's own padding)
+    // coordinates of the first voxel by 32-bit division (the launcher checks nvox < 2^31; 64-bit divisions -- three per voxel,
+    // ~100 instructions each, redundantly on every lane -- made the 128-channel prologue issue-bound at 1.85 TB/s), the
+    // following U - 1 by stepping
+    const uint32_t p0 = static_cast<uint32_t>(pv0), Wp = static_cast<uint32_t>(W + 2), Hp = static_cast<uint32_t>(H + 2);
+    int pw = static_cast<int>(p0 % Wp), ph = static_cast<int>((p0 / Wp) % Hp), pt = static_cast<int>(p0 / (Wp * Hp));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t pv = pv0 + u;
-      const int pw = static_cast<int>(pv % (W + 2));
-      const int ph = static_cast<int>((pv / (W + 2)) % (H + 2));
-      const int pt = static_cast<int>(pv / (static_cast<int64_t>(W + 2) * (H + 2)));
+      if (u > 0 && ++pw == W + 2) {
+        pw = 0;
+        if (++ph == H + 2) { ph = 0; ++pt; }
+      }
       int ws = pw - 1, hs = ph - 1, ts = pt - (zero_t ? 1 : tshift);
       zero[u] = (zero_hw && (ws < 0 || ws >= W || hs < 0 || hs >= H)) || (zero_t && (ts < 0 || ts >= T));
       ws = ws < 0 ? -ws : (ws >= W ? 2 * W - 2 - ws : ws);   // reflect (VideoConvolution.swift:257-266)
@@ -551,24 +605,45 @@ void conv_launch_ks(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGe
   LTX_CUDA(cudaGetLastError());
 }
 
+// CTA pairs: one work item = two adjacent voxel tiles x one channel tile (x one tap group); a cluster per SM pair
 template <int BN, int MODE>
-void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+void conv_launch_pair(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+  using Cfg = ConvCfg<BN, 2, true>;
+  auto kern = conv3d_pair_tcgen05<BN, MODE, 2>;
+  ensure_dyn_smem(kern, Cfg::SMEM);
+  const int items = ((g.nt * g.nh * g.nw + 1) / 2) * ((g.Cout + BN - 1) / BN) * g.ksplit;
+  const int clusters = device_sm_count() / 2;
+  const int grid = 2 * (items < clusters ? items : clusters);
+  launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
+  LTX_CUDA(cudaGetLastError());
+}
+
+template <int BN, int MODE>
+void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s, bool pair) {
   // 128-channel stages where they fit: tiles up to 128 columns (3 / 4 stages of 64 / 48 KB stay in flight) and whole pairs of chunks
   static const int ks_env = [] { const char* e = getenv("LTX_CONV_KS"); return e ? atoi(e) : 2; }();
-  if (BN <= 128 && ks_env == 2 && g.Cin % (2 * CBK) == 0) conv_launch_ks<BN, MODE, (BN <= 128 ? 2 : 1)>(tmX, tmW, g, ep, s);
+  if (pair) conv_launch_pair<BN, MODE>(tmX, tmW, g, ep, s);
+  else if (BN <= 128 && ks_env == 2 && g.Cin % (2 * CBK) == 0) conv_launch_ks<BN, MODE, (BN <= 128 ? 2 : 1)>(tmX, tmW, g, ep, s);
   else conv_launch_ks<BN, MODE, 1>(tmX, tmW, g, ep, s);
 }
 
 template <int BN>
-void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s, bool pair) {
   switch (ep.mode) {
-    case 0: conv_launch<BN, 0>(tmX, tmW, g, ep, s); break;
-    case 1: conv_launch<BN, 1>(tmX, tmW, g, ep, s); break;
-    case 2: conv_launch<BN, 2>(tmX, tmW, g, ep, s); break;
-    case 3: conv_launch<BN, 3>(tmX, tmW, g, ep, s); break;
-    case 4: conv_launch<BN, 4>(tmX, tmW, g, ep, s); break;
+    case 0: conv_launch<BN, 0>(tmX, tmW, g, ep, s, pair); break;
+    case 1: conv_launch<BN, 1>(tmX, tmW, g, ep, s, pair); break;
+    case 2: conv_launch<BN, 2>(tmX, tmW, g, ep, s, pair); break;
+    case 3: conv_launch<BN, 3>(tmX, tmW, g, ep, s, pair); break;
+    case 4: conv_launch<BN, 4>(tmX, tmW, g, ep, s, pair); break;
     default: LTX_CHECK(false, 2, "bad conv epilogue mode");
   }
+}
+
+// LTX_CONV_PAIR (read per call: the parity tests run both forms): 0 = one CTA per voxel tile, default = CTA pairs whenever the
+// input channels come in 128-channel stages
+bool conv_pair_enabled() {
+  const char* e = getenv("LTX_CONV_PAIR");
+  return e ? atoi(e) != 0 : true;
 }
 
 }  // namespace
@@ -616,14 +691,15 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   float* final_out = epi.out;
   if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
   LTX_CHECK((epi.mode != 3 && epi.mode != 4) || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
+  const bool pair = conv_pair_enabled() && Cin % (2 * CBK) == 0 && device_sm_count() >= 2;
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
-  CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, bn);
+  CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, pair ? bn / 2 : bn);   // pair: each CTA stages half a weight tile
   if (bn == 256)
-    conv_launch_mode<256>(tmX, tmW, g, epi, s);
+    conv_launch_mode<256>(tmX, tmW, g, epi, s, pair);
   else if (bn == 128)
-    conv_launch_mode<128>(tmX, tmW, g, epi, s);
+    conv_launch_mode<128>(tmX, tmW, g, epi, s, pair);
   else
-    conv_launch_mode<64>(tmX, tmW, g, epi, s);
+    conv_launch_mode<64>(tmX, tmW, g, epi, s, pair);
   if (g.ksplit > 1) {
     const int64_t slab4 = static_cast<int64_t>(slab / 16);
     int64_t blocks = (slab4 + 255) / 256;
@@ -650,6 +726,7 @@ void launch_vae_prep(const float* x, bf16* out, int T, int H, int W, int C, int 
                      int pad, cudaStream_t s) {
   LTX_CHECK(C % 4 == 0 && C <= 2048 && H > 1 && W > 1, 2, "vae_prep: bad shape (C must be a multiple of 4, at most 2048)");
   const int64_t nvox = static_cast<int64_t>(T + 2) * (H + 2) * (W + 2);
+  LTX_CHECK(nvox < (1ll << 31), 2, "vae_prep: volume too large");
   int64_t blocks = (nvox + 7) / 8;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;

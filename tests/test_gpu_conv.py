@@ -16,11 +16,21 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["0", "1"])
+def conv_form(request, monkeypatch):
+    """LTX_CONV_PAIR (read by the launcher on every call): 0 = one CTA per voxel tile, 1 = CTA pairs (cta_group::2: two voxel
+    tiles against one weight tile, each CTA staging half of it) wherever Cin comes in 128-channel stages."""
+    monkeypatch.setenv("LTX_CONV_PAIR", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("T,H,W,Cin,Cout,causal", [
     (2, 4, 6, 64, 64, 0), (3, 8, 8, 128, 128, 0), (4, 16, 24, 128, 1024, 0), (2, 5, 7, 64, 128, 1),
     (7, 32, 48, 256, 256, 0), (1, 16, 24, 1024, 256, 0), (3, 6, 10, 128, 48, 0),
+    # odd numbers of voxel tiles (the pair's second tile lies past the volume), one tile only, 512 channels
+    (5, 8, 8, 128, 128, 1), (1, 8, 16, 256, 128, 0), (3, 16, 24, 512, 512, 0),
 ])
-def test_conv3d(ctx, T, H, W, Cin, Cout, causal):
+def test_conv3d(ctx, conv_form, T, H, W, Cin, Cout, causal):
     g = torch.Generator().manual_seed(T * H * W + Cin + Cout)
     x = torch.randn(1, Cin, T, H, W, generator=g)
     w = O.bf16_round(torch.randn(Cout, Cin, 3, 3, 3, generator=g) / math.sqrt(27 * Cin))
