@@ -1,22 +1,18 @@
 #!/bin/bash
 # ncu evidence for every hot kernel class: plain run first, then one `--set full` capture per kernel, then the launch list.
 mkdir -p gpurun_out
-R=${1:-r02}
+R=${1:-r02c}
 timeout 300 python tools/ncu_target.py > gpurun_out/plain_ncu_target.log 2>&1 || { echo "plain target failed"; tail -5 gpurun_out/plain_ncu_target.log; exit 1; }
 cap() {  # name regex skip
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/${R}_$1 python tools/ncu_target.py > gpurun_out/ncu_$1.log 2>&1
   echo "ncu $1 exit $?"
 }
 cap gemm_pair_ffn_in gemm_bf16_2cta 2
-cap gemm_pair_resid "gemm_bf16_2ctaILi2E" 1
-cap gemm_q_int8 gemm_q_tcgen05 1
 cap gemm_swapab_splitk gemm_swapab_2cta 1
-cap gemm_swapab_ffn_out "gemm_swapab_2ctaILi2E" 0
 cap attention attention_fwd 1
-cap conv3d conv3d_tcgen05 1
-cap rmsnorm_mod rmsnorm_mod_fast 1
-cap qknorm_rope qknorm_rope_fast 1
-cap guided_euler guided_euler_kernel 1
+cap conv3d_pair conv3d_pair_tcgen05 1
+cap rmsnorm_mod rmsnorm_mod_stream 1
+cap qknorm_rope qknorm_rope_stream 1
 cap vae_prep vae_prep_kernel 1
 ls -la gpurun_out/*.ncu-rep
 export LTX_GRAPH=0   # the launch list is of the eager step (a replayed graph issues the same kernels)
