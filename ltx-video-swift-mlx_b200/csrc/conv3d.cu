@@ -30,12 +30,21 @@ constexpr int CBM = 128, CBK = 64, CONV_THREADS = 192;
 // tcgen05.mma.cta_group::2 (M = 256): each CTA loads its own A tile and HALF of the weight tile.  Why: one CTA per tile is bound
 // by shared-memory traffic -- per 128-channel stage of the 128 -> 128 convs 64 KB of TMA writes + 64 KB of operand reads against
 // 512 clk x 128 B/clk of port bandwidth; in a pair the B half drops out of both: 96 KB.
-template <int BN, int KS = 1, bool PAIR = false>
+// SLAB (pairs, tiles up to 128 columns): a stage holds, for one (dt, dw) and 64 channels, the voxel tile's rows WITH their
+// two halo rows in h -- a [bh + 2, bw] slab, bt = 1 -- and the weight tiles of the three taps dh = 0, 1, 2.  Tap dh reads the
+// 128 rows starting bw * dh rows into the slab (a whole number of 8-row swizzle atoms: only the descriptor's start address
+// moves), so the activations come in once for three taps: (bh + 2) / (3 bh) of the A traffic (0.375-0.5).  Why: an SM takes
+// operands in at ~64 B/clk; at 128 output channels the per-tap form needs 94 B per tensor-clock (A 32 KB + half a weight
+// tile 16 KB per 512 clk), the GEMM at 256 columns 62.5 -- the 128 -> 128 convs (41 % of a decode) ran at ~900 TFLOP/s.
+constexpr int SLAB_ROWS_MAX = 192;
+
+template <int BN, int KS = 1, bool PAIR = false, bool SLAB = false>
 struct ConvCfg {
   static constexpr int BROWS = PAIR ? BN / 2 : BN;   // weight rows this CTA stages
-  static constexpr int STAGES = (PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8))) / KS;
-  static constexpr uint32_t A_BYTES = CBM * CBK * 2;
-  static constexpr uint32_t B_BYTES = BROWS * CBK * 2;
+  static constexpr int STAGES = SLAB ? (BN == 128 ? 4 : 5) : (PAIR ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8))) / KS;
+  static constexpr uint32_t A_BYTES = (SLAB ? SLAB_ROWS_MAX : CBM) * CBK * 2;
+  static constexpr uint32_t B_TAP_BYTES = BROWS * CBK * 2;
+  static constexpr uint32_t B_BYTES = (SLAB ? 3 : 1) * B_TAP_BYTES;
   static constexpr uint32_t A_STAGE = KS * A_BYTES, B_STAGE = KS * B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
   static constexpr size_t SMEM = 1024 + STAGES * (A_STAGE + B_STAGE) + (2 * STAGES + 4) * 8 + 16 + 128 + 4 * EPI_STAGE_BYTES;
@@ -46,6 +55,7 @@ struct ConvGeom {
   int bt, bh, bw;     // voxel box of one M tile (bt*bh*bw == 128)
   int nt, nh, nw;     // tiles per axis
   int tap0, ntaps;    // taps [tap0, tap0 + ntaps) of the 3x3x3 stencil (27: Conv3d; 9 starting at 9: per-frame Conv2d, dt = 1)
+  int slab;           // 1: slab stages (conv3d_slab_tcgen05): bt == 1, the A box is [bh + 2, bw] voxels
   int ksplit;         // > 1: the taps are split into ksplit groups, each an own work item writing raw partial sums to
                       // out + ks * T*H*W*Cout (MODE 0, no bias / residual); conv_splitk_reduce_kernel adds them up in a fixed order
 };
@@ -111,9 +121,10 @@ __device__ __forceinline__ void conv_epilogue_chunk(const uint32_t (&r)[32], int
   }
 }
 
-template <int BN, int MODE, int KS, bool PAIR>
+template <int BN, int MODE, int KS, bool PAIR, bool SLAB = false>
 __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep) {
-  using Cfg = ConvCfg<BN, KS, PAIR>;
+  static_assert(!SLAB || (PAIR && KS == 1 && BN <= 128), "slab stages: CTA pairs, 64-channel stages, tiles up to 128 columns");
+  using Cfg = ConvCfg<BN, KS, PAIR, SLAB>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -140,7 +151,9 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
   const int num_tiles = num_mn * g.ksplit;
   const int kchunks = g.Cin / (CBK * KS);   // pipeline steps per tap (KS * 64 channels each)
   const int taps_per_split = g.ntaps / g.ksplit;
-  const int num_k = taps_per_split * kchunks;
+  // SLAB: a pipeline step covers the three dh taps of one (dt, dw)
+  const int num_k = (SLAB ? taps_per_split / 3 : taps_per_split) * kchunks;
+  const uint32_t slab_bytes = static_cast<uint32_t>((g.bh + 2) * g.bw) * CBK * 2;   // SLAB: A bytes of one stage
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -174,6 +187,20 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
         const int iw = m_blk % g.nw, ih = (m_blk / g.nw) % g.nh, it = m_blk / (g.nw * g.nh);
         const int t0 = it * g.bt, h0 = ih * g.bh, w0 = iw * g.bw;
         for (int kb = 0; kb < num_k; ++kb) {
+          if constexpr (SLAB) {
+            // group gi = (dt_local, dw); its taps are wt0 + 3 * dh in the weight matrix
+            const int gi = ks * (taps_per_split / 3) + kb / kchunks, kc = kb % kchunks;
+            const int dtl = gi / 3, dw = gi % 3;
+            const int dt = g.tap0 / 9 + dtl, wt0 = dtl * 9 + dw;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (slab_bytes + Cfg::B_BYTES));
+            else mbar_arrive_remote(&full[stage], 0);
+            tma_load_4d_2sm(sA + stage * Cfg::A_STAGE, &tmX, &full[stage], kc * CBK, w0 + dw, h0, t0 + dt);
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh)
+              tma_load_2d_2sm(sB + stage * Cfg::B_STAGE + dh * Cfg::B_TAP_BYTES, &tmW, &full[stage], kc * CBK,
+                              (wt0 + 3 * dh) * g.Cout + n_blk * BN + static_cast<int>(rank) * Cfg::BROWS);
+          } else {
           const int wtap = ks * taps_per_split + kb / kchunks, kc = kb % kchunks;
           const int tap = g.tap0 + wtap;
           const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
@@ -192,6 +219,7 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
               tma_load_2d(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wrow);
             }
           }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -199,6 +227,11 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * CBM : CBM, BN);
+      // operand descriptors: built ONCE; per stage one add, per MMA a compile-time offset (the start-address field counts
+      // 16-byte units and cannot carry out of its 14 bits below 256 KB).  At 128 columns an MMA lasts 64 clk: a descriptor
+      // built from scratch for each operand kept the single issuing thread busier than the tensor pipe.
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA)), b_desc0 = umma_desc_sw128(smem_u32(sB));
+      const uint64_t slab_row = static_cast<uint64_t>((g.bw * CBK * 2) >> 4);   // SLAB: one h row of the slab, in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
@@ -211,18 +244,30 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_STAGE);
-          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_STAGE);
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(stage) * (Cfg::A_STAGE >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(stage) * (Cfg::B_STAGE >> 4);
+          if constexpr (SLAB) {
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh) {
+              const uint64_t a_tap = a_desc + dh * slab_row;   // tap dh: the tile's rows start dh h-rows into the slab
+#pragma unroll
+              for (int k = 0; k < CBK / 16; ++k)
+                umma_bf16_2cta(d_tmem, a_tap + ((k * 32) >> 4), b_desc + ((dh * Cfg::B_TAP_BYTES + k * 32) >> 4), idesc,
+                               (kb | dh | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty[stage]);
+          } else {
 #pragma unroll
           for (int s2 = 0; s2 < KS; ++s2)
 #pragma unroll
             for (int k = 0; k < CBK / 16; ++k) {
-              const uint64_t ad = umma_desc_sw128(a_addr + s2 * Cfg::A_BYTES + k * 32), bd = umma_desc_sw128(b_addr + s2 * Cfg::B_BYTES + k * 32);
+              const uint64_t ad = a_desc + ((s2 * Cfg::A_BYTES + k * 32) >> 4), bd = b_desc + ((s2 * Cfg::B_BYTES + k * 32) >> 4);
               if (PAIR) umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
               else umma_bf16(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
             }
           if (PAIR) umma_commit_2cta(&empty[stage]);
           else umma_commit(&empty[stage]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (PAIR) umma_commit_2cta(&tfull[as]);
@@ -243,9 +288,11 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
       const int vh = ih * g.bh + (m / g.bw) % g.bh;
       const int vt = it * g.bt + m / (g.bw * g.bh);
       const bool valid = vw < g.W && vh < g.H && vt < g.T;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      if (MODE != 0 && MODE != 4) {
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
+      }
       if (MODE == 0 || MODE == 4) {
         // plain conv (+bias, +residual): the accumulator chunk is transposed through a warp-private smem tile (see
         // gemm_epilogue.cuh) so that 8 lanes cover 128 contiguous bytes of one voxel's channels; the lane's 8 voxel
@@ -264,6 +311,20 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
           poff[i] = ((static_cast<int64_t>(t2 + ep.next_tshift) * (g.H + 2) + (h2 + 1)) * (g.W + 2) + (w2 + 1)) * g.Cout;
           ssv[i] = 0.f;
         }
+        // the residual values of a chunk are requested one chunk ahead -- the first before the accumulator is even waited
+        // for: fetched at the point of use, their latency (x 4 chunks) made this epilogue longer than the main loop of a
+        // 128-channel tile (ncu: the issuing thread spent 80 % of its time waiting for a free accumulator)
+        float4 xnext[8];
+        auto fetch_resid = [&](int c) {
+          const int col = n_blk * BN + c * 32 + cg * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            xnext[i] = (ep.resid && voff[i] >= 0 && col < g.Cout) ? *reinterpret_cast<const float4*>(ep.resid + voff[i] + col)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        fetch_resid(0);
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
         uint32_t r[32];
         tmem_ld32(taddr, r);
 #pragma unroll 1
@@ -273,13 +334,12 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
           __syncwarp();
           if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, r);
           const int col = n_blk * BN + c * 32 + cg * 4;
+          float4 xin[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xin[i] = xnext[i];
+          if (c + 1 < BN / 32) fetch_resid(c + 1);
           if (col < g.Cout) {
             const float4 bv = ep.bias ? *reinterpret_cast<const float4*>(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 xin[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              xin[i] = (ep.resid && voff[i] >= 0) ? *reinterpret_cast<const float4*>(ep.resid + voff[i] + col)
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (voff[i] < 0) continue;
@@ -298,6 +358,13 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
           // interior of the next conv's padded volume.  The 8 lanes that share a voxel combine their partial sums; each lane
           // then re-reads exactly the float4 it stored above (same thread: program order) and writes 8 bytes, 64 contiguous
           // bytes per voxel and chunk.
+          auto fetch_x = [&](int c) {   // (xnext is free again: one chunk ahead, as above)
+            const int col = c * 32 + cg * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              xnext[i] = (voff[i] >= 0 && col < g.Cout) ? *reinterpret_cast<const float4*>(outp + voff[i] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          fetch_x(0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float t = ssv[i];
@@ -318,8 +385,8 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
             }
             float4 xv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              xv[i] = voff[i] >= 0 ? *reinterpret_cast<const float4*>(outp + voff[i] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) xv[i] = xnext[i];
+            if (c + 1 < BN / 32) fetch_x(c + 1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (voff[i] < 0) continue;
@@ -403,6 +470,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
                const ConvEpi ep) {
   conv3d_body<BN, MODE, KS, false>(tmX, tmW, g, ep);
+}
+
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3d_slab_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvGeom g,
+                    const ConvEpi ep) {
+  conv3d_body<BN, MODE, 1, true, true>(tmX, tmW, g, ep);
 }
 
 template <int BN, int MODE, int KS>
@@ -619,7 +693,24 @@ void conv_launch_pair(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
 }
 
 template <int BN, int MODE>
+void conv_launch_slab(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s) {
+  if constexpr (BN <= 128) {
+    using Cfg = ConvCfg<BN, 1, true, true>;
+    auto kern = conv3d_slab_tcgen05<BN, MODE>;
+    ensure_dyn_smem(kern, Cfg::SMEM);
+    const int items = ((g.nt * g.nh * g.nw + 1) / 2) * ((g.Cout + BN - 1) / BN) * g.ksplit;
+    const int clusters = device_sm_count() / 2;
+    const int grid = 2 * (items < clusters ? items : clusters);
+    launch_pdl(PDL_VAE, kern, dim3(grid), dim3(CONV_THREADS), Cfg::SMEM, s, tmX, tmW, g, ep);
+    LTX_CUDA(cudaGetLastError());
+  } else {
+    LTX_CHECK(false, 2, "conv3d: slab stages are for tiles up to 128 columns");
+  }
+}
+
+template <int BN, int MODE>
 void conv_launch(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvGeom& g, const ConvEpi& ep, cudaStream_t s, bool pair) {
+  if (g.slab) { conv_launch_slab<BN, MODE>(tmX, tmW, g, ep, s); return; }
   // 128-channel stages where they fit: tiles up to 128 columns (3 / 4 stages of 64 / 48 KB stay in flight) and whole pairs of chunks
   static const int ks_env = [] { const char* e = getenv("LTX_CONV_KS"); return e ? atoi(e) : 2; }();
   if (pair) conv_launch_pair<BN, MODE>(tmX, tmW, g, ep, s);
@@ -637,6 +728,12 @@ void conv_launch_mode(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
     case 4: conv_launch<BN, 4>(tmX, tmW, g, ep, s, pair); break;
     default: LTX_CHECK(false, 2, "bad conv epilogue mode");
   }
+}
+
+// LTX_CONV_SLAB=0: per-tap A boxes also for tiles up to 128 columns (read per call, as LTX_CONV_PAIR)
+bool conv_slab_enabled() {
+  const char* e = getenv("LTX_CONV_SLAB");
+  return e ? atoi(e) != 0 : true;
 }
 
 // LTX_CONV_PAIR (read per call: the parity tests run both forms): 0 = one CTA per voxel tile, default = CTA pairs whenever the
@@ -692,7 +789,21 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
   LTX_CHECK((epi.mode != 3 && epi.mode != 4) || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
   const bool pair = conv_pair_enabled() && Cin % (2 * CBK) == 0 && device_sm_count() >= 2;
-  CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.bh, g.bw);
+  g.slab = 0;
+  if (pair && bn <= 128 && conv_slab_enabled()) {
+    // slab stages: one frame per tile (bt = 1), [bh, bw] voxels with bw a multiple of the 8-row swizzle atom; fewest tiles
+    // first, then fewest slab rows.  H and W only -- never T -- decide, so temporal shards tile like the whole clip.
+    int bbh = 0, bbw = 0;
+    int64_t btiles = 0, brows = 0;
+    for (int bw = 32; bw >= 8; bw >>= 1) {
+      const int bh = 128 / bw;
+      const int64_t tiles = static_cast<int64_t>((W + bw - 1) / bw) * ((H + bh - 1) / bh), rows = static_cast<int64_t>(bh + 2) * bw;
+      if (bbw == 0 || tiles < btiles || (tiles == btiles && rows < brows)) { bbh = bh; bbw = bw; btiles = tiles; brows = rows; }
+    }
+    g.slab = 1; g.bt = 1; g.bh = bbh; g.bw = bbw;
+    g.nt = T; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
+  }
+  CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.slab ? g.bh + 2 : g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, pair ? bn / 2 : bn);   // pair: each CTA stages half a weight tile
   if (bn == 256)
     conv_launch_mode<256>(tmX, tmW, g, epi, s, pair);

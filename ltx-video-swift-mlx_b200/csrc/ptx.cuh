@@ -320,7 +320,9 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + fast_tanh(k0 * (x + k1 * x * x * x)));
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x).  __fdividef (rcp.approx + multiply, <= 2 ulp): the IEEE division's check-and-fix-up sequence per element
+// made the VAE conv epilogues that apply it to every output (pixel-norm + SiLU hand-over) longer than their main loops.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -16,11 +16,13 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=["0", "1"])
+@pytest.fixture(params=["single", "pair", "pair+slab"])
 def conv_form(request, monkeypatch):
-    """LTX_CONV_PAIR (read by the launcher on every call): 0 = one CTA per voxel tile, 1 = CTA pairs (cta_group::2: two voxel
-    tiles against one weight tile, each CTA staging half of it) wherever Cin comes in 128-channel stages."""
-    monkeypatch.setenv("LTX_CONV_PAIR", request.param)
+    """LTX_CONV_PAIR / LTX_CONV_SLAB (read by the launcher on every call): one CTA per voxel tile; CTA pairs (cta_group::2: two
+    voxel tiles against one weight tile, each CTA staging half of it) wherever Cin comes in 128-channel stages; pairs whose
+    stages hold an h-haloed activation slab shared by three taps (tiles up to 128 columns; the default)."""
+    monkeypatch.setenv("LTX_CONV_PAIR", "0" if request.param == "single" else "1")
+    monkeypatch.setenv("LTX_CONV_SLAB", "1" if request.param == "pair+slab" else "0")
     return request.param
 
 
