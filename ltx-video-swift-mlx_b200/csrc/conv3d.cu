@@ -790,9 +790,11 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   LTX_CHECK((epi.mode != 3 && epi.mode != 4) || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
   const bool pair = conv_pair_enabled() && Cin % (2 * CBK) == 0 && device_sm_count() >= 2;
   g.slab = 0;
-  if (pair && bn <= 128 && conv_slab_enabled()) {
+  if (pair && Cout < 256 && conv_slab_enabled()) {
     // slab stages: one frame per tile (bt = 1), [bh, bw] voxels with bw a multiple of the 8-row swizzle atom; fewest tiles
-    // first, then fewest slab rows.  H and W only -- never T -- decide, so temporal shards tile like the whole clip.
+    // first, then fewest slab rows.  Slab stages add the taps up in another order than the per-tap stages, so the choice
+    // between them must not look at T (a temporal shard has to round like the whole clip): Cout < 256 -- NOT the tile width,
+    // which the tile-starved rule above narrows for short shards -- and H, W only.
     int bbh = 0, bbw = 0;
     int64_t btiles = 0, brows = 0;
     for (int bw = 32; bw >= 8; bw >>= 1) {
