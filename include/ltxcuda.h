@@ -396,6 +396,12 @@ int ltx_op_rmsnorm_mod(ltx_ctx* ctx, const float* x, void* out_bf16, int M, int 
                        const float* tbl_scale, const float* ada_shift, const float* ada_scale, float eps, int layernorm);
 int ltx_op_qknorm_rope(ltx_ctx* ctx, void* x_bf16, int M, int D, const float* w, const float* cos_tab, const float* sin_tab,
                        int rows_per_rope, float eps);
+/* What the conv launcher decides for a [T,H,W,Cin] -> Cout convolution (Conv3dFull, Models/VAE/VideoConvolution.swift:238-347)
+ * on a device with sm_count SMs; host-only (no context, no GPU).  plan7 = {tile width, CTA pairs, slab stages, bt, bh, bw,
+ * tap split}.  Slab stages and the tap split change the order in which the 27 taps are added up, so they depend on H, W and
+ * the channel counts only, never on T: a temporal shard of a clip rounds exactly like the whole clip (the multi-GPU decode is
+ * bit-identical to the single-GPU one).  mode: 0 plain, 1 depth-to-space, 2 unpatchify, 3 / 4 the fused hand-over epilogues. */
+int ltx_conv3d_plan(int T, int H, int W, int Cin, int Cout, int mode, int ntaps, int sm_count, int32_t* plan7);
 /* 3x3x3 conv on a channels-last fp32 volume [T,H,W,Cin] -> [T,H,W,Cout] fp32 with reflect/replicate padding. */
 int ltx_op_conv3d(ltx_ctx* ctx, const float* x, const void* w_bf16_27_O_I, const float* bias, float* out, int T, int H,
                   int W, int Cin, int Cout, int causal);

@@ -114,6 +114,7 @@ SIGNATURES = {
     "ltx_op_rmsnorm_mod": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _F, _I]),
     "ltx_op_qknorm_rope": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _F]),
     "ltx_op_conv3d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I]),
+    "ltx_conv3d_plan": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

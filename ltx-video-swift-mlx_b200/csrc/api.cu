@@ -1289,6 +1289,16 @@ int ltx_op_qknorm_rope(ltx_ctx* c, void* x_bf16, int M, int D, const float* w, c
   });
 }
 
+int ltx_conv3d_plan(int T, int H, int W, int Cin, int Cout, int mode, int ntaps, int sm_count, int32_t* plan7) {
+  // host-only: no context, no device
+  if (plan7 == nullptr || T <= 0 || H <= 1 || W <= 1 || Cin <= 0 || Cout <= 0 || (ntaps != 27 && ntaps != 9) || sm_count <= 0 || mode < 0 ||
+      mode > 4)
+    return LTX_ERR_INVALID_ARGUMENT;
+  const ConvPlan p = conv3d_plan(T, H, W, Cin, Cout, mode, ntaps, /*scratch_ok=*/true, sm_count, conv3d_pair_default(), conv3d_slab_default());
+  plan7[0] = p.bn; plan7[1] = p.pair; plan7[2] = p.slab; plan7[3] = p.bt; plan7[4] = p.bh; plan7[5] = p.bw; plan7[6] = p.ksplit;
+  return LTX_OK;
+}
+
 int ltx_op_conv3d(ltx_ctx* c, const float* x, const void* w, const float* bias, float* out, int T, int H, int W, int Cin,
                   int Cout, int causal) {
   return guarded(c, [&] {

@@ -749,6 +749,50 @@ bool conv3d_wants_tap_split(int H, int W, int Cin, int Cout) {
   return H * W <= 1024 && Cout >= 256 && Cout % 4 == 0 && static_cast<int64_t>(27) * Cin >= 8192;
 }
 
+// Everything launch_conv3d decides from the shape, as a pure function (also behind ltx_conv3d_plan for the host-side tests).
+// Two of the decisions change the ORDER in which the taps are added up -- slab stages and the tap split -- and so must never
+// depend on T: a temporal shard of a clip has to round exactly like the whole clip (tests/test_host.py holds the rule to that).
+ConvPlan conv3d_plan(int T, int H, int W, int Cin, int Cout, int mode, int ntaps, bool scratch_ok, int sm_count, bool pair_on,
+                     bool slab_on) {
+  ConvPlan p;
+  p.bw = best_pow2(W, 128);
+  p.bh = best_pow2(H, 128 / p.bw);
+  p.bt = 128 / (p.bw * p.bh);
+  p.ksplit = 1;
+  p.slab = 0;
+  // tile width: 256 when that still gives every SM a tile, else 128 (the 1024-channel stage of a 25-frame decode has only
+  // 12 voxel tiles: 48 tiles of 256 channels leave two thirds of the SMs idle); 64 for the narrow output conv (128 -> 48)
+  const int m_tiles = ((T + p.bt - 1) / p.bt) * ((H + p.bh - 1) / p.bh) * ((W + p.bw - 1) / p.bw);
+  p.bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
+  // Tile-starved convs (the 1024-channel stage of a 25-frame decode has 12 voxel tiles x 4 channel tiles for 148 SMs, each
+  // 27 x 1024 deep): split the taps into 3 groups (one per dt) -> 3x the work items at full tile width; the partial sums go to
+  // a scratch slab each and are added in a fixed order by a small reduction pass (+ bias, + residual).
+  // The rule looks at the frame geometry and the channel counts only -- never at T.
+  const bool can_split = mode == 0 && ntaps == 27 && scratch_ok && conv3d_wants_tap_split(H, W, Cin, Cout);
+  if (can_split) p.ksplit = 3;
+  else if (mode != 3 && mode != 4 && p.bn == 256 && m_tiles * ((Cout + 255) / 256) < sm_count * 2 / 3) p.bn = 128;   // (measured: 128-wide tiles
+  // cost ~0.7 of a 256-wide one, so they only pay when 256 leaves most SMs without a tile; same summation order either way)
+  p.pair = (pair_on && Cin % (2 * CBK) == 0 && sm_count >= 2) ? 1 : 0;
+  if (p.pair && Cout < 256 && slab_on) {
+    // slab stages: one frame per tile (bt = 1), [bh, bw] voxels with bw a multiple of the 8-row swizzle atom; fewest tiles
+    // first, then fewest slab rows.  Slab stages add the taps up in another order than the per-tap stages, so the choice
+    // between them must not look at T: Cout < 256 -- NOT the tile width, which the tile-starved rule above narrows for short
+    // shards -- and H, W only.
+    int bbh = 0, bbw = 0;
+    int64_t btiles = 0, brows = 0;
+    for (int bw = 32; bw >= 8; bw >>= 1) {
+      const int bh = 128 / bw;
+      const int64_t tiles = static_cast<int64_t>((W + bw - 1) / bw) * ((H + bh - 1) / bh), rows = static_cast<int64_t>(bh + 2) * bw;
+      if (bbw == 0 || tiles < btiles || (tiles == btiles && rows < brows)) { bbh = bh; bbw = bw; btiles = tiles; brows = rows; }
+    }
+    p.slab = 1; p.bt = 1; p.bh = bbh; p.bw = bbw;
+  }
+  return p;
+}
+
+bool conv3d_pair_default() { return conv_pair_enabled(); }
+bool conv3d_slab_default() { return conv_slab_enabled(); }
+
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi_in,
                    cudaStream_t s, int ntaps, float* splitk_scratch, size_t splitk_scratch_bytes) {
   ConvEpi epi = epi_in;
@@ -760,51 +804,23 @@ void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Ci
   LTX_CHECK(epi.mode != 4 || (epi.resid != nullptr && epi.out != nullptr), 2, "conv3d: mode 4 needs the residual stream");
   LTX_CHECK((epi.mode != 3 && epi.mode != 4) || (Cout % 32 == 0 && Cout <= 256 && Cout > 64 && epi.next_pad != nullptr && ntaps == 27), 2,
             "conv3d: the fused-prologue epilogue needs 64 < Cout <= 256 (one tile = all channels of a voxel)");
+  const size_t slab = static_cast<size_t>(T) * H * W * Cout * 4;
+  const bool scratch_ok = splitk_scratch != nullptr && 3 * slab <= splitk_scratch_bytes;
+  const ConvPlan pl = conv3d_plan(T, H, W, Cin, Cout, epi.mode, ntaps, scratch_ok, device_sm_count(), conv_pair_enabled(), conv_slab_enabled());
   ConvGeom g;
   g.T = T; g.H = H; g.W = W; g.Cin = Cin; g.Cout = Cout;
-  g.bw = best_pow2(W, 128);
-  g.bh = best_pow2(H, 128 / g.bw);
-  g.bt = 128 / (g.bw * g.bh);
+  g.bt = pl.bt; g.bh = pl.bh; g.bw = pl.bw;
   g.nt = (T + g.bt - 1) / g.bt; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
   g.ntaps = ntaps; g.tap0 = ntaps == 9 ? 9 : 0;
-  g.ksplit = 1;
-  // tile width: 256 when that still gives every SM a tile, else 128 (the 1024-channel stage of a 25-frame decode has only
-  // 12 voxel tiles: 48 tiles of 256 channels leave two thirds of the SMs idle); 64 for the narrow output conv (128 -> 48)
-  const int m_tiles = g.nt * g.nh * g.nw;
-  int bn = Cout >= 256 ? 256 : (Cout > 64 ? 128 : 64);
-  // Tile-starved convs (the 1024-channel stage of a 25-frame decode has 12 voxel tiles x 4 channel tiles for 148 SMs, each
-  // 27 x 1024 deep): split the taps into 3 groups (one per dt) -> 3x the work items at full tile width; the partial sums go to
-  // a scratch slab each and are added in a fixed order by a small reduction pass (+ bias, + residual).
-  // The rule looks at the frame geometry and the channel counts only -- never at T -- so that a temporal shard takes the same
-  // decision as the unsharded decode and multi-GPU results stay bit-identical.
-  const size_t slab = static_cast<size_t>(T) * H * W * Cout * 4;
-  const bool can_split = epi.mode == 0 && ntaps == 27 && splitk_scratch != nullptr && 3 * slab <= splitk_scratch_bytes &&
-                         conv3d_wants_tap_split(H, W, Cin, Cout);
-  if (can_split) g.ksplit = 3;
-  else if (epi.mode != 3 && epi.mode != 4 && bn == 256 && m_tiles * ((Cout + 255) / 256) < device_sm_count() * 2 / 3) bn = 128;   // (measured: 128-wide tiles
-  // cost ~0.7 of a 256-wide one, so they only pay when 256 leaves most SMs without a tile)
+  g.ksplit = pl.ksplit;
+  g.slab = pl.slab;
+  const int bn = pl.bn;
+  const bool pair = pl.pair != 0;
   const float* final_bias = epi.bias;
   const float* final_resid = epi.resid;
   float* final_out = epi.out;
   if (g.ksplit > 1) { epi.out = splitk_scratch; epi.bias = nullptr; epi.resid = nullptr; }
   LTX_CHECK((epi.mode != 3 && epi.mode != 4) || bn >= Cout, 2, "conv3d: fused-prologue epilogue needs the whole channel range in one tile");
-  const bool pair = conv_pair_enabled() && Cin % (2 * CBK) == 0 && device_sm_count() >= 2;
-  g.slab = 0;
-  if (pair && Cout < 256 && conv_slab_enabled()) {
-    // slab stages: one frame per tile (bt = 1), [bh, bw] voxels with bw a multiple of the 8-row swizzle atom; fewest tiles
-    // first, then fewest slab rows.  Slab stages add the taps up in another order than the per-tap stages, so the choice
-    // between them must not look at T (a temporal shard has to round like the whole clip): Cout < 256 -- NOT the tile width,
-    // which the tile-starved rule above narrows for short shards -- and H, W only.
-    int bbh = 0, bbw = 0;
-    int64_t btiles = 0, brows = 0;
-    for (int bw = 32; bw >= 8; bw >>= 1) {
-      const int bh = 128 / bw;
-      const int64_t tiles = static_cast<int64_t>((W + bw - 1) / bw) * ((H + bh - 1) / bh), rows = static_cast<int64_t>(bh + 2) * bw;
-      if (bbw == 0 || tiles < btiles || (tiles == btiles && rows < brows)) { bbh = bh; bbw = bw; btiles = tiles; brows = rows; }
-    }
-    g.slab = 1; g.bt = 1; g.bh = bbh; g.bw = bbw;
-    g.nt = T; g.nh = (H + g.bh - 1) / g.bh; g.nw = (W + g.bw - 1) / g.bw;
-  }
   CUtensorMap tmX = make_tmap_thwc(x_pad, T + 2, H + 2, W + 2, Cin, g.bt, g.slab ? g.bh + 2 : g.bh, g.bw);
   CUtensorMap tmW = make_tmap_2d(w, static_cast<uint64_t>(ntaps) * Cout, Cin, Cin, pair ? bn / 2 : bn);   // pair: each CTA stages half a weight tile
   if (bn == 256)

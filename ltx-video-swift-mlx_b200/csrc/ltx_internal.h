@@ -261,6 +261,19 @@ struct ConvEpi {
 // x_pad: bf16 [T+2, H+2, W+2, Cin] (already padded), w: bf16 [ntaps][Cout][Cin]; 3x3x3 cross-correlation (ntaps = 27) or a
 // per-frame 3x3 one (ntaps = 9: only the dt = 1 taps, the upscaler's Conv2d).
 bool conv3d_wants_tap_split(int H, int W, int Cin, int Cout);
+// what launch_conv3d decides from the shape (pure: no device access); slab and ksplit change the summation order of the taps
+// and never depend on T
+struct ConvPlan {
+  int bn;           // tile width (output channels per tile): 256 | 128 | 64
+  int pair;         // CTA pairs (cta_group::2)
+  int slab;         // slab stages (pairs, Cout < 256): h-haloed activation slab shared by the three dh taps
+  int bt, bh, bw;   // voxel box of one tile (bt * bh * bw == 128)
+  int ksplit;       // 3: the taps are split by dt over three work items + a fixed-order reduction pass
+};
+ConvPlan conv3d_plan(int T, int H, int W, int Cin, int Cout, int mode, int ntaps, bool scratch_ok, int sm_count, bool pair_on,
+                     bool slab_on);
+bool conv3d_pair_default();   // LTX_CONV_PAIR / LTX_CONV_SLAB as launch_conv3d reads them
+bool conv3d_slab_default();
 // splitk_scratch (optional, >= 3 * T*H*W*Cout fp32): lets tile-starved mode-0 convs split their taps over 3 work items.
 void launch_conv3d(const bf16* x_pad, const bf16* w, int T, int H, int W, int Cin, int Cout, const ConvEpi& epi,
                    cudaStream_t s, int ntaps = 27, float* splitk_scratch = nullptr, size_t splitk_scratch_bytes = 0);

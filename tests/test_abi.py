@@ -87,6 +87,47 @@ def test_pure_host_entry_points_without_a_gpu():
     assert lib.ltx_vae_tiled_frames(16, 8, 1) == 107 and lib.ltx_vae_tiled_frames(0, 8, 1) == -1
 
 
+def test_conv_plan_never_looks_at_the_frame_count(monkeypatch):
+    """ltx_conv3d_plan (host-only): the two launcher decisions that change the ORDER in which the taps are summed -- slab stages
+    and the tap split -- and the slab tile geometry must not depend on T, or a temporal shard of a clip would round differently
+    from the whole clip (the 8-GPU decode is held to bit-identity with the 1-GPU one).  Swept over every conv shape of the
+    decoder at 768 x 512 and a ragged size, T = 1 ... 123, all epilogue modes; plus the expected plans of the decoder's stages."""
+    import ctypes as C
+    lib = _lib.load()
+    for env in ({}, {"LTX_CONV_SLAB": "0"}, {"LTX_CONV_PAIR": "0"}):
+        for k in ("LTX_CONV_SLAB", "LTX_CONV_PAIR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+
+        def plan(T, H, W, Cin, Cout, mode=0, ntaps=27, sms=148):
+            out = (C.c_int32 * 7)()
+            assert lib.ltx_conv3d_plan(T, H, W, Cin, Cout, mode, ntaps, sms, out) == 0
+            return dict(zip(("bn", "pair", "slab", "bt", "bh", "bw", "ksplit"), list(out)))
+        shapes = [(16, 24, 128, 1024), (16, 24, 1024, 1024), (32, 48, 1024, 4096), (32, 48, 512, 512), (64, 96, 512, 2048),
+                  (64, 96, 256, 256), (128, 192, 256, 1024), (128, 192, 128, 128), (128, 192, 128, 48), (20, 30, 128, 128),
+                  (7, 11, 256, 64), (33, 47, 64, 128)]
+        for H, W, Cin, Cout in shapes:
+            for mode in ((0, 3, 4) if 64 < Cout <= 256 else (0, 1, 2)):
+                ref = plan(1, H, W, Cin, Cout, mode)
+                for T in list(range(1, 34)) + [57, 65, 121, 123]:
+                    p = plan(T, H, W, Cin, Cout, mode)
+                    assert (p["slab"], p["ksplit"], p["pair"]) == (ref["slab"], ref["ksplit"], ref["pair"]), (env, T, H, W, Cin, Cout, mode, p, ref)
+                    assert p["bt"] * p["bh"] * p["bw"] == 128 and p["bn"] in (64, 128, 256)
+                    if p["slab"]:
+                        assert (p["bt"], p["bh"], p["bw"]) == (1, ref["bh"], ref["bw"]) and p["bw"] % 8 == 0 and (p["bh"] + 2) * p["bw"] <= 192
+                        assert p["pair"] == 1 and Cout < 256 and p["bn"] <= 128
+        if not env:
+            assert plan(25, 128, 192, 128, 128, 4) == dict(bn=128, pair=1, slab=1, bt=1, bh=16, bw=8, ksplit=1)    # last stage, hand-over
+            assert plan(25, 128, 192, 128, 48, 2)["slab"] == 1 and plan(25, 128, 192, 128, 48, 2)["bn"] == 64      # output conv
+            assert plan(4, 16, 24, 1024, 1024, 0)["ksplit"] == 3 and plan(4, 16, 24, 1024, 1024, 0)["slab"] == 0   # tile-starved stage
+            assert plan(13, 64, 96, 256, 256, 3)["slab"] == 0 and plan(13, 64, 96, 256, 256, 3)["pair"] == 1
+            assert plan(1, 33, 47, 64, 128)["pair"] == 0                                                           # Cin not in 128-channel stages
+    bad = (C.c_int32 * 7)()
+    assert lib.ltx_conv3d_plan(0, 16, 24, 128, 128, 0, 27, 148, bad) != 0 and lib.ltx_conv3d_plan(4, 16, 24, 128, 128, 0, 5, 148, bad) != 0
+    assert lib.ltx_conv3d_plan(4, 16, 24, 128, 128, 0, 27, 148, None) != 0
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/ltxcuda.h compiled as C99 with -Wall -Werror -pedantic by gcc, linked against the in-tree library and run:
     the boundary a SwiftPM C target would import."""
