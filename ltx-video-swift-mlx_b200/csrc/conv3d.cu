@@ -11,6 +11,10 @@
 //   A tile (tap, k-chunk) = 4-D TMA box at (t0+dt, h0+dh, w0+dw, k0) of the padded volume -> [128 rows x 64 ch], 128B swizzle
 //   B tile               = rows [tap*Cout + n0, +BN) x cols [k0, +64) of the [27*Cout, Cin] weight matrix.
 // Warp roles and pipelines are those of gemm.cu (TMA producer / MMA issuer / 4 epilogue warps, 2 TMEM stages).
+// Three forms of the main loop share the epilogues (ConvCfg below): one CTA per voxel tile (conv3d_tcgen05), CTA pairs on
+// cta_group::2 (conv3d_pair_tcgen05: whenever Cin comes in 128-channel stages) and pairs with slab stages
+// (conv3d_slab_tcgen05: Cout < 256).  conv3d_plan() picks; slab stages and the tap split add the taps up in another order
+// than the rest, so those two choices never look at T (a temporal shard must round like the whole clip).
 #include <cstdlib>
 
 #include "gemm_epilogue.cuh"
@@ -201,24 +205,27 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
               tma_load_2d_2sm(sB + stage * Cfg::B_STAGE + dh * Cfg::B_TAP_BYTES, &tmW, &full[stage], kc * CBK,
                               (wt0 + 3 * dh) * g.Cout + n_blk * BN + static_cast<int>(rank) * Cfg::BROWS);
           } else {
-          const int wtap = ks * taps_per_split + kb / kchunks, kc = kb % kchunks;
-          const int tap = g.tap0 + wtap;
-          const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE + Cfg::B_STAGE);
-          else if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_STAGE + Cfg::B_STAGE));
-          else mbar_arrive_remote(&full[stage], 0);
-          const int wrow = wtap * g.Cout + n_blk * BN + static_cast<int>(rank) * Cfg::BROWS;   // PAIR: this CTA's half of the weight tile
+            const int wtap = ks * taps_per_split + kb / kchunks, kc = kb % kchunks;
+            const int tap = g.tap0 + wtap;
+            const int dt = tap / 9, dh = (tap / 3) % 3, dw = tap % 3;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::A_STAGE + Cfg::B_STAGE);
+            else if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_STAGE + Cfg::B_STAGE));
+            else mbar_arrive_remote(&full[stage], 0);
+            const int wrow = wtap * g.Cout + n_blk * BN + static_cast<int>(rank) * Cfg::BROWS;   // PAIR: this CTA's half of the weight tile
 #pragma unroll
-          for (int s2 = 0; s2 < KS; ++s2) {
-            if (PAIR) {
-              tma_load_4d_2sm(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
-              tma_load_2d_2sm(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wrow);
-            } else {
-              tma_load_4d(sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES, &tmX, &full[stage], (kc * KS + s2) * CBK, w0 + dw, h0 + dh, t0 + dt);
-              tma_load_2d(sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES, &tmW, &full[stage], (kc * KS + s2) * CBK, wrow);
+            for (int s2 = 0; s2 < KS; ++s2) {
+              uint8_t* a_dst = sA + stage * Cfg::A_STAGE + s2 * Cfg::A_BYTES;
+              uint8_t* b_dst = sB + stage * Cfg::B_STAGE + s2 * Cfg::B_BYTES;
+              const int c0 = (kc * KS + s2) * CBK;
+              if (PAIR) {
+                tma_load_4d_2sm(a_dst, &tmX, &full[stage], c0, w0 + dw, h0 + dh, t0 + dt);
+                tma_load_2d_2sm(b_dst, &tmW, &full[stage], c0, wrow);
+              } else {
+                tma_load_4d(a_dst, &tmX, &full[stage], c0, w0 + dw, h0 + dh, t0 + dt);
+                tma_load_2d(b_dst, &tmW, &full[stage], c0, wrow);
+              }
             }
-          }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -258,15 +265,15 @@ __device__ __forceinline__ void conv3d_body(const CUtensorMap& tmX, const CUtens
             umma_commit_2cta(&empty[stage]);
           } else {
 #pragma unroll
-          for (int s2 = 0; s2 < KS; ++s2)
+            for (int s2 = 0; s2 < KS; ++s2)
 #pragma unroll
-            for (int k = 0; k < CBK / 16; ++k) {
-              const uint64_t ad = a_desc + ((s2 * Cfg::A_BYTES + k * 32) >> 4), bd = b_desc + ((s2 * Cfg::B_BYTES + k * 32) >> 4);
-              if (PAIR) umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
-            }
-          if (PAIR) umma_commit_2cta(&empty[stage]);
-          else umma_commit(&empty[stage]);
+              for (int k = 0; k < CBK / 16; ++k) {
+                const uint64_t ad = a_desc + ((s2 * Cfg::A_BYTES + k * 32) >> 4), bd = b_desc + ((s2 * Cfg::B_BYTES + k * 32) >> 4);
+                if (PAIR) umma_bf16_2cta(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, ad, bd, idesc, (kb | s2 | k) != 0 ? 1u : 0u);
+              }
+            if (PAIR) umma_commit_2cta(&empty[stage]);
+            else umma_commit(&empty[stage]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

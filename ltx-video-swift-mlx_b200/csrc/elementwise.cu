@@ -1,6 +1,9 @@
 // HBM-bound row / elementwise kernels of the DiT step: AdaLN-modulated RMSNorm / LayerNorm, q/k RMSNorm-across-heads
 // fused with split RoPE, the timestep-embedding GEMV chain, patchify / unpatchify, and the fused
 // CFG + rescale + STG + GE + Euler update.  All vectorised 16-byte accesses, fp32 math.
+// The two row kernels of a DiT block have a streaming form for D = 4096 (rmsnorm_mod_stream_kernel, qknorm_rope_stream_kernel:
+// persistent CTAs whose rows arrive in shared memory by cp.async.bulk, all of a CTA's rows requested up front) and a
+// register-staged form for the same D (LTX_ROWS_STREAM=0) besides the generic one-row-per-CTA kernels for other widths.
 #include <algorithm>
 #include <cstdlib>
 
