@@ -38,3 +38,15 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = _run(dict(RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"), ("--gpus", "2"))
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: on a host without a CUDA device the product arm exits non-zero and prints no result line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                       env=env, timeout=300, cwd=ROOT)
+    assert r.returncode != 0 and r.stdout.strip() == "" and "no CPU fallback" in r.stderr
