@@ -116,3 +116,20 @@ def test_vae_tiled_arguments():
         ctx.vae_decode_tiled(np.zeros((128, 6, 2, 3), dtype=np.float32), 3, 3)
     assert e.value.code == 2
     ctx.close()
+
+
+def test_vae_decode_conv_forms_agree(monkeypatch):
+    """The three main-loop forms of the convolution on the full-width channel plan: CTA pairs add the taps up in the order of the
+    one-CTA form (bit-identical frames); slab stages use another order (same frames to 2e-3 on [0, 1])."""
+    ocfg, pcfg = small_vae_config(1024, 1)
+    ctx, w = make_ctx_with_vae(ocfg, pcfg, seed=61)
+    z = torch.randn(128, 3, 4, 6, generator=torch.Generator().manual_seed(67)).numpy()
+    frames = {}
+    for name, pair, slab in (("single", "0", "0"), ("pair", "1", "0"), ("pair+slab", "1", "1")):
+        monkeypatch.setenv("LTX_CONV_PAIR", pair)
+        monkeypatch.setenv("LTX_CONV_SLAB", slab)
+        frames[name] = ctx.vae_decode(z)
+    ctx.close()
+    assert np.array_equal(frames["single"], frames["pair"])
+    assert float(np.abs(frames["pair+slab"] - frames["pair"]).max()) <= 2e-3
+    assert not np.array_equal(frames["pair+slab"], frames["pair"])      # the slab form really ran
